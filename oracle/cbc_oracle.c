@@ -1,0 +1,960 @@
+/*
+ * oracle/cbc_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see cbc_oracle.h).
+ *
+ * Plain-C restatement of the reference's aligned-read coding path, written from the
+ * reference's behaviour (citations are reference file:line), not copied from it.
+ * Pinned against the unmodified reference built into oracle/_ref/ (byte-identical
+ * streams, identical symbol traces): tests/test_oracle_vs_reference.py, tests/golden/.
+ */
+#include "cbc_oracle.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ctype.h>
+
+/* ------------------------------------------------------------------ growable buffer */
+
+static int buf_reserve(cbco_buf *b, uint64_t extra) {
+    if (b->size + extra <= b->cap) return 0;
+    uint64_t cap = b->cap ? b->cap : 4096;
+    while (cap < b->size + extra) cap *= 2;
+    uint8_t *p = (uint8_t *)realloc(b->data, cap);
+    if (!p) return -1;
+    b->data = p; b->cap = cap;
+    return 0;
+}
+static void buf_put(cbco_buf *b, const void *src, uint64_t n) {
+    if (buf_reserve(b, n)) abort();
+    memcpy(b->data + b->size, src, n);
+    b->size += n;
+}
+static void buf_put_u32(cbco_buf *b, uint32_t v) { buf_put(b, &v, 4); }
+static void buf_put_u64(cbco_buf *b, uint64_t v) { buf_put(b, &v, 8); }
+void cbco_buf_free(cbco_buf *b) { free(b->data); b->data = NULL; b->size = b->cap = 0; }
+
+/* ------------------------------------------------------------------ base helpers
+ * char2basepair / basepair2char / bp_complement: src/sam_models.c:11-45 */
+static int base_code(int c) {
+    switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return 4; }
+}
+static int base_char(int b) {
+    switch (b) { case 0: return 'A'; case 1: return 'C'; case 2: return 'G'; case 3: return 'T'; default: return 'N'; }
+}
+
+/* ------------------------------------------------------------------ bit stream
+ * MSB-first bit packer: stream_write_bit / stream_finish_byte,
+ * src/Arithmetic_stream.c:155-194. The reader returns zeros past the end, which is what
+ * the reference's zero-filled 4 MiB buffer gives (src/Arithmetic_stream.c:30,117). */
+typedef struct { cbco_buf *out; uint32_t acc; uint32_t nbits; } bitw;
+static void bw_bit(bitw *w, uint32_t bit) {
+    w->acc = (w->acc << 1) | (bit & 1u);
+    if (++w->nbits == 8) { uint8_t v = (uint8_t)w->acc; buf_put(w->out, &v, 1); w->acc = 0; w->nbits = 0; }
+}
+static void bw_finish(bitw *w) {
+    /* stream_finish_byte always emits the byte in progress, even an empty one. */
+    uint8_t v = (uint8_t)(w->acc << (8 - w->nbits));
+    if (w->nbits == 0) v = 0;
+    buf_put(w->out, &v, 1);
+    w->acc = 0; w->nbits = 0;
+}
+typedef struct { const uint8_t *p; uint64_t len; uint64_t bitpos; } bitr;
+static uint32_t br_bit(bitr *r) {
+    uint64_t byte = r->bitpos >> 3;
+    uint32_t v = 0;
+    if (byte < r->len) v = (r->p[byte] >> (7 - (r->bitpos & 7))) & 1u;
+    r->bitpos++;
+    return v;
+}
+
+/* ------------------------------------------------------------------ arithmetic coder
+ * src/Arithmetic_stream.c:245-454. */
+typedef struct { uint32_t l, u, t; int32_t scale3; bitw w; bitr r; } acoder;
+
+static void ac_init_enc(acoder *a, cbco_buf *out) {
+    memset(a, 0, sizeof *a);
+    a->l = 0; a->u = CBCG_AC_TOP; a->w.out = out;
+}
+static void ac_init_dec(acoder *a, const uint8_t *p, uint64_t len) {
+    memset(a, 0, sizeof *a);
+    a->l = 0; a->u = CBCG_AC_TOP; a->r.p = p; a->r.len = len;
+    for (uint32_t i = 0; i < CBCG_AC_BITS; i++) a->t = (a->t << 1) | br_bit(&a->r);   /* :262 */
+}
+static int ac_cond(const acoder *a, int *e3) {
+    uint32_t ml = a->l >> (CBCG_AC_BITS - 1), mu = a->u >> (CBCG_AC_BITS - 1);
+    *e3 = 0;
+    if (ml == mu) return 1;
+    *e3 = ((a->l >> (CBCG_AC_BITS - 2)) == 1u && (a->u >> (CBCG_AC_BITS - 2)) == 2u);
+    return 0;
+}
+/* arithmetic_encoder_step :274-345 -- u is computed from the old l, then l. */
+static int ac_encode(acoder *a, uint32_t lo, uint32_t hi, uint32_t n) {
+    if (!(lo < hi) || n == 0) return -1;             /* reference: assert :293 */
+    uint64_t range = (uint64_t)a->u - a->l + 1;
+    a->u = a->l + (uint32_t)((range * hi) / n) - 1;
+    a->l = a->l + (uint32_t)((range * lo) / n);
+    int e3, e12 = ac_cond(a, &e3);
+    while (e12 || e3) {
+        if (e12) {
+            uint32_t msb = a->l >> (CBCG_AC_BITS - 1);
+            bw_bit(&a->w, msb);
+            a->l = (a->l & CBCG_AC_LOWMASK) << 1;
+            a->u = ((a->u & CBCG_AC_LOWMASK) << 1) + 1;
+            while (a->scale3 > 0) { bw_bit(&a->w, !msb); a->scale3--; }
+        } else {
+            a->scale3++;
+            a->u = (((a->u << 1) & CBCG_AC_LOWMASK) | CBCG_AC_MSB) + 1;
+            a->l = (a->l << 1) & CBCG_AC_LOWMASK;
+        }
+        e12 = ac_cond(a, &e3);
+    }
+    return 0;
+}
+/* encoder_last_step :348-364 */
+static void ac_flush(acoder *a) {
+    uint32_t msb = a->l >> (CBCG_AC_BITS - 1);
+    bw_bit(&a->w, msb);
+    while (a->scale3 > 0) { bw_bit(&a->w, !msb); a->scale3--; }
+    for (int bit = (int)CBCG_AC_BITS - 2; bit >= 0; --bit) bw_bit(&a->w, a->l >> bit);
+    bw_finish(&a->w);
+}
+/* arithmetic_get_symbol_range :373-381 */
+static uint32_t ac_target(const acoder *a, uint32_t n) {
+    uint64_t range = (uint64_t)a->u - a->l + 1;
+    uint64_t gap = (uint64_t)a->t - a->l + 1;
+    return (uint32_t)((gap * n - 1) / range);
+}
+/* arithmetic_decoder_step :389-454 */
+static void ac_decode(acoder *a, uint32_t lo, uint32_t hi, uint32_t n) {
+    uint64_t range = (uint64_t)a->u - a->l + 1;
+    a->u = a->l + (uint32_t)((range * hi) / n) - 1;
+    a->l = a->l + (uint32_t)((range * lo) / n);
+    int e3, e12 = ac_cond(a, &e3);
+    while (e12 || e3) {
+        if (e12) {
+            a->l = (a->l & CBCG_AC_LOWMASK) << 1;
+            a->u = ((a->u & CBCG_AC_LOWMASK) << 1) + 1;
+            a->t = ((a->t & CBCG_AC_LOWMASK) << 1) + br_bit(&a->r);
+        } else {
+            a->l = (a->l << 1) & CBCG_AC_LOWMASK;
+            a->u = (((a->u << 1) & CBCG_AC_LOWMASK) | CBCG_AC_MSB) + 1;
+            a->t = (((a->t & CBCG_AC_LOWMASK) << 1) ^ CBCG_AC_MSB) + br_bit(&a->r);
+        }
+        e12 = ac_cond(a, &e3);
+    }
+}
+
+/* ------------------------------------------------------------------ adaptive models
+ * stream_model_t / update_model / send_value_to_as / read_value_from_as:
+ * include/stream_model.h:16-27, src/stream_model.c:31-117. */
+typedef struct { uint32_t *c; uint32_t card, step, n; } model;
+
+static void model_ones(model *m, uint32_t card, uint32_t step) {
+    m->c = (uint32_t *)malloc(sizeof(uint32_t) * (card ? card : 1));
+    for (uint32_t i = 0; i < card; i++) m->c[i] = 1;
+    m->card = card; m->step = step; m->n = card;
+}
+static void model_free(model *m) { free(m->c); m->c = NULL; }
+static void model_update(model *m, uint32_t x) {
+    m->c[x] += m->step; m->n += m->step;
+    if (m->n >= CBCG_RESCALE) {
+        m->n = 0;
+        for (uint32_t i = 0; i < m->card; i++) { m->c[i] = (m->c[i] >> 1) + 1; m->n += m->c[i]; }
+    }
+}
+
+/* The pos model grows: new symbols are appended with count 0 (src/sam_models.c:132-162,
+ * src/read_compression.c:113-159). x -> slot lookup through a small hash map. */
+typedef struct {
+    model m; uint32_t cap; uint32_t *alpha;   /* alpha[slot] = x (slot 0 = escape) */
+    uint32_t *hkey, *hval; uint32_t hcap, hcount;
+} posmodel;
+
+static void pos_hash_put(posmodel *p, uint32_t x, uint32_t slot);
+static void pos_init(posmodel *p) {
+    memset(p, 0, sizeof *p);
+    p->cap = 1024;
+    p->m.c = (uint32_t *)calloc(p->cap, sizeof(uint32_t));
+    p->alpha = (uint32_t *)calloc(p->cap, sizeof(uint32_t));
+    p->m.card = 1; p->m.c[0] = 1; p->m.n = 1; p->m.step = 10;
+    p->hcap = 4096;
+    p->hkey = (uint32_t *)malloc(sizeof(uint32_t) * p->hcap);
+    p->hval = (uint32_t *)malloc(sizeof(uint32_t) * p->hcap);
+    memset(p->hkey, 0xff, sizeof(uint32_t) * p->hcap);
+}
+static void pos_free(posmodel *p) { free(p->m.c); free(p->alpha); free(p->hkey); free(p->hval); }
+static uint32_t pos_hash(uint32_t x) { x *= 0x9e3779b1u; return x ^ (x >> 15); }
+static int pos_find(const posmodel *p, uint32_t x) {
+    uint32_t s = pos_hash(x) & (p->hcap - 1);
+    while (p->hkey[s] != 0xffffffffu) {
+        if (p->hkey[s] == x) return (int)p->hval[s];
+        s = (s + 1) & (p->hcap - 1);
+    }
+    return -1;
+}
+static void pos_hash_put(posmodel *p, uint32_t x, uint32_t slot) {
+    if ((p->hcount + 1) * 2 > p->hcap) {
+        uint32_t ocap = p->hcap, *ok = p->hkey, *ov = p->hval;
+        p->hcap *= 2; p->hcount = 0;
+        p->hkey = (uint32_t *)malloc(sizeof(uint32_t) * p->hcap);
+        p->hval = (uint32_t *)malloc(sizeof(uint32_t) * p->hcap);
+        memset(p->hkey, 0xff, sizeof(uint32_t) * p->hcap);
+        for (uint32_t i = 0; i < ocap; i++) if (ok[i] != 0xffffffffu) pos_hash_put(p, ok[i], ov[i]);
+        free(ok); free(ov);
+    }
+    uint32_t s = pos_hash(x) & (p->hcap - 1);
+    while (p->hkey[s] != 0xffffffffu) s = (s + 1) & (p->hcap - 1);
+    p->hkey[s] = x; p->hval[s] = slot; p->hcount++;
+}
+static uint32_t pos_append(posmodel *p, uint32_t x) {
+    if (p->m.card == p->cap) {
+        p->cap *= 2;
+        p->m.c = (uint32_t *)realloc(p->m.c, sizeof(uint32_t) * p->cap);
+        p->alpha = (uint32_t *)realloc(p->alpha, sizeof(uint32_t) * p->cap);
+    }
+    uint32_t slot = p->m.card++;
+    p->m.c[slot] = 0; p->alpha[slot] = x;
+    pos_hash_put(p, x, slot);
+    return slot;
+}
+
+/* All models of one coder instance (alloc_read_models_t src/sam_models.c:562-586,
+ * alloc_rname_models_t :611-620, initialize_stream_model_codebook :734-770). var rows
+ * are created on first touch: their initial state is all-ones, so this is invisible. */
+typedef struct {
+    uint32_t L;                 /* header read length: alphabet of snps/indels/var */
+    model codebook[4], same_ref, rname[256], rlength[4], pos_alpha[4], flag, match[4], snps, indels, chars[6];
+    model *var;                 /* CBCG_VAR_CONTEXTS lazily initialised rows (c == NULL: untouched) */
+    posmodel pos;
+} models;
+
+static void chars_init(model *m, int row) {
+    /* initialize_stream_model_chars src/sam_models.c:350-411 */
+    m->c = (uint32_t *)malloc(sizeof(uint32_t) * 5);
+    m->card = 5; m->step = 8; m->n = 0;
+    for (int i = 0; i < 4; i++) { m->c[i] = (i == row) ? 0 : 8; m->n += m->c[i]; }
+    m->c[4] = 1; m->n++;
+    static const int fav[4][2] = { {1, 2}, {0, 3}, {0, 3}, {1, 2} };
+    if (row < 4) { m->c[fav[row][0]] += 8; m->c[fav[row][1]] += 8; m->n += 16; }
+}
+static void models_init(models *M, uint32_t L) {
+    memset(M, 0, sizeof *M);
+    M->L = L;
+    for (int i = 0; i < 4; i++) model_ones(&M->codebook[i], 256, 1);
+    model_ones(&M->same_ref, 2, 10);
+    for (int i = 0; i < 256; i++) model_ones(&M->rname[i], 256, 10);
+    for (int i = 0; i < 4; i++) model_ones(&M->rlength[i], 255, 10);
+    for (int i = 0; i < 4; i++) model_ones(&M->pos_alpha[i], 256, 10);
+    model_ones(&M->flag, 1u << 16, 8);
+    for (int i = 0; i < 4; i++) model_ones(&M->match[i], 2, 1);
+    model_ones(&M->snps, L, 10);
+    model_ones(&M->indels, L, 16);
+    for (int i = 0; i < 6; i++) chars_init(&M->chars[i], i);
+    M->var = (model *)calloc(CBCG_VAR_CONTEXTS, sizeof(model));
+    pos_init(&M->pos);
+}
+static void models_free(models *M) {
+    for (int i = 0; i < 4; i++) { model_free(&M->codebook[i]); model_free(&M->rlength[i]); model_free(&M->pos_alpha[i]); model_free(&M->match[i]); }
+    for (int i = 0; i < 256; i++) model_free(&M->rname[i]);
+    for (int i = 0; i < 6; i++) model_free(&M->chars[i]);
+    model_free(&M->same_ref); model_free(&M->flag); model_free(&M->snps); model_free(&M->indels);
+    for (uint32_t i = 0; i < CBCG_VAR_CONTEXTS; i++) if (M->var[i].c) model_free(&M->var[i]);
+    free(M->var);
+    pos_free(&M->pos);
+}
+static model *model_of(models *M, uint32_t stream, uint32_t ctx) {
+    switch (stream) {
+        case CBCG_S_CODEBOOK:  return ctx < 4 ? &M->codebook[ctx] : NULL;
+        case CBCG_S_SAME_REF:  return ctx == 0 ? &M->same_ref : NULL;
+        case CBCG_S_RNAME:     return ctx < 256 ? &M->rname[ctx] : NULL;
+        case CBCG_S_RLENGTH:   return ctx < 4 ? &M->rlength[ctx] : NULL;
+        case CBCG_S_POS:       return &M->pos.m;
+        case CBCG_S_POS_ALPHA: return ctx < 4 ? &M->pos_alpha[ctx] : NULL;
+        case CBCG_S_FLAG:      return &M->flag;
+        case CBCG_S_MATCH:     return ctx < 4 ? &M->match[ctx] : NULL;
+        case CBCG_S_SNPS:      return &M->snps;
+        case CBCG_S_INDELS:    return &M->indels;
+        case CBCG_S_CHARS:     return ctx < 6 ? &M->chars[ctx] : NULL;
+        case CBCG_S_VAR:
+            if (ctx >= CBCG_VAR_CONTEXTS) return NULL;
+            if (!M->var[ctx].c) model_ones(&M->var[ctx], M->L, 10);
+            return &M->var[ctx];
+        default: return NULL;
+    }
+}
+
+/* ------------------------------------------------------------------ coder front end
+ * One object for the three uses of the read-level logic: trace only, encode, decode. */
+typedef struct {
+    models M;
+    acoder ac;
+    int mode;               /* 0 trace only, 1 encode, 2 decode */
+    cbco_buf *trace;        /* optional (key, symbol) log, tracer format */
+    int err;
+    uint64_t n_symbols;
+} coder;
+
+/* send_value_to_as + update_model (src/stream_model.c:53-76,31-51) */
+static void put_sym(coder *c, uint32_t stream, uint32_t ctx, uint32_t x) {
+    if (c->err) return;
+    model *m = model_of(&c->M, stream, ctx);
+    if (!m || x >= m->card) { c->err = -2; return; }           /* reference: assert :62 */
+    if (c->trace) { uint32_t rec[2] = { CBCG_SYM_KEY(stream, ctx), x }; buf_put(c->trace, rec, 8); }
+    c->n_symbols++;
+    if (c->mode == 1) {
+        uint32_t lo = 0;
+        for (uint32_t i = 0; i < x; i++) lo += m->c[i];
+        if (ac_encode(&c->ac, lo, lo + m->c[x], m->n)) { c->err = -3; return; }   /* assert :71 */
+    }
+    model_update(m, x);
+}
+/* read_value_from_as + update_model (src/stream_model.c:78-117) */
+static uint32_t get_sym(coder *c, uint32_t stream, uint32_t ctx) {
+    if (c->err) return 0;
+    model *m = model_of(&c->M, stream, ctx);
+    if (!m) { c->err = -2; return 0; }
+    uint32_t target = ac_target(&c->ac, m->n);
+    uint32_t x = 0, cum = 0;
+    while (cum <= target) {
+        if (x >= m->card) { c->err = -4; return 0; }           /* corrupt stream */
+        cum += m->c[x++];
+    }
+    x--;
+    uint32_t lo = cum - m->c[x];
+    ac_decode(&c->ac, lo, cum, m->n);
+    if (c->trace) { uint32_t rec[2] = { CBCG_SYM_KEY(stream, ctx), x }; buf_put(c->trace, rec, 8); }
+    c->n_symbols++;
+    model_update(m, x);
+    return x;
+}
+
+/* compress_int / decompress_int: src/qv_codebook.c:14-95 */
+static void put_int(coder *c, uint32_t v) {
+    for (int k = 0; k < 4; k++) put_sym(c, CBCG_S_CODEBOOK, (uint32_t)k, (v >> (24 - 8 * k)) & 0xffu);
+}
+static uint32_t get_int(coder *c) {
+    uint32_t v = 0;
+    for (int k = 0; k < 4; k++) v |= get_sym(c, CBCG_S_CODEBOOK, (uint32_t)k) << (24 - 8 * k);
+    return v;
+}
+
+/* compress_pos / compress_pos_alpha: src/read_compression.c:75-159 */
+static void put_pos(coder *c, uint32_t x) {
+    int slot = pos_find(&c->M.pos, x);
+    if (slot >= 0) { put_sym(c, CBCG_S_POS, 0, (uint32_t)slot); return; }
+    put_sym(c, CBCG_S_POS, 0, 0);
+    for (int k = 0; k < 4; k++) put_sym(c, CBCG_S_POS_ALPHA, (uint32_t)k, (x >> (24 - 8 * k)) & 0xffu);
+    uint32_t s = pos_append(&c->M.pos, x);
+    model_update(&c->M.pos.m, s);                       /* :153, no coder step */
+}
+/* decompress_pos / decompress_pos_alpha: src/read_decompression.c:144-228 */
+static uint32_t get_pos(coder *c) {
+    uint32_t slot = get_sym(c, CBCG_S_POS, 0);
+    if (c->err) return 0;
+    if (slot != 0) return c->M.pos.alpha[slot];
+    uint32_t x = 0;
+    for (int k = 0; k < 4; k++) x |= get_sym(c, CBCG_S_POS_ALPHA, (uint32_t)k) << (24 - 8 * k);
+    uint32_t s = pos_append(&c->M.pos, x);
+    model_update(&c->M.pos.m, s);
+    return x;
+}
+
+/* ------------------------------------------------------------------ SNP-site memory
+ * snpInRef[] (include/read_compression.h:28): one byte per reference position of the
+ * current chromosome, set at every SNP site seen so far. Kept with an undo list so a
+ * block-local copy can be cleared cheaply. */
+typedef struct { uint8_t *mark; uint64_t cap; uint64_t *touched; uint64_t nt, tcap; } snpmem;
+static void snp_reset(snpmem *s, uint64_t need) {
+    if (need > s->cap) { free(s->mark); s->mark = (uint8_t *)calloc(need, 1); s->cap = need; s->nt = 0; return; }
+    for (uint64_t i = 0; i < s->nt; i++) s->mark[s->touched[i]] = 0;
+    s->nt = 0;
+}
+static void snp_set(snpmem *s, uint64_t i) {
+    if (i >= s->cap || s->mark[i]) return;
+    s->mark[i] = 1;
+    if (s->nt == s->tcap) { s->tcap = s->tcap ? s->tcap * 2 : 1024; s->touched = (uint64_t *)realloc(s->touched, 8 * s->tcap); }
+    s->touched[s->nt++] = i;
+}
+static void snp_free(snpmem *s) { free(s->mark); free(s->touched); memset(s, 0, sizeof *s); }
+/* compute_delta_to_first_snp: src/read_compression.c:703-718 (cumsumP == pos) */
+static uint32_t snp_delta(const snpmem *s, uint32_t pos, uint32_t prev, uint32_t len) {
+    for (uint32_t j = 0; j + prev < len; j++) {
+        uint64_t i = (uint64_t)pos - 1 + j + prev;
+        if (i < s->cap && s->mark[i]) return j;
+    }
+    return len + 2;
+}
+
+/* ------------------------------------------------------------------ edit extraction
+ * compress_edits (:265-606) and the resumable MD walker add_snps_to_array (:613-701),
+ * src/read_compression.c. */
+static uint32_t num_digits(uint32_t x) {     /* compute_num_digits :720-743 */
+    uint32_t d = 1;
+    while (x >= 10 && d < 9) { x /= 10; d++; }
+    return d;
+}
+static uint32_t md_atoi(const uint8_t *p, const uint8_t *end) {
+    uint32_t v = 0;
+    while (p < end && *p >= '0' && *p <= '9') v = v * 10 + (uint32_t)(*p++ - '0');
+    return v;
+}
+typedef struct { const uint8_t *md, *end; uint32_t ptr, cum; int done; } mdwalk;
+typedef struct { uint32_t pos; uint8_t refb, target; } snp_t;
+
+static int md_ch(const mdwalk *w, uint32_t off) { return (w->md + off < w->end) ? w->md[off] : 0; }
+
+/* Returns non-zero while SNPs may remain (the caller keeps calling), 0 when MD is used up. */
+static int md_walk(mdwalk *w, snp_t *snps, uint32_t *n_snps, uint32_t insertion_pos,
+                   const uint8_t *read, uint32_t read_len) {
+    while (md_ch(w, w->ptr) != 0) {
+        /* look ahead: matches up to the next mismatch, across deletions (:626-649) */
+        uint32_t pos = md_atoi(w->md + w->ptr, w->end), temp = pos;
+        uint32_t o = w->ptr + num_digits(pos);
+        int ch = md_ch(w, o); o++;
+        int hit_end = 0;
+        while (ch == '^') {
+            while (md_ch(w, o) != 0 && !isdigit(md_ch(w, o))) o++;
+            uint32_t v = md_atoi(w->md + o, w->end);
+            temp += v; o += num_digits(v);
+            ch = md_ch(w, o); o++;
+            if (ch == 0) { hit_end = 1; break; }
+        }
+        if (hit_end) break;
+        if (w->cum + temp >= insertion_pos) { w->cum++; return 1; }       /* :656-659 */
+        /* consume (:661-682) */
+        w->ptr += num_digits(pos);
+        ch = md_ch(w, w->ptr); w->ptr++;
+        while (ch == '^') {
+            while (md_ch(w, w->ptr) != 0 && !isdigit(md_ch(w, w->ptr))) w->ptr++;
+            uint32_t v = md_atoi(w->md + w->ptr, w->end);
+            pos += v; w->ptr += num_digits(v);
+            ch = md_ch(w, w->ptr); w->ptr++;
+        }
+        if (ch == 0) break;
+        w->cum += pos;
+        snps[*n_snps].pos = pos;
+        snps[*n_snps].refb = (uint8_t)base_code(ch);
+        snps[*n_snps].target = (uint8_t)base_code(w->cum < read_len ? read[w->cum] : 0);
+        (*n_snps)++;
+        w->cum++;
+        if (md_ch(w, w->ptr) == 0) break;
+    }
+    w->ptr = 0; w->cum = 0; w->done = 1;
+    return 0;
+}
+
+/* One read. Returns 0, or <0 when the read is outside what the reference can code. */
+static int extract_read(const uint8_t *read, uint32_t len, const uint8_t *cigar, uint32_t cigar_len,
+                        const uint8_t *md, uint32_t md_len, const uint8_t *ref, uint64_t ref_len,
+                        uint32_t pos, cbcg_read_rec *rec, uint16_t *edits, uint32_t *n_edits) {
+    *n_edits = 0;
+    rec->match = 0; rec->n_snps = rec->n_dels = rec->n_ins = 0;
+    if (pos == 0 || len == 0 || len > CBCG_MAX_READ_LEN) return -10;
+    /* perfect-match test, independent of CIGAR/MD (:291-296) */
+    int matches = ((uint64_t)pos - 1 + len <= ref_len);
+    for (uint32_t i = 0; matches && i < len; i++) if (read[i] != ref[pos - 1 + i]) matches = 0;
+    if (matches) { rec->match = 1; return 0; }
+
+    static __thread uint32_t dels[1024];
+    static __thread struct { uint32_t pos; uint8_t target; } ins[1024];
+    static __thread snp_t snps[1024];
+    uint32_t n_ins = 0, n_dels = 0, n_snps = 0;
+    uint32_t M = 0, prev_i = 0, prev_d = 0;
+    int last_snp = 1, first = 1;
+    mdwalk w = { md, md + md_len, 0, 0, 0 };
+
+    uint32_t i = 0;
+    while (i < cigar_len) {
+        uint32_t num = 0, j = i;
+        while (j < cigar_len && cigar[j] >= '0' && cigar[j] <= '9') num = num * 10 + (uint32_t)(cigar[j++] - '0');
+        if (j >= cigar_len) return -11;
+        int op = cigar[j];
+        switch (op) {
+            case 'M': case '=': case 'X':        /* reference handles only 'M' (:312) */
+                M += num; break;
+            case 'I':                            /* :321-337 */
+                for (uint32_t k = 0; k < num; k++) {
+                    if (n_ins >= 1000) return -12;
+                    if (last_snp) last_snp = md_walk(&w, snps, &n_snps, M + n_ins, read, len);
+                    ins[n_ins].pos = M - prev_i;
+                    ins[n_ins].target = (uint8_t)base_code(M + n_ins < len ? read[M + n_ins] : 0);
+                    prev_i = M; n_ins++;
+                }
+                break;
+            case 'D':                            /* :340-352 */
+                for (uint32_t k = 0; k < num; k++) {
+                    if (n_dels >= 1000) return -12;
+                    dels[n_dels++] = M - prev_d; prev_d = M;
+                }
+                break;
+            case 'S':
+                if (first) {                     /* leading clip (:358-468): bases coded as insertions at 0 */
+                    for (uint32_t k = 0; k < num; k++) {
+                        if (n_ins >= 1000) return -12;
+                        if (last_snp) last_snp = md_walk(&w, snps, &n_snps, n_ins, read, len);
+                        ins[n_ins].pos = 0;
+                        ins[n_ins].target = (uint8_t)base_code(k < len ? read[k] : 0);
+                        n_ins++;
+                    }
+                } else {                         /* trailing clip (:469-479) */
+                    for (uint32_t k = 0; k < num; k++) {
+                        if (n_ins >= 1000) return -12;
+                        ins[n_ins].pos = M - prev_i;
+                        ins[n_ins].target = (uint8_t)base_code(M + n_ins < len ? read[M + n_ins] : 0);
+                        prev_i = M; n_ins++;
+                    }
+                }
+                break;
+            case 'H': case 'P': break;           /* no effect on SEQ */
+            default: return -13;                 /* '*', 'N', junk: the reference cannot code these */
+        }
+        first = 0;
+        i = j + 1;
+    }
+    if (last_snp) md_walk(&w, snps, &n_snps, len + 1, read, len);       /* :551-552 */
+
+    if (n_snps > 255 || n_dels > 255 || n_ins > 255) return -14;
+    rec->n_snps = (uint8_t)n_snps; rec->n_dels = (uint8_t)n_dels; rec->n_ins = (uint8_t)n_ins;
+    uint32_t e = 0;
+    for (uint32_t k = 0; k < n_dels; k++) { if (dels[k] > 255) return -14; edits[e++] = CBCG_EDIT(dels[k], 0, 0); }
+    for (uint32_t k = 0; k < n_snps; k++) { if (snps[k].pos > 255) return -14; edits[e++] = CBCG_EDIT(snps[k].pos, snps[k].target, snps[k].refb); }
+    for (uint32_t k = 0; k < n_ins; k++) { if (ins[k].pos > 255) return -14; edits[e++] = CBCG_EDIT(ins[k].pos, ins[k].target, CBCG_BP_O); }
+    *n_edits = e;
+    return 0;
+}
+
+int64_t cbco_extract(const cbco_batch *b, const cbco_genome *g, cbcg_read_rec *recs,
+                     uint16_t *edits, uint64_t edits_cap) {
+    uint64_t total = 0;
+    for (uint64_t r = 0; r < b->n_reads; r++) {
+        uint32_t chr = b->chr[r];
+        if (chr >= g->n_chr) return -1;
+        uint32_t len = b->seq_len[r];
+        if (total + 3ull * len + 8 > edits_cap) return -2;
+        cbcg_read_rec *rec = &recs[r];
+        rec->pos = b->pos[r]; rec->flag = b->flag[r]; rec->len = (uint16_t)len; rec->edit_off = (uint32_t)total;
+        uint32_t ne = 0;
+        int rc = extract_read(b->seq + b->seq_off[r], len,
+                              b->cigar + b->cigar_off[r], (uint32_t)(b->cigar_off[r + 1] - b->cigar_off[r]),
+                              b->md + b->md_off[r], (uint32_t)(b->md_off[r + 1] - b->md_off[r]),
+                              g->bases[chr], g->len[chr], b->pos[r], rec, edits + total, &ne);
+        if (rc) return rc;
+        total += ne;
+    }
+    return (int64_t)total;
+}
+
+/* ------------------------------------------------------------------ reconstruction
+ * reconstruct_read (src/read_decompression.c:339-529) followed by print_line
+ * (src/compression.c:16-40). For reverse reads the reference builds the reverse
+ * complement and print_line reverses it again, so the emitted line is the forward
+ * construction for either strand. */
+static int rebuild_read(const cbcg_read_rec *rec, const uint16_t *e, const uint8_t *ref, uint64_t ref_len, uint8_t *out) {
+    uint32_t len = rec->len, pos = rec->pos;
+    if (rec->match) {
+        if ((uint64_t)pos - 1 + len > ref_len) return -1;
+        memcpy(out, ref + pos - 1, len);                         /* :383-384 */
+        return 0;
+    }
+    uint8_t tmp[1024];
+    uint32_t nd = rec->n_dels, ns = rec->n_snps, ni = rec->n_ins;
+    if (ni > len) return -1;
+    uint32_t aligned = len - ni, cur = 0;
+    if ((uint64_t)pos - 1 + aligned + nd > ref_len) return -1;
+    for (uint32_t k = 0; k < nd; k++) {                          /* :418-430 */
+        uint32_t d = CBCG_EDIT_DELTA(e[k]);
+        for (uint32_t t = 0; t < d && cur < aligned; t++) { tmp[cur] = ref[pos + cur - 1 + k]; cur++; }
+    }
+    for (; cur < aligned; cur++) tmp[cur] = ref[pos + cur - 1 + nd];   /* :434-437 */
+    cur = 0;
+    for (uint32_t k = 0; k < ns; k++) {                          /* :442-458 */
+        uint32_t p = CBCG_EDIT_DELTA(e[nd + k]);
+        if (cur + p >= aligned) return -1;
+        tmp[cur + p] = (uint8_t)base_char((int)CBCG_EDIT_TARGET(e[nd + k]));
+        cur += p + 1;
+    }
+    uint32_t o = 0; cur = 0;
+    for (uint32_t k = 0; k < ni; k++) {                          /* :467-483 */
+        uint32_t p = CBCG_EDIT_DELTA(e[nd + ns + k]);
+        for (uint32_t t = 0; t < p && cur < aligned; t++) out[o++] = tmp[cur++];
+        out[o++] = (uint8_t)base_char((int)CBCG_EDIT_TARGET(e[nd + ns + k]));
+    }
+    while (cur < aligned) out[o++] = tmp[cur++];                 /* :486-487 */
+    return o == len ? 0 : -1;
+}
+
+int64_t cbco_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint16_t *edits,
+                         const uint32_t *chr, const cbco_genome *g, uint8_t *out, uint64_t out_cap) {
+    uint64_t o = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        if (chr[r] >= g->n_chr || o + recs[r].len + 1 > out_cap) return -1;
+        if (rebuild_read(&recs[r], edits + recs[r].edit_off, g->bases[chr[r]], g->len[chr[r]], out + o)) return -2;
+        o += recs[r].len;
+        out[o++] = '\n';
+    }
+    return (int64_t)o;
+}
+
+/* ------------------------------------------------------------------ read-level coding
+ * State that the reference keeps in statics/globals, made explicit (SURVEY.md section 7,
+ * hard part 2): prevPos (src/read_compression.c:115), prevM (:167), prev_name/prevChar
+ * (src/id_compression.c:41-42), snpInRef. */
+typedef struct {
+    coder c;
+    uint32_t prev_pos, prev_m, prev_char;
+    int have_name; uint32_t cur_chr;
+    snpmem snp;
+    cbco_buf *raw;          /* optional raw symbol list (POS as CBCG_S_POS_X) */
+} rstate;
+
+static void raw_sym(rstate *s, uint32_t stream, uint32_t ctx, uint32_t v) {
+    if (s->raw) { uint32_t rec[2] = { CBCG_SYM_KEY(stream, ctx), v }; buf_put(s->raw, rec, 8); }
+}
+static void emit(rstate *s, uint32_t stream, uint32_t ctx, uint32_t v) {
+    raw_sym(s, stream, ctx, v);
+    put_sym(&s->c, stream, ctx, v);
+}
+
+/* compress_rname: src/id_compression.c:39-65 */
+static void put_rname(rstate *s, const char *name) {
+    emit(s, CBCG_S_SAME_REF, 0, 1);
+    for (const char *p = name; *p; p++) { emit(s, CBCG_S_RNAME, s->prev_char, (uint8_t)*p); s->prev_char = (uint8_t)*p; }
+    emit(s, CBCG_S_RNAME, s->prev_char, 0);
+}
+
+/* compress_read (:15-44) + the emission half of compress_edits (:557-600),
+ * src/read_compression.c. chr_change resets prevPos (:123-124). */
+static void put_read(rstate *s, const cbcg_read_rec *rec, const uint16_t *e) {
+    uint32_t len = rec->len;
+    emit(s, CBCG_S_RLENGTH, 0, len & 0xffu);                    /* :29-33: bytes 1..3 are always 0 */
+    for (uint32_t k = 1; k < 4; k++) emit(s, CBCG_S_RLENGTH, k, 0);
+    uint32_t x = rec->pos - s->prev_pos + 1;                    /* :128 */
+    raw_sym(s, CBCG_S_POS_X, 0, x);
+    put_pos(&s->c, x);
+    uint32_t same_pos = (x == 1);
+    s->prev_pos = rec->pos;
+    emit(s, CBCG_S_FLAG, 0, rec->flag);
+    uint32_t strand = (rec->flag >> 4) & 1u;                    /* :57-60 */
+    emit(s, CBCG_S_MATCH, (same_pos << 1) | s->prev_m, rec->match);   /* :164-188 */
+    s->prev_m = rec->match;
+    if (rec->match) return;
+    uint32_t nd = rec->n_dels, ns = rec->n_snps, ni = rec->n_ins;
+    if ((nd | ni) == 0) emit(s, CBCG_S_SNPS, 0, ns);
+    else { emit(s, CBCG_S_SNPS, 0, 0); emit(s, CBCG_S_INDELS, 0, ns); emit(s, CBCG_S_INDELS, 0, nd); emit(s, CBCG_S_INDELS, 0, ni); }
+    uint32_t prev = 0;
+    for (uint32_t k = 0; k < nd; k++) { uint32_t d = CBCG_EDIT_DELTA(e[k]); emit(s, CBCG_S_VAR, (prev << 1) | strand, d); prev += d; }
+    prev = 0;
+    for (uint32_t k = 0; k < ns; k++) {
+        uint16_t ed = e[nd + k];
+        uint32_t delta = snp_delta(&s->snp, rec->pos, prev, len);
+        emit(s, CBCG_S_VAR, ((((delta << CBCG_BITS_DELTA) + prev) << 1) | strand), CBCG_EDIT_DELTA(ed));
+        prev += CBCG_EDIT_DELTA(ed) + 1;
+        snp_set(&s->snp, (uint64_t)rec->pos + prev - 2);        /* :589 */
+        emit(s, CBCG_S_CHARS, CBCG_EDIT_REFB(ed), CBCG_EDIT_TARGET(ed));
+    }
+    prev = 0;
+    for (uint32_t k = 0; k < ni; k++) {
+        uint16_t ed = e[nd + ns + k];
+        emit(s, CBCG_S_VAR, (prev << 1) | strand, CBCG_EDIT_DELTA(ed)); prev += CBCG_EDIT_DELTA(ed);
+        emit(s, CBCG_S_CHARS, CBCG_BP_O, CBCG_EDIT_TARGET(ed));
+    }
+}
+
+/* decompress_read (:59-86) + the decoding half of reconstruct_read (:339-458,:462-511),
+ * src/read_decompression.c. Fills rec/edits; needs the reference for the chars context. */
+static void get_read(rstate *s, cbcg_read_rec *rec, uint16_t *e, uint32_t *n_edits,
+                     const uint8_t *ref, uint64_t ref_len) {
+    coder *c = &s->c;
+    uint32_t len = get_sym(c, CBCG_S_RLENGTH, 0);
+    for (uint32_t k = 1; k < 4; k++) len |= get_sym(c, CBCG_S_RLENGTH, k) << (8 * k);
+    uint32_t x = get_pos(c);
+    uint32_t pos = s->prev_pos + x - 1;
+    s->prev_pos = pos;
+    uint32_t flag = get_sym(c, CBCG_S_FLAG, 0);
+    uint32_t strand = (flag >> 4) & 1u;
+    uint32_t match = get_sym(c, CBCG_S_MATCH, ((uint32_t)(x == 1) << 1) | s->prev_m);
+    s->prev_m = match;
+    rec->pos = pos; rec->flag = (uint16_t)flag; rec->len = (uint16_t)len; rec->match = (uint8_t)match;
+    rec->n_snps = rec->n_dels = rec->n_ins = 0;
+    *n_edits = 0;
+    if (match || c->err) return;
+    uint32_t ns = get_sym(c, CBCG_S_SNPS, 0), nd = 0, ni = 0;
+    if (ns == 0) { ns = get_sym(c, CBCG_S_INDELS, 0); nd = get_sym(c, CBCG_S_INDELS, 0); ni = get_sym(c, CBCG_S_INDELS, 0); }
+    if (c->err || ni > len || ns > 255 || nd > 255 || ni > 255) { if (!c->err) c->err = -5; return; }
+    rec->n_snps = (uint8_t)ns; rec->n_dels = (uint8_t)nd; rec->n_ins = (uint8_t)ni;
+    uint32_t cumdel[256];
+    uint32_t prev = 0, ne = 0;
+    for (uint32_t k = 0; k < nd; k++) {
+        uint32_t d = get_sym(c, CBCG_S_VAR, (prev << 1) | strand); prev += d; cumdel[k] = prev;
+        e[ne++] = CBCG_EDIT(d, 0, 0);
+    }
+    prev = 0;
+    for (uint32_t k = 0; k < ns; k++) {
+        uint32_t delta = snp_delta(&s->snp, pos, prev, len);
+        uint32_t p = get_sym(c, CBCG_S_VAR, ((((delta << CBCG_BITS_DELTA) + prev) << 1) | strand));
+        uint32_t idx = prev + p;                                /* index in the insertion-free read */
+        prev += p + 1;
+        snp_set(&s->snp, (uint64_t)pos + prev - 2);
+        uint32_t skipped = 0;                                   /* deletions at or before idx (:426-437) */
+        while (skipped < nd && cumdel[skipped] <= idx) skipped++;
+        uint64_t ri = (uint64_t)pos - 1 + idx + skipped;
+        uint32_t refb = (uint32_t)base_code(ri < ref_len ? ref[ri] : 0);
+        uint32_t tgt = get_sym(c, CBCG_S_CHARS, refb);
+        e[ne++] = CBCG_EDIT(p, tgt, refb);
+        if (c->err) return;
+    }
+    prev = 0;
+    for (uint32_t k = 0; k < ni; k++) {
+        uint32_t p = get_sym(c, CBCG_S_VAR, (prev << 1) | strand); prev += p;
+        uint32_t tgt = get_sym(c, CBCG_S_CHARS, CBCG_BP_O);
+        e[ne++] = CBCG_EDIT(p, tgt, CBCG_BP_O);
+    }
+    *n_edits = ne;
+}
+
+static void rstate_init(rstate *s, uint32_t L, int mode) {
+    memset(s, 0, sizeof *s);
+    models_init(&s->c.M, L);
+    s->c.mode = mode;
+}
+static void rstate_free(rstate *s) { models_free(&s->c.M); snp_free(&s->snp); }
+
+/* ------------------------------------------------------------------ legacy single stream
+ * compress() / compress_line(): src/compression.c:42-69,112-170; header writers
+ * src/sam_file_allocation.c:363-404. */
+static void put_header(rstate *s, uint32_t L) {
+    uint32_t v[34]; v[0] = L; for (int i = 0; i < 32; i++) v[1 + i] = CBCG_WELL_DEBUG; v[33] = CBCG_LOSSLESS;
+    for (int i = 0; i < 34; i++)
+        for (int k = 0; k < 4; k++) emit(s, CBCG_S_CODEBOOK, (uint32_t)k, (v[i] >> (24 - 8 * k)) & 0xffu);
+}
+
+static int code_range(rstate *s, const cbco_batch *b, const cbco_genome *g, const cbcg_read_rec *recs,
+                      const uint16_t *edits, uint64_t r0, uint64_t r1, int legacy) {
+    for (uint64_t r = r0; r < r1; r++) {
+        uint32_t chr = b->chr[r];
+        int change = !s->have_name || chr != s->cur_chr;
+        if (legacy) {
+            if (change) put_rname(s, g->name[chr]); else emit(s, CBCG_S_SAME_REF, 0, 0);
+        } else {
+            if (change && r != r0) return -6;                   /* blocks never span chromosomes */
+            emit(s, CBCG_S_SAME_REF, 0, 0);
+        }
+        if (change) {                                           /* src/compression.c:58-64 */
+            s->have_name = 1; s->cur_chr = chr;
+            if (legacy) s->prev_pos = 0;
+            snp_reset(&s->snp, g->len[chr] + 2048);
+        }
+        put_read(s, &recs[r], edits + recs[r].edit_off);
+        if (s->c.err) return s->c.err;
+    }
+    return 0;
+}
+
+int cbco_encode_legacy(const cbco_batch *b, const cbco_genome *g, uint32_t L, cbco_buf *out, cbco_buf *trace) {
+    uint64_t cap = 16;
+    for (uint64_t r = 0; r < b->n_reads; r++) cap += 3ull * b->seq_len[r] + 8;
+    cbcg_read_rec *recs = (cbcg_read_rec *)malloc(sizeof(cbcg_read_rec) * (b->n_reads + 1));
+    uint16_t *edits = (uint16_t *)malloc(2 * cap);
+    int64_t ne = cbco_extract(b, g, recs, edits, cap);
+    int rc = ne < 0 ? (int)ne : 0;
+    if (!rc) {
+        rstate s; rstate_init(&s, L, 1);
+        s.c.trace = trace;
+        ac_init_enc(&s.c.ac, out);
+        put_header(&s, L);
+        rc = code_range(&s, b, g, recs, edits, 0, b->n_reads, 1);
+        if (!rc) {
+            put_rname(&s, "\n");                                /* src/compression.c:152 */
+            ac_flush(&s.c.ac);
+            rc = s.c.err;
+        }
+        rstate_free(&s);
+    }
+    free(recs); free(edits);
+    return rc;
+}
+
+/* decompress() / decompress_line(): src/compression.c:71-108,173-216;
+ * decompress_rname src/id_compression.c:67-94. Chromosomes are taken in FASTA order, as
+ * the reference does (it reads the next FASTA record on every name change). */
+int cbco_decode_legacy(const uint8_t *stream, uint64_t stream_len, const cbco_genome *g,
+                       cbco_buf *seq_out, uint64_t *n_reads_out) {
+    rstate s; rstate_init(&s, 1, 2);
+    ac_init_dec(&s.c.ac, stream, stream_len);
+    uint32_t L = get_int(&s.c);
+    for (int i = 0; i < 32; i++) (void)get_int(&s.c);
+    uint32_t lossiness = get_int(&s.c);
+    int rc = 0;
+    uint64_t n = 0;
+    if (s.c.err || L == 0 || L > 1024 || lossiness != CBCG_LOSSLESS) rc = -20;
+    else {
+        /* models that depend on L are (re)built now, as alloc_read_block_t does after the header int */
+        models_free(&s.c.M); models_init(&s.c.M, L);
+        /* keep the codebook state? It is not used past the header. */
+        int32_t chr = -1;
+        uint16_t e[3 * 256 + 8];
+        uint8_t line[1024 + 1];
+        for (;;) {
+            uint32_t change = get_sym(&s.c, CBCG_S_SAME_REF, 0);
+            if (s.c.err) { rc = s.c.err; break; }
+            if (change) {
+                int end = 0; uint32_t ch;
+                while ((ch = get_sym(&s.c, CBCG_S_RNAME, s.prev_char)) != 0) {
+                    if (s.c.err) break;
+                    if (ch == '\n') { end = 1; break; }
+                    s.prev_char = ch;
+                }
+                if (s.c.err) { rc = s.c.err; break; }
+                if (end) break;
+                chr++;
+                if ((uint32_t)chr >= g->n_chr) { rc = -21; break; }
+                s.prev_pos = 0;
+                snp_reset(&s.snp, g->len[chr] + 2048);
+            }
+            if (chr < 0) { rc = -22; break; }
+            cbcg_read_rec rec; uint32_t ne = 0;
+            get_read(&s, &rec, e, &ne, g->bases[chr], g->len[chr]);
+            if (s.c.err) { rc = s.c.err; break; }
+            rec.edit_off = 0;
+            if (rec.len > 1024 || rebuild_read(&rec, e, g->bases[chr], g->len[chr], line)) { rc = -23; break; }
+            line[rec.len] = '\n';
+            buf_put(seq_out, line, rec.len + 1u);
+            n++;
+        }
+    }
+    if (n_reads_out) *n_reads_out = n;
+    rstate_free(&s);
+    return rc;
+}
+
+int cbco_symbols(const cbco_batch *b, const cbco_genome *g, const cbcg_read_rec *recs,
+                 const uint16_t *edits, uint64_t r0, uint64_t r1, uint32_t L, int legacy, cbco_buf *symbols) {
+    rstate s; rstate_init(&s, L, 0);
+    s.raw = symbols;
+    int rc = 0;
+    if (legacy) put_header(&s, L);
+    else if (r0 < r1) { s.prev_pos = recs[r0].pos; s.have_name = 1; s.cur_chr = b->chr[r0]; snp_reset(&s.snp, g->len[b->chr[r0]] + 2048); }
+    rc = code_range(&s, b, g, recs, edits, r0, r1, legacy);
+    if (!rc && legacy) put_rname(&s, "\n");
+    rstate_free(&s);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ blocked container
+ * Our design (the reference stream has no framing). Layout, little endian:
+ *   header  : u32 magic, version, flags, read_len, u64 n_reads, u32 n_blocks, n_chr,
+ *             block_reads, gen_mode, then per chromosome u32 name_len + bytes (padded to 4)
+ *   index   : n_blocks x 8 u32 { n_reads, chr, base_pos, n_symbols, n_edits, payload_bytes, gen, 0 }
+ *   payload : block bitstreams back to back
+ * Each block: models at the reference's initial state (gen 0), fresh coder, prevPos = base_pos
+ * (= POS of its first read), prevM = 0, empty SNP-site memory; per read the reference's symbol
+ * order with same_ref = 0; closed by the reference's final flush. */
+typedef struct { uint32_t n_reads, chr, base_pos, n_symbols, n_edits, payload_bytes, gen, rsv; } blk_index;
+
+int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads,
+                        uint32_t gen_mode, cbco_buf *out) {
+    if (gen_mode != 0 || block_reads == 0) return -30;
+    uint64_t cap = 16;
+    for (uint64_t r = 0; r < b->n_reads; r++) cap += 3ull * b->seq_len[r] + 8;
+    cbcg_read_rec *recs = (cbcg_read_rec *)malloc(sizeof(cbcg_read_rec) * (b->n_reads + 1));
+    uint16_t *edits = (uint16_t *)malloc(2 * cap);
+    int64_t ne = cbco_extract(b, g, recs, edits, cap);
+    if (ne < 0) { free(recs); free(edits); return (int)ne; }
+    /* cut blocks */
+    uint64_t nb = 0, bcap = b->n_reads / block_reads + g->n_chr + 2;
+    blk_index *idx = (blk_index *)calloc(bcap, sizeof(blk_index));
+    uint64_t *first = (uint64_t *)calloc(bcap + 1, sizeof(uint64_t));
+    for (uint64_t r = 0; r < b->n_reads;) {
+        uint64_t e = r + 1;
+        while (e < b->n_reads && e - r < block_reads && b->chr[e] == b->chr[r]) e++;
+        if (nb >= bcap) { bcap *= 2; idx = (blk_index *)realloc(idx, bcap * sizeof(blk_index)); first = (uint64_t *)realloc(first, (bcap + 1) * 8); }
+        first[nb] = r;
+        idx[nb].n_reads = (uint32_t)(e - r); idx[nb].chr = b->chr[r]; idx[nb].base_pos = recs[r].pos;
+        idx[nb].gen = 0; idx[nb].rsv = 0;
+        nb++; r = e;
+    }
+    first[nb] = b->n_reads;
+    cbco_buf payload = {0};
+    int rc = 0;
+    for (uint64_t k = 0; k < nb && !rc; k++) {
+        rstate s; rstate_init(&s, L, 1);
+        uint64_t start = payload.size;
+        ac_init_enc(&s.c.ac, &payload);
+        s.prev_pos = idx[k].base_pos; s.have_name = 1; s.cur_chr = idx[k].chr;
+        snp_reset(&s.snp, g->len[idx[k].chr] + 2048);
+        rc = code_range(&s, b, g, recs, edits, first[k], first[k + 1], 0);
+        if (!rc) { ac_flush(&s.c.ac); rc = s.c.err; }
+        idx[k].n_symbols = (uint32_t)s.c.n_symbols;
+        uint64_t e_lo = recs[first[k]].edit_off;
+        uint64_t e_hi = (first[k + 1] < b->n_reads) ? recs[first[k + 1]].edit_off : (uint64_t)ne;
+        idx[k].n_edits = (uint32_t)(e_hi - e_lo);
+        idx[k].payload_bytes = (uint32_t)(payload.size - start);
+        rstate_free(&s);
+    }
+    if (!rc) {
+        buf_put_u32(out, CBCG_MAGIC); buf_put_u32(out, CBCG_VERSION); buf_put_u32(out, 0); buf_put_u32(out, L);
+        buf_put_u64(out, b->n_reads); buf_put_u32(out, (uint32_t)nb); buf_put_u32(out, g->n_chr);
+        buf_put_u32(out, block_reads); buf_put_u32(out, gen_mode);
+        for (uint32_t c = 0; c < g->n_chr; c++) {
+            uint32_t nl = (uint32_t)strlen(g->name[c]), pad = (4 - (nl & 3)) & 3; uint32_t z = 0;
+            buf_put_u32(out, nl); buf_put(out, g->name[c], nl); buf_put(out, &z, pad);
+        }
+        buf_put(out, idx, nb * sizeof(blk_index));
+        buf_put(out, payload.data, payload.size);
+    }
+    cbco_buf_free(&payload);
+    free(idx); free(first); free(recs); free(edits);
+    return rc;
+}
+
+int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cbco_buf *seq_out, uint64_t *n_reads_out) {
+    if (len < 40) return -40;
+    uint32_t h[10]; memcpy(h, p, 40);
+    if (h[0] != CBCG_MAGIC || h[1] != CBCG_VERSION) return -41;
+    uint32_t L = h[3]; uint64_t n_reads; memcpy(&n_reads, p + 16, 8);
+    uint32_t nb = h[6], n_chr = h[7], gen_mode = h[9];
+    if (gen_mode != 0 || n_chr > g->n_chr) return -42;
+    uint64_t o = 40;
+    /* container chromosome ordinal -> genome ordinal, by name */
+    uint32_t *chr_map = (uint32_t *)calloc(n_chr + 1, sizeof(uint32_t));
+    for (uint32_t c = 0; c < n_chr; c++) {
+        if (o + 4 > len) { free(chr_map); return -43; }
+        uint32_t nl; memcpy(&nl, p + o, 4); o += 4;
+        if (o + nl > len) { free(chr_map); return -43; }
+        uint32_t found = 0xffffffffu;
+        for (uint32_t k = 0; k < g->n_chr; k++) if (strlen(g->name[k]) == nl && !memcmp(g->name[k], p + o, nl)) found = k;
+        if (found == 0xffffffffu) { free(chr_map); return -44; }
+        chr_map[c] = found;
+        o += nl + ((4 - (nl & 3)) & 3);
+    }
+    if (o + (uint64_t)nb * sizeof(blk_index) > len) { free(chr_map); return -43; }
+    const blk_index *idx = (const blk_index *)(p + o);
+    o += (uint64_t)nb * sizeof(blk_index);
+    int rc = 0; uint64_t n = 0;
+    uint16_t e[3 * 256 + 8]; uint8_t line[1025];
+    for (uint32_t k = 0; k < nb && !rc; k++) {
+        blk_index bi; memcpy(&bi, &idx[k], sizeof bi);
+        if (bi.chr >= n_chr || o + bi.payload_bytes > len) { rc = -45; break; }
+        uint32_t chr = chr_map[bi.chr];
+        rstate s; rstate_init(&s, L, 2);
+        ac_init_dec(&s.c.ac, p + o, bi.payload_bytes);
+        s.prev_pos = bi.base_pos;
+        snp_reset(&s.snp, g->len[chr] + 2048);
+        for (uint32_t r = 0; r < bi.n_reads && !rc; r++) {
+            uint32_t same = get_sym(&s.c, CBCG_S_SAME_REF, 0);
+            if (s.c.err || same != 0) { rc = -46; break; }
+            cbcg_read_rec rec; uint32_t ne = 0;
+            get_read(&s, &rec, e, &ne, g->bases[chr], g->len[chr]);
+            if (s.c.err) { rc = s.c.err; break; }
+            if (rec.len > 1024 || rebuild_read(&rec, e, g->bases[chr], g->len[chr], line)) { rc = -47; break; }
+            line[rec.len] = '\n';
+            buf_put(seq_out, line, rec.len + 1u);
+            n++;
+        }
+        rstate_free(&s);
+        o += bi.payload_bytes;
+    }
+    free(chr_map);
+    if (n_reads_out) *n_reads_out = n;
+    return rc;
+}
