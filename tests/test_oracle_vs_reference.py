@@ -1,0 +1,148 @@
+"""Pins the CPU oracle (oracle/cbc_oracle.c) to the unmodified reference.
+
+* golden: tests/golden/*.cbc are byte streams written by the reference encoder built from
+  /root/reference (tests/golden/make_golden.py); the oracle must reproduce them byte for byte,
+  produce the same symbol trace (digest) and decode them to the reference decoder's output.
+* live: where oracle/_ref/cbc_ref is present (it travels prebuilt), fresh random shapes are pushed
+  through both.
+* known-answer: the traced example of SURVEY.md appendix A.
+"""
+import glob
+import hashlib
+import json
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from cbc_b200 import synth
+from cbc_b200.batch import Batch, Genome
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.json")))
+
+
+def _load(meta_path):
+    with open(meta_path) as f:
+        meta = json.load(f)
+    cfg = synth.SynthConfig(**meta["synth"])
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    with open(meta_path[:-5] + ".cbc", "rb") as f:
+        stream = f.read()
+    return meta, g, b, stream
+
+
+@pytest.mark.parametrize("meta_path", GOLDEN, ids=[os.path.basename(p)[:-5] for p in GOLDEN])
+def test_golden_stream_trace_and_decode(meta_path):
+    meta, g, b, ref_stream = _load(meta_path)
+    assert hashlib.sha256(ref_stream).hexdigest() == meta["stream_sha256"]
+    stream, trace = O.encode_legacy(b, g, meta["read_len_header"], want_trace=True)
+    assert stream == ref_stream                                   # byte-identical bitstream
+    assert len(trace) == meta["trace_symbols"]
+    assert hashlib.sha256(trace.tobytes()).hexdigest() == meta["trace_sha256"]   # identical symbol streams
+    decoded, n = O.decode_legacy(ref_stream, g)
+    assert n == meta["n_reads"]
+    assert hashlib.sha256(decoded).hexdigest() == meta["decoded_sha256"]
+    assert decoded == b.seq_lines()
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 10
+
+
+@pytest.mark.parametrize("meta_path", GOLDEN[:4], ids=[os.path.basename(p)[:-5] for p in GOLDEN[:4]])
+def test_raw_symbols_expand_to_trace(meta_path):
+    """cbco_symbols (raw POS values) + the dynamic pos alphabet replay == the tracer sequence."""
+    meta, g, b, _ = _load(meta_path)
+    recs, edits = O.extract(b, g)
+    raw = O.symbols(b, g, recs, edits, 0, b.n_reads, meta["read_len_header"], legacy=True)
+    exp = O.expand_pos(raw)
+    assert hashlib.sha256(exp.tobytes()).hexdigest() == meta["trace_sha256"]
+
+
+@pytest.mark.parametrize("meta_path", GOLDEN, ids=[os.path.basename(p)[:-5] for p in GOLDEN])
+def test_extract_reconstruct_roundtrip(meta_path):
+    _, g, b, _ = _load(meta_path)
+    recs, edits = O.extract(b, g)
+    assert O.reconstruct(recs, edits, b.chr, g) == b.seq_lines()
+
+
+@pytest.mark.parametrize("block_reads", [1, 7, 256, 100000])
+def test_blocked_container_roundtrip(block_reads):
+    meta, g, b, ref_stream = _load(GOLDEN[2])
+    c = O.encode_blocked(b, g, meta["read_len_header"], block_reads)
+    decoded, n = O.decode_blocked(c, g)
+    assert n == b.n_reads and decoded == b.seq_lines()
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kw,L", [
+    (dict(seed=101, genome_len=300_000, n_reads=30_000, len_min=100, len_max=100, p_sub=0.005, p_indel=0.001), 100),
+    (dict(seed=102, genome_len=100_000, n_reads=20_000, len_min=150, len_max=150, p_sub=0.005), 150),
+    (dict(seed=103, genome_len=200_000, n_reads=10_000, len_min=200, len_max=200, p_sub=0.01, p_indel=0.02, p_clip=0.3), 200),
+])
+def test_live_reference(kw, L):
+    cfg = synth.SynthConfig(**kw)
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g)
+        synth.write_sam(sam, b, g)
+        ref_stream, ref_trace, _ = O.run_reference(sam, fa, d, trace=True)
+        stream, trace = O.encode_legacy(b, g, L, want_trace=True)
+        assert stream == ref_stream
+        assert np.array_equal(trace, ref_trace)
+        sp = os.path.join(d, "s.cbc")
+        with open(sp, "wb") as f:
+            f.write(stream)
+        ref_decoded, _ = O.run_reference_decode(sp, fa, d)
+    decoded, _ = O.decode_legacy(stream, g)
+    assert decoded == ref_decoded == b.seq_lines()
+
+
+def _one_read_batch(pos, flag, seq, cigar, md):
+    def pool(items):
+        off = np.zeros(len(items) + 1, np.uint64)
+        off[1:] = np.cumsum([len(x) for x in items])
+        return off, np.frombuffer(b"".join(items), np.uint8).copy()
+    so, s = pool(seq); co, c = pool(cigar); mo, m = pool(md)
+    n = len(seq)
+    return Batch(np.array(pos, np.uint32), np.array(flag, np.uint16), np.array([len(x) for x in seq], np.uint16),
+                 np.zeros(n, np.uint32), so, s, co, c, mo, m)
+
+
+def test_known_answer_survey_appendix_a():
+    """FLAG=16 POS=4 CIGAR=17M2D32M1I41M1I1M3D7M MD:Z:17^TG74^AGC7."""
+    rng = np.random.default_rng(3)
+    ref = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 400)].copy()
+    # force the deleted reference bases named by the MD string
+    p0 = 3                                                   # 0-based start
+    ref[p0 + 17:p0 + 19] = np.frombuffer(b"TG", np.uint8)
+    ref[p0 + 19 + 74:p0 + 19 + 77] = np.frombuffer(b"AGC", np.uint8)
+    r = ref.tobytes()
+    seq = (r[p0:p0 + 17] + r[p0 + 19:p0 + 19 + 32] + b"A" + r[p0 + 51:p0 + 51 + 41] + b"C" + r[p0 + 92:p0 + 93]
+           + r[p0 + 96:p0 + 103])
+    assert len(seq) == 100
+    second = r[10:110]
+    b = _one_read_batch([4, 11], [16, 0], [seq, second], [b"17M2D32M1I41M1I1M3D7M", b"100M"], [b"17^TG74^AGC7", b"100"])
+    g = Genome(["chrI"], [ref])
+    _, trace = O.encode_legacy(b, g, 100, want_trace=True)
+    keys = (trace["key"] >> 24).tolist()
+    vals = trace["value"].tolist()
+    ctxs = (trace["key"] & 0xffffff).tolist()
+    # header: read_length, 32 x 0x55555555, LOSSLESS
+    assert vals[:4] == [0, 0, 0, 100] and vals[4:8] == [85] * 4 and vals[132:136] == [0, 0, 0, 8]
+    body = list(zip(keys[136:], ctxs[136:], vals[136:]))
+    S = {n: i for i, n in enumerate(O.STREAMS)}
+    expect = [(S["same_ref"], 0, 1), (S["rname"], 0, 99), (S["rname"], 99, 104), (S["rname"], 104, 114),
+              (S["rname"], 114, 73), (S["rname"], 73, 0),
+              (S["rlength"], 0, 100), (S["rlength"], 1, 0), (S["rlength"], 2, 0), (S["rlength"], 3, 0),
+              (S["pos"], 0, 0), (S["pos_alpha"], 0, 0), (S["pos_alpha"], 1, 0), (S["pos_alpha"], 2, 0), (S["pos_alpha"], 3, 5),
+              (S["flag"], 0, 16), (S["match"], 0, 0),
+              (S["snps"], 0, 0), (S["indels"], 0, 0), (S["indels"], 0, 5), (S["indels"], 0, 2),
+              (S["var"], 1, 17), (S["var"], 35, 0), (S["var"], 35, 74), (S["var"], 183, 0), (S["var"], 183, 0),
+              (S["var"], 1, 49), (S["chars"], 5, 0), (S["var"], 99, 41), (S["chars"], 5, 1)]
+    assert body[:len(expect)] == expect
