@@ -1,0 +1,85 @@
+/*
+ * ac_core.h -- the reference's 26-bit arithmetic coder (src/Arithmetic_stream.c:274-454) as
+ * closed-form integer steps.
+ *
+ * The reference renormalises one bit per loop iteration (E1/E2: equal MSBs -> emit; E3: l = 01..,
+ * u = 10.. -> count a pending bit). After an interval update that loop always runs as
+ *     k x (E1/E2)   followed by   m x (E3)
+ * because an E3 step leaves l's MSB 0 and u's MSB 1, so no E1/E2 step can follow it. Here k is the
+ * number of leading bits l and u share and m the length of the run, below the MSB, where l has ones
+ * and u zeros; both come from one count-leading-zeros each, so a symbol costs a fixed handful of
+ * integer instructions instead of a data-dependent loop. Compiled for host (unit tests against a
+ * bit-serial restatement) and device.
+ */
+#pragma once
+#include <stdint.h>
+#include "cbcg_format.h"
+
+#ifdef __CUDACC__
+#define AC_HD __host__ __device__ __forceinline__
+#else
+#define AC_HD static inline
+#endif
+
+AC_HD uint32_t ac_clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__clz((int)x);
+#else
+    return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
+
+/* floor(p / n) for p < 2^46, 0 < n < 2^26 (both exact in a double; round-down division keeps the floor). */
+AC_HD uint64_t ac_div(uint64_t p, uint32_t n) {
+#ifdef __CUDA_ARCH__
+    return (uint64_t)__double2ull_rz(__ddiv_rd(__ull2double_rz(p), (double)n));
+#else
+    return p / n;
+#endif
+}
+
+struct AcInterval { uint32_t l, u; };
+
+/* Interval update of arithmetic_encoder_step / arithmetic_decoder_step (:295-296, :402-403):
+ * u is computed from the old l, both products in 64 bits, truncated to 32. */
+AC_HD void ac_narrow(AcInterval &a, uint32_t lo, uint32_t hi, uint32_t n) {
+    const uint64_t range = (uint64_t)a.u - a.l + 1u;
+    const uint32_t nu = a.l + (uint32_t)ac_div(range * hi, n) - 1u;
+    const uint32_t nl = a.l + (uint32_t)ac_div(range * lo, n);
+    a.u = nu; a.l = nl;
+}
+
+/* Renormalisation shape: k E1/E2 shifts (the top k bits of l are the emitted bits), then m E3 shifts. */
+AC_HD void ac_renorm_shape(const AcInterval &a, uint32_t &k, uint32_t &bits, uint32_t &m, AcInterval &out) {
+    const uint32_t x = (a.l ^ a.u) & CBCG_AC_TOP;
+    k = x ? (ac_clz32(x) - (32u - CBCG_AC_BITS)) : CBCG_AC_BITS;
+    bits = k ? (a.l >> (CBCG_AC_BITS - k)) : 0u;
+    uint32_t l = (uint32_t)(((uint64_t)a.l << k) & CBCG_AC_TOP);
+    uint32_t u = (uint32_t)((((uint64_t)a.u << k) & CBCG_AC_TOP) | ((1ull << k) - 1ull));
+    /* run of (l bit = 1, u bit = 0) from bit 24 downwards */
+    const uint32_t z = (l & ~u) << (32u - (CBCG_AC_BITS - 1u));      /* bit 24 -> bit 31 */
+    m = ac_clz32(~z);
+    if (m > CBCG_AC_BITS - 1u) m = CBCG_AC_BITS - 1u;
+    if (m) {
+        l = (l << m) & CBCG_AC_LOWMASK;
+        u = ((u << m) & CBCG_AC_LOWMASK) | CBCG_AC_MSB | ((1u << m) - 1u);
+    }
+    out.l = l; out.u = u;
+}
+
+/* Decoder tag update for the same shape (:431-453): k plain shifts, then m shifts whose last one
+ * leaves the MSB flipped. `in` holds the next k + m stream bits, first bit most significant. */
+AC_HD uint32_t ac_tag_shift(uint32_t t, uint32_t k, uint32_t m, uint32_t in) {
+    const uint32_t s = k + m;
+    if (s == 0) return t;
+    uint32_t r = (uint32_t)((((uint64_t)t << s) & CBCG_AC_TOP) | in);
+    if (m) r ^= CBCG_AC_MSB;
+    return r;
+}
+
+/* arithmetic_get_symbol_range (:373-381) */
+AC_HD uint32_t ac_target(const AcInterval &a, uint32_t t, uint32_t n) {
+    const uint64_t range = (uint64_t)a.u - a.l + 1u;
+    const uint64_t gap = (uint64_t)t - a.l + 1u;
+    return (uint32_t)ac_div(gap * n - 1u, (uint32_t)range);
+}

@@ -1,0 +1,86 @@
+/* internal.h -- device-side data layout shared by the kernels and the host API (api.cu). */
+#pragma once
+#include <stdint.h>
+#include "cbcg.h"
+
+/* Read batch resident in HBM: the SoA arrays of cbcg_batch, pools padded by POOL_PAD bytes so that
+ * 16-byte-aligned bulk copies may over-read past the last record. */
+#define POOL_PAD 64u
+
+struct DevBatch {
+    uint64_t n_reads;
+    const uint32_t *pos;
+    const uint16_t *flag;
+    const uint16_t *seq_len;
+    const uint32_t *chr;
+    const uint64_t *seq_off;   const uint8_t *seq;
+    const uint64_t *cigar_off; const uint8_t *cigar;
+    const uint64_t *md_off;    const uint8_t *md;
+    uint32_t max_len;                      /* max(seq_len) */
+};
+
+/* Reference genome resident in HBM: one byte per base, upper-cased, records concatenated with
+ * each record start aligned to 256 bytes and REF_PAD bytes of 'N' after each record. */
+#define REF_PAD 1024u
+#define MAX_CHR 4096u
+
+struct DevGenome {
+    uint32_t n_chr;
+    const uint8_t *bases;                  /* whole buffer */
+    const uint64_t *chr_off;               /* [n_chr] byte offset of each record in `bases` */
+    const uint64_t *chr_len;               /* [n_chr] */
+};
+
+/* One independently coded block of position-ordered reads. */
+struct BlockDesc {
+    uint32_t first_read;                   /* ordinal of its first read in the shard */
+    uint32_t n_reads;
+    uint32_t chr;
+    uint32_t base_pos;                     /* prevPos at block start: POS of its first read (0 in single-block mode) */
+    uint32_t n_edits;                      /* edit entries of the block: bounds its var rows */
+    uint32_t gen;                          /* generation (0: reference initial state) */
+    uint32_t payload_bytes;                /* coded size (encoder output / decoder input) */
+    uint32_t n_symbols;
+    uint64_t edit_base;                    /* first edit entry of the block in the edit array */
+    uint64_t payload_off;                  /* decoder: offset of the block's bytes in the payload buffer;
+                                              encoder: offset of its scratch output region */
+    uint64_t ws_off;                       /* offset of its model workspace (bytes) */
+    uint64_t sym_off;                      /* symbol-list mode: first entry of its list */
+};
+
+/* Coder launch parameters. */
+struct CoderParams {
+    uint32_t n_blocks;
+    uint32_t L;                            /* header read length = alphabet of snps / indels / var */
+    uint32_t legacy;                       /* 1: single block in the reference's own stream layout */
+    uint32_t mode;                         /* 0 encode, 1 decode, 2 symbol list */
+    BlockDesc *blocks;
+    cbcg_read_rec *recs;                   /* in (encode, list) / out (decode) */
+    uint16_t *edits;                       /* in / out */
+    uint32_t *chr;                         /* per read: in (encode) / out (decode) */
+    DevGenome genome;
+    uint8_t *ws;                           /* model workspace */
+    uint8_t *payload;                      /* encode: per-block scratch regions; decode: compact payload */
+    cbcg_symbol *symbols;                  /* list mode */
+    const uint8_t *chr_names;              /* legacy: NUL-terminated names, MAX_NAME bytes each */
+    unsigned long long *err;
+};
+#define MAX_NAME 256u
+
+/* Host-callable launchers (defined in the .cu files). */
+int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, uint16_t *edits,
+                   uint64_t edits_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_edits,
+                   unsigned long long *err, cudaStream_t st);
+int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr, const uint16_t *edits,
+                       const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len,
+                       uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
+                       unsigned long long *err, cudaStream_t st);
+uint64_t extract_num_tiles(uint64_t n_reads);
+uint64_t reconstruct_num_tiles(uint64_t n_reads);
+int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap,
+                uint64_t payload_cap, uint64_t *totals, cudaStream_t st);
+int launch_coder(const CoderParams &p, cudaStream_t st);
+int launch_gather(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
+                  uint64_t *out_off, cudaStream_t st);
+uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy);
+uint64_t coder_payload_bound(uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy);

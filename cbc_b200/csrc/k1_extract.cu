@@ -1,0 +1,332 @@
+/*
+ * k1_extract.cu -- K1: per-read edit extraction (hot path part 1).
+ *
+ * Replaces compress_edits + add_snps_to_array of the reference (src/read_compression.c:265-606,
+ * 613-701) minus the symbol emission: for every read it decides the perfect-match bit
+ * (:291-296) and, for the others, walks CIGAR and MD into the deletion / SNP / insertion
+ * position-delta lists the reference's coder consumes (:308-552).
+ *
+ * B200 design. One CTA per tile of K1_TILE position-adjacent reads:
+ *   - the tile's SEQ bytes (contiguous in the pool) and the reference window under its first reads
+ *     are staged into shared memory by two 1-D TMA bulk copies completing on one mbarrier;
+ *   - phase 1, warp per read: 32-bit word compare of SEQ against the window (ballot -> match bit);
+ *   - phase 2, lane per read: serial CIGAR/MD walk of the non-matching reads, counting edits;
+ *   - a CTA scan of the counts and a decoupled look-back across tiles give every read its slot in
+ *     the edit array in ONE pass over the input (no count kernel + scan kernel + write kernel);
+ *   - phase 3, lane per read: the same walk again, now writing u16 edit entries and the 16-byte record.
+ * Algorithmic HBM bytes per read: L + CIGAR + MD + 24 (fixed fields) + L/coverage (window) + 16 + 2*edits.
+ */
+#include "common.cuh"
+#include "internal.h"
+
+#define K1_TILE     128u          /* reads per tile == threads per CTA */
+#define K1_WARPS    (K1_TILE / 32u)
+#define K1_REF_CAP  8192u         /* bytes of reference window staged per tile */
+
+uint64_t extract_num_tiles(uint64_t n_reads) { return (n_reads + K1_TILE - 1) / K1_TILE; }
+
+/* ------------------------------------------------------------------------------------------------
+ * The resumable MD walker: add_snps_to_array (src/read_compression.c:613-701) and
+ * compute_num_digits (:720-743). State (ptr, cum) mirrors the reference's statics prevEditPtr / cumPos. */
+struct MdWalk {
+    const uint8_t *md;
+    uint32_t n, ptr, cum;
+    __device__ __forceinline__ uint32_t ch(uint32_t off) const { return off < n ? md[off] : 0u; }
+    __device__ __forceinline__ uint32_t atoi_at(uint32_t off) const {
+        uint32_t v = 0;
+        while (off < n) {
+            uint32_t c = md[off];
+            if (c < '0' || c > '9') break;
+            v = v * 10u + (c - '0');
+            off++;
+        }
+        return v;
+    }
+};
+__device__ __forceinline__ uint32_t num_digits(uint32_t x) {
+    uint32_t d = 1;
+    while (x >= 10u && d < 9u) { x /= 10u; d++; }
+    return d;
+}
+__device__ __forceinline__ bool is_digit(uint32_t c) { return c >= '0' && c <= '9'; }
+
+struct EditSink {
+    uint16_t *dst;          /* NULL: count only */
+    uint32_t nd_total, ns_total;   /* write mode: counts from the count pass (slot bases) */
+    uint32_t n_dels, n_snps, n_ins;
+    int err;
+    __device__ __forceinline__ void del(uint32_t delta) {
+        if (delta > 255u) err = 1;
+        if (dst && n_dels < 255u) dst[n_dels] = CBCG_EDIT(delta & 0xffu, 0, 0);
+        n_dels++;
+    }
+    __device__ __forceinline__ void snp(uint32_t delta, uint32_t target, uint32_t refb) {
+        if (delta > 255u) err = 1;
+        if (dst && n_snps < 255u) dst[nd_total + n_snps] = CBCG_EDIT(delta & 0xffu, target, refb);
+        n_snps++;
+    }
+    __device__ __forceinline__ void ins(uint32_t delta, uint32_t target) {
+        if (delta > 255u) err = 1;
+        if (dst && n_ins < 255u) dst[nd_total + ns_total + n_ins] = CBCG_EDIT(delta & 0xffu, target, CBCG_BP_O);
+        n_ins++;
+    }
+};
+
+/* Returns non-zero while SNPs may remain, 0 when the MD string is used up. */
+__device__ static int md_walk(MdWalk &w, EditSink &out, uint32_t insertion_pos, const uint8_t *read, uint32_t read_len) {
+    while (w.ch(w.ptr) != 0) {
+        /* look ahead: matches up to the next mismatch, across deletions (:626-649) */
+        uint32_t pos = w.atoi_at(w.ptr), temp = pos;
+        uint32_t o = w.ptr + num_digits(pos);
+        uint32_t c = w.ch(o); o++;
+        bool hit_end = false;
+        while (c == '^') {
+            while (w.ch(o) != 0 && !is_digit(w.ch(o))) o++;
+            uint32_t v = w.atoi_at(o);
+            temp += v; o += num_digits(v);
+            c = w.ch(o); o++;
+            if (c == 0) { hit_end = true; break; }
+        }
+        if (hit_end) break;
+        if (w.cum + temp >= insertion_pos) { w.cum++; return 1; }          /* :656-659 */
+        /* consume (:661-682) */
+        w.ptr += num_digits(pos);
+        c = w.ch(w.ptr); w.ptr++;
+        while (c == '^') {
+            while (w.ch(w.ptr) != 0 && !is_digit(w.ch(w.ptr))) w.ptr++;
+            uint32_t v = w.atoi_at(w.ptr);
+            pos += v; w.ptr += num_digits(v);
+            c = w.ch(w.ptr); w.ptr++;
+        }
+        if (c == 0) break;
+        w.cum += pos;
+        out.snp(pos, base_code(w.cum < read_len ? read[w.cum] : 0u), base_code(c));
+        w.cum++;
+        if (w.ch(w.ptr) == 0) break;
+        if (out.n_snps > 1024u) { out.err = 1; break; }
+    }
+    w.ptr = 0; w.cum = 0;
+    return 0;
+}
+
+/* CIGAR walk of compress_edits (src/read_compression.c:308-552). read points into shared memory. */
+__device__ static void walk_read(const uint8_t *read, uint32_t len, const uint8_t *cigar, uint32_t cigar_len,
+                                 const uint8_t *md, uint32_t md_len, EditSink &out) {
+    MdWalk w = { md, md_len, 0u, 0u };
+    uint32_t M = 0, prev_i = 0, prev_d = 0;
+    int last_snp = 1, first = 1;
+    uint32_t i = 0;
+    while (i < cigar_len) {
+        uint32_t num = 0, j = i;
+        while (j < cigar_len && is_digit(cigar[j])) num = num * 10u + (uint32_t)(cigar[j++] - '0');
+        if (j >= cigar_len) { out.err = 1; return; }
+        uint32_t op = cigar[j];
+        if (num > 1024u && op != 'H' && op != 'P') { out.err = 1; return; }     /* cannot be a <=252-base read */
+        switch (op) {
+            case 'M': case '=': case 'X':
+                M += num; break;
+            case 'I':                                                          /* :321-337 */
+                for (uint32_t k = 0; k < num; k++) {
+                    if (last_snp) last_snp = md_walk(w, out, M + out.n_ins, read, len);
+                    uint32_t at = M + out.n_ins;
+                    out.ins(M - prev_i, base_code(at < len ? read[at] : 0u));
+                    prev_i = M;
+                }
+                break;
+            case 'D':                                                          /* :340-352 */
+                for (uint32_t k = 0; k < num; k++) { out.del(M - prev_d); prev_d = M; }
+                break;
+            case 'S':
+                if (first) {                                                   /* leading clip :358-468 */
+                    for (uint32_t k = 0; k < num; k++) {
+                        if (last_snp) last_snp = md_walk(w, out, out.n_ins, read, len);
+                        out.ins(0u, base_code(k < len ? read[k] : 0u));
+                    }
+                } else {                                                       /* trailing clip :469-479 */
+                    for (uint32_t k = 0; k < num; k++) {
+                        uint32_t at = M + out.n_ins;
+                        out.ins(M - prev_i, base_code(at < len ? read[at] : 0u));
+                        prev_i = M;
+                    }
+                }
+                break;
+            case 'H': case 'P': break;
+            default: out.err = 1; return;                                      /* '*', 'N', junk */
+        }
+        if (out.err) return;
+        first = 0;
+        i = j + 1;
+    }
+    if (last_snp) md_walk(w, out, len + 1u, read, len);                        /* :551-552 */
+    if (out.n_snps > 255u || out.n_dels > 255u || out.n_ins > 255u) out.err = 1;
+}
+
+struct K1Smem {
+    uint64_t bar;
+    uint64_t tile_base;
+    uint32_t tile;
+    uint32_t warp_tot[K1_WARPS];
+    uint32_t pos[K1_TILE];
+    uint32_t soff[K1_TILE];          /* offset of the read's SEQ in seq[] */
+    uint32_t cnt[K1_TILE];           /* n_snps | n_dels << 8 | n_ins << 16 | match << 24 | bad << 25 */
+    uint32_t excl[K1_TILE];
+    uint16_t len[K1_TILE];
+    uint16_t chr_ok[K1_TILE];        /* read may use the staged window */
+    __align__(16) uint8_t ref[K1_REF_CAP + 16];
+    __align__(16) uint8_t seq[16];   /* really K1_TILE * max_len + 48 (dynamic) */
+};
+
+__global__ void __launch_bounds__(K1_TILE)
+k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uint16_t *__restrict__ edits,
+                  uint64_t edits_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_edits,
+                  unsigned long long *err, uint32_t seq_cap) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    K1Smem &S = *reinterpret_cast<K1Smem *>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) {
+        S.tile = atomicAdd(ticket, 1u);
+        mbar_init(&S.bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const uint64_t r0 = (uint64_t)tile * K1_TILE;
+    const uint32_t nr = (uint32_t)min((uint64_t)K1_TILE, b.n_reads - r0);
+
+    /* tile geometry (uniform): SEQ byte range and reference window */
+    const uint64_t s0 = b.seq_off[r0], s1 = b.seq_off[r0 + nr];
+    const uint64_t a0 = s0 & ~15ull;
+    const uint64_t seq_bytes = (s1 - a0 + 15ull) & ~15ull;
+    const bool seq_ok = (s1 >= s0) && (seq_bytes <= seq_cap);
+    const uint32_t chr0 = b.chr[r0], pos0 = b.pos[r0];
+    uint64_t w0 = 0; uint32_t ref_bytes = 0; uint64_t clen0 = 0;
+    const uint8_t *ref0 = nullptr;
+    if (chr0 < g.n_chr) {
+        clen0 = g.chr_len[chr0];
+        ref0 = g.bases + g.chr_off[chr0];
+        w0 = pos0 ? ((uint64_t)(pos0 - 1u) & ~15ull) : 0ull;
+        uint64_t avail = (clen0 + REF_PAD > w0) ? ((clen0 + REF_PAD - w0) & ~15ull) : 0ull;
+        ref_bytes = (uint32_t)min((uint64_t)K1_REF_CAP, avail);
+    }
+    if (tid == 0) {
+        uint32_t tx = (seq_ok ? (uint32_t)seq_bytes : 0u) + ref_bytes;
+        mbar_expect_tx(&S.bar, tx);
+        if (seq_ok && seq_bytes) tma_load_1d(S.seq, b.seq + a0, (uint32_t)seq_bytes, &S.bar);
+        if (ref_bytes) tma_load_1d(S.ref, ref0 + w0, ref_bytes, &S.bar);
+    }
+
+    /* per-read fixed fields while the copies fly */
+    uint32_t my_pos = 0, my_len = 0, my_chr = 0, my_flag = 0;
+    uint64_t my_co = 0, my_mo = 0; uint32_t my_clen = 0, my_mlen = 0;
+    if (tid < nr) {
+        const uint64_t r = r0 + tid;
+        my_pos = b.pos[r]; my_len = b.seq_len[r]; my_chr = b.chr[r]; my_flag = b.flag[r];
+        const uint64_t so = b.seq_off[r];
+        my_co = b.cigar_off[r]; my_clen = (uint32_t)(b.cigar_off[r + 1] - my_co);
+        my_mo = b.md_off[r];    my_mlen = (uint32_t)(b.md_off[r + 1] - my_mo);
+        S.pos[tid] = my_pos; S.len[tid] = (uint16_t)my_len; S.soff[tid] = (uint32_t)(so - a0);
+        bool in_win = (my_chr == chr0) && ref_bytes && my_pos >= 1u && (uint64_t)(my_pos - 1u) >= w0 &&
+                      ((uint64_t)(my_pos - 1u) - w0 + my_len + 8u <= ref_bytes);
+        S.chr_ok[tid] = in_win ? 1 : 0;
+    }
+    __syncthreads();
+    mbar_wait(&S.bar, 0);
+
+    /* ---- phase 1: warp per read, perfect-match test (src/read_compression.c:291-296) */
+    for (uint32_t i = warp; i < nr; i += K1_WARPS) {
+        const uint32_t pos = S.pos[i], len = S.len[i], soff = S.soff[i];
+        const uint32_t chr = b.chr[r0 + i];
+        uint32_t diff = 0;
+        bool ok = seq_ok && pos >= 1u && len >= 1u && len <= CBCG_MAX_READ_LEN && chr < g.n_chr;
+        uint64_t clen = 0;
+        if (ok) { clen = (chr == chr0) ? clen0 : g.chr_len[chr]; ok = ((uint64_t)(pos - 1u) + len <= clen); }
+        if (ok) {
+            if (S.chr_ok[i]) {
+                const uint32_t roff = (uint32_t)((uint64_t)(pos - 1u) - w0);
+                const uint32_t words = (len + 3u) >> 2;
+                for (uint32_t j = lane; j < words; j += 32u) {
+                    uint32_t x = lds_u32_unaligned(S.seq, soff + 4u * j) ^ lds_u32_unaligned(S.ref, roff + 4u * j);
+                    uint32_t rem = len - 4u * j;
+                    if (rem < 4u) x &= (1u << (8u * rem)) - 1u;
+                    diff |= x;
+                }
+            } else {                                    /* window miss: straight from HBM */
+                const uint8_t *rp = g.bases + g.chr_off[chr] + (pos - 1u);
+                for (uint32_t j = lane; j < len; j += 32u) diff |= (uint32_t)(S.seq[soff + j] ^ rp[j]);
+            }
+        }
+        const bool match = ok && !__any_sync(FULL_MASK, diff != 0u);
+        if (lane == 0) S.cnt[i] = match ? (1u << 24) : 0u;
+    }
+    __syncthreads();
+
+    /* ---- phase 2: lane per read, count edits */
+    uint32_t my_cnt = 0, my_total = 0;
+    if (tid < nr) {
+        my_cnt = S.cnt[tid];
+        bool bad = !seq_ok || my_pos == 0u || my_len == 0u || my_len > CBCG_MAX_READ_LEN || my_chr >= g.n_chr;
+        if (!bad && !(my_cnt >> 24)) {
+            EditSink sink = { nullptr, 0u, 0u, 0u, 0u, 0u, 0 };
+            walk_read(S.seq + S.soff[tid], my_len, b.cigar + my_co, my_clen, b.md + my_mo, my_mlen, sink);
+            if (sink.err) bad = true;
+            else { my_cnt = sink.n_snps | (sink.n_dels << 8) | (sink.n_ins << 16); my_total = sink.n_snps + sink.n_dels + sink.n_ins; }
+        }
+        if (bad) { my_cnt = 1u << 25; my_total = 0; dev_set_error(err, CBCG_ERR_INPUT, r0 + tid); }
+    }
+    /* CTA exclusive scan of my_total */
+    uint32_t incl = warp_incl_scan(my_total);
+    if (lane == 31) S.warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t warp_base = 0, tile_total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < K1_WARPS; k++) { uint32_t t = S.warp_tot[k]; if (k < warp) warp_base += t; tile_total += t; }
+    const uint32_t my_excl = warp_base + incl - my_total;
+
+    if (warp == 0) {
+        uint64_t base = lookback_exclusive(tile_desc, tile, tile_total, err);
+        if (lane == 0) {
+            S.tile_base = base;
+            if (r0 + nr == b.n_reads) *total_edits = base + tile_total;
+        }
+    }
+    __syncthreads();
+    const uint64_t tile_base = S.tile_base;
+
+    /* ---- phase 3: write records and edit entries */
+    if (tid < nr) {
+        const uint64_t off = tile_base + my_excl;
+        cbcg_read_rec rec;
+        rec.pos = my_pos; rec.flag = (uint16_t)my_flag; rec.len = (uint16_t)my_len;
+        rec.edit_off = (uint32_t)off;
+        rec.match = (uint8_t)((my_cnt >> 24) & 1u);
+        rec.n_snps = (uint8_t)(my_cnt & 0xffu); rec.n_dels = (uint8_t)((my_cnt >> 8) & 0xffu); rec.n_ins = (uint8_t)((my_cnt >> 16) & 0xffu);
+        reinterpret_cast<uint4 *>(recs)[r0 + tid] = *reinterpret_cast<uint4 *>(&rec);
+        if (my_total) {
+            if (off + my_total > edits_cap) dev_set_error(err, CBCG_ERR_CAPACITY, r0 + tid);
+            else {
+                EditSink sink = { edits + off, rec.n_dels, rec.n_snps, 0u, 0u, 0u, 0 };
+                walk_read(S.seq + S.soff[tid], my_len, b.cigar + my_co, my_clen, b.md + my_mo, my_mlen, sink);
+            }
+        }
+    }
+}
+
+int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, uint16_t *edits,
+                   uint64_t edits_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_edits,
+                   unsigned long long *err, cudaStream_t st) {
+    if (b.n_reads == 0) return 0;
+    const uint64_t tiles = extract_num_tiles(b.n_reads);
+    const uint32_t seq_cap = (K1_TILE * b.max_len + 48u) & ~15u;
+    const size_t smem = sizeof(K1Smem) + seq_cap + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(k1_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured = smem;
+    }
+    if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;
+    k1_extract_kernel<<<(unsigned)tiles, K1_TILE, smem, st>>>(b, g, recs, edits, edits_cap, tile_desc, ticket,
+                                                             total_edits, err, seq_cap);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

@@ -1,0 +1,239 @@
+/*
+ * k3_reconstruct.cu -- K3: read reconstruction (hot path part 3).
+ *
+ * Replaces reconstruct_read's base-building half (src/read_decompression.c:383-384 perfect match,
+ * :418-437 deletions and fill, :442-458 SNP substitution, :464-515 insertions) followed by
+ * print_line (src/compression.c:16-40): reverse-strand reads are reverse-complemented by the
+ * first and again by the second, so the emitted line is the forward construction for both
+ * strands. Output is SEQ + '\n' per read, reads in input order.
+ *
+ * B200 design. One CTA per tile of K3_TILE reads; the reference window under the tile is staged by a
+ * 1-D TMA bulk copy; the tile's output bytes are assembled in shared memory (warp per read, one lane
+ * per output byte) and leave with one TMA bulk store (16-byte aligned middle) plus byte stores for the
+ * ragged ends. Output offsets come from a decoupled look-back over tile byte totals, so variable-length
+ * reads need no separate scan pass.
+ * Algorithmic HBM bytes per read: 16 (record) + 2*edits + 4 (chr) + L/coverage (window) + L + 1 (output).
+ */
+#include "common.cuh"
+#include "internal.h"
+
+#define K3_TILE     128u
+#define K3_WARPS    8u
+#define K3_THREADS  (K3_WARPS * 32u)
+#define K3_REF_CAP  8192u
+
+uint64_t reconstruct_num_tiles(uint64_t n_reads) { return (n_reads + K3_TILE - 1) / K3_TILE; }
+
+struct K3Warp {                       /* per-warp scratch: edit positions of the read being built */
+    uint16_t cumdel[256];             /* cumulative deletion offsets */
+    uint16_t snp_at[256];             /* aligned index of each SNP */
+    uint16_t ins_at[256];             /* output index of each inserted base */
+    uint8_t  snp_ch[256];
+    uint8_t  ins_ch[256];
+};
+
+struct K3Smem {
+    uint64_t bar;
+    uint64_t tile_base;
+    uint32_t tile;
+    uint32_t warp_tot[K3_WARPS];
+    uint32_t out_off[K3_TILE];        /* byte offset of each read's line inside the tile */
+    cbcg_read_rec rec[K3_TILE];
+    uint32_t chr[K3_TILE];
+    K3Warp w[K3_WARPS];
+    __align__(16) uint8_t ref[K3_REF_CAP + 16];
+    __align__(16) uint8_t out[16];    /* really K3_TILE * (max_len + 1) + 32 (dynamic) */
+};
+
+__global__ void __launch_bounds__(K3_THREADS)
+k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, const uint32_t *__restrict__ chr_of,
+                      const uint16_t *__restrict__ edits, DevGenome g, uint8_t *__restrict__ out, uint64_t out_cap,
+                      uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes, unsigned long long *err,
+                      uint32_t max_len) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    K3Smem &S = *reinterpret_cast<K3Smem *>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) {
+        S.tile = atomicAdd(ticket, 1u);
+        mbar_init(&S.bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const uint64_t r0 = (uint64_t)tile * K3_TILE;
+    const uint32_t nr = (uint32_t)min((uint64_t)K3_TILE, n_reads - r0);
+
+    /* records (16 B each, coalesced) and chromosome ordinals */
+    uint32_t my_bytes = 0;
+    if (tid < nr) {
+        uint4 v = reinterpret_cast<const uint4 *>(recs)[r0 + tid];
+        *reinterpret_cast<uint4 *>(&S.rec[tid]) = v;
+        S.chr[tid] = chr_of[r0 + tid];
+        uint32_t len = S.rec[tid].len;
+        if (len > max_len || len == 0) { dev_set_error(err, CBCG_ERR_CORRUPT, r0 + tid); len = 0; S.rec[tid].len = 0; }
+        my_bytes = len + 1u;
+    }
+    __syncthreads();
+
+    /* reference window under the tile's first read */
+    const uint32_t chr0 = S.chr[0], pos0 = S.rec[0].pos;
+    uint64_t w0 = 0; uint32_t ref_bytes = 0;
+    if (chr0 < g.n_chr) {
+        const uint64_t clen0 = g.chr_len[chr0];
+        w0 = pos0 ? ((uint64_t)(pos0 - 1u) & ~15ull) : 0ull;
+        uint64_t avail = (clen0 + REF_PAD > w0) ? ((clen0 + REF_PAD - w0) & ~15ull) : 0ull;
+        ref_bytes = (uint32_t)min((uint64_t)K3_REF_CAP, avail);
+    }
+    if (tid == 0) {
+        mbar_expect_tx(&S.bar, ref_bytes);
+        if (ref_bytes) tma_load_1d(S.ref, g.bases + g.chr_off[chr0] + w0, ref_bytes, &S.bar);
+    }
+
+    /* CTA scan of line sizes (threads >= K3_TILE carry 0) */
+    uint32_t incl = warp_incl_scan(my_bytes);
+    if (lane == 31) S.warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t warp_base = 0, tile_total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < K3_WARPS; k++) { uint32_t t = S.warp_tot[k]; if (k < warp) warp_base += t; tile_total += t; }
+    if (tid < nr) S.out_off[tid] = warp_base + incl - my_bytes;
+    if (warp == 0) {
+        uint64_t base = lookback_exclusive(tile_desc, tile, tile_total, err);
+        if (lane == 0) {
+            S.tile_base = base;
+            if (r0 + nr == n_reads) *total_bytes = base + tile_total;
+        }
+    }
+    __syncthreads();
+    const uint64_t tile_base = S.tile_base;
+    /* smem image is shifted so that smem offset == global offset (mod 16): the middle can leave by TMA */
+    const uint32_t shift = (uint32_t)((uint64_t)(out + tile_base) & 15ull);
+    uint8_t *img = S.out + shift;
+    mbar_wait(&S.bar, 0);
+
+    K3Warp &W = S.w[warp];
+    for (uint32_t i = warp; i < nr; i += K3_WARPS) {
+        const cbcg_read_rec rec = S.rec[i];
+        const uint32_t len = rec.len, pos = rec.pos, chr = S.chr[i];
+        uint8_t *dst = img + S.out_off[i];
+        if (len == 0) { if (lane == 0) dst[0] = '\n'; continue; }
+        bool bad = (pos == 0u) || chr >= g.n_chr;
+        const uint32_t nd = rec.match ? 0u : rec.n_dels, ns = rec.match ? 0u : rec.n_snps, ni = rec.match ? 0u : rec.n_ins;
+        if (ni > len) bad = true;
+        const uint32_t aligned = len - (bad ? 0u : ni);
+        uint64_t clen = 0; const uint8_t *gref = nullptr;
+        if (!bad) {
+            clen = g.chr_len[chr]; gref = g.bases + g.chr_off[chr];
+            if ((uint64_t)(pos - 1u) + aligned + nd > clen) bad = true;
+        }
+        if (bad) {
+            if (lane == 0) dev_set_error(err, CBCG_ERR_CORRUPT, r0 + i);
+            for (uint32_t j = lane; j < len; j += 32u) dst[j] = 'N';
+            if (lane == 0) dst[len] = '\n';
+            continue;
+        }
+        const bool in_win = (chr == chr0) && ref_bytes && (uint64_t)(pos - 1u) >= w0 &&
+                            ((uint64_t)(pos - 1u) - w0 + aligned + nd <= ref_bytes);
+        const uint8_t *src = in_win ? (S.ref + (uint32_t)((uint64_t)(pos - 1u) - w0)) : (gref + (pos - 1u));
+
+        if ((nd | ns | ni) == 0u) {                         /* perfect match or no edits: straight copy */
+            for (uint32_t j = lane; j < len; j += 32u) dst[j] = src[j];
+            if (lane == 0) dst[len] = '\n';
+            continue;
+        }
+        /* edit positions: prefix sums of the deltas (lists are short; 32 entries per step) */
+        const uint16_t *e = edits + rec.edit_off;
+        bool malformed = false;
+        {
+            uint32_t carry = 0;
+            for (uint32_t k0 = 0; k0 < nd; k0 += 32u) {
+                uint32_t k = k0 + lane, d = (k < nd) ? CBCG_EDIT_DELTA(e[k]) : 0u;
+                uint32_t s = warp_incl_scan(d) + carry;
+                if (k < nd) W.cumdel[k] = (uint16_t)s;
+                carry = __shfl_sync(FULL_MASK, s, 31);
+            }
+            carry = 0;                                      /* SNP k sits at sum_{i<k}(p_i + 1) + p_k */
+            for (uint32_t k0 = 0; k0 < ns; k0 += 32u) {
+                uint32_t k = k0 + lane; uint32_t ed = (k < ns) ? e[nd + k] : 0u;
+                uint32_t d = (k < ns) ? CBCG_EDIT_DELTA(ed) + 1u : 0u;
+                uint32_t s = warp_incl_scan(d) + carry;
+                if (k < ns) {
+                    W.snp_at[k] = (uint16_t)(s - 1u); W.snp_ch[k] = (uint8_t)base_char(CBCG_EDIT_TARGET(ed));
+                    if (s - 1u >= aligned) malformed = true;
+                }
+                carry = __shfl_sync(FULL_MASK, s, 31);
+            }
+            carry = 0;                                      /* insertion k lands at output index cum_k + k */
+            for (uint32_t k0 = 0; k0 < ni; k0 += 32u) {
+                uint32_t k = k0 + lane; uint32_t ed = (k < ni) ? e[nd + ns + k] : 0u;
+                uint32_t d = (k < ni) ? CBCG_EDIT_DELTA(ed) : 0u;
+                uint32_t s = warp_incl_scan(d) + carry;
+                if (k < ni) {
+                    W.ins_at[k] = (uint16_t)(s + k); W.ins_ch[k] = (uint8_t)base_char(CBCG_EDIT_TARGET(ed));
+                    if (s > aligned) malformed = true;
+                }
+                carry = __shfl_sync(FULL_MASK, s, 31);
+            }
+        }
+        malformed = __any_sync(FULL_MASK, malformed);
+        __syncwarp();
+        if (malformed) {
+            if (lane == 0) dev_set_error(err, CBCG_ERR_CORRUPT, r0 + i);
+            for (uint32_t j = lane; j < len; j += 32u) dst[j] = 'N';
+            if (lane == 0) dst[len] = '\n';
+            __syncwarp();
+            continue;
+        }
+        for (uint32_t j = lane; j < len; j += 32u) {
+            uint32_t q = 0; int hit = -1;
+            for (uint32_t k = 0; k < ni; k++) { uint32_t at = W.ins_at[k]; q += (at < j); if (at == j) hit = (int)k; }
+            uint32_t c;
+            if (hit >= 0) c = W.ins_ch[hit];
+            else {
+                const uint32_t a = j - q;
+                uint32_t sh = 0;
+                for (uint32_t k = 0; k < nd; k++) sh += (W.cumdel[k] <= a);
+                c = src[a + sh];
+                for (uint32_t k = 0; k < ns; k++) if (W.snp_at[k] == a) c = W.snp_ch[k];
+            }
+            dst[j] = (uint8_t)c;
+        }
+        if (lane == 0) dst[len] = '\n';
+        __syncwarp();
+    }
+    fence_proxy_async_smem();          /* generic-proxy smem writes -> visible to the bulk store */
+    __syncthreads();
+
+    /* ---- tile image -> HBM */
+    if (tile_base + tile_total > out_cap) { if (tid == 0) dev_set_error(err, CBCG_ERR_CAPACITY, r0); return; }
+    uint8_t *gdst = out + tile_base;
+    const uint32_t head = min(tile_total, (16u - shift) & 15u);
+    const uint32_t mid = (tile_total - head) & ~15u;
+    const uint32_t tail = tile_total - head - mid;
+    if (tid == 0 && mid) {
+        tma_store_1d(gdst + head, img + head, mid);
+        tma_store_commit_wait();
+    }
+    if (tid >= 32 && tid < 32 + head) gdst[tid - 32] = img[tid - 32];
+    if (tid >= 64 && tid < 64 + tail) gdst[head + mid + (tid - 64)] = img[head + mid + (tid - 64)];
+}
+
+int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr, const uint16_t *edits,
+                       const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len,
+                       uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
+                       unsigned long long *err, cudaStream_t st) {
+    if (n_reads == 0) return 0;
+    const uint64_t tiles = reconstruct_num_tiles(n_reads);
+    const size_t smem = sizeof(K3Smem) + (size_t)K3_TILE * (max_len + 1u) + 64;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(k3_reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured = smem;
+    }
+    if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;
+    k3_reconstruct_kernel<<<(unsigned)tiles, K3_THREADS, smem, st>>>(n_reads, recs, chr, edits, g, out, out_cap,
+                                                                    tile_desc, ticket, total_bytes, err, max_len);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

@@ -1,0 +1,145 @@
+/*
+ * cbcg.h -- C ABI of the B200 implementation of cbc's aligned-read coding path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no CUDA or torch
+ * types. The reference (1mishra/cbc) has no plugin/FFI interface; its seams are ordinary
+ * C functions over process-global state. Each entry point below
+ * names the reference function(s) it replaces. All functions return 0 on success or a
+ * negative cbcg_status; nothing asserts or exits (the reference does:
+ * src/stream_model.c:62,71, src/read_compression.c:41, src/main.c:248-250).
+ *
+ * Threading: one host thread per context; one context per GPU. No globals.
+ * Ownership: the caller owns every host buffer; the context owns all device memory.
+ * There is no CPU fallback: cbcg_create fails if no sm_100 device is usable.
+ */
+#ifndef CBCG_H
+#define CBCG_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include "cbcg_format.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cbcg_status {
+    CBCG_OK              = 0,
+    CBCG_ERR_ARG         = -1,   /* bad argument / NULL */
+    CBCG_ERR_CUDA        = -2,   /* CUDA runtime error (cbcg_last_error has the text) */
+    CBCG_ERR_NO_DEVICE   = -3,   /* no usable sm_100 GPU: there is no CPU path */
+    CBCG_ERR_NOMEM       = -4,
+    CBCG_ERR_CAPACITY    = -5,   /* caller's output buffer too small */
+    CBCG_ERR_INPUT       = -6,   /* a read is outside what the reference can code:
+                                    POS 0, length 0 or > 252, CIGAR '*'/'N'/junk, > 255 edits of a kind,
+                                    unsorted positions, zero-probability symbol (src/stream_model.c:71) */
+    CBCG_ERR_NO_REFERENCE = -7,  /* cbcg_set_reference not called / chromosome ordinal out of range */
+    CBCG_ERR_FORMAT      = -8,   /* container header / index malformed */
+    CBCG_ERR_CORRUPT     = -9,   /* bitstream decodes to an impossible symbol */
+    CBCG_ERR_LIMIT       = -10,  /* internal table limit (distinct FLAG values per block) */
+    CBCG_ERR_INTERNAL    = -11
+} cbcg_status;
+
+typedef struct cbcg_ctx cbcg_ctx;
+
+/* SoA batch of aligned reads: the product of load_sam_line (src/sam_file_allocation.c:437-529)
+ * for n_reads records. Offsets arrays have n_reads + 1 entries; pools are plain bytes. */
+typedef struct cbcg_batch {
+    uint64_t n_reads;
+    const uint32_t *pos;        /* POS, 1-based (sam_line_t.pos) */
+    const uint16_t *flag;       /* FLAG */
+    const uint16_t *seq_len;    /* strlen(SEQ) */
+    const uint32_t *chr;        /* chromosome ordinal into the table given to cbcg_set_reference */
+    const uint64_t *seq_off;    const uint8_t *seq;     /* SEQ */
+    const uint64_t *cigar_off;  const uint8_t *cigar;   /* CIGAR text */
+    const uint64_t *md_off;     const uint8_t *md;      /* MD:Z payload (read_line_t.edits) */
+} cbcg_batch;
+
+typedef struct cbcg_encode_opts {
+    uint32_t read_len_header;   /* what get_read_length returns (src/sam_file_allocation.c:26-79):
+                                   the alphabet size of the snps/indels/var models */
+    uint32_t block_reads;       /* reads per independently coded block; 0 = ONE block holding the whole
+                                   input in the reference's own stream layout (byte-identical to
+                                   `program -c 1` built with -DDEBUG): the verification mode */
+    uint32_t gen_mode;          /* 0: every block starts from the reference's initial model state;
+                                   1: generation-primed blocks */
+    uint32_t reserved;
+} cbcg_encode_opts;
+
+/* Per-call device timings (CUDA events on the library's stream), for bench.py / profiling. */
+typedef struct cbcg_stats {
+    float ms_h2d, ms_extract, ms_plan, ms_code, ms_gather, ms_reconstruct, ms_d2h, ms_total;
+    uint64_t n_reads, n_blocks, n_symbols, n_edits, payload_bytes, container_bytes;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t kernel_launches;
+    uint32_t reserved;
+} cbcg_stats;
+
+/* ---- lifetime */
+int  cbcg_create(int device, cbcg_ctx **out);
+void cbcg_destroy(cbcg_ctx *ctx);
+const char *cbcg_strerror(int status);
+const char *cbcg_last_error(const cbcg_ctx *ctx);      /* detail of the last failure on this context */
+int  cbcg_abi_version(void);
+int  cbcg_get_stats(const cbcg_ctx *ctx, cbcg_stats *out);   /* stats of the last call */
+
+/* ---- reference genome. Replaces store_reference_in_memory (src/read_decompression.c:17-53) and the
+ * chromosome switch in compress_line/decompress_line (src/compression.c:58-64,91-101): all records are
+ * resident at once, upper-cased on upload, addressed by ordinal. names are used for the container. */
+int cbcg_set_reference(cbcg_ctx *ctx, uint32_t n_chr, const char *const *names,
+                       const uint8_t *const *bases, const uint64_t *len);
+
+/* ---- K1: edit extraction. Replaces compress_edits + add_snps_to_array
+ * (src/read_compression.c:265-606, 613-701), without the symbol emission. recs[n_reads];
+ * edits_cap entries of u16; *n_edits receives the number written. */
+int cbcg_extract(cbcg_ctx *ctx, const cbcg_batch *batch, cbcg_read_rec *recs,
+                 uint16_t *edits, uint64_t edits_cap, uint64_t *n_edits);
+
+/* ---- symbol streams, for parity tests: the (stream, ctx, symbol) sequence compress_read hands to
+ * send_value_to_as (src/read_compression.c:15-44, 557-600; src/stream_model.c:53), one list per block.
+ * POS is reported as the raw value x = pos - prevPos + 1 under CBCG_S_POS_X. block_reads == 0 gives the
+ * whole-stream sequence including the 136 header symbols, RNAME symbols and the end marker.
+ * block_sym_count (optional) receives one count per block; *n_blocks the number of blocks. */
+int cbcg_extract_symbols(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_encode_opts *opts,
+                         cbcg_symbol *symbols, uint64_t symbols_cap, uint64_t *n_symbols,
+                         uint64_t *block_sym_count, uint64_t blocks_cap, uint64_t *n_blocks);
+
+/* ---- K1 + K2: encode. Replaces compress() (src/compression.c:112-170) from the first compress_line
+ * on, including the header ints of alloc_sam_models (src/sam_file_allocation.c:363-404) in
+ * single-block mode. out receives the whole container (or the bare reference stream when
+ * opts->block_reads == 0). */
+int cbcg_encode(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_encode_opts *opts,
+                uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+uint64_t cbcg_encode_bound(const cbcg_batch *batch, const cbcg_encode_opts *opts);
+
+/* ---- K2 + K3: decode. Replaces decompress() + print_line (src/compression.c:173-216, 16-40):
+ * seq_out receives SEQ + '\n' per read. legacy != 0: `in` is a bare reference stream. */
+int cbcg_decode(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy,
+                uint8_t *seq_out, uint64_t seq_cap, uint64_t *seq_len, uint64_t *n_reads);
+/* Output size of a container without decoding it (header only); 0 on a malformed header. */
+int cbcg_decoded_size(const uint8_t *in, uint64_t in_len, uint64_t *n_reads, uint64_t *max_seq_bytes);
+
+/* Decode to edit records instead of text (what decompress_read yields before reconstruct_read writes
+ * the bases): for parity tests of the block decoder alone. */
+int cbcg_decode_edits(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy,
+                      cbcg_read_rec *recs, uint64_t recs_cap, uint32_t *chr, uint16_t *edits,
+                      uint64_t edits_cap, uint64_t *n_reads, uint64_t *n_edits);
+
+/* ---- K3: read reconstruction from edit records. Replaces reconstruct_read + print_line
+ * (src/read_decompression.c:339-529, src/compression.c:16-40). */
+int cbcg_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr,
+                     const uint16_t *edits, uint64_t n_edits, uint8_t *seq_out, uint64_t seq_cap,
+                     uint64_t *seq_len);
+
+/* ---- device-resident variants (inputs already in HBM when the timed region starts): upload once,
+ * run many times. Results stay on the device until fetched. Used by bench.py for `value`. */
+int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *batch);                 /* replaces the resident batch */
+int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts);         /* K1 + plan + K2e + gather */
+int cbcg_decode_resident(cbcg_ctx *ctx);                                       /* K2d + K3 on the last encode's blocks */
+int cbcg_fetch_container(cbcg_ctx *ctx, uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+int cbcg_fetch_decoded(cbcg_ctx *ctx, uint8_t *seq_out, uint64_t seq_cap, uint64_t *seq_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBCG_H */
