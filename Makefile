@@ -11,7 +11,7 @@ HOST_SRC  := cbc_b200/csrc/host/sam_ingest.c cbc_b200/csrc/host/container.c
 HOST_HDR  := $(wildcard cbc_b200/csrc/host/*.h) $(wildcard include/*.h)
 
 .PHONY: all host cuda cli oracle clean
-all: host cuda cli
+all: host cuda
 
 host: $(BUILD)/libcbcsynth.so oracle
 

@@ -1,0 +1,286 @@
+"""ctypes binding of the C ABI in include/cbcg.h (cbc_b200/_build/libcbcg.so).
+
+Python mirror of the reference's seams for the aligned-read coding path:
+``Codec.compress`` / ``Codec.decompress`` stand where ``compress()`` / ``decompress()``
+(src/compression.c:112-216) stand in the reference, over SoA batches instead of SAM text.
+There is no CPU path: a missing library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .batch import Batch, CBatch, Genome
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libcbcg.so")
+
+REC_DTYPE = np.dtype([("pos", "<u4"), ("flag", "<u2"), ("len", "<u2"), ("edit_off", "<u4"),
+                      ("match", "u1"), ("n_snps", "u1"), ("n_dels", "u1"), ("n_ins", "u1")])
+SYM_DTYPE = np.dtype([("key", "<u4"), ("value", "<u4")])
+
+EXPORTS = ["cbcg_create", "cbcg_destroy", "cbcg_strerror", "cbcg_last_error", "cbcg_abi_version", "cbcg_get_stats",
+           "cbcg_host_alloc", "cbcg_host_free", "cbcg_set_reference", "cbcg_extract", "cbcg_extract_symbols",
+           "cbcg_encode", "cbcg_encode_bound", "cbcg_decode", "cbcg_decoded_size", "cbcg_decode_edits",
+           "cbcg_reconstruct", "cbcg_batch_upload", "cbcg_encode_resident", "cbcg_decode_resident",
+           "cbcg_fetch_container", "cbcg_fetch_decoded"]
+
+
+class EncodeOpts(C.Structure):
+    _fields_ = [("read_len_header", C.c_uint32), ("block_reads", C.c_uint32), ("gen_mode", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_h2d", C.c_float), ("ms_extract", C.c_float), ("ms_plan", C.c_float), ("ms_code", C.c_float),
+                ("ms_gather", C.c_float), ("ms_reconstruct", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
+                ("n_reads", C.c_uint64), ("n_blocks", C.c_uint64), ("n_symbols", C.c_uint64), ("n_edits", C.c_uint64),
+                ("payload_bytes", C.c_uint64), ("container_bytes", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class CbcgError(RuntimeError):
+    def __init__(self, status: int, text: str):
+        super().__init__(f"cbcg status {status}: {text}")
+        self.status = status
+
+
+_LIB = None
+
+
+def load_library():
+    """Loads libcbcg.so; raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make cuda` or __graft_entry__.build(); "
+                               "there is no CPU implementation of this path")
+        lib = C.CDLL(LIB_PATH)
+        vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+        P = C.POINTER
+        lib.cbcg_create.argtypes = [C.c_int, P(vp)]
+        lib.cbcg_destroy.argtypes = [vp]; lib.cbcg_destroy.restype = None
+        lib.cbcg_strerror.argtypes = [C.c_int]; lib.cbcg_strerror.restype = C.c_char_p
+        lib.cbcg_last_error.argtypes = [vp]; lib.cbcg_last_error.restype = C.c_char_p
+        lib.cbcg_get_stats.argtypes = [vp, P(Stats)]
+        lib.cbcg_host_alloc.argtypes = [C.c_size_t]; lib.cbcg_host_alloc.restype = vp
+        lib.cbcg_host_free.argtypes = [vp]; lib.cbcg_host_free.restype = None
+        lib.cbcg_set_reference.argtypes = [vp, u32, vp, vp, vp]
+        lib.cbcg_extract.argtypes = [vp, P(CBatch), vp, vp, u64, P(u64)]
+        lib.cbcg_extract_symbols.argtypes = [vp, P(CBatch), P(EncodeOpts), vp, u64, P(u64), vp, u64, P(u64)]
+        lib.cbcg_encode.argtypes = [vp, P(CBatch), P(EncodeOpts), vp, u64, P(u64)]
+        lib.cbcg_encode_bound.argtypes = [P(CBatch), P(EncodeOpts)]; lib.cbcg_encode_bound.restype = u64
+        lib.cbcg_decode.argtypes = [vp, vp, u64, C.c_int, vp, u64, P(u64), P(u64)]
+        lib.cbcg_decoded_size.argtypes = [vp, u64, P(u64), P(u64)]
+        lib.cbcg_decode_edits.argtypes = [vp, vp, u64, C.c_int, vp, u64, vp, vp, u64, P(u64), P(u64)]
+        lib.cbcg_reconstruct.argtypes = [vp, u64, vp, vp, vp, u64, vp, u64, P(u64)]
+        lib.cbcg_batch_upload.argtypes = [vp, P(CBatch)]
+        lib.cbcg_encode_resident.argtypes = [vp, P(EncodeOpts)]
+        lib.cbcg_decode_resident.argtypes = [vp]
+        lib.cbcg_fetch_container.argtypes = [vp, vp, u64, P(u64)]
+        lib.cbcg_fetch_decoded.argtypes = [vp, vp, u64, P(u64)]
+        _LIB = lib
+    return _LIB
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """numpy array over page-locked memory from cbcg_host_alloc (kept alive by the array's base)."""
+    lib = load_library()
+    dt = np.dtype(dtype)
+    nbytes = max(int(n) * dt.itemsize, 1)
+    p = lib.cbcg_host_alloc(nbytes)
+    if not p:
+        raise MemoryError("cbcg_host_alloc")
+
+    class _Owner:
+        def __init__(self, ptr): self.ptr = ptr
+        def __del__(self):
+            try: lib.cbcg_host_free(self.ptr)
+            except Exception: pass
+    buf = (C.c_uint8 * nbytes).from_address(p)
+    buf._owner = _Owner(p)
+    return np.frombuffer(buf, dtype=dt, count=int(n))
+
+
+def pin_batch(b: Batch) -> Batch:
+    """Copy of a batch in page-locked memory (what a production ingest thread would fill directly)."""
+    def pin(a):
+        out = pinned_empty(a.shape[0], a.dtype)
+        out[:] = a
+        return out
+    return Batch(pin(b.pos), pin(b.flag), pin(b.seq_len), pin(b.chr), pin(b.seq_off), pin(b.seq),
+                 pin(b.cigar_off), pin(b.cigar), pin(b.md_off), pin(b.md))
+
+
+class Codec:
+    """One context per GPU; one host thread per context."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.cbcg_create(device, C.byref(h))
+        if rc:
+            raise CbcgError(rc, self.lib.cbcg_strerror(rc).decode())
+        self.h = h
+        self._genome_keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cbcg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc:
+            raise CbcgError(rc, self.lib.cbcg_last_error(self.h).decode() or self.lib.cbcg_strerror(rc).decode())
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.lib.cbcg_get_stats(self.h, C.byref(s)))
+        return s.as_dict()
+
+    # ---- reference genome (store_reference_in_memory, src/read_decompression.c:17-53)
+    def set_reference(self, genome: Genome):
+        ptrs, lens, names = genome.c_arrays()
+        self._genome_keep = (genome, ptrs, lens, names)
+        self._check(self.lib.cbcg_set_reference(self.h, genome.n_chr, C.cast(names, C.c_void_p),
+                                                C.cast(ptrs, C.c_void_p), C.cast(lens, C.c_void_p)))
+
+    # ---- K1
+    def extract(self, batch: Batch) -> Tuple[np.ndarray, np.ndarray]:
+        cb = batch.c_struct()
+        recs = np.zeros(max(batch.n_reads, 1), REC_DTYPE)
+        cap = batch.total_bases() // 8 + 4096
+        while True:
+            edits = np.zeros(cap, np.uint16)
+            n = C.c_uint64(0)
+            rc = self.lib.cbcg_extract(self.h, C.byref(cb), recs.ctypes.data, edits.ctypes.data, cap, C.byref(n))
+            if rc == -5 and n.value > cap:
+                cap = n.value + 16
+                continue
+            self._check(rc)
+            return recs[:batch.n_reads], edits[:n.value].copy()
+
+    def symbols(self, batch: Batch, read_len_header: int, block_reads: int = 0):
+        cb = batch.c_struct()
+        opts = EncodeOpts(read_len_header, block_reads, 0, 0)
+        cap = 16 * batch.n_reads + batch.total_bases() // 4 + 8192
+        nb_cap = (batch.n_reads // block_reads + 4200) if block_reads else 1
+        while True:
+            syms = np.zeros(cap, SYM_DTYPE)
+            counts = np.zeros(nb_cap, np.uint64)
+            n, nb = C.c_uint64(0), C.c_uint64(0)
+            rc = self.lib.cbcg_extract_symbols(self.h, C.byref(cb), C.byref(opts), syms.ctypes.data, cap, C.byref(n),
+                                               counts.ctypes.data, nb_cap, C.byref(nb))
+            if rc == -5 and (n.value > cap or nb.value > nb_cap):
+                cap, nb_cap = max(cap, n.value + 16), max(nb_cap, nb.value + 1)
+                continue
+            self._check(rc)
+            return syms[:n.value].copy(), counts[:nb.value].copy()
+
+    # ---- compress() / decompress() (src/compression.c:112-216) over host buffers
+    def compress(self, batch: Batch, read_len_header: int, block_reads: int = 0, out: Optional[np.ndarray] = None) -> bytes:
+        """block_reads == 0: the reference's own single stream (byte-identical to `program -c 1`, -DDEBUG)."""
+        cb = batch.c_struct()
+        opts = EncodeOpts(read_len_header, block_reads, 0, 0)
+        cap = int(self.lib.cbcg_encode_bound(C.byref(cb), C.byref(opts)))
+        buf = out if out is not None and out.nbytes >= cap else np.empty(cap, np.uint8)
+        n = C.c_uint64(0)
+        rc = self.lib.cbcg_encode(self.h, C.byref(cb), C.byref(opts), buf.ctypes.data, buf.nbytes, C.byref(n))
+        if rc == -5 and n.value > buf.nbytes:
+            buf = np.empty(n.value, np.uint8)
+            rc = self.lib.cbcg_fetch_container(self.h, buf.ctypes.data, buf.nbytes, C.byref(n))
+        self._check(rc)
+        return buf[:n.value].tobytes()
+
+    def decompress(self, data: bytes, legacy: bool = False) -> Tuple[bytes, int]:
+        """Returns (SEQ + '\\n' per read, read count): what `program -x` writes (print_line, src/compression.c:16-40)."""
+        src = np.frombuffer(data, np.uint8)
+        n_reads, cap = C.c_uint64(0), C.c_uint64(0)
+        if not legacy:
+            rc = self.lib.cbcg_decoded_size(src.ctypes.data, src.nbytes, C.byref(n_reads), C.byref(cap))
+            if rc:
+                raise CbcgError(rc, self.lib.cbcg_strerror(rc).decode())
+            size = cap.value
+        else:
+            size = 1 << 20
+        while True:
+            out = np.empty(max(size, 1), np.uint8)
+            n, nr = C.c_uint64(0), C.c_uint64(0)
+            rc = self.lib.cbcg_decode(self.h, src.ctypes.data, src.nbytes, int(legacy), out.ctypes.data, out.nbytes,
+                                      C.byref(n), C.byref(nr))
+            if rc == -5 and n.value > out.nbytes:
+                out = np.empty(n.value, np.uint8)
+                rc = self.lib.cbcg_fetch_decoded(self.h, out.ctypes.data, out.nbytes, C.byref(n))
+            self._check(rc)
+            return out[:n.value].tobytes(), nr.value
+
+    def decode_edits(self, data: bytes, legacy: bool = False):
+        src = np.frombuffer(data, np.uint8)
+        rcap, ecap = 1 << 16, 1 << 18
+        while True:
+            recs = np.zeros(rcap, REC_DTYPE); chr_ = np.zeros(rcap, np.uint32); edits = np.zeros(ecap, np.uint16)
+            nr, ne = C.c_uint64(0), C.c_uint64(0)
+            rc = self.lib.cbcg_decode_edits(self.h, src.ctypes.data, src.nbytes, int(legacy), recs.ctypes.data, rcap,
+                                            chr_.ctypes.data, edits.ctypes.data, ecap, C.byref(nr), C.byref(ne))
+            if rc == -5 and (nr.value > rcap or ne.value > ecap):
+                rcap, ecap = max(rcap, nr.value), max(ecap, ne.value)
+                continue
+            self._check(rc)
+            return recs[:nr.value].copy(), chr_[:nr.value].copy(), edits[:ne.value].copy()
+
+    # ---- K3
+    def reconstruct(self, recs: np.ndarray, chr_: np.ndarray, edits: np.ndarray) -> bytes:
+        recs = np.ascontiguousarray(recs); chr_ = np.ascontiguousarray(chr_, np.uint32)
+        edits = np.ascontiguousarray(edits, np.uint16)
+        cap = int(recs["len"].astype(np.int64).sum()) + len(recs) + 64
+        out = np.empty(cap, np.uint8)
+        n = C.c_uint64(0)
+        self._check(self.lib.cbcg_reconstruct(self.h, len(recs), recs.ctypes.data, chr_.ctypes.data,
+                                              edits.ctypes.data if edits.size else None, edits.size,
+                                              out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].tobytes()
+
+    # ---- device-resident variants
+    def upload(self, batch: Batch):
+        cb = batch.c_struct()
+        self._check(self.lib.cbcg_batch_upload(self.h, C.byref(cb)))
+
+    def encode_resident(self, read_len_header: int, block_reads: int):
+        opts = EncodeOpts(read_len_header, block_reads, 0, 0)
+        self._check(self.lib.cbcg_encode_resident(self.h, C.byref(opts)))
+
+    def decode_resident(self):
+        self._check(self.lib.cbcg_decode_resident(self.h))
+
+    def fetch_container(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        n = C.c_uint64(0)
+        rc = self.lib.cbcg_fetch_container(self.h, out.ctypes.data if out is not None else None,
+                                           out.nbytes if out is not None else 0, C.byref(n))
+        if rc == -5:
+            out = np.empty(n.value, np.uint8)
+            rc = self.lib.cbcg_fetch_container(self.h, out.ctypes.data, out.nbytes, C.byref(n))
+        self._check(rc)
+        return out[:n.value]
+
+    def fetch_decoded(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        n = C.c_uint64(0)
+        rc = self.lib.cbcg_fetch_decoded(self.h, out.ctypes.data if out is not None else None,
+                                         out.nbytes if out is not None else 0, C.byref(n))
+        if rc == -5:
+            out = np.empty(n.value, np.uint8)
+            rc = self.lib.cbcg_fetch_decoded(self.h, out.ctypes.data, out.nbytes, C.byref(n))
+        self._check(rc)
+        return out[:n.value]

@@ -1,0 +1,898 @@
+/*
+ * api.cu -- the C ABI of include/cbcg.h over the K1 / K2 / K3 kernels.
+ *
+ * Host side of the drop-in boundary: owns every device buffer, sequences the kernels on one stream,
+ * turns device error words into cbcg_status codes, and frames the blocked container ("CBCB": header,
+ * per-block index, payload; the reference stream has no framing, src/compression.c:128-155). There is
+ * no CPU coding path here: every entry point that codes, extracts or reconstructs launches kernels,
+ * and cbcg_create fails without an sm_100 device.
+ */
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+#define ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------------ */
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct ChrRun { uint64_t first, n; uint32_t chr; };
+
+/* small device words + their pinned host mirror */
+struct Words {
+    unsigned long long err;
+    uint64_t total_edits;
+    uint64_t total_bytes;
+    uint64_t totals[5];
+    uint32_t ticket;
+    uint32_t pad;
+};
+
+struct cbcg_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8] = {};
+    char errtext[512] = {0};
+    cbcg_stats stats = {};
+
+    /* genome */
+    DevBuf g_bases, g_off, g_len, g_names;
+    std::vector<std::string> names;
+    std::vector<uint64_t> h_off, h_len;
+    DevGenome dg = {};
+
+    /* resident batch */
+    DevBuf b_pos, b_flag, b_len, b_chr, b_soff, b_seq, b_coff, b_cigar, b_moff, b_md;
+    DevBatch db = {};
+    std::vector<ChrRun> runs;
+    uint64_t total_bases = 0;
+    bool have_batch = false;
+
+    /* work buffers */
+    DevBuf recs, edits, chr_out, tile_desc, words, blocks, ws, scratch, payload, out_off, symbols, seq_out;
+    Words *hw = nullptr;                       /* pinned */
+    BlockDesc *hblocks = nullptr; size_t hblocks_cap = 0;   /* pinned */
+
+    /* result of the last encode */
+    bool have_encoded = false;
+    uint32_t enc_L = 0, enc_block_reads = 0, enc_gen_mode = 0, enc_legacy = 0, enc_max_len = 0;
+    uint64_t enc_n_reads = 0, enc_n_edits = 0, enc_n_blocks = 0, enc_payload_bytes = 0;
+    std::vector<uint8_t> enc_head;             /* container header + index */
+
+    /* result of the last decode */
+    bool have_decoded = false;
+    uint64_t dec_bytes = 0, dec_n_reads = 0;
+};
+
+static int fail(cbcg_ctx *c, int status, const char *fmt, ...) {
+    if (c) {
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(c->errtext, sizeof c->errtext, fmt, ap);
+        va_end(ap);
+    }
+    return status;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(ctx, e_ == cudaErrorMemoryAllocation ? CBCG_ERR_NOMEM : CBCG_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define TRY(call) do { int r_ = (call); if (r_) return r_; } while (0)
+
+static int ensure(cbcg_ctx *ctx, DevBuf &b, size_t bytes) {
+    bytes = (bytes + 255u) & ~(size_t)255u;
+    if (bytes <= b.cap && b.p) return 0;
+    if (b.p) { CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 4096;            /* a little slack so near-equal batches do not reallocate */
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { want = bytes; (void)cudaGetLastError(); e = cudaMalloc(&b.p, want); }
+    if (e != cudaSuccess) { b.p = nullptr; (void)cudaGetLastError(); return fail(ctx, CBCG_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+    b.cap = want;
+    return 0;
+}
+static int ensure_hblocks(cbcg_ctx *ctx, size_t n) {
+    if (n <= ctx->hblocks_cap) return 0;
+    if (ctx->hblocks) cudaFreeHost(ctx->hblocks);
+    ctx->hblocks = nullptr; ctx->hblocks_cap = 0;
+    size_t want = n + n / 4 + 64;
+    CU(cudaMallocHost(&ctx->hblocks, want * sizeof(BlockDesc)));
+    ctx->hblocks_cap = want;
+    return 0;
+}
+static void free_buf(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+/* device words */
+#define W_OFF(field) (offsetof(Words, field))
+template <class T> static T *wptr(cbcg_ctx *ctx, size_t off) { return reinterpret_cast<T *>(ctx->words.as<uint8_t>() + off); }
+
+static int device_error(cbcg_ctx *ctx, const char *stage) {
+    const unsigned long long v = ctx->hw->err;
+    if (!v) return 0;
+    const int code = -(int)(v >> 40);
+    const unsigned long long item = v & 0xffffffffffull;
+    return fail(ctx, code, "%s: %s at item %llu", stage, cbcg_strerror(code), item);
+}
+
+/* ------------------------------------------------------------------------------------------------ lifetime */
+extern "C" int cbcg_abi_version(void) { return ABI_VERSION; }
+
+extern "C" const char *cbcg_strerror(int s) {
+    switch (s) {
+        case CBCG_OK: return "ok";
+        case CBCG_ERR_ARG: return "bad argument";
+        case CBCG_ERR_CUDA: return "CUDA runtime error";
+        case CBCG_ERR_NO_DEVICE: return "no usable sm_100 GPU (there is no CPU path)";
+        case CBCG_ERR_NOMEM: return "out of memory";
+        case CBCG_ERR_CAPACITY: return "output buffer too small";
+        case CBCG_ERR_INPUT: return "read outside what the reference can code";
+        case CBCG_ERR_NO_REFERENCE: return "reference genome missing or chromosome out of range";
+        case CBCG_ERR_FORMAT: return "malformed container";
+        case CBCG_ERR_CORRUPT: return "corrupt bitstream";
+        case CBCG_ERR_LIMIT: return "internal table limit reached";
+        case CBCG_ERR_INTERNAL: return "internal error";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char *cbcg_last_error(const cbcg_ctx *ctx) { return ctx ? ctx->errtext : "no context"; }
+
+extern "C" int cbcg_create(int device, cbcg_ctx **out) {
+    if (!out) return CBCG_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { (void)cudaGetLastError(); return CBCG_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CBCG_ERR_NO_DEVICE;
+    if (prop.major != 10) return CBCG_ERR_NO_DEVICE;     /* kernels are sm_100a only */
+    if (cudaSetDevice(device) != cudaSuccess) return CBCG_ERR_NO_DEVICE;
+    cbcg_ctx *ctx = new (std::nothrow) cbcg_ctx();
+    if (!ctx) return CBCG_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CBCG_ERR_CUDA; }
+    for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return CBCG_ERR_CUDA; }
+    if (cudaMallocHost(&ctx->hw, sizeof(Words)) != cudaSuccess) { delete ctx; return CBCG_ERR_NOMEM; }
+    memset(ctx->hw, 0, sizeof(Words));
+    if (ensure(ctx, ctx->words, sizeof(Words))) { cudaFreeHost(ctx->hw); delete ctx; return CBCG_ERR_NOMEM; }
+    cudaMemsetAsync(ctx->words.p, 0, sizeof(Words), ctx->st);
+    cudaStreamSynchronize(ctx->st);
+    *out = ctx;
+    return CBCG_OK;
+}
+
+extern "C" void cbcg_destroy(cbcg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    DevBuf *all[] = { &ctx->g_bases, &ctx->g_off, &ctx->g_len, &ctx->g_names, &ctx->b_pos, &ctx->b_flag, &ctx->b_len, &ctx->b_chr,
+                      &ctx->b_soff, &ctx->b_seq, &ctx->b_coff, &ctx->b_cigar, &ctx->b_moff, &ctx->b_md, &ctx->recs, &ctx->edits,
+                      &ctx->chr_out, &ctx->tile_desc, &ctx->words, &ctx->blocks, &ctx->ws, &ctx->scratch, &ctx->payload,
+                      &ctx->out_off, &ctx->symbols, &ctx->seq_out };
+    for (DevBuf *b : all) free_buf(*b);
+    if (ctx->hw) cudaFreeHost(ctx->hw);
+    if (ctx->hblocks) cudaFreeHost(ctx->hblocks);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+extern "C" int cbcg_get_stats(const cbcg_ctx *ctx, cbcg_stats *out) {
+    if (!ctx || !out) return CBCG_ERR_ARG;
+    *out = ctx->stats;
+    return CBCG_OK;
+}
+
+extern "C" void *cbcg_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void cbcg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+/* ------------------------------------------------------------------------------------------------ genome */
+__global__ void genome_prepare_kernel(uint8_t *bases, uint64_t off, uint64_t len, uint64_t span) {
+    /* upper-case the record (store_reference_in_memory, src/read_decompression.c:38-44) and fill its tail pad */
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < span; i += stride) {
+        uint8_t c = (i < len) ? bases[off + i] : (uint8_t)'N';
+        if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+        bases[off + i] = c;
+    }
+}
+
+extern "C" int cbcg_set_reference(cbcg_ctx *ctx, uint32_t n_chr, const char *const *names,
+                                  const uint8_t *const *bases, const uint64_t *len) {
+    if (!ctx || !n_chr || !bases || !len || n_chr > MAX_CHR) return fail(ctx, CBCG_ERR_ARG, "cbcg_set_reference: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->names.clear(); ctx->h_off.clear(); ctx->h_len.clear();
+    uint64_t total = 0;
+    for (uint32_t c = 0; c < n_chr; c++) {
+        if (!bases[c]) return fail(ctx, CBCG_ERR_ARG, "cbcg_set_reference: NULL record %u", c);
+        char tmp[32];
+        const char *nm = (names && names[c]) ? names[c] : (snprintf(tmp, sizeof tmp, "chr%u", c + 1), tmp);
+        if (strlen(nm) >= MAX_NAME) return fail(ctx, CBCG_ERR_ARG, "chromosome name too long");
+        ctx->names.push_back(nm);
+        ctx->h_off.push_back(total);
+        ctx->h_len.push_back(len[c]);
+        total += (len[c] + REF_PAD + 255u) & ~255ull;
+    }
+    TRY(ensure(ctx, ctx->g_bases, total + 256));
+    TRY(ensure(ctx, ctx->g_off, n_chr * 8));
+    TRY(ensure(ctx, ctx->g_len, n_chr * 8));
+    TRY(ensure(ctx, ctx->g_names, (size_t)n_chr * MAX_NAME));
+    std::vector<uint8_t> nm((size_t)n_chr * MAX_NAME, 0);
+    for (uint32_t c = 0; c < n_chr; c++) memcpy(&nm[(size_t)c * MAX_NAME], ctx->names[c].c_str(), ctx->names[c].size());
+    CU(cudaMemcpyAsync(ctx->g_off.p, ctx->h_off.data(), n_chr * 8, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->g_len.p, ctx->h_len.data(), n_chr * 8, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->g_names.p, nm.data(), nm.size(), cudaMemcpyHostToDevice, ctx->st));
+    for (uint32_t c = 0; c < n_chr; c++) {
+        if (len[c]) CU(cudaMemcpyAsync(ctx->g_bases.as<uint8_t>() + ctx->h_off[c], bases[c], len[c], cudaMemcpyHostToDevice, ctx->st));
+        const uint64_t span = (len[c] + REF_PAD + 255u) & ~255ull;
+        genome_prepare_kernel<<<(unsigned)std::min<uint64_t>(148u * 8u, (span + 255u) / 256u), 256, 0, ctx->st>>>(
+            ctx->g_bases.as<uint8_t>(), ctx->h_off[c], len[c], span);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->dg.n_chr = n_chr;
+    ctx->dg.bases = ctx->g_bases.as<uint8_t>();
+    ctx->dg.chr_off = ctx->g_off.as<uint64_t>();
+    ctx->dg.chr_len = ctx->g_len.as<uint64_t>();
+    return CBCG_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ batch */
+static int check_batch(cbcg_ctx *ctx, const cbcg_batch *b) {
+    if (!b) return fail(ctx, CBCG_ERR_ARG, "NULL batch");
+    if (b->n_reads == 0) return 0;
+    if (!b->pos || !b->flag || !b->seq_len || !b->chr || !b->seq_off || !b->seq || !b->cigar_off || !b->cigar || !b->md_off || !b->md)
+        return fail(ctx, CBCG_ERR_ARG, "batch has NULL arrays");
+    if (b->n_reads >= 0xfffffff0ull) return fail(ctx, CBCG_ERR_ARG, "more than 2^32 reads in one shard");
+    return 0;
+}
+
+extern "C" int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *b) {
+    if (!ctx) return CBCG_ERR_ARG;
+    TRY(check_batch(ctx, b));
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = b->n_reads;
+    ctx->have_batch = false; ctx->have_encoded = false;
+    ctx->runs.clear();
+    ctx->stats = cbcg_stats();
+    CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    uint64_t h2d = 0;
+    uint32_t max_len = 0; uint64_t bases = 0;
+    if (n) {
+        const uint64_t seq_b = b->seq_off[n], cig_b = b->cigar_off[n], md_b = b->md_off[n];
+        TRY(ensure(ctx, ctx->b_pos, n * 4));  TRY(ensure(ctx, ctx->b_flag, n * 2)); TRY(ensure(ctx, ctx->b_len, n * 2));
+        TRY(ensure(ctx, ctx->b_chr, n * 4));
+        TRY(ensure(ctx, ctx->b_soff, (n + 1) * 8)); TRY(ensure(ctx, ctx->b_coff, (n + 1) * 8)); TRY(ensure(ctx, ctx->b_moff, (n + 1) * 8));
+        TRY(ensure(ctx, ctx->b_seq, seq_b + POOL_PAD)); TRY(ensure(ctx, ctx->b_cigar, cig_b + POOL_PAD)); TRY(ensure(ctx, ctx->b_md, md_b + POOL_PAD));
+        struct { void *d; const void *h; uint64_t bytes; } cp[] = {
+            { ctx->b_pos.p, b->pos, n * 4 }, { ctx->b_flag.p, b->flag, n * 2 }, { ctx->b_len.p, b->seq_len, n * 2 },
+            { ctx->b_chr.p, b->chr, n * 4 }, { ctx->b_soff.p, b->seq_off, (n + 1) * 8 }, { ctx->b_coff.p, b->cigar_off, (n + 1) * 8 },
+            { ctx->b_moff.p, b->md_off, (n + 1) * 8 }, { ctx->b_seq.p, b->seq, seq_b }, { ctx->b_cigar.p, b->cigar, cig_b },
+            { ctx->b_md.p, b->md, md_b } };
+        for (auto &c : cp) { if (c.bytes) CU(cudaMemcpyAsync(c.d, c.h, c.bytes, cudaMemcpyHostToDevice, ctx->st)); h2d += c.bytes; }
+        /* host scan while the copies fly: chromosome runs (blocks never span chromosomes), longest read */
+        ChrRun run = { 0, 0, b->chr[0] };
+        for (uint64_t r = 0; r < n; r++) {
+            const uint32_t l = b->seq_len[r];
+            if (l > max_len) max_len = l;
+            bases += l;
+            if (b->chr[r] != run.chr) { ctx->runs.push_back(run); run.first = r; run.n = 0; run.chr = b->chr[r]; }
+            run.n++;
+        }
+        ctx->runs.push_back(run);
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->db.n_reads = n;
+    ctx->db.pos = ctx->b_pos.as<uint32_t>(); ctx->db.flag = ctx->b_flag.as<uint16_t>(); ctx->db.seq_len = ctx->b_len.as<uint16_t>();
+    ctx->db.chr = ctx->b_chr.as<uint32_t>();
+    ctx->db.seq_off = ctx->b_soff.as<uint64_t>(); ctx->db.seq = ctx->b_seq.as<uint8_t>();
+    ctx->db.cigar_off = ctx->b_coff.as<uint64_t>(); ctx->db.cigar = ctx->b_cigar.as<uint8_t>();
+    ctx->db.md_off = ctx->b_moff.as<uint64_t>(); ctx->db.md = ctx->b_md.as<uint8_t>();
+    ctx->db.max_len = max_len;
+    ctx->total_bases = bases;
+    ctx->have_batch = true;
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_h2d = ms; ctx->stats.h2d_bytes = h2d; ctx->stats.n_reads = n;
+    return CBCG_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ K1 */
+static int reset_words(cbcg_ctx *ctx) {
+    CU(cudaMemsetAsync(ctx->words.p, 0, sizeof(Words), ctx->st));
+    return 0;
+}
+static int fetch_words(cbcg_ctx *ctx) {
+    CU(cudaMemcpyAsync(ctx->hw, ctx->words.p, sizeof(Words), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+/* Runs K1 on the resident batch; on return ctx->hw->total_edits is valid. */
+static int run_extract(cbcg_ctx *ctx) {
+    const uint64_t n = ctx->db.n_reads;
+    if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
+    TRY(ensure(ctx, ctx->recs, (n + 1) * sizeof(cbcg_read_rec)));
+    TRY(ensure(ctx, ctx->tile_desc, (extract_num_tiles(n) + 1) * 8));
+    uint64_t cap = ctx->edits.cap / 2;
+    const uint64_t guess = ctx->total_bases / 16 + 4096;          /* ~6 % of bases edited; grown on demand */
+    if (cap < guess) { TRY(ensure(ctx, ctx->edits, guess * 2)); cap = ctx->edits.cap / 2; }
+    for (int attempt = 0; attempt < 2; attempt++) {
+        TRY(reset_words(ctx));
+        if (launch_extract(ctx->db, ctx->dg, ctx->recs.as<cbcg_read_rec>(), ctx->edits.as<uint16_t>(), cap,
+                           ctx->tile_desc.as<uint64_t>(), wptr<uint32_t>(ctx, W_OFF(ticket)), wptr<uint64_t>(ctx, W_OFF(total_edits)),
+                           wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st))
+            return fail(ctx, CBCG_ERR_CUDA, "K1 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx->stats.kernel_launches++;
+        TRY(fetch_words(ctx));
+        const unsigned long long v = ctx->hw->err;
+        if (v && -(int)(v >> 40) == CBCG_ERR_CAPACITY && attempt == 0) {   /* edit array too small: the count is exact */
+            TRY(ensure(ctx, ctx->edits, (ctx->hw->total_edits + 64) * 2));
+            cap = ctx->edits.cap / 2;
+            continue;
+        }
+        return device_error(ctx, "edit extraction");
+    }
+    return fail(ctx, CBCG_ERR_INTERNAL, "edit extraction: capacity retry failed");
+}
+
+extern "C" int cbcg_extract(cbcg_ctx *ctx, const cbcg_batch *batch, cbcg_read_rec *recs,
+                            uint16_t *edits, uint64_t edits_cap, uint64_t *n_edits) {
+    if (!ctx || !recs || (!edits && edits_cap) || !n_edits) return fail(ctx, CBCG_ERR_ARG, "cbcg_extract: bad argument");
+    TRY(cbcg_batch_upload(ctx, batch));
+    *n_edits = 0;
+    if (!ctx->db.n_reads) return CBCG_OK;
+    TRY(run_extract(ctx));
+    const uint64_t ne = ctx->hw->total_edits;
+    *n_edits = ne;
+    if (ne > edits_cap) return fail(ctx, CBCG_ERR_CAPACITY, "cbcg_extract: %llu edit entries, room for %llu", (unsigned long long)ne, (unsigned long long)edits_cap);
+    CU(cudaMemcpyAsync(recs, ctx->recs.p, ctx->db.n_reads * sizeof(cbcg_read_rec), cudaMemcpyDeviceToHost, ctx->st));
+    if (ne) CU(cudaMemcpyAsync(edits, ctx->edits.p, ne * 2, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->stats.n_edits = ne;
+    return CBCG_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ blocks */
+static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint64_t *n_blocks_out) {
+    const uint64_t n = ctx->db.n_reads;
+    uint64_t nb = 0;
+    if (block_reads == 0) nb = 1;
+    else for (const ChrRun &r : ctx->runs) nb += (r.n + block_reads - 1) / block_reads;
+    if (nb >= 0xffffffffull) return fail(ctx, CBCG_ERR_ARG, "too many blocks");
+    TRY(ensure_hblocks(ctx, nb + 1));
+    BlockDesc *hb = ctx->hblocks;
+    memset(hb, 0, nb * sizeof(BlockDesc));
+    if (block_reads == 0) { hb[0].first_read = 0; hb[0].n_reads = (uint32_t)n; hb[0].chr = ctx->runs.empty() ? 0 : ctx->runs[0].chr; }
+    else {
+        uint64_t k = 0;
+        for (const ChrRun &r : ctx->runs)
+            for (uint64_t o = 0; o < r.n; o += block_reads, k++) {
+                hb[k].first_read = (uint32_t)(r.first + o);
+                hb[k].n_reads = (uint32_t)std::min<uint64_t>(block_reads, r.n - o);
+                hb[k].chr = r.chr;
+            }
+    }
+    TRY(ensure(ctx, ctx->blocks, (nb + 1) * sizeof(BlockDesc)));
+    CU(cudaMemcpyAsync(ctx->blocks.p, hb, nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
+    *n_blocks_out = nb;
+    return 0;
+}
+
+static CoderParams coder_params(cbcg_ctx *ctx, uint32_t n_blocks, uint32_t L, int legacy, int mode) {
+    CoderParams p;
+    memset(&p, 0, sizeof p);
+    p.n_blocks = n_blocks; p.L = L; p.legacy = legacy ? 1u : 0u; p.mode = (uint32_t)mode;
+    p.blocks = ctx->blocks.as<BlockDesc>();
+    p.recs = ctx->recs.as<cbcg_read_rec>();
+    p.edits = ctx->edits.as<uint16_t>();
+    p.genome = ctx->dg;
+    p.ws = ctx->ws.as<uint8_t>();
+    p.chr_names = ctx->g_names.as<uint8_t>();
+    p.err = wptr<unsigned long long>(ctx, W_OFF(err));
+    return p;
+}
+
+static void put32(std::vector<uint8_t> &v, uint32_t x) { for (int i = 0; i < 4; i++) v.push_back((uint8_t)(x >> (8 * i))); }
+static void put64(std::vector<uint8_t> &v, uint64_t x) { for (int i = 0; i < 8; i++) v.push_back((uint8_t)(x >> (8 * i))); }
+
+static int validate_opts(cbcg_ctx *ctx, const cbcg_encode_opts *o) {
+    if (!o) return fail(ctx, CBCG_ERR_ARG, "NULL options");
+    if (o->read_len_header == 0 || o->read_len_header > CBCG_MAX_READ_LEN) return fail(ctx, CBCG_ERR_ARG, "read_len_header must be in 1..%u", CBCG_MAX_READ_LEN);
+    if (o->gen_mode != 0) return fail(ctx, CBCG_ERR_ARG, "gen_mode %u is not supported by this build", o->gen_mode);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ encode */
+extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts) {
+    if (!ctx) return CBCG_ERR_ARG;
+    TRY(validate_opts(ctx, opts));
+    if (!ctx->have_batch) return fail(ctx, CBCG_ERR_ARG, "no resident batch: call cbcg_batch_upload first");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->db.n_reads;
+    const int legacy = opts->block_reads == 0;
+    const uint32_t L = opts->read_len_header;
+    ctx->have_encoded = false;
+    cbcg_stats &S = ctx->stats;
+    S.ms_extract = S.ms_plan = S.ms_code = S.ms_gather = S.ms_reconstruct = S.ms_d2h = S.ms_total = 0;
+    S.kernel_launches = 0; S.d2h_bytes = 0;
+    if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    uint64_t n_edits = 0, nb = 0;
+    if (n) { TRY(run_extract(ctx)); n_edits = ctx->hw->total_edits; }
+    CU(cudaEventRecord(ctx->ev[1], ctx->st));
+    uint64_t payload_total = 0;
+    if (n || legacy) {
+        if (!n) {                                          /* legacy stream of an empty input: header + end marker */
+            TRY(ensure(ctx, ctx->recs, sizeof(cbcg_read_rec))); TRY(ensure(ctx, ctx->edits, 64));
+            CU(cudaMemsetAsync(ctx->recs.p, 0, sizeof(cbcg_read_rec), ctx->st));
+            TRY(reset_words(ctx));
+        }
+        TRY(cut_blocks(ctx, opts->block_reads, &nb));
+        const uint64_t ws_cap = coder_ws_bytes_bound(L, n, n_edits, nb, legacy);
+        const uint64_t pay_cap = coder_payload_bound(n, n_edits, nb, legacy);
+        TRY(ensure(ctx, ctx->ws, ws_cap));
+        TRY(ensure(ctx, ctx->scratch, pay_cap));
+        TRY(ensure(ctx, ctx->out_off, (nb + 1) * 8));
+        CoderParams p = coder_params(ctx, (uint32_t)nb, L, legacy, 0);
+        p.chr = const_cast<uint32_t *>(ctx->db.chr);
+        p.payload = ctx->scratch.as<uint8_t>();
+        if (launch_plan(p, (uint32_t)n, n_edits, ws_cap, pay_cap, wptr<uint64_t>(ctx, W_OFF(totals)), ctx->st))
+            return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
+        CU(cudaEventRecord(ctx->ev[2], ctx->st));
+        if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        CU(cudaEventRecord(ctx->ev[3], ctx->st));
+        /* compact payload: bounded by the scratch size */
+        TRY(ensure(ctx, ctx->payload, pay_cap));
+        if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->st))
+            return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
+        S.kernel_launches += 4;
+        CU(cudaEventRecord(ctx->ev[4], ctx->st));
+        CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(&ctx->hw->total_bytes, ctx->out_off.as<uint64_t>() + nb, 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(&ctx->hw->err, wptr<unsigned long long>(ctx, W_OFF(err)), 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        TRY(device_error(ctx, "block coder"));
+        payload_total = ctx->hw->total_bytes;
+        S.d2h_bytes += nb * sizeof(BlockDesc) + 16;
+    } else {
+        CU(cudaEventRecord(ctx->ev[2], ctx->st)); CU(cudaEventRecord(ctx->ev[3], ctx->st)); CU(cudaEventRecord(ctx->ev[4], ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+    }
+    cudaEventElapsedTime(&S.ms_extract, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&S.ms_plan, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&S.ms_code, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&S.ms_gather, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&S.ms_total, ctx->ev[0], ctx->ev[4]);
+
+    /* container header + index (layout: DESIGN.md, "Container") */
+    std::vector<uint8_t> &h = ctx->enc_head;
+    h.clear();
+    uint64_t n_syms = 0;
+    for (uint64_t k = 0; k < nb; k++) n_syms += ctx->hblocks[k].n_symbols;
+    if (!legacy) {
+        put32(h, CBCG_MAGIC); put32(h, CBCG_VERSION); put32(h, ctx->db.max_len); put32(h, L);
+        put64(h, n); put32(h, (uint32_t)nb); put32(h, ctx->dg.n_chr); put32(h, opts->block_reads); put32(h, opts->gen_mode);
+        for (uint32_t c = 0; c < ctx->dg.n_chr; c++) {
+            const std::string &s = ctx->names[c];
+            put32(h, (uint32_t)s.size());
+            h.insert(h.end(), s.begin(), s.end());
+            for (size_t q = s.size(); q & 3; q++) h.push_back(0);
+        }
+        for (uint64_t k = 0; k < nb; k++) {
+            const BlockDesc &b = ctx->hblocks[k];
+            put32(h, b.n_reads); put32(h, b.chr); put32(h, b.base_pos); put32(h, b.n_symbols);
+            put32(h, b.n_edits); put32(h, b.payload_bytes); put32(h, b.gen); put32(h, 0);
+        }
+    }
+    ctx->enc_L = L; ctx->enc_block_reads = opts->block_reads; ctx->enc_gen_mode = opts->gen_mode; ctx->enc_legacy = legacy;
+    ctx->enc_max_len = ctx->db.max_len;
+    ctx->enc_n_reads = n; ctx->enc_n_edits = n_edits; ctx->enc_n_blocks = nb; ctx->enc_payload_bytes = payload_total;
+    ctx->have_encoded = true;
+    S.n_reads = n; S.n_blocks = nb; S.n_edits = n_edits; S.n_symbols = n_syms;
+    S.payload_bytes = payload_total; S.container_bytes = h.size() + payload_total;
+    return CBCG_OK;
+}
+
+extern "C" int cbcg_fetch_container(cbcg_ctx *ctx, uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+    if (!ctx || !out_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_fetch_container: bad argument");
+    if (!ctx->have_encoded) return fail(ctx, CBCG_ERR_ARG, "nothing encoded yet");
+    const uint64_t total = ctx->enc_head.size() + ctx->enc_payload_bytes;
+    *out_len = total;
+    if (total > out_cap || (!out && total)) return fail(ctx, CBCG_ERR_CAPACITY, "container is %llu bytes, room for %llu", (unsigned long long)total, (unsigned long long)out_cap);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev[5], ctx->st));
+    if (ctx->enc_payload_bytes)
+        CU(cudaMemcpyAsync(out + ctx->enc_head.size(), ctx->payload.p, ctx->enc_payload_bytes, cudaMemcpyDeviceToHost, ctx->st));
+    if (!ctx->enc_head.empty()) memcpy(out, ctx->enc_head.data(), ctx->enc_head.size());
+    CU(cudaEventRecord(ctx->ev[6], ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaEventElapsedTime(&ctx->stats.ms_d2h, ctx->ev[5], ctx->ev[6]);
+    ctx->stats.d2h_bytes += ctx->enc_payload_bytes;
+    return CBCG_OK;
+}
+
+extern "C" uint64_t cbcg_encode_bound(const cbcg_batch *b, const cbcg_encode_opts *o) {
+    if (!b || !o) return 0;
+    /* Practical bound: one byte per base plus 16 per read is four times the 2-bit packing of the
+       reads. A larger output makes cbcg_encode return CBCG_ERR_CAPACITY with the exact size in *out_len;
+       cbcg_fetch_container then retrieves it without re-encoding. */
+    const uint64_t n = b->n_reads;
+    const uint64_t bases = n ? b->seq_off[n] - b->seq_off[0] : 0;
+    const uint64_t nb = o->block_reads ? (n / o->block_reads + MAX_CHR + 2) : 1;
+    return 4096 + (uint64_t)MAX_CHR * 16 + nb * 32 + n * 16 + bases;
+}
+
+extern "C" int cbcg_encode(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_encode_opts *opts,
+                           uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+    if (!ctx || !out_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_encode: bad argument");
+    TRY(validate_opts(ctx, opts));
+    TRY(cbcg_batch_upload(ctx, batch));
+    const float ms_h2d = ctx->stats.ms_h2d; const uint64_t h2d = ctx->stats.h2d_bytes;
+    TRY(cbcg_encode_resident(ctx, opts));
+    ctx->stats.ms_h2d = ms_h2d; ctx->stats.h2d_bytes = h2d;
+    return cbcg_fetch_container(ctx, out, out_cap, out_len);
+}
+
+/* ------------------------------------------------------------------------------------------------ symbol lists */
+extern "C" int cbcg_extract_symbols(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_encode_opts *opts,
+                                    cbcg_symbol *symbols, uint64_t symbols_cap, uint64_t *n_symbols,
+                                    uint64_t *block_sym_count, uint64_t blocks_cap, uint64_t *n_blocks) {
+    if (!ctx || !n_symbols || (!symbols && symbols_cap)) return fail(ctx, CBCG_ERR_ARG, "cbcg_extract_symbols: bad argument");
+    TRY(validate_opts(ctx, opts));
+    TRY(cbcg_batch_upload(ctx, batch));
+    const uint64_t n = ctx->db.n_reads;
+    const int legacy = opts->block_reads == 0;
+    *n_symbols = 0; if (n_blocks) *n_blocks = 0;
+    uint64_t n_edits = 0, nb = 0;
+    if (n) { TRY(run_extract(ctx)); n_edits = ctx->hw->total_edits; }
+    else if (!legacy) return CBCG_OK;
+    else {
+        TRY(ensure(ctx, ctx->recs, sizeof(cbcg_read_rec))); TRY(ensure(ctx, ctx->edits, 64));
+        CU(cudaMemsetAsync(ctx->recs.p, 0, sizeof(cbcg_read_rec), ctx->st));
+        TRY(reset_words(ctx));
+    }
+    TRY(cut_blocks(ctx, opts->block_reads, &nb));
+    const uint64_t list_cap = 12u * n + 2u * n_edits + nb * 8u + (legacy ? 136u + 2048u : 0u) + 64u;
+    TRY(ensure(ctx, ctx->symbols, list_cap * sizeof(cbcg_symbol)));
+    TRY(ensure(ctx, ctx->ws, 4096));
+    CoderParams p = coder_params(ctx, (uint32_t)nb, opts->read_len_header, legacy, 2);
+    p.chr = const_cast<uint32_t *>(ctx->db.chr);
+    p.symbols = ctx->symbols.as<cbcg_symbol>();
+    if (launch_plan(p, (uint32_t)n, n_edits, ~0ull, ~0ull, wptr<uint64_t>(ctx, W_OFF(totals)), ctx->st))
+        return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
+    if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 (list) launch failed");
+    CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
+    TRY(fetch_words(ctx));
+    TRY(device_error(ctx, "symbol emission"));
+    if (ctx->hw->totals[2] > list_cap) return fail(ctx, CBCG_ERR_INTERNAL, "symbol list bound exceeded");
+    uint64_t total = 0;
+    for (uint64_t k = 0; k < nb; k++) total += ctx->hblocks[k].n_symbols;
+    *n_symbols = total;
+    if (n_blocks) *n_blocks = nb;
+    if (total > symbols_cap) return fail(ctx, CBCG_ERR_CAPACITY, "%llu symbols, room for %llu", (unsigned long long)total, (unsigned long long)symbols_cap);
+    if (block_sym_count && nb > blocks_cap) return fail(ctx, CBCG_ERR_CAPACITY, "%llu blocks, room for %llu", (unsigned long long)nb, (unsigned long long)blocks_cap);
+    uint64_t o = 0;
+    for (uint64_t k = 0; k < nb; k++) {
+        const BlockDesc &b = ctx->hblocks[k];
+        if (b.n_symbols)
+            CU(cudaMemcpyAsync(symbols + o, ctx->symbols.as<cbcg_symbol>() + b.sym_off, (size_t)b.n_symbols * sizeof(cbcg_symbol), cudaMemcpyDeviceToHost, ctx->st));
+        if (block_sym_count) block_sym_count[k] = b.n_symbols;
+        o += b.n_symbols;
+    }
+    CU(cudaStreamSynchronize(ctx->st));
+    return CBCG_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ decode */
+struct Container {
+    uint32_t max_len, L, n_blocks, n_chr, block_reads, gen_mode;
+    uint64_t n_reads;
+    uint64_t index_off, payload_off;
+    std::vector<uint32_t> chr_map;             /* container ordinal -> genome ordinal */
+};
+static uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint64_t rd64(const uint8_t *p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+/* names == NULL: structure only */
+static int parse_container(const uint8_t *in, uint64_t len, const std::vector<std::string> *names, Container &c) {
+    if (!in || len < 40) return CBCG_ERR_FORMAT;
+    if (rd32(in) != CBCG_MAGIC || rd32(in + 4) != CBCG_VERSION) return CBCG_ERR_FORMAT;
+    c.max_len = rd32(in + 8); c.L = rd32(in + 12); c.n_reads = rd64(in + 16);
+    c.n_blocks = rd32(in + 24); c.n_chr = rd32(in + 28); c.block_reads = rd32(in + 32); c.gen_mode = rd32(in + 36);
+    if (c.L == 0 || c.L > CBCG_MAX_READ_LEN || c.max_len > CBCG_MAX_READ_LEN || c.n_chr > MAX_CHR || c.gen_mode != 0) return CBCG_ERR_FORMAT;
+    if (c.n_reads >= 0xfffffff0ull) return CBCG_ERR_FORMAT;
+    uint64_t o = 40;
+    c.chr_map.assign(c.n_chr, 0xffffffffu);
+    for (uint32_t k = 0; k < c.n_chr; k++) {
+        if (o + 4 > len) return CBCG_ERR_FORMAT;
+        const uint32_t nl = rd32(in + o); o += 4;
+        if (nl >= MAX_NAME || o + nl > len) return CBCG_ERR_FORMAT;
+        if (names)
+            for (size_t g = 0; g < names->size(); g++)
+                if ((*names)[g].size() == nl && !memcmp((*names)[g].data(), in + o, nl)) c.chr_map[k] = (uint32_t)g;
+        o += nl + ((4 - (nl & 3)) & 3);
+    }
+    c.index_off = o;
+    if (o + (uint64_t)c.n_blocks * 32 > len) return CBCG_ERR_FORMAT;
+    c.payload_off = o + (uint64_t)c.n_blocks * 32;
+    return 0;
+}
+
+extern "C" int cbcg_decoded_size(const uint8_t *in, uint64_t in_len, uint64_t *n_reads, uint64_t *max_seq_bytes) {
+    Container c;
+    if (n_reads) *n_reads = 0;
+    if (max_seq_bytes) *max_seq_bytes = 0;
+    const int rc = parse_container(in, in_len, nullptr, c);
+    if (rc) return rc;
+    if (n_reads) *n_reads = c.n_reads;
+    if (max_seq_bytes) *max_seq_bytes = c.n_reads * ((uint64_t)c.max_len + 1u);
+    return CBCG_OK;
+}
+
+/* K2 decode of ctx->hblocks[0..nb) (n_reads, chr, base_pos, n_edits, payload_bytes filled in) whose payload
+ * bytes lie back to back in ctx->payload. Leaves recs / edits / chr_out on the device. */
+static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy, uint64_t reads_cap, uint64_t edits_cap,
+                             uint64_t *n_reads_out, uint64_t *n_edits_out) {
+    TRY(ensure(ctx, ctx->blocks, (nb + 1) * sizeof(BlockDesc)));
+    CU(cudaMemcpyAsync(ctx->blocks.p, ctx->hblocks, nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
+    TRY(ensure(ctx, ctx->recs, (reads_cap + 1) * sizeof(cbcg_read_rec)));
+    TRY(ensure(ctx, ctx->chr_out, (reads_cap + 1) * 4));
+    TRY(ensure(ctx, ctx->edits, (edits_cap + 64) * 2));
+    const uint64_t ws_cap = legacy ? coder_ws_bytes_bound(L ? L : CBCG_MAX_READ_LEN, reads_cap, 0xffffffffull, 1, 1)
+                                   : coder_ws_bytes_bound(L, reads_cap, edits_cap, nb, 0);
+    TRY(ensure(ctx, ctx->ws, ws_cap));
+    TRY(reset_words(ctx));
+    CoderParams p = coder_params(ctx, (uint32_t)nb, L, legacy, 1);
+    p.chr = ctx->chr_out.as<uint32_t>();
+    p.payload = ctx->payload.as<uint8_t>();
+    if (launch_plan(p, (uint32_t)reads_cap, edits_cap, ws_cap, ~0ull, wptr<uint64_t>(ctx, W_OFF(totals)), ctx->st))
+        return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
+    if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 (decode) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->stats.kernel_launches += 2;
+    CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
+    TRY(fetch_words(ctx));
+    TRY(device_error(ctx, "block decoder"));
+    uint64_t nr = 0, ne = 0;
+    for (uint64_t k = 0; k < nb; k++) { nr += ctx->hblocks[k].n_reads; ne += ctx->hblocks[k].n_edits; }
+    *n_reads_out = nr; *n_edits_out = ne;
+    return 0;
+}
+
+static int run_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, uint32_t max_len, const uint32_t *chr_dev) {
+    const uint64_t out_cap = n_reads * ((uint64_t)max_len + 1u);
+    TRY(ensure(ctx, ctx->seq_out, out_cap + 64));
+    TRY(ensure(ctx, ctx->tile_desc, (reconstruct_num_tiles(n_reads) + 1) * 8));
+    CU(cudaMemsetAsync(wptr<unsigned long long>(ctx, W_OFF(err)), 0, 8, ctx->st));
+    if (launch_reconstruct(n_reads, ctx->recs.as<cbcg_read_rec>(), chr_dev, ctx->edits.as<uint16_t>(), ctx->dg,
+                           ctx->seq_out.as<uint8_t>(), out_cap, max_len, ctx->tile_desc.as<uint64_t>(),
+                           wptr<uint32_t>(ctx, W_OFF(ticket)), wptr<uint64_t>(ctx, W_OFF(total_bytes)),
+                           wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st))
+        return fail(ctx, CBCG_ERR_CUDA, "K3 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->stats.kernel_launches++;
+    return 0;
+}
+
+/* index entries of a parsed container -> ctx->hblocks */
+static int blocks_from_index(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, const Container &c,
+                             uint64_t *reads_total, uint64_t *edits_total, uint64_t *payload_total) {
+    TRY(ensure_hblocks(ctx, (size_t)c.n_blocks + 1));
+    uint64_t nr = 0, ne = 0, pb = 0;
+    for (uint32_t k = 0; k < c.n_blocks; k++) {
+        const uint8_t *e = in + c.index_off + (uint64_t)k * 32;
+        BlockDesc &b = ctx->hblocks[k];
+        memset(&b, 0, sizeof b);
+        b.n_reads = rd32(e); const uint32_t chr = rd32(e + 4); b.base_pos = rd32(e + 8); b.n_symbols = rd32(e + 12);
+        b.n_edits = rd32(e + 16); b.payload_bytes = rd32(e + 20); b.gen = rd32(e + 24);
+        if (chr >= c.n_chr) return fail(ctx, CBCG_ERR_FORMAT, "block %u names chromosome %u of %u", k, chr, c.n_chr);
+        if (c.chr_map[chr] == 0xffffffffu) return fail(ctx, CBCG_ERR_NO_REFERENCE, "block %u: chromosome not in the loaded reference", k);
+        if (b.gen != 0) return fail(ctx, CBCG_ERR_FORMAT, "block %u: unsupported generation %u", k, b.gen);
+        b.chr = c.chr_map[chr];
+        nr += b.n_reads; ne += b.n_edits; pb += b.payload_bytes;
+    }
+    if (nr != c.n_reads) return fail(ctx, CBCG_ERR_FORMAT, "index holds %llu reads, header says %llu", (unsigned long long)nr, (unsigned long long)c.n_reads);
+    if (c.payload_off + pb > in_len) return fail(ctx, CBCG_ERR_FORMAT, "payload truncated");
+    *reads_total = nr; *edits_total = ne; *payload_total = pb;
+    return 0;
+}
+
+/* Shared by cbcg_decode / cbcg_decode_edits: container (or legacy stream) -> recs/edits/chr on the device. */
+static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy,
+                             uint64_t *n_reads, uint64_t *n_edits, uint32_t *max_len) {
+    if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_decoded = false;
+    cbcg_stats &S = ctx->stats;
+    S = cbcg_stats();
+    CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    if (!legacy) {
+        Container c;
+        int rc = parse_container(in, in_len, &ctx->names, c);
+        if (rc) return fail(ctx, rc, "malformed container header");
+        uint64_t nr = 0, ne = 0, pb = 0;
+        TRY(blocks_from_index(ctx, in, in_len, c, &nr, &ne, &pb));
+        *max_len = c.max_len ? c.max_len : 1;
+        *n_reads = 0; *n_edits = 0;
+        if (c.n_blocks == 0) return 0;
+        TRY(ensure(ctx, ctx->payload, pb + 64));
+        if (pb) CU(cudaMemcpyAsync(ctx->payload.p, in + c.payload_off, pb, cudaMemcpyHostToDevice, ctx->st));
+        S.h2d_bytes = pb + (uint64_t)c.n_blocks * sizeof(BlockDesc);
+        CU(cudaEventRecord(ctx->ev[1], ctx->st));
+        TRY(run_decode_blocks(ctx, c.n_blocks, c.L, 0, nr, ne, n_reads, n_edits));
+        S.n_blocks = c.n_blocks;
+    } else {
+        if (!in || in_len < 4) return fail(ctx, CBCG_ERR_FORMAT, "legacy stream too short");
+        if (in_len > 0xfffffff0ull) return fail(ctx, CBCG_ERR_ARG, "legacy stream too large");
+        TRY(ensure(ctx, ctx->payload, in_len + 64));
+        CU(cudaMemcpyAsync(ctx->payload.p, in, in_len, cudaMemcpyHostToDevice, ctx->st));
+        S.h2d_bytes = in_len;
+        CU(cudaEventRecord(ctx->ev[1], ctx->st));
+        /* the read count is not in the stream: decode into a guessed capacity, double on overflow */
+        uint64_t reads_cap = std::max<uint64_t>(in_len * 2, 1u << 16);
+        for (;;) {
+            TRY(ensure_hblocks(ctx, 2));
+            BlockDesc &b = ctx->hblocks[0];
+            memset(&b, 0, sizeof b);
+            b.n_reads = (uint32_t)std::min<uint64_t>(reads_cap, 0xfffffff0ull);
+            b.n_edits = (uint32_t)std::min<uint64_t>(reads_cap * 4, 0xfffffff0ull);
+            b.payload_bytes = (uint32_t)in_len;
+            int rc = run_decode_blocks(ctx, 1, 0, 1, b.n_reads, b.n_edits, n_reads, n_edits);
+            if (rc == CBCG_ERR_CAPACITY && reads_cap < (1ull << 31)) { reads_cap *= 4; continue; }
+            if (rc) return rc;
+            break;
+        }
+        *max_len = ctx->hblocks[0].gen;                     /* header read length (src/sam_file_allocation.c:365) */
+        S.n_blocks = 1;
+    }
+    CU(cudaEventRecord(ctx->ev[2], ctx->st));
+    S.n_reads = *n_reads; S.n_edits = *n_edits;
+    return 0;
+}
+
+extern "C" int cbcg_decode(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy,
+                           uint8_t *seq_out, uint64_t seq_cap, uint64_t *seq_len, uint64_t *n_reads) {
+    if (!ctx || !seq_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_decode: bad argument");
+    uint64_t nr = 0, ne = 0; uint32_t max_len = 1;
+    *seq_len = 0; if (n_reads) *n_reads = 0;
+    TRY(decode_to_records(ctx, in, in_len, legacy, &nr, &ne, &max_len));
+    if (n_reads) *n_reads = nr;
+    if (!nr) return CBCG_OK;
+    if (legacy) max_len = CBCG_MAX_READ_LEN;                /* per-read lengths are coded mod 256 (src/read_compression.c:29-33) */
+    TRY(run_reconstruct(ctx, nr, max_len, ctx->chr_out.as<uint32_t>()));
+    CU(cudaEventRecord(ctx->ev[3], ctx->st));
+    TRY(fetch_words(ctx));
+    TRY(device_error(ctx, "read reconstruction"));
+    const uint64_t bytes = ctx->hw->total_bytes;
+    *seq_len = bytes;
+    ctx->dec_bytes = bytes; ctx->dec_n_reads = nr; ctx->have_decoded = true;
+    cbcg_stats &S = ctx->stats;
+    cudaEventElapsedTime(&S.ms_h2d, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&S.ms_code, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&S.ms_reconstruct, ctx->ev[2], ctx->ev[3]);
+    if (bytes > seq_cap || !seq_out) return fail(ctx, CBCG_ERR_CAPACITY, "decoded text is %llu bytes, room for %llu", (unsigned long long)bytes, (unsigned long long)seq_cap);
+    CU(cudaEventRecord(ctx->ev[4], ctx->st));
+    CU(cudaMemcpyAsync(seq_out, ctx->seq_out.p, bytes, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaEventRecord(ctx->ev[5], ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    cudaEventElapsedTime(&S.ms_d2h, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&S.ms_total, ctx->ev[0], ctx->ev[5]);
+    S.d2h_bytes = bytes;
+    return CBCG_OK;
+}
+
+extern "C" int cbcg_decode_edits(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy,
+                                 cbcg_read_rec *recs, uint64_t recs_cap, uint32_t *chr, uint16_t *edits,
+                                 uint64_t edits_cap, uint64_t *n_reads, uint64_t *n_edits) {
+    if (!ctx || !n_reads || !n_edits) return fail(ctx, CBCG_ERR_ARG, "cbcg_decode_edits: bad argument");
+    uint64_t nr = 0, ne = 0; uint32_t max_len = 1;
+    *n_reads = 0; *n_edits = 0;
+    TRY(decode_to_records(ctx, in, in_len, legacy, &nr, &ne, &max_len));
+    *n_reads = nr; *n_edits = ne;
+    if (nr > recs_cap || ne > edits_cap) return fail(ctx, CBCG_ERR_CAPACITY, "%llu reads / %llu edits decoded, room for %llu / %llu",
+                                                     (unsigned long long)nr, (unsigned long long)ne, (unsigned long long)recs_cap, (unsigned long long)edits_cap);
+    /* blocks were decoded into disjoint [first_read, +n_reads) / [edit_base, +n_edits) ranges that are dense
+       because the index carries exact counts (legacy: one block) */
+    if (nr && recs) CU(cudaMemcpyAsync(recs, ctx->recs.p, nr * sizeof(cbcg_read_rec), cudaMemcpyDeviceToHost, ctx->st));
+    if (nr && chr) CU(cudaMemcpyAsync(chr, ctx->chr_out.p, nr * 4, cudaMemcpyDeviceToHost, ctx->st));
+    if (ne && edits) CU(cudaMemcpyAsync(edits, ctx->edits.p, ne * 2, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CBCG_OK;
+}
+
+/* K2d + K3 on the blocks of the last cbcg_encode_resident, everything staying in HBM. */
+extern "C" int cbcg_decode_resident(cbcg_ctx *ctx) {
+    if (!ctx) return CBCG_ERR_ARG;
+    if (!ctx->have_encoded) return fail(ctx, CBCG_ERR_ARG, "nothing encoded yet");
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_decoded = false;
+    cbcg_stats &S = ctx->stats;
+    S.ms_code = S.ms_reconstruct = S.ms_plan = S.ms_total = S.ms_extract = S.ms_gather = 0; S.kernel_launches = 0;
+    const uint64_t nb = ctx->enc_n_blocks;
+    if (!nb) { ctx->dec_bytes = 0; ctx->dec_n_reads = 0; ctx->have_decoded = true; return CBCG_OK; }
+    const int legacy = (int)ctx->enc_legacy;
+    /* hblocks still hold the encoder's descriptors (n_reads, chr, base_pos, n_edits, payload_bytes); the compact
+       payload is in ctx->payload in block order. */
+    uint64_t nr = 0, ne = 0;
+    CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    if (legacy) { ctx->hblocks[0].n_reads = (uint32_t)ctx->enc_n_reads + 1u; ctx->hblocks[0].n_edits = (uint32_t)ctx->enc_n_edits + 64u; }
+    TRY(run_decode_blocks(ctx, nb, legacy ? 0u : ctx->enc_L, legacy, legacy ? ctx->enc_n_reads + 1u : ctx->enc_n_reads,
+                          legacy ? ctx->enc_n_edits + 64u : ctx->enc_n_edits, &nr, &ne));
+    CU(cudaEventRecord(ctx->ev[1], ctx->st));
+    if (nr) {
+        TRY(run_reconstruct(ctx, nr, legacy ? CBCG_MAX_READ_LEN : std::max(ctx->enc_max_len, 1u), ctx->chr_out.as<uint32_t>()));
+        CU(cudaEventRecord(ctx->ev[2], ctx->st));
+        TRY(fetch_words(ctx));
+        TRY(device_error(ctx, "read reconstruction"));
+        ctx->dec_bytes = ctx->hw->total_bytes;
+    } else { CU(cudaEventRecord(ctx->ev[2], ctx->st)); CU(cudaStreamSynchronize(ctx->st)); ctx->dec_bytes = 0; }
+    ctx->dec_n_reads = nr; ctx->have_decoded = true;
+    cudaEventElapsedTime(&S.ms_code, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&S.ms_reconstruct, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&S.ms_total, ctx->ev[0], ctx->ev[2]);
+    S.n_reads = nr; S.n_edits = ne; S.n_blocks = nb;
+    if (legacy) { ctx->hblocks[0].n_reads = (uint32_t)ctx->enc_n_reads; ctx->hblocks[0].n_edits = (uint32_t)ctx->enc_n_edits; }
+    return CBCG_OK;
+}
+
+extern "C" int cbcg_fetch_decoded(cbcg_ctx *ctx, uint8_t *seq_out, uint64_t seq_cap, uint64_t *seq_len) {
+    if (!ctx || !seq_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_fetch_decoded: bad argument");
+    if (!ctx->have_decoded) return fail(ctx, CBCG_ERR_ARG, "nothing decoded yet");
+    *seq_len = ctx->dec_bytes;
+    if (ctx->dec_bytes > seq_cap || (!seq_out && ctx->dec_bytes)) return fail(ctx, CBCG_ERR_CAPACITY, "decoded text is %llu bytes", (unsigned long long)ctx->dec_bytes);
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->dec_bytes) CU(cudaMemcpyAsync(seq_out, ctx->seq_out.p, ctx->dec_bytes, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CBCG_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ K3 alone */
+extern "C" int cbcg_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr,
+                                const uint16_t *edits, uint64_t n_edits, uint8_t *seq_out, uint64_t seq_cap,
+                                uint64_t *seq_len) {
+    if (!ctx || !seq_len || (n_reads && (!recs || !chr)) || (n_edits && !edits)) return fail(ctx, CBCG_ERR_ARG, "cbcg_reconstruct: bad argument");
+    if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
+    CU(cudaSetDevice(ctx->device));
+    *seq_len = 0;
+    ctx->stats = cbcg_stats();
+    if (!n_reads) return CBCG_OK;
+    uint32_t max_len = 1;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        if (recs[r].len > max_len) max_len = recs[r].len;
+        if (!recs[r].match && (uint64_t)recs[r].edit_off + recs[r].n_dels + recs[r].n_snps + recs[r].n_ins > n_edits)
+            return fail(ctx, CBCG_ERR_ARG, "read %llu: edit range outside the edit array", (unsigned long long)r);
+    }
+    if (max_len > CBCG_MAX_READ_LEN) return fail(ctx, CBCG_ERR_INPUT, "read longer than %u", CBCG_MAX_READ_LEN);
+    TRY(ensure(ctx, ctx->recs, (n_reads + 1) * sizeof(cbcg_read_rec)));
+    TRY(ensure(ctx, ctx->chr_out, (n_reads + 1) * 4));
+    TRY(ensure(ctx, ctx->edits, (n_edits + 64) * 2));
+    CU(cudaMemcpyAsync(ctx->recs.p, recs, n_reads * sizeof(cbcg_read_rec), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->chr_out.p, chr, n_reads * 4, cudaMemcpyHostToDevice, ctx->st));
+    if (n_edits) CU(cudaMemcpyAsync(ctx->edits.p, edits, n_edits * 2, cudaMemcpyHostToDevice, ctx->st));
+    TRY(reset_words(ctx));
+    CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    TRY(run_reconstruct(ctx, n_reads, max_len, ctx->chr_out.as<uint32_t>()));
+    CU(cudaEventRecord(ctx->ev[1], ctx->st));
+    TRY(fetch_words(ctx));
+    cudaEventElapsedTime(&ctx->stats.ms_reconstruct, ctx->ev[0], ctx->ev[1]);
+    TRY(device_error(ctx, "read reconstruction"));
+    const uint64_t bytes = ctx->hw->total_bytes;
+    *seq_len = bytes;
+    ctx->dec_bytes = bytes; ctx->dec_n_reads = n_reads; ctx->have_decoded = true;
+    if (bytes > seq_cap || !seq_out) return fail(ctx, CBCG_ERR_CAPACITY, "text is %llu bytes, room for %llu", (unsigned long long)bytes, (unsigned long long)seq_cap);
+    CU(cudaMemcpyAsync(seq_out, ctx->seq_out.p, bytes, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->stats.n_reads = n_reads; ctx->stats.n_edits = n_edits;
+    return CBCG_OK;
+}

@@ -83,6 +83,11 @@ const char *cbcg_last_error(const cbcg_ctx *ctx);      /* detail of the last fai
 int  cbcg_abi_version(void);
 int  cbcg_get_stats(const cbcg_ctx *ctx, cbcg_stats *out);   /* stats of the last call */
 
+/* Page-locked host memory for batches and outputs: host<->device copies of pageable memory are staged
+ * and run at a fraction of the link rate. Optional; any host pointer is accepted everywhere. */
+void *cbcg_host_alloc(size_t bytes);
+void  cbcg_host_free(void *p);
+
 /* ---- reference genome. Replaces store_reference_in_memory (src/read_decompression.c:17-53) and the
  * chromosome switch in compress_line/decompress_line (src/compression.c:58-64,91-101): all records are
  * resident at once, upper-cased on upload, addressed by ordinal. names are used for the container. */

@@ -842,7 +842,7 @@ int cbco_symbols(const cbco_batch *b, const cbco_genome *g, const cbcg_read_rec 
 
 /* ------------------------------------------------------------------ blocked container
  * Our design (the reference stream has no framing). Layout, little endian:
- *   header  : u32 magic, version, flags, read_len, u64 n_reads, u32 n_blocks, n_chr,
+ *   header  : u32 magic, version, max_read_len, read_len, u64 n_reads, u32 n_blocks, n_chr,
  *             block_reads, gen_mode, then per chromosome u32 name_len + bytes (padded to 4)
  *   index   : n_blocks x 8 u32 { n_reads, chr, base_pos, n_symbols, n_edits, payload_bytes, gen, 0 }
  *   payload : block bitstreams back to back
@@ -892,7 +892,9 @@ int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, u
         rstate_free(&s);
     }
     if (!rc) {
-        buf_put_u32(out, CBCG_MAGIC); buf_put_u32(out, CBCG_VERSION); buf_put_u32(out, 0); buf_put_u32(out, L);
+        uint32_t max_len = 0;
+        for (uint64_t r = 0; r < b->n_reads; r++) if (b->seq_len[r] > max_len) max_len = b->seq_len[r];
+        buf_put_u32(out, CBCG_MAGIC); buf_put_u32(out, CBCG_VERSION); buf_put_u32(out, max_len); buf_put_u32(out, L);
         buf_put_u64(out, b->n_reads); buf_put_u32(out, (uint32_t)nb); buf_put_u32(out, g->n_chr);
         buf_put_u32(out, block_reads); buf_put_u32(out, gen_mode);
         for (uint32_t c = 0; c < g->n_chr; c++) {
