@@ -26,7 +26,7 @@ EXPORTS = ["cbcg_create", "cbcg_destroy", "cbcg_strerror", "cbcg_last_error", "c
            "cbcg_host_alloc", "cbcg_host_free", "cbcg_set_reference", "cbcg_extract", "cbcg_extract_symbols",
            "cbcg_encode", "cbcg_encode_bound", "cbcg_decode", "cbcg_decoded_size", "cbcg_decode_edits",
            "cbcg_reconstruct", "cbcg_batch_upload", "cbcg_encode_resident", "cbcg_decode_resident",
-           "cbcg_fetch_container", "cbcg_fetch_decoded"]
+           "cbcg_fetch_container", "cbcg_fetch_decoded", "cbcg_fetch_index", "cbcg_mark", "cbcg_elapsed_ms"]
 
 
 class EncodeOpts(C.Structure):
@@ -37,6 +37,7 @@ class EncodeOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms_h2d", C.c_float), ("ms_extract", C.c_float), ("ms_plan", C.c_float), ("ms_code", C.c_float),
                 ("ms_gather", C.c_float), ("ms_reconstruct", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
+                ("ms_k1", C.c_float), ("ms_k3", C.c_float),
                 ("n_reads", C.c_uint64), ("n_blocks", C.c_uint64), ("n_symbols", C.c_uint64), ("n_edits", C.c_uint64),
                 ("payload_bytes", C.c_uint64), ("container_bytes", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
@@ -86,6 +87,9 @@ def load_library():
         lib.cbcg_decode_resident.argtypes = [vp]
         lib.cbcg_fetch_container.argtypes = [vp, vp, u64, P(u64)]
         lib.cbcg_fetch_decoded.argtypes = [vp, vp, u64, P(u64)]
+        lib.cbcg_fetch_index.argtypes = [vp, vp, u64, P(u64), P(u64)]
+        lib.cbcg_mark.argtypes = [vp, C.c_int]
+        lib.cbcg_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, P(C.c_float)]
         _LIB = lib
     return _LIB
 
@@ -284,3 +288,19 @@ class Codec:
             rc = self.lib.cbcg_fetch_decoded(self.h, out.ctypes.data, out.nbytes, C.byref(n))
         self._check(rc)
         return out[:n.value]
+
+    def fetch_index(self) -> Tuple[bytes, int]:
+        """(container header + per-block index, payload byte count) of the last encode."""
+        n, pb = C.c_uint64(0), C.c_uint64(0)
+        self.lib.cbcg_fetch_index(self.h, None, 0, C.byref(n), C.byref(pb))
+        out = np.empty(max(n.value, 1), np.uint8)
+        self._check(self.lib.cbcg_fetch_index(self.h, out.ctypes.data, out.nbytes, C.byref(n), C.byref(pb)))
+        return out[:n.value].tobytes(), pb.value
+
+    def mark(self, slot: int):
+        self._check(self.lib.cbcg_mark(self.h, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        self._check(self.lib.cbcg_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value

@@ -44,6 +44,8 @@ struct cbcg_ctx {
     int device = 0;
     cudaStream_t st = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t kev[4] = {};                  /* tight around K1 (0,1) and K3 (2,3) */
+    cudaEvent_t mark[4] = {};
     char errtext[512] = {0};
     cbcg_stats stats = {};
 
@@ -159,6 +161,8 @@ extern "C" int cbcg_create(int device, cbcg_ctx **out) {
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CBCG_ERR_CUDA; }
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return CBCG_ERR_CUDA; }
+    for (auto &e : ctx->mark) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return CBCG_ERR_CUDA; }
+    for (auto &e : ctx->kev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return CBCG_ERR_CUDA; }
     if (cudaMallocHost(&ctx->hw, sizeof(Words)) != cudaSuccess) { delete ctx; return CBCG_ERR_NOMEM; }
     memset(ctx->hw, 0, sizeof(Words));
     if (ensure(ctx, ctx->words, sizeof(Words))) { cudaFreeHost(ctx->hw); delete ctx; return CBCG_ERR_NOMEM; }
@@ -180,6 +184,8 @@ extern "C" void cbcg_destroy(cbcg_ctx *ctx) {
     if (ctx->hw) cudaFreeHost(ctx->hw);
     if (ctx->hblocks) cudaFreeHost(ctx->hblocks);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->mark) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -187,6 +193,21 @@ extern "C" void cbcg_destroy(cbcg_ctx *ctx) {
 extern "C" int cbcg_get_stats(const cbcg_ctx *ctx, cbcg_stats *out) {
     if (!ctx || !out) return CBCG_ERR_ARG;
     *out = ctx->stats;
+    return CBCG_OK;
+}
+
+/* Timing marks on the library's own stream (torch events only see torch's stream). */
+extern "C" int cbcg_mark(cbcg_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 4) return fail(ctx, CBCG_ERR_ARG, "cbcg_mark: bad slot");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->mark[slot], ctx->st));
+    return CBCG_OK;
+}
+extern "C" int cbcg_elapsed_ms(cbcg_ctx *ctx, int from, int to, float *ms) {
+    if (!ctx || !ms || from < 0 || from >= 4 || to < 0 || to >= 4) return fail(ctx, CBCG_ERR_ARG, "cbcg_elapsed_ms: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->mark[to]));
+    CU(cudaEventElapsedTime(ms, ctx->mark[from], ctx->mark[to]));
     return CBCG_OK;
 }
 
@@ -332,10 +353,11 @@ static int run_extract(cbcg_ctx *ctx) {
         TRY(reset_words(ctx));
         if (launch_extract(ctx->db, ctx->dg, ctx->recs.as<cbcg_read_rec>(), ctx->edits.as<uint16_t>(), cap,
                            ctx->tile_desc.as<uint64_t>(), wptr<uint32_t>(ctx, W_OFF(ticket)), wptr<uint64_t>(ctx, W_OFF(total_edits)),
-                           wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st))
+                           wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st, ctx->kev[0], ctx->kev[1]))
             return fail(ctx, CBCG_ERR_CUDA, "K1 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->stats.kernel_launches++;
         TRY(fetch_words(ctx));
+        cudaEventElapsedTime(&ctx->stats.ms_k1, ctx->kev[0], ctx->kev[1]);
         const unsigned long long v = ctx->hw->err;
         if (v && -(int)(v >> 40) == CBCG_ERR_CAPACITY && attempt == 0) {   /* edit array too small: the count is exact */
             TRY(ensure(ctx, ctx->edits, (ctx->hw->total_edits + 64) * 2));
@@ -425,7 +447,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     const uint32_t L = opts->read_len_header;
     ctx->have_encoded = false;
     cbcg_stats &S = ctx->stats;
-    S.ms_extract = S.ms_plan = S.ms_code = S.ms_gather = S.ms_reconstruct = S.ms_d2h = S.ms_total = 0;
+    S.ms_extract = S.ms_plan = S.ms_code = S.ms_gather = S.ms_reconstruct = S.ms_d2h = S.ms_total = S.ms_k1 = S.ms_k3 = 0;
     S.kernel_launches = 0; S.d2h_bytes = 0;
     if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
 
@@ -521,6 +543,17 @@ extern "C" int cbcg_fetch_container(cbcg_ctx *ctx, uint8_t *out, uint64_t out_ca
     CU(cudaStreamSynchronize(ctx->st));
     cudaEventElapsedTime(&ctx->stats.ms_d2h, ctx->ev[5], ctx->ev[6]);
     ctx->stats.d2h_bytes += ctx->enc_payload_bytes;
+    return CBCG_OK;
+}
+
+/* Header + per-block index of the last encode (no payload): what a shard contributes to the container index. */
+extern "C" int cbcg_fetch_index(cbcg_ctx *ctx, uint8_t *out, uint64_t out_cap, uint64_t *out_len, uint64_t *payload_bytes) {
+    if (!ctx || !out_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_fetch_index: bad argument");
+    if (!ctx->have_encoded) return fail(ctx, CBCG_ERR_ARG, "nothing encoded yet");
+    *out_len = ctx->enc_head.size();
+    if (payload_bytes) *payload_bytes = ctx->enc_payload_bytes;
+    if (ctx->enc_head.size() > out_cap || (!out && !ctx->enc_head.empty())) return fail(ctx, CBCG_ERR_CAPACITY, "index is %zu bytes", ctx->enc_head.size());
+    if (!ctx->enc_head.empty()) memcpy(out, ctx->enc_head.data(), ctx->enc_head.size());
     return CBCG_OK;
 }
 
@@ -679,7 +712,7 @@ static int run_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, uint32_t max_len, co
     if (launch_reconstruct(n_reads, ctx->recs.as<cbcg_read_rec>(), chr_dev, ctx->edits.as<uint16_t>(), ctx->dg,
                            ctx->seq_out.as<uint8_t>(), out_cap, max_len, ctx->tile_desc.as<uint64_t>(),
                            wptr<uint32_t>(ctx, W_OFF(ticket)), wptr<uint64_t>(ctx, W_OFF(total_bytes)),
-                           wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st))
+                           wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st, ctx->kev[2], ctx->kev[3]))
         return fail(ctx, CBCG_ERR_CUDA, "K3 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     ctx->stats.kernel_launches++;
     return 0;
@@ -774,6 +807,7 @@ extern "C" int cbcg_decode(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, in
     CU(cudaEventRecord(ctx->ev[3], ctx->st));
     TRY(fetch_words(ctx));
     TRY(device_error(ctx, "read reconstruction"));
+    cudaEventElapsedTime(&ctx->stats.ms_k3, ctx->kev[2], ctx->kev[3]);
     const uint64_t bytes = ctx->hw->total_bytes;
     *seq_len = bytes;
     ctx->dec_bytes = bytes; ctx->dec_n_reads = nr; ctx->have_decoded = true;
@@ -835,6 +869,7 @@ extern "C" int cbcg_decode_resident(cbcg_ctx *ctx) {
         CU(cudaEventRecord(ctx->ev[2], ctx->st));
         TRY(fetch_words(ctx));
         TRY(device_error(ctx, "read reconstruction"));
+        cudaEventElapsedTime(&S.ms_k3, ctx->kev[2], ctx->kev[3]);
         ctx->dec_bytes = ctx->hw->total_bytes;
     } else { CU(cudaEventRecord(ctx->ev[2], ctx->st)); CU(cudaStreamSynchronize(ctx->st)); ctx->dec_bytes = 0; }
     ctx->dec_n_reads = nr; ctx->have_decoded = true;
@@ -886,6 +921,7 @@ extern "C" int cbcg_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, const cbcg_read
     CU(cudaEventRecord(ctx->ev[1], ctx->st));
     TRY(fetch_words(ctx));
     cudaEventElapsedTime(&ctx->stats.ms_reconstruct, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->stats.ms_k3, ctx->kev[2], ctx->kev[3]);
     TRY(device_error(ctx, "read reconstruction"));
     const uint64_t bytes = ctx->hw->total_bytes;
     *seq_len = bytes;

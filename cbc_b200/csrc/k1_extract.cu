@@ -296,7 +296,7 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
     /* ---- phase 3: write records and edit entries */
     if (tid < nr) {
         const uint64_t off = tile_base + my_excl;
-        cbcg_read_rec rec;
+        __align__(16) cbcg_read_rec rec;
         rec.pos = my_pos; rec.flag = (uint16_t)my_flag; rec.len = (uint16_t)my_len;
         rec.edit_off = (uint32_t)off;
         rec.match = (uint8_t)((my_cnt >> 24) & 1u);
@@ -314,7 +314,7 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
 
 int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, uint16_t *edits,
                    uint64_t edits_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_edits,
-                   unsigned long long *err, cudaStream_t st) {
+                   unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop) {
     if (b.n_reads == 0) return 0;
     const uint64_t tiles = extract_num_tiles(b.n_reads);
     const uint32_t seq_cap = (K1_TILE * b.max_len + 48u) & ~15u;
@@ -326,7 +326,9 @@ int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, u
     }
     if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;
     if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;
+    if (ev_start) cudaEventRecord(ev_start, st);
     k1_extract_kernel<<<(unsigned)tiles, K1_TILE, smem, st>>>(b, g, recs, edits, edits_cap, tile_desc, ticket,
                                                              total_edits, err, seq_cap);
+    if (ev_stop) cudaEventRecord(ev_stop, st);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

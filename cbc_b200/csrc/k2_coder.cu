@@ -806,7 +806,7 @@ k2_coder_kernel(CoderParams P) {
     for (uint32_t i = 0; !C.err; i++) {
         if (!(legacy && MODE == MODE_DEC) && i >= n_reads) break;
         const uint64_t r = r0 + i;
-        cbcg_read_rec rec;
+        __align__(16) cbcg_read_rec rec;
         uint32_t chr = cur_chr;
         if (MODE != MODE_DEC) {
             *reinterpret_cast<uint4 *>(&rec) = reinterpret_cast<const uint4 *>(P.recs)[r];

@@ -38,7 +38,7 @@ struct K3Smem {
     uint32_t tile;
     uint32_t warp_tot[K3_WARPS];
     uint32_t out_off[K3_TILE];        /* byte offset of each read's line inside the tile */
-    cbcg_read_rec rec[K3_TILE];
+    __align__(16) cbcg_read_rec rec[K3_TILE];
     uint32_t chr[K3_TILE];
     K3Warp w[K3_WARPS];
     __align__(16) uint8_t ref[K3_REF_CAP + 16];
@@ -114,7 +114,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
 
     K3Warp &W = S.w[warp];
     for (uint32_t i = warp; i < nr; i += K3_WARPS) {
-        const cbcg_read_rec rec = S.rec[i];
+        const cbcg_read_rec &rec = S.rec[i];
         const uint32_t len = rec.len, pos = rec.pos, chr = S.chr[i];
         uint8_t *dst = img + S.out_off[i];
         if (len == 0) { if (lane == 0) dst[0] = '\n'; continue; }
@@ -222,7 +222,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
 int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr, const uint16_t *edits,
                        const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len,
                        uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
-                       unsigned long long *err, cudaStream_t st) {
+                       unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop) {
     if (n_reads == 0) return 0;
     const uint64_t tiles = reconstruct_num_tiles(n_reads);
     const size_t smem = sizeof(K3Smem) + (size_t)K3_TILE * (max_len + 1u) + 64;
@@ -233,7 +233,9 @@ int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32
     }
     if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;
     if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;
+    if (ev_start) cudaEventRecord(ev_start, st);
     k3_reconstruct_kernel<<<(unsigned)tiles, K3_THREADS, smem, st>>>(n_reads, recs, chr, edits, g, out, out_cap,
                                                                     tile_desc, ticket, total_bytes, err, max_len);
+    if (ev_stop) cudaEventRecord(ev_stop, st);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

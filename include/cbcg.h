@@ -69,6 +69,8 @@ typedef struct cbcg_encode_opts {
 /* Per-call device timings (CUDA events on the library's stream), for bench.py / profiling. */
 typedef struct cbcg_stats {
     float ms_h2d, ms_extract, ms_plan, ms_code, ms_gather, ms_reconstruct, ms_d2h, ms_total;
+    float ms_k1, ms_k3;         /* K1 / K3 kernel alone (events tight around the launch; ms_extract and
+                                   ms_reconstruct also hold the host round trip that reads the totals) */
     uint64_t n_reads, n_blocks, n_symbols, n_edits, payload_bytes, container_bytes;
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t kernel_launches;
@@ -143,6 +145,13 @@ int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts);         /
 int cbcg_decode_resident(cbcg_ctx *ctx);                                       /* K2d + K3 on the last encode's blocks */
 int cbcg_fetch_container(cbcg_ctx *ctx, uint8_t *out, uint64_t out_cap, uint64_t *out_len);
 int cbcg_fetch_decoded(cbcg_ctx *ctx, uint8_t *seq_out, uint64_t seq_cap, uint64_t *seq_len);
+/* Container header + per-block index of the last encode, without the payload: what one shard contributes
+ * to a multi-GPU container index. *payload_bytes (optional) receives the payload size. */
+int cbcg_fetch_index(cbcg_ctx *ctx, uint8_t *out, uint64_t out_cap, uint64_t *out_len, uint64_t *payload_bytes);
+
+/* ---- timing marks: CUDA events on the library's own stream (slots 0..3), for bench.py. */
+int cbcg_mark(cbcg_ctx *ctx, int slot);
+int cbcg_elapsed_ms(cbcg_ctx *ctx, int from, int to, float *ms);
 
 #ifdef __cplusplus
 }
