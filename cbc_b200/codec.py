@@ -231,6 +231,21 @@ class Codec:
             self._check(rc)
             return out[:n.value].tobytes(), nr.value
 
+    def compress_into(self, batch: Batch, read_len_header: int, block_reads: int, out: np.ndarray) -> int:
+        """cbcg_encode into a caller-owned (ideally pinned) buffer; returns the container size."""
+        cb = batch.c_struct()
+        opts = EncodeOpts(read_len_header, block_reads, 0, 0)
+        n = C.c_uint64(0)
+        self._check(self.lib.cbcg_encode(self.h, C.byref(cb), C.byref(opts), out.ctypes.data, out.nbytes, C.byref(n)))
+        return n.value
+
+    def decompress_into(self, data: np.ndarray, out: np.ndarray, legacy: bool = False) -> Tuple[int, int]:
+        """cbcg_decode from / into caller-owned buffers; returns (text bytes, reads)."""
+        n, nr = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.cbcg_decode(self.h, data.ctypes.data, data.nbytes, int(legacy), out.ctypes.data, out.nbytes,
+                                         C.byref(n), C.byref(nr)))
+        return n.value, nr.value
+
     def decode_edits(self, data: bytes, legacy: bool = False):
         src = np.frombuffer(data, np.uint8)
         rcap, ecap = 1 << 16, 1 << 18
