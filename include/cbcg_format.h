@@ -87,4 +87,11 @@ typedef struct cbcg_read_rec {
 #define CBCG_MAGIC          0x42434243u   /* "CBCB" */
 #define CBCG_VERSION        1u
 
+/* Generation-primed blocks (gen_mode 1): generation i has CBCG_GEN_COUNTS[i] blocks of
+ * CBCG_GEN_READS[i] reads, each starting from the merged final states of the generation before; the
+ * last generation takes all remaining reads in blocks of block_reads. */
+#define CBCG_GEN_LEVELS     3
+#define CBCG_GEN_COUNTS     { 1u, 31u, 96u }
+#define CBCG_GEN_READS      { 128u, 128u, 256u }
+
 #endif /* CBCG_FORMAT_H */

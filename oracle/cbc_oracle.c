@@ -221,11 +221,12 @@ static uint32_t pos_append(posmodel *p, uint32_t x) {
 /* All models of one coder instance (alloc_read_models_t src/sam_models.c:562-586,
  * alloc_rname_models_t :611-620, initialize_stream_model_codebook :734-770). var rows
  * are created on first touch: their initial state is all-ones, so this is invisible. */
-typedef struct {
+typedef struct models_s {
     uint32_t L;                 /* header read length: alphabet of snps/indels/var */
     model codebook[4], same_ref, rname[256], rlength[4], pos_alpha[4], flag, match[4], snps, indels, chars[6];
     model *var;                 /* CBCG_VAR_CONTEXTS lazily initialised rows (c == NULL: untouched) */
     posmodel pos;
+    const struct models_s *base; /* primed blocks: untouched var rows are read from this snapshot (copy on first touch) */
 } models;
 
 static void chars_init(model *m, int row) {
@@ -262,6 +263,100 @@ static void models_free(models *M) {
     free(M->var);
     pos_free(&M->pos);
 }
+static model *model_of(models *M, uint32_t stream, uint32_t ctx);
+
+/* ------------------------------------------------------------------ generation-primed blocks (our design)
+ * A block of generation g starts from the snapshot S_{g-1} (S_{-1}: the reference's initial state) instead
+ * of from scratch; S_g = S_{g-1} + sum over the blocks b of generation g of (final state of b - S_{g-1}),
+ * count by count, clamped and rescaled like update_model does. The decoder rebuilds the same snapshots
+ * from the blocks it has decoded, so blocks of one generation are independent of each other. */
+static void model_clone(model *d, const model *s) {
+    d->c = (uint32_t *)malloc(sizeof(uint32_t) * (s->card ? s->card : 1));
+    memcpy(d->c, s->c, sizeof(uint32_t) * s->card);
+    d->card = s->card; d->step = s->step; d->n = s->n;
+}
+static void pos_clone(posmodel *d, const posmodel *s) {
+    memset(d, 0, sizeof *d);
+    d->cap = s->cap;
+    d->m.c = (uint32_t *)malloc(sizeof(uint32_t) * s->cap); memcpy(d->m.c, s->m.c, sizeof(uint32_t) * s->m.card);
+    d->alpha = (uint32_t *)malloc(sizeof(uint32_t) * s->cap); memcpy(d->alpha, s->alpha, sizeof(uint32_t) * s->m.card);
+    d->m.card = s->m.card; d->m.n = s->m.n; d->m.step = s->m.step;
+    d->hcap = s->hcap; d->hcount = s->hcount;
+    d->hkey = (uint32_t *)malloc(sizeof(uint32_t) * s->hcap); memcpy(d->hkey, s->hkey, sizeof(uint32_t) * s->hcap);
+    d->hval = (uint32_t *)malloc(sizeof(uint32_t) * s->hcap); memcpy(d->hval, s->hval, sizeof(uint32_t) * s->hcap);
+}
+/* A block's working copy of a snapshot: small models copied, var rows copied on first touch. */
+static void models_clone(models *M, const models *S) {
+    memset(M, 0, sizeof *M);
+    M->L = S->L;
+    for (int i = 0; i < 4; i++) { model_clone(&M->codebook[i], &S->codebook[i]); model_clone(&M->rlength[i], &S->rlength[i]);
+                                  model_clone(&M->pos_alpha[i], &S->pos_alpha[i]); model_clone(&M->match[i], &S->match[i]); }
+    for (int i = 0; i < 256; i++) model_clone(&M->rname[i], &S->rname[i]);
+    for (int i = 0; i < 6; i++) model_clone(&M->chars[i], &S->chars[i]);
+    model_clone(&M->same_ref, &S->same_ref); model_clone(&M->flag, &S->flag);
+    model_clone(&M->snps, &S->snps); model_clone(&M->indels, &S->indels);
+    M->var = (model *)calloc(CBCG_VAR_CONTEXTS, sizeof(model));
+    pos_clone(&M->pos, &S->pos);
+    M->base = S;
+}
+/* acc += (fin - prev), wrapping 32-bit (exact as long as the true sum stays inside int32). */
+static void merge_model(model *acc, const model *fin, const model *prev) {
+    for (uint32_t i = 0; i < acc->card; i++) acc->c[i] += fin->c[i] - prev->c[i];
+}
+static void merge_block(models *acc, const models *fin, const models *prev) {
+    for (int i = 0; i < 4; i++) { merge_model(&acc->rlength[i], &fin->rlength[i], &prev->rlength[i]);
+                                  merge_model(&acc->pos_alpha[i], &fin->pos_alpha[i], &prev->pos_alpha[i]);
+                                  merge_model(&acc->match[i], &fin->match[i], &prev->match[i]); }
+    for (int i = 0; i < 6; i++) merge_model(&acc->chars[i], &fin->chars[i], &prev->chars[i]);
+    merge_model(&acc->same_ref, &fin->same_ref, &prev->same_ref);
+    merge_model(&acc->flag, &fin->flag, &prev->flag);
+    merge_model(&acc->snps, &fin->snps, &prev->snps);
+    merge_model(&acc->indels, &fin->indels, &prev->indels);
+    for (uint32_t ctx = 0; ctx < CBCG_VAR_CONTEXTS; ctx++) {
+        if (!fin->var[ctx].c) continue;                       /* untouched by the block */
+        model *a = model_of(acc, CBCG_S_VAR, ctx);            /* materialises acc's copy of the snapshot row */
+        const model *f = &fin->var[ctx];
+        if (prev->var[ctx].c) for (uint32_t i = 0; i < a->card; i++) a->c[i] += f->c[i] - prev->var[ctx].c[i];
+        else for (uint32_t i = 0; i < a->card; i++) a->c[i] += f->c[i] - 1u;
+    }
+    /* pos: values new to the snapshot are appended in block order, then order of appearance */
+    for (uint32_t s = 0; s < fin->pos.m.card; s++) {
+        uint32_t x = fin->pos.alpha[s];
+        int ps = (s == 0) ? 0 : pos_find(&prev->pos, x);
+        uint32_t before = (ps >= 0) ? prev->pos.m.c[ps] : 0u;
+        int as = (s == 0) ? 0 : pos_find(&acc->pos, x);
+        if (as < 0) as = (int)pos_append(&acc->pos, x);
+        acc->pos.m.c[as] += fin->pos.m.c[s] - before;
+    }
+}
+static void finish_model(model *m, const model *prev, uint32_t prev_card) {
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < m->card; i++) {
+        int32_t v = (int32_t)m->c[i];
+        int32_t floor = (prev && i < prev_card && prev->c[i] == 0) ? 0 : 1;
+        if (v < floor) v = floor;
+        m->c[i] = (uint32_t)v; n += (uint32_t)v;
+    }
+    m->n = n;
+    while (m->n >= CBCG_RESCALE) {                             /* update_model's halve-and-increment, src/stream_model.c:38-49 */
+        m->n = 0;
+        for (uint32_t i = 0; i < m->card; i++) { m->c[i] = (m->c[i] >> 1) + 1; m->n += m->c[i]; }
+    }
+}
+static void merge_finish(models *acc, const models *prev) {
+    for (int i = 0; i < 4; i++) { finish_model(&acc->rlength[i], &prev->rlength[i], 255); finish_model(&acc->pos_alpha[i], &prev->pos_alpha[i], 256);
+                                  finish_model(&acc->match[i], &prev->match[i], 2); }
+    for (int i = 0; i < 6; i++) finish_model(&acc->chars[i], &prev->chars[i], 5);
+    finish_model(&acc->same_ref, &prev->same_ref, 2);
+    finish_model(&acc->flag, &prev->flag, 1u << 16);
+    finish_model(&acc->snps, &prev->snps, acc->L); finish_model(&acc->indels, &prev->indels, acc->L);
+    for (uint32_t ctx = 0; ctx < CBCG_VAR_CONTEXTS; ctx++) if (acc->var[ctx].c) finish_model(&acc->var[ctx], NULL, 0);
+    finish_model(&acc->pos.m, NULL, 0);
+    /* the snapshot must stand alone: pull in the rows it still shares with its predecessor */
+    for (uint32_t ctx = 0; ctx < CBCG_VAR_CONTEXTS; ctx++) if (!acc->var[ctx].c && prev->var[ctx].c) (void)model_of(acc, CBCG_S_VAR, ctx);
+    acc->base = NULL;
+}
+
 static model *model_of(models *M, uint32_t stream, uint32_t ctx) {
     switch (stream) {
         case CBCG_S_CODEBOOK:  return ctx < 4 ? &M->codebook[ctx] : NULL;
@@ -277,7 +372,15 @@ static model *model_of(models *M, uint32_t stream, uint32_t ctx) {
         case CBCG_S_CHARS:     return ctx < 6 ? &M->chars[ctx] : NULL;
         case CBCG_S_VAR:
             if (ctx >= CBCG_VAR_CONTEXTS) return NULL;
-            if (!M->var[ctx].c) model_ones(&M->var[ctx], M->L, 10);
+            if (!M->var[ctx].c) {
+                if (M->base && M->base->var[ctx].c) {
+                    const model *src = &M->base->var[ctx];
+                    model *d = &M->var[ctx];
+                    d->c = (uint32_t *)malloc(sizeof(uint32_t) * src->card);
+                    memcpy(d->c, src->c, sizeof(uint32_t) * src->card);
+                    d->card = src->card; d->step = src->step; d->n = src->n;
+                } else model_ones(&M->var[ctx], M->L, 10);
+            }
             return &M->var[ctx];
         default: return NULL;
     }
@@ -851,9 +954,18 @@ int cbco_symbols(const cbco_batch *b, const cbco_genome *g, const cbcg_read_rec 
  * order with same_ref = 0; closed by the reference's final flush. */
 typedef struct { uint32_t n_reads, chr, base_pos, n_symbols, n_edits, payload_bytes, gen, rsv; } blk_index;
 
-int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads,
-                        uint32_t gen_mode, cbco_buf *out) {
-    if (gen_mode != 0 || block_reads == 0) return -30;
+static void rstate_init_from(rstate *s, const models *snap, int mode) {
+    memset(s, 0, sizeof *s);
+    models_clone(&s->c.M, snap);
+    s->c.mode = mode;
+}
+
+/* Blocks: generation i < n_sched has sched_count[i] blocks of sched_reads[i] reads, the last generation
+ * takes the rest in blocks of block_reads reads; a chromosome change always ends a block. n_sched == 0:
+ * every block starts from the reference's initial state (gen_mode 0). */
+int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads,
+                          uint32_t n_sched, const uint32_t *sched_count, const uint32_t *sched_reads, cbco_buf *out) {
+    if (block_reads == 0) return -30;
     uint64_t cap = 16;
     for (uint64_t r = 0; r < b->n_reads; r++) cap += 3ull * b->seq_len[r] + 8;
     cbcg_read_rec *recs = (cbcg_read_rec *)malloc(sizeof(cbcg_read_rec) * (b->n_reads + 1));
@@ -861,23 +973,37 @@ int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, u
     int64_t ne = cbco_extract(b, g, recs, edits, cap);
     if (ne < 0) { free(recs); free(edits); return (int)ne; }
     /* cut blocks */
-    uint64_t nb = 0, bcap = b->n_reads / block_reads + g->n_chr + 2;
+    uint64_t nb = 0, bcap = 1024;
     blk_index *idx = (blk_index *)calloc(bcap, sizeof(blk_index));
     uint64_t *first = (uint64_t *)calloc(bcap + 1, sizeof(uint64_t));
+    uint32_t gen = 0, left_in_gen = n_sched ? sched_count[0] : 0;
+    while (gen < n_sched && left_in_gen == 0) { gen++; left_in_gen = gen < n_sched ? sched_count[gen] : 0; }
     for (uint64_t r = 0; r < b->n_reads;) {
+        uint32_t want = gen < n_sched ? sched_reads[gen] : block_reads;
+        if (want == 0) want = 1;
         uint64_t e = r + 1;
-        while (e < b->n_reads && e - r < block_reads && b->chr[e] == b->chr[r]) e++;
-        if (nb >= bcap) { bcap *= 2; idx = (blk_index *)realloc(idx, bcap * sizeof(blk_index)); first = (uint64_t *)realloc(first, (bcap + 1) * 8); }
+        while (e < b->n_reads && e - r < want && b->chr[e] == b->chr[r]) e++;
+        if (nb + 1 >= bcap) { bcap *= 2; idx = (blk_index *)realloc(idx, bcap * sizeof(blk_index)); first = (uint64_t *)realloc(first, (bcap + 1) * 8); }
         first[nb] = r;
-        idx[nb].n_reads = (uint32_t)(e - r); idx[nb].chr = b->chr[r]; idx[nb].base_pos = recs[r].pos;
-        idx[nb].gen = 0; idx[nb].rsv = 0;
+        memset(&idx[nb], 0, sizeof(blk_index));
+        idx[nb].n_reads = (uint32_t)(e - r); idx[nb].chr = b->chr[r]; idx[nb].base_pos = recs[r].pos; idx[nb].gen = gen;
         nb++; r = e;
+        if (gen < n_sched && --left_in_gen == 0) { gen++; while (gen < n_sched && sched_count[gen] == 0) gen++; left_in_gen = gen < n_sched ? sched_count[gen] : 0; }
     }
     first[nb] = b->n_reads;
+    const uint32_t last_gen = nb ? idx[nb - 1].gen : 0;
     cbco_buf payload = {0};
     int rc = 0;
+    models *prev = (models *)malloc(sizeof(models)), *acc = NULL;
+    models_init(prev, L);
+    uint32_t cur_gen = 0;
     for (uint64_t k = 0; k < nb && !rc; k++) {
-        rstate s; rstate_init(&s, L, 1);
+        if (idx[k].gen != cur_gen) {                           /* generation boundary: the merged state becomes the snapshot */
+            if (acc) { merge_finish(acc, prev); models_free(prev); free(prev); prev = acc; acc = NULL; }
+            cur_gen = idx[k].gen;
+        }
+        if (!acc && idx[k].gen != last_gen) { acc = (models *)malloc(sizeof(models)); models_clone(acc, prev); }
+        rstate s; rstate_init_from(&s, prev, 1);
         uint64_t start = payload.size;
         ac_init_enc(&s.c.ac, &payload);
         s.prev_pos = idx[k].base_pos; s.have_name = 1; s.cur_chr = idx[k].chr;
@@ -889,14 +1015,17 @@ int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, u
         uint64_t e_hi = (first[k + 1] < b->n_reads) ? recs[first[k + 1]].edit_off : (uint64_t)ne;
         idx[k].n_edits = (uint32_t)(e_hi - e_lo);
         idx[k].payload_bytes = (uint32_t)(payload.size - start);
+        if (acc && !rc) merge_block(acc, &s.c.M, prev);
         rstate_free(&s);
     }
+    if (acc) { models_free(acc); free(acc); }
+    models_free(prev); free(prev);
     if (!rc) {
         uint32_t max_len = 0;
         for (uint64_t r = 0; r < b->n_reads; r++) if (b->seq_len[r] > max_len) max_len = b->seq_len[r];
         buf_put_u32(out, CBCG_MAGIC); buf_put_u32(out, CBCG_VERSION); buf_put_u32(out, max_len); buf_put_u32(out, L);
         buf_put_u64(out, b->n_reads); buf_put_u32(out, (uint32_t)nb); buf_put_u32(out, g->n_chr);
-        buf_put_u32(out, block_reads); buf_put_u32(out, gen_mode);
+        buf_put_u32(out, block_reads); buf_put_u32(out, n_sched ? 1u : 0u);
         for (uint32_t c = 0; c < g->n_chr; c++) {
             uint32_t nl = (uint32_t)strlen(g->name[c]), pad = (4 - (nl & 3)) & 3; uint32_t z = 0;
             buf_put_u32(out, nl); buf_put(out, g->name[c], nl); buf_put(out, &z, pad);
@@ -909,13 +1038,20 @@ int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, u
     return rc;
 }
 
+int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads,
+                        uint32_t gen_mode, cbco_buf *out) {
+    static const uint32_t count[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, reads[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
+    if (gen_mode > 1) return -30;
+    return cbco_encode_scheduled(b, g, L, block_reads, gen_mode ? CBCG_GEN_LEVELS : 0u, count, reads, out);
+}
+
 int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cbco_buf *seq_out, uint64_t *n_reads_out) {
     if (len < 40) return -40;
     uint32_t h[10]; memcpy(h, p, 40);
     if (h[0] != CBCG_MAGIC || h[1] != CBCG_VERSION) return -41;
     uint32_t L = h[3]; uint64_t n_reads; memcpy(&n_reads, p + 16, 8);
     uint32_t nb = h[6], n_chr = h[7], gen_mode = h[9];
-    if (gen_mode != 0 || n_chr > g->n_chr) return -42;
+    if (gen_mode > 1 || n_chr > g->n_chr) return -42;
     uint64_t o = 40;
     /* container chromosome ordinal -> genome ordinal, by name */
     uint32_t *chr_map = (uint32_t *)calloc(n_chr + 1, sizeof(uint32_t));
@@ -934,11 +1070,21 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
     o += (uint64_t)nb * sizeof(blk_index);
     int rc = 0; uint64_t n = 0;
     uint16_t e[3 * 256 + 8]; uint8_t line[1025];
+    uint32_t last_gen = 0;
+    for (uint32_t k = 0; k < nb; k++) { blk_index bi; memcpy(&bi, &idx[k], sizeof bi); if (bi.gen < last_gen) { free(chr_map); return -48; } last_gen = bi.gen; }
+    models *prev = (models *)malloc(sizeof(models)), *acc = NULL;
+    models_init(prev, L);
+    uint32_t cur_gen = 0;
     for (uint32_t k = 0; k < nb && !rc; k++) {
         blk_index bi; memcpy(&bi, &idx[k], sizeof bi);
         if (bi.chr >= n_chr || o + bi.payload_bytes > len) { rc = -45; break; }
+        if (bi.gen != cur_gen) {
+            if (acc) { merge_finish(acc, prev); models_free(prev); free(prev); prev = acc; acc = NULL; }
+            cur_gen = bi.gen;
+        }
+        if (!acc && bi.gen != last_gen) { acc = (models *)malloc(sizeof(models)); models_clone(acc, prev); }
         uint32_t chr = chr_map[bi.chr];
-        rstate s; rstate_init(&s, L, 2);
+        rstate s; rstate_init_from(&s, prev, 2);
         ac_init_dec(&s.c.ac, p + o, bi.payload_bytes);
         s.prev_pos = bi.base_pos;
         snp_reset(&s.snp, g->len[chr] + 2048);
@@ -953,9 +1099,12 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
             buf_put(seq_out, line, rec.len + 1u);
             n++;
         }
+        if (acc && !rc) merge_block(acc, &s.c.M, prev);
         rstate_free(&s);
         o += bi.payload_bytes;
     }
+    if (acc) { models_free(acc); free(acc); }
+    models_free(prev); free(prev);
     free(chr_map);
     if (n_reads_out) *n_reads_out = n;
     return rc;
