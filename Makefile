@@ -3,7 +3,7 @@
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall -Iinclude -Icbc_b200/csrc
+NVFLAGS   := -O3 -std=c++17 -lineinfo --extended-lambda $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall -Iinclude -Icbc_b200/csrc
 BUILD     := cbc_b200/_build
 CU_SRC    := $(wildcard cbc_b200/csrc/*.cu)
 CU_HDR    := $(wildcard cbc_b200/csrc/*.cuh) $(wildcard include/*.h)

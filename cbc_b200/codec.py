@@ -177,9 +177,9 @@ class Codec:
             self._check(rc)
             return recs[:batch.n_reads], edits[:n.value].copy()
 
-    def symbols(self, batch: Batch, read_len_header: int, block_reads: int = 0):
+    def symbols(self, batch: Batch, read_len_header: int, block_reads: int = 0, gen_mode: int = 0):
         cb = batch.c_struct()
-        opts = EncodeOpts(read_len_header, block_reads, 0, 0)
+        opts = EncodeOpts(read_len_header, block_reads, gen_mode, 0)
         cap = 16 * batch.n_reads + batch.total_bases() // 4 + 8192
         nb_cap = (batch.n_reads // block_reads + 4200) if block_reads else 1
         while True:
@@ -195,10 +195,12 @@ class Codec:
             return syms[:n.value].copy(), counts[:nb.value].copy()
 
     # ---- compress() / decompress() (src/compression.c:112-216) over host buffers
-    def compress(self, batch: Batch, read_len_header: int, block_reads: int = 0, out: Optional[np.ndarray] = None) -> bytes:
-        """block_reads == 0: the reference's own single stream (byte-identical to `program -c 1`, -DDEBUG)."""
+    def compress(self, batch: Batch, read_len_header: int, block_reads: int = 0, gen_mode: int = 0,
+                 out: Optional[np.ndarray] = None) -> bytes:
+        """block_reads == 0: the reference's own single stream (byte-identical to `program -c 1`, -DDEBUG).
+        gen_mode 1: generation-primed blocks."""
         cb = batch.c_struct()
-        opts = EncodeOpts(read_len_header, block_reads, 0, 0)
+        opts = EncodeOpts(read_len_header, block_reads, gen_mode, 0)
         cap = int(self.lib.cbcg_encode_bound(C.byref(cb), C.byref(opts)))
         buf = out if out is not None and out.nbytes >= cap else np.empty(cap, np.uint8)
         n = C.c_uint64(0)
@@ -231,10 +233,10 @@ class Codec:
             self._check(rc)
             return out[:n.value].tobytes(), nr.value
 
-    def compress_into(self, batch: Batch, read_len_header: int, block_reads: int, out: np.ndarray) -> int:
+    def compress_into(self, batch: Batch, read_len_header: int, block_reads: int, out: np.ndarray, gen_mode: int = 0) -> int:
         """cbcg_encode into a caller-owned (ideally pinned) buffer; returns the container size."""
         cb = batch.c_struct()
-        opts = EncodeOpts(read_len_header, block_reads, 0, 0)
+        opts = EncodeOpts(read_len_header, block_reads, gen_mode, 0)
         n = C.c_uint64(0)
         self._check(self.lib.cbcg_encode(self.h, C.byref(cb), C.byref(opts), out.ctypes.data, out.nbytes, C.byref(n)))
         return n.value
@@ -277,8 +279,8 @@ class Codec:
         cb = batch.c_struct()
         self._check(self.lib.cbcg_batch_upload(self.h, C.byref(cb)))
 
-    def encode_resident(self, read_len_header: int, block_reads: int):
-        opts = EncodeOpts(read_len_header, block_reads, 0, 0)
+    def encode_resident(self, read_len_header: int, block_reads: int, gen_mode: int = 0):
+        opts = EncodeOpts(read_len_header, block_reads, gen_mode, 0)
         self._check(self.lib.cbcg_encode_resident(self.h, C.byref(opts)))
 
     def decode_resident(self):

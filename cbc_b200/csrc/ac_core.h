@@ -38,14 +38,37 @@ AC_HD uint64_t ac_div(uint64_t p, uint32_t n) {
 #endif
 }
 
+/* Exact floor(p / d) through one shared reciprocal: for p < 2^47 and 0 < d < 2^27 the estimate
+ * trunc(p * rcp(d)) is off by at most one (relative error of the product < 2^-51, quotient < 2^47), and the
+ * integer remainder check puts it right. The interval update needs two quotients by the same n, so the
+ * reciprocal is computed once per symbol: ~25 integer/FP64 instructions instead of two full divisions. */
+AC_HD double ac_rcp(uint32_t d) {
+#ifdef __CUDA_ARCH__
+    return __drcp_rn((double)d);
+#else
+    return 1.0 / (double)d;
+#endif
+}
+AC_HD uint64_t ac_div_r(uint64_t p, uint32_t d, double r) {
+#ifdef __CUDA_ARCH__
+    uint64_t q = (uint64_t)__double2ull_rz(__dmul_rn(__ull2double_rz(p), r));
+#else
+    uint64_t q = (uint64_t)((double)p * r);
+#endif
+    const int64_t rem = (int64_t)(p - q * (uint64_t)d);
+    if (rem < 0) q--; else if (rem >= (int64_t)d) q++;
+    return q;
+}
+
 struct AcInterval { uint32_t l, u; };
 
 /* Interval update of arithmetic_encoder_step / arithmetic_decoder_step (:295-296, :402-403):
  * u is computed from the old l, both products in 64 bits, truncated to 32. */
 AC_HD void ac_narrow(AcInterval &a, uint32_t lo, uint32_t hi, uint32_t n) {
     const uint64_t range = (uint64_t)a.u - a.l + 1u;
-    const uint32_t nu = a.l + (uint32_t)ac_div(range * hi, n) - 1u;
-    const uint32_t nl = a.l + (uint32_t)ac_div(range * lo, n);
+    const double r = ac_rcp(n);
+    const uint32_t nu = a.l + (uint32_t)ac_div_r(range * hi, n, r) - 1u;
+    const uint32_t nl = a.l + (uint32_t)ac_div_r(range * lo, n, r);
     a.u = nu; a.l = nl;
 }
 
@@ -81,5 +104,5 @@ AC_HD uint32_t ac_tag_shift(uint32_t t, uint32_t k, uint32_t m, uint32_t in) {
 AC_HD uint32_t ac_target(const AcInterval &a, uint32_t t, uint32_t n) {
     const uint64_t range = (uint64_t)a.u - a.l + 1u;
     const uint64_t gap = (uint64_t)t - a.l + 1u;
-    return (uint32_t)ac_div(gap * n - 1u, (uint32_t)range);
+    return (uint32_t)ac_div_r(gap * n - 1u, (uint32_t)range, ac_rcp((uint32_t)range));
 }

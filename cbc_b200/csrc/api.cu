@@ -64,6 +64,8 @@ struct cbcg_ctx {
 
     /* work buffers */
     DevBuf recs, edits, chr_out, tile_desc, words, blocks, ws, scratch, payload, out_off, symbols, seq_out;
+    DevBuf snap_a, snap_b, fin;                /* generation snapshots and per-block final states (gen_mode 1) */
+    std::vector<std::pair<uint32_t, uint32_t>> gens;   /* (first block, block count) per generation of the last cut */
     Words *hw = nullptr;                       /* pinned */
     BlockDesc *hblocks = nullptr; size_t hblocks_cap = 0;   /* pinned */
 
@@ -179,7 +181,7 @@ extern "C" void cbcg_destroy(cbcg_ctx *ctx) {
     DevBuf *all[] = { &ctx->g_bases, &ctx->g_off, &ctx->g_len, &ctx->g_names, &ctx->b_pos, &ctx->b_flag, &ctx->b_len, &ctx->b_chr,
                       &ctx->b_soff, &ctx->b_seq, &ctx->b_coff, &ctx->b_cigar, &ctx->b_moff, &ctx->b_md, &ctx->recs, &ctx->edits,
                       &ctx->chr_out, &ctx->tile_desc, &ctx->words, &ctx->blocks, &ctx->ws, &ctx->scratch, &ctx->payload,
-                      &ctx->out_off, &ctx->symbols, &ctx->seq_out };
+                      &ctx->out_off, &ctx->symbols, &ctx->seq_out, &ctx->snap_a, &ctx->snap_b, &ctx->fin };
     for (DevBuf *b : all) free_buf(*b);
     if (ctx->hw) cudaFreeHost(ctx->hw);
     if (ctx->hblocks) cudaFreeHost(ctx->hblocks);
@@ -387,28 +389,84 @@ extern "C" int cbcg_extract(cbcg_ctx *ctx, const cbcg_batch *batch, cbcg_read_re
 }
 
 /* ------------------------------------------------------------------------------------------------ blocks */
-static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint64_t *n_blocks_out) {
-    const uint64_t n = ctx->db.n_reads;
-    uint64_t nb = 0;
-    if (block_reads == 0) nb = 1;
-    else for (const ChrRun &r : ctx->runs) nb += (r.n + block_reads - 1) / block_reads;
-    if (nb >= 0xffffffffull) return fail(ctx, CBCG_ERR_ARG, "too many blocks");
-    TRY(ensure_hblocks(ctx, nb + 1));
-    BlockDesc *hb = ctx->hblocks;
-    memset(hb, 0, nb * sizeof(BlockDesc));
-    if (block_reads == 0) { hb[0].first_read = 0; hb[0].n_reads = (uint32_t)n; hb[0].chr = ctx->runs.empty() ? 0 : ctx->runs[0].chr; }
-    else {
-        uint64_t k = 0;
-        for (const ChrRun &r : ctx->runs)
-            for (uint64_t o = 0; o < r.n; o += block_reads, k++) {
-                hb[k].first_read = (uint32_t)(r.first + o);
-                hb[k].n_reads = (uint32_t)std::min<uint64_t>(block_reads, r.n - o);
-                hb[k].chr = r.chr;
-            }
+static void gens_from_blocks(cbcg_ctx *ctx, uint64_t nb) {
+    ctx->gens.clear();
+    for (uint64_t k = 0; k < nb; k++) {
+        if (ctx->gens.empty() || ctx->hblocks[k].gen != ctx->hblocks[ctx->gens.back().first].gen) ctx->gens.push_back({ (uint32_t)k, 0u });
+        ctx->gens.back().second++;
     }
+}
+
+/* Blocks of block_reads reads, never across a chromosome change. gen_mode 1: the first generations follow the
+ * CBCG_GEN_* schedule (small blocks that bootstrap the model snapshots), the last one takes the rest. */
+static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, uint64_t *n_blocks_out) {
+    static const uint32_t sched_count[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sched_reads[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
+    const uint32_t n_sched = gen_mode ? CBCG_GEN_LEVELS : 0u;
+    const uint64_t n = ctx->db.n_reads;
+    uint64_t bound = 1;
+    if (block_reads) { for (const ChrRun &r : ctx->runs) bound += r.n / block_reads + 1; for (uint32_t g = 0; g < n_sched; g++) bound += sched_count[g]; }
+    if (bound >= 0xffffffffull) return fail(ctx, CBCG_ERR_ARG, "too many blocks");
+    TRY(ensure_hblocks(ctx, bound + 1));
+    BlockDesc *hb = ctx->hblocks;
+    uint64_t nb = 0;
+    if (block_reads == 0) {
+        memset(&hb[0], 0, sizeof(BlockDesc));
+        hb[0].first_read = 0; hb[0].n_reads = (uint32_t)n; hb[0].chr = ctx->runs.empty() ? 0 : ctx->runs[0].chr;
+        nb = 1;
+    } else {
+        uint32_t gen = 0, left = n_sched ? sched_count[0] : 0;
+        for (const ChrRun &r : ctx->runs) {
+            uint64_t o = 0;
+            while (o < r.n) {
+                uint32_t want = gen < n_sched ? sched_reads[gen] : block_reads;
+                if (!want) want = 1;
+                BlockDesc &d = hb[nb++];
+                memset(&d, 0, sizeof d);
+                d.first_read = (uint32_t)(r.first + o);
+                d.n_reads = (uint32_t)std::min<uint64_t>(want, r.n - o);
+                d.chr = r.chr; d.gen = gen;
+                o += d.n_reads;
+                if (gen < n_sched && --left == 0) { gen++; left = gen < n_sched ? sched_count[gen] : 0; }
+            }
+        }
+    }
+    gens_from_blocks(ctx, nb);
     TRY(ensure(ctx, ctx->blocks, (nb + 1) * sizeof(BlockDesc)));
-    CU(cudaMemcpyAsync(ctx->blocks.p, hb, nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
+    if (nb) CU(cudaMemcpyAsync(ctx->blocks.p, hb, nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
     *n_blocks_out = nb;
+    return 0;
+}
+
+/* Runs the block coder (encode or decode) over all blocks of ctx->hblocks, generation by generation when primed:
+ * blocks of generation g start from snapshot S_{g-1}; after each generation but the last the merge kernels build S_g. */
+static int run_coder_generations(cbcg_ctx *ctx, CoderParams p, uint64_t nb, bool primed) {
+    if (!primed) {
+        p.block_begin = 0; p.n_blocks = (uint32_t)nb;
+        if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx->stats.kernel_launches++;
+        return 0;
+    }
+    const uint64_t sb = snapshot_bytes(p.L);
+    uint32_t max_merged = 1;
+    for (size_t g = 0; g + 1 < ctx->gens.size(); g++) max_merged = std::max(max_merged, ctx->gens[g].second);
+    TRY(ensure(ctx, ctx->snap_a, sb)); TRY(ensure(ctx, ctx->snap_b, sb));
+    TRY(ensure(ctx, ctx->fin, (uint64_t)max_merged * fin_stride_bytes()));
+    uint8_t *cur = ctx->snap_a.as<uint8_t>(), *other = ctx->snap_b.as<uint8_t>();
+    if (launch_snapshot_init(cur, p.L, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "snapshot init launch failed");
+    ctx->stats.kernel_launches++;
+    for (size_t g = 0; g < ctx->gens.size(); g++) {
+        const bool last = g + 1 == ctx->gens.size();
+        p.block_begin = ctx->gens[g].first; p.n_blocks = ctx->gens[g].second;
+        p.snap = cur; p.fin = last ? nullptr : ctx->fin.as<uint8_t>();
+        if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx->stats.kernel_launches++;
+        if (!last) {
+            if (launch_merge(p.blocks, p.block_begin, p.n_blocks, p.L, cur, other, ctx->fin.as<uint8_t>(), p.ws, p.err, ctx->st))
+                return fail(ctx, CBCG_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            ctx->stats.kernel_launches += 6;
+            std::swap(cur, other);
+        }
+    }
     return 0;
 }
 
@@ -429,10 +487,62 @@ static CoderParams coder_params(cbcg_ctx *ctx, uint32_t n_blocks, uint32_t L, in
 static void put32(std::vector<uint8_t> &v, uint32_t x) { for (int i = 0; i < 4; i++) v.push_back((uint8_t)(x >> (8 * i))); }
 static void put64(std::vector<uint8_t> &v, uint64_t x) { for (int i = 0; i < 8; i++) v.push_back((uint8_t)(x >> (8 * i))); }
 
+/* Block index of the container: per block a few delta-coded LEB128 varints ("Container"):
+ *   v0 = zigzag(n_reads - previous n_reads) << 2 | chromosome changed << 1 | generation changed
+ *   [chromosome ordinal]  [generation increment - 1]
+ *   zigzag(second difference of base_pos)  zigzag(difference of n_edits)  zigzag(difference of payload_bytes) */
+struct IndexState { int64_t n_reads, chr, gen, base, d1, edits, payload; };
+static void put_varint(std::vector<uint8_t> &v, uint64_t x) {
+    do { uint8_t c = (uint8_t)(x & 0x7f); x >>= 7; if (x) c |= 0x80; v.push_back(c); } while (x);
+}
+static uint64_t zz(int64_t v) { return ((uint64_t)v << 1) ^ (uint64_t)(v >> 63); }
+static int64_t unzz(uint64_t v) { return (int64_t)(v >> 1) ^ -(int64_t)(v & 1); }
+static void index_put(std::vector<uint8_t> &out, IndexState &st, const BlockDesc &b) {
+    const bool chr_ch = (int64_t)b.chr != st.chr, gen_ch = (int64_t)b.gen != st.gen;
+    put_varint(out, (zz((int64_t)b.n_reads - st.n_reads) << 2) | (chr_ch ? 2u : 0u) | (gen_ch ? 1u : 0u));
+    if (chr_ch) { put_varint(out, b.chr); st.base = 0; st.d1 = 0; }
+    if (gen_ch) put_varint(out, (uint64_t)((int64_t)b.gen - st.gen - 1));
+    const int64_t d1 = (int64_t)b.base_pos - st.base;
+    put_varint(out, zz(d1 - st.d1));
+    put_varint(out, zz((int64_t)b.n_edits - st.edits));
+    put_varint(out, zz((int64_t)b.payload_bytes - st.payload));
+    st.n_reads = b.n_reads; st.chr = b.chr; st.gen = b.gen; st.base = b.base_pos; st.d1 = d1; st.edits = b.n_edits; st.payload = b.payload_bytes;
+}
+static bool get_varint(const uint8_t *p, uint64_t end, uint64_t &o, uint64_t &v) {
+    uint64_t r = 0; int sh = 0;
+    for (;;) {
+        if (o >= end || sh > 63) return false;
+        const uint8_t c = p[o++];
+        r |= (uint64_t)(c & 0x7f) << sh; sh += 7;
+        if (!(c & 0x80)) break;
+    }
+    v = r; return true;
+}
+static bool index_get(const uint8_t *p, uint64_t end, uint64_t &o, IndexState &st, BlockDesc &b) {
+    uint64_t v;
+    if (!get_varint(p, end, o, v)) return false;
+    st.n_reads += unzz(v >> 2);
+    if (v & 2) { uint64_t c; if (!get_varint(p, end, o, c)) return false; st.chr = (int64_t)c; st.base = 0; st.d1 = 0; }
+    if (v & 1) { uint64_t gi; if (!get_varint(p, end, o, gi) || gi > 255) return false; st.gen += (int64_t)gi + 1; }
+    if (!get_varint(p, end, o, v)) return false;
+    st.d1 += unzz(v); st.base += st.d1;
+    if (!get_varint(p, end, o, v)) return false;
+    st.edits += unzz(v);
+    if (!get_varint(p, end, o, v)) return false;
+    st.payload += unzz(v);
+    const int64_t lim = 0xffffffffll;
+    if (st.n_reads < 0 || st.n_reads > lim || st.chr < 0 || st.chr > lim || st.gen < 0 || st.gen > 255 || st.base < 0 || st.base > lim ||
+        st.edits < 0 || st.edits > lim || st.payload < 0 || st.payload > lim) return false;
+    memset(&b, 0, sizeof b);
+    b.n_reads = (uint32_t)st.n_reads; b.chr = (uint32_t)st.chr; b.gen = (uint32_t)st.gen; b.base_pos = (uint32_t)st.base;
+    b.n_edits = (uint32_t)st.edits; b.payload_bytes = (uint32_t)st.payload;
+    return true;
+}
+
 static int validate_opts(cbcg_ctx *ctx, const cbcg_encode_opts *o) {
     if (!o) return fail(ctx, CBCG_ERR_ARG, "NULL options");
     if (o->read_len_header == 0 || o->read_len_header > CBCG_MAX_READ_LEN) return fail(ctx, CBCG_ERR_ARG, "read_len_header must be in 1..%u", CBCG_MAX_READ_LEN);
-    if (o->gen_mode != 0) return fail(ctx, CBCG_ERR_ARG, "gen_mode %u is not supported by this build", o->gen_mode);
+    if (o->gen_mode > 1) return fail(ctx, CBCG_ERR_ARG, "gen_mode %u is not supported by this build", o->gen_mode);
     return 0;
 }
 
@@ -462,8 +572,9 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
             CU(cudaMemsetAsync(ctx->recs.p, 0, sizeof(cbcg_read_rec), ctx->st));
             TRY(reset_words(ctx));
         }
-        TRY(cut_blocks(ctx, opts->block_reads, &nb));
-        const uint64_t ws_cap = coder_ws_bytes_bound(L, n, n_edits, nb, legacy);
+        const bool primed = !legacy && opts->gen_mode == 1;
+        TRY(cut_blocks(ctx, opts->block_reads, opts->gen_mode, &nb));
+        const uint64_t ws_cap = coder_ws_bytes_bound(L, n, n_edits, nb, legacy, primed);
         const uint64_t pay_cap = coder_payload_bound(n, n_edits, nb, legacy);
         TRY(ensure(ctx, ctx->ws, ws_cap));
         TRY(ensure(ctx, ctx->scratch, pay_cap));
@@ -471,16 +582,17 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
         CoderParams p = coder_params(ctx, (uint32_t)nb, L, legacy, 0);
         p.chr = const_cast<uint32_t *>(ctx->db.chr);
         p.payload = ctx->scratch.as<uint8_t>();
+        p.lean = legacy ? 0u : 1u; p.short_flush = legacy ? 0u : 1u; p.primed = primed ? 1u : 0u;
         if (launch_plan(p, (uint32_t)n, n_edits, ws_cap, pay_cap, wptr<uint64_t>(ctx, W_OFF(totals)), ctx->st))
             return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
         CU(cudaEventRecord(ctx->ev[2], ctx->st));
-        if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        TRY(run_coder_generations(ctx, p, nb, primed));
         CU(cudaEventRecord(ctx->ev[3], ctx->st));
         /* compact payload: bounded by the scratch size */
         TRY(ensure(ctx, ctx->payload, pay_cap));
         if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->st))
             return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
-        S.kernel_launches += 4;
+        S.kernel_launches += 3;
         CU(cudaEventRecord(ctx->ev[4], ctx->st));
         CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaMemcpyAsync(&ctx->hw->total_bytes, ctx->out_off.as<uint64_t>() + nb, 8, cudaMemcpyDeviceToHost, ctx->st));
@@ -513,11 +625,11 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
             h.insert(h.end(), s.begin(), s.end());
             for (size_t q = s.size(); q & 3; q++) h.push_back(0);
         }
-        for (uint64_t k = 0; k < nb; k++) {
-            const BlockDesc &b = ctx->hblocks[k];
-            put32(h, b.n_reads); put32(h, b.chr); put32(h, b.base_pos); put32(h, b.n_symbols);
-            put32(h, b.n_edits); put32(h, b.payload_bytes); put32(h, b.gen); put32(h, 0);
-        }
+        std::vector<uint8_t> ix;
+        IndexState st = { (int64_t)opts->block_reads, 0, 0, 0, 0, 0, 0 };
+        for (uint64_t k = 0; k < nb; k++) index_put(ix, st, ctx->hblocks[k]);
+        put32(h, (uint32_t)ix.size());
+        h.insert(h.end(), ix.begin(), ix.end());
     }
     ctx->enc_L = L; ctx->enc_block_reads = opts->block_reads; ctx->enc_gen_mode = opts->gen_mode; ctx->enc_legacy = legacy;
     ctx->enc_max_len = ctx->db.max_len;
@@ -597,7 +709,7 @@ extern "C" int cbcg_extract_symbols(cbcg_ctx *ctx, const cbcg_batch *batch, cons
         CU(cudaMemsetAsync(ctx->recs.p, 0, sizeof(cbcg_read_rec), ctx->st));
         TRY(reset_words(ctx));
     }
-    TRY(cut_blocks(ctx, opts->block_reads, &nb));
+    TRY(cut_blocks(ctx, opts->block_reads, opts->gen_mode, &nb));
     const uint64_t list_cap = 12u * n + 2u * n_edits + nb * 8u + (legacy ? 136u + 2048u : 0u) + 64u;
     TRY(ensure(ctx, ctx->symbols, list_cap * sizeof(cbcg_symbol)));
     TRY(ensure(ctx, ctx->ws, 4096));
@@ -633,7 +745,7 @@ extern "C" int cbcg_extract_symbols(cbcg_ctx *ctx, const cbcg_batch *batch, cons
 struct Container {
     uint32_t max_len, L, n_blocks, n_chr, block_reads, gen_mode;
     uint64_t n_reads;
-    uint64_t index_off, payload_off;
+    uint64_t index_off, index_bytes, payload_off;
     std::vector<uint32_t> chr_map;             /* container ordinal -> genome ordinal */
 };
 static uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -645,7 +757,7 @@ static int parse_container(const uint8_t *in, uint64_t len, const std::vector<st
     if (rd32(in) != CBCG_MAGIC || rd32(in + 4) != CBCG_VERSION) return CBCG_ERR_FORMAT;
     c.max_len = rd32(in + 8); c.L = rd32(in + 12); c.n_reads = rd64(in + 16);
     c.n_blocks = rd32(in + 24); c.n_chr = rd32(in + 28); c.block_reads = rd32(in + 32); c.gen_mode = rd32(in + 36);
-    if (c.L == 0 || c.L > CBCG_MAX_READ_LEN || c.max_len > CBCG_MAX_READ_LEN || c.n_chr > MAX_CHR || c.gen_mode != 0) return CBCG_ERR_FORMAT;
+    if (c.L == 0 || c.L > CBCG_MAX_READ_LEN || c.max_len > CBCG_MAX_READ_LEN || c.n_chr > MAX_CHR || c.gen_mode > 1) return CBCG_ERR_FORMAT;
     if (c.n_reads >= 0xfffffff0ull) return CBCG_ERR_FORMAT;
     uint64_t o = 40;
     c.chr_map.assign(c.n_chr, 0xffffffffu);
@@ -658,9 +770,11 @@ static int parse_container(const uint8_t *in, uint64_t len, const std::vector<st
                 if ((*names)[g].size() == nl && !memcmp((*names)[g].data(), in + o, nl)) c.chr_map[k] = (uint32_t)g;
         o += nl + ((4 - (nl & 3)) & 3);
     }
+    if (o + 4 > len) return CBCG_ERR_FORMAT;
+    c.index_bytes = rd32(in + o); o += 4;
     c.index_off = o;
-    if (o + (uint64_t)c.n_blocks * 32 > len) return CBCG_ERR_FORMAT;
-    c.payload_off = o + (uint64_t)c.n_blocks * 32;
+    if (o + c.index_bytes > len || (uint64_t)c.n_blocks * 4u > c.index_bytes) return CBCG_ERR_FORMAT;   /* >= 4 bytes per entry */
+    c.payload_off = o + c.index_bytes;
     return 0;
 }
 
@@ -677,24 +791,26 @@ extern "C" int cbcg_decoded_size(const uint8_t *in, uint64_t in_len, uint64_t *n
 
 /* K2 decode of ctx->hblocks[0..nb) (n_reads, chr, base_pos, n_edits, payload_bytes filled in) whose payload
  * bytes lie back to back in ctx->payload. Leaves recs / edits / chr_out on the device. */
-static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy, uint64_t reads_cap, uint64_t edits_cap,
+static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy, bool primed, uint64_t reads_cap, uint64_t edits_cap,
                              uint64_t *n_reads_out, uint64_t *n_edits_out) {
     TRY(ensure(ctx, ctx->blocks, (nb + 1) * sizeof(BlockDesc)));
     CU(cudaMemcpyAsync(ctx->blocks.p, ctx->hblocks, nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
     TRY(ensure(ctx, ctx->recs, (reads_cap + 1) * sizeof(cbcg_read_rec)));
     TRY(ensure(ctx, ctx->chr_out, (reads_cap + 1) * 4));
     TRY(ensure(ctx, ctx->edits, (edits_cap + 64) * 2));
-    const uint64_t ws_cap = legacy ? coder_ws_bytes_bound(L ? L : CBCG_MAX_READ_LEN, reads_cap, 0xffffffffull, 1, 1)
-                                   : coder_ws_bytes_bound(L, reads_cap, edits_cap, nb, 0);
+    const uint64_t ws_cap = legacy ? coder_ws_bytes_bound(L ? L : CBCG_MAX_READ_LEN, reads_cap, 0xffffffffull, 1, 1, 0)
+                                   : coder_ws_bytes_bound(L, reads_cap, edits_cap, nb, 0, primed);
     TRY(ensure(ctx, ctx->ws, ws_cap));
     TRY(reset_words(ctx));
     CoderParams p = coder_params(ctx, (uint32_t)nb, L, legacy, 1);
     p.chr = ctx->chr_out.as<uint32_t>();
     p.payload = ctx->payload.as<uint8_t>();
+    p.lean = legacy ? 0u : 1u; p.short_flush = legacy ? 0u : 1u; p.primed = primed ? 1u : 0u;
     if (launch_plan(p, (uint32_t)reads_cap, edits_cap, ws_cap, ~0ull, wptr<uint64_t>(ctx, W_OFF(totals)), ctx->st))
         return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
-    if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 (decode) launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    ctx->stats.kernel_launches += 2;
+    ctx->stats.kernel_launches++;
+    if (legacy) { ctx->gens.clear(); ctx->gens.push_back({ 0u, 1u }); }
+    TRY(run_coder_generations(ctx, p, nb, primed));
     CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
     TRY(fetch_words(ctx));
     TRY(device_error(ctx, "block decoder"));
@@ -723,18 +839,21 @@ static int blocks_from_index(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
                              uint64_t *reads_total, uint64_t *edits_total, uint64_t *payload_total) {
     TRY(ensure_hblocks(ctx, (size_t)c.n_blocks + 1));
     uint64_t nr = 0, ne = 0, pb = 0;
+    IndexState st = { (int64_t)c.block_reads, 0, 0, 0, 0, 0, 0 };
+    uint64_t o = c.index_off;
+    uint32_t prev_gen = 0;
     for (uint32_t k = 0; k < c.n_blocks; k++) {
-        const uint8_t *e = in + c.index_off + (uint64_t)k * 32;
         BlockDesc &b = ctx->hblocks[k];
-        memset(&b, 0, sizeof b);
-        b.n_reads = rd32(e); const uint32_t chr = rd32(e + 4); b.base_pos = rd32(e + 8); b.n_symbols = rd32(e + 12);
-        b.n_edits = rd32(e + 16); b.payload_bytes = rd32(e + 20); b.gen = rd32(e + 24);
+        if (!index_get(in, c.index_off + c.index_bytes, o, st, b)) return fail(ctx, CBCG_ERR_FORMAT, "block index entry %u malformed", k);
+        const uint32_t chr = b.chr;
         if (chr >= c.n_chr) return fail(ctx, CBCG_ERR_FORMAT, "block %u names chromosome %u of %u", k, chr, c.n_chr);
         if (c.chr_map[chr] == 0xffffffffu) return fail(ctx, CBCG_ERR_NO_REFERENCE, "block %u: chromosome not in the loaded reference", k);
-        if (b.gen != 0) return fail(ctx, CBCG_ERR_FORMAT, "block %u: unsupported generation %u", k, b.gen);
+        if (b.gen < prev_gen || (c.gen_mode == 0 && b.gen != 0)) return fail(ctx, CBCG_ERR_FORMAT, "block %u: bad generation %u", k, b.gen);
+        prev_gen = b.gen;
         b.chr = c.chr_map[chr];
         nr += b.n_reads; ne += b.n_edits; pb += b.payload_bytes;
     }
+    gens_from_blocks(ctx, c.n_blocks);
     if (nr != c.n_reads) return fail(ctx, CBCG_ERR_FORMAT, "index holds %llu reads, header says %llu", (unsigned long long)nr, (unsigned long long)c.n_reads);
     if (c.payload_off + pb > in_len) return fail(ctx, CBCG_ERR_FORMAT, "payload truncated");
     *reads_total = nr; *edits_total = ne; *payload_total = pb;
@@ -763,7 +882,7 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
         if (pb) CU(cudaMemcpyAsync(ctx->payload.p, in + c.payload_off, pb, cudaMemcpyHostToDevice, ctx->st));
         S.h2d_bytes = pb + (uint64_t)c.n_blocks * sizeof(BlockDesc);
         CU(cudaEventRecord(ctx->ev[1], ctx->st));
-        TRY(run_decode_blocks(ctx, c.n_blocks, c.L, 0, nr, ne, n_reads, n_edits));
+        TRY(run_decode_blocks(ctx, c.n_blocks, c.L, 0, c.gen_mode == 1, nr, ne, n_reads, n_edits));
         S.n_blocks = c.n_blocks;
     } else {
         if (!in || in_len < 4) return fail(ctx, CBCG_ERR_FORMAT, "legacy stream too short");
@@ -781,7 +900,7 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
             b.n_reads = (uint32_t)std::min<uint64_t>(reads_cap, 0xfffffff0ull);
             b.n_edits = (uint32_t)std::min<uint64_t>(reads_cap * 4, 0xfffffff0ull);
             b.payload_bytes = (uint32_t)in_len;
-            int rc = run_decode_blocks(ctx, 1, 0, 1, b.n_reads, b.n_edits, n_reads, n_edits);
+            int rc = run_decode_blocks(ctx, 1, 0, 1, false, b.n_reads, b.n_edits, n_reads, n_edits);
             if (rc == CBCG_ERR_CAPACITY && reads_cap < (1ull << 31)) { reads_cap *= 4; continue; }
             if (rc) return rc;
             break;
@@ -861,7 +980,9 @@ extern "C" int cbcg_decode_resident(cbcg_ctx *ctx) {
     uint64_t nr = 0, ne = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->st));
     if (legacy) { ctx->hblocks[0].n_reads = (uint32_t)ctx->enc_n_reads + 1u; ctx->hblocks[0].n_edits = (uint32_t)ctx->enc_n_edits + 64u; }
-    TRY(run_decode_blocks(ctx, nb, legacy ? 0u : ctx->enc_L, legacy, legacy ? ctx->enc_n_reads + 1u : ctx->enc_n_reads,
+    gens_from_blocks(ctx, nb);
+    TRY(run_decode_blocks(ctx, nb, legacy ? 0u : ctx->enc_L, legacy, !legacy && ctx->enc_gen_mode == 1,
+                          legacy ? ctx->enc_n_reads + 1u : ctx->enc_n_reads,
                           legacy ? ctx->enc_n_edits + 64u : ctx->enc_n_edits, &nr, &ne));
     CU(cudaEventRecord(ctx->ev[1], ctx->st));
     if (nr) {

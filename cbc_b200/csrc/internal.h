@@ -46,10 +46,15 @@ struct BlockDesc {
                                               encoder: offset of its scratch output region */
     uint64_t ws_off;                       /* offset of its model workspace (bytes) */
     uint64_t sym_off;                      /* symbol-list mode: first entry of its list */
+    uint32_t pos_card;                     /* primed blocks, out: final POS alphabet size */
+    uint32_t n_rows;                       /*   var rows created */
+    uint32_t pa_touched;                   /*   pos_alpha models instantiated */
+    uint32_t pad;
 };
 
 /* Coder launch parameters. */
 struct CoderParams {
+    uint32_t block_begin;                  /* this launch codes blocks [block_begin, block_begin + n_blocks) */
     uint32_t n_blocks;
     uint32_t L;                            /* header read length = alphabet of snps / indels / var */
     uint32_t legacy;                       /* 1: single block in the reference's own stream layout */
@@ -64,6 +69,12 @@ struct CoderParams {
     cbcg_symbol *symbols;                  /* list mode */
     const uint8_t *chr_names;              /* legacy: NUL-terminated names, MAX_NAME bytes each */
     unsigned long long *err;
+    uint32_t lean;                         /* blocked containers: same_ref and length bytes 1..3 are not coded */
+    uint32_t short_flush;                  /* blocked containers: 1 + scale3 closing bits instead of the reference's 26+ */
+    uint32_t primed;                       /* gen_mode 1: models start from `snap` instead of the initial state */
+    uint32_t pad;
+    const uint8_t *snap;                   /* snapshot S_{g-1} (snapshot_bytes(L) bytes) */
+    uint8_t *fin;                          /* per block of this launch: final small-model image (NULL: not merged) */
 };
 #define MAX_NAME 256u
 
@@ -82,5 +93,11 @@ int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_t
 int launch_coder(const CoderParams &p, cudaStream_t st);
 int launch_gather(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
                   uint64_t *out_off, cudaStream_t st);
-uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy);
+uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy, int primed);
+/* generation snapshots (gen_mode 1) */
+uint64_t snapshot_bytes(uint32_t L);
+uint64_t fin_stride_bytes(void);
+int launch_snapshot_init(uint8_t *snap, uint32_t L, cudaStream_t st);
+int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_blocks, uint32_t L, const uint8_t *prev,
+                 uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, cudaStream_t st);
 uint64_t coder_payload_bound(uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy);

@@ -58,11 +58,11 @@ struct WsLayout {
 
 __host__ __device__ inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 32; while (p < x) p <<= 1; return p; }
 
-__host__ __device__ inline WsLayout ws_layout(uint32_t L, uint64_t n_reads, uint64_t n_edits, int legacy) {
+__host__ __device__ inline WsLayout ws_layout(uint32_t L, uint64_t n_reads, uint64_t n_edits, int legacy, int primed) {
     WsLayout w;
     w.Lp = (L + 1u + 31u) & ~31u;
-    w.pos_cap = (uint32_t)(n_reads + 34u);
-    w.direct = (legacy || n_edits >= VAR_DIRECT_MIN_EDITS) ? 1u : 0u;
+    w.pos_cap = (uint32_t)(n_reads + 34u) + (primed ? CBCG_SNAP_POS_MAX : 0u);
+    w.direct = (!primed && (legacy || n_edits >= VAR_DIRECT_MIN_EDITS)) ? 1u : 0u;
     w.rows_cap = w.direct ? CBCG_VAR_CONTEXTS : (uint32_t)n_edits;
     w.hash_cap = w.direct ? 1024u : pow2_ceil((uint32_t)(2u * n_edits + 2u));   /* u64 slots */
     uint64_t o = 0;                                                            /* in bytes, 16-aligned pieces */
@@ -86,15 +86,15 @@ __host__ __device__ inline uint64_t symlist_cap(uint64_t n_reads, uint64_t n_edi
     return 12u * n_reads + 2u * n_edits + (legacy ? 136u + 2048u : 0u) + 8u;
 }
 
-uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy) {
-    if (legacy) return ws_layout(L, n_reads, n_edits, 1).total + 256;
+uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy, int primed) {
+    if (legacy) return ws_layout(L, n_reads, n_edits, 1, 0).total + 256;
     const uint64_t Lp = (L + 1u + 31u) & ~31u;
     /* per block: pos 2 x (n+34) x 4 (+32), pos_alpha 4128, hash <= max(32, 4 n_edits + 4) x 8, rows n_edits x Lp x 4;
        a block in direct mode replaces hash + rows by 8 KB + 65535 rows: bounded by its own n_edits >= 32768 rows. */
     uint64_t b = n_blocks * (2u * (34u * 4u + 16u) + 4u * 257u * 4u + 16u + 32u * 8u + 8192u + 512u);
     b += n_reads * 8u + n_edits * 32u + n_edits * Lp * 4u;
-    b += (n_edits / VAR_DIRECT_MIN_EDITS + 1u) * 0;          /* direct blocks use <= 2 x their hashed size */
-    return 2u * b + 4096u;
+    if (primed) b += n_blocks * (uint64_t)CBCG_SNAP_POS_MAX * 8u;
+    return 2u * b + 4096u;                                   /* direct blocks use <= 2 x their hashed size */
 }
 uint64_t coder_payload_bound(uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy) {
     return payload_cap_bytes(n_reads, n_edits, legacy) + n_blocks * 96u;
@@ -114,6 +114,42 @@ struct WarpModels {
     uint32_t flag_cnt[FLAG_CAP];
     uint32_t flag_used, flag_n;
     uint16_t cumdel[256];          /* decoder: cumulative deletion offsets of the current read */
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * generation snapshot (gen_mode 1): the state every block of the next generation starts from. */
+struct SnapLayout { uint64_t small, pos_hdr, pos_val, pos_cnt, pos_alpha, bitmap, flag_prev, flag_acc, var, total; uint32_t Lp; };
+__host__ __device__ inline SnapLayout snap_layout(uint32_t L) {
+    SnapLayout s; uint64_t o = 0;
+    s.Lp = (L + 1u + 31u) & ~31u;
+    s.small = o;     o += (sizeof(WarpModels) + 15u) & ~15ull;
+    s.pos_hdr = o;   o += 16u;                                         /* card, n */
+    s.pos_val = o;   o += (uint64_t)(CBCG_SNAP_POS_MAX + 32u) * 4u;
+    s.pos_cnt = o;   o += (uint64_t)(CBCG_SNAP_POS_MAX + 32u) * 4u;
+    s.pos_alpha = o; o += 4u * 257u * 4u + 16u;
+    s.bitmap = o;    o += 2048u * 4u;
+    s.flag_prev = o; o += 65536u * 4u;                                 /* merge scratch: dense FLAG counts */
+    s.flag_acc = o;  o += 65536u * 4u;
+    s.var = o;       o += (uint64_t)CBCG_VAR_CONTEXTS * s.Lp * 4u;
+    s.total = (o + 255u) & ~255ull;
+    return s;
+}
+uint64_t snapshot_bytes(uint32_t L) { return snap_layout(L).total; }
+uint64_t fin_stride_bytes(void) { return (sizeof(WarpModels) + 15u) & ~15ull; }
+
+__device__ __forceinline__ uint64_t fin_stride_dev() { return (sizeof(WarpModels) + 15u) & ~15ull; }
+
+struct SnapView {
+    const uint32_t *small, *pos_hdr, *pos_val, *pos_cnt, *pos_alpha, *bitmap, *var;
+    uint32_t Lp;
+    __host__ __device__ SnapView() {}
+    __host__ __device__ SnapView(const uint8_t *base, uint32_t L) {
+        const SnapLayout l = snap_layout(L);
+        small = (const uint32_t *)(base + l.small); pos_hdr = (const uint32_t *)(base + l.pos_hdr);
+        pos_val = (const uint32_t *)(base + l.pos_val); pos_cnt = (const uint32_t *)(base + l.pos_cnt);
+        pos_alpha = (const uint32_t *)(base + l.pos_alpha); bitmap = (const uint32_t *)(base + l.bitmap);
+        var = (const uint32_t *)(base + l.var); Lp = l.Lp;
+    }
 };
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -147,6 +183,8 @@ struct Coder {
     uint32_t *var_bitmap;
     /* legacy-only */
     uint32_t *codebook, *rname;
+    /* primed blocks */
+    bool primed, lean; SnapView snap;
     /* SNP-site ring: word (p >> 5) & 31 lives in lane; covers [ring_base, ring_base + 1024) */
     uint32_t ring; uint32_t ring_word;     /* ring_word = ring_base >> 5 */
 
@@ -170,16 +208,18 @@ struct Coder {
         if (count) put_bits(pat >> (32u - count), count);
     }
     /* stream_finish_byte (:189-194): the byte in progress always goes out, even an empty one */
-    __device__ __forceinline__ void finish_bits() {
+    __device__ __forceinline__ void finish_bits(bool always_last = true) {
         uint32_t full = nacc >> 3, rem = nacc & 7u;
         for (uint32_t i = 0; i < full; i++) {
             uint32_t byte = (uint32_t)(acc >> (nacc - 8u * (i + 1u))) & 0xffu;
             if (out_pos < out_cap) { if (lane == 0) out[out_pos] = (uint8_t)byte; } else err = CBCG_ERR_CAPACITY;
             out_pos++;
         }
-        uint32_t last = rem ? (((uint32_t)acc & ((1u << rem) - 1u)) << (8u - rem)) : 0u;
-        if (out_pos < out_cap) { if (lane == 0) out[out_pos] = (uint8_t)last; } else err = CBCG_ERR_CAPACITY;
-        out_pos++;
+        if (rem || always_last) {
+            uint32_t last = rem ? (((uint32_t)acc & ((1u << rem) - 1u)) << (8u - rem)) : 0u;
+            if (out_pos < out_cap) { if (lane == 0) out[out_pos] = (uint8_t)last; } else err = CBCG_ERR_CAPACITY;
+            out_pos++;
+        }
         nacc = 0; acc = 0;
     }
     /* next k bits of the input, first bit most significant; zeros past the end (the reference's
@@ -232,6 +272,14 @@ struct Coder {
         if (scale3 > 0) { put_run(msb ^ 1u, (uint32_t)scale3); scale3 = 0; }
         put_bits(a.l & CBCG_AC_LOWMASK, CBCG_AC_BITS - 1u);
         finish_bits();
+    }
+
+    /* Blocked containers: after renormalisation l < 2^25 <= u, so the value 2^25 -- "1", the pending E3 bits as
+       "0", zeros ever after -- lies in [l, u]; the decoder reads zeros past the end of a block. */
+    __device__ __forceinline__ void ac_flush_short() {
+        put_bits(1u, 1u);
+        if (scale3 > 0) { put_run(0u, (uint32_t)scale3); scale3 = 0; }
+        finish_bits(false);
     }
 
     /* one coder step given the symbol's interval; decode: caller found (lo, cnt) from the target */
@@ -426,7 +474,8 @@ struct Coder {
     }
     __device__ __forceinline__ void pa_ensure() {
         if (!pa_init) {
-            for (uint32_t k = 0; k < 4u; k++) dense_init_ones(pos_alpha + k * 257u, 256u);
+            if (primed) { for (uint32_t i = lane; i < 4u * 257u; i += 32u) pos_alpha[i] = snap.pos_alpha[i]; }
+            else for (uint32_t k = 0; k < 4u; k++) dense_init_ones(pos_alpha + k * 257u, 256u);
             pa_init = true;
             __syncwarp();
         }
@@ -518,7 +567,10 @@ struct Coder {
                 const uint32_t r = n_rows++;
                 uint32_t *row = var_rows + (uint64_t)r * Lp;
                 if (lane == el) var_hash[idx] = ((uint64_t)key << 32) | r;
-                dense_init_ones(row, L);
+                if (primed && ((snap.bitmap[ctx >> 5] >> (ctx & 31u)) & 1u)) {       /* copy on first touch */
+                    const uint32_t *src = snap.var + (uint64_t)ctx * Lp;
+                    for (uint32_t i = lane; i <= L; i += 32u) row[i] = src[i];
+                } else dense_init_ones(row, L);
                 __syncwarp();
                 return row;
             }
@@ -598,6 +650,18 @@ struct Coder {
         dense_init_ones(M->indels, L);
         __syncwarp();
     }
+    __device__ __forceinline__ void init_from_snapshot() {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(M);
+        for (uint32_t i = lane; i < (uint32_t)(sizeof(WarpModels) / 4u); i += 32u) dst[i] = snap.small[i];
+        pos_card = snap.pos_hdr[0]; pos_n = snap.pos_hdr[1];
+        pos_rv = (lane < pos_card) ? snap.pos_val[lane] : 0u;
+        pos_rc = (lane < pos_card) ? snap.pos_cnt[lane] : 0u;
+        for (uint32_t i = 32u + lane; i < pos_card; i += 32u) { pos_gval[i] = snap.pos_val[i]; pos_gcnt[i] = snap.pos_cnt[i]; }
+        pa_init = false;
+        n_rows = 0;
+        for (uint32_t i = lane; i <= hash_mask; i += 32u) var_hash[i] = 0ull;
+        __syncwarp();
+    }
     __device__ __forceinline__ void init_models(bool legacy) {
         if (MODE == MODE_LIST) return;
         dense_init_ones(M->rlen0, 255u);
@@ -644,7 +708,7 @@ __device__ __forceinline__ void code_read(Coder<MODE> &C, ReadState<MODE> &st, c
     const uint32_t lane = C.lane;
     /* length: byte 0 carries it, bytes 1..3 are always 0 (:29-33) */
     uint32_t len = C.sym(CBCG_S_RLENGTH, 0u, rec.len & 0xffu);
-    for (uint32_t k = 1; k < 4u; k++) len |= C.sym(CBCG_S_RLENGTH, k, 0u) << (8u * k);
+    if (!C.lean || MODE == MODE_LIST) for (uint32_t k = 1; k < 4u; k++) len |= C.sym(CBCG_S_RLENGTH, k, 0u) << (8u * k);
     if (C.err) return;
     if (MODE != MODE_DEC) len = rec.len;
     /* position (:113-159) */
@@ -745,20 +809,24 @@ __global__ void __launch_bounds__(K2_THREADS)
 k2_coder_kernel(CoderParams P) {
     __shared__ WarpModels smodels[K2_WARPS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t b = blockIdx.x * K2_WARPS + warp;
-    if (b >= P.n_blocks) return;
+    const uint32_t bl = blockIdx.x * K2_WARPS + warp;
+    if (bl >= P.n_blocks) return;
+    const uint32_t b = P.block_begin + bl;
     BlockDesc &B = P.blocks[b];
     const bool legacy = P.legacy != 0;
+    const bool primed = P.primed != 0 && MODE != MODE_LIST;
 
     Coder<MODE> C;
     C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &smodels[warp];
+    C.primed = primed; C.lean = P.lean != 0;
+    if (primed) C.snap = SnapView(P.snap, P.L);
     C.L = P.L; C.Lp = (P.L + 1u + 31u) & ~31u;
     /* workspace */
     const uint64_t ws_edits = (MODE == MODE_DEC && legacy) ? 0xffffffffull : B.n_edits;
     const uint64_t ws_reads = B.n_reads;
     uint32_t decode_L = P.L;
     {
-        const WsLayout w = ws_layout(P.L ? P.L : 252u, ws_reads, ws_edits, legacy);
+        const WsLayout w = ws_layout(P.L ? P.L : 252u, ws_reads, ws_edits, legacy, primed);
         uint8_t *base = P.ws + B.ws_off;
         C.pos_gcnt = reinterpret_cast<uint32_t *>(base + w.pos_cnt);
         C.pos_gval = reinterpret_cast<uint32_t *>(base + w.pos_val);
@@ -774,7 +842,7 @@ k2_coder_kernel(CoderParams P) {
     C.out = P.payload + B.payload_off; C.out_cap = (uint32_t)payload_cap_bytes(B.n_reads, B.n_edits, legacy);
     C.in = P.payload + B.payload_off; C.in_len = B.payload_bytes;
     C.list = P.symbols + B.sym_off; C.list_n = 0; C.list_cap = (uint32_t)symlist_cap(B.n_reads, B.n_edits, legacy);
-    C.init_models(legacy);
+    if (primed) C.init_from_snapshot(); else C.init_models(legacy);
     C.ring_reset();
     if (MODE != MODE_LIST) C.ac_init();
 
@@ -795,7 +863,7 @@ k2_coder_kernel(CoderParams P) {
             else { C.L = Lh; decode_L = Lh; }
         }
     } else if (MODE == MODE_DEC && B.chr >= P.genome.n_chr) C.err = CBCG_ERR_NO_REFERENCE;
-    if (MODE != MODE_LIST && !C.err) C.init_L_models();
+    if (MODE != MODE_LIST && !C.err && !primed) C.init_L_models();
 
     const uint64_t r0 = B.first_read;
     uint64_t e_cursor = B.edit_base;
@@ -849,8 +917,10 @@ k2_coder_kernel(CoderParams P) {
             }
         } else {
             if (MODE != MODE_DEC && chr != cur_chr) { C.err = CBCG_ERR_INTERNAL; break; }   /* blocks never span chromosomes */
-            const uint32_t same = C.sym(CBCG_S_SAME_REF, 0u, 0u);
-            if (MODE == MODE_DEC && same != 0u) { C.err = CBCG_ERR_CORRUPT; break; }
+            if (!C.lean || MODE == MODE_LIST) {
+                const uint32_t same = C.sym(CBCG_S_SAME_REF, 0u, 0u);
+                if (MODE == MODE_DEC && same != 0u) { C.err = CBCG_ERR_CORRUPT; break; }
+            }
         }
         if (C.err) break;
 
@@ -873,7 +943,7 @@ k2_coder_kernel(CoderParams P) {
             C.sym(CBCG_S_RNAME, prev_char, '\n'); prev_char = '\n';
             C.sym(CBCG_S_RNAME, prev_char, 0u);
         }
-        if (!C.err) C.ac_flush();
+        if (!C.err) { if (P.short_flush && !legacy) C.ac_flush_short(); else C.ac_flush(); }
     }
     if (MODE == MODE_LIST && legacy && !C.err) {
         C.sym(CBCG_S_SAME_REF, 0u, 1u);
@@ -881,6 +951,14 @@ k2_coder_kernel(CoderParams P) {
         C.sym(CBCG_S_RNAME, '\n', 0u);
     }
     if (C.err) dev_set_error(P.err, C.err, ((uint64_t)b << 20) | (n_done & 0xfffffu));
+    if (primed && P.fin && !C.err) {                     /* final state for the generation merge */
+        __syncwarp();
+        uint32_t *dst = reinterpret_cast<uint32_t *>(P.fin + (uint64_t)bl * fin_stride_dev());
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(C.M);
+        for (uint32_t i = lane; i < (uint32_t)(sizeof(WarpModels) / 4u); i += 32u) dst[i] = src[i];
+        if (lane < C.pos_card) { C.pos_gval[lane] = C.pos_rv; C.pos_gcnt[lane] = C.pos_rc; }
+        if (lane == 0) { B.pos_card = C.pos_card; B.n_rows = C.n_rows; B.pa_touched = C.pa_init ? 1u : 0u; }
+    }
     if (lane == 0) {
         B.n_symbols = (MODE == MODE_LIST) ? C.list_n : C.n_symbols;
         if (MODE == MODE_ENC) B.payload_bytes = C.out_pos;
@@ -925,7 +1003,7 @@ k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, ui
                 if (!P.legacy) d.base_pos = P.recs[d.first_read].pos;
             }
             const uint64_t ws_edits = (dec && P.legacy) ? 0xffffffffull : d.n_edits;
-            v[0] = ws_layout(P.L ? P.L : 252u, d.n_reads, ws_edits, P.legacy).total;
+            v[0] = ws_layout(P.L ? P.L : 252u, d.n_reads, ws_edits, P.legacy, P.primed && P.mode != MODE_LIST).total;
             v[1] = dec ? d.payload_bytes : payload_cap_bytes(d.n_reads, d.n_edits, P.legacy);
             v[2] = (P.mode == MODE_LIST) ? symlist_cap(d.n_reads, d.n_edits, P.legacy) : 0;
             v[3] = d.n_reads; v[4] = d.n_edits;
@@ -1017,5 +1095,299 @@ int launch_gather(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scr
     k2_payload_scan_kernel<<<1, PLAN_THREADS, 0, st>>>(blocks, n_blocks, out_off);
     unsigned grid = n_blocks < 148u * 8u ? n_blocks : 148u * 8u;
     k2_gather_kernel<<<grid, 128, 0, st>>>(blocks, n_blocks, scratch, out, out_off);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+/* ================================================================================================
+ * Generation snapshots (gen_mode 1). S_g = S_{g-1} + sum over the blocks b of generation g of
+ * (final state of b - S_{g-1}), count by count (wrapping 32-bit sums, read back as signed), clamped to
+ * >= 1 (>= 0 where the snapshot held 0) and rescaled like update_model (src/stream_model.c:38-49).
+ * The decoder runs the same kernels on the blocks it has decoded. `next` arrives as a byte copy of `prev`. */
+
+__global__ void __launch_bounds__(32) snapshot_init_kernel(uint8_t *snap, uint32_t L) {
+    __shared__ WarpModels M;
+    const SnapLayout l = snap_layout(L);
+    const uint32_t lane = threadIdx.x;
+    Coder<MODE_ENC> C;                                     /* borrow the initial-state code of the block coder */
+    C.lane = lane; C.M = &M; C.L = L; C.var_direct = false; C.hash_mask = 0; C.err = 0;
+    __shared__ uint64_t dummy_hash[32];                     /* init_models clears the block's hash table */
+    C.var_hash = dummy_hash; C.hash_mask = 31u;
+    C.init_models(false);
+    C.init_L_models();
+    for (uint32_t i = lane; i < 256u; i += 32u) M.cumdel[i] = 0;
+    __syncwarp();
+    uint32_t *small = reinterpret_cast<uint32_t *>(snap + l.small);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&M);
+    for (uint32_t i = lane; i < (uint32_t)(sizeof(WarpModels) / 4u); i += 32u) small[i] = src[i];
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(snap + l.pos_hdr);
+    uint32_t *pv = reinterpret_cast<uint32_t *>(snap + l.pos_val), *pc = reinterpret_cast<uint32_t *>(snap + l.pos_cnt);
+    if (lane == 0) { hdr[0] = 1u; hdr[1] = 1u; hdr[2] = 0u; hdr[3] = 0u; pv[0] = 0u; pc[0] = 1u; }   /* escape only (sam_models.c:132-162) */
+    uint32_t *pa = reinterpret_cast<uint32_t *>(snap + l.pos_alpha);
+    for (uint32_t k = 0; k < 4u; k++) { for (uint32_t i = lane; i < 256u; i += 32u) pa[k * 257u + i] = 1u; if (lane == 0) pa[k * 257u + 256u] = 256u; }
+    uint32_t *bm = reinterpret_cast<uint32_t *>(snap + l.bitmap);
+    for (uint32_t i = lane; i < 2048u; i += 32u) bm[i] = 0u;
+}
+
+int launch_snapshot_init(uint8_t *snap, uint32_t L, cudaStream_t st) {
+    snapshot_init_kernel<<<1, 32, 0, st>>>(snap, L);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+struct MergeParams {
+    const BlockDesc *blocks; uint32_t block_begin, n_blocks, L;
+    const uint8_t *prev; uint8_t *next; const uint8_t *fin; const uint8_t *ws;
+    unsigned long long *err;
+};
+
+/* One dense model by one warp. fin(b) -> the block's counts, or NULL when the block never touched the model. */
+template <class Fin>
+__device__ __forceinline__ void merge_dense(uint32_t lane, const uint32_t *prev_m, uint32_t *next_m, uint32_t card,
+                                            uint32_t implicit_ones, uint32_t n_blocks, Fin fin) {
+    uint32_t nsum = 0;
+    for (uint32_t i0 = 0; i0 < card; i0 += 32u) {
+        const uint32_t i = i0 + lane;
+        uint32_t p = 0, acc = 0;
+        if (i < card) { p = prev_m[i]; acc = p; }
+        for (uint32_t b = 0; b < n_blocks; b++) {
+            const uint32_t *f = fin(b);
+            if (f && i < card) acc += f[i] - p;
+        }
+        if (i < card) {
+            int32_t v = (int32_t)acc; const int32_t fl = p == 0u ? 0 : 1;
+            if (v < fl) v = fl;
+            next_m[i] = (uint32_t)v; nsum += (uint32_t)v;
+        }
+    }
+    __syncwarp();
+    uint32_t n = warp_sum(nsum) + implicit_ones;
+    while (n >= CBCG_RESCALE) {
+        uint32_t s = 0;
+        for (uint32_t i = lane; i < card; i += 32u) { const uint32_t c = (next_m[i] >> 1) + 1u; next_m[i] = c; s += c; }
+        n = warp_sum(s) + implicit_ones;
+    }
+    if (lane == 0) next_m[card] = n;
+    __syncwarp();
+}
+
+#define MERGE_SMALL_WARPS 21u
+__global__ void __launch_bounds__(MERGE_SMALL_WARPS * 32u) merge_small_kernel(MergeParams P) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const SnapLayout l = snap_layout(P.L);
+    const uint32_t *ps = reinterpret_cast<const uint32_t *>(P.prev + l.small);
+    uint32_t *ns = reinterpret_cast<uint32_t *>(P.next + l.small);
+    const uint64_t stride = fin_stride_dev();
+    uint32_t off = 0, card = 0, ones = 0;
+    if (warp == 0)       { off = offsetof(WarpModels, snps) / 4u;   card = P.L; }
+    else if (warp == 1)  { off = offsetof(WarpModels, indels) / 4u; card = P.L; }
+    else if (warp == 2)  { off = offsetof(WarpModels, rlen0) / 4u;  card = 255u; }
+    else if (warp < 9)   { off = offsetof(WarpModels, chars) / 4u + (warp - 3u) * 8u; card = 5u; }
+    else if (warp < 13)  { off = offsetof(WarpModels, match) / 4u + (warp - 9u) * 4u; card = 2u; }
+    else if (warp == 13) { off = offsetof(WarpModels, same_ref) / 4u; card = 2u; }
+    else if (warp < 17)  { off = offsetof(WarpModels, rlenk) / 4u + (warp - 14u) * 2u; card = 1u; ones = 254u; }
+    if (warp < 17) {
+        const uint8_t *fin = P.fin;
+        merge_dense(lane, ps + off, ns + off, card, ones, P.n_blocks,
+                    [=](uint32_t b) { return reinterpret_cast<const uint32_t *>(fin + (uint64_t)b * stride) + off; });
+    } else {                                              /* pos_alpha[k]: lives in each block's workspace, if instantiated */
+        const uint32_t k = warp - 17u;
+        const uint32_t *pa_prev = reinterpret_cast<const uint32_t *>(P.prev + l.pos_alpha) + k * 257u;
+        uint32_t *pa_next = reinterpret_cast<uint32_t *>(P.next + l.pos_alpha) + k * 257u;
+        const BlockDesc *blocks = P.blocks + P.block_begin; const uint8_t *ws = P.ws; const uint32_t L = P.L;
+        merge_dense(lane, pa_prev, pa_next, 256u, 0u, P.n_blocks, [=](uint32_t b) -> const uint32_t * {
+            const BlockDesc &B = blocks[b];
+            if (!B.pa_touched) return nullptr;
+            const WsLayout w = ws_layout(L, B.n_reads, B.n_edits, 0, 1);
+            return reinterpret_cast<const uint32_t *>(ws + B.ws_off + w.pos_alpha) + k * 257u;
+        });
+    }
+}
+
+/* FLAG: dense 65 536-entry accumulation in global scratch, then back to the sorted sparse form. */
+__global__ void __launch_bounds__(1024) merge_flag_kernel(MergeParams P) {
+    __shared__ uint32_t red[32];
+    __shared__ uint32_t scan[1024];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const SnapLayout l = snap_layout(P.L);
+    const WarpModels *pm = reinterpret_cast<const WarpModels *>(P.prev + l.small);
+    WarpModels *nm = reinterpret_cast<WarpModels *>(P.next + l.small);
+    uint32_t *dprev = reinterpret_cast<uint32_t *>(P.next + l.flag_prev), *dacc = reinterpret_cast<uint32_t *>(P.next + l.flag_acc);
+    for (uint32_t i = tid; i < 65536u; i += 1024u) { dprev[i] = 1u; dacc[i] = 1u; }
+    __syncthreads();
+    if (tid < pm->flag_used) { const uint32_t k = pm->flag_key[tid], c = pm->flag_cnt[tid]; dprev[k] = c; dacc[k] = c; }
+    __syncthreads();
+    const uint64_t stride = fin_stride_dev();
+    for (uint32_t b = 0; b < P.n_blocks; b++) {
+        const WarpModels *fm = reinterpret_cast<const WarpModels *>(P.fin + (uint64_t)b * stride);
+        if (tid < fm->flag_used) { const uint32_t k = fm->flag_key[tid] & 0xffffu; dacc[k] += fm->flag_cnt[tid] - dprev[k]; }
+        __syncthreads();
+    }
+    /* clamp, total, rescale */
+    uint32_t n;
+    {
+        uint32_t s = 0;
+        for (uint32_t i = tid; i < 65536u; i += 1024u) { int32_t v = (int32_t)dacc[i]; if (v < 1) v = 1; dacc[i] = (uint32_t)v; s += (uint32_t)v; }
+        s = warp_sum(s); if (lane == 0) red[warp] = s; __syncthreads();
+        n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
+        __syncthreads();
+    }
+    while (n >= CBCG_RESCALE) {
+        uint32_t s = 0;
+        for (uint32_t i = tid; i < 65536u; i += 1024u) { const uint32_t c = (dacc[i] >> 1) + 1u; dacc[i] = c; s += c; }
+        s = warp_sum(s); if (lane == 0) red[warp] = s; __syncthreads();
+        n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
+        __syncthreads();
+    }
+    /* ordered compaction of the values whose count is not 1: thread t owns values [64 t, 64 t + 64) */
+    uint32_t mine = 0;
+    for (uint32_t i = 0; i < 64u; i++) mine += dacc[tid * 64u + i] != 1u;
+    scan[tid] = mine; __syncthreads();
+    for (uint32_t o = 1; o < 1024u; o <<= 1) { uint32_t v = tid >= o ? scan[tid - o] : 0u; __syncthreads(); scan[tid] += v; __syncthreads(); }
+    const uint32_t total = scan[1023];
+    uint32_t at = scan[tid] - mine;
+    if (total > FLAG_CAP) { if (tid == 0) dev_set_error(P.err, CBCG_ERR_LIMIT, total); }
+    else for (uint32_t i = 0; i < 64u; i++) { const uint32_t c = dacc[tid * 64u + i]; if (c != 1u) { nm->flag_key[at] = tid * 64u + i; nm->flag_cnt[at] = c; at++; } }
+    if (tid == 0) { nm->flag_used = total > FLAG_CAP ? 0u : total; nm->flag_n = n; }
+}
+
+/* POS: slots below the snapshot's alphabet size are the same value in every block; new values are
+ * appended in block order, then order of appearance (one warp, blocks in sequence). */
+__global__ void __launch_bounds__(32) merge_pos_kernel(MergeParams P) {
+    const uint32_t lane = threadIdx.x;
+    const SnapLayout l = snap_layout(P.L);
+    const uint32_t *phdr = reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr);
+    const uint32_t *pcnt = reinterpret_cast<const uint32_t *>(P.prev + l.pos_cnt);
+    uint32_t *nhdr = reinterpret_cast<uint32_t *>(P.next + l.pos_hdr);
+    uint32_t *nval = reinterpret_cast<uint32_t *>(P.next + l.pos_val), *ncnt = reinterpret_cast<uint32_t *>(P.next + l.pos_cnt);
+    const BlockDesc *blocks = P.blocks + P.block_begin;
+    const uint32_t pc = phdr[0];
+    uint32_t an = pc;
+    for (uint32_t s0 = 0; s0 < pc; s0 += 32u) {
+        const uint32_t s = s0 + lane;
+        if (s < pc) {
+            const uint32_t p = pcnt[s]; uint32_t acc = p;
+            for (uint32_t b = 0; b < P.n_blocks; b++) {
+                const BlockDesc &B = blocks[b];
+                const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+                acc += reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_cnt)[s] - p;
+            }
+            ncnt[s] = acc;
+        }
+    }
+    __syncwarp();
+    for (uint32_t b = 0; b < P.n_blocks; b++) {
+        const BlockDesc &B = blocks[b];
+        const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+        const uint32_t *bval = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_val);
+        const uint32_t *bcnt = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_cnt);
+        for (uint32_t s = pc; s < B.pos_card; s++) {
+            const uint32_t x = bval[s], c = bcnt[s];
+            int found = -1;
+            for (uint32_t q0 = pc; q0 < an && found < 0; q0 += 32u) {
+                const uint32_t q = q0 + lane;
+                const uint32_t hit = __ballot_sync(FULL_MASK, q < an && nval[q] == x);
+                if (hit) found = (int)(q0 + (uint32_t)__ffs(hit) - 1u);
+            }
+            if (found >= 0) { if (lane == 0) ncnt[found] += c; }
+            else if (an < CBCG_SNAP_POS_MAX) { if (lane == 0) { nval[an] = x; ncnt[an] = c; } an++; }
+            __syncwarp();
+        }
+    }
+    uint32_t s = 0;
+    for (uint32_t i = lane; i < an; i += 32u) { int32_t v = (int32_t)ncnt[i]; if (v < 1) v = 1; ncnt[i] = (uint32_t)v; s += (uint32_t)v; }
+    uint32_t n = warp_sum(s);
+    while (n >= CBCG_RESCALE) {
+        s = 0;
+        for (uint32_t i = lane; i < an; i += 32u) { const uint32_t c = (ncnt[i] >> 1) + 1u; ncnt[i] = c; s += c; }
+        n = warp_sum(s);
+    }
+    if (lane == 0) { nhdr[0] = an; nhdr[1] = n; }
+}
+
+/* var rows, phase 1: rows new to the snapshot are created (all ones) by whichever block flips their bit. */
+__global__ void __launch_bounds__(128) merge_var_mark_kernel(MergeParams P) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t b = blockIdx.x * 4u + warp;
+    if (b >= P.n_blocks) return;
+    const SnapLayout l = snap_layout(P.L);
+    uint32_t *bm = reinterpret_cast<uint32_t *>(P.next + l.bitmap);
+    uint32_t *var = reinterpret_cast<uint32_t *>(P.next + l.var);
+    const BlockDesc &B = P.blocks[P.block_begin + b];
+    const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+    const uint64_t *hash = reinterpret_cast<const uint64_t *>(P.ws + B.ws_off + w.var_hash);
+    for (uint32_t h0 = 0; h0 < w.hash_cap; h0 += 32u) {
+        const uint64_t sl = hash[h0 + lane];
+        const uint32_t key = (uint32_t)(sl >> 32);
+        bool won = false; uint32_t ctx = 0;
+        if (key) { ctx = key - 1u; const uint32_t bit = 1u << (ctx & 31u); won = !(atomicOr(&bm[ctx >> 5], bit) & bit); }
+        uint32_t wm = __ballot_sync(FULL_MASK, won);
+        while (wm) {
+            const uint32_t src = (uint32_t)__ffs(wm) - 1u; wm &= wm - 1u;
+            const uint32_t c = __shfl_sync(FULL_MASK, ctx, src);
+            uint32_t *row = var + (uint64_t)c * l.Lp;
+            for (uint32_t i = lane; i < P.L; i += 32u) row[i] = 1u;
+            if (lane == 0) row[P.L] = P.L;
+        }
+    }
+}
+/* phase 2: add every block's row deltas. */
+__global__ void __launch_bounds__(128) merge_var_add_kernel(MergeParams P) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t b = blockIdx.x * 4u + warp;
+    if (b >= P.n_blocks) return;
+    const SnapLayout l = snap_layout(P.L);
+    const uint32_t *pbm = reinterpret_cast<const uint32_t *>(P.prev + l.bitmap);
+    const uint32_t *pvar = reinterpret_cast<const uint32_t *>(P.prev + l.var);
+    uint32_t *var = reinterpret_cast<uint32_t *>(P.next + l.var);
+    const BlockDesc &B = P.blocks[P.block_begin + b];
+    const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+    const uint64_t *hash = reinterpret_cast<const uint64_t *>(P.ws + B.ws_off + w.var_hash);
+    const uint32_t *rows = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.var_rows);
+    for (uint32_t h0 = 0; h0 < w.hash_cap; h0 += 32u) {
+        const uint64_t sl = hash[h0 + lane];
+        uint32_t km = __ballot_sync(FULL_MASK, (uint32_t)(sl >> 32) != 0u);
+        while (km) {
+            const uint32_t src = (uint32_t)__ffs(km) - 1u; km &= km - 1u;
+            const uint64_t e = __shfl_sync(FULL_MASK, sl, src);
+            const uint32_t ctx = (uint32_t)(e >> 32) - 1u, r = (uint32_t)e;
+            const bool in_prev = (pbm[ctx >> 5] >> (ctx & 31u)) & 1u;
+            const uint32_t *row = rows + (uint64_t)r * w.Lp, *prow = pvar + (uint64_t)ctx * l.Lp;
+            uint32_t *nrow = var + (uint64_t)ctx * l.Lp;
+            for (uint32_t i = lane; i < P.L; i += 32u) {
+                const uint32_t d = row[i] - (in_prev ? prow[i] : 1u);
+                if (d) atomicAdd(&nrow[i], d);
+            }
+        }
+    }
+}
+/* phase 3: clamp, total, rescale every row of the new snapshot (idempotent on rows no block touched). */
+__global__ void __launch_bounds__(256) merge_var_finish_kernel(MergeParams P) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t ctx = blockIdx.x * 8u + warp;
+    if (ctx >= CBCG_VAR_CONTEXTS) return;
+    const SnapLayout l = snap_layout(P.L);
+    const uint32_t *bm = reinterpret_cast<const uint32_t *>(P.next + l.bitmap);
+    if (!((bm[ctx >> 5] >> (ctx & 31u)) & 1u)) return;
+    uint32_t *row = reinterpret_cast<uint32_t *>(P.next + l.var) + (uint64_t)ctx * l.Lp;
+    uint32_t s = 0;
+    for (uint32_t i = lane; i < P.L; i += 32u) { int32_t v = (int32_t)row[i]; if (v < 1) v = 1; row[i] = (uint32_t)v; s += (uint32_t)v; }
+    uint32_t n = warp_sum(s);
+    while (n >= CBCG_RESCALE) {
+        s = 0;
+        for (uint32_t i = lane; i < P.L; i += 32u) { const uint32_t c = (row[i] >> 1) + 1u; row[i] = c; s += c; }
+        n = warp_sum(s);
+    }
+    if (lane == 0) row[P.L] = n;
+}
+
+int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_blocks, uint32_t L, const uint8_t *prev,
+                 uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, cudaStream_t st) {
+    if (cudaMemcpyAsync(next, prev, snapshot_bytes(L), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+    MergeParams P = { blocks, block_begin, n_blocks, L, prev, next, fin, ws, err };
+    merge_small_kernel<<<1, MERGE_SMALL_WARPS * 32u, 0, st>>>(P);
+    merge_flag_kernel<<<1, 1024, 0, st>>>(P);
+    merge_pos_kernel<<<1, 32, 0, st>>>(P);
+    merge_var_mark_kernel<<<(n_blocks + 3u) / 4u, 128, 0, st>>>(P);
+    merge_var_add_kernel<<<(n_blocks + 3u) / 4u, 128, 0, st>>>(P);
+    merge_var_finish_kernel<<<(CBCG_VAR_CONTEXTS + 7u) / 8u, 256, 0, st>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

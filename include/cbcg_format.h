@@ -85,13 +85,14 @@ typedef struct cbcg_read_rec {
 /* ---- blocked container ("CBCB"), new design: the reference stream has no framing
  * (src/compression.c:128-155). Little endian. */
 #define CBCG_MAGIC          0x42434243u   /* "CBCB" */
-#define CBCG_VERSION        1u
+#define CBCG_VERSION        2u
 
 /* Generation-primed blocks (gen_mode 1): generation i has CBCG_GEN_COUNTS[i] blocks of
  * CBCG_GEN_READS[i] reads, each starting from the merged final states of the generation before; the
  * last generation takes all remaining reads in blocks of block_reads. */
-#define CBCG_GEN_LEVELS     3
-#define CBCG_GEN_COUNTS     { 1u, 31u, 96u }
-#define CBCG_GEN_READS      { 128u, 128u, 256u }
+#define CBCG_GEN_LEVELS     5
+#define CBCG_GEN_COUNTS     { 1u, 31u, 96u, 256u, 512u }
+#define CBCG_GEN_READS      { 128u, 128u, 256u, 256u, 512u }
+#define CBCG_SNAP_POS_MAX   4096u         /* a snapshot keeps at most this many POS alphabet entries */
 
 #endif /* CBCG_FORMAT_H */

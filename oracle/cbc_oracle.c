@@ -118,6 +118,14 @@ static void ac_flush(acoder *a) {
     for (int bit = (int)CBCG_AC_BITS - 2; bit >= 0; --bit) bw_bit(&a->w, a->l >> bit);
     bw_finish(&a->w);
 }
+/* Blocked containers (our format): the shortest tail that still decodes. After renormalisation
+ * l < 2^25 <= u, so the value 2^25 ("1", the pending E3 bits as "0", then zeros) lies in [l, u]; the
+ * decoder reads zeros past the end of a block, so only 1 + scale3 bits go out, padded to a byte. */
+static void ac_flush_short(acoder *a) {
+    bw_bit(&a->w, 1);
+    while (a->scale3 > 0) { bw_bit(&a->w, 0); a->scale3--; }
+    if (a->w.nbits) bw_finish(&a->w);
+}
 /* arithmetic_get_symbol_range :373-381 */
 static uint32_t ac_target(const acoder *a, uint32_t n) {
     uint64_t range = (uint64_t)a->u - a->l + 1;
@@ -325,7 +333,10 @@ static void merge_block(models *acc, const models *fin, const models *prev) {
         int ps = (s == 0) ? 0 : pos_find(&prev->pos, x);
         uint32_t before = (ps >= 0) ? prev->pos.m.c[ps] : 0u;
         int as = (s == 0) ? 0 : pos_find(&acc->pos, x);
-        if (as < 0) as = (int)pos_append(&acc->pos, x);
+        if (as < 0) {
+            if (acc->pos.m.card >= CBCG_SNAP_POS_MAX) continue;   /* snapshot alphabet is capped; the value stays block-local */
+            as = (int)pos_append(&acc->pos, x);
+        }
         acc->pos.m.c[as] += fin->pos.m.c[s] - before;
     }
 }
@@ -708,6 +719,8 @@ typedef struct {
     int have_name; uint32_t cur_chr;
     snpmem snp;
     cbco_buf *raw;          /* optional raw symbol list (POS as CBCG_S_POS_X) */
+    int lean;               /* blocked containers: the per-read symbols that are constant by construction
+                               (same_ref = 0, length bytes 1..3 = 0) are not coded */
 } rstate;
 
 static void raw_sym(rstate *s, uint32_t stream, uint32_t ctx, uint32_t v) {
@@ -730,7 +743,7 @@ static void put_rname(rstate *s, const char *name) {
 static void put_read(rstate *s, const cbcg_read_rec *rec, const uint16_t *e) {
     uint32_t len = rec->len;
     emit(s, CBCG_S_RLENGTH, 0, len & 0xffu);                    /* :29-33: bytes 1..3 are always 0 */
-    for (uint32_t k = 1; k < 4; k++) emit(s, CBCG_S_RLENGTH, k, 0);
+    if (!s->lean) for (uint32_t k = 1; k < 4; k++) emit(s, CBCG_S_RLENGTH, k, 0);
     uint32_t x = rec->pos - s->prev_pos + 1;                    /* :128 */
     raw_sym(s, CBCG_S_POS_X, 0, x);
     put_pos(&s->c, x);
@@ -769,7 +782,7 @@ static void get_read(rstate *s, cbcg_read_rec *rec, uint16_t *e, uint32_t *n_edi
                      const uint8_t *ref, uint64_t ref_len) {
     coder *c = &s->c;
     uint32_t len = get_sym(c, CBCG_S_RLENGTH, 0);
-    for (uint32_t k = 1; k < 4; k++) len |= get_sym(c, CBCG_S_RLENGTH, k) << (8 * k);
+    if (!s->lean) for (uint32_t k = 1; k < 4; k++) len |= get_sym(c, CBCG_S_RLENGTH, k) << (8 * k);
     uint32_t x = get_pos(c);
     uint32_t pos = s->prev_pos + x - 1;
     s->prev_pos = pos;
@@ -840,7 +853,7 @@ static int code_range(rstate *s, const cbco_batch *b, const cbco_genome *g, cons
             if (change) put_rname(s, g->name[chr]); else emit(s, CBCG_S_SAME_REF, 0, 0);
         } else {
             if (change && r != r0) return -6;                   /* blocks never span chromosomes */
-            emit(s, CBCG_S_SAME_REF, 0, 0);
+            if (!s->lean) emit(s, CBCG_S_SAME_REF, 0, 0);
         }
         if (change) {                                           /* src/compression.c:58-64 */
             s->have_name = 1; s->cur_chr = chr;
@@ -954,6 +967,55 @@ int cbco_symbols(const cbco_batch *b, const cbco_genome *g, const cbcg_read_rec 
  * order with same_ref = 0; closed by the reference's final flush. */
 typedef struct { uint32_t n_reads, chr, base_pos, n_symbols, n_edits, payload_bytes, gen, rsv; } blk_index;
 
+/* Index entries are delta-coded LEB128 varints ("Container"). */
+static void put_varint(cbco_buf *b, uint64_t v) {
+    do { uint8_t c = (uint8_t)(v & 0x7f); v >>= 7; if (v) c |= 0x80; buf_put(b, &c, 1); } while (v);
+}
+static uint64_t zigzag(int64_t v) { return ((uint64_t)v << 1) ^ (uint64_t)(v >> 63); }
+static int64_t unzigzag(uint64_t v) { return (int64_t)(v >> 1) ^ -(int64_t)(v & 1); }
+static int get_varint(const uint8_t *p, uint64_t len, uint64_t *o, uint64_t *v) {
+    uint64_t r = 0; int sh = 0;
+    for (;;) {
+        if (*o >= len || sh > 63) return -1;
+        uint8_t c = p[(*o)++];
+        r |= (uint64_t)(c & 0x7f) << sh; sh += 7;
+        if (!(c & 0x80)) break;
+    }
+    *v = r; return 0;
+}
+typedef struct { int64_t n_reads, chr, gen, base, d1, edits, payload; } idx_state;
+static void index_put(cbco_buf *b, idx_state *st, const blk_index *e) {
+    int chr_ch = (int64_t)e->chr != st->chr, gen_ch = (int64_t)e->gen != st->gen;
+    put_varint(b, (zigzag((int64_t)e->n_reads - st->n_reads) << 2) | (chr_ch ? 2u : 0u) | (gen_ch ? 1u : 0u));
+    if (chr_ch) { put_varint(b, e->chr); st->base = 0; st->d1 = 0; }
+    if (gen_ch) put_varint(b, (uint64_t)((int64_t)e->gen - st->gen - 1));
+    int64_t d1 = (int64_t)e->base_pos - st->base;
+    put_varint(b, zigzag(d1 - st->d1));
+    put_varint(b, zigzag((int64_t)e->n_edits - st->edits));
+    put_varint(b, zigzag((int64_t)e->payload_bytes - st->payload));
+    st->n_reads = e->n_reads; st->chr = e->chr; st->gen = e->gen; st->base = e->base_pos; st->d1 = d1;
+    st->edits = e->n_edits; st->payload = e->payload_bytes;
+}
+static int index_get(const uint8_t *p, uint64_t len, uint64_t *o, idx_state *st, blk_index *e) {
+    uint64_t v;
+    if (get_varint(p, len, o, &v)) return -1;
+    st->n_reads += unzigzag(v >> 2);
+    if (v & 2) { uint64_t c; if (get_varint(p, len, o, &c)) return -1; st->chr = (int64_t)c; st->base = 0; st->d1 = 0; }
+    if (v & 1) { uint64_t gi; if (get_varint(p, len, o, &gi)) return -1; st->gen += (int64_t)gi + 1; }
+    if (get_varint(p, len, o, &v)) return -1;
+    st->d1 += unzigzag(v); st->base += st->d1;
+    if (get_varint(p, len, o, &v)) return -1;
+    st->edits += unzigzag(v);
+    if (get_varint(p, len, o, &v)) return -1;
+    st->payload += unzigzag(v);
+    if (st->n_reads < 0 || st->n_reads > 0xffffffffll || st->chr < 0 || st->gen < 0 || st->gen > 255 || st->base < 0 || st->base > 0xffffffffll ||
+        st->edits < 0 || st->edits > 0xffffffffll || st->payload < 0 || st->payload > 0xffffffffll) return -1;
+    memset(e, 0, sizeof *e);
+    e->n_reads = (uint32_t)st->n_reads; e->chr = (uint32_t)st->chr; e->gen = (uint32_t)st->gen; e->base_pos = (uint32_t)st->base;
+    e->n_edits = (uint32_t)st->edits; e->payload_bytes = (uint32_t)st->payload;
+    return 0;
+}
+
 static void rstate_init_from(rstate *s, const models *snap, int mode) {
     memset(s, 0, sizeof *s);
     models_clone(&s->c.M, snap);
@@ -1004,12 +1066,13 @@ int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t L,
         }
         if (!acc && idx[k].gen != last_gen) { acc = (models *)malloc(sizeof(models)); models_clone(acc, prev); }
         rstate s; rstate_init_from(&s, prev, 1);
+        s.lean = 1;
         uint64_t start = payload.size;
         ac_init_enc(&s.c.ac, &payload);
         s.prev_pos = idx[k].base_pos; s.have_name = 1; s.cur_chr = idx[k].chr;
         snp_reset(&s.snp, g->len[idx[k].chr] + 2048);
         rc = code_range(&s, b, g, recs, edits, first[k], first[k + 1], 0);
-        if (!rc) { ac_flush(&s.c.ac); rc = s.c.err; }
+        if (!rc) { ac_flush_short(&s.c.ac); rc = s.c.err; }
         idx[k].n_symbols = (uint32_t)s.c.n_symbols;
         uint64_t e_lo = recs[first[k]].edit_off;
         uint64_t e_hi = (first[k + 1] < b->n_reads) ? recs[first[k + 1]].edit_off : (uint64_t)ne;
@@ -1030,7 +1093,12 @@ int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t L,
             uint32_t nl = (uint32_t)strlen(g->name[c]), pad = (4 - (nl & 3)) & 3; uint32_t z = 0;
             buf_put_u32(out, nl); buf_put(out, g->name[c], nl); buf_put(out, &z, pad);
         }
-        buf_put(out, idx, nb * sizeof(blk_index));
+        cbco_buf ix = {0};
+        idx_state st = { block_reads, 0, 0, 0, 0, 0, 0 };
+        for (uint64_t k = 0; k < nb; k++) index_put(&ix, &st, &idx[k]);
+        buf_put_u32(out, (uint32_t)ix.size);
+        buf_put(out, ix.data, ix.size);
+        cbco_buf_free(&ix);
         buf_put(out, payload.data, payload.size);
     }
     cbco_buf_free(&payload);
@@ -1065,13 +1133,20 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
         chr_map[c] = found;
         o += nl + ((4 - (nl & 3)) & 3);
     }
-    if (o + (uint64_t)nb * sizeof(blk_index) > len) { free(chr_map); return -43; }
-    const blk_index *idx = (const blk_index *)(p + o);
-    o += (uint64_t)nb * sizeof(blk_index);
+    if (o + 4 > len) { free(chr_map); return -43; }
+    uint32_t ix_bytes; memcpy(&ix_bytes, p + o, 4); o += 4;
+    if (o + ix_bytes > len || nb > ix_bytes) { free(chr_map); return -43; }
+    blk_index *idx = (blk_index *)calloc((size_t)nb + 1, sizeof(blk_index));
+    {
+        idx_state st = { h[8], 0, 0, 0, 0, 0, 0 };
+        uint64_t io = o;
+        for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k])) { free(chr_map); free(idx); return -43; }
+    }
+    o += ix_bytes;
     int rc = 0; uint64_t n = 0;
     uint16_t e[3 * 256 + 8]; uint8_t line[1025];
     uint32_t last_gen = 0;
-    for (uint32_t k = 0; k < nb; k++) { blk_index bi; memcpy(&bi, &idx[k], sizeof bi); if (bi.gen < last_gen) { free(chr_map); return -48; } last_gen = bi.gen; }
+    for (uint32_t k = 0; k < nb; k++) last_gen = idx[k].gen;                  /* the index codes generations in ascending order */
     models *prev = (models *)malloc(sizeof(models)), *acc = NULL;
     models_init(prev, L);
     uint32_t cur_gen = 0;
@@ -1085,12 +1160,11 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
         if (!acc && bi.gen != last_gen) { acc = (models *)malloc(sizeof(models)); models_clone(acc, prev); }
         uint32_t chr = chr_map[bi.chr];
         rstate s; rstate_init_from(&s, prev, 2);
+        s.lean = 1;
         ac_init_dec(&s.c.ac, p + o, bi.payload_bytes);
         s.prev_pos = bi.base_pos;
         snp_reset(&s.snp, g->len[chr] + 2048);
         for (uint32_t r = 0; r < bi.n_reads && !rc; r++) {
-            uint32_t same = get_sym(&s.c, CBCG_S_SAME_REF, 0);
-            if (s.c.err || same != 0) { rc = -46; break; }
             cbcg_read_rec rec; uint32_t ne = 0;
             get_read(&s, &rec, e, &ne, g->bases[chr], g->len[chr]);
             if (s.c.err) { rc = s.c.err; break; }
@@ -1105,6 +1179,7 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
     }
     if (acc) { models_free(acc); free(acc); }
     models_free(prev); free(prev);
+    free(idx);
     free(chr_map);
     if (n_reads_out) *n_reads_out = n;
     return rc;

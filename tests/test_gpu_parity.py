@@ -142,14 +142,15 @@ def test_reconstruct_matches_oracle(codec, meta_path):
 
 # ------------------------------------------------------------------ blocked container
 
+@pytest.mark.parametrize("gen_mode", [0, 1])
 @pytest.mark.parametrize("name,block_reads", [("subs_150", 256), ("indels_100", 1), ("clips_100", 97),
                                               ("two_chr", 1000), ("indels_250", 64), ("paired_flags_n", 100000),
                                               ("sparse_cov", 33)])
-def test_blocked_container_equals_oracle_and_roundtrips(codec, name, block_reads):
+def test_blocked_container_equals_oracle_and_roundtrips(codec, name, block_reads, gen_mode):
     meta, g, b, _ = _load(GOLDEN[IDS.index(name)])
     codec.set_reference(g)
-    c = codec.compress(b, meta["read_len_header"], block_reads=block_reads)
-    assert c == O.encode_blocked(b, g, meta["read_len_header"], block_reads)      # same bytes as the CPU restatement
+    c = codec.compress(b, meta["read_len_header"], block_reads=block_reads, gen_mode=gen_mode)
+    assert c == O.encode_blocked(b, g, meta["read_len_header"], block_reads, gen_mode)      # same bytes as the CPU restatement
     text, n = codec.decompress(c)
     assert n == b.n_reads and text == b.seq_lines()
     otext, on = O.decode_blocked(c, g)
@@ -165,10 +166,11 @@ def test_variable_length_reads_roundtrip(codec):
     recs, edits = codec.extract(b)
     orecs, oedits = O.extract(b, g)
     assert np.array_equal(recs, orecs) and np.array_equal(edits, oedits)
-    c = codec.compress(b, 250, block_reads=512)
-    assert c == O.encode_blocked(b, g, 250, 512)
-    text, n = codec.decompress(c)
-    assert n == b.n_reads and text == b.seq_lines()
+    for gen_mode in (0, 1):
+        c = codec.compress(b, 250, block_reads=512, gen_mode=gen_mode)
+        assert c == O.encode_blocked(b, g, 250, 512, gen_mode)
+        text, n = codec.decompress(c)
+        assert n == b.n_reads and text == b.seq_lines()
 
 
 def test_large_block_uses_direct_var_rows(codec):
@@ -280,18 +282,27 @@ def test_config2_slice_roundtrip_and_resident_path(codec):
     g = synth.make_genome(cfg)
     b = synth.make_reads(cfg, g)
     codec.set_reference(g)
-    codec.upload(b)
-    codec.encode_resident(150, 4096)
-    st = codec.stats()
-    assert st["n_reads"] == b.n_reads and st["n_blocks"] == (b.n_reads + 4095) // 4096
-    cont = codec.fetch_container().tobytes()
-    codec.decode_resident()
-    text = codec.fetch_decoded().tobytes()
-    assert text == b.seq_lines()
-    assert cont == codec.compress(b, 150, block_reads=4096)
-    bits_per_base = 8.0 * len(cont) / b.total_bases()
-    assert 0.02 < bits_per_base < 0.5
-    # idempotence: a second encode of the resident batch gives the same bytes
-    codec.upload(b)
-    codec.encode_resident(150, 4096)
-    assert codec.fetch_container().tobytes() == cont
+    sizes = {}
+    for gen_mode in (0, 1):
+        codec.upload(b)
+        codec.encode_resident(150, 1024, gen_mode)
+        st = codec.stats()
+        assert st["n_reads"] == b.n_reads
+        if gen_mode == 0:
+            assert st["n_blocks"] == (b.n_reads + 1023) // 1024
+        cont = codec.fetch_container().tobytes()
+        codec.decode_resident()
+        text = codec.fetch_decoded().tobytes()
+        assert text == b.seq_lines()
+        assert cont == codec.compress(b, 150, block_reads=1024, gen_mode=gen_mode)
+        assert cont == O.encode_blocked(b, g, 150, 1024, gen_mode)
+        text2, n2 = codec.decompress(cont)
+        assert n2 == b.n_reads and text2 == text
+        bits_per_base = 8.0 * len(cont) / b.total_bases()
+        assert 0.02 < bits_per_base < 0.5
+        sizes[gen_mode] = len(cont)
+        # idempotence: a second encode of the resident batch gives the same bytes
+        codec.upload(b)
+        codec.encode_resident(150, 1024, gen_mode)
+        assert codec.fetch_container().tobytes() == cont
+    assert sizes[1] < 0.8 * sizes[0]              # primed blocks recover most of the cold-start loss

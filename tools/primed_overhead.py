@@ -38,7 +38,7 @@ def split(data):
     o = 40
     for _ in range(nchr):
         nl, = struct.unpack_from("<I", data, o); o += 4 + nl + ((4 - (nl & 3)) & 3)
-    return nb, o + 32 * nb, len(data) - o - 32 * nb
+    ixb, = struct.unpack_from("<I", data, o); return nb, o + 4 + ixb, len(data) - o - 4 - ixb
 
 SCHEDS = [([], []), ([1, 31, 96], [128, 128, 256]), ([1, 31, 96, 256], [128, 128, 256, 256]),
           ([1, 31, 96, 256, 512], [128, 128, 256, 256, 512]), ([1, 15, 48, 128, 512, 1024], [128, 128, 128, 256, 256, 512])]
