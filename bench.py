@@ -201,6 +201,7 @@ def run_b200_arm(args):
     cfg, g, b = workload(rank, args.scale)
     L = 150
     R = args.block_reads
+    G = args.gen_mode
     codec = Codec(local)
     codec.set_reference(g)
     pb = pin_batch(b)
@@ -235,7 +236,7 @@ def run_b200_arm(args):
 
     def resident_step(record: bool):
         nonlocal launches, index_bytes
-        codec.encode_resident(L, R)
+        codec.encode_resident(L, R, G)
         se = codec.stats()
         head, payload = codec.fetch_index()
         if dist is not None:                                  # container index: all-gather of per-shard block tables
@@ -280,7 +281,7 @@ def run_b200_arm(args):
     out_t = pinned_empty(bases + n + 64, np.uint8)
 
     def e2e_step():
-        nc = codec.compress_into(pb, L, R, out_c)
+        nc = codec.compress_into(pb, L, R, out_c, G)
         s1 = codec.stats()
         if dist is not None:
             head, payload = codec.fetch_index()
@@ -352,7 +353,7 @@ def run_b200_arm(args):
                         "compress_reads_per_s": ns / enc_s, "decompress_reads_per_s": ns / dec_s,
                         "bits_per_base": 8.0 * sz / sample.total_bases(), "cpu": cpu_model(), "host_cores": os.cpu_count()}
         # blocking overhead on the same sample; the single-block GPU stream must be the reference's bytes
-        blocked = codec.compress(sample, L, R)
+        blocked = codec.compress(sample, L, R, G)
         single = codec.compress(sample, L, 0)
         overhead = {"sample_reads": ns, "single_stream_bytes": len(single), "blocked_bytes": len(blocked),
                     "blocked_bits_per_base": 8.0 * len(blocked) / sample.total_bases(),
@@ -365,7 +366,7 @@ def run_b200_arm(args):
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": f"config2: 150bp reads at 30x over {cfg.genome_len} bp, 0.5% substitutions, one such region per GPU",
-                   "n_reads_per_gpu": n, "read_len": 150, "block_reads": R, "blocks_per_gpu": int(se["n_blocks"]),
+                   "n_reads_per_gpu": n, "read_len": 150, "block_reads": R, "gen_mode": G, "blocks_per_gpu": int(se["n_blocks"]),
                    "l2": "inputs larger than L2 (batch %.0f MB, decoded text %.0f MB per GPU)" % (s1["h2d_bytes"] / 1e6, (bases + n) / 1e6),
                    "parallelism": f"{world} region shard(s), no collective on the coding path"},
         "compress_reads_per_s": total_reads / (max_over_ranks(med["enc_total"]) * 1e-3),
@@ -395,6 +396,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block-reads", type=int, default=1024)
+    ap.add_argument("--gen-mode", type=int, default=1, help="1: generation-primed blocks (default), 0: cold blocks")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; the bench line needs 1.0)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()

@@ -16,7 +16,7 @@ import numpy as np
 from .batch import Batch, CBatch, Genome
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libcbcg.so")
+LIB_PATH = os.environ.get("CBCG_LIB") or os.path.join(_HERE, "_build", "libcbcg.so")   # CBCG_LIB: tuning builds only
 
 REC_DTYPE = np.dtype([("pos", "<u4"), ("flag", "<u2"), ("len", "<u2"), ("edit_off", "<u4"),
                       ("match", "u1"), ("n_snps", "u1"), ("n_dels", "u1"), ("n_ins", "u1")])

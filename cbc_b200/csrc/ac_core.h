@@ -95,7 +95,7 @@ AC_HD void ac_renorm_shape(const AcInterval &a, uint32_t &k, uint32_t &bits, uin
 AC_HD uint32_t ac_tag_shift(uint32_t t, uint32_t k, uint32_t m, uint32_t in) {
     const uint32_t s = k + m;
     if (s == 0) return t;
-    uint32_t r = (uint32_t)((((uint64_t)t << s) & CBCG_AC_TOP) | in);
+    uint32_t r = (uint32_t)(((((uint64_t)t << s) | in) & CBCG_AC_TOP));
     if (m) r ^= CBCG_AC_MSB;
     return r;
 }

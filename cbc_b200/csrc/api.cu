@@ -463,7 +463,7 @@ static int run_coder_generations(cbcg_ctx *ctx, CoderParams p, uint64_t nb, bool
         if (!last) {
             if (launch_merge(p.blocks, p.block_begin, p.n_blocks, p.L, cur, other, ctx->fin.as<uint8_t>(), p.ws, p.err, ctx->st))
                 return fail(ctx, CBCG_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            ctx->stats.kernel_launches += 6;
+            ctx->stats.kernel_launches += 4;
             std::swap(cur, other);
         }
     }
@@ -905,7 +905,7 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
             if (rc) return rc;
             break;
         }
-        *max_len = ctx->hblocks[0].gen;                     /* header read length (src/sam_file_allocation.c:365) */
+        *max_len = ctx->hblocks[0].pad;                     /* header read length (src/sam_file_allocation.c:365) */
         S.n_blocks = 1;
     }
     CU(cudaEventRecord(ctx->ev[2], ctx->st));

@@ -37,11 +37,20 @@
 #include "ac_core.h"
 
 #define K2_WARPS    4u
+#ifndef K2_MIN_CTAS
+#define K2_MIN_CTAS 4          /* resident CTAs per SM the register allocation is held to */
+#endif
 #define K2_THREADS  (K2_WARPS * 32u)
 #define FLAG_CAP    128u
 #define VAR_DIRECT_MIN_EDITS 32768u       /* blocks with more edits index var rows directly by context */
 
 enum { MODE_ENC = 0, MODE_DEC = 1, MODE_LIST = 2 };
+
+#ifdef K2_FENCE
+#define SYNCW() do { __syncwarp(); __threadfence_block(); } while (0)
+#else
+#define SYNCW() __syncwarp()
+#endif
 
 /* ------------------------------------------------------------------------------------------------
  * per-block workspace layout in HBM (u32 units unless noted) */
@@ -163,7 +172,7 @@ struct Coder {
     uint64_t acc; uint32_t nacc;
     uint8_t *out; uint32_t out_pos, out_cap;
     /* decoder bit reader */
-    const uint8_t *in; uint32_t in_len; uint64_t in_bit;
+    const uint8_t *in; uint32_t in_len, in_pos, dcnt; uint64_t dbuf;
     /* symbol list */
     cbcg_symbol *list; uint32_t list_n, list_cap;
 
@@ -223,25 +232,31 @@ struct Coder {
         nacc = 0; acc = 0;
     }
     /* next k bits of the input, first bit most significant; zeros past the end (the reference's
-       zero-filled buffer, src/Arithmetic_stream.c:30,117) */
+       zero-filled buffer, src/Arithmetic_stream.c:30,117). dbuf holds the upcoming bits left-aligned;
+       it is topped up 32 bits at a time, so a symbol costs shifts, not loads. */
     __device__ __forceinline__ uint32_t get_bits(uint32_t k) {               /* k <= 32 */
         if (k == 0) return 0u;
-        const uint64_t byte0 = in_bit >> 3;
-        uint64_t w = 0;
+        if (dcnt < k) {
+            uint32_t w = 0;
 #pragma unroll
-        for (uint32_t i = 0; i < 5; i++) {
-            uint64_t p = byte0 + i;
-            uint64_t v = (p < in_len) ? (uint64_t)in[p] : 0ull;
-            w = (w << 8) | v;
+            for (uint32_t i = 0; i < 4; i++) {
+                const uint32_t p = in_pos + i;
+                const uint32_t v = (p < in_len) ? (uint32_t)in[p] : 0u;
+                w = (w << 8) | v;
+            }
+            in_pos += 4u;
+            dbuf |= (uint64_t)w << (32u - dcnt);
+            dcnt += 32u;
         }
-        const uint32_t sh = 40u - (uint32_t)(in_bit & 7u) - k;
-        in_bit += k;
-        return (uint32_t)((w >> sh) & ((1ull << k) - 1ull));
+        const uint32_t r = (uint32_t)(dbuf >> (64u - k));
+        dbuf <<= k;
+        dcnt -= k;
+        return r;
     }
 
     /* ============================================================ arithmetic coder */
     __device__ __forceinline__ void ac_init() {
-        a.l = 0; a.u = CBCG_AC_TOP; scale3 = 0; t = 0; acc = 0; nacc = 0; out_pos = 0; in_bit = 0;
+        a.l = 0; a.u = CBCG_AC_TOP; scale3 = 0; t = 0; acc = 0; nacc = 0; out_pos = 0; in_pos = 0; dcnt = 0; dbuf = 0;
         if (MODE == MODE_DEC) t = get_bits(CBCG_AC_BITS);                    /* :262 */
     }
     __device__ __forceinline__ void ac_encode(uint32_t lo, uint32_t cnt, uint32_t n) {
@@ -262,7 +277,9 @@ struct Coder {
         ac_narrow(a, lo, lo + cnt, n);
         uint32_t k, bits, m; AcInterval nx;
         ac_renorm_shape(a, k, bits, m, nx);
-        t = ac_tag_shift(t, k, m, get_bits(k + m));
+        uint32_t s = k + m;
+        if (s > 32u) { (void)get_bits(s - 32u); s = 32u; }                   /* only the last 26 bits survive the shift */
+        t = ac_tag_shift(t, k, m, get_bits(s));
         a = nx;
     }
     /* encoder_last_step (:348-364) */
@@ -291,16 +308,16 @@ struct Coder {
     /* ============================================================ dense models (counts[card], n at [card]) */
     __device__ __forceinline__ void dense_update(uint32_t *m, uint32_t card, uint32_t step, uint32_t x) {
         uint32_t n = m[card] + step;
-        __syncwarp();
+        SYNCW();
         if (lane == 0) { m[x] += step; m[card] = n; }
-        __syncwarp();
+        SYNCW();
         if (n >= CBCG_RESCALE) {                                             /* update_model :38-49 */
             uint32_t s = 0;
             for (uint32_t i = lane; i < card; i += 32u) { uint32_t c = (m[i] >> 1) + 1u; m[i] = c; s += c; }
             s = warp_sum(s);
-            __syncwarp();
+            SYNCW();
             if (lane == 0) m[card] = s;
-            __syncwarp();
+            SYNCW();
         }
     }
     __device__ __forceinline__ uint32_t sym_dense(uint32_t *m, uint32_t card, uint32_t step, uint32_t x) {
@@ -352,9 +369,9 @@ struct Coder {
         code_interval(0u, c0, n);
         c0 += 10u; n += 10u;
         if (n >= CBCG_RESCALE) { c0 = (c0 >> 1) + 1u; n = c0 + 254u; }
-        __syncwarp();
+        SYNCW();
         if (lane == 0) { M->rlenk[k][0] = c0; M->rlenk[k][1] = n; }
-        __syncwarp();
+        SYNCW();
         return 0u;
     }
 
@@ -406,7 +423,7 @@ struct Coder {
         code_interval(lo, cnt, n);
         if (err) return 0u;
         /* update_model with step 8 */
-        __syncwarp();
+        SYNCW();
         uint32_t nused = used;
         if (found_idx >= 0) { if (lane == 0) M->flag_cnt[found_idx] += 8u; }
         else {
@@ -422,9 +439,9 @@ struct Coder {
                     const bool mv = (i >= p && i < used);
                     uint32_t k = 0, c = 0;
                     if (mv) { k = M->flag_key[i]; c = M->flag_cnt[i]; }
-                    __syncwarp();
+                    SYNCW();
                     if (mv) { M->flag_key[i + 1u] = k; M->flag_cnt[i + 1u] = c; }
-                    __syncwarp();
+                    SYNCW();
                     if ((uint32_t)base <= p) break;
                 }
             }
@@ -432,14 +449,14 @@ struct Coder {
             nused = used + 1u;
         }
         uint32_t nn = n + 8u;
-        __syncwarp();
+        SYNCW();
         if (nn >= CBCG_RESCALE) {
             uint32_t s = 0;
             for (uint32_t i = lane; i < nused; i += 32u) { uint32_t c = (M->flag_cnt[i] >> 1) + 1u; M->flag_cnt[i] = c; s += c; }
             nn = warp_sum(s) + (65536u - nused);
         }
         if (lane == 0) M->flag_n = nn;
-        __syncwarp();
+        SYNCW();
         return x;
     }
 
@@ -454,13 +471,13 @@ struct Coder {
         if (slot < 32u) { if (lane == slot) pos_rc += 10u; }
         else if (lane == 0) pos_gcnt[slot] += 10u;
         pos_n += 10u;
-        __syncwarp();
+        SYNCW();
         if (pos_n >= CBCG_RESCALE) {
             uint32_t s = 0;
             if (lane < pos_card) { pos_rc = (pos_rc >> 1) + 1u; s += pos_rc; }
             for (uint32_t i = 32u + lane; i < pos_card; i += 32u) { uint32_t c = (pos_gcnt[i] >> 1) + 1u; pos_gcnt[i] = c; s += c; }
             pos_n = warp_sum(s);
-            __syncwarp();
+            SYNCW();
         }
     }
     __device__ __forceinline__ void pos_append(uint32_t x) {                    /* new symbol, count 0, then updated (:147-153) */
@@ -469,7 +486,7 @@ struct Coder {
         if (slot < 32u) { if (lane == slot) { pos_rv = x; pos_rc = 0u; } }
         else if (lane == 0) { pos_gval[slot] = x; pos_gcnt[slot] = 0u; }
         pos_card = slot + 1u;
-        __syncwarp();
+        SYNCW();
         pos_update(slot);
     }
     __device__ __forceinline__ void pa_ensure() {
@@ -477,13 +494,15 @@ struct Coder {
             if (primed) { for (uint32_t i = lane; i < 4u * 257u; i += 32u) pos_alpha[i] = snap.pos_alpha[i]; }
             else for (uint32_t k = 0; k < 4u; k++) dense_init_ones(pos_alpha + k * 257u, 256u);
             pa_init = true;
-            __syncwarp();
+            SYNCW();
         }
     }
-    /* compress_pos / decompress_pos: x = pos - prevPos + 1 */
-    __device__ __forceinline__ uint32_t sym_pos(uint32_t x) {
+    /* compress_pos / decompress_pos, the POS symbol itself: x = pos - prevPos + 1. Returns the value (decode:
+       0 when the escape was decoded) and the slot; the caller codes the 4 escape bytes and calls pos_append. */
+    __device__ __forceinline__ uint32_t sym_pos_main(uint32_t x, uint32_t &slot) {
+        slot = 0;
         if (err) return 0u;
-        uint32_t lo = 0, cnt = 0, slot = 0;
+        uint32_t lo = 0, cnt = 0;
         if (MODE == MODE_ENC) {
             bool found = false;
             for (uint32_t base = 0; base < pos_card; base += 32u) {
@@ -521,17 +540,6 @@ struct Coder {
         code_interval(lo, cnt, pos_n);
         if (err) return 0u;
         pos_update(slot);
-        if (slot != 0u) return x;
-        /* escape: the value goes out as 4 bytes, MSB first (compress_pos_alpha :75-108) */
-        pa_ensure();
-        uint32_t y = 0;
-        for (uint32_t k = 0; k < 4u; k++) {
-            uint32_t byte = sym_dense(pos_alpha + k * 257u, 256u, 10u, (x >> (24u - 8u * k)) & 0xffu);
-            y |= byte << (24u - 8u * k);
-        }
-        if (MODE == MODE_DEC) x = y;
-        if (err) return 0u;
-        pos_append(x);
         return x;
     }
 
@@ -543,9 +551,9 @@ struct Coder {
             const uint32_t w = var_bitmap[ctx >> 5];
             if (!((w >> (ctx & 31u)) & 1u)) {
                 dense_init_ones(row, L);
-                __syncwarp();
+                SYNCW();
                 if (lane == 0) var_bitmap[ctx >> 5] = w | (1u << (ctx & 31u));
-                __syncwarp();
+                SYNCW();
             }
             return row;
         }
@@ -571,20 +579,13 @@ struct Coder {
                     const uint32_t *src = snap.var + (uint64_t)ctx * Lp;
                     for (uint32_t i = lane; i <= L; i += 32u) row[i] = src[i];
                 } else dense_init_ones(row, L);
-                __syncwarp();
+                SYNCW();
                 return row;
             }
         }
         err = CBCG_ERR_INTERNAL;
         return nullptr;
     }
-    __device__ __forceinline__ uint32_t sym_var(uint32_t ctx, uint32_t x) {
-        if (err) return 0u;
-        uint32_t *row = var_row(ctx);
-        if (!row) return 0u;
-        return sym_dense(row, L, 10u, x);
-    }
-
     /* ============================================================ SNP-site ring (snpInRef) */
     __device__ __forceinline__ void ring_reset() { ring = 0u; ring_word = 0u; }
     __device__ __forceinline__ void ring_advance(uint32_t pos) {               /* window must start at or below pos - 1 */
@@ -623,32 +624,11 @@ struct Coder {
         list_n++;
         n_symbols++;
     }
-    __device__ __forceinline__ uint32_t sym(uint32_t stream, uint32_t ctx, uint32_t x) {
-        if (MODE == MODE_LIST) { list_put(stream, ctx, x); return x; }
-        switch (stream) {
-            case CBCG_S_CODEBOOK:  return sym_dense(codebook + ctx * 257u, 256u, 1u, x);
-            case CBCG_S_SAME_REF:  return sym_dense(M->same_ref, 2u, 10u, x);
-            case CBCG_S_RNAME:     return sym_dense(rname + ctx * 257u, 256u, 10u, x);
-            case CBCG_S_RLENGTH:   return ctx == 0u ? sym_dense(M->rlen0, 255u, 10u, x) : sym_rlenk(ctx - 1u, x);
-            case CBCG_S_FLAG:      return sym_flag(x);
-            case CBCG_S_MATCH:     return sym_dense(M->match[ctx], 2u, 1u, x);
-            case CBCG_S_SNPS:      return sym_dense(M->snps, L, 10u, x);
-            case CBCG_S_INDELS:    return sym_dense(M->indels, L, 16u, x);
-            case CBCG_S_VAR:       return sym_var(ctx, x);
-            case CBCG_S_CHARS:     return sym_dense(M->chars[ctx], 5u, 8u, x);
-            default: err = CBCG_ERR_INTERNAL; return 0u;
-        }
-    }
-    __device__ __forceinline__ uint32_t sym_posx(uint32_t x) {
-        if (MODE == MODE_LIST) { list_put(CBCG_S_POS_X, 0u, x); return x; }
-        return sym_pos(x);
-    }
-
     /* ============================================================ model initial states */
     __device__ __forceinline__ void init_L_models() {          /* the models whose alphabet is the header read length */
         dense_init_ones(M->snps, L);
         dense_init_ones(M->indels, L);
-        __syncwarp();
+        SYNCW();
     }
     __device__ __forceinline__ void init_from_snapshot() {
         uint32_t *dst = reinterpret_cast<uint32_t *>(M);
@@ -660,7 +640,7 @@ struct Coder {
         pa_init = false;
         n_rows = 0;
         for (uint32_t i = lane; i <= hash_mask; i += 32u) var_hash[i] = 0ull;
-        __syncwarp();
+        SYNCW();
     }
     __device__ __forceinline__ void init_models(bool legacy) {
         if (MODE == MODE_LIST) return;
@@ -690,122 +670,25 @@ struct Coder {
             for (uint32_t k = 0; k < 4u; k++) dense_init_ones(codebook + k * 257u, 256u);
             for (uint32_t k = 0; k < 256u; k++) dense_init_ones(rname + k * 257u, 256u);
         }
-        __syncwarp();
+        SYNCW();
     }
 };
 
 /* ------------------------------------------------------------------------------------------------
- * read-level driver: compress_read / decompress_read and the emission / decoding half of
- * compress_edits / reconstruct_read. State kept by the reference in statics: prev_pos
- * (src/read_compression.c:115), prev_m (:167). */
-template <int MODE>
-struct ReadState { uint32_t prev_pos, prev_m; };
+ * The block coder proper: ONE loop that walks the reference's symbol order as a state machine, so that every
+ * model kind (dense, FLAG, POS) has a single call site in the generated code. (Inlining the coder at each
+ * of the reference's ~30 emission sites made a 28 000-instruction kernel that spent a third of its time
+ * waiting for instruction fetch.) States follow compress_read / decompress_read (src/read_compression.c:15-44,
+ * src/read_decompression.c:59-86), the emission / decoding half of compress_edits / reconstruct_read
+ * (:557-600 / :339-458), compress_rname / decompress_rname (src/id_compression.c:39-94) and the stream
+ * header (src/sam_file_allocation.c:363-404, src/compression.c:139,152). State the reference keeps in statics
+ * is explicit: prev_pos (src/read_compression.c:115), prev_m (:167), prev_char (src/id_compression.c:42). */
+enum : uint32_t { ST_HDR, ST_READ, ST_SAMEREF, ST_RNAME, ST_RLEN0, ST_RLENK, ST_POS, ST_POSESC, ST_FLAG, ST_MATCH, ST_SNPS,
+                  ST_INDELS, ST_DEL, ST_SNPVAR, ST_SNPCHAR, ST_INSVAR, ST_INSCHAR, ST_READ_END, ST_ENDMARK, ST_DONE };
+enum : uint32_t { K_NONE, K_DENSE, K_RLENK, K_FLAG, K_POS };
 
 template <int MODE>
-__device__ __forceinline__ void code_read(Coder<MODE> &C, ReadState<MODE> &st, cbcg_read_rec &rec,
-                                          const uint16_t *e_in, uint16_t *e_out, uint32_t &n_edits_out,
-                                          uint32_t edits_room, const uint8_t *ref, uint64_t ref_len) {
-    const uint32_t lane = C.lane;
-    /* length: byte 0 carries it, bytes 1..3 are always 0 (:29-33) */
-    uint32_t len = C.sym(CBCG_S_RLENGTH, 0u, rec.len & 0xffu);
-    if (!C.lean || MODE == MODE_LIST) for (uint32_t k = 1; k < 4u; k++) len |= C.sym(CBCG_S_RLENGTH, k, 0u) << (8u * k);
-    if (C.err) return;
-    if (MODE != MODE_DEC) len = rec.len;
-    /* position (:113-159) */
-    uint32_t x;
-    if (MODE == MODE_DEC) { x = C.sym_posx(0u); if (!C.err && x == 0u) C.err = CBCG_ERR_CORRUPT; }
-    else {
-        if (rec.pos == 0u || rec.len == 0u || rec.len > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_INPUT; return; }
-        if (rec.pos < st.prev_pos || rec.pos - st.prev_pos + 1u > CBCG_MAX_POS_X) { C.err = CBCG_ERR_INPUT; return; }
-        x = C.sym_posx(rec.pos - st.prev_pos + 1u);
-    }
-    if (C.err) return;
-    const uint32_t pos = (MODE == MODE_DEC) ? st.prev_pos + x - 1u : rec.pos;
-    if (MODE == MODE_DEC && (pos == 0u || len == 0u || len > CBCG_MAX_READ_LEN)) { C.err = CBCG_ERR_CORRUPT; return; }
-    st.prev_pos = pos;
-    C.ring_advance(pos);
-    const uint32_t flag = C.sym(CBCG_S_FLAG, 0u, rec.flag);
-    const uint32_t strand = (flag >> 4) & 1u;                                   /* :57-60 */
-    const uint32_t match = C.sym(CBCG_S_MATCH, ((uint32_t)(x == 1u) << 1) | st.prev_m, rec.match);
-    if (C.err) return;
-    st.prev_m = match;
-    if (MODE == MODE_DEC) {
-        rec.pos = pos; rec.flag = (uint16_t)flag; rec.len = (uint16_t)len; rec.match = (uint8_t)match;
-        rec.n_snps = rec.n_dels = rec.n_ins = 0;
-    }
-    n_edits_out = 0;
-    if (match) return;
-
-    uint32_t ns = rec.n_snps, nd = rec.n_dels, ni = rec.n_ins;
-    if (MODE == MODE_DEC) {
-        ns = C.sym(CBCG_S_SNPS, 0u, 0u); nd = 0; ni = 0;
-        if (ns == 0u) { ns = C.sym(CBCG_S_INDELS, 0u, 0u); nd = C.sym(CBCG_S_INDELS, 0u, 0u); ni = C.sym(CBCG_S_INDELS, 0u, 0u); }
-        if (C.err) return;
-        if (ni > len || ns > 255u || nd > 255u || ni > 255u) { C.err = CBCG_ERR_CORRUPT; return; }
-        if (ns + nd + ni > edits_room) { C.err = CBCG_ERR_CAPACITY; return; }
-        rec.n_snps = (uint8_t)ns; rec.n_dels = (uint8_t)nd; rec.n_ins = (uint8_t)ni;
-    } else {
-        if ((nd | ni) == 0u) C.sym(CBCG_S_SNPS, 0u, ns);
-        else { C.sym(CBCG_S_SNPS, 0u, 0u); C.sym(CBCG_S_INDELS, 0u, ns); C.sym(CBCG_S_INDELS, 0u, nd); C.sym(CBCG_S_INDELS, 0u, ni); }
-    }
-    uint32_t ne = 0;
-    /* deletions (:568-572) */
-    uint32_t prev = 0;
-    for (uint32_t k = 0; k < nd && !C.err; k++) {
-        const uint32_t d_in = (MODE == MODE_DEC) ? 0u : CBCG_EDIT_DELTA(e_in[k]);
-        const uint32_t d = C.sym(CBCG_S_VAR, (prev << 1) | strand, d_in);
-        prev += d;
-        if (MODE == MODE_DEC) {
-            if (lane == 0) { e_out[ne] = CBCG_EDIT(d, 0, 0); C.M->cumdel[k] = (uint16_t)min(prev, 0xffffu); }
-        }
-        ne++;
-    }
-    if (MODE == MODE_DEC) __syncwarp();
-    /* SNPs (:573-593) */
-    prev = 0;
-    for (uint32_t k = 0; k < ns && !C.err; k++) {
-        const uint32_t ed = (MODE == MODE_DEC) ? 0u : e_in[nd + k];
-        const uint32_t delta = C.ring_first(pos - 1u + prev, (prev < len) ? pos - 1u + len : pos - 1u + prev, len + 2u);
-        const uint32_t p = C.sym(CBCG_S_VAR, (((delta << CBCG_BITS_DELTA) + prev) << 1) | strand, CBCG_EDIT_DELTA(ed));
-        if (C.err) break;
-        const uint32_t idx = prev + p;                                          /* index in the insertion-free read */
-        prev += p + 1u;
-        C.ring_set(pos + prev - 2u);                                            /* :589 */
-        uint32_t refb;
-        if (MODE == MODE_DEC) {
-            uint32_t skipped = 0;                                               /* deletions at or before idx (:426-437) */
-            for (uint32_t q = lane; q < nd; q += 32u) skipped += (C.M->cumdel[q] <= idx);
-            skipped = warp_sum(skipped);
-            const uint64_t ri = (uint64_t)pos - 1u + idx + skipped;
-            refb = base_code(ri < ref_len ? (uint32_t)ref[ri] : 0u);
-        } else refb = CBCG_EDIT_REFB(ed);
-        const uint32_t tgt = C.sym(CBCG_S_CHARS, refb, CBCG_EDIT_TARGET(ed));
-        if (MODE == MODE_DEC && lane == 0) e_out[ne] = CBCG_EDIT(p, tgt, refb);
-        ne++;
-    }
-    /* insertions (:594-600) */
-    prev = 0;
-    for (uint32_t k = 0; k < ni && !C.err; k++) {
-        const uint32_t ed = (MODE == MODE_DEC) ? 0u : e_in[nd + ns + k];
-        const uint32_t p = C.sym(CBCG_S_VAR, (prev << 1) | strand, CBCG_EDIT_DELTA(ed));
-        prev += p;
-        const uint32_t tgt = C.sym(CBCG_S_CHARS, CBCG_BP_O, CBCG_EDIT_TARGET(ed));
-        if (MODE == MODE_DEC && lane == 0) e_out[ne] = CBCG_EDIT(p, tgt, CBCG_BP_O);
-        ne++;
-    }
-    n_edits_out = ne;
-}
-
-/* compress_int (src/qv_codebook.c:14-52): 4 bytes MSB first through codebook[0..3] */
-template <int MODE>
-__device__ __forceinline__ uint32_t code_int(Coder<MODE> &C, uint32_t v) {
-    uint32_t r = 0;
-    for (uint32_t k = 0; k < 4u; k++) r |= C.sym(CBCG_S_CODEBOOK, k, (v >> (24u - 8u * k)) & 0xffu) << (24u - 8u * k);
-    return r;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(K2_THREADS)
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
 k2_coder_kernel(CoderParams P) {
     __shared__ WarpModels smodels[K2_WARPS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -815,18 +698,18 @@ k2_coder_kernel(CoderParams P) {
     BlockDesc &B = P.blocks[b];
     const bool legacy = P.legacy != 0;
     const bool primed = P.primed != 0 && MODE != MODE_LIST;
+    const bool lean = P.lean != 0 && MODE != MODE_LIST;
 
     Coder<MODE> C;
     C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &smodels[warp];
-    C.primed = primed; C.lean = P.lean != 0;
+    C.primed = primed; C.lean = lean;
     if (primed) C.snap = SnapView(P.snap, P.L);
     C.L = P.L; C.Lp = (P.L + 1u + 31u) & ~31u;
     /* workspace */
     const uint64_t ws_edits = (MODE == MODE_DEC && legacy) ? 0xffffffffull : B.n_edits;
-    const uint64_t ws_reads = B.n_reads;
     uint32_t decode_L = P.L;
     {
-        const WsLayout w = ws_layout(P.L ? P.L : 252u, ws_reads, ws_edits, legacy, primed);
+        const WsLayout w = ws_layout(P.L ? P.L : 252u, B.n_reads, ws_edits, legacy, primed);
         uint8_t *base = P.ws + B.ws_off;
         C.pos_gcnt = reinterpret_cast<uint32_t *>(base + w.pos_cnt);
         C.pos_gval = reinterpret_cast<uint32_t *>(base + w.pos_val);
@@ -845,126 +728,291 @@ k2_coder_kernel(CoderParams P) {
     if (primed) C.init_from_snapshot(); else C.init_models(legacy);
     C.ring_reset();
     if (MODE != MODE_LIST) C.ac_init();
+    if (!legacy && MODE != MODE_LIST && !primed) C.init_L_models();
+    if (!legacy && MODE == MODE_DEC && B.chr >= P.genome.n_chr) C.err = CBCG_ERR_NO_REFERENCE;
 
-    ReadState<MODE> st; st.prev_pos = B.base_pos; st.prev_m = 0u;
-    uint32_t prev_char = 0u;
-    uint32_t cur_chr = legacy ? 0xffffffffu : B.chr;
+    /* ---- machine state */
+    uint32_t state = legacy ? ST_HDR : ST_READ;
+    uint32_t k = 0;                                      /* sub-index inside a state (header byte, edit ordinal ...) */
+    uint32_t prev_pos = B.base_pos, prev_m = 0u, prev_char = 0u;
+    uint32_t cur_chr = legacy ? 0xffffffffu : B.chr, chr = cur_chr;
     const uint8_t *ref = nullptr; uint64_t ref_len = 0;
     if (!legacy && B.chr < P.genome.n_chr) { ref = P.genome.bases + P.genome.chr_off[B.chr]; ref_len = P.genome.chr_len[B.chr]; }
-
-    if (legacy) {
-        /* stream header: read length, 32 WELL words, LOSSLESS (src/sam_file_allocation.c:363-404,
-           src/compression.c:139) */
-        uint32_t Lh = code_int(C, P.L);
-        for (uint32_t i = 0; i < CBCG_WELL_WORDS; i++) code_int(C, CBCG_WELL_DEBUG);
-        uint32_t lossy = code_int(C, CBCG_LOSSLESS);
-        if (MODE == MODE_DEC) {
-            if (C.err || Lh == 0u || Lh > CBCG_MAX_READ_LEN || lossy != CBCG_LOSSLESS) C.err = C.err ? C.err : CBCG_ERR_FORMAT;
-            else { C.L = Lh; decode_L = Lh; }
-        }
-    } else if (MODE == MODE_DEC && B.chr >= P.genome.n_chr) C.err = CBCG_ERR_NO_REFERENCE;
-    if (MODE != MODE_LIST && !C.err && !primed) C.init_L_models();
-
     const uint64_t r0 = B.first_read;
-    uint64_t e_cursor = B.edit_base;
-    uint32_t n_done = 0;
     const uint32_t n_reads = B.n_reads;                 /* legacy decode: capacity, the end marker stops the loop */
     const uint64_t edits_cap_abs = B.edit_base + B.n_edits;
+    uint64_t e_cursor = B.edit_base;
+    uint32_t i = 0, n_done = 0;
+    /* the read in flight */
+    uint32_t pos = 0, len = 0, flag = 0, match = 0, ns = 0, nd = 0, ni = 0, strand = 0, samepos = 0, posx = 0, acc = 0;
+    uint32_t prev = 0, ne = 0, ed = 0, edp = 0, refb = 0, change = 0, hdr_L = 0;
+    const uint16_t *e_in = P.edits;
+    const uint8_t *name = P.chr_names;
 
-    for (uint32_t i = 0; !C.err; i++) {
-        if (!(legacy && MODE == MODE_DEC) && i >= n_reads) break;
-        const uint64_t r = r0 + i;
-        __align__(16) cbcg_read_rec rec;
-        uint32_t chr = cur_chr;
-        if (MODE != MODE_DEC) {
-            *reinterpret_cast<uint4 *>(&rec) = reinterpret_cast<const uint4 *>(P.recs)[r];
-            chr = P.chr[r];
-        } else { rec.pos = 0; rec.flag = 0; rec.len = 0; rec.edit_off = 0; rec.match = 0; rec.n_snps = rec.n_dels = rec.n_ins = 0; }
-
-        /* compress_rname / decompress_rname (src/id_compression.c:39-94) */
-        if (legacy) {
-            bool change;
-            if (MODE == MODE_DEC) {
-                change = C.sym(CBCG_S_SAME_REF, 0u, 0u) != 0u;
-                if (C.err) break;
-                if (change) {
-                    bool end = false; uint32_t ch;
-                    while (!C.err && (ch = C.sym(CBCG_S_RNAME, prev_char, 0u)) != 0u) {
-                        if (ch == '\n') { end = true; break; }
-                        prev_char = ch;
-                    }
-                    if (C.err || end) break;
-                    chr = cur_chr + 1u;                  /* records are taken in FASTA order (src/compression.c:91-101) */
+    while (!C.err && state != ST_DONE) {
+        /* ================================================ 1. what is the next symbol? */
+        uint32_t kind = K_DENSE, card = 0, step = 0, x = 0, key = 0, ctx = 0;
+        uint32_t *m = nullptr;
+        bool is_var = false;
+        switch (state) {
+            case ST_HDR: {                               /* 34 ints x 4 bytes, MSB first, through codebook[0..3] (compress_int) */
+                const uint32_t word = k >> 2, byte = k & 3u;
+                const uint32_t v = word == 0u ? P.L : (word == 33u ? CBCG_LOSSLESS : CBCG_WELL_DEBUG);
+                x = (v >> (24u - 8u * byte)) & 0xffu;
+                m = C.codebook + byte * 257u; card = 256u; step = 1u; key = CBCG_SYM_KEY(CBCG_S_CODEBOOK, byte);
+                break;
+            }
+            case ST_READ: {                              /* not a symbol: fetch the next read */
+                kind = K_NONE;
+                if (!(legacy && MODE == MODE_DEC) && i >= n_reads) { state = (legacy && MODE != MODE_DEC) ? ST_ENDMARK : ST_DONE; k = 0; break; }
+                if (MODE != MODE_DEC) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(P.recs)[r0 + i];
+                    pos = v.x; flag = v.y & 0xffffu; len = v.y >> 16; match = v.w & 0xffu;
+                    ns = (v.w >> 8) & 0xffu; nd = (v.w >> 16) & 0xffu; ni = v.w >> 24;
+                    e_in = P.edits + v.z;
+                    chr = P.chr[r0 + i];
                     if (chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; break; }
+                    if (legacy) { change = chr != cur_chr; state = ST_SAMEREF; }
+                    else {
+                        if (chr != cur_chr) { C.err = CBCG_ERR_INTERNAL; break; }      /* blocks never span chromosomes */
+                        change = 0; state = lean ? ST_RLEN0 : ST_SAMEREF;
+                    }
+                } else { change = 0; state = (legacy || !lean) ? ST_SAMEREF : ST_RLEN0; }
+                break;
+            }
+            case ST_SAMEREF: m = C.M->same_ref; card = 2u; step = 10u; x = change; key = CBCG_SYM_KEY(CBCG_S_SAME_REF, 0u); break;
+            case ST_RNAME:                               /* name bytes then 0, context = previous byte (never reset) */
+                x = (MODE != MODE_DEC && k < MAX_NAME) ? (uint32_t)name[k] : 0u;
+                m = C.rname + prev_char * 257u; card = 256u; step = 10u; key = CBCG_SYM_KEY(CBCG_S_RNAME, prev_char);
+                break;
+            case ST_RLEN0: m = C.M->rlen0; card = 255u; step = 10u; x = len & 0xffu; key = CBCG_SYM_KEY(CBCG_S_RLENGTH, 0u); break;
+            case ST_RLENK: kind = K_RLENK; x = 0u; key = CBCG_SYM_KEY(CBCG_S_RLENGTH, k); break;    /* bytes 1..3 are always 0 (:29-33) */
+            case ST_POS:
+                kind = K_POS; key = CBCG_SYM_KEY(CBCG_S_POS_X, 0u);
+                if (MODE != MODE_DEC) {
+                    if (pos == 0u || len == 0u || len > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_INPUT; break; }
+                    if (pos < prev_pos || pos - prev_pos + 1u > CBCG_MAX_POS_X) { C.err = CBCG_ERR_INPUT; break; }
+                    x = pos - prev_pos + 1u;
                 }
-                if (cur_chr == 0xffffffffu && !change) { C.err = CBCG_ERR_CORRUPT; break; }
-                if (i >= n_reads) { C.err = CBCG_ERR_CAPACITY; break; }
-            } else {
-                change = (chr != cur_chr);
-                if (chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; break; }
-                if (change) {
-                    C.sym(CBCG_S_SAME_REF, 0u, 1u);
-                    const uint8_t *name = P.chr_names + (uint64_t)chr * MAX_NAME;
-                    for (uint32_t q = 0; q < MAX_NAME && name[q]; q++) { C.sym(CBCG_S_RNAME, prev_char, name[q]); prev_char = name[q]; }
-                    C.sym(CBCG_S_RNAME, prev_char, 0u);
-                } else C.sym(CBCG_S_SAME_REF, 0u, 0u);
+                break;
+            case ST_POSESC:                              /* the escaped value, 4 bytes MSB first (compress_pos_alpha :75-108) */
+                if (k == 0u) C.pa_ensure();
+                m = C.pos_alpha + k * 257u; card = 256u; step = 10u; x = (posx >> (24u - 8u * k)) & 0xffu;
+                key = CBCG_SYM_KEY(CBCG_S_POS_ALPHA, k);
+                break;
+            case ST_FLAG: kind = K_FLAG; x = flag; key = CBCG_SYM_KEY(CBCG_S_FLAG, 0u); break;
+            case ST_MATCH: ctx = (samepos << 1) | prev_m; m = C.M->match[ctx]; card = 2u; step = 1u; x = match; key = CBCG_SYM_KEY(CBCG_S_MATCH, ctx); break;
+            case ST_SNPS: m = C.M->snps; card = C.L; step = 10u; x = ((nd | ni) == 0u) ? ns : 0u; key = CBCG_SYM_KEY(CBCG_S_SNPS, 0u); break;
+            case ST_INDELS: m = C.M->indels; card = C.L; step = 16u; x = k == 0u ? ns : (k == 1u ? nd : ni); key = CBCG_SYM_KEY(CBCG_S_INDELS, 0u); break;
+            case ST_DEL:                                 /* :568-572 */
+                if (MODE != MODE_DEC) ed = e_in[k];
+                ctx = (prev << 1) | strand; is_var = true; x = CBCG_EDIT_DELTA(ed);
+                break;
+            case ST_SNPVAR: {                            /* :573-593 */
+                if (MODE != MODE_DEC) ed = e_in[nd + k];
+                const uint32_t delta = C.ring_first(pos - 1u + prev, (prev < len) ? pos - 1u + len : pos - 1u + prev, len + 2u);
+                ctx = (((delta << CBCG_BITS_DELTA) + prev) << 1) | strand; is_var = true; x = CBCG_EDIT_DELTA(ed);
+                break;
             }
-            if (change) {                                /* src/compression.c:58-64 */
-                cur_chr = chr;
-                st.prev_pos = 0u;
-                C.ring_reset();
-                ref = P.genome.bases + P.genome.chr_off[chr]; ref_len = P.genome.chr_len[chr];
-            }
-        } else {
-            if (MODE != MODE_DEC && chr != cur_chr) { C.err = CBCG_ERR_INTERNAL; break; }   /* blocks never span chromosomes */
-            if (!C.lean || MODE == MODE_LIST) {
-                const uint32_t same = C.sym(CBCG_S_SAME_REF, 0u, 0u);
-                if (MODE == MODE_DEC && same != 0u) { C.err = CBCG_ERR_CORRUPT; break; }
-            }
+            case ST_SNPCHAR: m = C.M->chars[refb]; card = 5u; step = 8u; x = CBCG_EDIT_TARGET(ed); key = CBCG_SYM_KEY(CBCG_S_CHARS, refb); break;
+            case ST_INSVAR:                              /* :594-600 */
+                if (MODE != MODE_DEC) ed = e_in[nd + ns + k];
+                ctx = (prev << 1) | strand; is_var = true; x = CBCG_EDIT_DELTA(ed);
+                break;
+            case ST_INSCHAR: m = C.M->chars[CBCG_BP_O]; card = 5u; step = 8u; x = CBCG_EDIT_TARGET(ed); key = CBCG_SYM_KEY(CBCG_S_CHARS, CBCG_BP_O); break;
+            case ST_READ_END:
+                kind = K_NONE;
+                if (MODE == MODE_DEC) {
+                    if (lane == 0) {
+                        uint4 v;
+                        v.x = pos; v.y = flag | (len << 16); v.z = (uint32_t)e_cursor;
+                        v.w = match | (match ? 0u : ((ns << 8) | (nd << 16) | (ni << 24)));
+                        reinterpret_cast<uint4 *>(P.recs)[r0 + i] = v;
+                        P.chr[r0 + i] = cur_chr;
+                    }
+                    e_cursor += ne;
+                }
+                n_done++; i++; state = ST_READ;
+                break;
+            case ST_ENDMARK:                             /* end of stream: name "\n" (src/compression.c:152) */
+                if (k == 0u) { m = C.M->same_ref; card = 2u; step = 10u; x = 1u; key = CBCG_SYM_KEY(CBCG_S_SAME_REF, 0u); }
+                else { x = k == 1u ? (uint32_t)'\n' : 0u; m = C.rname + prev_char * 257u; card = 256u; step = 10u; key = CBCG_SYM_KEY(CBCG_S_RNAME, prev_char); }
+                break;
+            default: C.err = CBCG_ERR_INTERNAL; break;
         }
         if (C.err) break;
+        if (kind == K_NONE) continue;
+        if (is_var) {
+            key = CBCG_SYM_KEY(CBCG_S_VAR, ctx);
+            card = C.L; step = 10u;
+            if (MODE != MODE_LIST) { m = C.var_row(ctx); if (!m) break; }
+        }
 
-        uint32_t ne = 0;
-        const uint64_t room64 = edits_cap_abs - e_cursor;
-        const uint32_t room = room64 > 0xffffffffull ? 0xffffffffu : (uint32_t)room64;
-        code_read<MODE>(C, st, rec, P.edits + (MODE == MODE_DEC ? 0 : rec.edit_off), P.edits + e_cursor, ne, room, ref, ref_len);
+        /* ================================================ 2. code it: one call site per model kind */
+        uint32_t y = x, slot = 1u;
+        if (MODE == MODE_LIST) C.list_put(key >> 24, key & 0xffffffu, x);
+        else if (kind == K_DENSE) y = C.sym_dense(m, card, step, x);
+        else if (kind == K_FLAG) y = C.sym_flag(x);
+        else if (kind == K_POS) y = C.sym_pos_main(x, slot);
+        else y = C.sym_rlenk(k - 1u, x);
         if (C.err) break;
-        if (MODE == MODE_DEC) {
-            rec.edit_off = (uint32_t)e_cursor;
-            if (lane == 0) { reinterpret_cast<uint4 *>(P.recs)[r] = *reinterpret_cast<uint4 *>(&rec); P.chr[r] = cur_chr; }
-            e_cursor += ne;
+
+        /* ================================================ 3. consume the value, pick the next state */
+        switch (state) {
+            case ST_HDR:
+                if (MODE == MODE_DEC) {
+                    const uint32_t word = k >> 2, byte = k & 3u;
+                    if (word == 0u) hdr_L |= y << (24u - 8u * byte);
+                    else if (y != (((word == 33u ? CBCG_LOSSLESS : 0u) >> (24u - 8u * byte)) & 0xffu) && word == 33u) C.err = CBCG_ERR_FORMAT;
+                }
+                if (++k == 136u) {
+                    if (MODE == MODE_DEC) {
+                        if (hdr_L == 0u || hdr_L > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_FORMAT; break; }
+                        C.L = hdr_L; decode_L = hdr_L;
+                    }
+                    if (MODE != MODE_LIST) C.init_L_models();         /* alloc_read_models_t runs after the header int (:371-375) */
+                    state = ST_READ;
+                }
+                break;
+            case ST_SAMEREF:
+                if (MODE == MODE_DEC) {
+                    if (!legacy) { if (y != 0u) { C.err = CBCG_ERR_CORRUPT; break; } }
+                    else change = y;
+                }
+                if (change) { state = ST_RNAME; k = 0; if (MODE != MODE_DEC) name = P.chr_names + (uint64_t)chr * MAX_NAME; break; }
+                if (legacy && MODE == MODE_DEC) {
+                    if (cur_chr == 0xffffffffu) { C.err = CBCG_ERR_CORRUPT; break; }
+                    if (i >= n_reads) { C.err = CBCG_ERR_CAPACITY; break; }
+                }
+                state = ST_RLEN0;
+                break;
+            case ST_RNAME: {
+                bool name_done = false;
+                if (MODE == MODE_DEC) {
+                    if (y == (uint32_t)'\n') { state = ST_DONE; break; }               /* end marker (decompress_rname :82-84) */
+                    if (y == 0u) { name_done = true; chr = cur_chr + 1u; }              /* records are taken in FASTA order */
+                    else prev_char = y;
+                } else { if (x == 0u) name_done = true; else { prev_char = x; k++; } }
+                if (name_done) {
+                    if (chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; break; }
+                    if (MODE == MODE_DEC && i >= n_reads) { C.err = CBCG_ERR_CAPACITY; break; }
+                    cur_chr = chr; prev_pos = 0u; C.ring_reset();                      /* src/compression.c:58-64 */
+                    ref = P.genome.bases + P.genome.chr_off[chr]; ref_len = P.genome.chr_len[chr];
+                    state = ST_RLEN0;
+                }
+                break;
+            }
+            case ST_RLEN0:
+                if (MODE == MODE_DEC) len = y;
+                if (lean) state = ST_POS; else { state = ST_RLENK; k = 1; }
+                break;
+            case ST_RLENK:
+                if (MODE == MODE_DEC) len |= y << (8u * k);
+                if (++k == 4u) state = ST_POS;
+                break;
+            case ST_POS:
+                if (MODE == MODE_DEC) x = y;
+                if (MODE != MODE_LIST && slot == 0u) { posx = x; acc = 0; k = 0; state = ST_POSESC; break; }
+                posx = x; goto pos_done;
+            case ST_POSESC:
+                acc |= y << (24u - 8u * k);
+                if (++k < 4u) break;
+                if (MODE == MODE_DEC) posx = acc;
+                C.pos_append(posx);
+                if (C.err) break;
+            pos_done:
+                if (MODE == MODE_DEC) {
+                    if (posx == 0u) { C.err = CBCG_ERR_CORRUPT; break; }
+                    pos = prev_pos + posx - 1u;
+                    if (pos == 0u || len == 0u || len > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_CORRUPT; break; }
+                }
+                samepos = posx == 1u;
+                prev_pos = pos;
+                C.ring_advance(pos);
+                state = ST_FLAG;
+                break;
+            case ST_FLAG: flag = y; strand = (flag >> 4) & 1u; state = ST_MATCH; break;       /* :57-60 */
+            case ST_MATCH:
+                match = y; prev_m = y; ne = 0;
+                if (MODE == MODE_DEC) { ns = nd = ni = 0; }
+                state = match ? ST_READ_END : ST_SNPS;
+                break;
+            case ST_SNPS:
+                if (MODE == MODE_DEC) { ns = y; nd = ni = 0; if (y == 0u) { state = ST_INDELS; k = 0; break; } }
+                else if ((nd | ni) != 0u) { state = ST_INDELS; k = 0; break; }
+                goto counts_done;
+            case ST_INDELS:
+                if (MODE == MODE_DEC) { if (k == 0u) ns = y; else if (k == 1u) nd = y; else ni = y; }
+                if (++k < 3u) break;
+            counts_done:
+                if (MODE == MODE_DEC) {
+                    if (ni > len || ns > 255u || nd > 255u || ni > 255u) { C.err = CBCG_ERR_CORRUPT; break; }
+                    if ((uint64_t)(ns + nd + ni) > edits_cap_abs - e_cursor) { C.err = CBCG_ERR_CAPACITY; break; }
+                }
+                prev = 0; k = 0; ne = 0;
+                state = nd ? ST_DEL : (ns ? ST_SNPVAR : (ni ? ST_INSVAR : ST_READ_END));
+                break;
+            case ST_DEL:
+                prev += y;
+                if (MODE == MODE_DEC && lane == 0) { P.edits[e_cursor + ne] = CBCG_EDIT(y, 0, 0); C.M->cumdel[k] = (uint16_t)min(prev, 0xffffu); }
+                ne++;
+                if (++k == nd) {
+                    if (MODE == MODE_DEC) SYNCW();
+                    prev = 0; k = 0;
+                    state = ns ? ST_SNPVAR : (ni ? ST_INSVAR : ST_READ_END);
+                }
+                break;
+            case ST_SNPVAR: {
+                edp = y;
+                const uint32_t idx = prev + y;                                         /* index in the insertion-free read */
+                prev += y + 1u;
+                C.ring_set(pos + prev - 2u);                                           /* :589 */
+                if (MODE == MODE_DEC) {
+                    uint32_t skipped = 0;                                              /* deletions at or before idx (:426-437) */
+                    for (uint32_t q = lane; q < nd; q += 32u) skipped += (C.M->cumdel[q] <= idx);
+                    skipped = warp_sum(skipped);
+                    const uint64_t ri = (uint64_t)pos - 1u + idx + skipped;
+                    refb = base_code(ri < ref_len ? (uint32_t)ref[ri] : 0u);
+                } else refb = CBCG_EDIT_REFB(ed);
+                state = ST_SNPCHAR;
+                break;
+            }
+            case ST_SNPCHAR:
+                if (MODE == MODE_DEC && lane == 0) P.edits[e_cursor + ne] = CBCG_EDIT(edp, y, refb);
+                ne++;
+                if (++k == ns) { prev = 0; k = 0; state = ni ? ST_INSVAR : ST_READ_END; } else state = ST_SNPVAR;
+                break;
+            case ST_INSVAR: edp = y; prev += y; state = ST_INSCHAR; break;
+            case ST_INSCHAR:
+                if (MODE == MODE_DEC && lane == 0) P.edits[e_cursor + ne] = CBCG_EDIT(edp, y, CBCG_BP_O);
+                ne++;
+                state = (++k == ni) ? ST_READ_END : ST_INSVAR;
+                break;
+            case ST_ENDMARK:
+                if (k == 1u) prev_char = '\n';
+                if (++k == 3u) state = ST_DONE;
+                break;
+            default: C.err = CBCG_ERR_INTERNAL; break;
         }
-        n_done++;
     }
 
-    if (MODE == MODE_ENC && !C.err) {
-        if (legacy) {                                    /* end-of-stream marker: name "\n" (src/compression.c:152) */
-            C.sym(CBCG_S_SAME_REF, 0u, 1u);
-            C.sym(CBCG_S_RNAME, prev_char, '\n'); prev_char = '\n';
-            C.sym(CBCG_S_RNAME, prev_char, 0u);
-        }
-        if (!C.err) { if (P.short_flush && !legacy) C.ac_flush_short(); else C.ac_flush(); }
-    }
-    if (MODE == MODE_LIST && legacy && !C.err) {
-        C.sym(CBCG_S_SAME_REF, 0u, 1u);
-        C.sym(CBCG_S_RNAME, prev_char, '\n');
-        C.sym(CBCG_S_RNAME, '\n', 0u);
-    }
+    if (MODE == MODE_ENC && !C.err) { if (P.short_flush && !legacy) C.ac_flush_short(); else C.ac_flush(); }
     if (C.err) dev_set_error(P.err, C.err, ((uint64_t)b << 20) | (n_done & 0xfffffu));
     if (primed && P.fin && !C.err) {                     /* final state for the generation merge */
-        __syncwarp();
+        SYNCW();
         uint32_t *dst = reinterpret_cast<uint32_t *>(P.fin + (uint64_t)bl * fin_stride_dev());
         const uint32_t *src = reinterpret_cast<const uint32_t *>(C.M);
-        for (uint32_t i = lane; i < (uint32_t)(sizeof(WarpModels) / 4u); i += 32u) dst[i] = src[i];
+        for (uint32_t q = lane; q < (uint32_t)(sizeof(WarpModels) / 4u); q += 32u) dst[q] = src[q];
         if (lane < C.pos_card) { C.pos_gval[lane] = C.pos_rv; C.pos_gcnt[lane] = C.pos_rc; }
         if (lane == 0) { B.pos_card = C.pos_card; B.n_rows = C.n_rows; B.pa_touched = C.pa_init ? 1u : 0u; }
     }
     if (lane == 0) {
         B.n_symbols = (MODE == MODE_LIST) ? C.list_n : C.n_symbols;
         if (MODE == MODE_ENC) B.payload_bytes = C.out_pos;
-        if (MODE == MODE_DEC) { B.n_reads = n_done; B.n_edits = (uint32_t)(e_cursor - B.edit_base); B.gen = decode_L; }
+        if (MODE == MODE_DEC) { B.n_reads = n_done; B.n_edits = (uint32_t)(e_cursor - B.edit_base); B.pad = decode_L; }
     }
 }
+
 
 int launch_coder(const CoderParams &p, cudaStream_t st) {
     if (p.n_blocks == 0) return 0;
@@ -1115,7 +1163,7 @@ __global__ void __launch_bounds__(32) snapshot_init_kernel(uint8_t *snap, uint32
     C.init_models(false);
     C.init_L_models();
     for (uint32_t i = lane; i < 256u; i += 32u) M.cumdel[i] = 0;
-    __syncwarp();
+    SYNCW();
     uint32_t *small = reinterpret_cast<uint32_t *>(snap + l.small);
     const uint32_t *src = reinterpret_cast<const uint32_t *>(&M);
     for (uint32_t i = lane; i < (uint32_t)(sizeof(WarpModels) / 4u); i += 32u) small[i] = src[i];
@@ -1139,89 +1187,194 @@ struct MergeParams {
     unsigned long long *err;
 };
 
-/* One dense model by one warp. fin(b) -> the block's counts, or NULL when the block never touched the model. */
-template <class Fin>
-__device__ __forceinline__ void merge_dense(uint32_t lane, const uint32_t *prev_m, uint32_t *next_m, uint32_t card,
-                                            uint32_t implicit_ones, uint32_t n_blocks, Fin fin) {
-    uint32_t nsum = 0;
-    for (uint32_t i0 = 0; i0 < card; i0 += 32u) {
-        const uint32_t i = i0 + lane;
-        uint32_t p = 0, acc = 0;
-        if (i < card) { p = prev_m[i]; acc = p; }
-        for (uint32_t b = 0; b < n_blocks; b++) {
-            const uint32_t *f = fin(b);
-            if (f && i < card) acc += f[i] - p;
-        }
-        if (i < card) {
-            int32_t v = (int32_t)acc; const int32_t fl = p == 0u ? 0 : 1;
-            if (v < fl) v = fl;
-            next_m[i] = (uint32_t)v; nsum += (uint32_t)v;
+/* Offsets (in words) of the count arrays of WarpModels that the merge handles as dense models. */
+#define WM_W(field) ((uint32_t)(offsetof(WarpModels, field) / 4u))
+
+/* merge step 1: dense FLAG scratch = the snapshot's counts (1 where untouched); rows new to the snapshot are
+ * created (all ones) by whichever block flips their bit. */
+__global__ void __launch_bounds__(128) merge_prep_kernel(MergeParams P) {
+    const SnapLayout l = snap_layout(P.L);
+    const uint32_t gtid = blockIdx.x * 128u + threadIdx.x, gsz = gridDim.x * 128u;
+    const WarpModels *pm = reinterpret_cast<const WarpModels *>(P.prev + l.small);
+    uint32_t *dprev = reinterpret_cast<uint32_t *>(P.next + l.flag_prev), *dacc = reinterpret_cast<uint32_t *>(P.next + l.flag_acc);
+    const uint32_t used = pm->flag_used;
+    for (uint32_t i = gtid; i < 65536u; i += gsz) {
+        uint32_t c = 1u;
+        for (uint32_t j = 0; j < used; j++) if (pm->flag_key[j] == i) c = pm->flag_cnt[j];
+        dprev[i] = c; dacc[i] = c;
+    }
+    /* var rows */
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint32_t *bm = reinterpret_cast<uint32_t *>(P.next + l.bitmap);
+    uint32_t *var = reinterpret_cast<uint32_t *>(P.next + l.var);
+    for (uint32_t b = blockIdx.x * 4u + warp; b < P.n_blocks; b += gridDim.x * 4u) {
+        const BlockDesc &B = P.blocks[P.block_begin + b];
+        const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+        const uint64_t *hash = reinterpret_cast<const uint64_t *>(P.ws + B.ws_off + w.var_hash);
+        for (uint32_t h0 = 0; h0 < w.hash_cap; h0 += 32u) {
+            const uint64_t sl = hash[h0 + lane];
+            const uint32_t key = (uint32_t)(sl >> 32);
+            bool won = false; uint32_t ctx = 0;
+            if (key) { ctx = key - 1u; const uint32_t bit = 1u << (ctx & 31u); won = !(atomicOr(&bm[ctx >> 5], bit) & bit); }
+            uint32_t wm = __ballot_sync(FULL_MASK, won);
+            while (wm) {
+                const uint32_t src = (uint32_t)__ffs(wm) - 1u; wm &= wm - 1u;
+                const uint32_t c = __shfl_sync(FULL_MASK, ctx, src);
+                uint32_t *row = var + (uint64_t)c * l.Lp;
+                for (uint32_t i = lane; i < P.L; i += 32u) row[i] = 1u;
+                if (lane == 0) row[P.L] = P.L;
+            }
         }
     }
-    __syncwarp();
-    uint32_t n = warp_sum(nsum) + implicit_ones;
+}
+
+/* merge step 2, one warp per block: every count of the block minus the snapshot's, added into `next`
+ * (which starts as a copy of the snapshot). Wrapping 32-bit sums; step 3 reads them back as signed. */
+__global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t b = blockIdx.x * 4u + warp;
+    if (b >= P.n_blocks) return;
+    const SnapLayout l = snap_layout(P.L);
+    const BlockDesc &B = P.blocks[P.block_begin + b];
+    const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+    const uint8_t *wsb = P.ws + B.ws_off;
+    /* small models: every word from snps up to the FLAG table (the n slots are recomputed in step 3) */
+    {
+        const uint32_t *ps = reinterpret_cast<const uint32_t *>(P.prev + l.small);
+        uint32_t *ns = reinterpret_cast<uint32_t *>(P.next + l.small);
+        const uint32_t *fs = reinterpret_cast<const uint32_t *>(P.fin + (uint64_t)b * fin_stride_dev());
+        for (uint32_t i = WM_W(snps) + lane; i < WM_W(flag_key); i += 32u) { const uint32_t d = fs[i] - ps[i]; if (d) atomicAdd(&ns[i], d); }
+        /* FLAG: the block's touched values against the dense scratch */
+        const WarpModels *fm = reinterpret_cast<const WarpModels *>(fs);
+        const uint32_t *dprev = reinterpret_cast<const uint32_t *>(P.next + l.flag_prev);
+        uint32_t *dacc = reinterpret_cast<uint32_t *>(P.next + l.flag_acc);
+        const uint32_t used = fm->flag_used;
+        for (uint32_t j = lane; j < used; j += 32u) { const uint32_t k = fm->flag_key[j] & 0xffffu; const uint32_t d = fm->flag_cnt[j] - dprev[k]; if (d) atomicAdd(&dacc[k], d); }
+    }
+    /* POS slots the block shares with the snapshot */
+    {
+        const uint32_t pc = reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr)[0];
+        const uint32_t *pcnt = reinterpret_cast<const uint32_t *>(P.prev + l.pos_cnt);
+        uint32_t *ncnt = reinterpret_cast<uint32_t *>(P.next + l.pos_cnt);
+        const uint32_t *bcnt = reinterpret_cast<const uint32_t *>(wsb + w.pos_cnt);
+        for (uint32_t s = lane; s < pc; s += 32u) { const uint32_t d = bcnt[s] - pcnt[s]; if (d) atomicAdd(&ncnt[s], d); }
+    }
+    if (B.pa_touched) {
+        const uint32_t *pa_prev = reinterpret_cast<const uint32_t *>(P.prev + l.pos_alpha);
+        uint32_t *pa_next = reinterpret_cast<uint32_t *>(P.next + l.pos_alpha);
+        const uint32_t *pa_blk = reinterpret_cast<const uint32_t *>(wsb + w.pos_alpha);
+        for (uint32_t i = lane; i < 4u * 257u; i += 32u) { const uint32_t d = pa_blk[i] - pa_prev[i]; if (d) atomicAdd(&pa_next[i], d); }
+    }
+    /* var rows */
+    {
+        const uint32_t *pbm = reinterpret_cast<const uint32_t *>(P.prev + l.bitmap);
+        const uint32_t *pvar = reinterpret_cast<const uint32_t *>(P.prev + l.var);
+        uint32_t *var = reinterpret_cast<uint32_t *>(P.next + l.var);
+        const uint64_t *hash = reinterpret_cast<const uint64_t *>(wsb + w.var_hash);
+        const uint32_t *rows = reinterpret_cast<const uint32_t *>(wsb + w.var_rows);
+        for (uint32_t h0 = 0; h0 < w.hash_cap; h0 += 32u) {
+            const uint64_t sl = hash[h0 + lane];
+            uint32_t km = __ballot_sync(FULL_MASK, (uint32_t)(sl >> 32) != 0u);
+            while (km) {
+                const uint32_t src = (uint32_t)__ffs(km) - 1u; km &= km - 1u;
+                const uint64_t e = __shfl_sync(FULL_MASK, sl, src);
+                const uint32_t ctx = (uint32_t)(e >> 32) - 1u, r = (uint32_t)e;
+                const bool in_prev = (pbm[ctx >> 5] >> (ctx & 31u)) & 1u;
+                const uint32_t *row = rows + (uint64_t)r * w.Lp, *prow = pvar + (uint64_t)ctx * l.Lp;
+                uint32_t *nrow = var + (uint64_t)ctx * l.Lp;
+                for (uint32_t i = lane; i < P.L; i += 32u) {
+                    const uint32_t d = row[i] - (in_prev ? prow[i] : 1u);
+                    if (d) atomicAdd(&nrow[i], d);
+                }
+            }
+        }
+    }
+}
+
+/* clamp to >= floor, total, rescale: one dense model by one warp (counts already summed in place). */
+__device__ __forceinline__ void finish_dense(uint32_t lane, const uint32_t *prev_m, uint32_t *m, uint32_t card, uint32_t implicit_ones) {
+    uint32_t s = 0;
+    for (uint32_t i = lane; i < card; i += 32u) {
+        int32_t v = (int32_t)m[i]; const int32_t fl = (prev_m && prev_m[i] == 0u) ? 0 : 1;
+        if (v < fl) v = fl;
+        m[i] = (uint32_t)v; s += (uint32_t)v;
+    }
+    uint32_t n = warp_sum(s) + implicit_ones;
     while (n >= CBCG_RESCALE) {
-        uint32_t s = 0;
-        for (uint32_t i = lane; i < card; i += 32u) { const uint32_t c = (next_m[i] >> 1) + 1u; next_m[i] = c; s += c; }
+        s = 0;
+        for (uint32_t i = lane; i < card; i += 32u) { const uint32_t c = (m[i] >> 1) + 1u; m[i] = c; s += c; }
         n = warp_sum(s) + implicit_ones;
     }
-    if (lane == 0) next_m[card] = n;
+    if (lane == 0) m[card] = n;
     __syncwarp();
 }
 
-#define MERGE_SMALL_WARPS 21u
-__global__ void __launch_bounds__(MERGE_SMALL_WARPS * 32u) merge_small_kernel(MergeParams P) {
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+/* merge step 3 (one CTA): small models, pos_alpha, POS (values new to the snapshot are appended in block
+ * order, then order of appearance), FLAG back to its sorted sparse form. */
+#define MERGE_FIN_WARPS 32u
+__global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(MergeParams P) {
+    __shared__ uint32_t red[32];
+    __shared__ uint32_t scan[1024];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const SnapLayout l = snap_layout(P.L);
     const uint32_t *ps = reinterpret_cast<const uint32_t *>(P.prev + l.small);
     uint32_t *ns = reinterpret_cast<uint32_t *>(P.next + l.small);
-    const uint64_t stride = fin_stride_dev();
-    uint32_t off = 0, card = 0, ones = 0;
-    if (warp == 0)       { off = offsetof(WarpModels, snps) / 4u;   card = P.L; }
-    else if (warp == 1)  { off = offsetof(WarpModels, indels) / 4u; card = P.L; }
-    else if (warp == 2)  { off = offsetof(WarpModels, rlen0) / 4u;  card = 255u; }
-    else if (warp < 9)   { off = offsetof(WarpModels, chars) / 4u + (warp - 3u) * 8u; card = 5u; }
-    else if (warp < 13)  { off = offsetof(WarpModels, match) / 4u + (warp - 9u) * 4u; card = 2u; }
-    else if (warp == 13) { off = offsetof(WarpModels, same_ref) / 4u; card = 2u; }
-    else if (warp < 17)  { off = offsetof(WarpModels, rlenk) / 4u + (warp - 14u) * 2u; card = 1u; ones = 254u; }
-    if (warp < 17) {
-        const uint8_t *fin = P.fin;
-        merge_dense(lane, ps + off, ns + off, card, ones, P.n_blocks,
-                    [=](uint32_t b) { return reinterpret_cast<const uint32_t *>(fin + (uint64_t)b * stride) + off; });
-    } else {                                              /* pos_alpha[k]: lives in each block's workspace, if instantiated */
+    if (warp == 0)       finish_dense(lane, ps + WM_W(snps), ns + WM_W(snps), P.L, 0u);
+    else if (warp == 1)  finish_dense(lane, ps + WM_W(indels), ns + WM_W(indels), P.L, 0u);
+    else if (warp == 2)  finish_dense(lane, ps + WM_W(rlen0), ns + WM_W(rlen0), 255u, 0u);
+    else if (warp < 9)   finish_dense(lane, ps + WM_W(chars) + (warp - 3u) * 8u, ns + WM_W(chars) + (warp - 3u) * 8u, 5u, 0u);
+    else if (warp < 13)  finish_dense(lane, ps + WM_W(match) + (warp - 9u) * 4u, ns + WM_W(match) + (warp - 9u) * 4u, 2u, 0u);
+    else if (warp == 13) finish_dense(lane, ps + WM_W(same_ref), ns + WM_W(same_ref), 2u, 0u);
+    else if (warp < 17)  finish_dense(lane, ps + WM_W(rlenk) + (warp - 14u) * 2u, ns + WM_W(rlenk) + (warp - 14u) * 2u, 1u, 254u);
+    else if (warp < 21) {
         const uint32_t k = warp - 17u;
-        const uint32_t *pa_prev = reinterpret_cast<const uint32_t *>(P.prev + l.pos_alpha) + k * 257u;
-        uint32_t *pa_next = reinterpret_cast<uint32_t *>(P.next + l.pos_alpha) + k * 257u;
-        const BlockDesc *blocks = P.blocks + P.block_begin; const uint8_t *ws = P.ws; const uint32_t L = P.L;
-        merge_dense(lane, pa_prev, pa_next, 256u, 0u, P.n_blocks, [=](uint32_t b) -> const uint32_t * {
-            const BlockDesc &B = blocks[b];
-            if (!B.pa_touched) return nullptr;
-            const WsLayout w = ws_layout(L, B.n_reads, B.n_edits, 0, 1);
-            return reinterpret_cast<const uint32_t *>(ws + B.ws_off + w.pos_alpha) + k * 257u;
-        });
+        finish_dense(lane, reinterpret_cast<const uint32_t *>(P.prev + l.pos_alpha) + k * 257u,
+                     reinterpret_cast<uint32_t *>(P.next + l.pos_alpha) + k * 257u, 256u, 0u);
+    } else if (warp == 21) {
+        const uint32_t pc = reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr)[0];
+        uint32_t *nhdr = reinterpret_cast<uint32_t *>(P.next + l.pos_hdr);
+        uint32_t *nval = reinterpret_cast<uint32_t *>(P.next + l.pos_val), *ncnt = reinterpret_cast<uint32_t *>(P.next + l.pos_cnt);
+        const BlockDesc *blocks = P.blocks + P.block_begin;
+        uint32_t an = pc;
+        for (uint32_t b0 = 0; b0 < P.n_blocks; b0 += 32u) {
+            const uint32_t bb = b0 + lane;
+            const uint32_t card = bb < P.n_blocks ? blocks[bb].pos_card : 0u;
+            uint32_t grown = __ballot_sync(FULL_MASK, card > pc);
+            while (grown) {                                  /* blocks in ascending order */
+                const uint32_t src = (uint32_t)__ffs(grown) - 1u; grown &= grown - 1u;
+                const BlockDesc &B = blocks[b0 + src];
+                const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+                const uint32_t *bval = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_val);
+                const uint32_t *bcnt = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_cnt);
+                const uint32_t bc = B.pos_card;
+                for (uint32_t s = pc; s < bc; s++) {
+                    const uint32_t x = bval[s], c = bcnt[s];
+                    int found = -1;
+                    for (uint32_t q0 = pc; q0 < an && found < 0; q0 += 32u) {
+                        const uint32_t q = q0 + lane;
+                        const uint32_t hit = __ballot_sync(FULL_MASK, q < an && nval[q] == x);
+                        if (hit) found = (int)(q0 + (uint32_t)__ffs(hit) - 1u);
+                    }
+                    if (found >= 0) { if (lane == 0) ncnt[found] += c; }
+                    else if (an < CBCG_SNAP_POS_MAX) { if (lane == 0) { nval[an] = x; ncnt[an] = c; } an++; }
+                    __syncwarp();
+                }
+            }
+        }
+        uint32_t s = 0;
+        for (uint32_t i = lane; i < an; i += 32u) { int32_t v = (int32_t)ncnt[i]; if (v < 1) v = 1; ncnt[i] = (uint32_t)v; s += (uint32_t)v; }
+        uint32_t n = warp_sum(s);
+        while (n >= CBCG_RESCALE) {
+            s = 0;
+            for (uint32_t i = lane; i < an; i += 32u) { const uint32_t c = (ncnt[i] >> 1) + 1u; ncnt[i] = c; s += c; }
+            n = warp_sum(s);
+        }
+        if (lane == 0) { nhdr[0] = an; nhdr[1] = n; }
     }
-}
-
-/* FLAG: dense 65 536-entry accumulation in global scratch, then back to the sorted sparse form. */
-__global__ void __launch_bounds__(1024) merge_flag_kernel(MergeParams P) {
-    __shared__ uint32_t red[32];
-    __shared__ uint32_t scan[1024];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const SnapLayout l = snap_layout(P.L);
-    const WarpModels *pm = reinterpret_cast<const WarpModels *>(P.prev + l.small);
+    __syncthreads();
+    /* FLAG: clamp, total, rescale over the dense scratch, then ordered compaction of the counts != 1 */
     WarpModels *nm = reinterpret_cast<WarpModels *>(P.next + l.small);
-    uint32_t *dprev = reinterpret_cast<uint32_t *>(P.next + l.flag_prev), *dacc = reinterpret_cast<uint32_t *>(P.next + l.flag_acc);
-    for (uint32_t i = tid; i < 65536u; i += 1024u) { dprev[i] = 1u; dacc[i] = 1u; }
-    __syncthreads();
-    if (tid < pm->flag_used) { const uint32_t k = pm->flag_key[tid], c = pm->flag_cnt[tid]; dprev[k] = c; dacc[k] = c; }
-    __syncthreads();
-    const uint64_t stride = fin_stride_dev();
-    for (uint32_t b = 0; b < P.n_blocks; b++) {
-        const WarpModels *fm = reinterpret_cast<const WarpModels *>(P.fin + (uint64_t)b * stride);
-        if (tid < fm->flag_used) { const uint32_t k = fm->flag_key[tid] & 0xffffu; dacc[k] += fm->flag_cnt[tid] - dprev[k]; }
-        __syncthreads();
-    }
-    /* clamp, total, rescale */
+    uint32_t *dacc = reinterpret_cast<uint32_t *>(P.next + l.flag_acc);
     uint32_t n;
     {
         uint32_t s = 0;
@@ -1237,7 +1390,6 @@ __global__ void __launch_bounds__(1024) merge_flag_kernel(MergeParams P) {
         n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
         __syncthreads();
     }
-    /* ordered compaction of the values whose count is not 1: thread t owns values [64 t, 64 t + 64) */
     uint32_t mine = 0;
     for (uint32_t i = 0; i < 64u; i++) mine += dacc[tid * 64u + i] != 1u;
     scan[tid] = mine; __syncthreads();
@@ -1249,116 +1401,6 @@ __global__ void __launch_bounds__(1024) merge_flag_kernel(MergeParams P) {
     if (tid == 0) { nm->flag_used = total > FLAG_CAP ? 0u : total; nm->flag_n = n; }
 }
 
-/* POS: slots below the snapshot's alphabet size are the same value in every block; new values are
- * appended in block order, then order of appearance (one warp, blocks in sequence). */
-__global__ void __launch_bounds__(32) merge_pos_kernel(MergeParams P) {
-    const uint32_t lane = threadIdx.x;
-    const SnapLayout l = snap_layout(P.L);
-    const uint32_t *phdr = reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr);
-    const uint32_t *pcnt = reinterpret_cast<const uint32_t *>(P.prev + l.pos_cnt);
-    uint32_t *nhdr = reinterpret_cast<uint32_t *>(P.next + l.pos_hdr);
-    uint32_t *nval = reinterpret_cast<uint32_t *>(P.next + l.pos_val), *ncnt = reinterpret_cast<uint32_t *>(P.next + l.pos_cnt);
-    const BlockDesc *blocks = P.blocks + P.block_begin;
-    const uint32_t pc = phdr[0];
-    uint32_t an = pc;
-    for (uint32_t s0 = 0; s0 < pc; s0 += 32u) {
-        const uint32_t s = s0 + lane;
-        if (s < pc) {
-            const uint32_t p = pcnt[s]; uint32_t acc = p;
-            for (uint32_t b = 0; b < P.n_blocks; b++) {
-                const BlockDesc &B = blocks[b];
-                const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
-                acc += reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_cnt)[s] - p;
-            }
-            ncnt[s] = acc;
-        }
-    }
-    __syncwarp();
-    for (uint32_t b = 0; b < P.n_blocks; b++) {
-        const BlockDesc &B = blocks[b];
-        const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
-        const uint32_t *bval = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_val);
-        const uint32_t *bcnt = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_cnt);
-        for (uint32_t s = pc; s < B.pos_card; s++) {
-            const uint32_t x = bval[s], c = bcnt[s];
-            int found = -1;
-            for (uint32_t q0 = pc; q0 < an && found < 0; q0 += 32u) {
-                const uint32_t q = q0 + lane;
-                const uint32_t hit = __ballot_sync(FULL_MASK, q < an && nval[q] == x);
-                if (hit) found = (int)(q0 + (uint32_t)__ffs(hit) - 1u);
-            }
-            if (found >= 0) { if (lane == 0) ncnt[found] += c; }
-            else if (an < CBCG_SNAP_POS_MAX) { if (lane == 0) { nval[an] = x; ncnt[an] = c; } an++; }
-            __syncwarp();
-        }
-    }
-    uint32_t s = 0;
-    for (uint32_t i = lane; i < an; i += 32u) { int32_t v = (int32_t)ncnt[i]; if (v < 1) v = 1; ncnt[i] = (uint32_t)v; s += (uint32_t)v; }
-    uint32_t n = warp_sum(s);
-    while (n >= CBCG_RESCALE) {
-        s = 0;
-        for (uint32_t i = lane; i < an; i += 32u) { const uint32_t c = (ncnt[i] >> 1) + 1u; ncnt[i] = c; s += c; }
-        n = warp_sum(s);
-    }
-    if (lane == 0) { nhdr[0] = an; nhdr[1] = n; }
-}
-
-/* var rows, phase 1: rows new to the snapshot are created (all ones) by whichever block flips their bit. */
-__global__ void __launch_bounds__(128) merge_var_mark_kernel(MergeParams P) {
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t b = blockIdx.x * 4u + warp;
-    if (b >= P.n_blocks) return;
-    const SnapLayout l = snap_layout(P.L);
-    uint32_t *bm = reinterpret_cast<uint32_t *>(P.next + l.bitmap);
-    uint32_t *var = reinterpret_cast<uint32_t *>(P.next + l.var);
-    const BlockDesc &B = P.blocks[P.block_begin + b];
-    const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
-    const uint64_t *hash = reinterpret_cast<const uint64_t *>(P.ws + B.ws_off + w.var_hash);
-    for (uint32_t h0 = 0; h0 < w.hash_cap; h0 += 32u) {
-        const uint64_t sl = hash[h0 + lane];
-        const uint32_t key = (uint32_t)(sl >> 32);
-        bool won = false; uint32_t ctx = 0;
-        if (key) { ctx = key - 1u; const uint32_t bit = 1u << (ctx & 31u); won = !(atomicOr(&bm[ctx >> 5], bit) & bit); }
-        uint32_t wm = __ballot_sync(FULL_MASK, won);
-        while (wm) {
-            const uint32_t src = (uint32_t)__ffs(wm) - 1u; wm &= wm - 1u;
-            const uint32_t c = __shfl_sync(FULL_MASK, ctx, src);
-            uint32_t *row = var + (uint64_t)c * l.Lp;
-            for (uint32_t i = lane; i < P.L; i += 32u) row[i] = 1u;
-            if (lane == 0) row[P.L] = P.L;
-        }
-    }
-}
-/* phase 2: add every block's row deltas. */
-__global__ void __launch_bounds__(128) merge_var_add_kernel(MergeParams P) {
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t b = blockIdx.x * 4u + warp;
-    if (b >= P.n_blocks) return;
-    const SnapLayout l = snap_layout(P.L);
-    const uint32_t *pbm = reinterpret_cast<const uint32_t *>(P.prev + l.bitmap);
-    const uint32_t *pvar = reinterpret_cast<const uint32_t *>(P.prev + l.var);
-    uint32_t *var = reinterpret_cast<uint32_t *>(P.next + l.var);
-    const BlockDesc &B = P.blocks[P.block_begin + b];
-    const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
-    const uint64_t *hash = reinterpret_cast<const uint64_t *>(P.ws + B.ws_off + w.var_hash);
-    const uint32_t *rows = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.var_rows);
-    for (uint32_t h0 = 0; h0 < w.hash_cap; h0 += 32u) {
-        const uint64_t sl = hash[h0 + lane];
-        uint32_t km = __ballot_sync(FULL_MASK, (uint32_t)(sl >> 32) != 0u);
-        while (km) {
-            const uint32_t src = (uint32_t)__ffs(km) - 1u; km &= km - 1u;
-            const uint64_t e = __shfl_sync(FULL_MASK, sl, src);
-            const uint32_t ctx = (uint32_t)(e >> 32) - 1u, r = (uint32_t)e;
-            const bool in_prev = (pbm[ctx >> 5] >> (ctx & 31u)) & 1u;
-            const uint32_t *row = rows + (uint64_t)r * w.Lp, *prow = pvar + (uint64_t)ctx * l.Lp;
-            uint32_t *nrow = var + (uint64_t)ctx * l.Lp;
-            for (uint32_t i = lane; i < P.L; i += 32u) {
-                const uint32_t d = row[i] - (in_prev ? prow[i] : 1u);
-                if (d) atomicAdd(&nrow[i], d);
-            }
-        }
-    }
-}
 /* phase 3: clamp, total, rescale every row of the new snapshot (idempotent on rows no block touched). */
 __global__ void __launch_bounds__(256) merge_var_finish_kernel(MergeParams P) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -1383,11 +1425,9 @@ int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_block
                  uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, cudaStream_t st) {
     if (cudaMemcpyAsync(next, prev, snapshot_bytes(L), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
     MergeParams P = { blocks, block_begin, n_blocks, L, prev, next, fin, ws, err };
-    merge_small_kernel<<<1, MERGE_SMALL_WARPS * 32u, 0, st>>>(P);
-    merge_flag_kernel<<<1, 1024, 0, st>>>(P);
-    merge_pos_kernel<<<1, 32, 0, st>>>(P);
-    merge_var_mark_kernel<<<(n_blocks + 3u) / 4u, 128, 0, st>>>(P);
-    merge_var_add_kernel<<<(n_blocks + 3u) / 4u, 128, 0, st>>>(P);
+    merge_prep_kernel<<<148, 128, 0, st>>>(P);
+    merge_add_kernel<<<(n_blocks + 3u) / 4u, 128, 0, st>>>(P);
+    merge_finish_kernel<<<1, MERGE_FIN_WARPS * 32u, 0, st>>>(P);
     merge_var_finish_kernel<<<(CBCG_VAR_CONTEXTS + 7u) / 8u, 256, 0, st>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -90,9 +90,9 @@ typedef struct cbcg_read_rec {
 /* Generation-primed blocks (gen_mode 1): generation i has CBCG_GEN_COUNTS[i] blocks of
  * CBCG_GEN_READS[i] reads, each starting from the merged final states of the generation before; the
  * last generation takes all remaining reads in blocks of block_reads. */
-#define CBCG_GEN_LEVELS     5
-#define CBCG_GEN_COUNTS     { 1u, 31u, 96u, 256u, 512u }
-#define CBCG_GEN_READS      { 128u, 128u, 256u, 256u, 512u }
+#define CBCG_GEN_LEVELS     4
+#define CBCG_GEN_COUNTS     { 8u, 56u, 192u, 768u }
+#define CBCG_GEN_READS      { 32u, 64u, 128u, 256u }
 #define CBCG_SNAP_POS_MAX   4096u         /* a snapshot keeps at most this many POS alphabet entries */
 
 #endif /* CBCG_FORMAT_H */

@@ -40,10 +40,11 @@ def split(data):
         nl, = struct.unpack_from("<I", data, o); o += 4 + nl + ((4 - (nl & 3)) & 3)
     ixb, = struct.unpack_from("<I", data, o); return nb, o + 4 + ixb, len(data) - o - 4 - ixb
 
-SCHEDS = [([], []), ([1, 31, 96], [128, 128, 256]), ([1, 31, 96, 256], [128, 128, 256, 256]),
-          ([1, 31, 96, 256, 512], [128, 128, 256, 256, 512]), ([1, 15, 48, 128, 512, 1024], [128, 128, 128, 256, 256, 512])]
-for R in (256, 512, 1024):
+SCHEDS = [([8, 56, 192, 768], [32, 64, 128, 256]), ([32, 224, 768], [32, 64, 256]), ([16, 112, 896], [32, 64, 256]),
+          ([64, 448, 1536], [16, 64, 256]), ([256, 2048], [32, 128]), ([8, 56, 448, 1024], [32, 64, 128, 256]),
+          ([16, 112, 448, 1024], [16, 32, 128, 256]), ([16, 240, 768], [32, 64, 256]), ([8, 120, 384, 1024], [32, 32, 128, 256])]
+for R in (768,):
     for counts, reads in SCHEDS:
         data, dt = sched(R, counts, reads)
         nb, head, pay = split(data)
-        print(f"R={R} sched={list(zip(counts, reads))} blocks={nb} payload={pay} ({100*(pay-len(single))/len(single):+.2f}%) head={head} ({100*head/len(single):.2f}%) flush~{100*nb*4/len(single):.2f}% {dt:.1f}s", flush=True)
+        print(f"serial={sum(reads)} early_reads={sum(c*r for c,r in zip(counts,reads))} R={R} sched={list(zip(counts, reads))} blocks={nb} payload={pay} ({100*(pay-len(single))/len(single):+.2f}%) head={head} ({100*head/len(single):.2f}%) flush~{100*nb*4/len(single):.2f}% {dt:.1f}s", flush=True)

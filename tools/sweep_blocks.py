@@ -12,6 +12,7 @@ from cbc_b200.codec import Codec, pin_batch     # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 sizes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [256, 512, 1024, 2048, 4096, 16384, 65536]
+gen_mode = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 cfg = synth.SynthConfig.named("config2", scale=scale)
 g = synth.make_genome(cfg)
 b = synth.make_reads(cfg, g)
@@ -22,7 +23,7 @@ ref = b.seq_lines()
 for R in sizes:
     rows = []
     for it in range(4):
-        c.encode_resident(150, R)
+        c.encode_resident(150, R, gen_mode)
         se = c.stats()
         c.decode_resident()
         sd = c.stats()
@@ -30,7 +31,7 @@ for R in sizes:
                      sd["ms_code"], sd["ms_k3"], sd["ms_reconstruct"], sd["ms_total"]))
     ok = c.fetch_decoded().tobytes() == ref
     m = np.median(np.array(rows[1:]), axis=0)
-    print(json.dumps({"block_reads": R, "blocks": se["n_blocks"], "ok": ok, "container_bytes": se["container_bytes"],
+    print(json.dumps({"gen_mode": gen_mode, "block_reads": R, "blocks": se["n_blocks"], "ok": ok, "container_bytes": se["container_bytes"],
                       "bits_per_base": 8.0 * se["container_bytes"] / b.total_bases(), "n_symbols": se["n_symbols"],
                       "n_edits": se["n_edits"],
                       "ms": dict(zip(["k1", "extract", "plan", "k2e", "gather", "enc_total", "k2d", "k3", "recon", "dec_total"],
