@@ -42,6 +42,7 @@
 #endif
 #define K2_THREADS  (K2_WARPS * 32u)
 #define FLAG_CAP    128u
+#define PA_STRIDE   260u              /* words per 256-symbol model row: 256 counts, n, padding to 16 bytes */
 #define VAR_DIRECT_MIN_EDITS 32768u       /* blocks with more edits index var rows directly by context */
 
 enum { MODE_ENC = 0, MODE_DEC = 1, MODE_LIST = 2 };
@@ -77,11 +78,11 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t L, uint64_t n_reads, uint
     uint64_t o = 0;                                                            /* in bytes, 16-aligned pieces */
     w.pos_cnt = o;   o += ((uint64_t)w.pos_cap * 4u + 15u) & ~15ull;
     w.pos_val = o;   o += ((uint64_t)w.pos_cap * 4u + 15u) & ~15ull;
-    w.pos_alpha = o; o += 4u * 257u * 4u + 16u;
+    w.pos_alpha = o; o += 4u * PA_STRIDE * 4u + 16u;
     w.var_hash = o;  o += (uint64_t)w.hash_cap * 8u;
     w.var_rows = o;  o += (uint64_t)w.rows_cap * w.Lp * 4u;
-    w.codebook = o;  if (legacy) o += 4u * 257u * 4u + 16u;
-    w.rname = o;     if (legacy) o += 256u * 257u * 4u + 16u;
+    w.codebook = o;  if (legacy) o += 4u * PA_STRIDE * 4u + 16u;
+    w.rname = o;     if (legacy) o += 256u * PA_STRIDE * 4u + 16u;
     w.total = (o + 255u) & ~255ull;
     return w;
 }
@@ -100,7 +101,7 @@ uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, ui
     const uint64_t Lp = (L + 1u + 31u) & ~31u;
     /* per block: pos 2 x (n+34) x 4 (+32), pos_alpha 4128, hash <= max(32, 4 n_edits + 4) x 8, rows n_edits x Lp x 4;
        a block in direct mode replaces hash + rows by 8 KB + 65535 rows: bounded by its own n_edits >= 32768 rows. */
-    uint64_t b = n_blocks * (2u * (34u * 4u + 16u) + 4u * 257u * 4u + 16u + 32u * 8u + 8192u + 512u);
+    uint64_t b = n_blocks * (2u * (34u * 4u + 16u) + 4u * PA_STRIDE * 4u + 16u + 32u * 8u + 8192u + 512u);
     b += n_reads * 8u + n_edits * 32u + n_edits * Lp * 4u;
     if (primed) b += n_blocks * (uint64_t)CBCG_SNAP_POS_MAX * 8u;
     return 2u * b + 4096u;                                   /* direct blocks use <= 2 x their hashed size */
@@ -135,7 +136,7 @@ __host__ __device__ inline SnapLayout snap_layout(uint32_t L) {
     s.pos_hdr = o;   o += 16u;                                         /* card, n */
     s.pos_val = o;   o += (uint64_t)(CBCG_SNAP_POS_MAX + 32u) * 4u;
     s.pos_cnt = o;   o += (uint64_t)(CBCG_SNAP_POS_MAX + 32u) * 4u;
-    s.pos_alpha = o; o += 4u * 257u * 4u + 16u;
+    s.pos_alpha = o; o += 4u * PA_STRIDE * 4u + 16u;
     s.bitmap = o;    o += 2048u * 4u;
     s.flag_prev = o; o += 65536u * 4u;                                 /* merge scratch: dense FLAG counts */
     s.flag_acc = o;  o += 65536u * 4u;
@@ -161,6 +162,13 @@ struct SnapView {
     }
 };
 
+/* All-ones initial state of a dense model (every initialize_stream_model_* of sam_models.c but chars).
+ * Out of line on purpose: it is cold code, and the block coder's loop has to fit the instruction cache. */
+__device__ __noinline__ void fill_ones(uint32_t *m, uint32_t card, uint32_t lane) {
+    for (uint32_t i = lane; i < card; i += 32u) m[i] = 1u;
+    if (lane == 0) m[card] = card;
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 template <int MODE>
 struct Coder {
@@ -179,6 +187,7 @@ struct Coder {
     uint32_t lane;
     int err;
     uint32_t n_symbols;
+    uint32_t last_lo, last_n;              /* interval start and model total of the last dense symbol */
 
     /* --- models */
     WarpModels *M;
@@ -211,10 +220,28 @@ struct Coder {
             acc &= (1ull << nacc) - 1ull;
         }
     }
-    __device__ __forceinline__ void put_run(uint32_t bit, uint32_t count) {
-        const uint32_t pat = bit ? 0xffffffffu : 0u;
-        while (count >= 32u) { put_bits(pat, 32u); count -= 32u; }
-        if (count) put_bits(pat >> (32u - count), count);
+    /* One bit b0, then `run` copies of its inverse (the pending E3 bits, src/Arithmetic_stream.c:318-322), then the
+       low rest_bits of rest. Written so that the bit packer is instantiated once: the hot loop has to fit the
+       instruction cache. */
+    __device__ __forceinline__ void emit(uint32_t b0, uint32_t run, uint32_t rest, uint32_t rest_bits) {
+        const uint32_t inv = b0 ? 0u : 0xffffffffu;
+        uint32_t phase = 0;                                  /* 0: b0 + start of the run, 1: rest of the run, 2: rest, 3: done */
+        while (phase < 3u) {
+            uint32_t v, nb;
+            if (phase == 0u) {
+                if (run + 1u + rest_bits <= 32u) {           /* the usual case: everything in one go */
+                    v = (b0 << (run + rest_bits)) | ((inv & ((1u << run) - 1u)) << rest_bits) | rest;
+                    nb = run + 1u + rest_bits; phase = 3u;
+                } else {
+                    const uint32_t r = run < 31u ? run : 31u;
+                    v = (b0 << r) | (inv & ((1u << r) - 1u)); nb = r + 1u; run -= r; phase = run ? 1u : 2u;
+                }
+            } else if (phase == 1u) {
+                const uint32_t r = run < 32u ? run : 32u;
+                v = r == 32u ? inv : (inv & ((1u << r) - 1u)); nb = r; run -= r; if (!run) phase = 2u;
+            } else { v = rest; nb = rest_bits; phase = 3u; }
+            put_bits(v, nb);
+        }
     }
     /* stream_finish_byte (:189-194): the byte in progress always goes out, even an empty one */
     __device__ __forceinline__ void finish_bits(bool always_last = true) {
@@ -265,10 +292,8 @@ struct Coder {
         uint32_t k, bits, m; AcInterval nx;
         ac_renorm_shape(a, k, bits, m, nx);
         if (k) {
-            const uint32_t b0 = (bits >> (k - 1u)) & 1u;
-            put_bits(b0, 1u);
-            if (scale3 > 0) { put_run(b0 ^ 1u, (uint32_t)scale3); scale3 = 0; }
-            if (k > 1u) put_bits(bits & ((1u << (k - 1u)) - 1u), k - 1u);
+            emit((bits >> (k - 1u)) & 1u, (uint32_t)scale3, bits & ((1u << (k - 1u)) - 1u), k - 1u);
+            scale3 = 0;
         }
         scale3 += (int32_t)m;
         a = nx;
@@ -284,18 +309,16 @@ struct Coder {
     }
     /* encoder_last_step (:348-364) */
     __device__ __forceinline__ void ac_flush() {
-        const uint32_t msb = a.l >> (CBCG_AC_BITS - 1u);
-        put_bits(msb, 1u);
-        if (scale3 > 0) { put_run(msb ^ 1u, (uint32_t)scale3); scale3 = 0; }
-        put_bits(a.l & CBCG_AC_LOWMASK, CBCG_AC_BITS - 1u);
+        emit(a.l >> (CBCG_AC_BITS - 1u), (uint32_t)scale3, a.l & CBCG_AC_LOWMASK, CBCG_AC_BITS - 1u);
+        scale3 = 0;
         finish_bits();
     }
 
     /* Blocked containers: after renormalisation l < 2^25 <= u, so the value 2^25 -- "1", the pending E3 bits as
        "0", zeros ever after -- lies in [l, u]; the decoder reads zeros past the end of a block. */
     __device__ __forceinline__ void ac_flush_short() {
-        put_bits(1u, 1u);
-        if (scale3 > 0) { put_run(0u, (uint32_t)scale3); scale3 = 0; }
+        emit(1u, (uint32_t)scale3, 0u, 0u);
+        scale3 = 0;
         finish_bits(false);
     }
 
@@ -320,45 +343,67 @@ struct Coder {
             SYNCW();
         }
     }
-    __device__ __forceinline__ uint32_t sym_dense(uint32_t *m, uint32_t card, uint32_t step, uint32_t x) {
+    /* Four counts per lane per step (rows are 16-byte aligned): 128 symbols of cumulative count in one load,
+       where the reference walks them one by one (src/stream_model.c:64-67, :96-99). */
+    __device__ __forceinline__ uint4 load4(const uint32_t *m, uint32_t i, uint32_t card) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (i < card) {
+            v = *reinterpret_cast<const uint4 *>(m + i);
+            if (i + 1u >= card) v.y = 0u;
+            if (i + 2u >= card) v.z = 0u;
+            if (i + 3u >= card) v.w = 0u;
+        }
+        return v;
+    }
+    /* pre: the caller already knows the symbol and its cumulative count (pre_lo); no scan. */
+    __device__ __forceinline__ uint32_t sym_dense(uint32_t *m, uint32_t card, uint32_t step, uint32_t x, bool pre, uint32_t pre_lo) {
         if (err) return 0u;
         const uint32_t n = m[card];
-        uint32_t lo, cnt;
-        if (MODE == MODE_ENC) {
+        uint32_t lo = 0, cnt = 0;
+        if (pre) { lo = pre_lo; cnt = m[x]; }
+        else if (MODE == MODE_ENC) {
             if (x >= card) { err = CBCG_ERR_INPUT; return 0u; }              /* reference: assert :62 */
             uint32_t s = 0;
-            for (uint32_t i = lane; i < x; i += 32u) s += m[i];
+            for (uint32_t base = 0; base < x; base += 128u) {
+                const uint32_t i = base + 4u * lane;
+                const uint4 v = load4(m, i, card);
+                s += (i < x ? v.x : 0u) + (i + 1u < x ? v.y : 0u) + (i + 2u < x ? v.z : 0u) + (i + 3u < x ? v.w : 0u);
+            }
             lo = warp_sum(s); cnt = m[x];
         } else {
             const uint32_t target = ac_target(a, t, n);
             uint32_t carry = 0; bool found = false;
-            lo = 0; cnt = 0; x = 0;
-            for (uint32_t base = 0; base < card; base += 32u) {
-                const uint32_t i = base + lane;
-                const uint32_t c = (i < card) ? m[i] : 0u;
-                const uint32_t incl = warp_incl_scan(c) + carry;
-                const uint32_t hit = __ballot_sync(FULL_MASK, i < card && incl > target);
+            x = 0;
+            for (uint32_t base = 0; base < card; base += 128u) {
+                const uint32_t i = base + 4u * lane;
+                const uint4 v = load4(m, i, card);
+                const uint32_t mine = v.x + v.y + v.z + v.w;
+                const uint32_t incl = warp_incl_scan(mine) + carry;
+                const uint32_t hit = __ballot_sync(FULL_MASK, incl > target);     /* lanes past the row add 0: never first */
                 if (hit) {
                     const uint32_t h = (uint32_t)__ffs(hit) - 1u;
-                    cnt = __shfl_sync(FULL_MASK, c, h);
-                    lo = __shfl_sync(FULL_MASK, incl, h) - cnt;
-                    x = base + h; found = true;
+                    const uint32_t before = __shfl_sync(FULL_MASK, incl - mine, h);
+                    const uint32_t c0 = __shfl_sync(FULL_MASK, v.x, h), c1 = __shfl_sync(FULL_MASK, v.y, h);
+                    const uint32_t c2 = __shfl_sync(FULL_MASK, v.z, h), c3 = __shfl_sync(FULL_MASK, v.w, h);
+                    uint32_t q = 0; lo = before; cnt = c0;
+                    if (lo + cnt <= target) { lo += cnt; cnt = c1; q = 1u; }
+                    if (lo + cnt <= target) { lo += cnt; cnt = c2; q = 2u; }
+                    if (lo + cnt <= target) { lo += cnt; cnt = c3; q = 3u; }
+                    x = base + 4u * h + q; found = true;
                     break;
                 }
                 carry = __shfl_sync(FULL_MASK, incl, 31);
             }
-            if (!found) { err = CBCG_ERR_CORRUPT; return 0u; }
+            if (!found || x >= card) { err = CBCG_ERR_CORRUPT; return 0u; }
         }
+        last_lo = lo; last_n = n;
         code_interval(lo, cnt, n);
         if (err) return 0u;
         dense_update(m, card, step, x);
         return x;
     }
 
-    __device__ __forceinline__ void dense_init_ones(uint32_t *m, uint32_t card) {
-        for (uint32_t i = lane; i < card; i += 32u) m[i] = 1u;
-        if (lane == 0) m[card] = card;
-    }
+    __device__ __forceinline__ void dense_init_ones(uint32_t *m, uint32_t card) { fill_ones(m, card, lane); }
 
     /* ============================================================ length bytes 1..3 (always symbol 0) */
     __device__ __forceinline__ uint32_t sym_rlenk(uint32_t k, uint32_t x) {
@@ -491,8 +536,8 @@ struct Coder {
     }
     __device__ __forceinline__ void pa_ensure() {
         if (!pa_init) {
-            if (primed) { for (uint32_t i = lane; i < 4u * 257u; i += 32u) pos_alpha[i] = snap.pos_alpha[i]; }
-            else for (uint32_t k = 0; k < 4u; k++) dense_init_ones(pos_alpha + k * 257u, 256u);
+            if (primed) { for (uint32_t i = lane; i < 4u * PA_STRIDE; i += 32u) pos_alpha[i] = snap.pos_alpha[i]; }
+            else for (uint32_t k = 0; k < 4u; k++) dense_init_ones(pos_alpha + k * PA_STRIDE, 256u);
             pa_init = true;
             SYNCW();
         }
@@ -667,8 +712,8 @@ struct Coder {
         if (var_direct) { for (uint32_t i = lane; i < 2048u; i += 32u) var_bitmap[i] = 0u; }
         else { for (uint32_t i = lane; i <= hash_mask; i += 32u) var_hash[i] = 0ull; }
         if (legacy) {
-            for (uint32_t k = 0; k < 4u; k++) dense_init_ones(codebook + k * 257u, 256u);
-            for (uint32_t k = 0; k < 256u; k++) dense_init_ones(rname + k * 257u, 256u);
+            for (uint32_t k = 0; k < 4u; k++) dense_init_ones(codebook + k * PA_STRIDE, 256u);
+            for (uint32_t k = 0; k < 256u; k++) dense_init_ones(rname + k * PA_STRIDE, 256u);
         }
         SYNCW();
     }
@@ -690,7 +735,7 @@ enum : uint32_t { K_NONE, K_DENSE, K_RLENK, K_FLAG, K_POS };
 template <int MODE>
 __global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
 k2_coder_kernel(CoderParams P) {
-    __shared__ WarpModels smodels[K2_WARPS];
+    __shared__ __align__(16) WarpModels smodels[K2_WARPS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t bl = blockIdx.x * K2_WARPS + warp;
     if (bl >= P.n_blocks) return;
@@ -746,20 +791,21 @@ k2_coder_kernel(CoderParams P) {
     /* the read in flight */
     uint32_t pos = 0, len = 0, flag = 0, match = 0, ns = 0, nd = 0, ni = 0, strand = 0, samepos = 0, posx = 0, acc = 0;
     uint32_t prev = 0, ne = 0, ed = 0, edp = 0, refb = 0, change = 0, hdr_L = 0;
+    uint32_t rl_x = 0xffffffffu, rl_lo = 0;             /* remembered length symbol and its cumulative count */
     const uint16_t *e_in = P.edits;
     const uint8_t *name = P.chr_names;
 
     while (!C.err && state != ST_DONE) {
         /* ================================================ 1. what is the next symbol? */
-        uint32_t kind = K_DENSE, card = 0, step = 0, x = 0, key = 0, ctx = 0;
+        uint32_t kind = K_DENSE, card = 0, step = 0, x = 0, key = 0, ctx = 0, pre_lo = 0;
         uint32_t *m = nullptr;
-        bool is_var = false;
+        bool is_var = false, pre = false;
         switch (state) {
             case ST_HDR: {                               /* 34 ints x 4 bytes, MSB first, through codebook[0..3] (compress_int) */
                 const uint32_t word = k >> 2, byte = k & 3u;
                 const uint32_t v = word == 0u ? P.L : (word == 33u ? CBCG_LOSSLESS : CBCG_WELL_DEBUG);
                 x = (v >> (24u - 8u * byte)) & 0xffu;
-                m = C.codebook + byte * 257u; card = 256u; step = 1u; key = CBCG_SYM_KEY(CBCG_S_CODEBOOK, byte);
+                m = C.codebook + byte * PA_STRIDE; card = 256u; step = 1u; key = CBCG_SYM_KEY(CBCG_S_CODEBOOK, byte);
                 break;
             }
             case ST_READ: {                              /* not a symbol: fetch the next read */
@@ -767,6 +813,9 @@ k2_coder_kernel(CoderParams P) {
                 if (!(legacy && MODE == MODE_DEC) && i >= n_reads) { state = (legacy && MODE != MODE_DEC) ? ST_ENDMARK : ST_DONE; k = 0; break; }
                 if (MODE != MODE_DEC) {
                     const uint4 v = reinterpret_cast<const uint4 *>(P.recs)[r0 + i];
+                    if (i + 1u < n_reads) {                                            /* next read's record: hide its latency */
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint4 *>(P.recs) + r0 + i + 1u));
+                    }
                     pos = v.x; flag = v.y & 0xffffu; len = v.y >> 16; match = v.w & 0xffu;
                     ns = (v.w >> 8) & 0xffu; nd = (v.w >> 16) & 0xffu; ni = v.w >> 24;
                     e_in = P.edits + v.z;
@@ -783,9 +832,18 @@ k2_coder_kernel(CoderParams P) {
             case ST_SAMEREF: m = C.M->same_ref; card = 2u; step = 10u; x = change; key = CBCG_SYM_KEY(CBCG_S_SAME_REF, 0u); break;
             case ST_RNAME:                               /* name bytes then 0, context = previous byte (never reset) */
                 x = (MODE != MODE_DEC && k < MAX_NAME) ? (uint32_t)name[k] : 0u;
-                m = C.rname + prev_char * 257u; card = 256u; step = 10u; key = CBCG_SYM_KEY(CBCG_S_RNAME, prev_char);
+                m = C.rname + prev_char * PA_STRIDE; card = 256u; step = 10u; key = CBCG_SYM_KEY(CBCG_S_RNAME, prev_char);
                 break;
-            case ST_RLEN0: m = C.M->rlen0; card = 255u; step = 10u; x = len & 0xffu; key = CBCG_SYM_KEY(CBCG_S_RLENGTH, 0u); break;
+            case ST_RLEN0:
+                m = C.M->rlen0; card = 255u; step = 10u; x = len & 0xffu; key = CBCG_SYM_KEY(CBCG_S_RLENGTH, 0u);
+                /* fixed-length input codes the same symbol every read; its cumulative count only moves when a
+                   smaller symbol is coded or the model rescales, so it is remembered instead of re-summed */
+                if (MODE != MODE_LIST && rl_x < 255u) {
+                    if (MODE == MODE_ENC) pre = (x == rl_x);
+                    else { const uint32_t tg = ac_target(C.a, C.t, m[255]); pre = tg >= rl_lo && tg < rl_lo + m[rl_x]; if (pre) x = rl_x; }
+                    pre_lo = rl_lo;
+                }
+                break;
             case ST_RLENK: kind = K_RLENK; x = 0u; key = CBCG_SYM_KEY(CBCG_S_RLENGTH, k); break;    /* bytes 1..3 are always 0 (:29-33) */
             case ST_POS:
                 kind = K_POS; key = CBCG_SYM_KEY(CBCG_S_POS_X, 0u);
@@ -797,7 +855,7 @@ k2_coder_kernel(CoderParams P) {
                 break;
             case ST_POSESC:                              /* the escaped value, 4 bytes MSB first (compress_pos_alpha :75-108) */
                 if (k == 0u) C.pa_ensure();
-                m = C.pos_alpha + k * 257u; card = 256u; step = 10u; x = (posx >> (24u - 8u * k)) & 0xffu;
+                m = C.pos_alpha + k * PA_STRIDE; card = 256u; step = 10u; x = (posx >> (24u - 8u * k)) & 0xffu;
                 key = CBCG_SYM_KEY(CBCG_S_POS_ALPHA, k);
                 break;
             case ST_FLAG: kind = K_FLAG; x = flag; key = CBCG_SYM_KEY(CBCG_S_FLAG, 0u); break;
@@ -836,7 +894,7 @@ k2_coder_kernel(CoderParams P) {
                 break;
             case ST_ENDMARK:                             /* end of stream: name "\n" (src/compression.c:152) */
                 if (k == 0u) { m = C.M->same_ref; card = 2u; step = 10u; x = 1u; key = CBCG_SYM_KEY(CBCG_S_SAME_REF, 0u); }
-                else { x = k == 1u ? (uint32_t)'\n' : 0u; m = C.rname + prev_char * 257u; card = 256u; step = 10u; key = CBCG_SYM_KEY(CBCG_S_RNAME, prev_char); }
+                else { x = k == 1u ? (uint32_t)'\n' : 0u; m = C.rname + prev_char * PA_STRIDE; card = 256u; step = 10u; key = CBCG_SYM_KEY(CBCG_S_RNAME, prev_char); }
                 break;
             default: C.err = CBCG_ERR_INTERNAL; break;
         }
@@ -851,7 +909,7 @@ k2_coder_kernel(CoderParams P) {
         /* ================================================ 2. code it: one call site per model kind */
         uint32_t y = x, slot = 1u;
         if (MODE == MODE_LIST) C.list_put(key >> 24, key & 0xffffffu, x);
-        else if (kind == K_DENSE) y = C.sym_dense(m, card, step, x);
+        else if (kind == K_DENSE) y = C.sym_dense(m, card, step, x, pre, pre_lo);
         else if (kind == K_FLAG) y = C.sym_flag(x);
         else if (kind == K_POS) y = C.sym_pos_main(x, slot);
         else y = C.sym_rlenk(k - 1u, x);
@@ -904,6 +962,7 @@ k2_coder_kernel(CoderParams P) {
             }
             case ST_RLEN0:
                 if (MODE == MODE_DEC) len = y;
+                if (MODE != MODE_LIST) { rl_x = (C.last_n + 10u >= CBCG_RESCALE) ? 0xffffffffu : y; rl_lo = C.last_lo; }
                 if (lean) state = ST_POS; else { state = ST_RLENK; k = 1; }
                 break;
             case ST_RLENK:
@@ -1171,7 +1230,7 @@ __global__ void __launch_bounds__(32) snapshot_init_kernel(uint8_t *snap, uint32
     uint32_t *pv = reinterpret_cast<uint32_t *>(snap + l.pos_val), *pc = reinterpret_cast<uint32_t *>(snap + l.pos_cnt);
     if (lane == 0) { hdr[0] = 1u; hdr[1] = 1u; hdr[2] = 0u; hdr[3] = 0u; pv[0] = 0u; pc[0] = 1u; }   /* escape only (sam_models.c:132-162) */
     uint32_t *pa = reinterpret_cast<uint32_t *>(snap + l.pos_alpha);
-    for (uint32_t k = 0; k < 4u; k++) { for (uint32_t i = lane; i < 256u; i += 32u) pa[k * 257u + i] = 1u; if (lane == 0) pa[k * 257u + 256u] = 256u; }
+    for (uint32_t k = 0; k < 4u; k++) { for (uint32_t i = lane; i < 256u; i += 32u) pa[k * PA_STRIDE + i] = 1u; if (lane == 0) pa[k * PA_STRIDE + 256u] = 256u; }
     uint32_t *bm = reinterpret_cast<uint32_t *>(snap + l.bitmap);
     for (uint32_t i = lane; i < 2048u; i += 32u) bm[i] = 0u;
 }
@@ -1263,7 +1322,7 @@ __global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
         const uint32_t *pa_prev = reinterpret_cast<const uint32_t *>(P.prev + l.pos_alpha);
         uint32_t *pa_next = reinterpret_cast<uint32_t *>(P.next + l.pos_alpha);
         const uint32_t *pa_blk = reinterpret_cast<const uint32_t *>(wsb + w.pos_alpha);
-        for (uint32_t i = lane; i < 4u * 257u; i += 32u) { const uint32_t d = pa_blk[i] - pa_prev[i]; if (d) atomicAdd(&pa_next[i], d); }
+        for (uint32_t i = lane; i < 4u * PA_STRIDE; i += 32u) { const uint32_t d = pa_blk[i] - pa_prev[i]; if (d) atomicAdd(&pa_next[i], d); }
     }
     /* var rows */
     {
@@ -1328,8 +1387,8 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
     else if (warp < 17)  finish_dense(lane, ps + WM_W(rlenk) + (warp - 14u) * 2u, ns + WM_W(rlenk) + (warp - 14u) * 2u, 1u, 254u);
     else if (warp < 21) {
         const uint32_t k = warp - 17u;
-        finish_dense(lane, reinterpret_cast<const uint32_t *>(P.prev + l.pos_alpha) + k * 257u,
-                     reinterpret_cast<uint32_t *>(P.next + l.pos_alpha) + k * 257u, 256u, 0u);
+        finish_dense(lane, reinterpret_cast<const uint32_t *>(P.prev + l.pos_alpha) + k * PA_STRIDE,
+                     reinterpret_cast<uint32_t *>(P.next + l.pos_alpha) + k * PA_STRIDE, 256u, 0u);
     } else if (warp == 21) {
         const uint32_t pc = reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr)[0];
         uint32_t *nhdr = reinterpret_cast<uint32_t *>(P.next + l.pos_hdr);
