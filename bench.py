@@ -395,7 +395,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--block-reads", type=int, default=1024)
+    ap.add_argument("--block-reads", type=int, default=768)
     ap.add_argument("--gen-mode", type=int, default=1, help="1: generation-primed blocks (default), 0: cold blocks")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; the bench line needs 1.0)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
