@@ -7,13 +7,13 @@ NVFLAGS   := -O3 -std=c++17 -lineinfo --extended-lambda $(ARCH) -Xcompiler -fPIC
 BUILD     := cbc_b200/_build
 CU_SRC    := $(wildcard cbc_b200/csrc/*.cu)
 CU_HDR    := $(wildcard cbc_b200/csrc/*.cuh) $(wildcard include/*.h)
-HOST_SRC  := cbc_b200/csrc/host/sam_ingest.c cbc_b200/csrc/host/container.c
+HOST_SRC  := cbc_b200/csrc/host/sam_ingest.c
 HOST_HDR  := $(wildcard cbc_b200/csrc/host/*.h) $(wildcard include/*.h)
 
 .PHONY: all host cuda cli oracle clean
-all: host cuda
+all: host cuda cli
 
-host: $(BUILD)/libcbcsynth.so oracle
+host: $(BUILD)/libcbcsynth.so $(BUILD)/libcbchost.so oracle
 
 oracle:
 	@$(MAKE) -s -C oracle port
@@ -22,6 +22,10 @@ oracle:
 $(BUILD)/libcbcsynth.so: cbc_b200/csrc/host/synth.c cbc_b200/csrc/host/synth.h
 	@mkdir -p $(BUILD)
 	$(CC) -O2 -Wall -fPIC -shared $< -o $@
+
+$(BUILD)/libcbchost.so: $(HOST_SRC) $(HOST_HDR)
+	@mkdir -p $(BUILD)
+	$(CC) -O2 -Wall -fPIC -shared -Iinclude -Icbc_b200/csrc/host $(HOST_SRC) -o $@
 
 cuda: $(BUILD)/libcbcg.so
 

@@ -1,0 +1,48 @@
+/*
+ * sam_ingest.h -- host-side SAM / FASTA ingest into the SoA batch of include/cbcg.h.
+ *
+ * Replaces, for the read path, load_sam_line + get_read_length (src/sam_file_allocation.c:26-79,
+ * 437-529) and the FASTA half of store_reference_in_memory (src/read_decompression.c:17-53). Plain C,
+ * no CUDA: the CLI hands the result to the C ABI; the CPU tests check it against the generator.
+ */
+#ifndef CBC_SAM_INGEST_H
+#define CBC_SAM_INGEST_H
+#include <stddef.h>
+#include <stdint.h>
+#include "cbcg.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cbch_fasta {
+    uint32_t n;
+    char **names;            /* record names: text after '>' up to the first blank */
+    uint8_t **bases;         /* as in the file (case kept; the device upper-cases) */
+    uint64_t *len;
+} cbch_fasta;
+
+typedef struct cbch_batch {
+    uint64_t n_reads, cap;
+    uint32_t *pos; uint16_t *flag; uint16_t *seq_len; uint32_t *chr;
+    uint64_t *seq_off, *cigar_off, *md_off;
+    uint8_t *seq, *cigar, *md;
+    uint64_t seq_cap, cigar_cap, md_cap;
+    uint32_t read_len_header;     /* get_read_length: SEQ length of the 2nd record, or the maximum (var_length) */
+    uint32_t max_len;
+    uint64_t n_unmapped;          /* records skipped: FLAG & 4 (src/compression.c:50) */
+    uint64_t n_lines;
+} cbch_batch;
+
+enum { CBCH_OK = 0, CBCH_ERR_IO = -1, CBCH_ERR_NOMEM = -2, CBCH_ERR_PARSE = -3, CBCH_ERR_RNAME = -4, CBCH_ERR_NO_MD = -5 };
+
+int  cbch_read_fasta(const char *path, cbch_fasta *out, char *err, size_t errlen);
+void cbch_free_fasta(cbch_fasta *fa);
+/* Mapped records of a SAM file; RNAME is resolved against the FASTA record names. */
+int  cbch_read_sam(const char *path, const cbch_fasta *fa, int var_length, cbch_batch *out, char *err, size_t errlen);
+void cbch_free_batch(cbch_batch *b);
+void cbch_batch_view(const cbch_batch *b, cbcg_batch *view);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,56 @@
+"""The `cbc` command line (host C ingest + C ABI) on the GPU box: README interface, reference-compatible streams."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+import oracle_lib as O
+from cbc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "cbc_b200", "_build", "cbc")
+
+
+def _run(*args):
+    p = subprocess.run([CLI, *args], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return p.stdout
+
+
+@pytest.mark.parametrize("kw,L", [
+    (dict(seed=41, genome_len=300_000, n_reads=30_000, len_min=100, len_max=100, p_sub=0.005, p_indel=0.002, p_clip=0.05), 100),
+    (dict(seed=42, genome_len=600_000, n_chr=2, n_reads=20_000, len_min=150, len_max=150, p_sub=0.005), 150),
+])
+def test_cli_roundtrip_and_reference_compatibility(kw, L):
+    cfg = synth.SynthConfig(**kw)
+    g = synth.make_genome(cfg); b = synth.make_reads(cfg, g)
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g); synth.write_sam(sam, b, g)
+        # README interface, blocked container
+        out = _run("-c", sam, os.path.join(d, "a.cbc"), fa)
+        assert "Final Size:" in out and "Compression took" in out
+        _run("-d", os.path.join(d, "a.cbc"), os.path.join(d, "a.txt"), fa)
+        with open(os.path.join(d, "a.txt"), "rb") as f:
+            assert f.read() == b.seq_lines()
+        # single-block mode == the reference's stream; checked-in spelling `-c 1` / `-x`
+        _run("-c", "1", "-1", sam, os.path.join(d, "s.cbc"), fa)
+        with open(os.path.join(d, "s.cbc"), "rb") as f:
+            stream = f.read()
+        ostream, _ = O.encode_legacy(b, g, L)
+        assert stream == ostream
+        if O.have_reference():
+            ref_stream, _, _ = O.run_reference(sam, fa, d)
+            assert stream == ref_stream                              # byte-identical to the unmodified reference
+            ref_text, _ = O.run_reference_decode(os.path.join(d, "s.cbc"), fa, d)   # the reference decodes our stream
+            assert ref_text == b.seq_lines()
+        _run("-x", os.path.join(d, "s.cbc"), os.path.join(d, "s.txt"), fa)          # we decode a reference-format stream
+        with open(os.path.join(d, "s.txt"), "rb") as f:
+            assert f.read() == b.seq_lines()
+
+
+def test_cli_errors():
+    p = subprocess.run([CLI, "-c", "only_one_file"], capture_output=True, text=True)
+    assert p.returncode != 0 and "Missing required filenames" in p.stderr

@@ -1,0 +1,108 @@
+"""Host C ingest (cbc_b200/csrc/host/sam_ingest.c): SAM + FASTA text -> the SoA batch of include/cbcg.h.
+Checked against the generator, which writes the same reads as text and as a batch. CPU only."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from cbc_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "cbc_b200", "_build", "libcbchost.so")
+
+
+class Fasta(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("names", C.POINTER(C.c_char_p)), ("bases", C.POINTER(C.POINTER(C.c_uint8))),
+                ("len", C.POINTER(C.c_uint64))]
+
+
+class HBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("cap", C.c_uint64),
+                ("pos", C.POINTER(C.c_uint32)), ("flag", C.POINTER(C.c_uint16)), ("seq_len", C.POINTER(C.c_uint16)),
+                ("chr", C.POINTER(C.c_uint32)), ("seq_off", C.POINTER(C.c_uint64)), ("cigar_off", C.POINTER(C.c_uint64)),
+                ("md_off", C.POINTER(C.c_uint64)), ("seq", C.POINTER(C.c_uint8)), ("cigar", C.POINTER(C.c_uint8)),
+                ("md", C.POINTER(C.c_uint8)), ("seq_cap", C.c_uint64), ("cigar_cap", C.c_uint64), ("md_cap", C.c_uint64),
+                ("read_len_header", C.c_uint32), ("max_len", C.c_uint32), ("n_unmapped", C.c_uint64), ("n_lines", C.c_uint64)]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.run(["make", "-s", "-C", ROOT, "host"], check=True)
+    l = C.CDLL(LIB)
+    l.cbch_read_fasta.argtypes = [C.c_char_p, C.POINTER(Fasta), C.c_char_p, C.c_size_t]
+    l.cbch_read_sam.argtypes = [C.c_char_p, C.POINTER(Fasta), C.c_int, C.POINTER(HBatch), C.c_char_p, C.c_size_t]
+    return l
+
+
+def _arr(ptr, n, dt):
+    return np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n].astype(dt, copy=True)
+
+
+def _parse(lib, sam, fa, var_length=0):
+    f, b = Fasta(), HBatch()
+    err = C.create_string_buffer(256)
+    assert lib.cbch_read_fasta(fa.encode(), C.byref(f), err, 256) == 0, err.value
+    rc = lib.cbch_read_sam(sam.encode(), C.byref(f), var_length, C.byref(b), err, 256)
+    return rc, f, b, err.value.decode()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(seed=31, genome_len=200_000, n_reads=5000, len_min=100, len_max=100, p_sub=0.01, p_indel=0.01, p_clip=0.2),
+    dict(seed=32, genome_len=400_000, n_chr=3, n_reads=4000, len_min=50, len_max=250, p_sub=0.01, p_indel=0.02, p_clip=0.3),
+])
+def test_sam_text_parses_to_the_generators_batch(lib, kw):
+    cfg = synth.SynthConfig(**kw)
+    g = synth.make_genome(cfg); b = synth.make_reads(cfg, g)
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g); synth.write_sam(sam, b, g)
+        rc, f, hb, err = _parse(lib, sam, fa, var_length=int(cfg.len_min != cfg.len_max))
+        assert rc == 0, err
+        n = hb.n_reads
+        assert n == b.n_reads and f.n == g.n_chr
+        for c in range(g.n_chr):
+            assert f.names[c].decode() == g.names[c] and f.len[c] == len(g.bases[c])
+            assert np.array_equal(_arr(f.bases[c], f.len[c], np.uint8), g.bases[c])
+        assert np.array_equal(_arr(hb.pos, n, np.uint32), b.pos) and np.array_equal(_arr(hb.flag, n, np.uint16), b.flag)
+        assert np.array_equal(_arr(hb.seq_len, n, np.uint16), b.seq_len) and np.array_equal(_arr(hb.chr, n, np.uint32), b.chr)
+        for name in ("seq", "cigar", "md"):
+            off = _arr(getattr(hb, name + "_off"), n + 1, np.uint64)
+            assert np.array_equal(off, getattr(b, name + "_off"))
+            assert np.array_equal(_arr(getattr(hb, name), int(off[-1]), np.uint8), getattr(b, name)[:int(off[-1])])
+        want = int(b.seq_len.max()) if cfg.len_min != cfg.len_max else int(b.seq_len[1])
+        assert hb.read_len_header == want                         # get_read_length, src/sam_file_allocation.c:26-79
+
+
+def test_edge_records(lib):
+    ref = "ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT"
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        with open(fa, "w") as f:
+            f.write(">chrA some description\nACGTACGTAC\nGTACGTACGT\r\nACGTACGTACGTACGTACGT\n>chrB\nTTTT\n")
+        lines = ["@HD\tVN:1.6", "@SQ\tSN:chrA\tLN:40",
+                 "r0\t0\tchrA\t1\t60\t8M\t*\t0\t0\tACGTACGT\tIIIIIIII\tNM:i:0\tMD:Z:8",            # MD last field, no trailing tab
+                 "r1\t4\t*\t0\t0\t*\t*\t0\t0\tACGTAC\tIIIIII",                                      # unmapped: skipped
+                 "r2\t16\tchrA\t5\t60\t6M\t*\t0\t0\tACGTAC\tIIIIII\tMD:Z:6\tAS:i:0\r",            # CRLF
+                 "r3\t0\tchrB\t1\t60\t4M\t*\t0\t0\tTTTA\tIIII\tXX:Z:q\tMD:Z:3T0"]
+        with open(sam, "w") as f:
+            f.write("\n".join(lines) + "\n")
+        rc, f, hb, err = _parse(lib, sam, fa)
+        assert rc == 0, err
+        assert f.n == 2 and f.names[0] == b"chrA" and f.len[0] == 40 and bytes(_arr(f.bases[0], 40, np.uint8)) == ref.encode()
+        assert hb.n_reads == 3 and hb.n_unmapped == 1
+        assert _arr(hb.pos, 3, np.uint32).tolist() == [1, 5, 1] and _arr(hb.chr, 3, np.uint32).tolist() == [0, 0, 1]
+        md_off = _arr(hb.md_off, 4, np.uint64); md = bytes(_arr(hb.md, int(md_off[-1]), np.uint8))
+        assert md == b"863T0" and md_off.tolist() == [0, 1, 2, 5]
+        assert hb.read_len_header == 6                              # second record's SEQ length, mapped or not
+        # errors are reported, not asserted
+        with open(sam, "w") as f:
+            f.write("r0\t0\tchrZ\t1\t60\t4M\t*\t0\t0\tACGT\tIIII\tMD:Z:4\n")
+        rc, _, _, err = _parse(lib, sam, fa)
+        assert rc == -4 and "chrZ" in err
+        with open(sam, "w") as f:
+            f.write("r0\t0\tchrA\t1\t60\t4M\t*\t0\t0\tACGT\tIIII\n")
+        rc, _, _, err = _parse(lib, sam, fa)
+        assert rc == -5
