@@ -50,24 +50,33 @@ __device__ __forceinline__ uint32_t num_digits(uint32_t x) {
 }
 __device__ __forceinline__ bool is_digit(uint32_t c) { return c >= '0' && c <= '9'; }
 
+#define K1_ECACHE 4u          /* edits per read remembered from the count pass (kind in bits 14..15) */
 struct EditSink {
     uint16_t *dst;          /* NULL: count only */
     uint32_t nd_total, ns_total;   /* write mode: counts from the count pass (slot bases) */
     uint32_t n_dels, n_snps, n_ins;
     int err;
+    uint16_t *cache;        /* count pass: first K1_ECACHE entries in emission order (shared memory), or NULL */
+    __device__ __forceinline__ void remember(uint32_t kind, uint32_t e) {
+        const uint32_t k = n_dels + n_snps + n_ins;
+        if (cache && k < K1_ECACHE) cache[k] = (uint16_t)(e | (kind << 14));
+    }
     __device__ __forceinline__ void del(uint32_t delta) {
         if (delta > 255u) err = 1;
         if (dst && n_dels < 255u) dst[n_dels] = CBCG_EDIT(delta & 0xffu, 0, 0);
+        remember(0u, CBCG_EDIT(delta & 0xffu, 0, 0));
         n_dels++;
     }
     __device__ __forceinline__ void snp(uint32_t delta, uint32_t target, uint32_t refb) {
         if (delta > 255u) err = 1;
         if (dst && n_snps < 255u) dst[nd_total + n_snps] = CBCG_EDIT(delta & 0xffu, target, refb);
+        remember(1u, CBCG_EDIT(delta & 0xffu, target, refb));
         n_snps++;
     }
     __device__ __forceinline__ void ins(uint32_t delta, uint32_t target) {
         if (delta > 255u) err = 1;
         if (dst && n_ins < 255u) dst[nd_total + ns_total + n_ins] = CBCG_EDIT(delta & 0xffu, target, CBCG_BP_O);
+        remember(2u, CBCG_EDIT(delta & 0xffu, target, CBCG_BP_O));
         n_ins++;
     }
 };
@@ -170,8 +179,10 @@ struct K1Smem {
     uint32_t soff[K1_TILE];          /* offset of the read's SEQ in seq[] */
     uint32_t cnt[K1_TILE];           /* n_snps | n_dels << 8 | n_ins << 16 | match << 24 | bad << 25 */
     uint32_t excl[K1_TILE];
+    uint32_t roff[K1_TILE];          /* offset of the read's reference bases in ref[] (when in the window) */
     uint16_t len[K1_TILE];
-    uint16_t chr_ok[K1_TILE];        /* read may use the staged window */
+    uint16_t chr_ok[K1_TILE];        /* bit 0: read may use the staged window, bit 1: read passes the input checks */
+    uint16_t ecache[K1_TILE][K1_ECACHE];
     __align__(16) uint8_t ref[K1_REF_CAP + 16];
     __align__(16) uint8_t seq[16];   /* really K1_TILE * max_len + 48 (dynamic) */
 };
@@ -228,36 +239,50 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
         S.pos[tid] = my_pos; S.len[tid] = (uint16_t)my_len; S.soff[tid] = (uint32_t)(so - a0);
         bool in_win = (my_chr == chr0) && ref_bytes && my_pos >= 1u && (uint64_t)(my_pos - 1u) >= w0 &&
                       ((uint64_t)(my_pos - 1u) - w0 + my_len + 8u <= ref_bytes);
-        S.chr_ok[tid] = in_win ? 1 : 0;
+        bool ok = seq_ok && my_pos >= 1u && my_len >= 1u && my_len <= CBCG_MAX_READ_LEN && my_chr < g.n_chr;
+        if (ok) { const uint64_t clen = (my_chr == chr0) ? clen0 : g.chr_len[my_chr]; ok = ((uint64_t)(my_pos - 1u) + my_len <= clen); }
+        S.roff[tid] = in_win ? (uint32_t)((uint64_t)(my_pos - 1u) - w0) : 0u;
+        S.chr_ok[tid] = (uint16_t)((in_win ? 1u : 0u) | (ok ? 2u : 0u));
     }
     __syncthreads();
     mbar_wait(&S.bar, 0);
 
-    /* ---- phase 1: warp per read, perfect-match test (src/read_compression.c:291-296) */
-    for (uint32_t i = warp; i < nr; i += K1_WARPS) {
-        const uint32_t pos = S.pos[i], len = S.len[i], soff = S.soff[i];
-        const uint32_t chr = b.chr[r0 + i];
-        uint32_t diff = 0;
-        bool ok = seq_ok && pos >= 1u && len >= 1u && len <= CBCG_MAX_READ_LEN && chr < g.n_chr;
-        uint64_t clen = 0;
-        if (ok) { clen = (chr == chr0) ? clen0 : g.chr_len[chr]; ok = ((uint64_t)(pos - 1u) + len <= clen); }
-        if (ok) {
-            if (S.chr_ok[i]) {
-                const uint32_t roff = (uint32_t)((uint64_t)(pos - 1u) - w0);
-                const uint32_t words = (len + 3u) >> 2;
-                for (uint32_t j = lane; j < words; j += 32u) {
-                    uint32_t x = lds_u32_unaligned(S.seq, soff + 4u * j) ^ lds_u32_unaligned(S.ref, roff + 4u * j);
-                    uint32_t rem = len - 4u * j;
-                    if (rem < 4u) x &= (1u << (8u * rem)) - 1u;
-                    diff |= x;
+    /* ---- phase 1: perfect-match test (src/read_compression.c:291-296). Half a warp per read, 16 bytes per lane:
+       SEQ against the staged window, both at arbitrary byte offsets in shared memory. */
+    {
+        const uint32_t half = lane >> 4, sub = lane & 15u;
+        for (uint32_t i0 = warp * 2u; i0 < nr; i0 += K1_WARPS * 2u) {
+            const uint32_t i = i0 + half;
+            uint32_t diff = 0; bool ok = false;
+            if (i < nr) {
+                const uint32_t fl = S.chr_ok[i], len = S.len[i], soff = S.soff[i];
+                ok = (fl & 2u) != 0u;
+                if (ok && (fl & 1u)) {
+                    const uint32_t o = sub * 16u;
+                    if (o < len) {
+                        const uint32_t so = soff + o, ro = S.roff[i] + o, rem = len - o;
+                        const uint32_t *sw = reinterpret_cast<const uint32_t *>(S.seq + (so & ~3u));
+                        const uint32_t *rw = reinterpret_cast<const uint32_t *>(S.ref + (ro & ~3u));
+                        const uint32_t ss = (so & 3u) * 8u, rs = (ro & 3u) * 8u;
+                        uint32_t s_prev = sw[0], r_prev = rw[0];
+#pragma unroll
+                        for (uint32_t q = 0; q < 4u; q++) {
+                            const uint32_t s_next = sw[q + 1u], r_next = rw[q + 1u];
+                            uint32_t x = __funnelshift_r(s_prev, s_next, ss) ^ __funnelshift_r(r_prev, r_next, rs);
+                            const uint32_t vb = rem > 4u * q ? rem - 4u * q : 0u;           /* bytes of this word inside the read */
+                            if (vb < 4u) x &= (1u << (8u * vb)) - 1u;
+                            diff |= x;
+                            s_prev = s_next; r_prev = r_next;
+                        }
+                    }
+                } else if (ok) {                          /* window miss: straight from HBM */
+                    const uint8_t *rp = g.bases + g.chr_off[b.chr[r0 + i]] + (S.pos[i] - 1u);
+                    for (uint32_t j = sub; j < len; j += 16u) diff |= (uint32_t)(S.seq[soff + j] ^ rp[j]);
                 }
-            } else {                                    /* window miss: straight from HBM */
-                const uint8_t *rp = g.bases + g.chr_off[chr] + (pos - 1u);
-                for (uint32_t j = lane; j < len; j += 32u) diff |= (uint32_t)(S.seq[soff + j] ^ rp[j]);
             }
+            const uint32_t bal = __ballot_sync(FULL_MASK, diff != 0u);
+            if (sub == 0u && i < nr) S.cnt[i] = (ok && !((bal >> (half * 16u)) & 0xffffu)) ? (1u << 24) : 0u;
         }
-        const bool match = ok && !__any_sync(FULL_MASK, diff != 0u);
-        if (lane == 0) S.cnt[i] = match ? (1u << 24) : 0u;
     }
     __syncthreads();
 
@@ -267,7 +292,7 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
         my_cnt = S.cnt[tid];
         bool bad = !seq_ok || my_pos == 0u || my_len == 0u || my_len > CBCG_MAX_READ_LEN || my_chr >= g.n_chr;
         if (!bad && !(my_cnt >> 24)) {
-            EditSink sink = { nullptr, 0u, 0u, 0u, 0u, 0u, 0 };
+            EditSink sink = { nullptr, 0u, 0u, 0u, 0u, 0u, 0, S.ecache[tid] };
             walk_read(S.seq + S.soff[tid], my_len, b.cigar + my_co, my_clen, b.md + my_mo, my_mlen, sink);
             if (sink.err) bad = true;
             else { my_cnt = sink.n_snps | (sink.n_dels << 8) | (sink.n_ins << 16); my_total = sink.n_snps + sink.n_dels + sink.n_ins; }
@@ -304,8 +329,15 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
         reinterpret_cast<uint4 *>(recs)[r0 + tid] = *reinterpret_cast<uint4 *>(&rec);
         if (my_total) {
             if (off + my_total > edits_cap) dev_set_error(err, CBCG_ERR_CAPACITY, r0 + tid);
-            else {
-                EditSink sink = { edits + off, rec.n_dels, rec.n_snps, 0u, 0u, 0u, 0 };
+            else if (my_total <= K1_ECACHE) {           /* the count pass kept them: no second walk */
+                uint32_t at[3] = { 0u, rec.n_dels, (uint32_t)rec.n_dels + rec.n_snps };
+                for (uint32_t k = 0; k < my_total; k++) {
+                    const uint32_t e = S.ecache[tid][k], kind = e >> 14;
+                    const uint32_t slot = kind == 0u ? at[0]++ : (kind == 1u ? at[1]++ : at[2]++);
+                    edits[off + slot] = (uint16_t)(e & 0x3fffu);
+                }
+            } else {
+                EditSink sink = { edits + off, rec.n_dels, rec.n_snps, 0u, 0u, 0u, 0, nullptr };
                 walk_read(S.seq + S.soff[tid], my_len, b.cigar + my_co, my_clen, b.md + my_mo, my_mlen, sink);
             }
         }

@@ -302,9 +302,10 @@ struct Coder {
         ac_narrow(a, lo, lo + cnt, n);
         uint32_t k, bits, m; AcInterval nx;
         ac_renorm_shape(a, k, bits, m, nx);
-        uint32_t s = k + m;
-        if (s > 32u) { (void)get_bits(s - 32u); s = 32u; }                   /* only the last 26 bits survive the shift */
-        t = ac_tag_shift(t, k, m, get_bits(s));
+        uint32_t s = k + m;                                                   /* up to 51 bits; the tag keeps the last 26 */
+        uint64_t in64 = 0;
+        do { const uint32_t take = s < 32u ? s : 32u; in64 = (in64 << take) | get_bits(take); s -= take; } while (s);
+        t = ac_tag_shift(t, k, m, (uint32_t)in64);
         a = nx;
     }
     /* encoder_last_step (:348-364) */

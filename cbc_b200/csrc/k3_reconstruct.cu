@@ -142,9 +142,28 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
             if (lane == 0) dst[len] = '\n';
             continue;
         }
-        /* edit positions: prefix sums of the deltas (lists are short; 32 entries per step) */
         const uint16_t *e = edits + rec.edit_off;
         bool malformed = false;
+        if ((nd | ni) == 0u) {                              /* substitutions only: copy, then patch the SNP sites (:442-458) */
+            for (uint32_t j = lane; j < len; j += 32u) dst[j] = src[j];
+            if (lane == 0) dst[len] = '\n';
+            __syncwarp();
+            uint32_t carry = 0;                             /* SNP k sits at sum_{i<k}(p_i + 1) + p_k */
+            for (uint32_t k0 = 0; k0 < ns; k0 += 32u) {
+                const uint32_t k = k0 + lane; const uint32_t ed = (k < ns) ? e[k] : 0u;
+                const uint32_t d = (k < ns) ? CBCG_EDIT_DELTA(ed) + 1u : 0u;
+                const uint32_t s = warp_incl_scan(d) + carry;
+                if (k < ns) { if (s - 1u >= len) malformed = true; else dst[s - 1u] = (uint8_t)base_char(CBCG_EDIT_TARGET(ed)); }
+                carry = __shfl_sync(FULL_MASK, s, 31);
+            }
+            if (__any_sync(FULL_MASK, malformed)) {
+                if (lane == 0) dev_set_error(err, CBCG_ERR_CORRUPT, r0 + i);
+                for (uint32_t j = lane; j < len; j += 32u) dst[j] = 'N';
+            }
+            __syncwarp();
+            continue;
+        }
+        /* edit positions: prefix sums of the deltas (lists are short; 32 entries per step) */
         {
             uint32_t carry = 0;
             for (uint32_t k0 = 0; k0 < nd; k0 += 32u) {

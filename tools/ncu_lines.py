@@ -14,7 +14,9 @@ for l in dis:
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m: cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
     if re.match(r'\s+/\*[0-9a-f]{4,}\*/\s', l): lines.append(cur)
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+import os
+kf = os.environ.get('NCU_KERNEL')
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + (['--kernel-name', 'regex:' + kf, '--launch-count', '1'] if kf else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
 hdr = rows[h]; idx = {x: i for i, x in enumerate(hdr)}
