@@ -38,24 +38,32 @@ AC_HD uint64_t ac_div(uint64_t p, uint32_t n) {
 #endif
 }
 
-/* Exact floor(p / d) through one shared reciprocal: for p < 2^47 and 0 < d < 2^27 the estimate
- * trunc(p * rcp(d)) is off by at most one (relative error of the product < 2^-51, quotient < 2^47), and the
- * integer remainder check puts it right. The interval update needs two quotients by the same n, so the
- * reciprocal is computed once per symbol: ~25 integer/FP64 instructions instead of two full divisions. */
+/* Exact floor((a * b - sub) / d) for a, b, d < 2^27 whose quotient is < 2^27 (every division of this coder:
+ * range <= 2^26, counts and totals < 2^21). The product is exact in a double (< 2^54 ... here < 2^48), the
+ * reciprocal comes from rcp.approx (relative error <= 2^-23) plus one Newton step (<= 2^-45), so the estimate
+ * trunc(p * r) is off by at most one and the integer remainder check puts it right. One reciprocal serves both
+ * quotients of an interval update: ~15 instructions each instead of a full 64-bit division. */
 AC_HD double ac_rcp(uint32_t d) {
 #ifdef __CUDA_ARCH__
-    return __drcp_rn((double)d);
+    const double x = (double)d;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = __fma_rn(-x, r, 1.0);
+    return __fma_rn(r, e, r);
 #else
     return 1.0 / (double)d;
 #endif
 }
-AC_HD uint64_t ac_div_r(uint64_t p, uint32_t d, double r) {
+AC_HD uint32_t ac_muldiv(uint32_t a, uint32_t b, uint32_t sub, uint32_t d, double r) {
 #ifdef __CUDA_ARCH__
-    uint64_t q = (uint64_t)__double2ull_rz(__dmul_rn(__ull2double_rz(p), r));
+    const double pd = __dmul_rn(__uint2double_rn(a), __uint2double_rn(b)) - (double)sub;
+    uint32_t q = __double2uint_rz(__dmul_rn(pd, r));
 #else
-    uint64_t q = (uint64_t)((double)p * r);
+    const double pd = (double)a * (double)b - (double)sub;
+    uint32_t q = (uint32_t)(pd * r);
 #endif
-    const int64_t rem = (int64_t)(p - q * (uint64_t)d);
+    const uint64_t p = (uint64_t)a * b - sub;
+    const int64_t rem = (int64_t)(p - (uint64_t)q * d);
     if (rem < 0) q--; else if (rem >= (int64_t)d) q++;
     return q;
 }
@@ -65,10 +73,10 @@ struct AcInterval { uint32_t l, u; };
 /* Interval update of arithmetic_encoder_step / arithmetic_decoder_step (:295-296, :402-403):
  * u is computed from the old l, both products in 64 bits, truncated to 32. */
 AC_HD void ac_narrow(AcInterval &a, uint32_t lo, uint32_t hi, uint32_t n) {
-    const uint64_t range = (uint64_t)a.u - a.l + 1u;
+    const uint32_t range = a.u - a.l + 1u;                 /* <= 2^26 */
     const double r = ac_rcp(n);
-    const uint32_t nu = a.l + (uint32_t)ac_div_r(range * hi, n, r) - 1u;
-    const uint32_t nl = a.l + (uint32_t)ac_div_r(range * lo, n, r);
+    const uint32_t nu = a.l + ac_muldiv(range, hi, 0u, n, r) - 1u;
+    const uint32_t nl = a.l + ac_muldiv(range, lo, 0u, n, r);
     a.u = nu; a.l = nl;
 }
 
@@ -102,7 +110,7 @@ AC_HD uint32_t ac_tag_shift(uint32_t t, uint32_t k, uint32_t m, uint32_t in) {
 
 /* arithmetic_get_symbol_range (:373-381) */
 AC_HD uint32_t ac_target(const AcInterval &a, uint32_t t, uint32_t n) {
-    const uint64_t range = (uint64_t)a.u - a.l + 1u;
-    const uint64_t gap = (uint64_t)t - a.l + 1u;
-    return (uint32_t)ac_div_r(gap * n - 1u, (uint32_t)range, ac_rcp((uint32_t)range));
+    const uint32_t range = a.u - a.l + 1u;
+    const uint32_t gap = t - a.l + 1u;
+    return ac_muldiv(gap, n, 1u, range, ac_rcp(range));
 }

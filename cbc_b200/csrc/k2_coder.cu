@@ -364,38 +364,54 @@ struct Coder {
         if (pre) { lo = pre_lo; cnt = m[x]; }
         else if (MODE == MODE_ENC) {
             if (x >= card) { err = CBCG_ERR_INPUT; return 0u; }              /* reference: assert :62 */
-            uint32_t s = 0;
-            for (uint32_t base = 0; base < x; base += 128u) {
-                const uint32_t i = base + 4u * lane;
-                const uint4 v = load4(m, i, card);
-                s += (i < x ? v.x : 0u) + (i + 1u < x ? v.y : 0u) + (i + 2u < x ? v.z : 0u) + (i + 3u < x ? v.w : 0u);
+            if (x < 4u) {                                                    /* most symbols are small: one broadcast load */
+                const uint4 v = load4(m, 0u, card);
+                lo = (x > 0u ? v.x : 0u) + (x > 1u ? v.y : 0u) + (x > 2u ? v.z : 0u);
+                cnt = x == 0u ? v.x : (x == 1u ? v.y : (x == 2u ? v.z : v.w));
+            } else {
+                uint32_t s = 0;
+                for (uint32_t base = 0; base < x; base += 128u) {
+                    const uint32_t i = base + 4u * lane;
+                    const uint4 v = load4(m, i, card);
+                    s += (i < x ? v.x : 0u) + (i + 1u < x ? v.y : 0u) + (i + 2u < x ? v.z : 0u) + (i + 3u < x ? v.w : 0u);
+                }
+                lo = warp_sum(s); cnt = m[x];
             }
-            lo = warp_sum(s); cnt = m[x];
         } else {
             const uint32_t target = ac_target(a, t, n);
-            uint32_t carry = 0; bool found = false;
-            x = 0;
-            for (uint32_t base = 0; base < card; base += 128u) {
-                const uint32_t i = base + 4u * lane;
-                const uint4 v = load4(m, i, card);
-                const uint32_t mine = v.x + v.y + v.z + v.w;
-                const uint32_t incl = warp_incl_scan(mine) + carry;
-                const uint32_t hit = __ballot_sync(FULL_MASK, incl > target);     /* lanes past the row add 0: never first */
-                if (hit) {
-                    const uint32_t h = (uint32_t)__ffs(hit) - 1u;
-                    const uint32_t before = __shfl_sync(FULL_MASK, incl - mine, h);
-                    const uint32_t c0 = __shfl_sync(FULL_MASK, v.x, h), c1 = __shfl_sync(FULL_MASK, v.y, h);
-                    const uint32_t c2 = __shfl_sync(FULL_MASK, v.z, h), c3 = __shfl_sync(FULL_MASK, v.w, h);
-                    uint32_t q = 0; lo = before; cnt = c0;
-                    if (lo + cnt <= target) { lo += cnt; cnt = c1; q = 1u; }
-                    if (lo + cnt <= target) { lo += cnt; cnt = c2; q = 2u; }
-                    if (lo + cnt <= target) { lo += cnt; cnt = c3; q = 3u; }
-                    x = base + 4u * h + q; found = true;
-                    break;
+            const uint4 f = load4(m, 0u, card);
+            if (target < f.x + f.y + f.z + f.w) {                            /* resolved by the first four counts: no scan */
+                uint32_t q = 0; lo = 0; cnt = f.x;
+                if (lo + cnt <= target) { lo += cnt; cnt = f.y; q = 1u; }
+                if (lo + cnt <= target) { lo += cnt; cnt = f.z; q = 2u; }
+                if (lo + cnt <= target) { lo += cnt; cnt = f.w; q = 3u; }
+                x = q;
+            } else {
+                uint32_t carry = 0; bool found = false;
+                x = 0;
+                for (uint32_t base = 0; base < card; base += 128u) {
+                    const uint32_t i = base + 4u * lane;
+                    const uint4 v = load4(m, i, card);
+                    const uint32_t mine = v.x + v.y + v.z + v.w;
+                    const uint32_t incl = warp_incl_scan(mine) + carry;
+                    const uint32_t hit = __ballot_sync(FULL_MASK, incl > target);     /* lanes past the row add 0: never first */
+                    if (hit) {
+                        const uint32_t h = (uint32_t)__ffs(hit) - 1u;
+                        const uint32_t before = __shfl_sync(FULL_MASK, incl - mine, h);
+                        const uint32_t c0 = __shfl_sync(FULL_MASK, v.x, h), c1 = __shfl_sync(FULL_MASK, v.y, h);
+                        const uint32_t c2 = __shfl_sync(FULL_MASK, v.z, h), c3 = __shfl_sync(FULL_MASK, v.w, h);
+                        uint32_t q = 0; lo = before; cnt = c0;
+                        if (lo + cnt <= target) { lo += cnt; cnt = c1; q = 1u; }
+                        if (lo + cnt <= target) { lo += cnt; cnt = c2; q = 2u; }
+                        if (lo + cnt <= target) { lo += cnt; cnt = c3; q = 3u; }
+                        x = base + 4u * h + q; found = true;
+                        break;
+                    }
+                    carry = __shfl_sync(FULL_MASK, incl, 31);
                 }
-                carry = __shfl_sync(FULL_MASK, incl, 31);
+                if (!found) { err = CBCG_ERR_CORRUPT; return 0u; }
             }
-            if (!found || x >= card) { err = CBCG_ERR_CORRUPT; return 0u; }
+            if (x >= card) { err = CBCG_ERR_CORRUPT; return 0u; }
         }
         last_lo = lo; last_n = n;
         code_interval(lo, cnt, n);
