@@ -233,9 +233,10 @@ def run_b200_arm(args):
     stage = {k: [] for k in ("k1", "plan", "k2e", "gather", "k2d", "k3", "enc_total", "dec_total")}
     launches = 0
     index_bytes = 0
+    block_reads_used = R
 
     def resident_step(record: bool):
-        nonlocal launches, index_bytes
+        nonlocal launches, index_bytes, block_reads_used
         codec.encode_resident(L, R, G)
         se = codec.stats()
         head, payload = codec.fetch_index()
@@ -249,6 +250,7 @@ def run_b200_arm(args):
             stage["k2d"].append(sd["ms_code"]); stage["k3"].append(sd["ms_k3"]); stage["dec_total"].append(sd["ms_total"])
             launches += se["kernel_launches"] + sd["kernel_launches"]
         index_bytes = len(head)
+        block_reads_used = int.from_bytes(head[32:36], "little")
         return se, sd
 
     for _ in range(args.warmup):
@@ -369,7 +371,7 @@ def run_b200_arm(args):
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": f"config2: 150bp reads at 30x over {cfg.genome_len} bp, 0.5% substitutions, one such region per GPU",
-                   "n_reads_per_gpu": n, "read_len": 150, "block_reads": R, "gen_mode": G, "blocks_per_gpu": int(se["n_blocks"]),
+                   "n_reads_per_gpu": n, "read_len": 150, "block_reads": block_reads_used, "block_reads_auto": R == 0xffffffff, "gen_mode": G, "blocks_per_gpu": int(se["n_blocks"]),
                    "l2": "inputs larger than L2 (batch %.0f MB, decoded text %.0f MB per GPU)" % (s1["h2d_bytes"] / 1e6, (bases + n) / 1e6),
                    "parallelism": f"{world} region shard(s), no collective on the coding path"},
         "compress_reads_per_s": total_reads / (max_over_ranks(med["enc_total"]) * 1e-3),
@@ -398,7 +400,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--block-reads", type=int, default=768)
+    ap.add_argument("--block-reads", type=int, default=0xffffffff, help="reads per block; default: sized to whole waves (CBCG_BLOCK_AUTO)")
     ap.add_argument("--gen-mode", type=int, default=1, help="1: generation-primed blocks (default), 0: cold blocks")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; the bench line needs 1.0)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")

@@ -555,6 +555,18 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     const uint64_t n = ctx->db.n_reads;
     const int legacy = opts->block_reads == 0;
     const uint32_t L = opts->read_len_header;
+    cbcg_encode_opts auto_opts = *opts;
+    if (opts->block_reads == CBCG_BLOCK_AUTO) {             /* last generation = a whole number of full waves */
+        static const uint32_t sc[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sr[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
+        uint64_t early = 0;
+        if (opts->gen_mode) for (uint32_t g = 0; g < CBCG_GEN_LEVELS; g++) early += (uint64_t)sc[g] * sr[g];
+        const uint64_t main_reads = n > early ? n - early : n;
+        const uint64_t slots = coder_resident_blocks(ctx->device);
+        const uint64_t waves = std::max<uint64_t>(1, (main_reads + slots * CBCG_BLOCK_AUTO_MAX - 1) / (slots * CBCG_BLOCK_AUTO_MAX));
+        uint64_t r = (main_reads + waves * slots - 1) / (waves * slots);
+        auto_opts.block_reads = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(r, 64), CBCG_BLOCK_AUTO_MAX);
+        opts = &auto_opts;
+    }
     ctx->have_encoded = false;
     cbcg_stats &S = ctx->stats;
     S.ms_extract = S.ms_plan = S.ms_code = S.ms_gather = S.ms_reconstruct = S.ms_d2h = S.ms_total = S.ms_k1 = S.ms_k3 = 0;

@@ -91,6 +91,7 @@ uint64_t reconstruct_num_tiles(uint64_t n_reads);
 int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap,
                 uint64_t payload_cap, uint64_t *totals, cudaStream_t st);
 int launch_coder(const CoderParams &p, cudaStream_t st);
+uint32_t coder_resident_blocks(int device);     /* blocks (warps) of the encode kernel the whole GPU holds at once */
 int launch_gather(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
                   uint64_t *out_off, cudaStream_t st);
 uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy, int primed);

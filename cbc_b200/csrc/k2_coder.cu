@@ -1090,6 +1090,13 @@ k2_coder_kernel(CoderParams P) {
 }
 
 
+uint32_t coder_resident_blocks(int device) {
+    int sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) return 148u * 16u;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_coder_kernel<MODE_ENC>, (int)K2_THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = K2_MIN_CTAS;
+    return (uint32_t)sms * (uint32_t)per_sm * K2_WARPS;
+}
+
 int launch_coder(const CoderParams &p, cudaStream_t st) {
     if (p.n_blocks == 0) return 0;
     const unsigned grid = (p.n_blocks + K2_WARPS - 1) / K2_WARPS;

@@ -55,6 +55,12 @@ typedef struct cbcg_batch {
     const uint64_t *md_off;     const uint8_t *md;      /* MD:Z payload (read_line_t.edits) */
 } cbcg_batch;
 
+/* block_reads value that lets the library size blocks so that the last generation fills the GPU's resident
+ * block slots a whole number of times (reads per block <= CBCG_BLOCK_AUTO_MAX). The choice is written to the
+ * container header like any other block size. */
+#define CBCG_BLOCK_AUTO      0xffffffffu
+#define CBCG_BLOCK_AUTO_MAX  1280u
+
 typedef struct cbcg_encode_opts {
     uint32_t read_len_header;   /* what get_read_length returns (src/sam_file_allocation.c:26-79):
                                    the alphabet size of the snps/indels/var models */

@@ -11,7 +11,7 @@ from cbc_b200 import synth                      # noqa: E402
 from cbc_b200.codec import Codec, pin_batch     # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-sizes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [256, 512, 1024, 2048, 4096, 16384, 65536]
+sizes = [int(x) if x != "auto" else 0xffffffff for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [256, 512, 1024, 2048, 4096, 16384, 65536]
 gen_mode = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 cfg = synth.SynthConfig.named("config2", scale=scale)
 g = synth.make_genome(cfg)
