@@ -836,11 +836,13 @@ k2_coder_kernel(CoderParams P) {
                     pos = v.x; flag = v.y & 0xffffu; len = v.y >> 16; match = v.w & 0xffu;
                     ns = (v.w >> 8) & 0xffu; nd = (v.w >> 16) & 0xffu; ni = v.w >> 24;
                     e_in = P.edits + v.z;
-                    chr = P.chr[r0 + i];
-                    if (chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; break; }
-                    if (legacy) { change = chr != cur_chr; state = ST_SAMEREF; }
-                    else {
-                        if (chr != cur_chr) { C.err = CBCG_ERR_INTERNAL; break; }      /* blocks never span chromosomes */
+                    if (!match) asm volatile("prefetch.global.L1 [%0];" ::"l"(e_in));
+                    if (legacy) {
+                        chr = P.chr[r0 + i];
+                        if (chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; break; }
+                        change = chr != cur_chr; state = ST_SAMEREF;
+                    } else {                                                           /* blocks never span chromosomes: the host cut them */
+                        if (cur_chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; break; }
                         change = 0; state = lean ? ST_RLEN0 : ST_SAMEREF;
                     }
                 } else { change = 0; state = (legacy || !lean) ? ST_SAMEREF : ST_RLEN0; }
@@ -1313,16 +1315,18 @@ __global__ void __launch_bounds__(128) merge_prep_kernel(MergeParams P) {
 
 /* merge step 2, one warp per block: every count of the block minus the snapshot's, added into `next`
  * (which starts as a copy of the snapshot). Wrapping 32-bit sums; step 3 reads them back as signed. */
+#define MERGE_PARTS 8u
 __global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t b = blockIdx.x * 4u + warp;
     if (b >= P.n_blocks) return;
+    const uint32_t part = blockIdx.y;                      /* the block's work is split over MERGE_PARTS warps */
     const SnapLayout l = snap_layout(P.L);
     const BlockDesc &B = P.blocks[P.block_begin + b];
     const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
     const uint8_t *wsb = P.ws + B.ws_off;
     /* small models: every word from snps up to the FLAG table (the n slots are recomputed in step 3) */
-    {
+    if (part == 0u) {
         const uint32_t *ps = reinterpret_cast<const uint32_t *>(P.prev + l.small);
         uint32_t *ns = reinterpret_cast<uint32_t *>(P.next + l.small);
         const uint32_t *fs = reinterpret_cast<const uint32_t *>(P.fin + (uint64_t)b * fin_stride_dev());
@@ -1335,14 +1339,14 @@ __global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
         for (uint32_t j = lane; j < used; j += 32u) { const uint32_t k = fm->flag_key[j] & 0xffffu; const uint32_t d = fm->flag_cnt[j] - dprev[k]; if (d) atomicAdd(&dacc[k], d); }
     }
     /* POS slots the block shares with the snapshot */
-    {
+    if (part == 1u % MERGE_PARTS) {
         const uint32_t pc = reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr)[0];
         const uint32_t *pcnt = reinterpret_cast<const uint32_t *>(P.prev + l.pos_cnt);
         uint32_t *ncnt = reinterpret_cast<uint32_t *>(P.next + l.pos_cnt);
         const uint32_t *bcnt = reinterpret_cast<const uint32_t *>(wsb + w.pos_cnt);
         for (uint32_t s = lane; s < pc; s += 32u) { const uint32_t d = bcnt[s] - pcnt[s]; if (d) atomicAdd(&ncnt[s], d); }
     }
-    if (B.pa_touched) {
+    if (B.pa_touched && part == 2u % MERGE_PARTS) {
         const uint32_t *pa_prev = reinterpret_cast<const uint32_t *>(P.prev + l.pos_alpha);
         uint32_t *pa_next = reinterpret_cast<uint32_t *>(P.next + l.pos_alpha);
         const uint32_t *pa_blk = reinterpret_cast<const uint32_t *>(wsb + w.pos_alpha);
@@ -1355,7 +1359,7 @@ __global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
         uint32_t *var = reinterpret_cast<uint32_t *>(P.next + l.var);
         const uint64_t *hash = reinterpret_cast<const uint64_t *>(wsb + w.var_hash);
         const uint32_t *rows = reinterpret_cast<const uint32_t *>(wsb + w.var_rows);
-        for (uint32_t h0 = 0; h0 < w.hash_cap; h0 += 32u) {
+        for (uint32_t h0 = part * 32u; h0 < w.hash_cap; h0 += 32u * MERGE_PARTS) {
             const uint64_t sl = hash[h0 + lane];
             uint32_t km = __ballot_sync(FULL_MASK, (uint32_t)(sl >> 32) != 0u);
             while (km) {
@@ -1455,32 +1459,49 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
         if (lane == 0) { nhdr[0] = an; nhdr[1] = n; }
     }
     __syncthreads();
-    /* FLAG: clamp, total, rescale over the dense scratch, then ordered compaction of the counts != 1 */
+    /* FLAG: clamp, total, rescale over the dense scratch, then ordered compaction of the counts != 1. Warp w owns
+       values [2048 w, 2048 w + 2048), read 32 at a time (coalesced). */
     WarpModels *nm = reinterpret_cast<WarpModels *>(P.next + l.small);
     uint32_t *dacc = reinterpret_cast<uint32_t *>(P.next + l.flag_acc);
-    uint32_t n;
+    const uint32_t base = warp * 2048u;
+    uint32_t n, mine = 0;
     {
         uint32_t s = 0;
-        for (uint32_t i = tid; i < 65536u; i += 1024u) { int32_t v = (int32_t)dacc[i]; if (v < 1) v = 1; dacc[i] = (uint32_t)v; s += (uint32_t)v; }
+        for (uint32_t j = 0; j < 64u; j++) {
+            const uint32_t i = base + 32u * j + lane;
+            int32_t v = (int32_t)dacc[i]; if (v < 1) v = 1;
+            dacc[i] = (uint32_t)v; s += (uint32_t)v;
+            mine += (uint32_t)__popc(__ballot_sync(FULL_MASK, v != 1));
+        }
         s = warp_sum(s); if (lane == 0) red[warp] = s; __syncthreads();
         n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
         __syncthreads();
     }
-    while (n >= CBCG_RESCALE) {
-        uint32_t s = 0;
-        for (uint32_t i = tid; i < 65536u; i += 1024u) { const uint32_t c = (dacc[i] >> 1) + 1u; dacc[i] = c; s += c; }
-        s = warp_sum(s); if (lane == 0) red[warp] = s; __syncthreads();
-        n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
-        __syncthreads();
+    if (n >= CBCG_RESCALE) {                               /* rare: halve-and-increment until the total fits */
+        while (n >= CBCG_RESCALE) {
+            uint32_t s = 0;
+            for (uint32_t j = 0; j < 64u; j++) { const uint32_t i = base + 32u * j + lane; const uint32_t c = (dacc[i] >> 1) + 1u; dacc[i] = c; s += c; }
+            s = warp_sum(s); if (lane == 0) red[warp] = s; __syncthreads();
+            n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
+            __syncthreads();
+        }
+        mine = 0;
+        for (uint32_t j = 0; j < 64u; j++) mine += (uint32_t)__popc(__ballot_sync(FULL_MASK, dacc[base + 32u * j + lane] != 1u));
     }
-    uint32_t mine = 0;
-    for (uint32_t i = 0; i < 64u; i++) mine += dacc[tid * 64u + i] != 1u;
-    scan[tid] = mine; __syncthreads();
-    for (uint32_t o = 1; o < 1024u; o <<= 1) { uint32_t v = tid >= o ? scan[tid - o] : 0u; __syncthreads(); scan[tid] += v; __syncthreads(); }
-    const uint32_t total = scan[1023];
-    uint32_t at = scan[tid] - mine;
+    if (lane == 0) scan[warp] = mine;
+    __syncthreads();
+    uint32_t at = 0, total = 0;
+    for (uint32_t k = 0; k < 32u; k++) { const uint32_t c = scan[k]; if (k < warp) at += c; total += c; }
     if (total > FLAG_CAP) { if (tid == 0) dev_set_error(P.err, CBCG_ERR_LIMIT, total); }
-    else for (uint32_t i = 0; i < 64u; i++) { const uint32_t c = dacc[tid * 64u + i]; if (c != 1u) { nm->flag_key[at] = tid * 64u + i; nm->flag_cnt[at] = c; at++; } }
+    else if (mine) {
+        for (uint32_t j = 0; j < 64u; j++) {
+            const uint32_t i = base + 32u * j + lane;
+            const uint32_t c = dacc[i];
+            const uint32_t bal = __ballot_sync(FULL_MASK, c != 1u);
+            if (c != 1u) { const uint32_t o = at + (uint32_t)__popc(bal & ((1u << lane) - 1u)); nm->flag_key[o] = i; nm->flag_cnt[o] = c; }
+            at += (uint32_t)__popc(bal);
+        }
+    }
     if (tid == 0) { nm->flag_used = total > FLAG_CAP ? 0u : total; nm->flag_n = n; }
 }
 
@@ -1509,7 +1530,7 @@ int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_block
     if (cudaMemcpyAsync(next, prev, snapshot_bytes(L), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
     MergeParams P = { blocks, block_begin, n_blocks, L, prev, next, fin, ws, err };
     merge_prep_kernel<<<148, 128, 0, st>>>(P);
-    merge_add_kernel<<<(n_blocks + 3u) / 4u, 128, 0, st>>>(P);
+    merge_add_kernel<<<dim3((n_blocks + 3u) / 4u, MERGE_PARTS), 128, 0, st>>>(P);
     merge_finish_kernel<<<1, MERGE_FIN_WARPS * 32u, 0, st>>>(P);
     merge_var_finish_kernel<<<(CBCG_VAR_CONTEXTS + 7u) / 8u, 256, 0, st>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
