@@ -91,8 +91,8 @@ typedef struct cbcg_read_rec {
  * CBCG_GEN_READS[i] reads, each starting from the merged final states of the generation before; the
  * last generation takes all remaining reads in blocks of block_reads. */
 #define CBCG_GEN_LEVELS     4
-#define CBCG_GEN_COUNTS     { 8u, 56u, 192u, 768u }
-#define CBCG_GEN_READS      { 32u, 64u, 128u, 256u }
+#define CBCG_GEN_COUNTS     { 16u, 112u, 384u, 1536u }
+#define CBCG_GEN_READS      { 16u, 32u, 64u, 128u }
 #define CBCG_SNAP_POS_MAX   4096u         /* a snapshot keeps at most this many POS alphabet entries */
 
 #endif /* CBCG_FORMAT_H */

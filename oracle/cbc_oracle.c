@@ -443,7 +443,7 @@ static uint32_t get_sym(coder *c, uint32_t stream, uint32_t ctx) {
 }
 
 /* compress_int / decompress_int: src/qv_codebook.c:14-95 */
-static void put_int(coder *c, uint32_t v) {
+__attribute__((unused)) static void put_int(coder *c, uint32_t v) {
     for (int k = 0; k < 4; k++) put_sym(c, CBCG_S_CODEBOOK, (uint32_t)k, (v >> (24 - 8 * k)) & 0xffu);
 }
 static uint32_t get_int(coder *c) {

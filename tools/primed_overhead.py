@@ -40,10 +40,9 @@ def split(data):
         nl, = struct.unpack_from("<I", data, o); o += 4 + nl + ((4 - (nl & 3)) & 3)
     ixb, = struct.unpack_from("<I", data, o); return nb, o + 4 + ixb, len(data) - o - 4 - ixb
 
-SCHEDS = [([8, 56, 192, 768], [32, 64, 128, 256]), ([32, 224, 768], [32, 64, 256]), ([16, 112, 896], [32, 64, 256]),
-          ([64, 448, 1536], [16, 64, 256]), ([256, 2048], [32, 128]), ([8, 56, 448, 1024], [32, 64, 128, 256]),
-          ([16, 112, 448, 1024], [16, 32, 128, 256]), ([16, 240, 768], [32, 64, 256]), ([8, 120, 384, 1024], [32, 32, 128, 256])]
-for R in (768,):
+SCHEDS = [([8, 56, 192, 768], [32, 64, 128, 256]), ([8, 56, 384, 1536], [32, 64, 64, 128]), ([8, 56, 192, 1536], [32, 64, 128, 128]),
+          ([16, 112, 384, 1536], [16, 32, 64, 128]), ([8, 56, 192, 2048], [32, 64, 128, 96])]
+for R in (1179,):
     for counts, reads in SCHEDS:
         data, dt = sched(R, counts, reads)
         nb, head, pay = split(data)
