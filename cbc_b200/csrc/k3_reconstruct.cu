@@ -40,6 +40,8 @@ struct K3Smem {
     uint32_t out_off[K3_TILE];        /* byte offset of each read's line inside the tile */
     __align__(16) cbcg_read_rec rec[K3_TILE];
     uint32_t chr[K3_TILE];
+    uint32_t fast[K3_TILE];           /* offset of the read's bases in ref[] when it takes the word-copy path, else ~0 */
+    uint8_t  nsnp[K3_TILE];           /* SNPs to patch on that path */
     K3Warp w[K3_WARPS];
     __align__(16) uint8_t ref[K3_REF_CAP + 16];
     __align__(16) uint8_t out[16];    /* really K3_TILE * (max_len + 1) + 32 (dynamic) */
@@ -110,10 +112,66 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
     /* smem image is shifted so that smem offset == global offset (mod 16): the middle can leave by TMA */
     const uint32_t shift = (uint32_t)((uint64_t)(out + tile_base) & 15ull);
     uint8_t *img = S.out + shift;
+    /* Which reads are plain copies of the window, possibly with a few substituted bases? (perfect matches :383-384
+       and substitution-only reads :442-458: all of config 2.) They take the word-copy path below. */
+    if (tid < nr) {
+        const cbcg_read_rec &rec = S.rec[tid];
+        const uint32_t len = rec.len, pos = rec.pos, chr = S.chr[tid];
+        const uint32_t ns = rec.match ? 0u : rec.n_snps;
+        bool ok = len > 0u && pos >= 1u && chr == chr0 && chr < g.n_chr && ref_bytes != 0u &&
+                  (rec.match || (rec.n_dels == 0u && rec.n_ins == 0u && ns <= 16u));
+        if (ok) ok = (uint64_t)(pos - 1u) + len <= g.chr_len[chr] && (uint64_t)(pos - 1u) >= w0 &&
+                     ((uint64_t)(pos - 1u) - w0 + len + 8u <= ref_bytes);
+        S.fast[tid] = ok ? (uint32_t)((uint64_t)(pos - 1u) - w0) : 0xffffffffu;
+        S.nsnp[tid] = (uint8_t)ns;
+    }
+    __syncthreads();
     mbar_wait(&S.bar, 0);
+
+    /* ---- word-copy path: half a warp per read, one aligned 4-byte word of the tile image per lane and step
+       (unaligned source word = two shared loads and a funnel shift); the line's first and last words, shared with
+       the neighbouring reads, go out byte by byte. */
+    {
+        const uint32_t half = lane >> 4, sub = lane & 15u;
+        for (uint32_t i0 = warp * 2u; i0 < nr; i0 += K3_WARPS * 2u) {
+            const uint32_t i = i0 + half;
+            uint32_t so = 0xffffffffu, len = 0, doff = 0, ns = 0;
+            if (i < nr) { so = S.fast[i]; len = S.rec[i].len; doff = shift + S.out_off[i]; ns = S.nsnp[i]; }
+            if (so != 0xffffffffu) {
+                const uint32_t w_last = (doff + len) >> 2;
+                for (uint32_t w = (doff >> 2) + sub; w <= w_last; w += 16u) {
+                    const int32_t j0 = (int32_t)(4u * w) - (int32_t)doff;          /* read-relative index of the word's first byte */
+                    if (j0 >= 0 && (uint32_t)j0 + 3u <= len) {
+                        uint32_t v = lds_u32_unaligned(S.ref, so + (uint32_t)j0);
+                        if ((uint32_t)j0 + 3u == len) v = (v & 0x00ffffffu) | ((uint32_t)'\n' << 24);
+                        reinterpret_cast<uint32_t *>(S.out)[w] = v;
+                    } else {
+#pragma unroll
+                        for (uint32_t q = 0; q < 4u; q++) {
+                            const int32_t j = j0 + (int32_t)q;
+                            if (j >= 0 && (uint32_t)j <= len) S.out[4u * w + q] = ((uint32_t)j == len) ? (uint8_t)'\n' : S.ref[so + (uint32_t)j];
+                        }
+                    }
+                }
+            } else ns = 0;
+            __syncwarp();
+            if (__any_sync(FULL_MASK, ns != 0u)) {           /* SNP k sits at sum_{i<k}(p_i + 1) + p_k: 16-lane scan per read */
+                uint32_t ed = 0, d = 0;
+                if (sub < ns) { ed = edits[S.rec[i].edit_off + sub]; d = CBCG_EDIT_DELTA(ed) + 1u; }
+                uint32_t sc = d;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL_MASK, sc, o, 16); if (sub >= (uint32_t)o) sc += t; }
+                if (sub < ns) {
+                    if (sc - 1u >= len) dev_set_error(err, CBCG_ERR_CORRUPT, r0 + i);
+                    else S.out[doff + sc - 1u] = (uint8_t)base_char(CBCG_EDIT_TARGET(ed));
+                }
+            }
+        }
+    }
 
     K3Warp &W = S.w[warp];
     for (uint32_t i = warp; i < nr; i += K3_WARPS) {
+        if (S.fast[i] != 0xffffffffu) continue;             /* done above */
         const cbcg_read_rec &rec = S.rec[i];
         const uint32_t len = rec.len, pos = rec.pos, chr = S.chr[i];
         uint8_t *dst = img + S.out_off[i];
