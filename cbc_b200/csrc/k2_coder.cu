@@ -812,267 +812,319 @@ k2_coder_kernel(CoderParams P) {
     const uint16_t *e_in = P.edits;
     const uint8_t *name = P.chr_names;
 
-    while (!C.err && state != ST_DONE) {
-        /* ================================================ 1. what is the next symbol? */
-        uint32_t kind = K_DENSE, card = 0, step = 0, x = 0, key = 0, ctx = 0, pre_lo = 0;
-        uint32_t *m = nullptr;
-        bool is_var = false, pre = false;
-        switch (state) {
-            case ST_HDR: {                               /* 34 ints x 4 bytes, MSB first, through codebook[0..3] (compress_int) */
-                const uint32_t word = k >> 2, byte = k & 3u;
-                const uint32_t v = word == 0u ? P.L : (word == 33u ? CBCG_LOSSLESS : CBCG_WELL_DEBUG);
-                x = (v >> (24u - 8u * byte)) & 0xffu;
-                m = C.codebook + byte * PA_STRIDE; card = 256u; step = 1u; key = CBCG_SYM_KEY(CBCG_S_CODEBOOK, byte);
-                break;
-            }
-            case ST_READ: {                              /* not a symbol: fetch the next read */
-                kind = K_NONE;
-                if (!(legacy && MODE == MODE_DEC) && i >= n_reads) { state = (legacy && MODE != MODE_DEC) ? ST_ENDMARK : ST_DONE; k = 0; break; }
-                if (MODE != MODE_DEC) {
-                    const uint4 v = reinterpret_cast<const uint4 *>(P.recs)[r0 + i];
-                    if (i + 1u < n_reads) {                                            /* next read's record: hide its latency */
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint4 *>(P.recs) + r0 + i + 1u));
-                    }
-                    pos = v.x; flag = v.y & 0xffffu; len = v.y >> 16; match = v.w & 0xffu;
-                    ns = (v.w >> 8) & 0xffu; nd = (v.w >> 16) & 0xffu; ni = v.w >> 24;
-                    e_in = P.edits + v.z;
-                    if (!match) asm volatile("prefetch.global.L1 [%0];" ::"l"(e_in));
-                    if (legacy) {
-                        chr = P.chr[r0 + i];
-                        if (chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; break; }
-                        change = chr != cur_chr; state = ST_SAMEREF;
-                    } else {                                                           /* blocks never span chromosomes: the host cut them */
-                        if (cur_chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; break; }
-                        change = 0; state = lean ? ST_RLEN0 : ST_SAMEREF;
-                    }
-                } else { change = 0; state = (legacy || !lean) ? ST_SAMEREF : ST_RLEN0; }
-                break;
-            }
-            case ST_SAMEREF: m = C.M->same_ref; card = 2u; step = 10u; x = change; key = CBCG_SYM_KEY(CBCG_S_SAME_REF, 0u); break;
-            case ST_RNAME:                               /* name bytes then 0, context = previous byte (never reset) */
-                x = (MODE != MODE_DEC && k < MAX_NAME) ? (uint32_t)name[k] : 0u;
-                m = C.rname + prev_char * PA_STRIDE; card = 256u; step = 10u; key = CBCG_SYM_KEY(CBCG_S_RNAME, prev_char);
-                break;
-            case ST_RLEN0:
-                m = C.M->rlen0; card = 255u; step = 10u; x = len & 0xffu; key = CBCG_SYM_KEY(CBCG_S_RLENGTH, 0u);
-                /* fixed-length input codes the same symbol every read; its cumulative count only moves when a
-                   smaller symbol is coded or the model rescales, so it is remembered instead of re-summed */
-                if (MODE != MODE_LIST && rl_x < 255u) {
-                    if (MODE == MODE_ENC) pre = (x == rl_x);
-                    else { const uint32_t tg = ac_target(C.a, C.t, m[255]); pre = tg >= rl_lo && tg < rl_lo + m[rl_x]; if (pre) x = rl_x; }
-                    pre_lo = rl_lo;
-                }
-                break;
-            case ST_RLENK: kind = K_RLENK; x = 0u; key = CBCG_SYM_KEY(CBCG_S_RLENGTH, k); break;    /* bytes 1..3 are always 0 (:29-33) */
-            case ST_POS:
-                kind = K_POS; key = CBCG_SYM_KEY(CBCG_S_POS_X, 0u);
-                if (MODE != MODE_DEC) {
-                    if (pos == 0u || len == 0u || len > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_INPUT; break; }
-                    if (pos < prev_pos || pos - prev_pos + 1u > CBCG_MAX_POS_X) { C.err = CBCG_ERR_INPUT; break; }
-                    x = pos - prev_pos + 1u;
-                }
-                break;
-            case ST_POSESC:                              /* the escaped value, 4 bytes MSB first (compress_pos_alpha :75-108) */
-                if (k == 0u) C.pa_ensure();
-                m = C.pos_alpha + k * PA_STRIDE; card = 256u; step = 10u; x = (posx >> (24u - 8u * k)) & 0xffu;
-                key = CBCG_SYM_KEY(CBCG_S_POS_ALPHA, k);
-                break;
-            case ST_FLAG: kind = K_FLAG; x = flag; key = CBCG_SYM_KEY(CBCG_S_FLAG, 0u); break;
-            case ST_MATCH: ctx = (samepos << 1) | prev_m; m = C.M->match[ctx]; card = 2u; step = 1u; x = match; key = CBCG_SYM_KEY(CBCG_S_MATCH, ctx); break;
-            case ST_SNPS: m = C.M->snps; card = C.L; step = 10u; x = ((nd | ni) == 0u) ? ns : 0u; key = CBCG_SYM_KEY(CBCG_S_SNPS, 0u); break;
-            case ST_INDELS: m = C.M->indels; card = C.L; step = 16u; x = k == 0u ? ns : (k == 1u ? nd : ni); key = CBCG_SYM_KEY(CBCG_S_INDELS, 0u); break;
-            case ST_DEL:                                 /* :568-572 */
-                if (MODE != MODE_DEC) ed = e_in[k];
-                ctx = (prev << 1) | strand; is_var = true; x = CBCG_EDIT_DELTA(ed);
-                break;
-            case ST_SNPVAR: {                            /* :573-593 */
-                if (MODE != MODE_DEC) ed = e_in[nd + k];
-                const uint32_t delta = C.ring_first(pos - 1u + prev, (prev < len) ? pos - 1u + len : pos - 1u + prev, len + 2u);
-                ctx = (((delta << CBCG_BITS_DELTA) + prev) << 1) | strand; is_var = true; x = CBCG_EDIT_DELTA(ed);
-                break;
-            }
-            case ST_SNPCHAR: m = C.M->chars[refb]; card = 5u; step = 8u; x = CBCG_EDIT_TARGET(ed); key = CBCG_SYM_KEY(CBCG_S_CHARS, refb); break;
-            case ST_INSVAR:                              /* :594-600 */
-                if (MODE != MODE_DEC) ed = e_in[nd + ns + k];
-                ctx = (prev << 1) | strand; is_var = true; x = CBCG_EDIT_DELTA(ed);
-                break;
-            case ST_INSCHAR: m = C.M->chars[CBCG_BP_O]; card = 5u; step = 8u; x = CBCG_EDIT_TARGET(ed); key = CBCG_SYM_KEY(CBCG_S_CHARS, CBCG_BP_O); break;
-            case ST_READ_END:
-                kind = K_NONE;
-                if (MODE == MODE_DEC) {
-                    if (lane == 0) {
-                        uint4 v;
-                        v.x = pos; v.y = flag | (len << 16); v.z = (uint32_t)e_cursor;
-                        v.w = match | (match ? 0u : ((ns << 8) | (nd << 16) | (ni << 24)));
-                        reinterpret_cast<uint4 *>(P.recs)[r0 + i] = v;
-                        P.chr[r0 + i] = cur_chr;
-                    }
-                    e_cursor += ne;
-                }
-                n_done++; i++; state = ST_READ;
-                break;
-            case ST_ENDMARK:                             /* end of stream: name "\n" (src/compression.c:152) */
-                if (k == 0u) { m = C.M->same_ref; card = 2u; step = 10u; x = 1u; key = CBCG_SYM_KEY(CBCG_S_SAME_REF, 0u); }
-                else { x = k == 1u ? (uint32_t)'\n' : 0u; m = C.rname + prev_char * PA_STRIDE; card = 256u; step = 10u; key = CBCG_SYM_KEY(CBCG_S_RNAME, prev_char); }
-                break;
-            default: C.err = CBCG_ERR_INTERNAL; break;
-        }
-        if (C.err) break;
-        if (kind == K_NONE) continue;
-        if (is_var) {
-            key = CBCG_SYM_KEY(CBCG_S_VAR, ctx);
-            card = C.L; step = 10u;
-            if (MODE != MODE_LIST) { m = C.var_row(ctx); if (!m) break; }
-        }
+    /* The machine is threaded with gotos: every state has a set-up block S_x (describe its symbol, then CODE) and a
+       post block P_x (consume the value, jump straight to the next state's set-up). One dispatch per symbol --
+       CODE's switch on `state` -- instead of a loop with a set-up switch and a post switch. */
+    uint32_t kind, card, step, x, key, ctx, pre_lo, y, slot;
+    uint32_t *m;
+    bool is_var, pre;
+#define SYMBOL(KIND, M, CARD, STEP, X, KEY) do { kind = (KIND); m = (M); card = (CARD); step = (STEP); x = (X); key = (KEY); is_var = false; pre = false; pre_lo = 0; } while (0)
+#define VAR_SYMBOL(CTX, X) do { kind = K_DENSE; m = nullptr; ctx = (CTX); card = C.L; step = 10u; x = (X); key = CBCG_SYM_KEY(CBCG_S_VAR, ctx); is_var = true; pre = false; pre_lo = 0; } while (0)
+    kind = K_NONE; card = step = x = key = ctx = pre_lo = y = 0; slot = 1u; m = nullptr; is_var = pre = false;
+    if (C.err) goto M_DONE;
+    if (legacy) goto S_HDR;
+    goto S_READ;
 
-        /* ================================================ 2. code it: one call site per model kind */
-        uint32_t y = x, slot = 1u;
-        if (MODE == MODE_LIST) C.list_put(key >> 24, key & 0xffffffu, x);
-        else if (kind == K_DENSE) y = C.sym_dense(m, card, step, x, pre, pre_lo);
-        else if (kind == K_FLAG) y = C.sym_flag(x);
-        else if (kind == K_POS) y = C.sym_pos_main(x, slot);
-        else y = C.sym_rlenk(k - 1u, x);
-        if (C.err) break;
-
-        /* ================================================ 3. consume the value, pick the next state */
-        switch (state) {
-            case ST_HDR:
-                if (MODE == MODE_DEC) {
-                    const uint32_t word = k >> 2, byte = k & 3u;
-                    if (word == 0u) hdr_L |= y << (24u - 8u * byte);
-                    else if (y != (((word == 33u ? CBCG_LOSSLESS : 0u) >> (24u - 8u * byte)) & 0xffu) && word == 33u) C.err = CBCG_ERR_FORMAT;
-                }
-                if (++k == 136u) {
-                    if (MODE == MODE_DEC) {
-                        if (hdr_L == 0u || hdr_L > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_FORMAT; break; }
-                        C.L = hdr_L; decode_L = hdr_L;
-                    }
-                    if (MODE != MODE_LIST) C.init_L_models();         /* alloc_read_models_t runs after the header int (:371-375) */
-                    state = ST_READ;
-                }
-                break;
-            case ST_SAMEREF:
-                if (MODE == MODE_DEC) {
-                    if (!legacy) { if (y != 0u) { C.err = CBCG_ERR_CORRUPT; break; } }
-                    else change = y;
-                }
-                if (change) { state = ST_RNAME; k = 0; if (MODE != MODE_DEC) name = P.chr_names + (uint64_t)chr * MAX_NAME; break; }
-                if (legacy && MODE == MODE_DEC) {
-                    if (cur_chr == 0xffffffffu) { C.err = CBCG_ERR_CORRUPT; break; }
-                    if (i >= n_reads) { C.err = CBCG_ERR_CAPACITY; break; }
-                }
-                state = ST_RLEN0;
-                break;
-            case ST_RNAME: {
-                bool name_done = false;
-                if (MODE == MODE_DEC) {
-                    if (y == (uint32_t)'\n') { state = ST_DONE; break; }               /* end marker (decompress_rname :82-84) */
-                    if (y == 0u) { name_done = true; chr = cur_chr + 1u; }              /* records are taken in FASTA order */
-                    else prev_char = y;
-                } else { if (x == 0u) name_done = true; else { prev_char = x; k++; } }
-                if (name_done) {
-                    if (chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; break; }
-                    if (MODE == MODE_DEC && i >= n_reads) { C.err = CBCG_ERR_CAPACITY; break; }
-                    cur_chr = chr; prev_pos = 0u; C.ring_reset();                      /* src/compression.c:58-64 */
-                    ref = P.genome.bases + P.genome.chr_off[chr]; ref_len = P.genome.chr_len[chr];
-                    state = ST_RLEN0;
-                }
-                break;
-            }
-            case ST_RLEN0:
-                if (MODE == MODE_DEC) len = y;
-                if (MODE != MODE_LIST) { rl_x = (C.last_n + 10u >= CBCG_RESCALE) ? 0xffffffffu : y; rl_lo = C.last_lo; }
-                if (lean) state = ST_POS; else { state = ST_RLENK; k = 1; }
-                break;
-            case ST_RLENK:
-                if (MODE == MODE_DEC) len |= y << (8u * k);
-                if (++k == 4u) state = ST_POS;
-                break;
-            case ST_POS:
-                if (MODE == MODE_DEC) x = y;
-                if (MODE != MODE_LIST && slot == 0u) { posx = x; acc = 0; k = 0; state = ST_POSESC; break; }
-                posx = x; goto pos_done;
-            case ST_POSESC:
-                acc |= y << (24u - 8u * k);
-                if (++k < 4u) break;
-                if (MODE == MODE_DEC) posx = acc;
-                C.pos_append(posx);
-                if (C.err) break;
-            pos_done:
-                if (MODE == MODE_DEC) {
-                    if (posx == 0u) { C.err = CBCG_ERR_CORRUPT; break; }
-                    pos = prev_pos + posx - 1u;
-                    if (pos == 0u || len == 0u || len > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_CORRUPT; break; }
-                }
-                samepos = posx == 1u;
-                prev_pos = pos;
-                C.ring_advance(pos);
-                state = ST_FLAG;
-                break;
-            case ST_FLAG: flag = y; strand = (flag >> 4) & 1u; state = ST_MATCH; break;       /* :57-60 */
-            case ST_MATCH:
-                match = y; prev_m = y; ne = 0;
-                if (MODE == MODE_DEC) { ns = nd = ni = 0; }
-                state = match ? ST_READ_END : ST_SNPS;
-                break;
-            case ST_SNPS:
-                if (MODE == MODE_DEC) { ns = y; nd = ni = 0; if (y == 0u) { state = ST_INDELS; k = 0; break; } }
-                else if ((nd | ni) != 0u) { state = ST_INDELS; k = 0; break; }
-                goto counts_done;
-            case ST_INDELS:
-                if (MODE == MODE_DEC) { if (k == 0u) ns = y; else if (k == 1u) nd = y; else ni = y; }
-                if (++k < 3u) break;
-            counts_done:
-                if (MODE == MODE_DEC) {
-                    if (ni > len || ns > 255u || nd > 255u || ni > 255u) { C.err = CBCG_ERR_CORRUPT; break; }
-                    if ((uint64_t)(ns + nd + ni) > edits_cap_abs - e_cursor) { C.err = CBCG_ERR_CAPACITY; break; }
-                }
-                prev = 0; k = 0; ne = 0;
-                state = nd ? ST_DEL : (ns ? ST_SNPVAR : (ni ? ST_INSVAR : ST_READ_END));
-                break;
-            case ST_DEL:
-                prev += y;
-                if (MODE == MODE_DEC && lane == 0) { P.edits[e_cursor + ne] = CBCG_EDIT(y, 0, 0); C.M->cumdel[k] = (uint16_t)min(prev, 0xffffu); }
-                ne++;
-                if (++k == nd) {
-                    if (MODE == MODE_DEC) SYNCW();
-                    prev = 0; k = 0;
-                    state = ns ? ST_SNPVAR : (ni ? ST_INSVAR : ST_READ_END);
-                }
-                break;
-            case ST_SNPVAR: {
-                edp = y;
-                const uint32_t idx = prev + y;                                         /* index in the insertion-free read */
-                prev += y + 1u;
-                C.ring_set(pos + prev - 2u);                                           /* :589 */
-                if (MODE == MODE_DEC) {
-                    uint32_t skipped = 0;                                              /* deletions at or before idx (:426-437) */
-                    for (uint32_t q = lane; q < nd; q += 32u) skipped += (C.M->cumdel[q] <= idx);
-                    skipped = warp_sum(skipped);
-                    const uint64_t ri = (uint64_t)pos - 1u + idx + skipped;
-                    refb = base_code(ri < ref_len ? (uint32_t)ref[ri] : 0u);
-                } else refb = CBCG_EDIT_REFB(ed);
-                state = ST_SNPCHAR;
-                break;
-            }
-            case ST_SNPCHAR:
-                if (MODE == MODE_DEC && lane == 0) P.edits[e_cursor + ne] = CBCG_EDIT(edp, y, refb);
-                ne++;
-                if (++k == ns) { prev = 0; k = 0; state = ni ? ST_INSVAR : ST_READ_END; } else state = ST_SNPVAR;
-                break;
-            case ST_INSVAR: edp = y; prev += y; state = ST_INSCHAR; break;
-            case ST_INSCHAR:
-                if (MODE == MODE_DEC && lane == 0) P.edits[e_cursor + ne] = CBCG_EDIT(edp, y, CBCG_BP_O);
-                ne++;
-                state = (++k == ni) ? ST_READ_END : ST_INSVAR;
-                break;
-            case ST_ENDMARK:
-                if (k == 1u) prev_char = '\n';
-                if (++k == 3u) state = ST_DONE;
-                break;
-            default: C.err = CBCG_ERR_INTERNAL; break;
-        }
+    /* ================================================ code the described symbol: one call site per model kind */
+CODE:
+    if (is_var && MODE != MODE_LIST) { m = C.var_row(ctx); if (!m) goto M_DONE; }
+    y = x; slot = 1u;
+    if (MODE == MODE_LIST) C.list_put(key >> 24, key & 0xffffffu, x);
+    else if (kind == K_DENSE) y = C.sym_dense(m, card, step, x, pre, pre_lo);
+    else if (kind == K_FLAG) y = C.sym_flag(x);
+    else if (kind == K_POS) y = C.sym_pos_main(x, slot);
+    else y = C.sym_rlenk(k - 1u, x);
+    if (C.err) goto M_DONE;
+    switch (state) {
+        case ST_HDR: goto P_HDR;       case ST_SAMEREF: goto P_SAMEREF; case ST_RNAME: goto P_RNAME;   case ST_RLEN0: goto P_RLEN0;
+        case ST_RLENK: goto P_RLENK;   case ST_POS: goto P_POS;         case ST_POSESC: goto P_POSESC; case ST_FLAG: goto P_FLAG;
+        case ST_MATCH: goto P_MATCH;   case ST_SNPS: goto P_SNPS;       case ST_INDELS: goto P_INDELS; case ST_DEL: goto P_DEL;
+        case ST_SNPVAR: goto P_SNPVAR; case ST_SNPCHAR: goto P_SNPCHAR; case ST_INSVAR: goto P_INSVAR; case ST_INSCHAR: goto P_INSCHAR;
+        case ST_ENDMARK: goto P_ENDMARK;
+        default: C.err = CBCG_ERR_INTERNAL; goto M_DONE;
     }
+
+    /* ---- stream header: 34 ints x 4 bytes, MSB first, through codebook[0..3] (compress_int) */
+S_HDR: {
+        const uint32_t word = k >> 2, byte = k & 3u;
+        const uint32_t v = word == 0u ? P.L : (word == 33u ? CBCG_LOSSLESS : CBCG_WELL_DEBUG);
+        state = ST_HDR;
+        SYMBOL(K_DENSE, C.codebook + byte * PA_STRIDE, 256u, 1u, (v >> (24u - 8u * byte)) & 0xffu, CBCG_SYM_KEY(CBCG_S_CODEBOOK, byte));
+        goto CODE;
+    }
+P_HDR:
+    if (MODE == MODE_DEC) {
+        const uint32_t word = k >> 2, byte = k & 3u;
+        if (word == 0u) hdr_L |= y << (24u - 8u * byte);
+        else if (word == 33u && y != ((CBCG_LOSSLESS >> (24u - 8u * byte)) & 0xffu)) { C.err = CBCG_ERR_FORMAT; goto M_DONE; }
+    }
+    if (++k < 136u) goto S_HDR;
+    if (MODE == MODE_DEC) {
+        if (hdr_L == 0u || hdr_L > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_FORMAT; goto M_DONE; }
+        C.L = hdr_L; decode_L = hdr_L;
+    }
+    if (MODE != MODE_LIST) C.init_L_models();                 /* alloc_read_models_t runs after the header int (:371-375) */
+    goto S_READ;
+
+    /* ---- next read (not a symbol) */
+S_READ:
+    if (!(legacy && MODE == MODE_DEC) && i >= n_reads) {
+        if (legacy && MODE != MODE_DEC) { k = 0; goto S_ENDMARK; }
+        goto M_DONE;
+    }
+    if (MODE != MODE_DEC) {
+        const uint4 v = reinterpret_cast<const uint4 *>(P.recs)[r0 + i];
+        if (i + 1u < n_reads) {                                            /* next read's record: hide its latency */
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint4 *>(P.recs) + r0 + i + 1u));
+        }
+        pos = v.x; flag = v.y & 0xffffu; len = v.y >> 16; match = v.w & 0xffu;
+        ns = (v.w >> 8) & 0xffu; nd = (v.w >> 16) & 0xffu; ni = v.w >> 24;
+        e_in = P.edits + v.z;
+        if (!match) asm volatile("prefetch.global.L1 [%0];" ::"l"(e_in));
+        if (legacy) {
+            chr = P.chr[r0 + i];
+            if (chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; goto M_DONE; }
+            change = chr != cur_chr;
+            goto S_SAMEREF;
+        }
+        if (cur_chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; goto M_DONE; }   /* blocks never span chromosomes: the host cut them */
+        change = 0;
+        if (lean) goto S_RLEN0;
+        goto S_SAMEREF;
+    }
+    change = 0;
+    if (legacy || !lean) goto S_SAMEREF;
+    goto S_RLEN0;
+
+    /* ---- compress_rname / decompress_rname (src/id_compression.c:39-94) */
+S_SAMEREF:
+    state = ST_SAMEREF;
+    SYMBOL(K_DENSE, C.M->same_ref, 2u, 10u, change, CBCG_SYM_KEY(CBCG_S_SAME_REF, 0u));
+    goto CODE;
+P_SAMEREF:
+    if (MODE == MODE_DEC) {
+        if (!legacy) { if (y != 0u) { C.err = CBCG_ERR_CORRUPT; goto M_DONE; } }
+        else change = y;
+    }
+    if (change) { k = 0; if (MODE != MODE_DEC) name = P.chr_names + (uint64_t)chr * MAX_NAME; goto S_RNAME; }
+    if (legacy && MODE == MODE_DEC) {
+        if (cur_chr == 0xffffffffu) { C.err = CBCG_ERR_CORRUPT; goto M_DONE; }
+        if (i >= n_reads) { C.err = CBCG_ERR_CAPACITY; goto M_DONE; }
+    }
+    goto S_RLEN0;
+S_RNAME:                                                      /* name bytes then 0, context = previous byte (never reset) */
+    state = ST_RNAME;
+    SYMBOL(K_DENSE, C.rname + prev_char * PA_STRIDE, 256u, 10u, (MODE != MODE_DEC && k < MAX_NAME) ? (uint32_t)name[k] : 0u,
+           CBCG_SYM_KEY(CBCG_S_RNAME, prev_char));
+    goto CODE;
+P_RNAME: {
+        bool name_done = false;
+        if (MODE == MODE_DEC) {
+            if (y == (uint32_t)'\n') goto M_DONE;                           /* end marker (decompress_rname :82-84) */
+            if (y == 0u) { name_done = true; chr = cur_chr + 1u; }           /* records are taken in FASTA order */
+            else prev_char = y;
+        } else { if (x == 0u) name_done = true; else { prev_char = x; k++; } }
+        if (!name_done) goto S_RNAME;
+        if (chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; goto M_DONE; }
+        if (MODE == MODE_DEC && i >= n_reads) { C.err = CBCG_ERR_CAPACITY; goto M_DONE; }
+        cur_chr = chr; prev_pos = 0u; C.ring_reset();                       /* src/compression.c:58-64 */
+        ref = P.genome.bases + P.genome.chr_off[chr]; ref_len = P.genome.chr_len[chr];
+        goto S_RLEN0;
+    }
+
+    /* ---- length: byte 0 carries it, bytes 1..3 are always 0 (src/read_compression.c:29-33) */
+S_RLEN0:
+    state = ST_RLEN0;
+    SYMBOL(K_DENSE, C.M->rlen0, 255u, 10u, len & 0xffu, CBCG_SYM_KEY(CBCG_S_RLENGTH, 0u));
+    /* fixed-length input codes the same symbol every read; its cumulative count only moves when a smaller symbol is
+       coded or the model rescales, so it is remembered instead of re-summed */
+    if (MODE != MODE_LIST && rl_x < 255u) {
+        if (MODE == MODE_ENC) pre = (x == rl_x);
+        else { const uint32_t tg = ac_target(C.a, C.t, m[255]); pre = tg >= rl_lo && tg < rl_lo + m[rl_x]; if (pre) x = rl_x; }
+        pre_lo = rl_lo;
+    }
+    goto CODE;
+P_RLEN0:
+    if (MODE == MODE_DEC) len = y;
+    if (MODE != MODE_LIST) { rl_x = (C.last_n + 10u >= CBCG_RESCALE) ? 0xffffffffu : y; rl_lo = C.last_lo; }
+    if (lean) goto S_POS;
+    k = 1;
+S_RLENK:
+    state = ST_RLENK;
+    SYMBOL(K_RLENK, nullptr, 0u, 0u, 0u, CBCG_SYM_KEY(CBCG_S_RLENGTH, k));
+    goto CODE;
+P_RLENK:
+    if (MODE == MODE_DEC) len |= y << (8u * k);
+    if (++k < 4u) goto S_RLENK;
+
+    /* ---- position (src/read_compression.c:113-159): x = pos - prevPos + 1 through the growing alphabet */
+S_POS:
+    state = ST_POS;
+    SYMBOL(K_POS, nullptr, 0u, 0u, 0u, CBCG_SYM_KEY(CBCG_S_POS_X, 0u));
+    if (MODE != MODE_DEC) {
+        if (pos == 0u || len == 0u || len > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_INPUT; goto M_DONE; }
+        if (pos < prev_pos || pos - prev_pos + 1u > CBCG_MAX_POS_X) { C.err = CBCG_ERR_INPUT; goto M_DONE; }
+        x = pos - prev_pos + 1u;
+    }
+    goto CODE;
+P_POS:
+    posx = (MODE == MODE_DEC) ? y : x;
+    if (MODE == MODE_LIST || slot != 0u) goto M_POS_DONE;
+    acc = 0; k = 0;
+S_POSESC:                                                     /* the escaped value, 4 bytes MSB first (compress_pos_alpha :75-108) */
+    state = ST_POSESC;
+    if (k == 0u) C.pa_ensure();
+    SYMBOL(K_DENSE, C.pos_alpha + k * PA_STRIDE, 256u, 10u, (posx >> (24u - 8u * k)) & 0xffu, CBCG_SYM_KEY(CBCG_S_POS_ALPHA, k));
+    goto CODE;
+P_POSESC:
+    acc |= y << (24u - 8u * k);
+    if (++k < 4u) goto S_POSESC;
+    if (MODE == MODE_DEC) posx = acc;
+    C.pos_append(posx);
+    if (C.err) goto M_DONE;
+M_POS_DONE:
+    if (MODE == MODE_DEC) {
+        if (posx == 0u) { C.err = CBCG_ERR_CORRUPT; goto M_DONE; }
+        pos = prev_pos + posx - 1u;
+        if (pos == 0u || len == 0u || len > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_CORRUPT; goto M_DONE; }
+    }
+    samepos = posx == 1u;
+    prev_pos = pos;
+    C.ring_advance(pos);
+
+    /* ---- flag, match */
+    state = ST_FLAG;
+    SYMBOL(K_FLAG, nullptr, 0u, 0u, flag, CBCG_SYM_KEY(CBCG_S_FLAG, 0u));
+    goto CODE;
+P_FLAG:
+    flag = y; strand = (flag >> 4) & 1u;                                   /* :57-60 */
+    state = ST_MATCH;
+    ctx = (samepos << 1) | prev_m;
+    SYMBOL(K_DENSE, C.M->match[ctx], 2u, 1u, match, CBCG_SYM_KEY(CBCG_S_MATCH, ctx));
+    goto CODE;
+P_MATCH:
+    match = y; prev_m = y; ne = 0;
+    if (MODE == MODE_DEC) { ns = nd = ni = 0; }
+    if (match) goto M_READ_END;
+
+    /* ---- counts (:557-565) */
+    state = ST_SNPS;
+    SYMBOL(K_DENSE, C.M->snps, C.L, 10u, ((nd | ni) == 0u) ? ns : 0u, CBCG_SYM_KEY(CBCG_S_SNPS, 0u));
+    goto CODE;
+P_SNPS:
+    if (MODE == MODE_DEC) { ns = y; nd = ni = 0; if (y != 0u) goto M_COUNTS_DONE; }
+    else if ((nd | ni) == 0u) goto M_COUNTS_DONE;
+    k = 0;
+S_INDELS:
+    state = ST_INDELS;
+    SYMBOL(K_DENSE, C.M->indels, C.L, 16u, k == 0u ? ns : (k == 1u ? nd : ni), CBCG_SYM_KEY(CBCG_S_INDELS, 0u));
+    goto CODE;
+P_INDELS:
+    if (MODE == MODE_DEC) { if (k == 0u) ns = y; else if (k == 1u) nd = y; else ni = y; }
+    if (++k < 3u) goto S_INDELS;
+M_COUNTS_DONE:
+    if (MODE == MODE_DEC) {
+        if (ni > len || ns > 255u || nd > 255u || ni > 255u) { C.err = CBCG_ERR_CORRUPT; goto M_DONE; }
+        if ((uint64_t)(ns + nd + ni) > edits_cap_abs - e_cursor) { C.err = CBCG_ERR_CAPACITY; goto M_DONE; }
+    }
+    prev = 0; k = 0; ne = 0;
+    if (nd) goto S_DEL;
+    if (ns) goto S_SNPVAR;
+    if (ni) goto S_INSVAR;
+    goto M_READ_END;
+
+    /* ---- deletions (:568-572) */
+S_DEL:
+    state = ST_DEL;
+    if (MODE != MODE_DEC) ed = e_in[k];
+    VAR_SYMBOL((prev << 1) | strand, CBCG_EDIT_DELTA(ed));
+    goto CODE;
+P_DEL:
+    prev += y;
+    if (MODE == MODE_DEC && lane == 0) { P.edits[e_cursor + ne] = CBCG_EDIT(y, 0, 0); C.M->cumdel[k] = (uint16_t)min(prev, 0xffffu); }
+    ne++;
+    if (++k < nd) goto S_DEL;
+    if (MODE == MODE_DEC) SYNCW();
+    prev = 0; k = 0;
+    if (ns) goto S_SNPVAR;
+    if (ni) goto S_INSVAR;
+    goto M_READ_END;
+
+    /* ---- SNPs (:573-593) */
+S_SNPVAR: {
+        state = ST_SNPVAR;
+        if (MODE != MODE_DEC) ed = e_in[nd + k];
+        const uint32_t delta = C.ring_first(pos - 1u + prev, (prev < len) ? pos - 1u + len : pos - 1u + prev, len + 2u);
+        VAR_SYMBOL((((delta << CBCG_BITS_DELTA) + prev) << 1) | strand, CBCG_EDIT_DELTA(ed));
+        goto CODE;
+    }
+P_SNPVAR: {
+        edp = y;
+        const uint32_t idx = prev + y;                                         /* index in the insertion-free read */
+        prev += y + 1u;
+        C.ring_set(pos + prev - 2u);                                           /* :589 */
+        if (MODE == MODE_DEC) {
+            uint32_t skipped = 0;                                              /* deletions at or before idx (:426-437) */
+            for (uint32_t q = lane; q < nd; q += 32u) skipped += (C.M->cumdel[q] <= idx);
+            skipped = warp_sum(skipped);
+            const uint64_t ri = (uint64_t)pos - 1u + idx + skipped;
+            refb = base_code(ri < ref_len ? (uint32_t)ref[ri] : 0u);
+        } else refb = CBCG_EDIT_REFB(ed);
+        state = ST_SNPCHAR;
+        SYMBOL(K_DENSE, C.M->chars[refb], 5u, 8u, CBCG_EDIT_TARGET(ed), CBCG_SYM_KEY(CBCG_S_CHARS, refb));
+        goto CODE;
+    }
+P_SNPCHAR:
+    if (MODE == MODE_DEC && lane == 0) P.edits[e_cursor + ne] = CBCG_EDIT(edp, y, refb);
+    ne++;
+    if (++k < ns) goto S_SNPVAR;
+    prev = 0; k = 0;
+    if (ni) goto S_INSVAR;
+    goto M_READ_END;
+
+    /* ---- insertions (:594-600) */
+S_INSVAR:
+    state = ST_INSVAR;
+    if (MODE != MODE_DEC) ed = e_in[nd + ns + k];
+    VAR_SYMBOL((prev << 1) | strand, CBCG_EDIT_DELTA(ed));
+    goto CODE;
+P_INSVAR:
+    edp = y; prev += y;
+    state = ST_INSCHAR;
+    SYMBOL(K_DENSE, C.M->chars[CBCG_BP_O], 5u, 8u, CBCG_EDIT_TARGET(ed), CBCG_SYM_KEY(CBCG_S_CHARS, CBCG_BP_O));
+    goto CODE;
+P_INSCHAR:
+    if (MODE == MODE_DEC && lane == 0) P.edits[e_cursor + ne] = CBCG_EDIT(edp, y, CBCG_BP_O);
+    ne++;
+    if (++k < ni) goto S_INSVAR;
+
+M_READ_END:
+    if (MODE == MODE_DEC) {
+        if (lane == 0) {
+            uint4 v;
+            v.x = pos; v.y = flag | (len << 16); v.z = (uint32_t)e_cursor;
+            v.w = match | (match ? 0u : ((ns << 8) | (nd << 16) | (ni << 24)));
+            reinterpret_cast<uint4 *>(P.recs)[r0 + i] = v;
+            P.chr[r0 + i] = cur_chr;
+        }
+        e_cursor += ne;
+    }
+    n_done++; i++;
+    goto S_READ;
+
+    /* ---- end of stream: name "\n" (src/compression.c:152) */
+S_ENDMARK:
+    state = ST_ENDMARK;
+    if (k == 0u) SYMBOL(K_DENSE, C.M->same_ref, 2u, 10u, 1u, CBCG_SYM_KEY(CBCG_S_SAME_REF, 0u));
+    else SYMBOL(K_DENSE, C.rname + prev_char * PA_STRIDE, 256u, 10u, k == 1u ? (uint32_t)'\n' : 0u, CBCG_SYM_KEY(CBCG_S_RNAME, prev_char));
+    goto CODE;
+P_ENDMARK:
+    if (k == 1u) prev_char = '\n';
+    if (++k < 3u) goto S_ENDMARK;
+
+M_DONE:
+#undef SYMBOL
+#undef VAR_SYMBOL
 
     if (MODE == MODE_ENC && !C.err) { if (P.short_flush && !legacy) C.ac_flush_short(); else C.ac_flush(); }
     if (C.err) dev_set_error(P.err, C.err, ((uint64_t)b << 20) | (n_done & 0xfffffu));
