@@ -278,33 +278,58 @@ def run_b200_arm(args):
     container_bytes = se["container_bytes"]
     n_edits = se["n_edits"]
 
-    # ---------------- end-to-end step through the host-buffer C ABI (e2e)
-    out_c = pinned_empty(int(container_bytes * 1.25) + 4096, np.uint8)
-    out_t = pinned_empty(bases + n + 64, np.uint8)
+    # ---------------- end-to-end step through the host-buffer C ABI (e2e): pinned host buffers in, pinned host buffers
+    # out, every copy inside the timed region. The batch goes through `--inflight` contexts (one host thread and one
+    # CUDA stream each, the ABI's threading model): sub-batch k+1 is on the PCIe link while sub-batch k is being coded,
+    # which is how a streaming caller keeps both busy. Each sub-batch is a self-contained container (a shard).
+    from concurrent.futures import ThreadPoolExecutor
+    K = max(1, args.inflight)
+    cuts = shard.shard_ranges(n, K)
+    codecs = [codec] + [Codec(local) for _ in range(K - 1)]
+    for c2 in codecs[1:]:
+        c2.set_reference(g)
+    subs = [pin_batch(b.slice(r0_, r1_)) if K > 1 else pb for r0_, r1_ in cuts]
+    outs_c = [pinned_empty(int(container_bytes * 1.5 / K) + 65536, np.uint8) for _ in range(K)]
+    outs_t = [pinned_empty(sb_.total_bases() + sb_.n_reads + 64, np.uint8) for sb_ in subs]
+
+    def e2e_one(k):
+        c2 = codecs[k]
+        nc = c2.compress_into(subs[k], L, R, outs_c[k], G)
+        s1 = c2.stats()
+        head, payload = c2.fetch_index()
+        nt, nr = c2.decompress_into(outs_c[k][:nc], outs_t[k])
+        s2 = c2.stats()
+        return nc, nt, s1, s2, head, payload
+
+    pool = ThreadPoolExecutor(K)
 
     def e2e_step():
-        nc = codec.compress_into(pb, L, R, out_c, G)
-        s1 = codec.stats()
-        if dist is not None:
-            head, payload = codec.fetch_index()
-            shard.gather_index(head, payload, dist, dev)
-        nt, nr = codec.decompress_into(out_c[:nc], out_t)
-        s2 = codec.stats()
-        return nc, nt, s1, s2
+        res = list(pool.map(e2e_one, range(K)))
+        if dist is not None:                                  # container index across ranks (first sub-batch's table stands for the shard)
+            shard.gather_index(res[0][4], sum(r_[5] for r_ in res), dist, dev)
+        return res
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        nc, nt, s1, s2 = e2e_step()
+        res = e2e_step()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    if out_t[:nt].tobytes() != b.seq_lines():
+    text_all = b"".join(outs_t[k][:res[k][1]].tobytes() for k in range(K))
+    if text_all != b.seq_lines():
         raise RuntimeError("e2e round trip mismatch")
+    e2e_container = sum(r_[0] for r_ in res)
     e2e = {"value": total_reads / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(s1["h2d_bytes"] + s2["h2d_bytes"]),
-           "d2h_bytes_per_step": int(s1["d2h_bytes"] + s2["d2h_bytes"])}
+           "h2d_bytes_per_step": int(sum(r_[2]["h2d_bytes"] + r_[3]["h2d_bytes"] for r_ in res)),
+           "d2h_bytes_per_step": int(sum(r_[2]["d2h_bytes"] + r_[3]["d2h_bytes"] for r_ in res)),
+           "contexts_in_flight": K, "container_bytes": int(e2e_container),
+           "bits_per_base": 8.0 * e2e_container / bases}
+    s1 = {"h2d_bytes": sum(r_[2]["h2d_bytes"] for r_ in res)}
+    pool.shutdown()
+    for c2 in codecs[1:]:
+        c2.close()
 
     # ---------------- roofline (SURVEY.md 8d figures, DESIGN.md "Measurement")
     peak, peak_src = peaks()
@@ -401,6 +426,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block-reads", type=int, default=0xffffffff, help="reads per block; default: sized to whole waves (CBCG_BLOCK_AUTO)")
+    ap.add_argument("--inflight", type=int, default=1, help="contexts (host threads / streams) the e2e leg keeps in flight")
     ap.add_argument("--gen-mode", type=int, default=1, help="1: generation-primed blocks (default), 0: cold blocks")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; the bench line needs 1.0)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
