@@ -29,15 +29,6 @@ AC_HD uint32_t ac_clz32(uint32_t x) {
 #endif
 }
 
-/* floor(p / n) for p < 2^46, 0 < n < 2^26 (both exact in a double; round-down division keeps the floor). */
-AC_HD uint64_t ac_div(uint64_t p, uint32_t n) {
-#ifdef __CUDA_ARCH__
-    return (uint64_t)__double2ull_rz(__ddiv_rd(__ull2double_rz(p), (double)n));
-#else
-    return p / n;
-#endif
-}
-
 /* Exact floor((a * b - sub) / d) for a, b, d < 2^27 whose quotient is < 2^27 (every division of this coder:
  * range <= 2^26, counts and totals < 2^21). The product is exact in a double (< 2^54 ... here < 2^48), the
  * reciprocal comes from rcp.approx (relative error <= 2^-23) plus one Newton step (<= 2^-45), so the estimate

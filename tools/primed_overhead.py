@@ -40,8 +40,8 @@ def split(data):
         nl, = struct.unpack_from("<I", data, o); o += 4 + nl + ((4 - (nl & 3)) & 3)
     ixb, = struct.unpack_from("<I", data, o); return nb, o + 4 + ixb, len(data) - o - 4 - ixb
 
-SCHEDS = [([8, 56, 192, 768], [32, 64, 128, 256]), ([8, 56, 384, 1536], [32, 64, 64, 128]), ([8, 56, 192, 1536], [32, 64, 128, 128]),
-          ([16, 112, 384, 1536], [16, 32, 64, 128]), ([8, 56, 192, 2048], [32, 64, 128, 96])]
+SCHEDS = [([16, 112, 384, 1536], [16, 32, 64, 128]), ([128, 384, 1536], [16, 64, 128]), ([64, 448, 1536], [16, 48, 128]),
+          ([256, 768, 1536], [8, 32, 128]), ([32, 224, 1536], [16, 64, 128])]
 for R in (1179,):
     for counts, reads in SCHEDS:
         data, dt = sched(R, counts, reads)
