@@ -36,7 +36,9 @@
 #include "internal.h"
 #include "ac_core.h"
 
+#ifndef K2_WARPS
 #define K2_WARPS    4u
+#endif
 #ifndef K2_MIN_CTAS
 #define K2_MIN_CTAS 4          /* resident CTAs per SM the register allocation is held to */
 #endif
