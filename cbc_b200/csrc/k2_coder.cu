@@ -267,11 +267,10 @@ struct Coder {
         if (k == 0) return 0u;
         if (dcnt < k) {
             uint32_t w = 0;
-#pragma unroll
-            for (uint32_t i = 0; i < 4; i++) {
-                const uint32_t p = in_pos + i;
-                const uint32_t v = (p < in_len) ? (uint32_t)in[p] : 0u;
-                w = (w << 8) | v;
+            if (in_pos + 4u <= in_len) {
+                w = ((uint32_t)in[in_pos] << 24) | ((uint32_t)in[in_pos + 1u] << 16) | ((uint32_t)in[in_pos + 2u] << 8) | (uint32_t)in[in_pos + 3u];
+            } else if (in_pos < in_len) {                     /* the block's last 1..3 bytes, zeros behind them */
+                for (uint32_t i = 0; i < 4u; i++) { w <<= 8; if (in_pos + i < in_len) w |= (uint32_t)in[in_pos + i]; }
             }
             in_pos += 4u;
             dbuf |= (uint64_t)w << (32u - dcnt);
@@ -751,8 +750,13 @@ enum : uint32_t { ST_HDR, ST_READ, ST_SAMEREF, ST_RNAME, ST_RLEN0, ST_RLENK, ST_
                   ST_INDELS, ST_DEL, ST_SNPVAR, ST_SNPCHAR, ST_INSVAR, ST_INSCHAR, ST_READ_END, ST_ENDMARK, ST_DONE };
 enum : uint32_t { K_NONE, K_DENSE, K_RLENK, K_FLAG, K_POS };
 
+#ifdef K2_MAXNREG
+#define K2_KERNEL_BOUNDS __maxnreg__(K2_MAXNREG)
+#else
+#define K2_KERNEL_BOUNDS __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
+__global__ void K2_KERNEL_BOUNDS
 k2_coder_kernel(CoderParams P) {
     __shared__ __align__(16) WarpModels smodels[K2_WARPS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;

@@ -9,7 +9,7 @@ cfg = synth.SynthConfig.named("config2", scale=0.3); g = synth.make_genome(cfg);
 c = Codec(0); c.set_reference(g)
 orecs, oedits = O.extract(b, g)
 off = orecs["edit_off"].astype(np.int64)
-for R in (64,):
+for R in (64, 1000):
     cont = c.compress(b, 150, R, 0)
     assert cont == O.encode_blocked(b, g, 150, R, 0)
     for it in range(3):
