@@ -171,6 +171,37 @@ __device__ __noinline__ void fill_ones(uint32_t *m, uint32_t card, uint32_t lane
     if (lane == 0) m[card] = card;
 }
 
+/* Cold paths, out of line for the same reason. */
+struct WarpModels;
+/* update_model's rescale (src/stream_model.c:38-49): halve-and-increment every count; returns the new total. */
+__device__ __noinline__ uint32_t rescale_counts(uint32_t *m, uint32_t card, uint32_t lane) {
+    uint32_t s = 0;
+    for (uint32_t i = lane; i < card; i += 32u) { const uint32_t c = (m[i] >> 1) + 1u; m[i] = c; s += c; }
+    return __reduce_add_sync(FULL_MASK, s);
+}
+/* A FLAG value seen for the first time in this block: insert (x, 1 + 8) into the ascending sparse table. */
+__device__ __noinline__ void flag_insert(uint32_t *key, uint32_t *cnt, uint32_t used, uint32_t x, uint32_t lane) {
+    uint32_t p = 0;                                        /* insertion point: touched values below x */
+    for (uint32_t base = 0; base < used; base += 32u) {
+        const uint32_t i = base + lane;
+        p += (uint32_t)__popc(__ballot_sync(FULL_MASK, i < used && key[i] < x));
+    }
+    if (used > p) {
+        for (int base = (int)((used - 1u) & ~31u); base >= 0; base -= 32) {
+            const uint32_t i = (uint32_t)base + lane;
+            const bool mv = (i >= p && i < used);
+            uint32_t k = 0, c = 0;
+            if (mv) { k = key[i]; c = cnt[i]; }
+            __syncwarp();
+            if (mv) { key[i + 1u] = k; cnt[i + 1u] = c; }
+            __syncwarp();
+            if ((uint32_t)base <= p) break;
+        }
+    }
+    if (lane == 0) { key[p] = x; cnt[p] = 1u + 8u; }
+    __syncwarp();
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 template <int MODE>
 struct Coder {
@@ -337,9 +368,7 @@ struct Coder {
         if (lane == 0) { m[x] += step; m[card] = n; }
         SYNCW();
         if (n >= CBCG_RESCALE) {                                             /* update_model :38-49 */
-            uint32_t s = 0;
-            for (uint32_t i = lane; i < card; i += 32u) { uint32_t c = (m[i] >> 1) + 1u; m[i] = c; s += c; }
-            s = warp_sum(s);
+            const uint32_t s = rescale_counts(m, card, lane);
             SYNCW();
             if (lane == 0) m[card] = s;
             SYNCW();
@@ -491,33 +520,13 @@ struct Coder {
         if (found_idx >= 0) { if (lane == 0) M->flag_cnt[found_idx] += 8u; }
         else {
             if (used >= FLAG_CAP) { err = CBCG_ERR_LIMIT; return 0u; }
-            uint32_t p = 0;                                        /* insertion point: touched values below x */
-            for (uint32_t base = 0; base < used; base += 32u) {
-                const uint32_t i = base + lane;
-                p += (uint32_t)__popc(__ballot_sync(FULL_MASK, i < used && M->flag_key[i] < x));
-            }
-            if (used > p) {
-                for (int base = (int)((used - 1u) & ~31u); base >= 0; base -= 32) {
-                    const uint32_t i = (uint32_t)base + lane;
-                    const bool mv = (i >= p && i < used);
-                    uint32_t k = 0, c = 0;
-                    if (mv) { k = M->flag_key[i]; c = M->flag_cnt[i]; }
-                    SYNCW();
-                    if (mv) { M->flag_key[i + 1u] = k; M->flag_cnt[i + 1u] = c; }
-                    SYNCW();
-                    if ((uint32_t)base <= p) break;
-                }
-            }
-            if (lane == 0) { M->flag_key[p] = x; M->flag_cnt[p] = 1u + 8u; M->flag_used = used + 1u; }
+            flag_insert(M->flag_key, M->flag_cnt, used, x, lane);
+            if (lane == 0) M->flag_used = used + 1u;
             nused = used + 1u;
         }
         uint32_t nn = n + 8u;
         SYNCW();
-        if (nn >= CBCG_RESCALE) {
-            uint32_t s = 0;
-            for (uint32_t i = lane; i < nused; i += 32u) { uint32_t c = (M->flag_cnt[i] >> 1) + 1u; M->flag_cnt[i] = c; s += c; }
-            nn = warp_sum(s) + (65536u - nused);
-        }
+        if (nn >= CBCG_RESCALE) nn = rescale_counts(M->flag_cnt, nused, lane) + (65536u - nused);
         if (lane == 0) M->flag_n = nn;
         SYNCW();
         return x;
@@ -755,7 +764,7 @@ enum : uint32_t { K_NONE, K_DENSE, K_RLENK, K_FLAG, K_POS };
 #else
 #define K2_KERNEL_BOUNDS __launch_bounds__(K2_THREADS, K2_MIN_CTAS)
 #endif
-template <int MODE>
+template <int MODE, bool LEGACY>
 __global__ void K2_KERNEL_BOUNDS
 k2_coder_kernel(CoderParams P) {
     __shared__ __align__(16) WarpModels smodels[K2_WARPS];
@@ -764,9 +773,10 @@ k2_coder_kernel(CoderParams P) {
     if (bl >= P.n_blocks) return;
     const uint32_t b = P.block_begin + bl;
     BlockDesc &B = P.blocks[b];
-    const bool legacy = P.legacy != 0;
-    const bool primed = P.primed != 0 && MODE != MODE_LIST;
-    const bool lean = P.lean != 0 && MODE != MODE_LIST;
+    constexpr bool legacy = LEGACY;                     /* single-block mode is its own instantiation: its header, RNAME and
+                                                           end-marker states stay out of the blocked kernels' instruction stream */
+    const bool primed = !LEGACY && P.primed != 0 && MODE != MODE_LIST;
+    const bool lean = !LEGACY && P.lean != 0 && MODE != MODE_LIST;
 
     Coder<MODE> C;
     C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &smodels[warp];
@@ -1153,16 +1163,22 @@ M_DONE:
 uint32_t coder_resident_blocks(int device) {
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) return 148u * 16u;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_coder_kernel<MODE_ENC>, (int)K2_THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = K2_MIN_CTAS;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_coder_kernel<MODE_ENC, false>, (int)K2_THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = K2_MIN_CTAS;
     return (uint32_t)sms * (uint32_t)per_sm * K2_WARPS;
 }
 
 int launch_coder(const CoderParams &p, cudaStream_t st) {
     if (p.n_blocks == 0) return 0;
     const unsigned grid = (p.n_blocks + K2_WARPS - 1) / K2_WARPS;
-    if (p.mode == MODE_ENC) k2_coder_kernel<MODE_ENC><<<grid, K2_THREADS, 0, st>>>(p);
-    else if (p.mode == MODE_DEC) k2_coder_kernel<MODE_DEC><<<grid, K2_THREADS, 0, st>>>(p);
-    else k2_coder_kernel<MODE_LIST><<<grid, K2_THREADS, 0, st>>>(p);
+    if (p.legacy) {
+        if (p.mode == MODE_ENC) k2_coder_kernel<MODE_ENC, true><<<grid, K2_THREADS, 0, st>>>(p);
+        else if (p.mode == MODE_DEC) k2_coder_kernel<MODE_DEC, true><<<grid, K2_THREADS, 0, st>>>(p);
+        else k2_coder_kernel<MODE_LIST, true><<<grid, K2_THREADS, 0, st>>>(p);
+    } else {
+        if (p.mode == MODE_ENC) k2_coder_kernel<MODE_ENC, false><<<grid, K2_THREADS, 0, st>>>(p);
+        else if (p.mode == MODE_DEC) k2_coder_kernel<MODE_DEC, false><<<grid, K2_THREADS, 0, st>>>(p);
+        else k2_coder_kernel<MODE_LIST, false><<<grid, K2_THREADS, 0, st>>>(p);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
