@@ -202,6 +202,39 @@ __device__ __noinline__ void flag_insert(uint32_t *key, uint32_t *cnt, uint32_t 
     __syncwarp();
 }
 
+/* The last 1..3 bytes of a block's payload, zeros behind them (big-endian word). */
+__device__ __noinline__ uint32_t refill_tail(const uint8_t *in, uint32_t in_pos, uint32_t in_len) {
+    uint32_t w = 0;
+    for (uint32_t i = 0; i < 4u; i++) { w <<= 8; if (in_pos + i < in_len) w |= (uint32_t)in[in_pos + i]; }
+    return w;
+}
+/* Bit packer state, passed to the out-of-line long-run emitter. */
+struct BitSink { uint64_t acc; uint32_t nacc, out_pos, out_cap; uint8_t *out; int err; };
+__device__ __forceinline__ void sink_put(BitSink &b, uint32_t v, uint32_t k, uint32_t lane) {
+    if (k == 0) return;
+    b.acc = (b.acc << k) | (uint64_t)v;
+    b.nacc += k;
+    if (b.nacc >= 32u) {
+        const uint32_t w = (uint32_t)(b.acc >> (b.nacc - 32u));
+        if (b.out_pos + 4u <= b.out_cap) { if (lane == 0) *reinterpret_cast<uint32_t *>(b.out + b.out_pos) = __byte_perm(w, 0u, 0x0123); }
+        else b.err = CBCG_ERR_CAPACITY;
+        b.out_pos += 4u;
+        b.nacc -= 32u;
+        b.acc &= (1ull << b.nacc) - 1ull;
+    }
+}
+/* b0, then `run` inverse bits (more than fit one 32-bit put: a long E3 run), then the low rest_bits of rest. */
+__device__ __noinline__ void emit_long(BitSink *bs, uint32_t b0, uint32_t run, uint32_t rest, uint32_t rest_bits, uint32_t lane) {
+    BitSink b = *bs;
+    const uint32_t inv = b0 ? 0u : 0xffffffffu;
+    uint32_t r = run < 31u ? run : 31u;
+    sink_put(b, (b0 << r) | (inv & ((1u << r) - 1u)), r + 1u, lane);
+    run -= r;
+    while (run) { r = run < 32u ? run : 32u; sink_put(b, r == 32u ? inv : (inv & ((1u << r) - 1u)), r, lane); run -= r; }
+    sink_put(b, rest, rest_bits, lane);
+    *bs = b;
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 template <int MODE>
 struct Coder {
@@ -254,26 +287,16 @@ struct Coder {
         }
     }
     /* One bit b0, then `run` copies of its inverse (the pending E3 bits, src/Arithmetic_stream.c:318-322), then the
-       low rest_bits of rest. Written so that the bit packer is instantiated once: the hot loop has to fit the
+       low rest_bits of rest. The usual case is one put; long runs go out of line: the hot loop has to fit the
        instruction cache. */
     __device__ __forceinline__ void emit(uint32_t b0, uint32_t run, uint32_t rest, uint32_t rest_bits) {
-        const uint32_t inv = b0 ? 0u : 0xffffffffu;
-        uint32_t phase = 0;                                  /* 0: b0 + start of the run, 1: rest of the run, 2: rest, 3: done */
-        while (phase < 3u) {
-            uint32_t v, nb;
-            if (phase == 0u) {
-                if (run + 1u + rest_bits <= 32u) {           /* the usual case: everything in one go */
-                    v = (b0 << (run + rest_bits)) | ((inv & ((1u << run) - 1u)) << rest_bits) | rest;
-                    nb = run + 1u + rest_bits; phase = 3u;
-                } else {
-                    const uint32_t r = run < 31u ? run : 31u;
-                    v = (b0 << r) | (inv & ((1u << r) - 1u)); nb = r + 1u; run -= r; phase = run ? 1u : 2u;
-                }
-            } else if (phase == 1u) {
-                const uint32_t r = run < 32u ? run : 32u;
-                v = r == 32u ? inv : (inv & ((1u << r) - 1u)); nb = r; run -= r; if (!run) phase = 2u;
-            } else { v = rest; nb = rest_bits; phase = 3u; }
-            put_bits(v, nb);
+        if (run + 1u + rest_bits <= 32u) {
+            const uint32_t inv = b0 ? 0u : 0xffffffffu;
+            put_bits((b0 << (run + rest_bits)) | ((inv & ((1u << run) - 1u)) << rest_bits) | rest, run + 1u + rest_bits);
+        } else {
+            BitSink b = { acc, nacc, out_pos, out_cap, out, err };
+            emit_long(&b, b0, run, rest, rest_bits, lane);
+            acc = b.acc; nacc = b.nacc; out_pos = b.out_pos; err = b.err;
         }
     }
     /* stream_finish_byte (:189-194): the byte in progress always goes out, even an empty one */
@@ -300,9 +323,7 @@ struct Coder {
             uint32_t w = 0;
             if (in_pos + 4u <= in_len) {
                 w = ((uint32_t)in[in_pos] << 24) | ((uint32_t)in[in_pos + 1u] << 16) | ((uint32_t)in[in_pos + 2u] << 8) | (uint32_t)in[in_pos + 3u];
-            } else if (in_pos < in_len) {                     /* the block's last 1..3 bytes, zeros behind them */
-                for (uint32_t i = 0; i < 4u; i++) { w <<= 8; if (in_pos + i < in_len) w |= (uint32_t)in[in_pos + i]; }
-            }
+            } else if (in_pos < in_len) w = refill_tail(in, in_pos, in_len);
             in_pos += 4u;
             dbuf |= (uint64_t)w << (32u - dcnt);
             dcnt += 32u;
@@ -776,7 +797,7 @@ k2_coder_kernel(CoderParams P) {
     constexpr bool legacy = LEGACY;                     /* single-block mode is its own instantiation: its header, RNAME and
                                                            end-marker states stay out of the blocked kernels' instruction stream */
     const bool primed = !LEGACY && P.primed != 0 && MODE != MODE_LIST;
-    const bool lean = !LEGACY && P.lean != 0 && MODE != MODE_LIST;
+    constexpr bool lean = !LEGACY && MODE != MODE_LIST;  /* blocked containers never code same_ref / length bytes 1..3 */
 
     Coder<MODE> C;
     C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &smodels[warp];
