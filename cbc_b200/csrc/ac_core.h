@@ -53,9 +53,10 @@ AC_HD uint32_t ac_muldiv(uint32_t a, uint32_t b, uint32_t sub, uint32_t d, doubl
     const double pd = (double)a * (double)b - (double)sub;
     uint32_t q = (uint32_t)(pd * r);
 #endif
-    const uint64_t p = (uint64_t)a * b - sub;
-    const int64_t rem = (int64_t)(p - (uint64_t)q * d);
-    if (rem < 0) q--; else if (rem >= (int64_t)d) q++;
+    /* the estimate is off by at most one, so the true remainder lies in (-d, 2d): |.| < 2^28, and the low 32 bits
+       of the product carry it exactly (no 64-bit arithmetic on the dependent chain) */
+    const int32_t rem = (int32_t)(a * b - sub - q * d);
+    if (rem < 0) q--; else if (rem >= (int32_t)d) q++;
     return q;
 }
 
@@ -76,8 +77,8 @@ AC_HD void ac_renorm_shape(const AcInterval &a, uint32_t &k, uint32_t &bits, uin
     const uint32_t x = (a.l ^ a.u) & CBCG_AC_TOP;
     k = x ? (ac_clz32(x) - (32u - CBCG_AC_BITS)) : CBCG_AC_BITS;
     bits = k ? (a.l >> (CBCG_AC_BITS - k)) : 0u;
-    uint32_t l = (uint32_t)(((uint64_t)a.l << k) & CBCG_AC_TOP);
-    uint32_t u = (uint32_t)((((uint64_t)a.u << k) & CBCG_AC_TOP) | ((1ull << k) - 1ull));
+    uint32_t l = (a.l << k) & CBCG_AC_TOP;                            /* k <= 26: the bits shifted past 32 are masked anyway */
+    uint32_t u = ((a.u << k) & CBCG_AC_TOP) | ((1u << k) - 1u);
     /* run of (l bit = 1, u bit = 0) from bit 24 downwards */
     const uint32_t z = (l & ~u) << (32u - (CBCG_AC_BITS - 1u));      /* bit 24 -> bit 31 */
     m = ac_clz32(~z);

@@ -71,7 +71,8 @@ struct cbcg_ctx {
 
     /* result of the last encode */
     bool have_encoded = false;
-    uint32_t enc_L = 0, enc_block_reads = 0, enc_gen_mode = 0, enc_legacy = 0, enc_max_len = 0;
+    uint32_t enc_L = 0, enc_block_reads = 0, enc_gen_mode = 0, enc_legacy = 0, enc_max_len = 0, enc_fixed = 0;
+    uint32_t batch_min_len = 0;               /* shortest read of the resident batch (host scan at upload) */
     uint64_t enc_n_reads = 0, enc_n_edits = 0, enc_n_blocks = 0, enc_payload_bytes = 0;
     std::vector<uint8_t> enc_head;             /* container header + index */
 
@@ -291,7 +292,7 @@ extern "C" int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *b) {
     ctx->stats = cbcg_stats();
     CU(cudaEventRecord(ctx->ev[0], ctx->st));
     uint64_t h2d = 0;
-    uint32_t max_len = 0; uint64_t bases = 0;
+    uint32_t max_len = 0, min_len = 0xffffffffu; uint64_t bases = 0;
     if (n) {
         const uint64_t seq_b = b->seq_off[n], cig_b = b->cigar_off[n], md_b = b->md_off[n];
         TRY(ensure(ctx, ctx->b_pos, n * 4));  TRY(ensure(ctx, ctx->b_flag, n * 2)); TRY(ensure(ctx, ctx->b_len, n * 2));
@@ -309,6 +310,7 @@ extern "C" int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *b) {
         for (uint64_t r = 0; r < n; r++) {
             const uint32_t l = b->seq_len[r];
             if (l > max_len) max_len = l;
+            if (l < min_len) min_len = l;
             bases += l;
             if (b->chr[r] != run.chr) { ctx->runs.push_back(run); run.first = r; run.n = 0; run.chr = b->chr[r]; }
             run.n++;
@@ -324,6 +326,7 @@ extern "C" int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *b) {
     ctx->db.cigar_off = ctx->b_coff.as<uint64_t>(); ctx->db.cigar = ctx->b_cigar.as<uint8_t>();
     ctx->db.md_off = ctx->b_moff.as<uint64_t>(); ctx->db.md = ctx->b_md.as<uint8_t>();
     ctx->db.max_len = max_len;
+    ctx->batch_min_len = n ? min_len : 0;
     ctx->total_bases = bases;
     ctx->have_batch = true;
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
@@ -578,6 +581,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     if (n) { TRY(run_extract(ctx)); n_edits = ctx->hw->total_edits; }
     CU(cudaEventRecord(ctx->ev[1], ctx->st));
     uint64_t payload_total = 0;
+    bool fixed = false;
     if (n || legacy) {
         if (!n) {                                          /* legacy stream of an empty input: header + end marker */
             TRY(ensure(ctx, ctx->recs, sizeof(cbcg_read_rec))); TRY(ensure(ctx, ctx->edits, 64));
@@ -585,6 +589,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
             TRY(reset_words(ctx));
         }
         const bool primed = !legacy && opts->gen_mode == 1;
+        fixed = !legacy && ctx->batch_min_len == L && ctx->db.max_len == L;   /* CBCG_MODE_FIXED_LEN */
         TRY(cut_blocks(ctx, opts->block_reads, opts->gen_mode, &nb));
         const uint64_t ws_cap = coder_ws_bytes_bound(L, n, n_edits, nb, legacy, primed);
         const uint64_t pay_cap = coder_payload_bound(n, n_edits, nb, legacy);
@@ -594,7 +599,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
         CoderParams p = coder_params(ctx, (uint32_t)nb, L, legacy, 0);
         p.chr = const_cast<uint32_t *>(ctx->db.chr);
         p.payload = ctx->scratch.as<uint8_t>();
-        p.lean = legacy ? 0u : 1u; p.short_flush = legacy ? 0u : 1u; p.primed = primed ? 1u : 0u;
+        p.lean = legacy ? 0u : 1u; p.short_flush = legacy ? 0u : 1u; p.primed = primed ? 1u : 0u; p.fixed_len = fixed ? 1u : 0u;
         if (launch_plan(p, (uint32_t)n, n_edits, ws_cap, pay_cap, wptr<uint64_t>(ctx, W_OFF(totals)), ctx->st))
             return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
         CU(cudaEventRecord(ctx->ev[2], ctx->st));
@@ -630,7 +635,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     for (uint64_t k = 0; k < nb; k++) n_syms += ctx->hblocks[k].n_symbols;
     if (!legacy) {
         put32(h, CBCG_MAGIC); put32(h, CBCG_VERSION); put32(h, ctx->db.max_len); put32(h, L);
-        put64(h, n); put32(h, (uint32_t)nb); put32(h, ctx->dg.n_chr); put32(h, opts->block_reads); put32(h, opts->gen_mode);
+        put64(h, n); put32(h, (uint32_t)nb); put32(h, ctx->dg.n_chr); put32(h, opts->block_reads); put32(h, opts->gen_mode | (fixed ? CBCG_MODE_FIXED_LEN : 0u));
         for (uint32_t c = 0; c < ctx->dg.n_chr; c++) {
             const std::string &s = ctx->names[c];
             put32(h, (uint32_t)s.size());
@@ -644,7 +649,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
         h.insert(h.end(), ix.begin(), ix.end());
     }
     ctx->enc_L = L; ctx->enc_block_reads = opts->block_reads; ctx->enc_gen_mode = opts->gen_mode; ctx->enc_legacy = legacy;
-    ctx->enc_max_len = ctx->db.max_len;
+    ctx->enc_max_len = ctx->db.max_len; ctx->enc_fixed = fixed ? 1u : 0u;
     ctx->enc_n_reads = n; ctx->enc_n_edits = n_edits; ctx->enc_n_blocks = nb; ctx->enc_payload_bytes = payload_total;
     ctx->have_encoded = true;
     S.n_reads = n; S.n_blocks = nb; S.n_edits = n_edits; S.n_symbols = n_syms;
@@ -755,7 +760,7 @@ extern "C" int cbcg_extract_symbols(cbcg_ctx *ctx, const cbcg_batch *batch, cons
 
 /* ------------------------------------------------------------------------------------------------ decode */
 struct Container {
-    uint32_t max_len, L, n_blocks, n_chr, block_reads, gen_mode;
+    uint32_t max_len, L, n_blocks, n_chr, block_reads, gen_mode, fixed_len;
     uint64_t n_reads;
     uint64_t index_off, index_bytes, payload_off;
     std::vector<uint32_t> chr_map;             /* container ordinal -> genome ordinal */
@@ -768,7 +773,10 @@ static int parse_container(const uint8_t *in, uint64_t len, const std::vector<st
     if (!in || len < 40) return CBCG_ERR_FORMAT;
     if (rd32(in) != CBCG_MAGIC || rd32(in + 4) != CBCG_VERSION) return CBCG_ERR_FORMAT;
     c.max_len = rd32(in + 8); c.L = rd32(in + 12); c.n_reads = rd64(in + 16);
-    c.n_blocks = rd32(in + 24); c.n_chr = rd32(in + 28); c.block_reads = rd32(in + 32); c.gen_mode = rd32(in + 36);
+    c.n_blocks = rd32(in + 24); c.n_chr = rd32(in + 28); c.block_reads = rd32(in + 32);
+    const uint32_t mode = rd32(in + 36);
+    c.gen_mode = mode & CBCG_MODE_GEN_MASK; c.fixed_len = (mode & CBCG_MODE_FIXED_LEN) ? 1u : 0u;
+    if ((mode & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_FIXED_LEN)) || (c.fixed_len && c.max_len != c.L)) return CBCG_ERR_FORMAT;
     if (c.L == 0 || c.L > CBCG_MAX_READ_LEN || c.max_len > CBCG_MAX_READ_LEN || c.n_chr > MAX_CHR || c.gen_mode > 1) return CBCG_ERR_FORMAT;
     if (c.n_reads >= 0xfffffff0ull) return CBCG_ERR_FORMAT;
     uint64_t o = 40;
@@ -803,7 +811,7 @@ extern "C" int cbcg_decoded_size(const uint8_t *in, uint64_t in_len, uint64_t *n
 
 /* K2 decode of ctx->hblocks[0..nb) (n_reads, chr, base_pos, n_edits, payload_bytes filled in) whose payload
  * bytes lie back to back in ctx->payload. Leaves recs / edits / chr_out on the device. */
-static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy, bool primed, uint64_t reads_cap, uint64_t edits_cap,
+static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy, bool primed, bool fixed, uint64_t reads_cap, uint64_t edits_cap,
                              uint64_t *n_reads_out, uint64_t *n_edits_out) {
     TRY(ensure(ctx, ctx->blocks, (nb + 1) * sizeof(BlockDesc)));
     CU(cudaMemcpyAsync(ctx->blocks.p, ctx->hblocks, nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
@@ -817,7 +825,7 @@ static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy,
     CoderParams p = coder_params(ctx, (uint32_t)nb, L, legacy, 1);
     p.chr = ctx->chr_out.as<uint32_t>();
     p.payload = ctx->payload.as<uint8_t>();
-    p.lean = legacy ? 0u : 1u; p.short_flush = legacy ? 0u : 1u; p.primed = primed ? 1u : 0u;
+    p.lean = legacy ? 0u : 1u; p.short_flush = legacy ? 0u : 1u; p.primed = primed ? 1u : 0u; p.fixed_len = fixed ? 1u : 0u;
     if (launch_plan(p, (uint32_t)reads_cap, edits_cap, ws_cap, ~0ull, wptr<uint64_t>(ctx, W_OFF(totals)), ctx->st))
         return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
     ctx->stats.kernel_launches++;
@@ -894,7 +902,7 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
         if (pb) CU(cudaMemcpyAsync(ctx->payload.p, in + c.payload_off, pb, cudaMemcpyHostToDevice, ctx->st));
         S.h2d_bytes = pb + (uint64_t)c.n_blocks * sizeof(BlockDesc);
         CU(cudaEventRecord(ctx->ev[1], ctx->st));
-        TRY(run_decode_blocks(ctx, c.n_blocks, c.L, 0, c.gen_mode == 1, nr, ne, n_reads, n_edits));
+        TRY(run_decode_blocks(ctx, c.n_blocks, c.L, 0, c.gen_mode == 1, c.fixed_len != 0, nr, ne, n_reads, n_edits));
         S.n_blocks = c.n_blocks;
     } else {
         if (!in || in_len < 4) return fail(ctx, CBCG_ERR_FORMAT, "legacy stream too short");
@@ -912,7 +920,7 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
             b.n_reads = (uint32_t)std::min<uint64_t>(reads_cap, 0xfffffff0ull);
             b.n_edits = (uint32_t)std::min<uint64_t>(reads_cap * 4, 0xfffffff0ull);
             b.payload_bytes = (uint32_t)in_len;
-            int rc = run_decode_blocks(ctx, 1, 0, 1, false, b.n_reads, b.n_edits, n_reads, n_edits);
+            int rc = run_decode_blocks(ctx, 1, 0, 1, false, false, b.n_reads, b.n_edits, n_reads, n_edits);
             if (rc == CBCG_ERR_CAPACITY && reads_cap < (1ull << 31)) { reads_cap *= 4; continue; }
             if (rc) return rc;
             break;
@@ -993,7 +1001,7 @@ extern "C" int cbcg_decode_resident(cbcg_ctx *ctx) {
     CU(cudaEventRecord(ctx->ev[0], ctx->st));
     if (legacy) { ctx->hblocks[0].n_reads = (uint32_t)ctx->enc_n_reads + 1u; ctx->hblocks[0].n_edits = (uint32_t)ctx->enc_n_edits + 64u; }
     gens_from_blocks(ctx, nb);
-    TRY(run_decode_blocks(ctx, nb, legacy ? 0u : ctx->enc_L, legacy, !legacy && ctx->enc_gen_mode == 1,
+    TRY(run_decode_blocks(ctx, nb, legacy ? 0u : ctx->enc_L, legacy, !legacy && ctx->enc_gen_mode == 1, !legacy && ctx->enc_fixed,
                           legacy ? ctx->enc_n_reads + 1u : ctx->enc_n_reads,
                           legacy ? ctx->enc_n_edits + 64u : ctx->enc_n_edits, &nr, &ne));
     CU(cudaEventRecord(ctx->ev[1], ctx->st));

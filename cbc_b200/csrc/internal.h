@@ -72,6 +72,7 @@ struct CoderParams {
     uint32_t lean;                         /* blocked containers: same_ref and length bytes 1..3 are not coded */
     uint32_t short_flush;                  /* blocked containers: 1 + scale3 closing bits instead of the reference's 26+ */
     uint32_t primed;                       /* gen_mode 1: models start from `snap` instead of the initial state */
+    uint32_t fixed_len;                    /* CBCG_MODE_FIXED_LEN: every read is L bases, the length symbol is not coded */
     uint32_t pad;
     const uint8_t *snap;                   /* snapshot S_{g-1} (snapshot_bytes(L) bytes) */
     uint8_t *fin;                          /* per block of this launch: final small-model image (NULL: not merged) */

@@ -46,6 +46,7 @@
 #define FLAG_CAP    128u
 #define PA_STRIDE   260u              /* words per 256-symbol model row: 256 counts, n, padding to 16 bytes */
 #define VAR_DIRECT_MIN_EDITS 32768u       /* blocks with more edits index var rows directly by context */
+#define VAR_DEFERRED 0x80000000u           /* hash value: row not built yet, low 16 bits = the one symbol coded in it */
 
 enum { MODE_ENC = 0, MODE_DEC = 1, MODE_LIST = 2 };
 
@@ -130,7 +131,7 @@ struct WarpModels {
 
 /* ------------------------------------------------------------------------------------------------
  * generation snapshot (gen_mode 1): the state every block of the next generation starts from. */
-struct SnapLayout { uint64_t small, pos_hdr, pos_val, pos_cnt, pos_alpha, bitmap, flag_prev, flag_acc, var, total; uint32_t Lp; };
+struct SnapLayout { uint64_t small, pos_hdr, pos_val, pos_cnt, pos_alpha, bitmap, flag_prev, flag_acc, ones, var, total; uint32_t Lp; };
 __host__ __device__ inline SnapLayout snap_layout(uint32_t L) {
     SnapLayout s; uint64_t o = 0;
     s.Lp = (L + 1u + 31u) & ~31u;
@@ -142,6 +143,7 @@ __host__ __device__ inline SnapLayout snap_layout(uint32_t L) {
     s.bitmap = o;    o += 2048u * 4u;
     s.flag_prev = o; o += 65536u * 4u;                                 /* merge scratch: dense FLAG counts */
     s.flag_acc = o;  o += 65536u * 4u;
+    s.ones = o;      o += (uint64_t)s.Lp * 4u;                         /* the initial state of a var row, read only */
     s.var = o;       o += (uint64_t)CBCG_VAR_CONTEXTS * s.Lp * 4u;
     s.total = (o + 255u) & ~255ull;
     return s;
@@ -152,7 +154,7 @@ uint64_t fin_stride_bytes(void) { return (sizeof(WarpModels) + 15u) & ~15ull; }
 __device__ __forceinline__ uint64_t fin_stride_dev() { return (sizeof(WarpModels) + 15u) & ~15ull; }
 
 struct SnapView {
-    const uint32_t *small, *pos_hdr, *pos_val, *pos_cnt, *pos_alpha, *bitmap, *var;
+    const uint32_t *small, *pos_hdr, *pos_val, *pos_cnt, *pos_alpha, *bitmap, *ones, *var;
     uint32_t Lp;
     __host__ __device__ SnapView() {}
     __host__ __device__ SnapView(const uint8_t *base, uint32_t L) {
@@ -160,7 +162,7 @@ struct SnapView {
         small = (const uint32_t *)(base + l.small); pos_hdr = (const uint32_t *)(base + l.pos_hdr);
         pos_val = (const uint32_t *)(base + l.pos_val); pos_cnt = (const uint32_t *)(base + l.pos_cnt);
         pos_alpha = (const uint32_t *)(base + l.pos_alpha); bitmap = (const uint32_t *)(base + l.bitmap);
-        var = (const uint32_t *)(base + l.var); Lp = l.Lp;
+        ones = (const uint32_t *)(base + l.ones); var = (const uint32_t *)(base + l.var); Lp = l.Lp;
     }
 };
 
@@ -202,6 +204,10 @@ __device__ __noinline__ void flag_insert(uint32_t *key, uint32_t *cnt, uint32_t 
     __syncwarp();
 }
 
+/* A var row built from its read-only source with one touch (count of x and the total, +step) already applied. */
+__device__ __noinline__ void copy_row_touched(uint32_t *row, const uint32_t *src, uint32_t L, uint32_t x, uint32_t step, uint32_t lane) {
+    for (uint32_t i = lane; i <= L; i += 32u) row[i] = src[i] + ((i == x || i == L) ? step : 0u);
+}
 /* The last 1..3 bytes of a block's payload, zeros behind them (big-endian word). */
 __device__ __noinline__ uint32_t refill_tail(const uint8_t *in, uint32_t in_pos, uint32_t in_len) {
     uint32_t w = 0;
@@ -265,6 +271,7 @@ struct Coder {
     /* var */
     uint64_t *var_hash; uint32_t hash_mask; uint32_t *var_rows; uint32_t n_rows, rows_cap; bool var_direct;
     uint32_t *var_bitmap;
+    bool var_defer, var_ro; uint32_t defer_idx, defer_key;   /* deferred rows of the last generation (var_row) */
     /* legacy-only */
     uint32_t *codebook, *rname;
     /* primed blocks */
@@ -383,10 +390,32 @@ struct Coder {
     }
 
     /* ============================================================ dense models (counts[card], n at [card]) */
-    __device__ __forceinline__ void dense_update(uint32_t *m, uint32_t card, uint32_t step, uint32_t x) {
-        uint32_t n = m[card] + step;
+    /* cnt and n are the symbol's count and the model total the caller just coded with: no reload on the dependent
+       chain. A deferred var row (var_ro, see var_row) is not written: the touch is noted in its hash slot instead. */
+    __device__ __forceinline__ void dense_update(uint32_t *m, uint32_t card, uint32_t step, uint32_t x, uint32_t cnt, uint32_t n) {
+        n += step;
+        if (var_ro) {
+            var_ro = false;
+            if (n < CBCG_RESCALE) {
+                if (lane == 0) var_hash[defer_idx] = ((uint64_t)defer_key << 32) | VAR_DEFERRED | x;
+                SYNCW();
+                return;
+            }
+            /* the touch rescales the row: build it after all (cold) */
+            if (n_rows >= rows_cap) { err = CBCG_ERR_INTERNAL; return; }
+            uint32_t *row = var_rows + (uint64_t)n_rows * Lp;
+            copy_row_touched(row, m, L, x, step, lane);
+            if (lane == 0) var_hash[defer_idx] = ((uint64_t)defer_key << 32) | n_rows;
+            n_rows++;
+            SYNCW();
+            const uint32_t s = rescale_counts(row, card, lane);
+            SYNCW();
+            if (lane == 0) row[card] = s;
+            SYNCW();
+            return;
+        }
         SYNCW();
-        if (lane == 0) { m[x] += step; m[card] = n; }
+        if (lane == 0) { m[x] = cnt + step; m[card] = n; }
         SYNCW();
         if (n >= CBCG_RESCALE) {                                             /* update_model :38-49 */
             const uint32_t s = rescale_counts(m, card, lane);
@@ -467,7 +496,7 @@ struct Coder {
         last_lo = lo; last_n = n;
         code_interval(lo, cnt, n);
         if (err) return 0u;
-        dense_update(m, card, step, x);
+        dense_update(m, card, step, x, cnt, n);
         return x;
     }
 
@@ -652,6 +681,7 @@ struct Coder {
         }
         const uint32_t key = ctx + 1u;
         uint32_t h = (ctx * 0x9E3779B1u) >> 7;
+        const uint32_t snap_w = primed ? snap.bitmap[ctx >> 5] : 0u;           /* in flight with the probe */
         for (uint32_t probes = 0; probes <= hash_mask; probes += 32u, h += 32u) {
             const uint32_t idx = (h + lane) & hash_mask;
             const uint64_t s = var_hash[idx];
@@ -659,16 +689,34 @@ struct Coder {
             const uint32_t mm = __ballot_sync(FULL_MASK, k == key);
             const uint32_t ee = __ballot_sync(FULL_MASK, k == 0u);
             if (mm && (!ee || __ffs(mm) < __ffs(ee))) {
-                const uint32_t r = __shfl_sync(FULL_MASK, (uint32_t)s, __ffs(mm) - 1);
-                return var_rows + (uint64_t)r * Lp;
+                const uint32_t hl = (uint32_t)__ffs(mm) - 1u;
+                const uint32_t r = __shfl_sync(FULL_MASK, (uint32_t)s, hl);
+                if (!(r & VAR_DEFERRED)) return var_rows + (uint64_t)r * Lp;
+                /* second touch of a deferred row: build it now, with the first touch's update applied */
+                if (n_rows >= rows_cap) { err = CBCG_ERR_INTERNAL; return nullptr; }
+                const uint32_t nr = n_rows++, x1 = r & 0xffffu;
+                uint32_t *row = var_rows + (uint64_t)nr * Lp;
+                const uint32_t *src = ((snap_w >> (ctx & 31u)) & 1u) ? snap.var + (uint64_t)ctx * Lp : snap.ones;
+                copy_row_touched(row, src, L, x1, 10u, lane);
+                if (lane == hl) var_hash[idx] = ((uint64_t)key << 32) | nr;
+                SYNCW();
+                return row;
             }
             if (ee) {
                 const uint32_t el = (uint32_t)__ffs(ee) - 1u;
+                const bool in_snap = primed && ((snap_w >> (ctx & 31u)) & 1u);
+                if (var_defer) {
+                    /* Last generation: nobody merges this block's rows, and most contexts are touched once per block.
+                       Code straight from the snapshot's row (read only) and note the touch in the hash slot
+                       (dense_update); the row is only built if the context comes back. */
+                    defer_idx = (h + el) & hash_mask; defer_key = key; var_ro = true;
+                    return const_cast<uint32_t *>(in_snap ? snap.var + (uint64_t)ctx * Lp : snap.ones);
+                }
                 if (n_rows >= rows_cap) { err = CBCG_ERR_INTERNAL; return nullptr; }
                 const uint32_t r = n_rows++;
                 uint32_t *row = var_rows + (uint64_t)r * Lp;
                 if (lane == el) var_hash[idx] = ((uint64_t)key << 32) | r;
-                if (primed && ((snap.bitmap[ctx >> 5] >> (ctx & 31u)) & 1u)) {       /* copy on first touch */
+                if (in_snap) {                                                       /* copy on first touch */
                     const uint32_t *src = snap.var + (uint64_t)ctx * Lp;
                     for (uint32_t i = lane; i <= L; i += 32u) row[i] = src[i];
                 } else dense_init_ones(row, L);
@@ -798,10 +846,12 @@ k2_coder_kernel(CoderParams P) {
                                                            end-marker states stay out of the blocked kernels' instruction stream */
     const bool primed = !LEGACY && P.primed != 0 && MODE != MODE_LIST;
     constexpr bool lean = !LEGACY && MODE != MODE_LIST;  /* blocked containers never code same_ref / length bytes 1..3 */
+    const bool fixed = lean && P.fixed_len != 0;         /* ... nor length byte 0 when every read is L bases long */
 
     Coder<MODE> C;
     C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &smodels[warp];
     C.primed = primed; C.lean = lean;
+    C.var_defer = primed && P.fin == nullptr; C.var_ro = false; C.defer_idx = 0; C.defer_key = 0;
     if (primed) C.snap = SnapView(P.snap, P.L);
     C.L = P.L; C.Lp = (P.L + 1u + 31u) & ~31u;
     /* workspace */
@@ -926,11 +976,16 @@ S_READ:
         }
         if (cur_chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; goto M_DONE; }   /* blocks never span chromosomes: the host cut them */
         change = 0;
-        if (lean) goto S_RLEN0;
+        if (lean) {
+            if (!fixed) goto S_RLEN0;
+            if (len != P.L) { C.err = CBCG_ERR_INPUT; goto M_DONE; }        /* the host checked the batch */
+            goto S_POS;
+        }
         goto S_SAMEREF;
     }
     change = 0;
     if (legacy || !lean) goto S_SAMEREF;
+    if (fixed) { len = P.L; goto S_POS; }                                      /* CBCG_MODE_FIXED_LEN: no length symbol */
     goto S_RLEN0;
 
     /* ---- compress_rname / decompress_rname (src/id_compression.c:39-94) */
@@ -1337,7 +1392,7 @@ __global__ void __launch_bounds__(32) snapshot_init_kernel(uint8_t *snap, uint32
     const SnapLayout l = snap_layout(L);
     const uint32_t lane = threadIdx.x;
     Coder<MODE_ENC> C;                                     /* borrow the initial-state code of the block coder */
-    C.lane = lane; C.M = &M; C.L = L; C.var_direct = false; C.hash_mask = 0; C.err = 0;
+    C.lane = lane; C.M = &M; C.L = L; C.var_direct = false; C.hash_mask = 0; C.err = 0; C.primed = false; C.var_defer = false; C.var_ro = false;
     __shared__ uint64_t dummy_hash[32];                     /* init_models clears the block's hash table */
     C.var_hash = dummy_hash; C.hash_mask = 31u;
     C.init_models(false);
@@ -1354,6 +1409,9 @@ __global__ void __launch_bounds__(32) snapshot_init_kernel(uint8_t *snap, uint32
     for (uint32_t k = 0; k < 4u; k++) { for (uint32_t i = lane; i < 256u; i += 32u) pa[k * PA_STRIDE + i] = 1u; if (lane == 0) pa[k * PA_STRIDE + 256u] = 256u; }
     uint32_t *bm = reinterpret_cast<uint32_t *>(snap + l.bitmap);
     for (uint32_t i = lane; i < 2048u; i += 32u) bm[i] = 0u;
+    uint32_t *ones = reinterpret_cast<uint32_t *>(snap + l.ones);
+    for (uint32_t i = lane; i < L; i += 32u) ones[i] = 1u;
+    if (lane == 0) ones[L] = L;
 }
 
 int launch_snapshot_init(uint8_t *snap, uint32_t L, cudaStream_t st) {

@@ -85,7 +85,11 @@ typedef struct cbcg_read_rec {
 /* ---- blocked container ("CBCB"), new design: the reference stream has no framing
  * (src/compression.c:128-155). Little endian. */
 #define CBCG_MAGIC          0x42434243u   /* "CBCB" */
-#define CBCG_VERSION        2u
+#define CBCG_VERSION        3u
+/* header word 9: low byte = gen_mode; bit 8 = every read is read_len_header bases long, so the length symbol
+ * (src/read_compression.c:29-33, one zero-information coder step per read) is not coded either */
+#define CBCG_MODE_GEN_MASK  0xffu
+#define CBCG_MODE_FIXED_LEN 0x100u
 
 /* Generation-primed blocks (gen_mode 1): generation i has CBCG_GEN_COUNTS[i] blocks of
  * CBCG_GEN_READS[i] reads, each starting from the merged final states of the generation before; the

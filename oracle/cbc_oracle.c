@@ -721,6 +721,8 @@ typedef struct {
     cbco_buf *raw;          /* optional raw symbol list (POS as CBCG_S_POS_X) */
     int lean;               /* blocked containers: the per-read symbols that are constant by construction
                                (same_ref = 0, length bytes 1..3 = 0) are not coded */
+    uint32_t fixed_len;     /* blocked containers of equal-length reads (CBCG_MODE_FIXED_LEN): length byte 0 is not
+                               coded either; this is the length */
 } rstate;
 
 static void raw_sym(rstate *s, uint32_t stream, uint32_t ctx, uint32_t v) {
@@ -742,7 +744,7 @@ static void put_rname(rstate *s, const char *name) {
  * src/read_compression.c. chr_change resets prevPos (:123-124). */
 static void put_read(rstate *s, const cbcg_read_rec *rec, const uint16_t *e) {
     uint32_t len = rec->len;
-    emit(s, CBCG_S_RLENGTH, 0, len & 0xffu);                    /* :29-33: bytes 1..3 are always 0 */
+    if (!s->fixed_len) emit(s, CBCG_S_RLENGTH, 0, len & 0xffu); /* :29-33: bytes 1..3 are always 0 */
     if (!s->lean) for (uint32_t k = 1; k < 4; k++) emit(s, CBCG_S_RLENGTH, k, 0);
     uint32_t x = rec->pos - s->prev_pos + 1;                    /* :128 */
     raw_sym(s, CBCG_S_POS_X, 0, x);
@@ -781,7 +783,7 @@ static void put_read(rstate *s, const cbcg_read_rec *rec, const uint16_t *e) {
 static void get_read(rstate *s, cbcg_read_rec *rec, uint16_t *e, uint32_t *n_edits,
                      const uint8_t *ref, uint64_t ref_len) {
     coder *c = &s->c;
-    uint32_t len = get_sym(c, CBCG_S_RLENGTH, 0);
+    uint32_t len = s->fixed_len ? s->fixed_len : get_sym(c, CBCG_S_RLENGTH, 0);
     if (!s->lean) for (uint32_t k = 1; k < 4; k++) len |= get_sym(c, CBCG_S_RLENGTH, k) << (8 * k);
     uint32_t x = get_pos(c);
     uint32_t pos = s->prev_pos + x - 1;
@@ -1054,6 +1056,8 @@ int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t L,
     }
     first[nb] = b->n_reads;
     const uint32_t last_gen = nb ? idx[nb - 1].gen : 0;
+    uint32_t fixed_len = b->n_reads ? L : 0;                   /* every read exactly L bases: CBCG_MODE_FIXED_LEN */
+    for (uint64_t r = 0; r < b->n_reads; r++) if (b->seq_len[r] != L) { fixed_len = 0; break; }
     cbco_buf payload = {0};
     int rc = 0;
     models *prev = (models *)malloc(sizeof(models)), *acc = NULL;
@@ -1066,7 +1070,7 @@ int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t L,
         }
         if (!acc && idx[k].gen != last_gen) { acc = (models *)malloc(sizeof(models)); models_clone(acc, prev); }
         rstate s; rstate_init_from(&s, prev, 1);
-        s.lean = 1;
+        s.lean = 1; s.fixed_len = fixed_len;
         uint64_t start = payload.size;
         ac_init_enc(&s.c.ac, &payload);
         s.prev_pos = idx[k].base_pos; s.have_name = 1; s.cur_chr = idx[k].chr;
@@ -1088,7 +1092,7 @@ int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t L,
         for (uint64_t r = 0; r < b->n_reads; r++) if (b->seq_len[r] > max_len) max_len = b->seq_len[r];
         buf_put_u32(out, CBCG_MAGIC); buf_put_u32(out, CBCG_VERSION); buf_put_u32(out, max_len); buf_put_u32(out, L);
         buf_put_u64(out, b->n_reads); buf_put_u32(out, (uint32_t)nb); buf_put_u32(out, g->n_chr);
-        buf_put_u32(out, block_reads); buf_put_u32(out, n_sched ? 1u : 0u);
+        buf_put_u32(out, block_reads); buf_put_u32(out, (n_sched ? 1u : 0u) | (fixed_len ? CBCG_MODE_FIXED_LEN : 0u));
         for (uint32_t c = 0; c < g->n_chr; c++) {
             uint32_t nl = (uint32_t)strlen(g->name[c]), pad = (4 - (nl & 3)) & 3; uint32_t z = 0;
             buf_put_u32(out, nl); buf_put(out, g->name[c], nl); buf_put(out, &z, pad);
@@ -1118,8 +1122,10 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
     uint32_t h[10]; memcpy(h, p, 40);
     if (h[0] != CBCG_MAGIC || h[1] != CBCG_VERSION) return -41;
     uint32_t L = h[3]; uint64_t n_reads; memcpy(&n_reads, p + 16, 8);
-    uint32_t nb = h[6], n_chr = h[7], gen_mode = h[9];
-    if (gen_mode > 1 || n_chr > g->n_chr) return -42;
+    uint32_t nb = h[6], n_chr = h[7], gen_mode = h[9] & CBCG_MODE_GEN_MASK;
+    const uint32_t fixed_len = (h[9] & CBCG_MODE_FIXED_LEN) ? L : 0;
+    if (gen_mode > 1 || (h[9] & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_FIXED_LEN)) || n_chr > g->n_chr) return -42;
+    if (fixed_len && h[2] != L) return -42;
     uint64_t o = 40;
     /* container chromosome ordinal -> genome ordinal, by name */
     uint32_t *chr_map = (uint32_t *)calloc(n_chr + 1, sizeof(uint32_t));
@@ -1160,7 +1166,7 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
         if (!acc && bi.gen != last_gen) { acc = (models *)malloc(sizeof(models)); models_clone(acc, prev); }
         uint32_t chr = chr_map[bi.chr];
         rstate s; rstate_init_from(&s, prev, 2);
-        s.lean = 1;
+        s.lean = 1; s.fixed_len = fixed_len;
         ac_init_dec(&s.c.ac, p + o, bi.payload_bytes);
         s.prev_pos = bi.base_pos;
         snp_reset(&s.snp, g->len[chr] + 2048);
