@@ -40,7 +40,8 @@
 #define K2_WARPS    4u
 #endif
 #ifndef K2_MIN_CTAS
-#define K2_MIN_CTAS 4          /* resident CTAs per SM the register allocation is held to */
+#define K2_MIN_CTAS 5          /* resident CTAs per SM the register allocation is held to: 96 registers, no spills
+                                  (cold per-warp values live in shared memory, WarpCold); 6 spills and is slower */
 #endif
 #define K2_THREADS  (K2_WARPS * 32u)
 #define FLAG_CAP    128u
@@ -129,6 +130,17 @@ struct WarpModels {
     uint16_t cumdel[256];          /* decoder: cumulative deletion offsets of the current read */
 };
 
+/* Per-warp values the hot loop rarely needs (once per 32 payload bits, per POS escape, per decoded SNP): kept in
+ * shared memory behind the models instead of in registers. */
+struct WarpCold {
+    uint8_t *io;                   /* the block's payload: written by the encoder, read by the decoder */
+    const uint8_t *ref;            /* decoder: the block's chromosome */
+    uint64_t ref_len, edits_cap_abs;
+    uint32_t io_cap;               /* encoder: room in io; decoder: payload bytes */
+    uint32_t pos_cap, rows_cap, pad;
+};
+struct WarpShared { WarpModels m; WarpCold c; };
+
 /* ------------------------------------------------------------------------------------------------
  * generation snapshot (gen_mode 1): the state every block of the next generation starts from. */
 struct SnapLayout { uint64_t small, pos_hdr, pos_val, pos_cnt, pos_alpha, bitmap, flag_prev, flag_acc, ones, var, total; uint32_t Lp; };
@@ -153,17 +165,21 @@ uint64_t fin_stride_bytes(void) { return (sizeof(WarpModels) + 15u) & ~15ull; }
 
 __device__ __forceinline__ uint64_t fin_stride_dev() { return (sizeof(WarpModels) + 15u) & ~15ull; }
 
+/* Only `var` (the last piece) moves with L: every other offset is a compile-time constant, so the block coder keeps
+ * one base pointer and forms the addresses where it uses them (registers are what bounds its occupancy). */
 struct SnapView {
-    const uint32_t *small, *pos_hdr, *pos_val, *pos_cnt, *pos_alpha, *bitmap, *ones, *var;
-    uint32_t Lp;
+    const uint8_t *base; uint32_t Lp;
     __host__ __device__ SnapView() {}
-    __host__ __device__ SnapView(const uint8_t *base, uint32_t L) {
-        const SnapLayout l = snap_layout(L);
-        small = (const uint32_t *)(base + l.small); pos_hdr = (const uint32_t *)(base + l.pos_hdr);
-        pos_val = (const uint32_t *)(base + l.pos_val); pos_cnt = (const uint32_t *)(base + l.pos_cnt);
-        pos_alpha = (const uint32_t *)(base + l.pos_alpha); bitmap = (const uint32_t *)(base + l.bitmap);
-        ones = (const uint32_t *)(base + l.ones); var = (const uint32_t *)(base + l.var); Lp = l.Lp;
-    }
+    __host__ __device__ SnapView(const uint8_t *b, uint32_t L) : base(b), Lp((L + 1u + 31u) & ~31u) {}
+    __host__ __device__ __forceinline__ const uint32_t *at(uint64_t off) const { return (const uint32_t *)(base + off); }
+    __host__ __device__ __forceinline__ const uint32_t *small() const { return at(snap_layout(1).small); }
+    __host__ __device__ __forceinline__ const uint32_t *pos_hdr() const { return at(snap_layout(1).pos_hdr); }
+    __host__ __device__ __forceinline__ const uint32_t *pos_val() const { return at(snap_layout(1).pos_val); }
+    __host__ __device__ __forceinline__ const uint32_t *pos_cnt() const { return at(snap_layout(1).pos_cnt); }
+    __host__ __device__ __forceinline__ const uint32_t *pos_alpha() const { return at(snap_layout(1).pos_alpha); }
+    __host__ __device__ __forceinline__ const uint32_t *bitmap() const { return at(snap_layout(1).bitmap); }
+    __host__ __device__ __forceinline__ const uint32_t *ones() const { return at(snap_layout(1).ones); }
+    __host__ __device__ __forceinline__ const uint32_t *var_row(uint32_t ctx) const { return at(snap_layout(1).ones + (uint64_t)Lp * 4u) + (uint64_t)ctx * Lp; }
 };
 
 /* All-ones initial state of a dense model (every initialize_stream_model_* of sam_models.c but chars).
@@ -250,9 +266,9 @@ struct Coder {
     int32_t scale3;
     /* encoder bit packer */
     uint64_t acc; uint32_t nacc;
-    uint8_t *out; uint32_t out_pos, out_cap;
+    uint32_t out_pos;
     /* decoder bit reader */
-    const uint8_t *in; uint32_t in_len, in_pos, dcnt; uint64_t dbuf;
+    uint32_t in_pos, dcnt; uint64_t dbuf;
     /* symbol list */
     cbcg_symbol *list; uint32_t list_n, list_cap;
 
@@ -265,12 +281,18 @@ struct Coder {
     WarpModels *M;
     uint32_t L, Lp;
     /* pos: slots 0..31 one per lane, the rest in HBM */
-    uint32_t pos_rv, pos_rc, pos_card, pos_n, pos_cap;
-    uint32_t *pos_gval, *pos_gcnt;
-    uint32_t *pos_alpha; bool pa_init;
+    uint32_t pos_rv, pos_rc, pos_card, pos_n;
+    bool pa_init;
     /* var */
-    uint64_t *var_hash; uint32_t hash_mask; uint32_t *var_rows; uint32_t n_rows, rows_cap; bool var_direct;
-    uint32_t *var_bitmap;
+    uint64_t *var_hash; uint32_t hash_mask; uint32_t n_rows; bool var_direct;
+    /* the rest of the block's workspace, addressed from var_hash (ws_layout: pos_cnt | pos_val | pos_alpha | var_hash | var_rows) */
+    __device__ __forceinline__ WarpCold &cold() const { return reinterpret_cast<WarpShared *>(M)->c; }
+    __device__ __forceinline__ uint32_t pos_stride() const { return (uint32_t)((((uint64_t)cold().pos_cap * 4u + 15u) & ~15ull) >> 2); }
+    __device__ __forceinline__ uint32_t *pos_alpha() const { return reinterpret_cast<uint32_t *>(var_hash) - (4u * PA_STRIDE + 4u); }
+    __device__ __forceinline__ uint32_t *pos_gval() const { return pos_alpha() - pos_stride(); }
+    __device__ __forceinline__ uint32_t *pos_gcnt() const { return pos_alpha() - 2u * pos_stride(); }
+    __device__ __forceinline__ uint32_t *var_rows() const { return reinterpret_cast<uint32_t *>(var_hash + hash_mask + 1u); }
+    __device__ __forceinline__ uint32_t *var_bitmap() const { return reinterpret_cast<uint32_t *>(var_hash); }
     bool var_defer, var_ro; uint32_t defer_idx, defer_key;   /* deferred rows of the last generation (var_row) */
     /* legacy-only */
     uint32_t *codebook, *rname;
@@ -286,7 +308,7 @@ struct Coder {
         nacc += k;
         if (nacc >= 32u) {
             uint32_t w = (uint32_t)(acc >> (nacc - 32u));
-            if (out_pos + 4u <= out_cap) { if (lane == 0) *reinterpret_cast<uint32_t *>(out + out_pos) = __byte_perm(w, 0u, 0x0123); }
+            if (out_pos + 4u <= cold().io_cap) { if (lane == 0) *reinterpret_cast<uint32_t *>(cold().io + out_pos) = __byte_perm(w, 0u, 0x0123); }
             else err = CBCG_ERR_CAPACITY;
             out_pos += 4u;
             nacc -= 32u;
@@ -301,7 +323,7 @@ struct Coder {
             const uint32_t inv = b0 ? 0u : 0xffffffffu;
             put_bits((b0 << (run + rest_bits)) | ((inv & ((1u << run) - 1u)) << rest_bits) | rest, run + 1u + rest_bits);
         } else {
-            BitSink b = { acc, nacc, out_pos, out_cap, out, err };
+            BitSink b = { acc, nacc, out_pos, cold().io_cap, cold().io, err };
             emit_long(&b, b0, run, rest, rest_bits, lane);
             acc = b.acc; nacc = b.nacc; out_pos = b.out_pos; err = b.err;
         }
@@ -311,12 +333,12 @@ struct Coder {
         uint32_t full = nacc >> 3, rem = nacc & 7u;
         for (uint32_t i = 0; i < full; i++) {
             uint32_t byte = (uint32_t)(acc >> (nacc - 8u * (i + 1u))) & 0xffu;
-            if (out_pos < out_cap) { if (lane == 0) out[out_pos] = (uint8_t)byte; } else err = CBCG_ERR_CAPACITY;
+            if (out_pos < cold().io_cap) { if (lane == 0) cold().io[out_pos] = (uint8_t)byte; } else err = CBCG_ERR_CAPACITY;
             out_pos++;
         }
         if (rem || always_last) {
             uint32_t last = rem ? (((uint32_t)acc & ((1u << rem) - 1u)) << (8u - rem)) : 0u;
-            if (out_pos < out_cap) { if (lane == 0) out[out_pos] = (uint8_t)last; } else err = CBCG_ERR_CAPACITY;
+            if (out_pos < cold().io_cap) { if (lane == 0) cold().io[out_pos] = (uint8_t)last; } else err = CBCG_ERR_CAPACITY;
             out_pos++;
         }
         nacc = 0; acc = 0;
@@ -328,6 +350,7 @@ struct Coder {
         if (k == 0) return 0u;
         if (dcnt < k) {
             uint32_t w = 0;
+            const uint8_t *in = cold().io; const uint32_t in_len = cold().io_cap;
             if (in_pos + 4u <= in_len) {
                 w = ((uint32_t)in[in_pos] << 24) | ((uint32_t)in[in_pos + 1u] << 16) | ((uint32_t)in[in_pos + 2u] << 8) | (uint32_t)in[in_pos + 3u];
             } else if (in_pos < in_len) w = refill_tail(in, in_pos, in_len);
@@ -402,8 +425,8 @@ struct Coder {
                 return;
             }
             /* the touch rescales the row: build it after all (cold) */
-            if (n_rows >= rows_cap) { err = CBCG_ERR_INTERNAL; return; }
-            uint32_t *row = var_rows + (uint64_t)n_rows * Lp;
+            if (n_rows >= cold().rows_cap) { err = CBCG_ERR_INTERNAL; return; }
+            uint32_t *row = var_rows() + (uint64_t)n_rows * Lp;
             copy_row_touched(row, m, L, x, step, lane);
             if (lane == 0) var_hash[defer_idx] = ((uint64_t)defer_key << 32) | n_rows;
             n_rows++;
@@ -586,35 +609,36 @@ struct Coder {
     __device__ __forceinline__ void pos_load(uint32_t base, uint32_t &v, uint32_t &c) {
         const uint32_t i = base + lane;
         if (base == 0u) { v = pos_rv; c = (i < pos_card) ? pos_rc : 0u; }
-        else if (i < pos_card) { v = pos_gval[i]; c = pos_gcnt[i]; }
+        else if (i < pos_card) { v = pos_gval()[i]; c = pos_gcnt()[i]; }
         else { v = 0u; c = 0u; }
     }
     __device__ __forceinline__ void pos_update(uint32_t slot) {                 /* update_model, step 10 */
         if (slot < 32u) { if (lane == slot) pos_rc += 10u; }
-        else if (lane == 0) pos_gcnt[slot] += 10u;
+        else if (lane == 0) pos_gcnt()[slot] += 10u;
         pos_n += 10u;
         SYNCW();
         if (pos_n >= CBCG_RESCALE) {
             uint32_t s = 0;
             if (lane < pos_card) { pos_rc = (pos_rc >> 1) + 1u; s += pos_rc; }
-            for (uint32_t i = 32u + lane; i < pos_card; i += 32u) { uint32_t c = (pos_gcnt[i] >> 1) + 1u; pos_gcnt[i] = c; s += c; }
+            { uint32_t *gc = pos_gcnt(); for (uint32_t i = 32u + lane; i < pos_card; i += 32u) { uint32_t c = (gc[i] >> 1) + 1u; gc[i] = c; s += c; } }
             pos_n = warp_sum(s);
             SYNCW();
         }
     }
     __device__ __forceinline__ void pos_append(uint32_t x) {                    /* new symbol, count 0, then updated (:147-153) */
         const uint32_t slot = pos_card;
-        if (slot >= pos_cap) { err = CBCG_ERR_INTERNAL; return; }
+        if (slot >= cold().pos_cap) { err = CBCG_ERR_INTERNAL; return; }
         if (slot < 32u) { if (lane == slot) { pos_rv = x; pos_rc = 0u; } }
-        else if (lane == 0) { pos_gval[slot] = x; pos_gcnt[slot] = 0u; }
+        else if (lane == 0) { pos_gval()[slot] = x; pos_gcnt()[slot] = 0u; }
         pos_card = slot + 1u;
         SYNCW();
         pos_update(slot);
     }
     __device__ __forceinline__ void pa_ensure() {
         if (!pa_init) {
-            if (primed) { for (uint32_t i = lane; i < 4u * PA_STRIDE; i += 32u) pos_alpha[i] = snap.pos_alpha[i]; }
-            else for (uint32_t k = 0; k < 4u; k++) dense_init_ones(pos_alpha + k * PA_STRIDE, 256u);
+            uint32_t *pa = pos_alpha();
+            if (primed) { for (uint32_t i = lane; i < 4u * PA_STRIDE; i += 32u) pa[i] = snap.pos_alpha()[i]; }
+            else for (uint32_t k = 0; k < 4u; k++) dense_init_ones(pa + k * PA_STRIDE, 256u);
             pa_init = true;
             SYNCW();
         }
@@ -669,19 +693,19 @@ struct Coder {
     __device__ __forceinline__ uint32_t *var_row(uint32_t ctx) {
         if (ctx >= CBCG_VAR_CONTEXTS) { err = (MODE == MODE_ENC) ? CBCG_ERR_INPUT : CBCG_ERR_CORRUPT; return nullptr; }
         if (var_direct) {
-            uint32_t *row = var_rows + (uint64_t)ctx * Lp;
-            const uint32_t w = var_bitmap[ctx >> 5];
+            uint32_t *row = var_rows() + (uint64_t)ctx * Lp;
+            const uint32_t w = var_bitmap()[ctx >> 5];
             if (!((w >> (ctx & 31u)) & 1u)) {
                 dense_init_ones(row, L);
                 SYNCW();
-                if (lane == 0) var_bitmap[ctx >> 5] = w | (1u << (ctx & 31u));
+                if (lane == 0) var_bitmap()[ctx >> 5] = w | (1u << (ctx & 31u));
                 SYNCW();
             }
             return row;
         }
         const uint32_t key = ctx + 1u;
         uint32_t h = (ctx * 0x9E3779B1u) >> 7;
-        const uint32_t snap_w = primed ? snap.bitmap[ctx >> 5] : 0u;           /* in flight with the probe */
+        const uint32_t snap_w = primed ? snap.bitmap()[ctx >> 5] : 0u;           /* in flight with the probe */
         for (uint32_t probes = 0; probes <= hash_mask; probes += 32u, h += 32u) {
             const uint32_t idx = (h + lane) & hash_mask;
             const uint64_t s = var_hash[idx];
@@ -691,12 +715,12 @@ struct Coder {
             if (mm && (!ee || __ffs(mm) < __ffs(ee))) {
                 const uint32_t hl = (uint32_t)__ffs(mm) - 1u;
                 const uint32_t r = __shfl_sync(FULL_MASK, (uint32_t)s, hl);
-                if (!(r & VAR_DEFERRED)) return var_rows + (uint64_t)r * Lp;
+                if (!(r & VAR_DEFERRED)) return var_rows() + (uint64_t)r * Lp;
                 /* second touch of a deferred row: build it now, with the first touch's update applied */
-                if (n_rows >= rows_cap) { err = CBCG_ERR_INTERNAL; return nullptr; }
+                if (n_rows >= cold().rows_cap) { err = CBCG_ERR_INTERNAL; return nullptr; }
                 const uint32_t nr = n_rows++, x1 = r & 0xffffu;
-                uint32_t *row = var_rows + (uint64_t)nr * Lp;
-                const uint32_t *src = ((snap_w >> (ctx & 31u)) & 1u) ? snap.var + (uint64_t)ctx * Lp : snap.ones;
+                uint32_t *row = var_rows() + (uint64_t)nr * Lp;
+                const uint32_t *src = ((snap_w >> (ctx & 31u)) & 1u) ? snap.var_row(ctx) : snap.ones();
                 copy_row_touched(row, src, L, x1, 10u, lane);
                 if (lane == hl) var_hash[idx] = ((uint64_t)key << 32) | nr;
                 SYNCW();
@@ -710,14 +734,14 @@ struct Coder {
                        Code straight from the snapshot's row (read only) and note the touch in the hash slot
                        (dense_update); the row is only built if the context comes back. */
                     defer_idx = (h + el) & hash_mask; defer_key = key; var_ro = true;
-                    return const_cast<uint32_t *>(in_snap ? snap.var + (uint64_t)ctx * Lp : snap.ones);
+                    return const_cast<uint32_t *>(in_snap ? snap.var_row(ctx) : snap.ones());
                 }
-                if (n_rows >= rows_cap) { err = CBCG_ERR_INTERNAL; return nullptr; }
+                if (n_rows >= cold().rows_cap) { err = CBCG_ERR_INTERNAL; return nullptr; }
                 const uint32_t r = n_rows++;
-                uint32_t *row = var_rows + (uint64_t)r * Lp;
+                uint32_t *row = var_rows() + (uint64_t)r * Lp;
                 if (lane == el) var_hash[idx] = ((uint64_t)key << 32) | r;
                 if (in_snap) {                                                       /* copy on first touch */
-                    const uint32_t *src = snap.var + (uint64_t)ctx * Lp;
+                    const uint32_t *src = snap.var_row(ctx);
                     for (uint32_t i = lane; i <= L; i += 32u) row[i] = src[i];
                 } else dense_init_ones(row, L);
                 SYNCW();
@@ -773,11 +797,11 @@ struct Coder {
     }
     __device__ __forceinline__ void init_from_snapshot() {
         uint32_t *dst = reinterpret_cast<uint32_t *>(M);
-        for (uint32_t i = lane; i < (uint32_t)(sizeof(WarpModels) / 4u); i += 32u) dst[i] = snap.small[i];
-        pos_card = snap.pos_hdr[0]; pos_n = snap.pos_hdr[1];
-        pos_rv = (lane < pos_card) ? snap.pos_val[lane] : 0u;
-        pos_rc = (lane < pos_card) ? snap.pos_cnt[lane] : 0u;
-        for (uint32_t i = 32u + lane; i < pos_card; i += 32u) { pos_gval[i] = snap.pos_val[i]; pos_gcnt[i] = snap.pos_cnt[i]; }
+        for (uint32_t i = lane; i < (uint32_t)(sizeof(WarpModels) / 4u); i += 32u) dst[i] = snap.small()[i];
+        pos_card = snap.pos_hdr()[0]; pos_n = snap.pos_hdr()[1];
+        pos_rv = (lane < pos_card) ? snap.pos_val()[lane] : 0u;
+        pos_rc = (lane < pos_card) ? snap.pos_cnt()[lane] : 0u;
+        for (uint32_t i = 32u + lane; i < pos_card; i += 32u) { pos_gval()[i] = snap.pos_val()[i]; pos_gcnt()[i] = snap.pos_cnt()[i]; }
         pa_init = false;
         n_rows = 0;
         for (uint32_t i = lane; i <= hash_mask; i += 32u) var_hash[i] = 0ull;
@@ -805,7 +829,7 @@ struct Coder {
         pos_rv = 0u; pos_rc = (lane == 0u) ? 1u : 0u; pos_card = 1u; pos_n = 1u;   /* escape only (:132-162) */
         pa_init = false;
         n_rows = 0;
-        if (var_direct) { for (uint32_t i = lane; i < 2048u; i += 32u) var_bitmap[i] = 0u; }
+        if (var_direct) { for (uint32_t i = lane; i < 2048u; i += 32u) var_bitmap()[i] = 0u; }
         else { for (uint32_t i = lane; i <= hash_mask; i += 32u) var_hash[i] = 0ull; }
         if (legacy) {
             for (uint32_t k = 0; k < 4u; k++) dense_init_ones(codebook + k * PA_STRIDE, 256u);
@@ -836,7 +860,7 @@ enum : uint32_t { K_NONE, K_DENSE, K_RLENK, K_FLAG, K_POS };
 template <int MODE, bool LEGACY>
 __global__ void K2_KERNEL_BOUNDS
 k2_coder_kernel(CoderParams P) {
-    __shared__ __align__(16) WarpModels smodels[K2_WARPS];
+    __shared__ __align__(16) WarpShared sshared[K2_WARPS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t bl = blockIdx.x * K2_WARPS + warp;
     if (bl >= P.n_blocks) return;
@@ -849,7 +873,7 @@ k2_coder_kernel(CoderParams P) {
     const bool fixed = lean && P.fixed_len != 0;         /* ... nor length byte 0 when every read is L bases long */
 
     Coder<MODE> C;
-    C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &smodels[warp];
+    C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &sshared[warp].m;
     C.primed = primed; C.lean = lean;
     C.var_defer = primed && P.fin == nullptr; C.var_ro = false; C.defer_idx = 0; C.defer_key = 0;
     if (primed) C.snap = SnapView(P.snap, P.L);
@@ -860,19 +884,22 @@ k2_coder_kernel(CoderParams P) {
     {
         const WsLayout w = ws_layout(P.L ? P.L : 252u, B.n_reads, ws_edits, legacy, primed);
         uint8_t *base = P.ws + B.ws_off;
-        C.pos_gcnt = reinterpret_cast<uint32_t *>(base + w.pos_cnt);
-        C.pos_gval = reinterpret_cast<uint32_t *>(base + w.pos_val);
-        C.pos_alpha = reinterpret_cast<uint32_t *>(base + w.pos_alpha);
         C.var_hash = reinterpret_cast<uint64_t *>(base + w.var_hash);
-        C.var_bitmap = reinterpret_cast<uint32_t *>(base + w.var_hash);
-        C.var_rows = reinterpret_cast<uint32_t *>(base + w.var_rows);
         C.codebook = reinterpret_cast<uint32_t *>(base + w.codebook);
         C.rname = reinterpret_cast<uint32_t *>(base + w.rname);
-        C.pos_cap = w.pos_cap; C.hash_mask = w.hash_cap - 1u; C.rows_cap = w.rows_cap; C.var_direct = w.direct != 0u;
+        C.hash_mask = w.hash_cap - 1u; C.var_direct = w.direct != 0u;
         C.Lp = w.Lp;
+        if (lane == 0) {
+            WarpCold &W = C.cold();
+            W.pos_cap = w.pos_cap; W.rows_cap = w.rows_cap;
+            W.io = P.payload + B.payload_off;
+            W.io_cap = (MODE == MODE_DEC) ? B.payload_bytes : (uint32_t)payload_cap_bytes(B.n_reads, B.n_edits, legacy);
+            W.ref = nullptr; W.ref_len = 0;
+            if (!legacy && B.chr < P.genome.n_chr) { W.ref = P.genome.bases + P.genome.chr_off[B.chr]; W.ref_len = P.genome.chr_len[B.chr]; }
+            W.edits_cap_abs = B.edit_base + B.n_edits;
+        }
+        SYNCW();
     }
-    C.out = P.payload + B.payload_off; C.out_cap = (uint32_t)payload_cap_bytes(B.n_reads, B.n_edits, legacy);
-    C.in = P.payload + B.payload_off; C.in_len = B.payload_bytes;
     C.list = P.symbols + B.sym_off; C.list_n = 0; C.list_cap = (uint32_t)symlist_cap(B.n_reads, B.n_edits, legacy);
     if (primed) C.init_from_snapshot(); else C.init_models(legacy);
     C.ring_reset();
@@ -885,11 +912,8 @@ k2_coder_kernel(CoderParams P) {
     uint32_t k = 0;                                      /* sub-index inside a state (header byte, edit ordinal ...) */
     uint32_t prev_pos = B.base_pos, prev_m = 0u, prev_char = 0u;
     uint32_t cur_chr = legacy ? 0xffffffffu : B.chr, chr = cur_chr;
-    const uint8_t *ref = nullptr; uint64_t ref_len = 0;
-    if (!legacy && B.chr < P.genome.n_chr) { ref = P.genome.bases + P.genome.chr_off[B.chr]; ref_len = P.genome.chr_len[B.chr]; }
     const uint64_t r0 = B.first_read;
     const uint32_t n_reads = B.n_reads;                 /* legacy decode: capacity, the end marker stops the loop */
-    const uint64_t edits_cap_abs = B.edit_base + B.n_edits;
     uint64_t e_cursor = B.edit_base;
     uint32_t i = 0, n_done = 0;
     /* the read in flight */
@@ -1020,7 +1044,9 @@ P_RNAME: {
         if (chr >= P.genome.n_chr) { C.err = CBCG_ERR_NO_REFERENCE; goto M_DONE; }
         if (MODE == MODE_DEC && i >= n_reads) { C.err = CBCG_ERR_CAPACITY; goto M_DONE; }
         cur_chr = chr; prev_pos = 0u; C.ring_reset();                       /* src/compression.c:58-64 */
-        ref = P.genome.bases + P.genome.chr_off[chr]; ref_len = P.genome.chr_len[chr];
+        SYNCW();
+        if (lane == 0) { C.cold().ref = P.genome.bases + P.genome.chr_off[chr]; C.cold().ref_len = P.genome.chr_len[chr]; }
+        SYNCW();
         goto S_RLEN0;
     }
 
@@ -1066,7 +1092,7 @@ P_POS:
 S_POSESC:                                                     /* the escaped value, 4 bytes MSB first (compress_pos_alpha :75-108) */
     state = ST_POSESC;
     if (k == 0u) C.pa_ensure();
-    SYMBOL(K_DENSE, C.pos_alpha + k * PA_STRIDE, 256u, 10u, (posx >> (24u - 8u * k)) & 0xffu, CBCG_SYM_KEY(CBCG_S_POS_ALPHA, k));
+    SYMBOL(K_DENSE, C.pos_alpha() + k * PA_STRIDE, 256u, 10u, (posx >> (24u - 8u * k)) & 0xffu, CBCG_SYM_KEY(CBCG_S_POS_ALPHA, k));
     goto CODE;
 P_POSESC:
     acc |= y << (24u - 8u * k);
@@ -1117,7 +1143,7 @@ P_INDELS:
 M_COUNTS_DONE:
     if (MODE == MODE_DEC) {
         if (ni > len || ns > 255u || nd > 255u || ni > 255u) { C.err = CBCG_ERR_CORRUPT; goto M_DONE; }
-        if ((uint64_t)(ns + nd + ni) > edits_cap_abs - e_cursor) { C.err = CBCG_ERR_CAPACITY; goto M_DONE; }
+        if ((uint64_t)(ns + nd + ni) > C.cold().edits_cap_abs - e_cursor) { C.err = CBCG_ERR_CAPACITY; goto M_DONE; }
     }
     prev = 0; k = 0; ne = 0;
     if (nd) goto S_DEL;
@@ -1160,7 +1186,7 @@ P_SNPVAR: {
             for (uint32_t q = lane; q < nd; q += 32u) skipped += (C.M->cumdel[q] <= idx);
             skipped = warp_sum(skipped);
             const uint64_t ri = (uint64_t)pos - 1u + idx + skipped;
-            refb = base_code(ri < ref_len ? (uint32_t)ref[ri] : 0u);
+            refb = base_code(ri < C.cold().ref_len ? (uint32_t)C.cold().ref[ri] : 0u);
         } else refb = CBCG_EDIT_REFB(ed);
         state = ST_SNPCHAR;
         SYMBOL(K_DENSE, C.M->chars[refb], 5u, 8u, CBCG_EDIT_TARGET(ed), CBCG_SYM_KEY(CBCG_S_CHARS, refb));
@@ -1225,7 +1251,7 @@ M_DONE:
         uint32_t *dst = reinterpret_cast<uint32_t *>(P.fin + (uint64_t)bl * fin_stride_dev());
         const uint32_t *src = reinterpret_cast<const uint32_t *>(C.M);
         for (uint32_t q = lane; q < (uint32_t)(sizeof(WarpModels) / 4u); q += 32u) dst[q] = src[q];
-        if (lane < C.pos_card) { C.pos_gval[lane] = C.pos_rv; C.pos_gcnt[lane] = C.pos_rc; }
+        if (lane < C.pos_card) { C.pos_gval()[lane] = C.pos_rv; C.pos_gcnt()[lane] = C.pos_rc; }
         if (lane == 0) { B.pos_card = C.pos_card; B.n_rows = C.n_rows; B.pa_touched = C.pa_init ? 1u : 0u; }
     }
     if (lane == 0) {
@@ -1388,7 +1414,8 @@ int launch_gather(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scr
  * The decoder runs the same kernels on the blocks it has decoded. `next` arrives as a byte copy of `prev`. */
 
 __global__ void __launch_bounds__(32) snapshot_init_kernel(uint8_t *snap, uint32_t L) {
-    __shared__ WarpModels M;
+    __shared__ WarpShared WS;
+    WarpModels &M = WS.m;
     const SnapLayout l = snap_layout(L);
     const uint32_t lane = threadIdx.x;
     Coder<MODE_ENC> C;                                     /* borrow the initial-state code of the block coder */
