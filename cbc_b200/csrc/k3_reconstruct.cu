@@ -21,6 +21,7 @@
 #define K3_WARPS    8u
 #define K3_THREADS  (K3_WARPS * 32u)
 #define K3_REF_CAP  8192u
+#define K3_CHUNKS   ((K3_TILE * (CBCG_MAX_READ_LEN + 1u) + 48u) / 16u)   /* 16-byte pieces of the largest tile image */
 
 uint64_t reconstruct_num_tiles(uint64_t n_reads) { return (n_reads + K3_TILE - 1) / K3_TILE; }
 
@@ -36,16 +37,43 @@ struct K3Smem {
     uint64_t bar;
     uint64_t tile_base;
     uint32_t tile;
+    uint32_t n_slow;
     uint32_t warp_tot[K3_WARPS];
-    uint32_t out_off[K3_TILE];        /* byte offset of each read's line inside the tile */
+    uint32_t out_off[K3_TILE + 1];    /* byte offset of each read's line inside the tile; [nr] = tile total */
     __align__(16) cbcg_read_rec rec[K3_TILE];
     uint32_t chr[K3_TILE];
-    uint32_t fast[K3_TILE];           /* offset of the read's bases in ref[] when it takes the word-copy path, else ~0 */
-    uint8_t  nsnp[K3_TILE];           /* SNPs to patch on that path */
+    uint32_t so[K3_TILE + 1];         /* offset of the read's first base in ref[] (reads on the copy path), else 0 */
+    uint8_t  slow[K3_TILE];           /* reads built base by base (indels, reads outside the window) */
+    uint8_t  is_slow[K3_TILE];
+    uint8_t  rd_of[K3_CHUNKS + 2];    /* read that owns the first byte of each 16-byte piece of the image */
     K3Warp w[K3_WARPS];
-    __align__(16) uint8_t ref[K3_REF_CAP + 16];
-    __align__(16) uint8_t out[16];    /* really K3_TILE * (max_len + 1) + 32 (dynamic) */
+    __align__(16) uint8_t ref_front[32];   /* pieces at a tile's edge read up to 16 bytes before a read's first base */
+    __align__(16) uint8_t ref[K3_REF_CAP + 64];
+    __align__(16) uint8_t out[16];    /* really K3_TILE * (max_len + 1) + 48 (dynamic) */
 };
+
+/* 16 bytes of the staged window from byte offset `off` (any alignment, >= -32): two aligned 16-byte loads, the
+ * word rotation as selects (registers cannot be indexed), the byte rotation as funnel shifts. */
+__device__ __forceinline__ uint4 lds_16_unaligned(const uint8_t *base, int32_t off) {
+    const uint4 q0 = *reinterpret_cast<const uint4 *>(base + (off & ~15));
+    const uint4 q1 = *reinterpret_cast<const uint4 *>(base + (off & ~15) + 16);
+    const bool r2 = (off & 8) != 0, r1 = (off & 4) != 0;
+    const uint32_t x0 = r2 ? q0.z : q0.x, x1 = r2 ? q0.w : q0.y, x2 = r2 ? q1.x : q0.z, x3 = r2 ? q1.y : q0.w,
+                   x4 = r2 ? q1.z : q1.x, x5 = r2 ? q1.w : q1.y;
+    const uint32_t y0 = r1 ? x1 : x0, y1 = r1 ? x2 : x1, y2 = r1 ? x3 : x2, y3 = r1 ? x4 : x3, y4 = r1 ? x5 : x4;
+    const uint32_t sh = ((uint32_t)off & 3u) * 8u;
+    return make_uint4(__funnelshift_r(y0, y1, sh), __funnelshift_r(y1, y2, sh), __funnelshift_r(y2, y3, sh), __funnelshift_r(y3, y4, sh));
+}
+/* One word of a piece that holds a line end: bytes below r from a (the read that ends), byte r = '\n', bytes above r
+ * from b (the next read); r < 0: all from b, r >= 4: all from a. */
+__device__ __forceinline__ uint32_t k3_merge(uint32_t a, uint32_t b, int32_t r) {
+    if (r >= 4) return a;
+    if (r < 0) return b;
+    const uint32_t sh = 8u * (uint32_t)r;
+    const uint32_t lo = (1u << sh) - 1u;
+    const uint32_t hi = (uint32_t)(0xffffffff00ull << sh);
+    return (a & lo) | ((uint32_t)'\n' << sh) | (b & hi);
+}
 
 __global__ void __launch_bounds__(K3_THREADS)
 k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, const uint32_t *__restrict__ chr_of,
@@ -58,6 +86,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
 
     if (tid == 0) {
         S.tile = atomicAdd(ticket, 1u);
+        S.n_slow = 0;
         mbar_init(&S.bar, 1);
         mbar_fence_init();
     }
@@ -76,7 +105,8 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
         if (len > max_len || len == 0) { dev_set_error(err, CBCG_ERR_CORRUPT, r0 + tid); len = 0; S.rec[tid].len = 0; }
         my_bytes = len + 1u;
     }
-    __syncthreads();
+    /* the copy path needs every line of the tile to span a whole 16-byte piece */
+    const int tile_short = __syncthreads_or(tid < nr && my_bytes < 17u);
 
     /* reference window under the tile's first read */
     const uint32_t chr0 = S.chr[0], pos0 = S.rec[0].pos;
@@ -92,6 +122,31 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
         if (ref_bytes) tma_load_1d(S.ref, g.bases + g.chr_off[chr0] + w0, ref_bytes, &S.bar);
     }
 
+    /* Which reads are plain copies of the window, possibly with a few substituted bases? (perfect matches :383-384
+       and substitution-only reads :442-458: all of config 2.) They take the copy path; the others are listed. The
+       first SNPs of a copy-path read are fetched now, so that their latency hides behind the window's. */
+    bool fast = false; uint32_t ns = 0, e_first[4] = { 0u, 0u, 0u, 0u };
+    const uint16_t *e_mine = edits;
+    if (tid < nr) {
+        const cbcg_read_rec &rec = S.rec[tid];
+        const uint32_t len = rec.len, pos = rec.pos, chr = S.chr[tid];
+        ns = rec.match ? 0u : rec.n_snps;
+        bool ok = !tile_short && len > 0u && pos >= 1u && chr == chr0 && chr < g.n_chr && ref_bytes != 0u &&
+                  (rec.match || (rec.n_dels == 0u && rec.n_ins == 0u));
+        if (ok) ok = (uint64_t)(pos - 1u) + len <= g.chr_len[chr] && (uint64_t)(pos - 1u) >= w0 &&
+                     ((uint64_t)(pos - 1u) - w0 + len + 8u <= ref_bytes);
+        fast = ok;
+        S.so[tid] = ok ? (uint32_t)((uint64_t)(pos - 1u) - w0) : 0u;
+        S.is_slow[tid] = ok ? 0u : 1u;
+        if (!ok) { S.slow[atomicAdd(&S.n_slow, 1u)] = (uint8_t)tid; ns = 0; }
+        else if (ns) {
+            e_mine = edits + rec.edit_off;
+#pragma unroll
+            for (uint32_t q = 0; q < 4u; q++) if (q < ns) e_first[q] = e_mine[q];
+        }
+    }
+    if (tid == nr) S.so[nr] = 0u;
+
     /* CTA scan of line sizes (threads >= K3_TILE carry 0) */
     uint32_t incl = warp_incl_scan(my_bytes);
     if (lane == 31) S.warp_tot[warp] = incl;
@@ -99,7 +154,9 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
     uint32_t warp_base = 0, tile_total = 0;
 #pragma unroll
     for (uint32_t k = 0; k < K3_WARPS; k++) { uint32_t t = S.warp_tot[k]; if (k < warp) warp_base += t; tile_total += t; }
-    if (tid < nr) S.out_off[tid] = warp_base + incl - my_bytes;
+    const uint32_t my_off = warp_base + incl - my_bytes;
+    if (tid < nr) S.out_off[tid] = my_off;
+    if (tid == nr) S.out_off[nr] = tile_total;
     if (warp == 0) {
         uint64_t base = lookback_exclusive(tile_desc, tile, tile_total, err);
         if (lane == 0) {
@@ -112,66 +169,58 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
     /* smem image is shifted so that smem offset == global offset (mod 16): the middle can leave by TMA */
     const uint32_t shift = (uint32_t)((uint64_t)(out + tile_base) & 15ull);
     uint8_t *img = S.out + shift;
-    /* Which reads are plain copies of the window, possibly with a few substituted bases? (perfect matches :383-384
-       and substitution-only reads :442-458: all of config 2.) They take the word-copy path below. */
+    const uint32_t n_chunks = (shift + tile_total + 15u) >> 4;
+    /* owner of the first byte of every 16-byte piece: read i owns the pieces that start inside its line */
     if (tid < nr) {
-        const cbcg_read_rec &rec = S.rec[tid];
-        const uint32_t len = rec.len, pos = rec.pos, chr = S.chr[tid];
-        const uint32_t ns = rec.match ? 0u : rec.n_snps;
-        bool ok = len > 0u && pos >= 1u && chr == chr0 && chr < g.n_chr && ref_bytes != 0u &&
-                  (rec.match || (rec.n_dels == 0u && rec.n_ins == 0u && ns <= 16u));
-        if (ok) ok = (uint64_t)(pos - 1u) + len <= g.chr_len[chr] && (uint64_t)(pos - 1u) >= w0 &&
-                     ((uint64_t)(pos - 1u) - w0 + len + 8u <= ref_bytes);
-        S.fast[tid] = ok ? (uint32_t)((uint64_t)(pos - 1u) - w0) : 0xffffffffu;
-        S.nsnp[tid] = (uint8_t)ns;
+        const uint32_t c_lo = (tid == 0u) ? 0u : ((shift + my_off + 15u) >> 4);
+        const uint32_t c_hi = (shift + my_off + my_bytes + 15u) >> 4;       /* first piece of the next read */
+        for (uint32_t c = c_lo; c < c_hi && c < n_chunks; c++) S.rd_of[c] = (uint8_t)tid;
     }
     __syncthreads();
     mbar_wait(&S.bar, 0);
 
-    /* ---- word-copy path: half a warp per read, one aligned 4-byte word of the tile image per lane and step
-       (unaligned source word = two shared loads and a funnel shift); the line's first and last words, shared with
-       the neighbouring reads, go out byte by byte. */
-    {
-        const uint32_t half = lane >> 4, sub = lane & 15u;
-        for (uint32_t i0 = warp * 2u; i0 < nr; i0 += K3_WARPS * 2u) {
-            const uint32_t i = i0 + half;
-            uint32_t so = 0xffffffffu, len = 0, doff = 0, ns = 0;
-            if (i < nr) { so = S.fast[i]; len = S.rec[i].len; doff = shift + S.out_off[i]; ns = S.nsnp[i]; }
-            if (so != 0xffffffffu) {
-                const uint32_t w_last = (doff + len) >> 2;
-                for (uint32_t w = (doff >> 2) + sub; w <= w_last; w += 16u) {
-                    const int32_t j0 = (int32_t)(4u * w) - (int32_t)doff;          /* read-relative index of the word's first byte */
-                    if (j0 >= 0 && (uint32_t)j0 + 3u <= len) {
-                        uint32_t v = lds_u32_unaligned(S.ref, so + (uint32_t)j0);
-                        if ((uint32_t)j0 + 3u == len) v = (v & 0x00ffffffu) | ((uint32_t)'\n' << 24);
-                        reinterpret_cast<uint32_t *>(S.out)[w] = v;
-                    } else {
+    /* ---- copy path, one 16-byte piece of the tile image per lane and step. A piece lies inside one line, or holds the
+       end of line i and the start of line i + 1 (lines are >= 17 bytes here). Reads off the copy path get filler
+       bytes that their own builder overwrites below. */
+    if (!tile_short && ref_bytes) {
+        for (uint32_t c = tid; c < n_chunks; c += K3_THREADS) {
+            const uint32_t i = S.rd_of[c];
+            const int32_t j0 = (int32_t)(16u * c) - (int32_t)(shift + S.out_off[i]);   /* read-relative index of the piece's first byte */
+            const int32_t rem = (int32_t)S.rec[i].len - j0;                             /* bases of read i from there on */
+            uint4 v = lds_16_unaligned(S.ref, (int32_t)S.so[i] + j0);
+            if (rem < 16) {
+                const uint4 nx = lds_16_unaligned(S.ref, (int32_t)S.so[i + 1u] - rem - 1);
+                v.x = k3_merge(v.x, nx.x, rem); v.y = k3_merge(v.y, nx.y, rem - 4);
+                v.z = k3_merge(v.z, nx.z, rem - 8); v.w = k3_merge(v.w, nx.w, rem - 12);
+            }
+            *reinterpret_cast<uint4 *>(S.out + 16u * c) = v;
+        }
+    }
+    __syncthreads();
+    /* substituted bases of the copy-path reads: SNP k sits at sum_{i<k}(p_i + 1) + p_k (:442-458) */
+    if (fast && ns) {
+        const uint32_t len = S.rec[tid].len;
+        uint8_t *dst = img + my_off;
+        uint32_t at = 0; bool bad = false;
 #pragma unroll
-                        for (uint32_t q = 0; q < 4u; q++) {
-                            const int32_t j = j0 + (int32_t)q;
-                            if (j >= 0 && (uint32_t)j <= len) S.out[4u * w + q] = ((uint32_t)j == len) ? (uint8_t)'\n' : S.ref[so + (uint32_t)j];
-                        }
-                    }
-                }
-            } else ns = 0;
-            __syncwarp();
-            if (__any_sync(FULL_MASK, ns != 0u)) {           /* SNP k sits at sum_{i<k}(p_i + 1) + p_k: 16-lane scan per read */
-                uint32_t ed = 0, d = 0;
-                if (sub < ns) { ed = edits[S.rec[i].edit_off + sub]; d = CBCG_EDIT_DELTA(ed) + 1u; }
-                uint32_t sc = d;
-#pragma unroll
-                for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL_MASK, sc, o, 16); if (sub >= (uint32_t)o) sc += t; }
-                if (sub < ns) {
-                    if (sc - 1u >= len) dev_set_error(err, CBCG_ERR_CORRUPT, r0 + i);
-                    else S.out[doff + sc - 1u] = (uint8_t)base_char(CBCG_EDIT_TARGET(ed));
-                }
+        for (uint32_t q = 0; q < 4u; q++) {
+            if (q < ns && !bad) {
+                at += CBCG_EDIT_DELTA(e_first[q]) + 1u;
+                if (at - 1u >= len) bad = true; else dst[at - 1u] = (uint8_t)base_char(CBCG_EDIT_TARGET(e_first[q]));
             }
         }
+        for (uint32_t q = 4u; q < ns && !bad; q++) {
+            const uint32_t ed = e_mine[q];
+            at += CBCG_EDIT_DELTA(ed) + 1u;
+            if (at - 1u >= len) bad = true; else dst[at - 1u] = (uint8_t)base_char(CBCG_EDIT_TARGET(ed));
+        }
+        if (bad) { dev_set_error(err, CBCG_ERR_CORRUPT, r0 + tid); for (uint32_t j = 0; j < len; j++) dst[j] = 'N'; }
     }
 
     K3Warp &W = S.w[warp];
-    for (uint32_t i = warp; i < nr; i += K3_WARPS) {
-        if (S.fast[i] != 0xffffffffu) continue;             /* done above */
+    const uint32_t n_slow = S.n_slow;
+    for (uint32_t sidx = warp; sidx < n_slow; sidx += K3_WARPS) {
+        const uint32_t i = S.slow[sidx];
         const cbcg_read_rec &rec = S.rec[i];
         const uint32_t len = rec.len, pos = rec.pos, chr = S.chr[i];
         uint8_t *dst = img + S.out_off[i];
@@ -302,7 +351,7 @@ int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32
                        unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop) {
     if (n_reads == 0) return 0;
     const uint64_t tiles = reconstruct_num_tiles(n_reads);
-    const size_t smem = sizeof(K3Smem) + (size_t)K3_TILE * (max_len + 1u) + 64;
+    const size_t smem = sizeof(K3Smem) + (size_t)K3_TILE * (max_len + 1u) + 80;
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(k3_reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
