@@ -840,13 +840,14 @@ static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy,
     return 0;
 }
 
-static int run_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, uint32_t max_len, const uint32_t *chr_dev) {
+/* fixed_len != 0: every record is that long (CBCG_MODE_FIXED_LEN container, or checked by the caller). */
+static int run_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, uint32_t max_len, uint32_t fixed_len, const uint32_t *chr_dev) {
     const uint64_t out_cap = n_reads * ((uint64_t)max_len + 1u);
     TRY(ensure(ctx, ctx->seq_out, out_cap + 64));
     TRY(ensure(ctx, ctx->tile_desc, (reconstruct_num_tiles(n_reads) + 1) * 8));
     CU(cudaMemsetAsync(wptr<unsigned long long>(ctx, W_OFF(err)), 0, 8, ctx->st));
     if (launch_reconstruct(n_reads, ctx->recs.as<cbcg_read_rec>(), chr_dev, ctx->edits.as<uint16_t>(), ctx->dg,
-                           ctx->seq_out.as<uint8_t>(), out_cap, max_len, ctx->tile_desc.as<uint64_t>(),
+                           ctx->seq_out.as<uint8_t>(), out_cap, max_len, fixed_len, ctx->tile_desc.as<uint64_t>(),
                            wptr<uint32_t>(ctx, W_OFF(ticket)), wptr<uint64_t>(ctx, W_OFF(total_bytes)),
                            wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st, ctx->kev[2], ctx->kev[3]))
         return fail(ctx, CBCG_ERR_CUDA, "K3 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -882,7 +883,8 @@ static int blocks_from_index(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
 
 /* Shared by cbcg_decode / cbcg_decode_edits: container (or legacy stream) -> recs/edits/chr on the device. */
 static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy,
-                             uint64_t *n_reads, uint64_t *n_edits, uint32_t *max_len) {
+                             uint64_t *n_reads, uint64_t *n_edits, uint32_t *max_len, uint32_t *fixed_len) {
+    *fixed_len = 0;
     if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
     CU(cudaSetDevice(ctx->device));
     ctx->have_decoded = false;
@@ -896,6 +898,7 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
         uint64_t nr = 0, ne = 0, pb = 0;
         TRY(blocks_from_index(ctx, in, in_len, c, &nr, &ne, &pb));
         *max_len = c.max_len ? c.max_len : 1;
+        *fixed_len = c.fixed_len ? c.L : 0u;
         *n_reads = 0; *n_edits = 0;
         if (c.n_blocks == 0) return 0;
         TRY(ensure(ctx, ctx->payload, pb + 64));
@@ -936,13 +939,13 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
 extern "C" int cbcg_decode(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy,
                            uint8_t *seq_out, uint64_t seq_cap, uint64_t *seq_len, uint64_t *n_reads) {
     if (!ctx || !seq_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_decode: bad argument");
-    uint64_t nr = 0, ne = 0; uint32_t max_len = 1;
+    uint64_t nr = 0, ne = 0; uint32_t max_len = 1, fixed_len = 0;
     *seq_len = 0; if (n_reads) *n_reads = 0;
-    TRY(decode_to_records(ctx, in, in_len, legacy, &nr, &ne, &max_len));
+    TRY(decode_to_records(ctx, in, in_len, legacy, &nr, &ne, &max_len, &fixed_len));
     if (n_reads) *n_reads = nr;
     if (!nr) return CBCG_OK;
     if (legacy) max_len = CBCG_MAX_READ_LEN;                /* per-read lengths are coded mod 256 (src/read_compression.c:29-33) */
-    TRY(run_reconstruct(ctx, nr, max_len, ctx->chr_out.as<uint32_t>()));
+    TRY(run_reconstruct(ctx, nr, max_len, fixed_len, ctx->chr_out.as<uint32_t>()));
     CU(cudaEventRecord(ctx->ev[3], ctx->st));
     TRY(fetch_words(ctx));
     TRY(device_error(ctx, "read reconstruction"));
@@ -969,9 +972,9 @@ extern "C" int cbcg_decode_edits(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_l
                                  cbcg_read_rec *recs, uint64_t recs_cap, uint32_t *chr, uint16_t *edits,
                                  uint64_t edits_cap, uint64_t *n_reads, uint64_t *n_edits) {
     if (!ctx || !n_reads || !n_edits) return fail(ctx, CBCG_ERR_ARG, "cbcg_decode_edits: bad argument");
-    uint64_t nr = 0, ne = 0; uint32_t max_len = 1;
+    uint64_t nr = 0, ne = 0; uint32_t max_len = 1, fixed_len = 0;
     *n_reads = 0; *n_edits = 0;
-    TRY(decode_to_records(ctx, in, in_len, legacy, &nr, &ne, &max_len));
+    TRY(decode_to_records(ctx, in, in_len, legacy, &nr, &ne, &max_len, &fixed_len));
     *n_reads = nr; *n_edits = ne;
     if (nr > recs_cap || ne > edits_cap) return fail(ctx, CBCG_ERR_CAPACITY, "%llu reads / %llu edits decoded, room for %llu / %llu",
                                                      (unsigned long long)nr, (unsigned long long)ne, (unsigned long long)recs_cap, (unsigned long long)edits_cap);
@@ -1006,7 +1009,8 @@ extern "C" int cbcg_decode_resident(cbcg_ctx *ctx) {
                           legacy ? ctx->enc_n_edits + 64u : ctx->enc_n_edits, &nr, &ne));
     CU(cudaEventRecord(ctx->ev[1], ctx->st));
     if (nr) {
-        TRY(run_reconstruct(ctx, nr, legacy ? CBCG_MAX_READ_LEN : std::max(ctx->enc_max_len, 1u), ctx->chr_out.as<uint32_t>()));
+        TRY(run_reconstruct(ctx, nr, legacy ? CBCG_MAX_READ_LEN : std::max(ctx->enc_max_len, 1u),
+                            (!legacy && ctx->enc_fixed) ? ctx->enc_L : 0u, ctx->chr_out.as<uint32_t>()));
         CU(cudaEventRecord(ctx->ev[2], ctx->st));
         TRY(fetch_words(ctx));
         TRY(device_error(ctx, "read reconstruction"));
@@ -1043,9 +1047,10 @@ extern "C" int cbcg_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, const cbcg_read
     *seq_len = 0;
     ctx->stats = cbcg_stats();
     if (!n_reads) return CBCG_OK;
-    uint32_t max_len = 1;
+    uint32_t max_len = 1, min_len = 0xffffffffu;
     for (uint64_t r = 0; r < n_reads; r++) {
         if (recs[r].len > max_len) max_len = recs[r].len;
+        if (recs[r].len < min_len) min_len = recs[r].len;
         if (!recs[r].match && (uint64_t)recs[r].edit_off + recs[r].n_dels + recs[r].n_snps + recs[r].n_ins > n_edits)
             return fail(ctx, CBCG_ERR_ARG, "read %llu: edit range outside the edit array", (unsigned long long)r);
     }
@@ -1058,7 +1063,7 @@ extern "C" int cbcg_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, const cbcg_read
     if (n_edits) CU(cudaMemcpyAsync(ctx->edits.p, edits, n_edits * 2, cudaMemcpyHostToDevice, ctx->st));
     TRY(reset_words(ctx));
     CU(cudaEventRecord(ctx->ev[0], ctx->st));
-    TRY(run_reconstruct(ctx, n_reads, max_len, ctx->chr_out.as<uint32_t>()));
+    TRY(run_reconstruct(ctx, n_reads, max_len, min_len == max_len ? max_len : 0u, ctx->chr_out.as<uint32_t>()));
     CU(cudaEventRecord(ctx->ev[1], ctx->st));
     TRY(fetch_words(ctx));
     cudaEventElapsedTime(&ctx->stats.ms_reconstruct, ctx->ev[0], ctx->ev[1]);

@@ -84,7 +84,7 @@ int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, u
                    uint64_t edits_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_edits,
                    unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop);
 int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr, const uint16_t *edits,
-                       const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len,
+                       const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len, uint32_t fixed_len,
                        uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
                        unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop);
 uint64_t extract_num_tiles(uint64_t n_reads);

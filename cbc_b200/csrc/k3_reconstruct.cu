@@ -79,19 +79,24 @@ __global__ void __launch_bounds__(K3_THREADS)
 k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, const uint32_t *__restrict__ chr_of,
                       const uint16_t *__restrict__ edits, DevGenome g, uint8_t *__restrict__ out, uint64_t out_cap,
                       uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes, unsigned long long *err,
-                      uint32_t max_len) {
+                      uint32_t max_len, uint32_t fixed_len) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     K3Smem &S = *reinterpret_cast<K3Smem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
+    /* Tiles take their index from a ticket so that the look-back below cannot deadlock; with closed-form offsets
+       (fixed_len) the CTA index will do, and the records are requested one barrier earlier. */
+    uint32_t tile = blockIdx.x;
+    if (!fixed_len) {
+        if (tid == 0) S.tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        tile = S.tile;
+    }
     if (tid == 0) {
-        S.tile = atomicAdd(ticket, 1u);
         S.n_slow = 0;
         mbar_init(&S.bar, 1);
         mbar_fence_init();
     }
-    __syncthreads();
-    const uint32_t tile = S.tile;
     const uint64_t r0 = (uint64_t)tile * K3_TILE;
     const uint32_t nr = (uint32_t)min((uint64_t)K3_TILE, n_reads - r0);
 
@@ -102,7 +107,10 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
         *reinterpret_cast<uint4 *>(&S.rec[tid]) = v;
         S.chr[tid] = chr_of[r0 + tid];
         uint32_t len = S.rec[tid].len;
-        if (len > max_len || len == 0) { dev_set_error(err, CBCG_ERR_CORRUPT, r0 + tid); len = 0; S.rec[tid].len = 0; }
+        if (len > max_len || len == 0 || (fixed_len && len != fixed_len)) {
+            dev_set_error(err, CBCG_ERR_CORRUPT, r0 + tid);
+            len = fixed_len; S.rec[tid].len = (uint16_t)len; S.rec[tid].pos = 0u;     /* pos 0: rebuilt as N's below */
+        }
         my_bytes = len + 1u;
     }
     /* the copy path needs every line of the tile to span a whole 16-byte piece */
@@ -157,7 +165,12 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
     const uint32_t my_off = warp_base + incl - my_bytes;
     if (tid < nr) S.out_off[tid] = my_off;
     if (tid == nr) S.out_off[nr] = tile_total;
-    if (warp == 0) {
+    /* Output offset of the tile. Equal-length reads (CBCG_MODE_FIXED_LEN containers): closed form. Otherwise a
+       decoupled look-back over the tiles' byte totals, whose wait for the slowest of 32 neighbouring tiles is the
+       longest stall of this kernel. */
+    if (fixed_len) {
+        if (tid == 0 && r0 + nr == n_reads) *total_bytes = n_reads * (uint64_t)(fixed_len + 1u);
+    } else if (warp == 0) {
         uint64_t base = lookback_exclusive(tile_desc, tile, tile_total, err);
         if (lane == 0) {
             S.tile_base = base;
@@ -165,7 +178,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
         }
     }
     __syncthreads();
-    const uint64_t tile_base = S.tile_base;
+    const uint64_t tile_base = fixed_len ? r0 * (uint64_t)(fixed_len + 1u) : S.tile_base;
     /* smem image is shifted so that smem offset == global offset (mod 16): the middle can leave by TMA */
     const uint32_t shift = (uint32_t)((uint64_t)(out + tile_base) & 15ull);
     uint8_t *img = S.out + shift;
@@ -346,7 +359,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
 }
 
 int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr, const uint16_t *edits,
-                       const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len,
+                       const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len, uint32_t fixed_len,
                        uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
                        unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop) {
     if (n_reads == 0) return 0;
@@ -361,7 +374,7 @@ int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32
     if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;
     if (ev_start) cudaEventRecord(ev_start, st);
     k3_reconstruct_kernel<<<(unsigned)tiles, K3_THREADS, smem, st>>>(n_reads, recs, chr, edits, g, out, out_cap,
-                                                                    tile_desc, ticket, total_bytes, err, max_len);
+                                                                    tile_desc, ticket, total_bytes, err, max_len, fixed_len);
     if (ev_stop) cudaEventRecord(ev_stop, st);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
