@@ -29,6 +29,7 @@ struct DevBuf {
 };
 
 struct ChrRun { uint64_t first, n; uint32_t chr; };
+#define PIPE_MAX 6             /* side streams: with the main and the copy stream that makes 8, the default number of hardware queues (more would alias and serialise) */
 
 /* small device words + their pinned host mirror */
 struct Words {
@@ -38,6 +39,7 @@ struct Words {
     uint64_t totals[5];
     uint32_t ticket;
     uint32_t pad;
+    uint64_t chain[2];                        /* pipelined encode: edit entries so far, ping-pong between K1 launches */
 };
 
 struct cbcg_ctx {
@@ -46,6 +48,11 @@ struct cbcg_ctx {
     cudaEvent_t ev[8] = {};
     cudaEvent_t kev[4] = {};                  /* tight around K1 (0,1) and K3 (2,3) */
     cudaEvent_t mark[4] = {};
+    /* pipelined host-buffer calls (cbcg_encode / cbcg_decode on large batches): a copy stream, side streams for the
+       groups of last-generation blocks, and the events that order them */
+    cudaStream_t cs = nullptr, ps[PIPE_MAX] = {};
+    cudaEvent_t cev[PIPE_MAX + 2] = {}, kev2[PIPE_MAX + 2] = {}, dev2[PIPE_MAX + 2] = {};
+    bool pipe_ready = false;
     char errtext[512] = {0};
     cbcg_stats stats = {};
 
@@ -190,6 +197,11 @@ extern "C" void cbcg_destroy(cbcg_ctx *ctx) {
     for (auto &e : ctx->mark) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
     if (ctx->st) cudaStreamDestroy(ctx->st);
+    if (ctx->cs) cudaStreamDestroy(ctx->cs);
+    for (auto &s : ctx->ps) if (s) cudaStreamDestroy(s);
+    for (auto &e : ctx->cev) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->kev2) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->dev2) if (e) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -282,52 +294,75 @@ static int check_batch(cbcg_ctx *ctx, const cbcg_batch *b) {
     return 0;
 }
 
-extern "C" int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *b) {
-    if (!ctx) return CBCG_ERR_ARG;
-    TRY(check_batch(ctx, b));
-    CU(cudaSetDevice(ctx->device));
+/* Device buffers for the batch and ctx->db pointing at them (no copies yet). */
+static int batch_prepare(cbcg_ctx *ctx, const cbcg_batch *b) {
     const uint64_t n = b->n_reads;
     ctx->have_batch = false; ctx->have_encoded = false;
     ctx->runs.clear();
     ctx->stats = cbcg_stats();
-    CU(cudaEventRecord(ctx->ev[0], ctx->st));
-    uint64_t h2d = 0;
-    uint32_t max_len = 0, min_len = 0xffffffffu; uint64_t bases = 0;
     if (n) {
         const uint64_t seq_b = b->seq_off[n], cig_b = b->cigar_off[n], md_b = b->md_off[n];
         TRY(ensure(ctx, ctx->b_pos, n * 4));  TRY(ensure(ctx, ctx->b_flag, n * 2)); TRY(ensure(ctx, ctx->b_len, n * 2));
         TRY(ensure(ctx, ctx->b_chr, n * 4));
         TRY(ensure(ctx, ctx->b_soff, (n + 1) * 8)); TRY(ensure(ctx, ctx->b_coff, (n + 1) * 8)); TRY(ensure(ctx, ctx->b_moff, (n + 1) * 8));
         TRY(ensure(ctx, ctx->b_seq, seq_b + POOL_PAD)); TRY(ensure(ctx, ctx->b_cigar, cig_b + POOL_PAD)); TRY(ensure(ctx, ctx->b_md, md_b + POOL_PAD));
-        struct { void *d; const void *h; uint64_t bytes; } cp[] = {
-            { ctx->b_pos.p, b->pos, n * 4 }, { ctx->b_flag.p, b->flag, n * 2 }, { ctx->b_len.p, b->seq_len, n * 2 },
-            { ctx->b_chr.p, b->chr, n * 4 }, { ctx->b_soff.p, b->seq_off, (n + 1) * 8 }, { ctx->b_coff.p, b->cigar_off, (n + 1) * 8 },
-            { ctx->b_moff.p, b->md_off, (n + 1) * 8 }, { ctx->b_seq.p, b->seq, seq_b }, { ctx->b_cigar.p, b->cigar, cig_b },
-            { ctx->b_md.p, b->md, md_b } };
-        for (auto &c : cp) { if (c.bytes) CU(cudaMemcpyAsync(c.d, c.h, c.bytes, cudaMemcpyHostToDevice, ctx->st)); h2d += c.bytes; }
-        /* host scan while the copies fly: chromosome runs (blocks never span chromosomes), longest read */
-        ChrRun run = { 0, 0, b->chr[0] };
-        for (uint64_t r = 0; r < n; r++) {
-            const uint32_t l = b->seq_len[r];
-            if (l > max_len) max_len = l;
-            if (l < min_len) min_len = l;
-            bases += l;
-            if (b->chr[r] != run.chr) { ctx->runs.push_back(run); run.first = r; run.n = 0; run.chr = b->chr[r]; }
-            run.n++;
-        }
-        ctx->runs.push_back(run);
     }
-    CU(cudaEventRecord(ctx->ev[1], ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
     ctx->db.n_reads = n;
     ctx->db.pos = ctx->b_pos.as<uint32_t>(); ctx->db.flag = ctx->b_flag.as<uint16_t>(); ctx->db.seq_len = ctx->b_len.as<uint16_t>();
     ctx->db.chr = ctx->b_chr.as<uint32_t>();
     ctx->db.seq_off = ctx->b_soff.as<uint64_t>(); ctx->db.seq = ctx->b_seq.as<uint8_t>();
     ctx->db.cigar_off = ctx->b_coff.as<uint64_t>(); ctx->db.cigar = ctx->b_cigar.as<uint8_t>();
     ctx->db.md_off = ctx->b_moff.as<uint64_t>(); ctx->db.md = ctx->b_md.as<uint8_t>();
+    return 0;
+}
+/* Reads [r0, r1) of every array of the batch, host -> device, on stream st (pool offsets are absolute, so a slice
+   of the offset arrays indexes the same pools). */
+static int batch_copy_range(cbcg_ctx *ctx, const cbcg_batch *b, uint64_t r0, uint64_t r1, cudaStream_t st, uint64_t *bytes) {
+    if (r1 <= r0) return 0;
+    const uint64_t m = r1 - r0;
+    const uint64_t s0 = b->seq_off[r0], s1 = b->seq_off[r1], c0 = b->cigar_off[r0], c1 = b->cigar_off[r1], m0 = b->md_off[r0], m1 = b->md_off[r1];
+    struct { void *d; const void *h; uint64_t bytes; } cp[] = {
+        { ctx->b_pos.as<uint32_t>() + r0, b->pos + r0, m * 4 }, { ctx->b_flag.as<uint16_t>() + r0, b->flag + r0, m * 2 },
+        { ctx->b_len.as<uint16_t>() + r0, b->seq_len + r0, m * 2 }, { ctx->b_chr.as<uint32_t>() + r0, b->chr + r0, m * 4 },
+        { ctx->b_soff.as<uint64_t>() + r0, b->seq_off + r0, (m + 1) * 8 }, { ctx->b_coff.as<uint64_t>() + r0, b->cigar_off + r0, (m + 1) * 8 },
+        { ctx->b_moff.as<uint64_t>() + r0, b->md_off + r0, (m + 1) * 8 }, { ctx->b_seq.as<uint8_t>() + s0, b->seq + s0, s1 - s0 },
+        { ctx->b_cigar.as<uint8_t>() + c0, b->cigar + c0, c1 - c0 }, { ctx->b_md.as<uint8_t>() + m0, b->md + m0, m1 - m0 } };
+    for (auto &c : cp) { if (c.bytes) CU(cudaMemcpyAsync(c.d, c.h, c.bytes, cudaMemcpyHostToDevice, st)); *bytes += c.bytes; }
+    return 0;
+}
+/* Host scan of the batch: chromosome runs (blocks never span chromosomes), longest and shortest read. */
+static void batch_scan(cbcg_ctx *ctx, const cbcg_batch *b) {
+    const uint64_t n = b->n_reads;
+    uint32_t max_len = 0, min_len = 0xffffffffu;
+    ctx->runs.clear();
+    if (n) {
+        const uint16_t *sl = b->seq_len;
+        for (uint64_t r = 0; r < n; r++) { const uint32_t l = sl[r]; max_len = l > max_len ? l : max_len; min_len = l < min_len ? l : min_len; }
+        ChrRun run = { 0, 0, b->chr[0] };
+        const uint32_t *ch = b->chr;
+        for (uint64_t r = 0; r < n; r++) {
+            if (ch[r] != run.chr) { ctx->runs.push_back(run); run.first = r; run.n = 0; run.chr = ch[r]; }
+            run.n++;
+        }
+        ctx->runs.push_back(run);
+    }
     ctx->db.max_len = max_len;
     ctx->batch_min_len = n ? min_len : 0;
-    ctx->total_bases = bases;
+    ctx->total_bases = n ? b->seq_off[n] - b->seq_off[0] : 0;
+}
+
+extern "C" int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *b) {
+    if (!ctx) return CBCG_ERR_ARG;
+    TRY(check_batch(ctx, b));
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = b->n_reads;
+    TRY(batch_prepare(ctx, b));
+    CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    uint64_t h2d = 0;
+    TRY(batch_copy_range(ctx, b, 0, n, ctx->st, &h2d));
+    batch_scan(ctx, b);                                   /* while the copies fly */
+    CU(cudaEventRecord(ctx->ev[1], ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
     ctx->have_batch = true;
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
     ctx->stats.ms_h2d = ms; ctx->stats.h2d_bytes = h2d; ctx->stats.n_reads = n;
@@ -402,12 +437,16 @@ static void gens_from_blocks(cbcg_ctx *ctx, uint64_t nb) {
 
 /* Blocks of block_reads reads, never across a chromosome change. gen_mode 1: the first generations follow the
  * CBCG_GEN_* schedule (small blocks that bootstrap the model snapshots), the last one takes the rest. */
-static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, uint64_t *n_blocks_out) {
+struct SizeStep { uint64_t r_limit; uint32_t block_reads; };    /* last-generation blocks that start below r_limit get this size */
+static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, uint64_t *n_blocks_out,
+                      const std::vector<SizeStep> *ramp = nullptr, bool upload = true) {
     static const uint32_t sched_count[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sched_reads[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
     const uint32_t n_sched = gen_mode ? CBCG_GEN_LEVELS : 0u;
     const uint64_t n = ctx->db.n_reads;
     uint64_t bound = 1;
-    if (block_reads) { for (const ChrRun &r : ctx->runs) bound += r.n / block_reads + 1; for (uint32_t g = 0; g < n_sched; g++) bound += sched_count[g]; }
+    uint32_t min_reads = block_reads;
+    if (ramp) for (const SizeStep &st : *ramp) min_reads = std::min(min_reads, std::max(st.block_reads, 1u));
+    if (block_reads) { for (const ChrRun &r : ctx->runs) bound += r.n / min_reads + 1; for (uint32_t g = 0; g < n_sched; g++) bound += sched_count[g]; }
     if (bound >= 0xffffffffull) return fail(ctx, CBCG_ERR_ARG, "too many blocks");
     TRY(ensure_hblocks(ctx, bound + 1));
     BlockDesc *hb = ctx->hblocks;
@@ -418,10 +457,15 @@ static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, ui
         nb = 1;
     } else {
         uint32_t gen = 0, left = n_sched ? sched_count[0] : 0;
+        size_t ramp_i = 0;
         for (const ChrRun &r : ctx->runs) {
             uint64_t o = 0;
             while (o < r.n) {
                 uint32_t want = gen < n_sched ? sched_reads[gen] : block_reads;
+                if (gen >= n_sched && ramp) {
+                    while (ramp_i + 1 < ramp->size() && r.first + o >= (*ramp)[ramp_i].r_limit) ramp_i++;
+                    want = (*ramp)[ramp_i].block_reads;
+                }
                 if (!want) want = 1;
                 BlockDesc &d = hb[nb++];
                 memset(&d, 0, sizeof d);
@@ -435,8 +479,47 @@ static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, ui
     }
     gens_from_blocks(ctx, nb);
     TRY(ensure(ctx, ctx->blocks, (nb + 1) * sizeof(BlockDesc)));
-    if (nb) CU(cudaMemcpyAsync(ctx->blocks.p, hb, nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
+    if (nb && upload) CU(cudaMemcpyAsync(ctx->blocks.p, hb, nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
     *n_blocks_out = nb;
+    return 0;
+}
+
+/* CBCG_BLOCK_AUTO: reads per last-generation block such that the generation fills the GPU's resident block slots a
+ * whole number of times. */
+static uint32_t auto_block_reads(cbcg_ctx *ctx, uint64_t n, uint32_t gen_mode, uint64_t *slots_out = nullptr) {
+    static const uint32_t sc[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sr[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
+    uint64_t early = 0;
+    if (gen_mode) for (uint32_t g = 0; g < CBCG_GEN_LEVELS; g++) early += (uint64_t)sc[g] * sr[g];
+    const uint64_t main_reads = n > early ? n - early : n;
+    const uint64_t slots = coder_resident_blocks(ctx->device);
+    const uint64_t waves = std::max<uint64_t>(1, (main_reads + slots * CBCG_BLOCK_AUTO_MAX - 1) / (slots * CBCG_BLOCK_AUTO_MAX));
+    uint64_t r = (main_reads + waves * slots - 1) / (waves * slots);
+    if (slots_out) *slots_out = slots;
+    return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(r, 64), CBCG_BLOCK_AUTO_MAX);
+}
+
+/* Generations 0 .. last-1 of ctx->gens with the merges that build the snapshots; *snap_out = the snapshot the last
+ * generation starts from. */
+static int run_early_generations(cbcg_ctx *ctx, CoderParams p, uint8_t **snap_out) {
+    const uint64_t sb = snapshot_bytes(p.L);
+    uint32_t max_merged = 1;
+    for (size_t g = 0; g + 1 < ctx->gens.size(); g++) max_merged = std::max(max_merged, ctx->gens[g].second);
+    TRY(ensure(ctx, ctx->snap_a, sb)); TRY(ensure(ctx, ctx->snap_b, sb));
+    TRY(ensure(ctx, ctx->fin, (uint64_t)max_merged * fin_stride_bytes()));
+    uint8_t *cur = ctx->snap_a.as<uint8_t>(), *other = ctx->snap_b.as<uint8_t>();
+    if (launch_snapshot_init(cur, p.L, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "snapshot init launch failed");
+    ctx->stats.kernel_launches++;
+    for (size_t g = 0; g + 1 < ctx->gens.size(); g++) {
+        p.block_begin = ctx->gens[g].first; p.n_blocks = ctx->gens[g].second;
+        p.snap = cur; p.fin = ctx->fin.as<uint8_t>();
+        if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx->stats.kernel_launches++;
+        if (launch_merge(p.blocks, p.block_begin, p.n_blocks, p.L, cur, other, ctx->fin.as<uint8_t>(), p.ws, p.err, ctx->st))
+            return fail(ctx, CBCG_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx->stats.kernel_launches += 4;
+        std::swap(cur, other);
+    }
+    *snap_out = cur;
     return 0;
 }
 
@@ -449,27 +532,13 @@ static int run_coder_generations(cbcg_ctx *ctx, CoderParams p, uint64_t nb, bool
         ctx->stats.kernel_launches++;
         return 0;
     }
-    const uint64_t sb = snapshot_bytes(p.L);
-    uint32_t max_merged = 1;
-    for (size_t g = 0; g + 1 < ctx->gens.size(); g++) max_merged = std::max(max_merged, ctx->gens[g].second);
-    TRY(ensure(ctx, ctx->snap_a, sb)); TRY(ensure(ctx, ctx->snap_b, sb));
-    TRY(ensure(ctx, ctx->fin, (uint64_t)max_merged * fin_stride_bytes()));
-    uint8_t *cur = ctx->snap_a.as<uint8_t>(), *other = ctx->snap_b.as<uint8_t>();
-    if (launch_snapshot_init(cur, p.L, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "snapshot init launch failed");
+    if (ctx->gens.empty()) return 0;
+    uint8_t *cur = nullptr;
+    TRY(run_early_generations(ctx, p, &cur));
+    p.block_begin = ctx->gens.back().first; p.n_blocks = ctx->gens.back().second;
+    p.snap = cur; p.fin = nullptr;
+    if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     ctx->stats.kernel_launches++;
-    for (size_t g = 0; g < ctx->gens.size(); g++) {
-        const bool last = g + 1 == ctx->gens.size();
-        p.block_begin = ctx->gens[g].first; p.n_blocks = ctx->gens[g].second;
-        p.snap = cur; p.fin = last ? nullptr : ctx->fin.as<uint8_t>();
-        if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        ctx->stats.kernel_launches++;
-        if (!last) {
-            if (launch_merge(p.blocks, p.block_begin, p.n_blocks, p.L, cur, other, ctx->fin.as<uint8_t>(), p.ws, p.err, ctx->st))
-                return fail(ctx, CBCG_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            ctx->stats.kernel_launches += 4;
-            std::swap(cur, other);
-        }
-    }
     return 0;
 }
 
@@ -549,6 +618,39 @@ static int validate_opts(cbcg_ctx *ctx, const cbcg_encode_opts *o) {
     return 0;
 }
 
+/* Container header + index of the blocks in ctx->hblocks (layout: DESIGN.md, "Container"), and the bookkeeping of
+ * "the last encode" that cbcg_fetch_container / cbcg_decode_resident use. */
+static void finish_encode(cbcg_ctx *ctx, const cbcg_encode_opts *opts, int legacy, bool fixed, uint64_t n, uint64_t n_edits,
+                          uint64_t nb, uint64_t payload_total) {
+    const uint32_t L = opts->read_len_header;
+    cbcg_stats &S = ctx->stats;
+    std::vector<uint8_t> &h = ctx->enc_head;
+    h.clear();
+    uint64_t n_syms = 0;
+    for (uint64_t k = 0; k < nb; k++) n_syms += ctx->hblocks[k].n_symbols;
+    if (!legacy) {
+        put32(h, CBCG_MAGIC); put32(h, CBCG_VERSION); put32(h, ctx->db.max_len); put32(h, L);
+        put64(h, n); put32(h, (uint32_t)nb); put32(h, ctx->dg.n_chr); put32(h, opts->block_reads); put32(h, opts->gen_mode | (fixed ? CBCG_MODE_FIXED_LEN : 0u));
+        for (uint32_t c = 0; c < ctx->dg.n_chr; c++) {
+            const std::string &s = ctx->names[c];
+            put32(h, (uint32_t)s.size());
+            h.insert(h.end(), s.begin(), s.end());
+            for (size_t q = s.size(); q & 3; q++) h.push_back(0);
+        }
+        std::vector<uint8_t> ix;
+        IndexState st = { (int64_t)opts->block_reads, 0, 0, 0, 0, 0, 0 };
+        for (uint64_t k = 0; k < nb; k++) index_put(ix, st, ctx->hblocks[k]);
+        put32(h, (uint32_t)ix.size());
+        h.insert(h.end(), ix.begin(), ix.end());
+    }
+    ctx->enc_L = L; ctx->enc_block_reads = opts->block_reads; ctx->enc_gen_mode = opts->gen_mode; ctx->enc_legacy = legacy;
+    ctx->enc_max_len = ctx->db.max_len; ctx->enc_fixed = fixed ? 1u : 0u;
+    ctx->enc_n_reads = n; ctx->enc_n_edits = n_edits; ctx->enc_n_blocks = nb; ctx->enc_payload_bytes = payload_total;
+    ctx->have_encoded = true;
+    S.n_reads = n; S.n_blocks = nb; S.n_edits = n_edits; S.n_symbols = n_syms;
+    S.payload_bytes = payload_total; S.container_bytes = h.size() + payload_total;
+}
+
 /* ------------------------------------------------------------------------------------------------ encode */
 extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts) {
     if (!ctx) return CBCG_ERR_ARG;
@@ -560,14 +662,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     const uint32_t L = opts->read_len_header;
     cbcg_encode_opts auto_opts = *opts;
     if (opts->block_reads == CBCG_BLOCK_AUTO) {             /* last generation = a whole number of full waves */
-        static const uint32_t sc[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sr[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
-        uint64_t early = 0;
-        if (opts->gen_mode) for (uint32_t g = 0; g < CBCG_GEN_LEVELS; g++) early += (uint64_t)sc[g] * sr[g];
-        const uint64_t main_reads = n > early ? n - early : n;
-        const uint64_t slots = coder_resident_blocks(ctx->device);
-        const uint64_t waves = std::max<uint64_t>(1, (main_reads + slots * CBCG_BLOCK_AUTO_MAX - 1) / (slots * CBCG_BLOCK_AUTO_MAX));
-        uint64_t r = (main_reads + waves * slots - 1) / (waves * slots);
-        auto_opts.block_reads = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(r, 64), CBCG_BLOCK_AUTO_MAX);
+        auto_opts.block_reads = auto_block_reads(ctx, n, opts->gen_mode);
         opts = &auto_opts;
     }
     ctx->have_encoded = false;
@@ -628,32 +723,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     cudaEventElapsedTime(&S.ms_gather, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&S.ms_total, ctx->ev[0], ctx->ev[4]);
 
-    /* container header + index (layout: DESIGN.md, "Container") */
-    std::vector<uint8_t> &h = ctx->enc_head;
-    h.clear();
-    uint64_t n_syms = 0;
-    for (uint64_t k = 0; k < nb; k++) n_syms += ctx->hblocks[k].n_symbols;
-    if (!legacy) {
-        put32(h, CBCG_MAGIC); put32(h, CBCG_VERSION); put32(h, ctx->db.max_len); put32(h, L);
-        put64(h, n); put32(h, (uint32_t)nb); put32(h, ctx->dg.n_chr); put32(h, opts->block_reads); put32(h, opts->gen_mode | (fixed ? CBCG_MODE_FIXED_LEN : 0u));
-        for (uint32_t c = 0; c < ctx->dg.n_chr; c++) {
-            const std::string &s = ctx->names[c];
-            put32(h, (uint32_t)s.size());
-            h.insert(h.end(), s.begin(), s.end());
-            for (size_t q = s.size(); q & 3; q++) h.push_back(0);
-        }
-        std::vector<uint8_t> ix;
-        IndexState st = { (int64_t)opts->block_reads, 0, 0, 0, 0, 0, 0 };
-        for (uint64_t k = 0; k < nb; k++) index_put(ix, st, ctx->hblocks[k]);
-        put32(h, (uint32_t)ix.size());
-        h.insert(h.end(), ix.begin(), ix.end());
-    }
-    ctx->enc_L = L; ctx->enc_block_reads = opts->block_reads; ctx->enc_gen_mode = opts->gen_mode; ctx->enc_legacy = legacy;
-    ctx->enc_max_len = ctx->db.max_len; ctx->enc_fixed = fixed ? 1u : 0u;
-    ctx->enc_n_reads = n; ctx->enc_n_edits = n_edits; ctx->enc_n_blocks = nb; ctx->enc_payload_bytes = payload_total;
-    ctx->have_encoded = true;
-    S.n_reads = n; S.n_blocks = nb; S.n_edits = n_edits; S.n_symbols = n_syms;
-    S.payload_bytes = payload_total; S.container_bytes = h.size() + payload_total;
+    finish_encode(ctx, opts, legacy, fixed, n, n_edits, nb, payload_total);
     return CBCG_OK;
 }
 
@@ -697,10 +767,210 @@ extern "C" uint64_t cbcg_encode_bound(const cbcg_batch *b, const cbcg_encode_opt
     return 4096 + (uint64_t)MAX_CHR * 16 + nb * 32 + n * 16 + bases;
 }
 
+/* ------------------------------------------------------------------------------------------------ pipelined encode
+ * cbcg_encode on a large batch with automatic block size: the batch crosses PCIe in chunks of whole K1 tiles on a copy
+ * stream; K1 and the block plan follow chunk by chunk, the early generations are coded while the rest of the batch is
+ * still on the link, and the last generation is launched group by group (one side stream each) as its reads arrive.
+ * Last-generation blocks shrink towards the end of the batch (the ramp), so that the blocks whose reads arrive last are
+ * the ones that take least time: all groups end together shortly after the last byte has landed. The same layout lets
+ * cbcg_decode start returning text while the large blocks are still being decoded. The cut is recorded in the
+ * container's index like any other; the coded bits of a block depend only on its reads and its generation. */
+#define PIPE_FALLBACK 1            /* not an error: the caller takes the one-stream path */
+static uint64_t pipe_min_reads() {
+    const char *e = getenv("CBCG_PIPE_MIN_READS");
+    return e ? strtoull(e, nullptr, 10) : (1ull << 20);
+}
+static void pipe_ramp(double *hi, double *lo) {
+    *hi = 1.85; *lo = 0.45;
+    const char *e = getenv("CBCG_PIPE_RAMP");               /* "hi,lo" multipliers of the mean block size (tuning) */
+    if (e) { double a = 0, b = 0; if (sscanf(e, "%lf,%lf", &a, &b) == 2 && a >= b && b > 0.05 && a < 8.0) { *hi = a; *lo = b; } }
+}
+static int pipe_init(cbcg_ctx *ctx) {
+    if (ctx->pipe_ready) return 0;
+    CU(cudaStreamCreateWithFlags(&ctx->cs, cudaStreamNonBlocking));
+    for (auto &s : ctx->ps) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto &e : ctx->cev) CU(cudaEventCreate(&e));
+    for (auto &e : ctx->kev2) CU(cudaEventCreate(&e));
+    for (auto &e : ctx->dev2) CU(cudaEventCreate(&e));
+    ctx->pipe_ready = true;
+    return 0;
+}
+#define PIPE_CHUNKS 5u             /* tail chunks (after the head that feeds the early generations); <= PIPE_MAX - 1 */
+
+static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encode_opts *opts) {
+    static const uint32_t sc[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sr[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
+    const uint64_t n = b->n_reads;
+    const uint32_t L = opts->read_len_header;
+    const uint64_t tile = 128;                              /* K1 tile: chunk boundaries are whole tiles */
+    uint64_t early = 0;
+    for (uint32_t g = 0; g < CBCG_GEN_LEVELS; g++) early += (uint64_t)sc[g] * sr[g];
+    if (n < early + tile * (PIPE_CHUNKS + 1)) return PIPE_FALLBACK;
+    TRY(pipe_init(ctx));
+    TRY(batch_prepare(ctx, b));
+    cbcg_stats &S = ctx->stats;
+
+    /* chunks: [0] = the head (early generations + one tile, so that the record after the last early block exists),
+       [1..PIPE_CHUNKS] = the tail in equal parts */
+    uint64_t cut[PIPE_CHUNKS + 2];
+    const uint64_t head_end = ((early + tile - 1) / tile + 1) * tile;
+    cut[0] = 0; cut[1] = head_end;
+    for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) cut[c + 1] = c == PIPE_CHUNKS ? n : head_end + ((n - head_end) * c / PIPE_CHUNKS) / tile * tile;
+    CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    CU(cudaStreamWaitEvent(ctx->cs, ctx->ev[0], 0));        /* copies start after whatever the caller left on the main stream */
+    uint64_t h2d = 0;
+    for (uint32_t c = 0; c <= PIPE_CHUNKS; c++) {
+        TRY(batch_copy_range(ctx, b, cut[c], cut[c + 1], ctx->cs, &h2d));
+        CU(cudaEventRecord(ctx->cev[c], ctx->cs));
+    }
+    batch_scan(ctx, b);                                     /* while the copies fly */
+    const bool fixed = ctx->batch_min_len == L && ctx->db.max_len == L;
+    if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
+
+    /* the cut: early generations on their schedule, then the ramp */
+    uint64_t slots = 0;
+    cbcg_encode_opts used = *opts;
+    used.block_reads = auto_block_reads(ctx, n, 1, &slots);
+    double hi, lo; pipe_ramp(&hi, &lo);
+    std::vector<SizeStep> ramp;
+    double mult[PIPE_CHUNKS], inv = 0;
+    for (uint32_t c = 0; c < PIPE_CHUNKS; c++) { mult[c] = hi - (hi - lo) * (double)c / (double)(PIPE_CHUNKS - 1); inv += 1.0 / mult[c]; }
+    inv /= PIPE_CHUNKS;                                     /* > 1: more blocks than resident slots, the last ones would queue */
+    for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) {
+        const double m = mult[c - 1] * (inv > 1.0 ? inv : 1.0);
+        ramp.push_back({ cut[c + 1], (uint32_t)std::max(64.0, std::min(2.0 * CBCG_BLOCK_AUTO_MAX, m * used.block_reads)) });
+    }
+    uint64_t nb = 0;
+    TRY(cut_blocks(ctx, used.block_reads, 1, &nb, &ramp, false));
+    if (ctx->gens.size() != CBCG_GEN_LEVELS + 1) return PIPE_FALLBACK;   /* chromosome runs too short for the schedule */
+    const BlockDesc *hb = ctx->hblocks;
+    const uint32_t last_first = ctx->gens.back().first, last_n = ctx->gens.back().second;
+    if ((uint64_t)hb[last_first].first_read + tile > head_end) return PIPE_FALLBACK;
+    /* groups of last-generation blocks: group c = the blocks that end inside chunk c + 1 or before (not yet taken) */
+    uint32_t gb[PIPE_CHUNKS + 1]; gb[0] = last_first;
+    {
+        uint32_t k = last_first;
+        for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) {
+            while (k < last_first + last_n && (uint64_t)hb[k].first_read + hb[k].n_reads <= cut[c + 1]) k++;
+            gb[c] = k;
+        }
+        if (gb[PIPE_CHUNKS] != last_first + last_n) return fail(ctx, CBCG_ERR_INTERNAL, "pipelined encode: block groups do not cover the cut");
+    }
+
+    /* buffers (sized from bounds: no host round trip between the stages) */
+    const uint64_t edits_cap_guess = ctx->total_bases / 16 + 4096;
+    TRY(ensure(ctx, ctx->recs, (n + 1) * sizeof(cbcg_read_rec)));
+    TRY(ensure(ctx, ctx->tile_desc, ((n + tile - 1) / tile + 1) * 8));
+    if (ctx->edits.cap / 2 < edits_cap_guess) TRY(ensure(ctx, ctx->edits, edits_cap_guess * 2));
+    const uint64_t edits_cap = ctx->edits.cap / 2;
+    uint64_t ws_cap = 0, pay_cap = 0;                       /* sized once the head chunk has told the edit density */
+    TRY(ensure(ctx, ctx->out_off, (nb + 1) * 8));
+    TRY(ensure(ctx, ctx->blocks, (nb + 1) * sizeof(BlockDesc)));
+    S.ms_extract = S.ms_plan = S.ms_code = S.ms_gather = S.ms_reconstruct = S.ms_d2h = S.ms_total = S.ms_k1 = S.ms_k3 = 0;
+    S.kernel_launches = 0; S.d2h_bytes = 0;
+
+    TRY(reset_words(ctx));
+    /* the descriptors are read from pinned host memory by a kernel: a cudaMemcpyAsync would queue on the host -> device
+       copy engine behind every chunk enqueued above */
+    if (launch_copy16(ctx->blocks.p, hb, nb * sizeof(BlockDesc), ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "descriptor copy launch failed");
+    CoderParams p = coder_params(ctx, (uint32_t)nb, L, 0, 0);
+    p.chr = const_cast<uint32_t *>(ctx->db.chr);
+    p.payload = ctx->scratch.as<uint8_t>();
+    p.lean = 1u; p.short_flush = 1u; p.primed = 1u; p.fixed_len = fixed ? 1u : 0u;
+    uint64_t *chain = wptr<uint64_t>(ctx, W_OFF(chain));
+    uint64_t *totals = wptr<uint64_t>(ctx, W_OFF(totals));
+    uint8_t *snap = nullptr;
+    uint64_t tile_off = 0;
+    for (uint32_t c = 0; c <= PIPE_CHUNKS; c++) {
+        CU(cudaStreamWaitEvent(ctx->st, ctx->cev[c], 0));
+        /* K1 on the chunk; its edit entries continue the previous chunk's */
+        if (launch_extract(ctx->db, ctx->dg, ctx->recs.as<cbcg_read_rec>(), ctx->edits.as<uint16_t>(), edits_cap,
+                           ctx->tile_desc.as<uint64_t>() + tile_off, wptr<uint32_t>(ctx, W_OFF(ticket)), &chain[(c + 1u) & 1u],
+                           wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st, nullptr, nullptr, cut[c], cut[c + 1],
+                           c ? &chain[c & 1u] : nullptr))
+            return fail(ctx, CBCG_ERR_CUDA, "K1 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        tile_off += (cut[c + 1] - cut[c] + tile - 1) / tile;
+        S.kernel_launches++;
+        if (c == 0) {
+            /* the model workspace is bounded by the number of edit entries: project it from the head's (the one host
+               round trip of the pipeline; the copies go on meanwhile). Too small a projection shows up as a device
+               error and the call falls back to the one-stream path. */
+            CU(cudaMemcpyAsync(&ctx->hw->total_edits, &chain[1], 8, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaStreamSynchronize(ctx->st));
+            const uint64_t proj = std::min<uint64_t>(edits_cap, (uint64_t)((double)ctx->hw->total_edits * ((double)n / (double)head_end) * 1.5) + 65536u);
+            ws_cap = coder_ws_bytes_bound(L, n, proj, nb, 0, 1);
+            pay_cap = coder_payload_bound(n, proj, nb, 0);
+            TRY(ensure(ctx, ctx->ws, ws_cap)); TRY(ensure(ctx, ctx->scratch, pay_cap)); TRY(ensure(ctx, ctx->payload, pay_cap));
+            p.ws = ctx->ws.as<uint8_t>(); p.payload = ctx->scratch.as<uint8_t>();
+        }
+        /* plan of the blocks that are now complete */
+        CoderParams q = p;
+        q.block_begin = c ? gb[c - 1] : 0u; q.n_blocks = c ? gb[c] - gb[c - 1] : last_first;
+        if (q.n_blocks) {
+            if (launch_plan(q, (uint32_t)cut[c + 1], 0, ws_cap, pay_cap, totals, ctx->st, c ? totals : nullptr, &chain[(c + 1u) & 1u]))
+                return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
+            S.kernel_launches++;
+        }
+        if (c == 0) {                                        /* generations 0 .. 3 while the tail is on the link */
+            TRY(run_early_generations(ctx, p, &snap));
+        } else if (q.n_blocks) {
+            CU(cudaEventRecord(ctx->kev2[c], ctx->st));
+            cudaStream_t sd = ctx->ps[c % PIPE_MAX];
+            CU(cudaStreamWaitEvent(sd, ctx->kev2[c], 0));
+            q.snap = snap; q.fin = nullptr;
+            if (launch_coder(q, sd)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            S.kernel_launches++;
+            CU(cudaEventRecord(ctx->dev2[c], sd));
+        }
+    }
+    for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) if (gb[c] > gb[c - 1]) CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[c], 0));
+    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->st))
+        return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
+    S.kernel_launches += 2;
+    CU(cudaEventRecord(ctx->ev[4], ctx->st));
+    CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&ctx->hw->total_bytes, ctx->out_off.as<uint64_t>() + nb, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&ctx->hw->total_edits, &chain[(PIPE_CHUNKS + 1u) & 1u], 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&ctx->hw->err, wptr<unsigned long long>(ctx, W_OFF(err)), 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->have_batch = true;
+    if (getenv("CBCG_PIPE_TRACE")) {                        /* when each chunk landed, was extracted and planned, and was coded */
+        for (uint32_t c = 0; c <= PIPE_CHUNKS; c++) {
+            float a = 0, k = 0, d = 0;
+            cudaEventElapsedTime(&a, ctx->ev[0], ctx->cev[c]);
+            if (c && gb[c] > gb[c - 1]) { cudaEventElapsedTime(&k, ctx->ev[0], ctx->kev2[c]); cudaEventElapsedTime(&d, ctx->ev[0], ctx->dev2[c]); }
+            fprintf(stderr, "[cbcg pipe enc] chunk %u reads %llu..%llu blocks %u size %u: copied %.2f ms, planned %.2f ms, coded %.2f ms\n", c,
+                    (unsigned long long)cut[c], (unsigned long long)cut[c + 1], c ? gb[c] - gb[c - 1] : last_first,
+                    c ? ramp[c - 1].block_reads : 0u, a, k, d);
+        }
+        float t = 0; cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[4]); fprintf(stderr, "[cbcg pipe enc] gathered %.2f ms\n", t);
+    }
+    S.h2d_bytes = h2d; S.d2h_bytes = nb * sizeof(BlockDesc) + 24;
+    cudaEventElapsedTime(&S.ms_total, ctx->ev[0], ctx->ev[4]);
+    if (ctx->hw->err) {
+        const int code = -(int)(ctx->hw->err >> 40);
+        /* edit array or workspace guessed too small: the batch is resident now, take the one-stream path */
+        if (code == CBCG_ERR_CAPACITY || code == CBCG_ERR_INTERNAL) return PIPE_FALLBACK;
+        return device_error(ctx, "pipelined encode");
+    }
+    finish_encode(ctx, &used, 0, fixed, n, ctx->hw->total_edits, nb, ctx->hw->total_bytes);
+    return CBCG_OK;
+}
+
 extern "C" int cbcg_encode(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_encode_opts *opts,
                            uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
     if (!ctx || !out_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_encode: bad argument");
     TRY(validate_opts(ctx, opts));
+    if (opts->block_reads == CBCG_BLOCK_AUTO && opts->gen_mode == 1 && batch && batch->n_reads >= pipe_min_reads()) {
+        TRY(check_batch(ctx, batch));
+        CU(cudaSetDevice(ctx->device));
+        const int rc = encode_pipelined(ctx, batch, opts);
+        if (rc < 0) return rc;
+        if (rc == CBCG_OK) return cbcg_fetch_container(ctx, out, out_cap, out_len);
+        if (ctx->have_batch) {                              /* fallback with the batch already resident */
+            TRY(cbcg_encode_resident(ctx, opts));
+            return cbcg_fetch_container(ctx, out, out_cap, out_len);
+        }
+    }
     TRY(cbcg_batch_upload(ctx, batch));
     const float ms_h2d = ctx->stats.ms_h2d; const uint64_t h2d = ctx->stats.h2d_bytes;
     TRY(cbcg_encode_resident(ctx, opts));
@@ -936,11 +1206,128 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------ pipelined decode
+ * cbcg_decode of a large container of equal-length reads: the last generation is decoded group by group on side
+ * streams, each group followed by its own K3 launch and its own device -> host copy (output offsets are closed-form),
+ * so text is on the PCIe link while other groups are still being decoded. Containers written by the pipelined encoder
+ * have their small blocks at the end of the batch: those groups finish first. */
+static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, uint8_t *seq_out, uint64_t seq_cap,
+                            uint64_t *seq_len, uint64_t *n_reads) {
+    Container c;
+    if (parse_container(in, in_len, &ctx->names, c)) return PIPE_FALLBACK;         /* the one-stream path reports it */
+    if (!c.fixed_len || c.gen_mode != 1 || c.n_reads < pipe_min_reads() || !ctx->dg.n_chr || !seq_out) return PIPE_FALLBACK;
+    const uint64_t line = (uint64_t)c.L + 1u, bytes = c.n_reads * line;
+    if (bytes > seq_cap) return PIPE_FALLBACK;
+    TRY(pipe_init(ctx));
+    ctx->have_decoded = false;
+    cbcg_stats &S = ctx->stats;
+    S = cbcg_stats();
+    uint64_t nr = 0, ne = 0, pb = 0;
+    TRY(blocks_from_index(ctx, in, in_len, c, &nr, &ne, &pb));
+    if (ctx->gens.size() < 2) return PIPE_FALLBACK;
+    const uint32_t nb = c.n_blocks;
+    BlockDesc *hb = ctx->hblocks;
+    const uint32_t last_first = ctx->gens.back().first, last_n = ctx->gens.back().second;
+    uint64_t early_reads = 0;
+    for (uint32_t k = 0; k < last_first; k++) early_reads += hb[k].n_reads;
+    /* groups of last-generation blocks with about equal read counts */
+    uint32_t gb[PIPE_CHUNKS + 1]; uint64_t gr[PIPE_CHUNKS + 1];
+    gb[0] = last_first; gr[0] = early_reads;
+    {
+        uint32_t k = last_first; uint64_t r = early_reads;
+        for (uint32_t g = 1; g <= PIPE_CHUNKS; g++) {
+            const uint64_t want = early_reads + (nr - early_reads) * g / PIPE_CHUNKS;
+            while (k < last_first + last_n && (r < want || g == PIPE_CHUNKS)) r += hb[k++].n_reads;
+            gb[g] = k; gr[g] = r;
+        }
+    }
+    TRY(ensure(ctx, ctx->payload, pb + 64));
+    TRY(ensure(ctx, ctx->blocks, ((uint64_t)nb + 1) * sizeof(BlockDesc)));
+    TRY(ensure(ctx, ctx->recs, (nr + 1) * sizeof(cbcg_read_rec)));
+    TRY(ensure(ctx, ctx->chr_out, (nr + 1) * 4));
+    TRY(ensure(ctx, ctx->edits, (ne + 64) * 2));
+    const uint64_t ws_cap = coder_ws_bytes_bound(c.L, nr, ne, nb, 0, 1);
+    TRY(ensure(ctx, ctx->ws, ws_cap));
+    TRY(ensure(ctx, ctx->seq_out, bytes + 64));
+    TRY(ensure(ctx, ctx->tile_desc, (reconstruct_num_tiles(nr) + 1) * 8));
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    if (pb) CU(cudaMemcpyAsync(ctx->payload.p, in + c.payload_off, pb, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->blocks.p, hb, (uint64_t)nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
+    TRY(reset_words(ctx));
+    CoderParams p = coder_params(ctx, nb, c.L, 0, 1);
+    p.chr = ctx->chr_out.as<uint32_t>();
+    p.payload = ctx->payload.as<uint8_t>();
+    p.lean = 1u; p.short_flush = 1u; p.primed = 1u; p.fixed_len = 1u;
+    if (launch_plan(p, (uint32_t)nr, ne, ws_cap, ~0ull, wptr<uint64_t>(ctx, W_OFF(totals)), ctx->st))
+        return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
+    S.kernel_launches++;
+    uint8_t *snap = nullptr;
+    TRY(run_early_generations(ctx, p, &snap));
+    for (uint32_t g = 0; g <= PIPE_CHUNKS; g++) {            /* g = 0: the reads of the early generations */
+        const uint64_t r0 = g ? gr[g - 1] : 0, r1 = g ? gr[g] : early_reads;
+        /* the early generations' reads are rebuilt on the main stream BEFORE the last generation is launched: once its
+           CTAs hold every SM, a K3 CTA finds room only when one of them retires */
+        cudaStream_t sd = g ? ctx->ps[g % PIPE_MAX] : ctx->st;
+        if (g) CU(cudaStreamWaitEvent(sd, ctx->kev2[0], 0));
+        if (g && gb[g] > gb[g - 1]) {
+            CoderParams q = p;
+            q.block_begin = gb[g - 1]; q.n_blocks = gb[g] - gb[g - 1]; q.snap = snap; q.fin = nullptr;
+            if (launch_coder(q, sd)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            S.kernel_launches++;
+        }
+        if (r1 > r0) {
+            if (launch_reconstruct(r1 - r0, ctx->recs.as<cbcg_read_rec>() + r0, ctx->chr_out.as<uint32_t>() + r0, ctx->edits.as<uint16_t>(),
+                                   ctx->dg, ctx->seq_out.as<uint8_t>() + r0 * line, (r1 - r0) * line, c.L, c.L, ctx->tile_desc.as<uint64_t>(),
+                                   wptr<uint32_t>(ctx, W_OFF(ticket)), wptr<uint64_t>(ctx, W_OFF(total_bytes)),
+                                   wptr<unsigned long long>(ctx, W_OFF(err)), sd, nullptr, nullptr))
+                return fail(ctx, CBCG_ERR_CUDA, "K3 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            S.kernel_launches++;
+            if (!g) {                                        /* its copy rides a side stream; the groups start behind the K3 launch */
+                CU(cudaEventRecord(ctx->kev2[0], ctx->st));
+                sd = ctx->ps[0];
+                CU(cudaStreamWaitEvent(sd, ctx->kev2[0], 0));
+            }
+            CU(cudaMemcpyAsync(seq_out + r0 * line, ctx->seq_out.as<uint8_t>() + r0 * line, (r1 - r0) * line, cudaMemcpyDeviceToHost, sd));
+        } else if (!g) CU(cudaEventRecord(ctx->kev2[0], ctx->st));
+        CU(cudaEventRecord(ctx->dev2[g], sd));
+    }
+    for (uint32_t g = 0; g <= PIPE_CHUNKS; g++) CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[g], 0));
+    CU(cudaEventRecord(ctx->ev[1], ctx->st));
+    CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, (uint64_t)nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
+    TRY(fetch_words(ctx));
+    TRY(device_error(ctx, "pipelined decode"));
+    uint64_t got_r = 0, got_e = 0;
+    for (uint32_t k = 0; k < nb; k++) { got_r += hb[k].n_reads; got_e += hb[k].n_edits; }
+    if (got_r != nr) return fail(ctx, CBCG_ERR_CORRUPT, "decoded %llu reads, the index says %llu", (unsigned long long)got_r, (unsigned long long)nr);
+    cudaEventElapsedTime(&S.ms_total, ctx->ev[0], ctx->ev[1]);
+    if (getenv("CBCG_PIPE_TRACE")) {
+        float t0 = 0; cudaEventElapsedTime(&t0, ctx->ev[0], ctx->kev2[0]);
+        fprintf(stderr, "[cbcg pipe dec] early generations done %.2f ms\n", t0);
+        for (uint32_t g = 0; g <= PIPE_CHUNKS; g++) {
+            float d = 0; cudaEventElapsedTime(&d, ctx->ev[0], ctx->dev2[g]);
+            fprintf(stderr, "[cbcg pipe dec] group %u blocks %u reads %llu: text on the host %.2f ms\n", g, g ? gb[g] - gb[g - 1] : last_first,
+                    (unsigned long long)(g ? gr[g] - gr[g - 1] : early_reads), d);
+        }
+        fprintf(stderr, "[cbcg pipe dec] all %.2f ms\n", S.ms_total);
+    }
+    S.h2d_bytes = pb + (uint64_t)nb * sizeof(BlockDesc); S.d2h_bytes = bytes;
+    S.n_reads = nr; S.n_edits = got_e; S.n_blocks = nb;
+    *seq_len = bytes; if (n_reads) *n_reads = nr;
+    ctx->dec_bytes = bytes; ctx->dec_n_reads = nr; ctx->have_decoded = true;
+    return CBCG_OK;
+}
+
 extern "C" int cbcg_decode(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy,
                            uint8_t *seq_out, uint64_t seq_cap, uint64_t *seq_len, uint64_t *n_reads) {
     if (!ctx || !seq_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_decode: bad argument");
     uint64_t nr = 0, ne = 0; uint32_t max_len = 1, fixed_len = 0;
     *seq_len = 0; if (n_reads) *n_reads = 0;
+    if (!legacy) {
+        CU(cudaSetDevice(ctx->device));
+        const int rc = decode_pipelined(ctx, in, in_len, seq_out, seq_cap, seq_len, n_reads);
+        if (rc != PIPE_FALLBACK) return rc;
+    }
     TRY(decode_to_records(ctx, in, in_len, legacy, &nr, &ne, &max_len, &fixed_len));
     if (n_reads) *n_reads = nr;
     if (!nr) return CBCG_OK;

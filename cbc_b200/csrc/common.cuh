@@ -126,7 +126,12 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *desc, uint32_t 
         int64_t idx = j - (int64_t)lane;
         uint64_t d = (idx >= 0) ? ld_volatile_u64(&desc[idx]) : LB_PFX;
         uint32_t spins = 0;
-        while (__any_sync(FULL_MASK, (d >> 62) == 0)) {
+        /* only the tiles between this one and the nearest published prefix matter: wait for those, not for all 32 */
+        for (;;) {
+            const uint32_t inv = __ballot_sync(FULL_MASK, (d >> 62) == 0);
+            const uint32_t pfx = __ballot_sync(FULL_MASK, (d >> 62) == 2);
+            const uint32_t upto = pfx ? ((2u << ((uint32_t)__ffs(pfx) - 1u)) - 1u) : 0xffffffffu;   /* lanes 0..first prefix */
+            if (!(inv & upto)) break;
             if ((d >> 62) == 0) d = ld_volatile_u64(&desc[idx]);
             if (++spins > (1u << 24)) {            /* never expected: bail out loudly instead of hanging */
                 if (lane == 0) dev_set_error(err, CBCG_ERR_INTERNAL, tile);

@@ -82,7 +82,8 @@ struct CoderParams {
 /* Host-callable launchers (defined in the .cu files). */
 int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, uint16_t *edits,
                    uint64_t edits_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_edits,
-                   unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop);
+                   unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop,
+                   uint64_t r_begin = 0, uint64_t r_end = ~0ull, const uint64_t *edit_base = nullptr);
 int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr, const uint16_t *edits,
                        const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len, uint32_t fixed_len,
                        uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
@@ -90,7 +91,8 @@ int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32
 uint64_t extract_num_tiles(uint64_t n_reads);
 uint64_t reconstruct_num_tiles(uint64_t n_reads);
 int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap,
-                uint64_t payload_cap, uint64_t *totals, cudaStream_t st);
+                uint64_t payload_cap, uint64_t *totals, cudaStream_t st,
+                const uint64_t *carry_in = nullptr, const uint64_t *n_edits_dev = nullptr);
 int launch_coder(const CoderParams &p, cudaStream_t st);
 uint32_t coder_resident_blocks(int device);     /* blocks (warps) of the encode kernel the whole GPU holds at once */
 int launch_gather(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
@@ -102,4 +104,6 @@ uint64_t fin_stride_bytes(void);
 int launch_snapshot_init(uint8_t *snap, uint32_t L, cudaStream_t st);
 int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_blocks, uint32_t L, const uint8_t *prev,
                  uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, cudaStream_t st);
+int cbcg_carveout_percent(void);               /* shared-memory carveout every kernel asks for */
+int launch_copy16(void *dst, const void *src, uint64_t bytes, cudaStream_t st);
 uint64_t coder_payload_bound(uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy);

@@ -190,7 +190,7 @@ struct K1Smem {
 __global__ void __launch_bounds__(K1_TILE)
 k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uint16_t *__restrict__ edits,
                   uint64_t edits_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_edits,
-                  unsigned long long *err, uint32_t seq_cap) {
+                  unsigned long long *err, uint32_t seq_cap, uint64_t r_begin, uint64_t r_end, const uint64_t *edit_base) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     K1Smem &S = *reinterpret_cast<K1Smem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -202,15 +202,17 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
     }
     __syncthreads();
     const uint32_t tile = S.tile;
-    const uint64_t r0 = (uint64_t)tile * K1_TILE;
-    const uint32_t nr = (uint32_t)min((uint64_t)K1_TILE, b.n_reads - r0);
+    /* this launch extracts reads [r_begin, r_end): the whole batch, or one chunk of it while the next chunk is still on
+       the PCIe link (api.cu); a chunk's edit entries start where the previous chunk's ended (*edit_base). */
+    const uint64_t r0 = r_begin + (uint64_t)tile * K1_TILE;
+    const uint32_t nr = (uint32_t)min((uint64_t)K1_TILE, r_end - r0);
 
     /* tile geometry (uniform): SEQ byte range and reference window */
     const uint64_t s0 = b.seq_off[r0], s1 = b.seq_off[r0 + nr];
     const uint64_t a0 = s0 & ~15ull;
     const uint64_t seq_bytes = (s1 - a0 + 15ull) & ~15ull;
     const bool seq_ok = (s1 >= s0) && (seq_bytes <= seq_cap);
-    const uint32_t chr0 = b.chr[r0], pos0 = b.pos[r0];
+    const uint32_t chr0 = b.chr[r0], pos0 = b.pos[r0], chr_l = b.chr[r0 + nr - 1u], pos_l = b.pos[r0 + nr - 1u];
     uint64_t w0 = 0; uint32_t ref_bytes = 0; uint64_t clen0 = 0;
     const uint8_t *ref0 = nullptr;
     if (chr0 < g.n_chr) {
@@ -219,6 +221,11 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
         w0 = pos0 ? ((uint64_t)(pos0 - 1u) & ~15ull) : 0ull;
         uint64_t avail = (clen0 + REF_PAD > w0) ? ((clen0 + REF_PAD - w0) & ~15ull) : 0ull;
         ref_bytes = (uint32_t)min((uint64_t)K1_REF_CAP, avail);
+        /* position-sorted input: the tile's last read bounds the window (a read beyond it takes the HBM path) */
+        if (chr_l == chr0 && pos_l >= pos0 && pos0) {
+            const uint64_t need = ((uint64_t)(pos_l - 1u) - w0 + b.max_len + 8u + 15u) & ~15ull;
+            if (need < ref_bytes) ref_bytes = (uint32_t)need;
+        }
     }
     if (tid == 0) {
         uint32_t tx = (seq_ok ? (uint32_t)seq_bytes : 0u) + ref_bytes;
@@ -309,10 +316,10 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
     const uint32_t my_excl = warp_base + incl - my_total;
 
     if (warp == 0) {
-        uint64_t base = lookback_exclusive(tile_desc, tile, tile_total, err);
+        uint64_t base = lookback_exclusive(tile_desc, tile, tile_total, err) + (edit_base ? *edit_base : 0ull);
         if (lane == 0) {
             S.tile_base = base;
-            if (r0 + nr == b.n_reads) *total_edits = base + tile_total;
+            if (r0 + nr == r_end) *total_edits = base + tile_total;
         }
     }
     __syncthreads();
@@ -346,21 +353,24 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
 
 int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, uint16_t *edits,
                    uint64_t edits_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_edits,
-                   unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop) {
-    if (b.n_reads == 0) return 0;
-    const uint64_t tiles = extract_num_tiles(b.n_reads);
+                   unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop,
+                   uint64_t r_begin, uint64_t r_end, const uint64_t *edit_base) {
+    if (r_end > b.n_reads) r_end = b.n_reads;
+    if (r_begin >= r_end) return 0;
+    const uint64_t tiles = extract_num_tiles(r_end - r_begin);
     const uint32_t seq_cap = (K1_TILE * b.max_len + 48u) & ~15u;
     const size_t smem = sizeof(K1Smem) + seq_cap + 16;
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(k1_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        cudaFuncSetAttribute(k1_extract_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cbcg_carveout_percent());   /* see k2_coder.cu */
         configured = smem;
     }
     if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;
     if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;
     if (ev_start) cudaEventRecord(ev_start, st);
     k1_extract_kernel<<<(unsigned)tiles, K1_TILE, smem, st>>>(b, g, recs, edits, edits_cap, tile_desc, ticket,
-                                                             total_edits, err, seq_cap);
+                                                             total_edits, err, seq_cap, r_begin, r_end, edit_base);
     if (ev_stop) cudaEventRecord(ev_stop, st);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

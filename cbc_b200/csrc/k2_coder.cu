@@ -32,6 +32,7 @@
  * The coder is latency-bound integer work, not HBM-bound: throughput comes from the number of
  * resident warps (blocks), see DESIGN.md.
  */
+#include <algorithm>
 #include "common.cuh"
 #include "internal.h"
 #include "ac_core.h"
@@ -864,6 +865,7 @@ k2_coder_kernel(CoderParams P) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t bl = blockIdx.x * K2_WARPS + warp;
     if (bl >= P.n_blocks) return;
+    if (*reinterpret_cast<volatile unsigned long long *>(P.err)) return;   /* an earlier stage failed (e.g. the plan ran out of workspace): offsets may be out of range */
     const uint32_t b = P.block_begin + bl;
     BlockDesc &B = P.blocks[b];
     constexpr bool legacy = LEGACY;                     /* single-block mode is its own instantiation: its header, RNAME and
@@ -1269,8 +1271,41 @@ uint32_t coder_resident_blocks(int device) {
     return (uint32_t)sms * (uint32_t)per_sm * K2_WARPS;
 }
 
+__global__ void k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap, uint64_t payload_cap,
+                               uint64_t *totals, const uint64_t *carry_in, const uint64_t *n_edits_dev);
+__global__ void k2_payload_scan_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off);
+__global__ void k2_gather_kernel(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out, const uint64_t *out_off);
+__global__ void snapshot_init_kernel(uint8_t *snap, uint32_t L);
+__global__ void snapshot_copy_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint64_t n16);
+struct MergeParams;
+__global__ void merge_prep_kernel(MergeParams P);
+__global__ void merge_add_kernel(MergeParams P);
+__global__ void merge_finish_kernel(MergeParams P);
+__global__ void merge_var_finish_kernel(MergeParams P);
+
+/* One shared-memory carveout for every kernel of the library: an SM cannot host CTAs of kernels that ask for different
+ * L1 / shared-memory splits at the same time, so K1 / K3 launches of a pipelined call (api.cu) would otherwise wait for
+ * the resident block-coder CTAs to drain before they get an SM. */
+int cbcg_carveout_percent(void) {
+    static int pct = -1;
+    if (pct < 0) { const char *e = getenv("CBCG_CARVEOUT"); pct = e ? atoi(e) : 100; if (pct < 0 || pct > 100) pct = 100; }
+    return pct;
+}
+template <class K> static void set_carveout(K kernel) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cbcg_carveout_percent()); }
+static void coder_carveouts() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    set_carveout(k2_coder_kernel<MODE_ENC, false>); set_carveout(k2_coder_kernel<MODE_DEC, false>); set_carveout(k2_coder_kernel<MODE_LIST, false>);
+    set_carveout(k2_coder_kernel<MODE_ENC, true>); set_carveout(k2_coder_kernel<MODE_DEC, true>); set_carveout(k2_coder_kernel<MODE_LIST, true>);
+    set_carveout(k2_plan_kernel); set_carveout(k2_payload_scan_kernel); set_carveout(k2_gather_kernel);
+    set_carveout(snapshot_init_kernel); set_carveout(snapshot_copy_kernel);
+    set_carveout(merge_prep_kernel); set_carveout(merge_add_kernel); set_carveout(merge_finish_kernel); set_carveout(merge_var_finish_kernel);
+}
+
 int launch_coder(const CoderParams &p, cudaStream_t st) {
     if (p.n_blocks == 0) return 0;
+    coder_carveouts();
     const unsigned grid = (p.n_blocks + K2_WARPS - 1) / K2_WARPS;
     if (p.legacy) {
         if (p.mode == MODE_ENC) k2_coder_kernel<MODE_ENC, true><<<grid, K2_THREADS, 0, st>>>(p);
@@ -1287,21 +1322,25 @@ int launch_coder(const CoderParams &p, cudaStream_t st) {
 /* ------------------------------------------------------------------------------------------------
  * plan: per-block sizes -> offsets (one CTA; blocks in chunks of 1024 with a running carry).
  * totals[0] = workspace bytes, [1] = payload bytes, [2] = symbol-list entries, [3] = reads, [4] = edits. */
-#define PLAN_THREADS 1024u
+#define PLAN_THREADS 256u          /* a small CTA: during a pipelined call it has to find room beside resident block-coder CTAs */
 __global__ void __launch_bounds__(PLAN_THREADS)
 k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap, uint64_t payload_cap,
-               uint64_t *totals) {
+               uint64_t *totals, const uint64_t *carry_in, const uint64_t *n_edits_dev) {
+    /* Plans blocks [P.block_begin, + P.n_blocks). A pipelined encode (api.cu) plans chunk by chunk as the reads arrive:
+       the offsets carry on from the previous call's totals (carry_in) and the edit count so far is read on the device. */
+    if (n_edits_dev) n_edits_total = *n_edits_dev;
     __shared__ uint64_t wsum[5][32];
     __shared__ uint64_t carry[5];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid < 5) carry[tid] = 0;
+    if (tid < 5) carry[tid] = carry_in ? carry_in[tid] : 0;
     __syncthreads();
     const bool dec = (P.mode == MODE_DEC);
-    for (uint32_t base = 0; base < P.n_blocks; base += PLAN_THREADS) {
+    const uint32_t b_end = P.block_begin + P.n_blocks;
+    for (uint32_t base = P.block_begin; base < b_end; base += PLAN_THREADS) {
         const uint32_t b = base + tid;
         uint64_t v[5] = { 0, 0, 0, 0, 0 };
         BlockDesc d;
-        if (b < P.n_blocks) {
+        if (b < b_end) {
             d = P.blocks[b];
             if (!dec) {                                  /* edits of the block from the records' offsets */
                 const uint64_t lo = P.recs[d.first_read].edit_off;
@@ -1334,7 +1373,7 @@ k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, ui
             for (uint32_t k = 0; k < warp; k++) wb += wsum[q][k];
             off[q] = carry[q] + wb + incl[q] - v[q];
         }
-        if (b < P.n_blocks) {
+        if (b < b_end) {
             d.ws_off = off[0];
             if (!dec) d.payload_off = off[1];
             else { d.payload_off = off[1]; d.first_read = (uint32_t)off[3]; d.edit_base = off[4]; }
@@ -1355,8 +1394,9 @@ k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, ui
 }
 
 int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap,
-                uint64_t payload_cap, uint64_t *totals, cudaStream_t st) {
-    k2_plan_kernel<<<1, PLAN_THREADS, 0, st>>>(p, n_reads_total, n_edits_total, ws_cap, payload_cap, totals);
+                uint64_t payload_cap, uint64_t *totals, cudaStream_t st, const uint64_t *carry_in, const uint64_t *n_edits_dev) {
+    coder_carveouts();
+    k2_plan_kernel<<<1, PLAN_THREADS, 0, st>>>(p, n_reads_total, n_edits_total, ws_cap, payload_cap, totals, carry_in, n_edits_dev);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1705,9 +1745,25 @@ __global__ void __launch_bounds__(256) merge_var_finish_kernel(MergeParams P) {
     if (lane == 0) row[P.L] = n;
 }
 
+__global__ void __launch_bounds__(256) snapshot_copy_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint64_t n16) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+}
+
+/* 16-byte-granular copy by the SMs; src may be pinned host memory (read over PCIe without queueing on a copy engine). */
+int launch_copy16(void *dst, const void *src, uint64_t bytes, cudaStream_t st) {
+    coder_carveouts();
+    if (!bytes) return 0;
+    const uint64_t n16 = (bytes + 15u) / 16u;
+    snapshot_copy_kernel<<<(unsigned)std::min<uint64_t>(148u * 8u, (n16 + 255u) / 256u), 256, 0, st>>>(reinterpret_cast<uint4 *>(dst), reinterpret_cast<const uint4 *>(src), n16);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_blocks, uint32_t L, const uint8_t *prev,
                  uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, cudaStream_t st) {
-    if (cudaMemcpyAsync(next, prev, snapshot_bytes(L), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return -1;
+    /* next = prev, by a kernel: a cudaMemcpyAsync would queue on a copy engine behind the host <-> device traffic of a
+       pipelined call (api.cu) and stall the generations for milliseconds */
+    snapshot_copy_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<uint4 *>(next), reinterpret_cast<const uint4 *>(prev), snapshot_bytes(L) / 16u);
     MergeParams P = { blocks, block_begin, n_blocks, L, prev, next, fin, ws, err };
     merge_prep_kernel<<<148, 128, 0, st>>>(P);
     merge_add_kernel<<<dim3((n_blocks + 3u) / 4u, MERGE_PARTS), 128, 0, st>>>(P);

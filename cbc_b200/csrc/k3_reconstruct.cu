@@ -124,6 +124,13 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
         w0 = pos0 ? ((uint64_t)(pos0 - 1u) & ~15ull) : 0ull;
         uint64_t avail = (clen0 + REF_PAD > w0) ? ((clen0 + REF_PAD - w0) & ~15ull) : 0ull;
         ref_bytes = (uint32_t)min((uint64_t)K3_REF_CAP, avail);
+        /* position-sorted input: the tile's last read bounds the window (a read beyond it misses the window and is
+           built from HBM) */
+        const uint32_t pos_l = S.rec[nr - 1u].pos;
+        if (S.chr[nr - 1u] == chr0 && pos_l >= pos0 && pos0) {
+            const uint64_t need = ((uint64_t)(pos_l - 1u) - w0 + max_len + 8u + 15u) & ~15ull;
+            if (need < ref_bytes) ref_bytes = (uint32_t)need;
+        }
     }
     if (tid == 0) {
         mbar_expect_tx(&S.bar, ref_bytes);
@@ -368,10 +375,13 @@ int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(k3_reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        cudaFuncSetAttribute(k3_reconstruct_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cbcg_carveout_percent());   /* see k2_coder.cu */
         configured = smem;
     }
-    if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;
-    if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;
+    if (!fixed_len) {                                       /* closed-form offsets use neither the ticket nor the descriptors */
+        if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;
+        if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;
+    }
     if (ev_start) cudaEventRecord(ev_start, st);
     k3_reconstruct_kernel<<<(unsigned)tiles, K3_THREADS, smem, st>>>(n_reads, recs, chr, edits, g, out, out_cap,
                                                                     tile_desc, ticket, total_bytes, err, max_len, fixed_len);

@@ -1027,8 +1027,43 @@ static void rstate_init_from(rstate *s, const models *snap, int mode) {
 /* Blocks: generation i < n_sched has sched_count[i] blocks of sched_reads[i] reads, the last generation
  * takes the rest in blocks of block_reads reads; a chromosome change always ends a block. n_sched == 0:
  * every block starts from the reference's initial state (gen_mode 0). */
+static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads, uint32_t n_sched,
+                      const uint32_t *sched_count, const uint32_t *sched_reads, const blk_index *given, uint64_t n_given,
+                      cbco_buf *out);
+
 int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads,
                           uint32_t n_sched, const uint32_t *sched_count, const uint32_t *sched_reads, cbco_buf *out) {
+    return encode_cut(b, g, L, block_reads, n_sched, sched_count, sched_reads, NULL, 0, out);
+}
+
+/* The batch coded with the block cut of an existing container (per-block read counts and generations taken from its
+ * index; header block size and mode word too): the check for cuts the encoder chose itself (the pipelined cbcg_encode
+ * sizes last-generation blocks by their place in the batch). */
+int cbco_encode_like(const uint8_t *p, uint64_t len, const cbco_batch *b, const cbco_genome *g, cbco_buf *out) {
+    if (len < 40) return -40;
+    uint32_t h[10]; memcpy(h, p, 40);
+    if (h[0] != CBCG_MAGIC || h[1] != CBCG_VERSION) return -41;
+    uint32_t nb = h[6], n_chr = h[7];
+    uint64_t o = 40;
+    for (uint32_t c = 0; c < n_chr; c++) {
+        if (o + 4 > len) return -43;
+        uint32_t nl; memcpy(&nl, p + o, 4); o += 4 + nl + ((4 - (nl & 3)) & 3);
+    }
+    if (o + 4 > len) return -43;
+    uint32_t ix_bytes; memcpy(&ix_bytes, p + o, 4); o += 4;
+    if (o + ix_bytes > len) return -43;
+    blk_index *idx = (blk_index *)calloc((size_t)nb + 1, sizeof(blk_index));
+    idx_state st = { h[8], 0, 0, 0, 0, 0, 0 };
+    uint64_t io = o;
+    for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k])) { free(idx); return -43; }
+    int rc = encode_cut(b, g, h[3], h[8], (h[9] & CBCG_MODE_GEN_MASK) ? 1u : 0u, NULL, NULL, idx, nb, out);
+    free(idx);
+    return rc;
+}
+
+static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads, uint32_t n_sched,
+                      const uint32_t *sched_count, const uint32_t *sched_reads, const blk_index *given, uint64_t n_given,
+                      cbco_buf *out) {
     if (block_reads == 0) return -30;
     uint64_t cap = 16;
     for (uint64_t r = 0; r < b->n_reads; r++) cap += 3ull * b->seq_len[r] + 8;
@@ -1040,18 +1075,24 @@ int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t L,
     uint64_t nb = 0, bcap = 1024;
     blk_index *idx = (blk_index *)calloc(bcap, sizeof(blk_index));
     uint64_t *first = (uint64_t *)calloc(bcap + 1, sizeof(uint64_t));
-    uint32_t gen = 0, left_in_gen = n_sched ? sched_count[0] : 0;
-    while (gen < n_sched && left_in_gen == 0) { gen++; left_in_gen = gen < n_sched ? sched_count[gen] : 0; }
+    uint32_t gen = 0, left_in_gen = (n_sched && !given) ? sched_count[0] : 0;
+    while (!given && gen < n_sched && left_in_gen == 0) { gen++; left_in_gen = gen < n_sched ? sched_count[gen] : 0; }
     for (uint64_t r = 0; r < b->n_reads;) {
-        uint32_t want = gen < n_sched ? sched_reads[gen] : block_reads;
+        uint32_t want = given ? 0u : (gen < n_sched ? sched_reads[gen] : block_reads);
+        if (given) {                                           /* the cut of an existing container */
+            if (nb >= n_given || given[nb].n_reads == 0) { free(idx); free(first); free(recs); free(edits); return -48; }
+            want = given[nb].n_reads; gen = given[nb].gen;
+        }
         if (want == 0) want = 1;
         uint64_t e = r + 1;
         while (e < b->n_reads && e - r < want && b->chr[e] == b->chr[r]) e++;
+        if (given && e - r != want) { free(idx); free(first); free(recs); free(edits); return -48; }
         if (nb + 1 >= bcap) { bcap *= 2; idx = (blk_index *)realloc(idx, bcap * sizeof(blk_index)); first = (uint64_t *)realloc(first, (bcap + 1) * 8); }
         first[nb] = r;
         memset(&idx[nb], 0, sizeof(blk_index));
         idx[nb].n_reads = (uint32_t)(e - r); idx[nb].chr = b->chr[r]; idx[nb].base_pos = recs[r].pos; idx[nb].gen = gen;
         nb++; r = e;
+        if (given) continue;
         if (gen < n_sched && --left_in_gen == 0) { gen++; while (gen < n_sched && sched_count[gen] == 0) gen++; left_in_gen = gen < n_sched ? sched_count[gen] : 0; }
     }
     first[nb] = b->n_reads;

@@ -81,6 +81,8 @@ int cbco_symbols(const cbco_batch *b, const cbco_genome *g, const cbcg_read_rec 
  * chromosome changes, each with its own coder; model snapshots per generation (n_gens >= 1). */
 int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t read_len_header,
                         uint32_t block_reads, uint32_t gen_mode, cbco_buf *out);
+/* The batch coded with the block cut (per-block read counts, generations, header words) of an existing container. */
+int cbco_encode_like(const uint8_t *container, uint64_t len, const cbco_batch *b, const cbco_genome *g, cbco_buf *out);
 /* Same container with an explicit generation schedule (experiments; gen_mode 1 uses CBCG_GEN_*). */
 int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t read_len_header, uint32_t block_reads,
                           uint32_t n_sched, const uint32_t *sched_count, const uint32_t *sched_reads, cbco_buf *out);

@@ -145,6 +145,17 @@ def encode_blocked(batch: Batch, genome: Genome, read_len_header: int, block_rea
     return _take(out)
 
 
+def encode_like(container: bytes, batch: Batch, genome: Genome) -> bytes:
+    """The batch coded by the CPU restatement with the block cut recorded in `container`'s index."""
+    g = _G(genome)
+    cb = batch.c_struct()
+    out = _Buf()
+    rc = lib().cbco_encode_like(container, C.c_uint64(len(container)), C.byref(cb), C.byref(g.s), C.byref(out))
+    if rc:
+        raise RuntimeError(f"cbco_encode_like: {rc}")
+    return _take(out)
+
+
 def decode_blocked(container: bytes, genome: Genome):
     g = _G(genome)
     out = _Buf()

@@ -69,3 +69,43 @@ def test_config4_shape_many_chromosomes(codec):
     cfg = synth.SynthConfig.named("config4", scale=0.002)                 # 24 records, ~1.2 M reads
     g, b, cont = _roundtrip(codec, cfg, 150)
     assert struct.unpack_from("<I", cont, 28)[0] == 24
+
+
+def test_pipelined_host_buffer_encode_and_decode(codec, monkeypatch):
+    """cbcg_encode / cbcg_decode on a large batch overlap the PCIe copies with the kernels and size last-generation
+    blocks by their place in the batch. Whatever cut the encoder chose, the CPU restatement given the same cut writes
+    the same bytes, both decoders return the input, and the <= 1 % budget holds."""
+    monkeypatch.setenv("CBCG_PIPE_MIN_READS", "200000")
+    cfg = synth.SynthConfig.named("config2", scale=0.25)                  # ~750 k reads
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    codec.set_reference(g)
+    cont = codec.compress(b, 150, block_reads=AUTO, gen_mode=1)           # host buffers: the pipelined path
+    codec.upload(b)
+    codec.encode_resident(150, AUTO, 1)
+    resident = codec.fetch_container().tobytes()
+    assert cont != resident                                               # a different cut (the ramp) ...
+    assert struct.unpack_from("<Q", cont, 16)[0] == b.n_reads
+    assert cont == O.encode_like(cont, b, g)                              # ... that the restatement reproduces byte for byte
+    assert resident == O.encode_like(resident, b, g)
+    for c in (cont, resident):
+        text, n = codec.decompress(c)                                     # pipelined decode
+        assert n == b.n_reads and text == b.seq_lines()
+    otext, on = O.decode_blocked(cont, g)
+    assert on == b.n_reads and otext == b.seq_lines()
+    monkeypatch.setenv("CBCG_PIPE_MIN_READS", "1000000000")               # same containers through the one-stream decoder
+    text, n = codec.decompress(cont)
+    assert n == b.n_reads and text == b.seq_lines()
+
+
+def test_pipelined_full_size_budget(codec):
+    cfg = synth.SynthConfig.named("config2")
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    codec.set_reference(g)
+    cont = codec.compress(b, 150, block_reads=AUTO, gen_mode=1)
+    single, _ = O.encode_legacy(b, g, 150)
+    overhead = (len(cont) - len(single)) / len(single)
+    assert 0.0 < overhead <= 0.01, overhead
+    text, n = codec.decompress(cont)
+    assert n == b.n_reads and text == b.seq_lines()
