@@ -51,7 +51,7 @@ struct cbcg_ctx {
     /* pipelined host-buffer calls (cbcg_encode / cbcg_decode on large batches): a copy stream, side streams for the
        groups of last-generation blocks, and the events that order them */
     cudaStream_t cs = nullptr, ps[PIPE_MAX] = {};
-    cudaEvent_t cev[PIPE_MAX + 2] = {}, kev2[PIPE_MAX + 2] = {}, dev2[PIPE_MAX + 2] = {};
+    cudaEvent_t cev[PIPE_MAX + 2] = {}, kev2[PIPE_MAX + 2] = {}, dev2[PIPE_MAX + 2] = {}, tev[2 * PIPE_MAX + 4] = {};
     bool pipe_ready = false;
     char errtext[512] = {0};
     cbcg_stats stats = {};
@@ -202,6 +202,7 @@ extern "C" void cbcg_destroy(cbcg_ctx *ctx) {
     for (auto &e : ctx->cev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->kev2) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->dev2) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->tev) if (e) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -657,6 +658,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     TRY(validate_opts(ctx, opts));
     if (!ctx->have_batch) return fail(ctx, CBCG_ERR_ARG, "no resident batch: call cbcg_batch_upload first");
     CU(cudaSetDevice(ctx->device));
+    set_carveout_all(-1);
     const uint64_t n = ctx->db.n_reads;
     const int legacy = opts->block_reads == 0;
     const uint32_t L = opts->read_len_header;
@@ -781,7 +783,7 @@ static uint64_t pipe_min_reads() {
     return e ? strtoull(e, nullptr, 10) : (1ull << 20);
 }
 static void pipe_ramp(double *hi, double *lo) {
-    *hi = 1.85; *lo = 0.45;
+    *hi = 1.3; *lo = 0.7;                                   /* measured on config 2: encode 15.6 ms + decode 15.8 ms against 19.2 + 17.6 on one stream */
     const char *e = getenv("CBCG_PIPE_RAMP");               /* "hi,lo" multipliers of the mean block size (tuning) */
     if (e) { double a = 0, b = 0; if (sscanf(e, "%lf,%lf", &a, &b) == 2 && a >= b && b > 0.05 && a < 8.0) { *hi = a; *lo = b; } }
 }
@@ -792,6 +794,7 @@ static int pipe_init(cbcg_ctx *ctx) {
     for (auto &e : ctx->cev) CU(cudaEventCreate(&e));
     for (auto &e : ctx->kev2) CU(cudaEventCreate(&e));
     for (auto &e : ctx->dev2) CU(cudaEventCreate(&e));
+    for (auto &e : ctx->tev) CU(cudaEventCreate(&e));
     ctx->pipe_ready = true;
     return 0;
 }
@@ -807,6 +810,7 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     if (n < early + tile * (PIPE_CHUNKS + 1)) return PIPE_FALLBACK;
     TRY(pipe_init(ctx));
     TRY(batch_prepare(ctx, b));
+    set_carveout_all(100);
     cbcg_stats &S = ctx->stats;
 
     /* chunks: [0] = the head (early generations + one tile, so that the record after the last early block exists),
@@ -851,6 +855,9 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
         uint32_t k = last_first;
         for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) {
             while (k < last_first + last_n && (uint64_t)hb[k].first_read + hb[k].n_reads <= cut[c + 1]) k++;
+            /* whole CTAs (4 blocks) per group, so that the groups together need no more CTAs than one launch would:
+               a CTA beyond the resident slots starts when the first block anywhere retires and ends a block late */
+            if (c < PIPE_CHUNKS) k = last_first + ((k - last_first) & ~3u);
             gb[c] = k;
         }
         if (gb[PIPE_CHUNKS] != last_first + last_n) return fail(ctx, CBCG_ERR_INTERNAL, "pipelined encode: block groups do not cover the cut");
@@ -1157,6 +1164,7 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
     *fixed_len = 0;
     if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
     CU(cudaSetDevice(ctx->device));
+    set_carveout_all(-1);
     ctx->have_decoded = false;
     cbcg_stats &S = ctx->stats;
     S = cbcg_stats();
@@ -1219,6 +1227,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
     const uint64_t line = (uint64_t)c.L + 1u, bytes = c.n_reads * line;
     if (bytes > seq_cap) return PIPE_FALLBACK;
     TRY(pipe_init(ctx));
+    set_carveout_all(100);
     ctx->have_decoded = false;
     cbcg_stats &S = ctx->stats;
     S = cbcg_stats();
@@ -1237,7 +1246,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
         uint32_t k = last_first; uint64_t r = early_reads;
         for (uint32_t g = 1; g <= PIPE_CHUNKS; g++) {
             const uint64_t want = early_reads + (nr - early_reads) * g / PIPE_CHUNKS;
-            while (k < last_first + last_n && (r < want || g == PIPE_CHUNKS)) r += hb[k++].n_reads;
+            while (k < last_first + last_n && (r < want || g == PIPE_CHUNKS || ((k - last_first) & 3u))) r += hb[k++].n_reads;   /* whole CTAs */
             gb[g] = k; gr[g] = r;
         }
     }
@@ -1276,6 +1285,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
             if (launch_coder(q, sd)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             S.kernel_launches++;
         }
+        CU(cudaEventRecord(ctx->tev[2 * g], sd));
         if (r1 > r0) {
             if (launch_reconstruct(r1 - r0, ctx->recs.as<cbcg_read_rec>() + r0, ctx->chr_out.as<uint32_t>() + r0, ctx->edits.as<uint16_t>(),
                                    ctx->dg, ctx->seq_out.as<uint8_t>() + r0 * line, (r1 - r0) * line, c.L, c.L, ctx->tile_desc.as<uint64_t>(),
@@ -1283,6 +1293,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
                                    wptr<unsigned long long>(ctx, W_OFF(err)), sd, nullptr, nullptr))
                 return fail(ctx, CBCG_ERR_CUDA, "K3 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             S.kernel_launches++;
+            CU(cudaEventRecord(ctx->tev[2 * g + 1], sd));
             if (!g) {                                        /* its copy rides a side stream; the groups start behind the K3 launch */
                 CU(cudaEventRecord(ctx->kev2[0], ctx->st));
                 sd = ctx->ps[0];
@@ -1305,9 +1316,10 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
         float t0 = 0; cudaEventElapsedTime(&t0, ctx->ev[0], ctx->kev2[0]);
         fprintf(stderr, "[cbcg pipe dec] early generations done %.2f ms\n", t0);
         for (uint32_t g = 0; g <= PIPE_CHUNKS; g++) {
-            float d = 0; cudaEventElapsedTime(&d, ctx->ev[0], ctx->dev2[g]);
-            fprintf(stderr, "[cbcg pipe dec] group %u blocks %u reads %llu: text on the host %.2f ms\n", g, g ? gb[g] - gb[g - 1] : last_first,
-                    (unsigned long long)(g ? gr[g] - gr[g - 1] : early_reads), d);
+            float d = 0, k2 = 0, k3 = 0; cudaEventElapsedTime(&d, ctx->ev[0], ctx->dev2[g]);
+            cudaEventElapsedTime(&k2, ctx->ev[0], ctx->tev[2 * g]); cudaEventElapsedTime(&k3, ctx->ev[0], ctx->tev[2 * g + 1]);
+            fprintf(stderr, "[cbcg pipe dec] group %u blocks %u reads %llu: decoded %.2f ms, rebuilt %.2f ms, text on the host %.2f ms\n", g,
+                    g ? gb[g] - gb[g - 1] : last_first, (unsigned long long)(g ? gr[g] - gr[g - 1] : early_reads), k2, k3, d);
         }
         fprintf(stderr, "[cbcg pipe dec] all %.2f ms\n", S.ms_total);
     }
@@ -1379,6 +1391,7 @@ extern "C" int cbcg_decode_resident(cbcg_ctx *ctx) {
     if (!ctx) return CBCG_ERR_ARG;
     if (!ctx->have_encoded) return fail(ctx, CBCG_ERR_ARG, "nothing encoded yet");
     CU(cudaSetDevice(ctx->device));
+    set_carveout_all(-1);
     ctx->have_decoded = false;
     cbcg_stats &S = ctx->stats;
     S.ms_code = S.ms_reconstruct = S.ms_plan = S.ms_total = S.ms_extract = S.ms_gather = 0; S.kernel_launches = 0;

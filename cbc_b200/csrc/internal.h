@@ -104,6 +104,6 @@ uint64_t fin_stride_bytes(void);
 int launch_snapshot_init(uint8_t *snap, uint32_t L, cudaStream_t st);
 int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_blocks, uint32_t L, const uint8_t *prev,
                  uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, cudaStream_t st);
-int cbcg_carveout_percent(void);               /* shared-memory carveout every kernel asks for */
+void set_carveout_all(int pct);                 /* -1: driver default per kernel; 0..100: one split for every kernel */
 int launch_copy16(void *dst, const void *src, uint64_t bytes, cudaStream_t st);
 uint64_t coder_payload_bound(uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy);

@@ -351,6 +351,8 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
     }
 }
 
+void extract_set_carveout(int pct) { cudaFuncSetAttribute(k1_extract_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }   /* see k2_coder.cu */
+
 int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, uint16_t *edits,
                    uint64_t edits_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_edits,
                    unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop,
@@ -363,7 +365,6 @@ int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, u
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(k1_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        cudaFuncSetAttribute(k1_extract_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cbcg_carveout_percent());   /* see k2_coder.cu */
         configured = smem;
     }
     if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;

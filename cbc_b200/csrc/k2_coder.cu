@@ -1283,29 +1283,31 @@ __global__ void merge_add_kernel(MergeParams P);
 __global__ void merge_finish_kernel(MergeParams P);
 __global__ void merge_var_finish_kernel(MergeParams P);
 
-/* One shared-memory carveout for every kernel of the library: an SM cannot host CTAs of kernels that ask for different
- * L1 / shared-memory splits at the same time, so K1 / K3 launches of a pipelined call (api.cu) would otherwise wait for
- * the resident block-coder CTAs to drain before they get an SM. */
-int cbcg_carveout_percent(void) {
-    static int pct = -1;
-    if (pct < 0) { const char *e = getenv("CBCG_CARVEOUT"); pct = e ? atoi(e) : 100; if (pct < 0 || pct > 100) pct = 100; }
-    return pct;
-}
-template <class K> static void set_carveout(K kernel) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cbcg_carveout_percent()); }
-static void coder_carveouts() {
-    static bool done = false;
-    if (done) return;
-    done = true;
-    set_carveout(k2_coder_kernel<MODE_ENC, false>); set_carveout(k2_coder_kernel<MODE_DEC, false>); set_carveout(k2_coder_kernel<MODE_LIST, false>);
-    set_carveout(k2_coder_kernel<MODE_ENC, true>); set_carveout(k2_coder_kernel<MODE_DEC, true>); set_carveout(k2_coder_kernel<MODE_LIST, true>);
-    set_carveout(k2_plan_kernel); set_carveout(k2_payload_scan_kernel); set_carveout(k2_gather_kernel);
-    set_carveout(snapshot_init_kernel); set_carveout(snapshot_copy_kernel);
-    set_carveout(merge_prep_kernel); set_carveout(merge_add_kernel); set_carveout(merge_finish_kernel); set_carveout(merge_var_finish_kernel);
+/* Shared-memory carveout. An SM cannot host CTAs of kernels that ask for different L1 / shared-memory splits at the same
+ * time: with the driver's per-kernel choices the K1 / K3 launches of a pipelined call (api.cu) wait for the resident
+ * block-coder CTAs to drain (measured: the whole gain of the pipeline is lost). Pipelined calls therefore put every
+ * kernel on the same split; one-stream calls keep the driver's choices, which are 0.3 ms better for the block coder. */
+void extract_set_carveout(int pct);        /* k1_extract.cu */
+void reconstruct_set_carveout(int pct);    /* k3_reconstruct.cu */
+template <class K> static void set_carveout(K kernel, int pct) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }
+/* pct = -1: every kernel gets the split the driver prefers for it (best for each kernel on its own: the one-stream
+ * calls); 0..100: that share of shared memory for all of them (the pipelined calls). */
+void set_carveout_all(int pct) {
+    static int current = -1;
+    const char *e = getenv("CBCG_CARVEOUT");               /* tuning: force one value everywhere */
+    if (e) pct = atoi(e);
+    if (pct == current) return;
+    current = pct;
+    set_carveout(k2_coder_kernel<MODE_ENC, false>, pct); set_carveout(k2_coder_kernel<MODE_DEC, false>, pct); set_carveout(k2_coder_kernel<MODE_LIST, false>, pct);
+    set_carveout(k2_coder_kernel<MODE_ENC, true>, pct); set_carveout(k2_coder_kernel<MODE_DEC, true>, pct); set_carveout(k2_coder_kernel<MODE_LIST, true>, pct);
+    set_carveout(k2_plan_kernel, pct); set_carveout(k2_payload_scan_kernel, pct); set_carveout(k2_gather_kernel, pct);
+    set_carveout(snapshot_init_kernel, pct); set_carveout(snapshot_copy_kernel, pct);
+    set_carveout(merge_prep_kernel, pct); set_carveout(merge_add_kernel, pct); set_carveout(merge_finish_kernel, pct); set_carveout(merge_var_finish_kernel, pct);
+    extract_set_carveout(pct); reconstruct_set_carveout(pct);
 }
 
 int launch_coder(const CoderParams &p, cudaStream_t st) {
     if (p.n_blocks == 0) return 0;
-    coder_carveouts();
     const unsigned grid = (p.n_blocks + K2_WARPS - 1) / K2_WARPS;
     if (p.legacy) {
         if (p.mode == MODE_ENC) k2_coder_kernel<MODE_ENC, true><<<grid, K2_THREADS, 0, st>>>(p);
@@ -1395,7 +1397,6 @@ k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, ui
 
 int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap,
                 uint64_t payload_cap, uint64_t *totals, cudaStream_t st, const uint64_t *carry_in, const uint64_t *n_edits_dev) {
-    coder_carveouts();
     k2_plan_kernel<<<1, PLAN_THREADS, 0, st>>>(p, n_reads_total, n_edits_total, ws_cap, payload_cap, totals, carry_in, n_edits_dev);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1752,7 +1753,6 @@ __global__ void __launch_bounds__(256) snapshot_copy_kernel(uint4 *__restrict__ 
 
 /* 16-byte-granular copy by the SMs; src may be pinned host memory (read over PCIe without queueing on a copy engine). */
 int launch_copy16(void *dst, const void *src, uint64_t bytes, cudaStream_t st) {
-    coder_carveouts();
     if (!bytes) return 0;
     const uint64_t n16 = (bytes + 15u) / 16u;
     snapshot_copy_kernel<<<(unsigned)std::min<uint64_t>(148u * 8u, (n16 + 255u) / 256u), 256, 0, st>>>(reinterpret_cast<uint4 *>(dst), reinterpret_cast<const uint4 *>(src), n16);

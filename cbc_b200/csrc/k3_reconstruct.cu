@@ -365,6 +365,8 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
     if (tid >= 64 && tid < 64 + tail) gdst[head + mid + (tid - 64)] = img[head + mid + (tid - 64)];
 }
 
+void reconstruct_set_carveout(int pct) { cudaFuncSetAttribute(k3_reconstruct_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }   /* see k2_coder.cu */
+
 int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr, const uint16_t *edits,
                        const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len, uint32_t fixed_len,
                        uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
@@ -375,7 +377,6 @@ int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(k3_reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        cudaFuncSetAttribute(k3_reconstruct_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cbcg_carveout_percent());   /* see k2_coder.cu */
         configured = smem;
     }
     if (!fixed_len) {                                       /* closed-form offsets use neither the ticket nor the descriptors */
