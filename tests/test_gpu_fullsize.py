@@ -98,6 +98,19 @@ def test_pipelined_host_buffer_encode_and_decode(codec, monkeypatch):
     assert n == b.n_reads and text == b.seq_lines()
 
 
+def test_pipelined_encode_many_chromosomes_and_variable_length(codec, monkeypatch):
+    monkeypatch.setenv("CBCG_PIPE_MIN_READS", "200000")
+    for name, scale, L in (("config4", 0.001, 150), ("config5", 0.25, 250)):     # 24 records; 50-250 bp with indels and clips
+        cfg = synth.SynthConfig.named(name, scale=scale)
+        g = synth.make_genome(cfg)
+        b = synth.make_reads(cfg, g)
+        codec.set_reference(g)
+        cont = codec.compress(b, L, block_reads=AUTO, gen_mode=1)
+        assert cont == O.encode_like(cont, b, g)
+        text, n = codec.decompress(cont)                                  # variable length: the one-stream decoder
+        assert n == b.n_reads and text == b.seq_lines()
+
+
 def test_pipelined_full_size_budget(codec):
     cfg = synth.SynthConfig.named("config2")
     g = synth.make_genome(cfg)
