@@ -25,7 +25,7 @@ $(BUILD)/libcbcsynth.so: cbc_b200/csrc/host/synth.c cbc_b200/csrc/host/synth.h
 
 $(BUILD)/libcbchost.so: $(HOST_SRC) $(HOST_HDR)
 	@mkdir -p $(BUILD)
-	$(CC) -O2 -Wall -fPIC -shared -Iinclude -Icbc_b200/csrc/host $(HOST_SRC) -o $@
+	$(CC) -O2 -Wall -fPIC -shared -Iinclude -Icbc_b200/csrc/host $(HOST_SRC) -o $@ -lpthread
 
 cuda: $(BUILD)/libcbcg.so
 

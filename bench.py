@@ -60,7 +60,8 @@ def workload(rank: int, scale: float):
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "utilization.gpu")
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
@@ -68,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
@@ -81,7 +82,7 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
+        sm, mx, busy, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -89,6 +90,7 @@ class ClockSampler:
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2]))
+                busy.append(float(f[9]) if len(f) > 9 else 100.0)
             except ValueError:
                 continue
             for nm, v in zip(names, f[5:9]):
@@ -96,7 +98,9 @@ class ClockSampler:
                     reasons.add(nm)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        loaded = [c for c, u in zip(sm, busy) if u >= 10.0] or sm       # samples taken while the GPU was working
+        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "samples_under_load": len(loaded) if len(loaded) != len(sm) or busy and min(busy) >= 10.0 else 0}
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference
@@ -191,6 +195,7 @@ def run_b200_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner goes to stdout otherwise: stdout is the JSON line
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -253,11 +258,13 @@ def run_b200_arm(args):
         block_reads_used = int.from_bytes(head[32:36], "little")
         return se, sd
 
+    # nvidia-smi needs ~0.1 s to come up and the timed region of the resident leg is ~0.1 s long: the sampler starts
+    # before the warm-up steps (the same work) and runs until the end of the e2e leg, 20 ms apart
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         resident_step(False)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     codec.mark(0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -266,7 +273,6 @@ def run_b200_arm(args):
     dev_ms = codec.elapsed_ms(0, 1)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop()
     step_ms = max_over_ranks(dev_ms) / args.steps
     total_reads = sum_over_ranks(float(n))
     value = total_reads / (step_ms * 1e-3)
@@ -317,6 +323,7 @@ def run_b200_arm(args):
         res = e2e_step()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    clocks = sampler.stop()
     text_all = b"".join(outs_t[k][:res[k][1]].tobytes() for k in range(K))
     if text_all != b.seq_lines():
         raise RuntimeError("e2e round trip mismatch")

@@ -5,12 +5,14 @@
 #include "sam_ingest.h"
 
 #include <fcntl.h>
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
 static int fail(char *err, size_t n, int rc, const char *fmt, ...) {
@@ -27,7 +29,7 @@ static int map_file(const char *path, mapped *m) {
     if (fstat(m->fd, &st)) { close(m->fd); return -1; }
     m->n = (size_t)st.st_size;
     if (m->n == 0) return 0;
-    void *p = mmap(NULL, m->n, PROT_READ, MAP_PRIVATE, m->fd, 0);
+    void *p = mmap(NULL, m->n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, m->fd, 0);   /* page tables filled once, not by faults of the workers */
     if (p == MAP_FAILED) { close(m->fd); return -1; }
     madvise(p, m->n, MADV_SEQUENTIAL);
     m->p = (const uint8_t *)p;
@@ -124,15 +126,36 @@ static int parse_u32(const uint8_t *s, const uint8_t *e, uint32_t *v) {
     return 0;
 }
 
-int cbch_read_sam(const char *path, const cbch_fasta *fa, int var_length, cbch_batch *b, char *err, size_t errlen) {
+/* One worker's share of the file: the lines of [begin, end) parsed into its own batch (pool offsets from 0), plus what
+ * the merge needs to restate whole-file facts: the SEQ lengths of its first two records (get_read_length looks at the
+ * file's second record, mapped or not) and its line count (error messages carry whole-file line numbers). */
+typedef struct {
+    const uint8_t *begin, *end;
+    const cbch_fasta *fa;
+    cbch_batch part;
+    uint64_t records; uint32_t len1, len2;
+    int rc; uint64_t err_line; char err[200];
+} ingest_part;
+
+static int part_fail(ingest_part *w, int rc, const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(w->err, sizeof w->err, fmt, ap); va_end(ap);
+    w->rc = rc; w->err_line = w->part.n_lines;
+    return rc;
+}
+
+static void parse_range(ingest_part *w) {
+    cbch_batch *b = &w->part;
+    const cbch_fasta *fa = w->fa;
     memset(b, 0, sizeof *b);
-    mapped m;
-    if (map_file(path, &m)) return fail(err, errlen, CBCH_ERR_IO, "cannot open %s", path);
-    const uint8_t *p = m.p, *end = m.p + m.n;
+    w->records = 0; w->len1 = w->len2 = 0; w->rc = CBCH_OK; w->err_line = 0; w->err[0] = 0;
+    const uint8_t *p = w->begin, *end = w->end;
     int rc = CBCH_OK;
     uint32_t last_chr = 0; const uint8_t *last_name = NULL; size_t last_name_len = 0;
-    uint64_t records = 0; uint32_t second_len = 0, first_len = 0;
-    if (reserve_reads(b, 4096)) rc = CBCH_ERR_NOMEM;
+    /* sized from the range once (a record is at least 22 bytes of text, its SEQ / CIGAR / MD are substrings of it): no
+       reallocation while parsing; untouched pages cost nothing */
+    const uint64_t range = (uint64_t)(end - p);
+    if (reserve_reads(b, range / 22u + 16u) || grow((void **)&b->seq, &b->seq_cap, range + 64, 1) ||
+        grow((void **)&b->cigar, &b->cigar_cap, range / 2u + 64, 1) || grow((void **)&b->md, &b->md_cap, range / 2u + 64, 1)) rc = part_fail(w, CBCH_ERR_NOMEM, "out of memory");
     uint64_t so = 0, co = 0, mo = 0;
     while (!rc && p < end) {
         const uint8_t *nl = memchr(p, '\n', (size_t)(end - p));
@@ -151,26 +174,24 @@ int cbch_read_sam(const char *path, const cbch_fasta *fa, int var_length, cbch_b
             if (!t) { s = le + 1; break; }
             s = t + 1;
         }
-        if (nf < 11) { rc = fail(err, errlen, CBCH_ERR_PARSE, "line %llu: fewer than 11 fields", (unsigned long long)b->n_lines); break; }
+        if (nf < 11) { rc = part_fail(w, CBCH_ERR_PARSE, "fewer than 11 fields"); break; }
         f[11] = s;                                                /* start of the optional fields (or le + 1) */
 #define FEND(i) ((i) < 10 ? f[(i) + 1] - 1 : (f[11] > le ? le : f[11] - 1))
         uint32_t flag, pos;
-        if (parse_u32(f[1], FEND(1), &flag) || flag > 0xffffu || parse_u32(f[3], FEND(3), &pos)) {
-            rc = fail(err, errlen, CBCH_ERR_PARSE, "line %llu: bad FLAG or POS", (unsigned long long)b->n_lines); break;
-        }
+        if (parse_u32(f[1], FEND(1), &flag) || flag > 0xffffu || parse_u32(f[3], FEND(3), &pos)) { rc = part_fail(w, CBCH_ERR_PARSE, "bad FLAG or POS"); break; }
         const uint32_t seqlen = (uint32_t)(FEND(9) - f[9]);
-        records++;
-        if (records == 1) first_len = seqlen;
-        if (records == 2) second_len = seqlen;
+        w->records++;
+        if (w->records == 1) w->len1 = seqlen;
+        if (w->records == 2) w->len2 = seqlen;
         if (flag & 4u) { b->n_unmapped++; continue; }             /* src/compression.c:50 */
-        if (seqlen > 0xffffu) { rc = fail(err, errlen, CBCH_ERR_PARSE, "line %llu: SEQ too long", (unsigned long long)b->n_lines); break; }
+        if (seqlen > 0xffffu) { rc = part_fail(w, CBCH_ERR_PARSE, "SEQ too long"); break; }
         /* RNAME -> ordinal (consecutive records mostly share it) */
         const uint8_t *rn = f[2]; size_t rl = (size_t)(FEND(2) - f[2]);
         uint32_t chr = last_chr;
         if (!(last_name && rl == last_name_len && !memcmp(rn, last_name, rl))) {
             uint32_t c;
             for (c = 0; c < fa->n; c++) if (strlen(fa->names[c]) == rl && !memcmp(fa->names[c], rn, rl)) break;
-            if (c == fa->n) { rc = fail(err, errlen, CBCH_ERR_RNAME, "line %llu: RNAME %.*s is not in the reference", (unsigned long long)b->n_lines, (int)rl, rn); break; }
+            if (c == fa->n) { rc = part_fail(w, CBCH_ERR_RNAME, "RNAME %.*s is not in the reference", (int)rl, rn); break; }
             chr = c; last_chr = c; last_name = rn; last_name_len = rl;
         }
         /* MD:Z among the optional fields */
@@ -181,10 +202,10 @@ int cbch_read_sam(const char *path, const cbch_fasta *fa, int var_length, cbch_b
             if (oe - o >= 5 && o[0] == 'M' && o[1] == 'D' && o[2] == ':' && o[3] == 'Z' && o[4] == ':') { md = o + 5; mdl = (size_t)(oe - md); break; }
             o = oe + 1;
         }
-        if (!md) { rc = fail(err, errlen, CBCH_ERR_NO_MD, "line %llu: no MD:Z tag (README.md:25-29 requires it)", (unsigned long long)b->n_lines); break; }
+        if (!md) { rc = part_fail(w, CBCH_ERR_NO_MD, "no MD:Z tag (README.md:25-29 requires it)"); break; }
         const size_t cgl = (size_t)(FEND(5) - f[5]);
         if (reserve_reads(b, b->n_reads + 1) || grow((void **)&b->seq, &b->seq_cap, so + seqlen + 64, 1) ||
-            grow((void **)&b->cigar, &b->cigar_cap, co + cgl + 64, 1) || grow((void **)&b->md, &b->md_cap, mo + mdl + 64, 1)) { rc = CBCH_ERR_NOMEM; break; }
+            grow((void **)&b->cigar, &b->cigar_cap, co + cgl + 64, 1) || grow((void **)&b->md, &b->md_cap, mo + mdl + 64, 1)) { rc = part_fail(w, CBCH_ERR_NOMEM, "out of memory"); break; }
         const uint64_t r = b->n_reads++;
         b->pos[r] = pos; b->flag[r] = (uint16_t)flag; b->seq_len[r] = (uint16_t)seqlen; b->chr[r] = chr;
         b->seq_off[r] = so; memcpy(b->seq + so, f[9], seqlen); so += seqlen;
@@ -192,16 +213,110 @@ int cbch_read_sam(const char *path, const cbch_fasta *fa, int var_length, cbch_b
         b->md_off[r] = mo; memcpy(b->md + mo, md, mdl); mo += mdl;
         if (seqlen > b->max_len) b->max_len = seqlen;
     }
-    unmap_file(&m);
-    if (rc == CBCH_ERR_NOMEM) fail(err, errlen, rc, "out of memory reading %s", path);
-    if (rc) { cbch_free_batch(b); return rc; }
-    if (b->n_reads == 0) {                                    /* keep the arrays addressable */
-        if (reserve_reads(b, 1) || grow((void **)&b->seq, &b->seq_cap, 64, 1) || grow((void **)&b->cigar, &b->cigar_cap, 64, 1) ||
-            grow((void **)&b->md, &b->md_cap, 64, 1)) return fail(err, errlen, CBCH_ERR_NOMEM, "out of memory");
+    if (!rc) { b->seq_off[b->n_reads] = so; b->cigar_off[b->n_reads] = co; b->md_off[b->n_reads] = mo; }
+}
+
+/* second phase of the threaded ingest: every worker copies its part to its place in the merged batch */
+typedef struct { ingest_part *w; cbch_batch *dst; uint64_t r0, s0, c0, m0; } merge_job;
+static void merge_part(merge_job *j) {
+    const cbch_batch *s = &j->w->part; cbch_batch *d = j->dst;
+    const uint64_t n = s->n_reads;
+    if (!n) return;
+    memcpy(d->pos + j->r0, s->pos, n * sizeof *d->pos); memcpy(d->flag + j->r0, s->flag, n * sizeof *d->flag);
+    memcpy(d->seq_len + j->r0, s->seq_len, n * sizeof *d->seq_len); memcpy(d->chr + j->r0, s->chr, n * sizeof *d->chr);
+    for (uint64_t r = 0; r < n; r++) { d->seq_off[j->r0 + r] = s->seq_off[r] + j->s0; d->cigar_off[j->r0 + r] = s->cigar_off[r] + j->c0; d->md_off[j->r0 + r] = s->md_off[r] + j->m0; }
+    memcpy(d->seq + j->s0, s->seq, s->seq_off[n]); memcpy(d->cigar + j->c0, s->cigar, s->cigar_off[n]); memcpy(d->md + j->m0, s->md, s->md_off[n]);
+}
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + (double)t.tv_nsec * 1e-9; }
+static void *parse_thread(void *arg) { parse_range((ingest_part *)arg); return NULL; }
+static void *merge_thread(void *arg) { merge_part((merge_job *)arg); return NULL; }
+
+int cbch_default_threads(void) {
+    const char *e = getenv("CBCH_THREADS");
+    long t = e ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+    if (t < 1) t = 1;
+    if (t > 64) t = 64;
+    return (int)t;
+}
+
+int cbch_read_sam(const char *path, const cbch_fasta *fa, int var_length, cbch_batch *b, char *err, size_t errlen) {
+    return cbch_read_sam_mt(path, fa, var_length, cbch_default_threads(), b, err, errlen);
+}
+
+/* The file is cut at line starts into n_threads ranges of about equal bytes; every worker parses its range into its own
+ * batch, then copies it to its place in the merged one (two rounds of threads, no locks). The result does not depend
+ * on n_threads. */
+int cbch_read_sam_mt(const char *path, const cbch_fasta *fa, int var_length, int n_threads, cbch_batch *b, char *err, size_t errlen) {
+    memset(b, 0, sizeof *b);
+    mapped m;
+    if (map_file(path, &m)) return fail(err, errlen, CBCH_ERR_IO, "cannot open %s", path);
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    if (m.n < (size_t)n_threads * 4096u) n_threads = (int)(m.n / 4096u) + 1;       /* small files: fewer workers */
+    ingest_part *w = calloc((size_t)n_threads, sizeof *w);
+    merge_job *jobs = calloc((size_t)n_threads, sizeof *jobs);
+    pthread_t *th = calloc((size_t)n_threads, sizeof *th);
+    if (!w || !jobs || !th) { free(w); free(jobs); free(th); unmap_file(&m); return fail(err, errlen, CBCH_ERR_NOMEM, "out of memory"); }
+    const uint8_t *end = m.p + m.n, *cur = m.p;
+    for (int t = 0; t < n_threads; t++) {
+        const uint8_t *stop = end;
+        if (t + 1 < n_threads) {
+            const uint8_t *guess = m.p + m.n / (size_t)n_threads * (size_t)(t + 1);
+            if (guess < cur) guess = cur;
+            const uint8_t *nl = guess < end ? memchr(guess, '\n', (size_t)(end - guess)) : NULL;
+            stop = nl ? nl + 1 : end;
+        }
+        w[t].begin = cur; w[t].end = stop; w[t].fa = fa;
+        cur = stop;
     }
-    b->seq_off[b->n_reads] = so; b->cigar_off[b->n_reads] = co; b->md_off[b->n_reads] = mo;
-    /* get_read_length (:47-53): fixed-length mode takes the SECOND record's SEQ length; -l takes the maximum */
-    b->read_len_header = var_length ? b->max_len : (records >= 2 ? second_len : first_len);
+    const int trace = getenv("CBCH_TRACE") != NULL;
+    const double t_begin = now_s();
+    int started = 0;
+    for (int t = 1; t < n_threads; t++) { if (pthread_create(&th[t], NULL, parse_thread, &w[t])) break; started = t; }
+    for (int t = started + 1; t < n_threads; t++) parse_range(&w[t]);           /* threads that could not start: here */
+    parse_range(&w[0]);
+    for (int t = 1; t <= started; t++) pthread_join(th[t], NULL);
+    const double t_parsed = now_s();
+    unmap_file(&m);
+
+    /* whole-file facts, and the first error in file order */
+    int rc = CBCH_OK;
+    uint64_t lines = 0, records = 0, n = 0, so = 0, co = 0, mo = 0; uint32_t lens[2] = { 0, 0 };
+    for (int t = 0; t < n_threads && !rc; t++) {
+        if (w[t].rc) {
+            rc = w[t].rc;
+            if (rc == CBCH_ERR_NOMEM) fail(err, errlen, rc, "out of memory reading %s", path);
+            else fail(err, errlen, rc, "line %llu: %s", (unsigned long long)(lines + w[t].err_line), w[t].err);
+            break;
+        }
+        if (records < 2 && w[t].records) { lens[records] = w[t].len1; if (records == 0 && w[t].records >= 2) lens[1] = w[t].len2; }
+        records += w[t].records;
+        jobs[t].w = &w[t]; jobs[t].dst = b; jobs[t].r0 = n; jobs[t].s0 = so; jobs[t].c0 = co; jobs[t].m0 = mo;
+        n += w[t].part.n_reads; lines += w[t].part.n_lines; b->n_unmapped += w[t].part.n_unmapped;
+        if (w[t].part.n_reads) { so += w[t].part.seq_off[w[t].part.n_reads]; co += w[t].part.cigar_off[w[t].part.n_reads]; mo += w[t].part.md_off[w[t].part.n_reads]; }
+        if (w[t].part.max_len > b->max_len) b->max_len = w[t].part.max_len;
+    }
+    if (!rc) {
+        if (reserve_reads(b, n + 1) || grow((void **)&b->seq, &b->seq_cap, so + 64, 1) || grow((void **)&b->cigar, &b->cigar_cap, co + 64, 1) ||
+            grow((void **)&b->md, &b->md_cap, mo + 64, 1)) rc = fail(err, errlen, CBCH_ERR_NOMEM, "out of memory reading %s", path);
+    }
+    if (!rc) {
+        b->n_reads = n; b->n_lines = lines;
+        started = 0;
+        for (int t = 1; t < n_threads; t++) { if (pthread_create(&th[t], NULL, merge_thread, &jobs[t])) break; started = t; }
+        for (int t = started + 1; t < n_threads; t++) merge_part(&jobs[t]);
+        merge_part(&jobs[0]);
+        for (int t = 1; t <= started; t++) pthread_join(th[t], NULL);
+        b->seq_off[n] = so; b->cigar_off[n] = co; b->md_off[n] = mo;
+        /* get_read_length (:47-53): fixed-length mode takes the SECOND record's SEQ length; -l takes the maximum */
+        b->read_len_header = var_length ? b->max_len : (records >= 2 ? lens[1] : lens[0]);
+    }
+    const double t_merged = now_s();
+    for (int t = 0; t < n_threads; t++) cbch_free_batch(&w[t].part);
+    free(w); free(jobs); free(th);
+    if (trace) fprintf(stderr, "[cbch ingest] %d workers: parse %.1f ms, merge %.1f ms, free %.1f ms\n", n_threads, (t_parsed - t_begin) * 1e3,
+                       (t_merged - t_parsed) * 1e3, (now_s() - t_merged) * 1e3);
+    if (rc) { cbch_free_batch(b); return rc; }
     return CBCH_OK;
 }
 

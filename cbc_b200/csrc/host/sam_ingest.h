@@ -39,6 +39,10 @@ int  cbch_read_fasta(const char *path, cbch_fasta *out, char *err, size_t errlen
 void cbch_free_fasta(cbch_fasta *fa);
 /* Mapped records of a SAM file; RNAME is resolved against the FASTA record names. */
 int  cbch_read_sam(const char *path, const cbch_fasta *fa, int var_length, cbch_batch *out, char *err, size_t errlen);
+/* The same with an explicit worker count (cbch_read_sam uses CBCH_THREADS or the online cores, at most 64): the file is
+ * cut at line starts, the ranges are parsed in parallel and merged; the result does not depend on the count. */
+int  cbch_read_sam_mt(const char *path, const cbch_fasta *fa, int var_length, int n_threads, cbch_batch *out, char *err, size_t errlen);
+int  cbch_default_threads(void);
 void cbch_free_batch(cbch_batch *b);
 void cbch_batch_view(const cbch_batch *b, cbcg_batch *view);
 

@@ -34,6 +34,7 @@ def lib():
     l = C.CDLL(LIB)
     l.cbch_read_fasta.argtypes = [C.c_char_p, C.POINTER(Fasta), C.c_char_p, C.c_size_t]
     l.cbch_read_sam.argtypes = [C.c_char_p, C.POINTER(Fasta), C.c_int, C.POINTER(HBatch), C.c_char_p, C.c_size_t]
+    l.cbch_read_sam_mt.argtypes = [C.c_char_p, C.POINTER(Fasta), C.c_int, C.c_int, C.POINTER(HBatch), C.c_char_p, C.c_size_t]
     return l
 
 
@@ -106,3 +107,55 @@ def test_edge_records(lib):
             f.write("r0\t0\tchrA\t1\t60\t4M\t*\t0\t0\tACGT\tIIII\n")
         rc, _, _, err = _parse(lib, sam, fa)
         assert rc == -5
+
+
+def _snapshot(hb):
+    n = hb.n_reads
+    d = {"n": n, "L": hb.read_len_header, "max": hb.max_len, "unmapped": hb.n_unmapped, "lines": hb.n_lines}
+    for name, dt in (("pos", np.uint32), ("flag", np.uint16), ("seq_len", np.uint16), ("chr", np.uint32)):
+        d[name] = _arr(getattr(hb, name), n, dt)
+    for name in ("seq", "cigar", "md"):
+        off = _arr(getattr(hb, name + "_off"), n + 1, np.uint64)
+        d[name + "_off"] = off
+        d[name] = _arr(getattr(hb, name), int(off[-1]), np.uint8)
+    return d
+
+
+def test_threaded_ingest_does_not_depend_on_the_worker_count(lib):
+    """cbch_read_sam_mt cuts the file at line starts, parses the ranges in parallel and merges them: same batch, same
+    whole-file facts (second record's length, line and unmapped counts), same error line for any worker count."""
+    cfg = synth.SynthConfig(seed=33, genome_len=300_000, n_chr=3, n_reads=6000, len_min=50, len_max=250, p_sub=0.01, p_indel=0.02, p_clip=0.3)
+    g = synth.make_genome(cfg); b = synth.make_reads(cfg, g)
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g); synth.write_sam(sam, b, g)
+        text = open(sam).read().split("\n")
+        # headers, an unmapped record as the file's second record, and unmapped records sprinkled through the file
+        body = [l for l in text if l and not l.startswith("@")]
+        unm = "u\t4\t*\t0\t0\t*\t*\t0\t0\tACGTACG\tIIIIIII"
+        lines = ["@HD\tVN:1.6", body[0], unm] + [x for i, l in enumerate(body[1:]) for x in ([l, unm] if i % 97 == 0 else [l])]
+        with open(sam, "w") as f:
+            f.write("\n".join(lines) + "\n")
+        f_, ref = Fasta(), None
+        err = C.create_string_buffer(256)
+        assert lib.cbch_read_fasta(fa.encode(), C.byref(f_), err, 256) == 0
+        for T in (1, 2, 3, 7, 16, 64):
+            hb = HBatch()
+            assert lib.cbch_read_sam_mt(sam.encode(), C.byref(f_), 0, T, C.byref(hb), err, 256) == 0, err.value
+            snap = _snapshot(hb)
+            if ref is None:
+                ref = snap
+                assert snap["n"] == b.n_reads and snap["L"] == 7 and snap["unmapped"] == lines.count(unm) and snap["lines"] == len(lines)
+                assert np.array_equal(snap["pos"], b.pos) and np.array_equal(snap["seq"], b.seq[:len(snap["seq"])])
+            else:
+                for k, v in ref.items():
+                    assert np.array_equal(v, snap[k]) if isinstance(v, np.ndarray) else v == snap[k], (T, k)
+        # a record without MD:Z three quarters into the file: every worker count reports the same whole-file line number
+        bad_at = 3 * len(lines) // 4
+        lines[bad_at] = "\t".join(lines[bad_at].split("\t")[:11])
+        with open(sam, "w") as f:
+            f.write("\n".join(lines) + "\n")
+        for T in (1, 5, 32):
+            hb = HBatch()
+            assert lib.cbch_read_sam_mt(sam.encode(), C.byref(f_), 0, T, C.byref(hb), err, 256) == -5
+            assert err.value.decode().startswith(f"line {bad_at + 1}:"), (T, err.value)
