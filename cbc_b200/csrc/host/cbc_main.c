@@ -3,7 +3,7 @@
  *
  *   cbc -c <sam> <out> <ref.fa>     compress   (README.md:59;  checked-in spelling `-c <ratio> ...`, src/main.c:114-123, also accepted)
  *   cbc -d <in>  <out> <ref.fa>     decompress (README.md:67;  checked-in spelling `-x`, src/main.c:136-139, also accepted)
- * options: -b N   reads per block (default 768; the container is the blocked "CBCB" format)
+ * options: -b N   reads per block (default: sized to the GPU, CBCG_BLOCK_AUTO; the container is the blocked "CBCB" format)
  *          -1     single-block mode: the reference's own stream, byte-identical to `program -c 1` built with -DDEBUG
  *          -l     variable-length reads: header read length = longest SEQ (src/main.c -l)
  *          -g N   CUDA device
@@ -29,7 +29,7 @@ static int usage(void) {
 
 int main(int argc, char **argv) {
     int mode = 0, single = 0, var_length = 0, device = 0;
-    uint32_t block_reads = 768;
+    uint32_t block_reads = CBCG_BLOCK_AUTO;                 /* sized to the GPU (cbcg.h) */
     const char *files[4]; int nfiles = 0;
     for (int i = 1; i < argc; i++) {
         const char *a = argv[i];
@@ -50,7 +50,7 @@ int main(int argc, char **argv) {
         files[0] = files[1]; files[1] = files[2]; files[2] = files[3]; nfiles = 3;
     }
     if (!mode || nfiles != 3) { fprintf(stderr, "Missing required filenames\n"); return usage(); }
-    if (!single && block_reads == 0) block_reads = 768;
+    if (!single && block_reads == 0) block_reads = CBCG_BLOCK_AUTO;
 
     char err[256] = "";
     const double t0 = now();

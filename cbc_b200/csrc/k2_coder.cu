@@ -407,6 +407,13 @@ struct Coder {
         finish_bits(false);
     }
 
+    /* Decoder search without the division of arithmetic_get_symbol_range (:373-381): target = floor(A / range) with
+       A = (t - l + 1) n - 1, and for an integer cumulative count c,  c <= target  <=>  c * range <= A.  The 32 lanes
+       test their candidates with one 64-bit multiply each instead of waiting for a reciprocal and a corrected quotient. */
+    __device__ __forceinline__ uint64_t dec_A(uint32_t n) const { return (uint64_t)(t - a.l + 1u) * n - 1ull; }
+    __device__ __forceinline__ uint32_t dec_range() const { return a.u - a.l + 1u; }
+#define DEC_LE(c) ((uint64_t)(c) * range <= A)               /* c <= target */
+
     /* one coder step given the symbol's interval; decode: caller found (lo, cnt) from the target */
     __device__ __forceinline__ void code_interval(uint32_t lo, uint32_t cnt, uint32_t n) {
         if (MODE == MODE_ENC) ac_encode(lo, cnt, n); else ac_decode_step(lo, cnt, n);
@@ -482,13 +489,13 @@ struct Coder {
                 lo = warp_sum(s); cnt = m[x];
             }
         } else {
-            const uint32_t target = ac_target(a, t, n);
+            const uint64_t A = dec_A(n); const uint32_t range = dec_range();
             const uint4 f = load4(m, 0u, card);
-            if (target < f.x + f.y + f.z + f.w) {                            /* resolved by the first four counts: no scan */
-                uint32_t q = 0; lo = 0; cnt = f.x;
-                if (lo + cnt <= target) { lo += cnt; cnt = f.y; q = 1u; }
-                if (lo + cnt <= target) { lo += cnt; cnt = f.z; q = 2u; }
-                if (lo + cnt <= target) { lo += cnt; cnt = f.w; q = 3u; }
+            const uint32_t s1 = f.x, s2 = s1 + f.y, s3 = s2 + f.z, s4 = s3 + f.w;
+            if (!DEC_LE(s4)) {                                               /* resolved by the first four counts: no scan */
+                const uint32_t q = (uint32_t)DEC_LE(s1) + (uint32_t)DEC_LE(s2) + (uint32_t)DEC_LE(s3);
+                lo = q == 0u ? 0u : (q == 1u ? s1 : (q == 2u ? s2 : s3));
+                cnt = q == 0u ? f.x : (q == 1u ? f.y : (q == 2u ? f.z : f.w));
                 x = q;
             } else {
                 uint32_t carry = 0; bool found = false;
@@ -498,16 +505,16 @@ struct Coder {
                     const uint4 v = load4(m, i, card);
                     const uint32_t mine = v.x + v.y + v.z + v.w;
                     const uint32_t incl = warp_incl_scan(mine) + carry;
-                    const uint32_t hit = __ballot_sync(FULL_MASK, incl > target);     /* lanes past the row add 0: never first */
+                    const uint32_t hit = __ballot_sync(FULL_MASK, !DEC_LE(incl));     /* lanes past the row add 0: never first */
                     if (hit) {
                         const uint32_t h = (uint32_t)__ffs(hit) - 1u;
                         const uint32_t before = __shfl_sync(FULL_MASK, incl - mine, h);
                         const uint32_t c0 = __shfl_sync(FULL_MASK, v.x, h), c1 = __shfl_sync(FULL_MASK, v.y, h);
                         const uint32_t c2 = __shfl_sync(FULL_MASK, v.z, h), c3 = __shfl_sync(FULL_MASK, v.w, h);
-                        uint32_t q = 0; lo = before; cnt = c0;
-                        if (lo + cnt <= target) { lo += cnt; cnt = c1; q = 1u; }
-                        if (lo + cnt <= target) { lo += cnt; cnt = c2; q = 2u; }
-                        if (lo + cnt <= target) { lo += cnt; cnt = c3; q = 3u; }
+                        const uint32_t t1 = before + c0, t2 = t1 + c1, t3 = t2 + c2;
+                        const uint32_t q = (uint32_t)DEC_LE(t1) + (uint32_t)DEC_LE(t2) + (uint32_t)DEC_LE(t3);
+                        lo = q == 0u ? before : (q == 1u ? t1 : (q == 2u ? t2 : t3));
+                        cnt = q == 0u ? c0 : (q == 1u ? c1 : (q == 2u ? c2 : c3));
                         x = base + 4u * h + q; found = true;
                         break;
                     }
@@ -531,7 +538,7 @@ struct Coder {
         if (err) return 0u;
         uint32_t c0 = M->rlenk[k][0], n = M->rlenk[k][1];
         if (MODE == MODE_ENC) { if (x != 0u) { err = CBCG_ERR_INPUT; return 0u; } }
-        else { if (ac_target(a, t, n) >= c0) { err = CBCG_ERR_CORRUPT; return 0u; } }
+        else { const uint64_t A = dec_A(n); const uint32_t range = dec_range(); if (DEC_LE(c0)) { err = CBCG_ERR_CORRUPT; return 0u; } }
         code_interval(0u, c0, n);
         c0 += 10u; n += 10u;
         if (n >= CBCG_RESCALE) { c0 = (c0 >> 1) + 1u; n = c0 + 254u; }
@@ -559,9 +566,11 @@ struct Coder {
             }
             lo = x + warp_sum(extra);
         } else {
-            const uint32_t target = ac_target(a, t, n);
+            /* the touched values are tested with DEC_LE; the target itself (one division) is only needed when the
+               symbol turns out to be an untouched value, whose ordinal is target minus the extras below it */
+            const uint64_t A = dec_A(n); const uint32_t range = dec_range();
             uint32_t carry = 0; bool done = false;
-            lo = target; cnt = 1u; x = 0;
+            lo = 0; cnt = 1u; x = 0;
             for (uint32_t base = 0; base < used && !done; base += 32u) {
                 const uint32_t i = base + lane;
                 const bool valid = i < used;
@@ -570,20 +579,20 @@ struct Coder {
                 const uint32_t e = c - 1u;
                 const uint32_t incl = warp_incl_scan(e) + carry;
                 const uint32_t E = incl - e;                       /* extras of all touched values below this one */
-                const uint32_t A = k + E;                          /* cumulative count at the start of value k */
-                const uint32_t below = __ballot_sync(FULL_MASK, valid && (A + c <= target));
+                const uint32_t Ak = k + E;                         /* cumulative count at the start of value k */
+                const uint32_t below = __ballot_sync(FULL_MASK, valid && DEC_LE(Ak + c));
                 const uint32_t nb = (uint32_t)__popc(below);
                 if (nb == 32u) { carry = __shfl_sync(FULL_MASK, incl, 31); continue; }
                 const uint32_t Ec = __shfl_sync(FULL_MASK, E, nb);
-                const uint32_t Ac = __shfl_sync(FULL_MASK, A, nb);
+                const uint32_t Ac = __shfl_sync(FULL_MASK, Ak, nb);
                 const uint32_t cc = __shfl_sync(FULL_MASK, c, nb);
                 const uint32_t kc = __shfl_sync(FULL_MASK, k, nb);
                 const bool vc = (base + nb) < used;
-                if (vc && Ac <= target) { x = kc; lo = Ac; cnt = cc; found_idx = (int)(base + nb); }
-                else { x = target - Ec; lo = target; cnt = 1u; }
+                if (vc && DEC_LE(Ac)) { x = kc; lo = Ac; cnt = cc; found_idx = (int)(base + nb); }
+                else { const uint32_t target = ac_target(a, t, n); x = target - Ec; lo = target; cnt = 1u; }
                 carry = Ec; done = true;
             }
-            if (!done) x = target - carry;                         /* every touched value lies below */
+            if (!done) { const uint32_t target = ac_target(a, t, n); x = target - carry; lo = target; cnt = 1u; }   /* every touched value lies below */
             if (x > 0xffffu) { err = CBCG_ERR_CORRUPT; return 0u; }
         }
         code_interval(lo, cnt, n);
@@ -667,12 +676,12 @@ struct Coder {
             }
             if (!found) { slot = 0; lo = 0; cnt = __shfl_sync(FULL_MASK, pos_rc, 0); }
         } else {
-            const uint32_t target = ac_target(a, t, pos_n);
+            const uint64_t A = dec_A(pos_n); const uint32_t range = dec_range();
             uint32_t carry = 0; bool found = false;
             for (uint32_t base = 0; base < pos_card; base += 32u) {
                 uint32_t v, c; pos_load(base, v, c);
                 const uint32_t incl = warp_incl_scan(c) + carry;
-                const uint32_t hit = __ballot_sync(FULL_MASK, (base + lane) < pos_card && incl > target);
+                const uint32_t hit = __ballot_sync(FULL_MASK, (base + lane) < pos_card && !DEC_LE(incl));
                 if (hit) {
                     const uint32_t h = (uint32_t)__ffs(hit) - 1u;
                     cnt = __shfl_sync(FULL_MASK, c, h);
@@ -1060,7 +1069,11 @@ S_RLEN0:
        coded or the model rescales, so it is remembered instead of re-summed */
     if (MODE != MODE_LIST && rl_x < 255u) {
         if (MODE == MODE_ENC) pre = (x == rl_x);
-        else { const uint32_t tg = ac_target(C.a, C.t, m[255]); pre = tg >= rl_lo && tg < rl_lo + m[rl_x]; if (pre) x = rl_x; }
+        else {
+            const uint64_t A = C.dec_A(m[255]); const uint32_t range = C.dec_range();
+            pre = DEC_LE(rl_lo) && !DEC_LE(rl_lo + m[rl_x]);
+            if (pre) x = rl_x;
+        }
         pre_lo = rl_lo;
     }
     goto CODE;
