@@ -778,6 +778,10 @@ extern "C" uint64_t cbcg_encode_bound(const cbcg_batch *b, const cbcg_encode_opt
  * cbcg_decode start returning text while the large blocks are still being decoded. The cut is recorded in the
  * container's index like any other; the coded bits of a block depend only on its reads and its generation. */
 #define PIPE_FALLBACK 1            /* not an error: the caller takes the one-stream path */
+#define PIPE_CHUNKS 5u             /* tail chunks (after the head that feeds the early generations); <= PIPE_MAX - 1 */
+/* shares of the tail per chunk. Shrinking shares (0.30 .. 0.10) with a steeper ramp were measured and did not pay: a
+ * group ends with its slowest block, and small blocks spread more (15.2 + 16.1 ms against 15.6 + 15.7 ms for equal shares). */
+static const double PIPE_SHARE[PIPE_CHUNKS] = { 0.20, 0.20, 0.20, 0.20, 0.20 };
 static uint64_t pipe_min_reads() {
     const char *e = getenv("CBCG_PIPE_MIN_READS");
     return e ? strtoull(e, nullptr, 10) : (1ull << 20);
@@ -798,8 +802,6 @@ static int pipe_init(cbcg_ctx *ctx) {
     ctx->pipe_ready = true;
     return 0;
 }
-#define PIPE_CHUNKS 5u             /* tail chunks (after the head that feeds the early generations); <= PIPE_MAX - 1 */
-
 static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encode_opts *opts) {
     static const uint32_t sc[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sr[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
     const uint64_t n = b->n_reads;
@@ -818,7 +820,14 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     uint64_t cut[PIPE_CHUNKS + 2];
     const uint64_t head_end = ((early + tile - 1) / tile + 1) * tile;
     cut[0] = 0; cut[1] = head_end;
-    for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) cut[c + 1] = c == PIPE_CHUNKS ? n : head_end + ((n - head_end) * c / PIPE_CHUNKS) / tile * tile;
+    /* tail chunks by their share of the tail (PIPE_SHARE) */
+    {
+        double acc = 0;
+        for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) {
+            acc += PIPE_SHARE[c - 1];
+            cut[c + 1] = c == PIPE_CHUNKS ? n : head_end + (uint64_t)((double)(n - head_end) * acc) / tile * tile;
+        }
+    }
     CU(cudaEventRecord(ctx->ev[0], ctx->st));
     CU(cudaStreamWaitEvent(ctx->cs, ctx->ev[0], 0));        /* copies start after whatever the caller left on the main stream */
     uint64_t h2d = 0;
@@ -837,8 +846,8 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     double hi, lo; pipe_ramp(&hi, &lo);
     std::vector<SizeStep> ramp;
     double mult[PIPE_CHUNKS], inv = 0;
-    for (uint32_t c = 0; c < PIPE_CHUNKS; c++) { mult[c] = hi - (hi - lo) * (double)c / (double)(PIPE_CHUNKS - 1); inv += 1.0 / mult[c]; }
-    inv /= PIPE_CHUNKS;                                     /* > 1: more blocks than resident slots, the last ones would queue */
+    for (uint32_t c = 0; c < PIPE_CHUNKS; c++) { mult[c] = hi - (hi - lo) * (double)c / (double)(PIPE_CHUNKS - 1); inv += PIPE_SHARE[c] / mult[c]; }
+    /* inv > 1: more blocks than resident slots, the last ones would queue */
     for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) {
         const double m = mult[c - 1] * (inv > 1.0 ? inv : 1.0);
         ramp.push_back({ cut[c + 1], (uint32_t)std::max(64.0, std::min(2.0 * CBCG_BLOCK_AUTO_MAX, m * used.block_reads)) });
@@ -1239,10 +1248,31 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
     const uint32_t last_first = ctx->gens.back().first, last_n = ctx->gens.back().second;
     uint64_t early_reads = 0;
     for (uint32_t k = 0; k < last_first; k++) early_reads += hb[k].n_reads;
-    /* groups of last-generation blocks with about equal read counts */
+    /* groups of last-generation blocks: the size classes the encoder's ramp left (blocks of one class end together),
+       else about equal read counts */
     uint32_t gb[PIPE_CHUNKS + 1]; uint64_t gr[PIPE_CHUNKS + 1];
     gb[0] = last_first; gr[0] = early_reads;
+    bool by_class = false;
     {
+        uint32_t marks[PIPE_CHUNKS + 1], nm = 0, ref_size = hb[last_first].n_reads;
+        for (uint32_t k = last_first + 1; k + 1 < last_first + last_n && nm <= PIPE_CHUNKS; k++) {
+            const uint32_t sz = hb[k].n_reads;
+            if (hb[k].chr == hb[k - 1].chr && (sz * 8u > ref_size * 9u || sz * 9u < ref_size * 8u) && sz == hb[k + 1].n_reads) {
+                if (nm < PIPE_CHUNKS + 1) marks[nm] = k;
+                nm++; ref_size = sz;
+            }
+        }
+        if (nm >= 1 && nm <= PIPE_CHUNKS - 1) {
+            uint64_t r = early_reads; uint32_t k = last_first, g = 1;
+            for (; g <= PIPE_CHUNKS; g++) {
+                const uint32_t stop = (g <= nm) ? last_first + ((marks[g - 1] - last_first + 3u) & ~3u) : last_first + last_n;   /* whole CTAs */
+                while (k < stop && k < last_first + last_n) r += hb[k++].n_reads;
+                gb[g] = k; gr[g] = r;
+            }
+            by_class = true;
+        }
+    }
+    if (!by_class) {
         uint32_t k = last_first; uint64_t r = early_reads;
         for (uint32_t g = 1; g <= PIPE_CHUNKS; g++) {
             const uint64_t want = early_reads + (nr - early_reads) * g / PIPE_CHUNKS;
