@@ -77,6 +77,22 @@ def test_blocked_container_roundtrip(block_reads):
     assert n == b.n_reads and decoded == b.seq_lines()
 
 
+def test_container_v3_fixed_length_flag_and_recoding_with_a_given_cut():
+    """Equal-length input sets CBCG_MODE_FIXED_LEN (no length symbol), variable-length input does not; the restatement
+    re-encodes a batch with the cut of an existing container (what the GPU's self-chosen cuts are checked with)."""
+    import struct
+    for lens, L, fixed in (((100, 100), 100, True), ((50, 250), 250, False)):
+        cfg = synth.SynthConfig(seed=91, genome_len=120_000, n_chr=2, n_reads=6000, len_min=lens[0], len_max=lens[1], p_sub=0.01, p_indel=0.004, p_clip=0.1)
+        g = synth.make_genome(cfg); b = synth.make_reads(cfg, g)
+        for gen_mode in (0, 1):
+            c = O.encode_blocked(b, g, L, 384, gen_mode)
+            version, mode = struct.unpack_from("<I", c, 4)[0], struct.unpack_from("<I", c, 36)[0]
+            assert version == 3 and (mode & 0xff) == gen_mode and bool(mode & 0x100) == fixed
+            text, n = O.decode_blocked(c, g)
+            assert n == b.n_reads and text == b.seq_lines()
+            assert O.encode_like(c, b, g) == c
+
+
 @pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("kw,L", [
     (dict(seed=101, genome_len=300_000, n_reads=30_000, len_min=100, len_max=100, p_sub=0.005, p_indel=0.001), 100),
