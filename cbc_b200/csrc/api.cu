@@ -725,6 +725,17 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     cudaEventElapsedTime(&S.ms_gather, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&S.ms_total, ctx->ev[0], ctx->ev[4]);
 
+    if (getenv("CBCG_BLOCK_TIMES") && !ctx->gens.empty()) {  /* with -DK2_BLOCK_TIMES: balance of the last generation */
+        const uint32_t f0 = ctx->gens.back().first, cnt = ctx->gens.back().second;
+        std::vector<double> t;
+        for (uint32_t k = f0; k < f0 + cnt; k++) if (ctx->hblocks[k].n_reads == ctx->hblocks[f0].n_reads) t.push_back((double)ctx->hblocks[k].sym_off * 1e-6);
+        std::sort(t.begin(), t.end());
+        double sum = 0; for (double x : t) sum += x;
+        double init = 0; for (uint32_t k = f0; k < f0 + cnt; k++) init += (double)ctx->hblocks[k].pa_touched * 1e-6;
+        fprintf(stderr, "[cbcg] mean block set-up (workspace, models from the snapshot, coder init): %.4f ms\n", init / cnt);
+        if (!t.empty()) fprintf(stderr, "[cbcg] last generation, %zu full blocks of %u reads: block time mean %.3f ms, median %.3f, p90 %.3f, p99 %.3f, max %.3f ms\n",
+                                t.size(), ctx->hblocks[f0].n_reads, sum / t.size(), t[t.size() / 2], t[t.size() * 9 / 10], t[t.size() * 99 / 100], t.back());
+    }
     finish_encode(ctx, opts, legacy, fixed, n, n_edits, nb, payload_total);
     return CBCG_OK;
 }

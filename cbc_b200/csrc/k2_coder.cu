@@ -883,6 +883,9 @@ k2_coder_kernel(CoderParams P) {
     constexpr bool lean = !LEGACY && MODE != MODE_LIST;  /* blocked containers never code same_ref / length bytes 1..3 */
     const bool fixed = lean && P.fixed_len != 0;         /* ... nor length byte 0 when every read is L bases long */
 
+#ifdef K2_BLOCK_TIMES
+    unsigned long long k2_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k2_t0));
+#endif
     Coder<MODE> C;
     C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &sshared[warp].m;
     C.primed = primed; C.lean = lean;
@@ -918,6 +921,9 @@ k2_coder_kernel(CoderParams P) {
     if (!legacy && MODE != MODE_LIST && !primed) C.init_L_models();
     if (!legacy && MODE == MODE_DEC && B.chr >= P.genome.n_chr) C.err = CBCG_ERR_NO_REFERENCE;
 
+#ifdef K2_BLOCK_TIMES
+    unsigned long long k2_t_init; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k2_t_init));
+#endif
     /* ---- machine state */
     uint32_t state = legacy ? ST_HDR : ST_READ;
     uint32_t k = 0;                                      /* sub-index inside a state (header byte, edit ordinal ...) */
@@ -1269,6 +1275,9 @@ M_DONE:
         if (lane < C.pos_card) { C.pos_gval()[lane] = C.pos_rv; C.pos_gcnt()[lane] = C.pos_rc; }
         if (lane == 0) { B.pos_card = C.pos_card; B.n_rows = C.n_rows; B.pa_touched = C.pa_init ? 1u : 0u; }
     }
+#ifdef K2_BLOCK_TIMES                                       /* experiment: how long each block took (ns), for the balance of a generation */
+    if (lane == 0 && MODE != MODE_LIST) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); B.sym_off = t1 - k2_t0; if (!P.fin) B.pa_touched = (uint32_t)(k2_t_init - k2_t0); }
+#endif
     if (lane == 0) {
         B.n_symbols = (MODE == MODE_LIST) ? C.list_n : C.n_symbols;
         if (MODE == MODE_ENC) B.payload_bytes = C.out_pos;

@@ -64,15 +64,20 @@ __device__ __forceinline__ uint4 lds_16_unaligned(const uint8_t *base, int32_t o
     const uint32_t sh = ((uint32_t)off & 3u) * 8u;
     return make_uint4(__funnelshift_r(y0, y1, sh), __funnelshift_r(y1, y2, sh), __funnelshift_r(y2, y3, sh), __funnelshift_r(y3, y4, sh));
 }
-/* One word of a piece that holds a line end: bytes below r from a (the read that ends), byte r = '\n', bytes above r
- * from b (the next read); r < 0: all from b, r >= 4: all from a. */
-__device__ __forceinline__ uint32_t k3_merge(uint32_t a, uint32_t b, int32_t r) {
-    if (r >= 4) return a;
-    if (r < 0) return b;
-    const uint32_t sh = 8u * (uint32_t)r;
-    const uint32_t lo = (1u << sh) - 1u;
-    const uint32_t hi = (uint32_t)(0xffffffff00ull << sh);
-    return (a & lo) | ((uint32_t)'\n' << sh) | (b & hi);
+/* A piece that holds a line end: bytes below `rem` from a (the read that ends), byte rem = '\n', bytes above from b (the
+ * next read). Only the word with the '\n' mixes the two sources; the words before it are a's, the ones after it b's. */
+__device__ __forceinline__ uint4 k3_merge(const uint4 a, const uint4 b, uint32_t rem) {       /* rem in 0..15 */
+    const uint32_t kk = rem >> 2, sh = (rem & 3u) * 8u;
+    const uint32_t as = kk == 0u ? a.x : (kk == 1u ? a.y : (kk == 2u ? a.z : a.w));
+    const uint32_t bs = kk == 0u ? b.x : (kk == 1u ? b.y : (kk == 2u ? b.z : b.w));
+    const uint32_t lo = (1u << sh) - 1u;                                                    /* bytes below the '\n' */
+    const uint32_t mix = (as & lo) | ((uint32_t)'\n' << sh) | (bs & ~(lo | (0xffu << sh)));
+    uint4 v;
+    v.x = kk == 0u ? mix : a.x;                                                             /* word 0 is never after the '\n' */
+    v.y = kk == 1u ? mix : (kk > 1u ? a.y : b.y);
+    v.z = kk == 2u ? mix : (kk > 2u ? a.z : b.z);
+    v.w = kk == 3u ? mix : b.w;
+    return v;
 }
 
 __global__ void __launch_bounds__(K3_THREADS)
@@ -208,11 +213,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
             const int32_t j0 = (int32_t)(16u * c) - (int32_t)(shift + S.out_off[i]);   /* read-relative index of the piece's first byte */
             const int32_t rem = (int32_t)S.rec[i].len - j0;                             /* bases of read i from there on */
             uint4 v = lds_16_unaligned(S.ref, (int32_t)S.so[i] + j0);
-            if (rem < 16) {
-                const uint4 nx = lds_16_unaligned(S.ref, (int32_t)S.so[i + 1u] - rem - 1);
-                v.x = k3_merge(v.x, nx.x, rem); v.y = k3_merge(v.y, nx.y, rem - 4);
-                v.z = k3_merge(v.z, nx.z, rem - 8); v.w = k3_merge(v.w, nx.w, rem - 12);
-            }
+            if (rem < 16) v = k3_merge(v, lds_16_unaligned(S.ref, (int32_t)S.so[i + 1u] - rem - 1), (uint32_t)rem);   /* rem >= 0: the piece starts inside line i */
             *reinterpret_cast<uint4 *>(S.out + 16u * c) = v;
         }
     }
