@@ -170,6 +170,19 @@ __device__ static void walk_read(const uint8_t *read, uint32_t len, const uint8_
     if (out.n_snps > 255u || out.n_dels > 255u || out.n_ins > 255u) out.err = 1;
 }
 
+/* 16 bytes from byte offset `off` (any alignment) of a 16-byte-aligned shared array: two aligned 16-byte loads, the
+ * word rotation as selects, the byte rotation as funnel shifts (the same fetch as K3's copy path). */
+__device__ __forceinline__ uint4 k1_lds16(const uint8_t *base, uint32_t off) {
+    const uint4 q0 = *reinterpret_cast<const uint4 *>(base + (off & ~15u));
+    const uint4 q1 = *reinterpret_cast<const uint4 *>(base + (off & ~15u) + 16u);
+    const bool r2 = (off & 8u) != 0u, r1 = (off & 4u) != 0u;
+    const uint32_t x0 = r2 ? q0.z : q0.x, x1 = r2 ? q0.w : q0.y, x2 = r2 ? q1.x : q0.z, x3 = r2 ? q1.y : q0.w,
+                   x4 = r2 ? q1.z : q1.x, x5 = r2 ? q1.w : q1.y;
+    const uint32_t y0 = r1 ? x1 : x0, y1 = r1 ? x2 : x1, y2 = r1 ? x3 : x2, y3 = r1 ? x4 : x3, y4 = r1 ? x5 : x4;
+    const uint32_t sh = (off & 3u) * 8u;
+    return make_uint4(__funnelshift_r(y0, y1, sh), __funnelshift_r(y1, y2, sh), __funnelshift_r(y2, y3, sh), __funnelshift_r(y3, y4, sh));
+}
+
 struct K1Smem {
     uint64_t bar;
     uint64_t tile_base;
@@ -183,7 +196,7 @@ struct K1Smem {
     uint16_t len[K1_TILE];
     uint16_t chr_ok[K1_TILE];        /* bit 0: read may use the staged window, bit 1: read passes the input checks */
     uint16_t ecache[K1_TILE][K1_ECACHE];
-    __align__(16) uint8_t ref[K1_REF_CAP + 16];
+    __align__(16) uint8_t ref[K1_REF_CAP + 64];
     __align__(16) uint8_t seq[16];   /* really K1_TILE * max_len + 48 (dynamic) */
 };
 
@@ -264,23 +277,13 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
             if (i < nr) {
                 const uint32_t fl = S.chr_ok[i], len = S.len[i], soff = S.soff[i];
                 ok = (fl & 2u) != 0u;
-                if (ok && (fl & 1u)) {
-                    const uint32_t o = sub * 16u;
-                    if (o < len) {
-                        const uint32_t so = soff + o, ro = S.roff[i] + o, rem = len - o;
-                        const uint32_t *sw = reinterpret_cast<const uint32_t *>(S.seq + (so & ~3u));
-                        const uint32_t *rw = reinterpret_cast<const uint32_t *>(S.ref + (ro & ~3u));
-                        const uint32_t ss = (so & 3u) * 8u, rs = (ro & 3u) * 8u;
-                        uint32_t s_prev = sw[0], r_prev = rw[0];
-#pragma unroll
-                        for (uint32_t q = 0; q < 4u; q++) {
-                            const uint32_t s_next = sw[q + 1u], r_next = rw[q + 1u];
-                            uint32_t x = __funnelshift_r(s_prev, s_next, ss) ^ __funnelshift_r(r_prev, r_next, rs);
-                            const uint32_t vb = rem > 4u * q ? rem - 4u * q : 0u;           /* bytes of this word inside the read */
-                            if (vb < 4u) x &= (1u << (8u * vb)) - 1u;
-                            diff |= x;
-                            s_prev = s_next; r_prev = r_next;
-                        }
+                if (ok && (fl & 1u) && len >= 16u) {
+                    /* 16-byte pieces at read offsets 0, 16, 32, ... with the last one pulled back to len - 16: every piece
+                       lies inside the read, so nothing has to be masked; both sides are fetched at their own alignment */
+                    const uint32_t o = min(sub * 16u, len - 16u);
+                    if (sub * 16u < len) {
+                        const uint4 sv = k1_lds16(S.seq, soff + o), rv = k1_lds16(S.ref, S.roff[i] + o);
+                        diff = (sv.x ^ rv.x) | (sv.y ^ rv.y) | (sv.z ^ rv.z) | (sv.w ^ rv.w);
                     }
                 } else if (ok) {                          /* window miss: straight from HBM */
                     const uint8_t *rp = g.bases + g.chr_off[b.chr[r0 + i]] + (S.pos[i] - 1u);
@@ -294,13 +297,16 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
     __syncthreads();
 
     /* ---- phase 2: lane per read, count edits */
+    /* (staging the tile's CIGAR / MD text in shared memory as well was measured: 7 % slower, the extra bulk copies and
+       the lost CTA per SM cost more than the L1 hits they replace) */
+    const uint8_t *my_cig = b.cigar + my_co, *my_md = b.md + my_mo;
     uint32_t my_cnt = 0, my_total = 0;
     if (tid < nr) {
         my_cnt = S.cnt[tid];
         bool bad = !seq_ok || my_pos == 0u || my_len == 0u || my_len > CBCG_MAX_READ_LEN || my_chr >= g.n_chr;
         if (!bad && !(my_cnt >> 24)) {
             EditSink sink = { nullptr, 0u, 0u, 0u, 0u, 0u, 0, S.ecache[tid] };
-            walk_read(S.seq + S.soff[tid], my_len, b.cigar + my_co, my_clen, b.md + my_mo, my_mlen, sink);
+            walk_read(S.seq + S.soff[tid], my_len, my_cig, my_clen, my_md, my_mlen, sink);
             if (sink.err) bad = true;
             else { my_cnt = sink.n_snps | (sink.n_dels << 8) | (sink.n_ins << 16); my_total = sink.n_snps + sink.n_dels + sink.n_ins; }
         }
@@ -345,7 +351,7 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
                 }
             } else {
                 EditSink sink = { edits + off, rec.n_dels, rec.n_snps, 0u, 0u, 0u, 0, nullptr };
-                walk_read(S.seq + S.soff[tid], my_len, b.cigar + my_co, my_clen, b.md + my_mo, my_mlen, sink);
+                walk_read(S.seq + S.soff[tid], my_len, my_cig, my_clen, my_md, my_mlen, sink);
             }
         }
     }
