@@ -20,7 +20,7 @@ b = synth.make_reads(cfg, g)
 c = Codec(0)
 c.set_reference(g)
 pb = pin_batch(b)
-out_c = pinned_empty(16 << 20, np.uint8)
+out_c = pinned_empty(max(16 << 20, b.n_reads * 4), np.uint8)
 out_t = pinned_empty(b.total_bases() + b.n_reads + 64, np.uint8)
 ref = b.seq_lines()
 AUTO = 0xffffffff
