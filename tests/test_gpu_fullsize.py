@@ -111,6 +111,36 @@ def test_pipelined_encode_many_chromosomes_and_variable_length(codec, monkeypatc
         assert n == b.n_reads and text == b.seq_lines()
 
 
+def test_pipelined_decode_of_damaged_containers_reports_and_returns(codec, monkeypatch):
+    """The pipelined decoder on a container with a damaged payload, a truncated one and too small an output buffer:
+    a status (or, for damage the coder cannot see, different text), never a hang, and the context stays usable."""
+    from cbc_b200.codec import CbcgError
+    monkeypatch.setenv("CBCG_PIPE_MIN_READS", "200000")
+    cfg = synth.SynthConfig.named("config2", scale=0.1)                   # ~300 k reads
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    codec.set_reference(g)
+    cont = codec.compress(b, 150, block_reads=AUTO, gen_mode=1)
+    good, n = codec.decompress(cont)
+    assert n == b.n_reads and good == b.seq_lines()
+    bad = bytearray(cont)
+    for k in range(len(bad) // 2, len(bad) // 2 + 64):
+        bad[k] ^= 0x5a
+    try:
+        text, n2 = codec.decompress(bytes(bad))
+        assert text != good or n2 != n
+    except CbcgError as e:
+        assert e.status in (-9, -5, -6, -8, -10, -11)                     # corrupt, capacity, input, format, limit, internal
+    with pytest.raises(CbcgError):
+        codec.decompress(cont[:len(cont) - 1000])                          # payload truncated
+    out = np.empty(1000, np.uint8)
+    with pytest.raises(CbcgError) as e:
+        codec.decompress_into(np.frombuffer(cont, np.uint8), out)          # room for 1000 bytes of text
+    assert e.value.status == -5
+    text, n3 = codec.decompress(cont)                                      # and the context still works
+    assert n3 == b.n_reads and text == good
+
+
 def test_pipelined_full_size_budget(codec):
     cfg = synth.SynthConfig.named("config2")
     g = synth.make_genome(cfg)
