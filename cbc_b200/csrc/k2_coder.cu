@@ -943,29 +943,33 @@ k2_coder_kernel(CoderParams P) {
     /* The machine is threaded with gotos: every state has a set-up block S_x (describe its symbol, then CODE) and a
        post block P_x (consume the value, jump straight to the next state's set-up). One dispatch per symbol --
        CODE's switch on `state` -- instead of a loop with a set-up switch and a post switch. */
-    uint32_t kind, card, step, x, key, ctx, pre_lo, y, slot;
+    uint32_t card, step, x, key, ctx, pre_lo, y, slot;
     uint32_t *m;
     bool is_var, pre;
-#define SYMBOL(KIND, M, CARD, STEP, X, KEY) do { kind = (KIND); m = (M); card = (CARD); step = (STEP); x = (X); key = (KEY); is_var = false; pre = false; pre_lo = 0; } while (0)
-#define VAR_SYMBOL(CTX, X) do { kind = K_DENSE; m = nullptr; ctx = (CTX); card = C.L; step = 10u; x = (X); key = CBCG_SYM_KEY(CBCG_S_VAR, ctx); is_var = true; pre = false; pre_lo = 0; } while (0)
-    kind = K_NONE; card = step = x = key = ctx = pre_lo = y = 0; slot = 1u; m = nullptr; is_var = pre = false;
+#define SYMBOL(KIND, M, CARD, STEP, X, KEY) do { m = (M); card = (CARD); step = (STEP); x = (X); key = (KEY); is_var = false; pre = false; pre_lo = 0; } while (0)
+#define VAR_SYMBOL(CTX, X) do { m = nullptr; ctx = (CTX); card = C.L; step = 10u; x = (X); key = CBCG_SYM_KEY(CBCG_S_VAR, ctx); is_var = true; pre = false; pre_lo = 0; } while (0)
+    card = step = x = key = ctx = pre_lo = y = 0; slot = 1u; m = nullptr; is_var = pre = false;
     if (C.err) goto M_DONE;
     if (legacy) goto S_HDR;
     goto S_READ;
 
     /* ================================================ code the described symbol: one call site per model kind */
+    /* POS, FLAG and the constant length bytes have one state each: their coder call sits in that state and continues
+       straight to its post block (CODE_DIRECT), no dispatch at all. Every other symbol is a dense model and comes here. */
+#define CODE_DIRECT(CALL, STREAM, CTXV, XV, NEXT) do { \
+        y = (XV); slot = 1u; \
+        if (MODE == MODE_LIST) C.list_put((STREAM), (CTXV), (XV)); else y = (CALL); \
+        if (C.err) goto M_DONE; \
+        goto NEXT; } while (0)
 CODE:
     if (is_var && MODE != MODE_LIST) { m = C.var_row(ctx); if (!m) goto M_DONE; }
-    y = x; slot = 1u;
+    y = x;
     if (MODE == MODE_LIST) C.list_put(key >> 24, key & 0xffffffu, x);
-    else if (kind == K_DENSE) y = C.sym_dense(m, card, step, x, pre, pre_lo);
-    else if (kind == K_FLAG) y = C.sym_flag(x);
-    else if (kind == K_POS) y = C.sym_pos_main(x, slot);
-    else y = C.sym_rlenk(k - 1u, x);
+    else y = C.sym_dense(m, card, step, x, pre, pre_lo);
     if (C.err) goto M_DONE;
     switch (state) {
         case ST_HDR: goto P_HDR;       case ST_SAMEREF: goto P_SAMEREF; case ST_RNAME: goto P_RNAME;   case ST_RLEN0: goto P_RLEN0;
-        case ST_RLENK: goto P_RLENK;   case ST_POS: goto P_POS;         case ST_POSESC: goto P_POSESC; case ST_FLAG: goto P_FLAG;
+        case ST_POSESC: goto P_POSESC;
         case ST_MATCH: goto P_MATCH;   case ST_SNPS: goto P_SNPS;       case ST_INDELS: goto P_INDELS; case ST_DEL: goto P_DEL;
         case ST_SNPVAR: goto P_SNPVAR; case ST_SNPCHAR: goto P_SNPCHAR; case ST_INSVAR: goto P_INSVAR; case ST_INSCHAR: goto P_INSCHAR;
         case ST_ENDMARK: goto P_ENDMARK;
@@ -1090,8 +1094,7 @@ P_RLEN0:
     k = 1;
 S_RLENK:
     state = ST_RLENK;
-    SYMBOL(K_RLENK, nullptr, 0u, 0u, 0u, CBCG_SYM_KEY(CBCG_S_RLENGTH, k));
-    goto CODE;
+    CODE_DIRECT(C.sym_rlenk(k - 1u, 0u), CBCG_S_RLENGTH, k, 0u, P_RLENK);
 P_RLENK:
     if (MODE == MODE_DEC) len |= y << (8u * k);
     if (++k < 4u) goto S_RLENK;
@@ -1099,13 +1102,13 @@ P_RLENK:
     /* ---- position (src/read_compression.c:113-159): x = pos - prevPos + 1 through the growing alphabet */
 S_POS:
     state = ST_POS;
-    SYMBOL(K_POS, nullptr, 0u, 0u, 0u, CBCG_SYM_KEY(CBCG_S_POS_X, 0u));
+    x = 0u;
     if (MODE != MODE_DEC) {
         if (pos == 0u || len == 0u || len > CBCG_MAX_READ_LEN) { C.err = CBCG_ERR_INPUT; goto M_DONE; }
         if (pos < prev_pos || pos - prev_pos + 1u > CBCG_MAX_POS_X) { C.err = CBCG_ERR_INPUT; goto M_DONE; }
         x = pos - prev_pos + 1u;
     }
-    goto CODE;
+    CODE_DIRECT(C.sym_pos_main(x, slot), CBCG_S_POS_X, 0u, x, P_POS);
 P_POS:
     posx = (MODE == MODE_DEC) ? y : x;
     if (MODE == MODE_LIST || slot != 0u) goto M_POS_DONE;
@@ -1133,8 +1136,8 @@ M_POS_DONE:
 
     /* ---- flag, match */
     state = ST_FLAG;
-    SYMBOL(K_FLAG, nullptr, 0u, 0u, flag, CBCG_SYM_KEY(CBCG_S_FLAG, 0u));
-    goto CODE;
+    x = flag;
+    CODE_DIRECT(C.sym_flag(x), CBCG_S_FLAG, 0u, x, P_FLAG);
 P_FLAG:
     flag = y; strand = (flag >> 4) & 1u;                                   /* :57-60 */
     state = ST_MATCH;
@@ -1264,6 +1267,7 @@ P_ENDMARK:
 M_DONE:
 #undef SYMBOL
 #undef VAR_SYMBOL
+#undef CODE_DIRECT
 
     if (MODE == MODE_ENC && !C.err) { if (P.short_flush && !legacy) C.ac_flush_short(); else C.ac_flush(); }
     if (C.err) dev_set_error(P.err, C.err, ((uint64_t)b << 20) | (n_done & 0xfffffu));
