@@ -961,6 +961,13 @@ k2_coder_kernel(CoderParams P) {
         if (MODE == MODE_LIST) C.list_put((STREAM), (CTXV), (XV)); else y = (CALL); \
         if (C.err) goto M_DONE; \
         goto NEXT; } while (0)
+    /* The four dense symbols of nearly every read (match bit, SNP count, SNP position, SNP base) get their own coder
+       call too; the rare states share the CODE site below and its dispatch. */
+#define DENSE_DIRECT(M, CARD, STEP, STREAM, CTXV, XV, NEXT) do { \
+        y = (XV); \
+        if (MODE == MODE_LIST) C.list_put((STREAM), (CTXV), (XV)); else y = C.sym_dense((M), (CARD), (STEP), (XV), false, 0u); \
+        if (C.err) goto M_DONE; \
+        goto NEXT; } while (0)
 CODE:
     if (is_var && MODE != MODE_LIST) { m = C.var_row(ctx); if (!m) goto M_DONE; }
     y = x;
@@ -970,8 +977,8 @@ CODE:
     switch (state) {
         case ST_HDR: goto P_HDR;       case ST_SAMEREF: goto P_SAMEREF; case ST_RNAME: goto P_RNAME;   case ST_RLEN0: goto P_RLEN0;
         case ST_POSESC: goto P_POSESC;
-        case ST_MATCH: goto P_MATCH;   case ST_SNPS: goto P_SNPS;       case ST_INDELS: goto P_INDELS; case ST_DEL: goto P_DEL;
-        case ST_SNPVAR: goto P_SNPVAR; case ST_SNPCHAR: goto P_SNPCHAR; case ST_INSVAR: goto P_INSVAR; case ST_INSCHAR: goto P_INSCHAR;
+        case ST_INDELS: goto P_INDELS; case ST_DEL: goto P_DEL;
+        case ST_INSVAR: goto P_INSVAR; case ST_INSCHAR: goto P_INSCHAR;
         case ST_ENDMARK: goto P_ENDMARK;
         default: C.err = CBCG_ERR_INTERNAL; goto M_DONE;
     }
@@ -1142,8 +1149,8 @@ P_FLAG:
     flag = y; strand = (flag >> 4) & 1u;                                   /* :57-60 */
     state = ST_MATCH;
     ctx = (samepos << 1) | prev_m;
-    SYMBOL(K_DENSE, C.M->match[ctx], 2u, 1u, match, CBCG_SYM_KEY(CBCG_S_MATCH, ctx));
-    goto CODE;
+    x = match;
+    DENSE_DIRECT(C.M->match[ctx], 2u, 1u, CBCG_S_MATCH, ctx, x, P_MATCH);
 P_MATCH:
     match = y; prev_m = y; ne = 0;
     if (MODE == MODE_DEC) { ns = nd = ni = 0; }
@@ -1151,8 +1158,8 @@ P_MATCH:
 
     /* ---- counts (:557-565) */
     state = ST_SNPS;
-    SYMBOL(K_DENSE, C.M->snps, C.L, 10u, ((nd | ni) == 0u) ? ns : 0u, CBCG_SYM_KEY(CBCG_S_SNPS, 0u));
-    goto CODE;
+    x = ((nd | ni) == 0u) ? ns : 0u;
+    DENSE_DIRECT(C.M->snps, C.L, 10u, CBCG_S_SNPS, 0u, x, P_SNPS);
 P_SNPS:
     if (MODE == MODE_DEC) { ns = y; nd = ni = 0; if (y != 0u) goto M_COUNTS_DONE; }
     else if ((nd | ni) == 0u) goto M_COUNTS_DONE;
@@ -1197,8 +1204,11 @@ S_SNPVAR: {
         state = ST_SNPVAR;
         if (MODE != MODE_DEC) ed = e_in[nd + k];
         const uint32_t delta = C.ring_first(pos - 1u + prev, (prev < len) ? pos - 1u + len : pos - 1u + prev, len + 2u);
-        VAR_SYMBOL((((delta << CBCG_BITS_DELTA) + prev) << 1) | strand, CBCG_EDIT_DELTA(ed));
-        goto CODE;
+        ctx = (((delta << CBCG_BITS_DELTA) + prev) << 1) | strand;
+        x = CBCG_EDIT_DELTA(ed);
+        m = nullptr;
+        if (MODE != MODE_LIST) { m = C.var_row(ctx); if (!m) goto M_DONE; }
+        DENSE_DIRECT(m, C.L, 10u, CBCG_S_VAR, ctx, x, P_SNPVAR);
     }
 P_SNPVAR: {
         edp = y;
@@ -1213,8 +1223,8 @@ P_SNPVAR: {
             refb = base_code(ri < C.cold().ref_len ? (uint32_t)C.cold().ref[ri] : 0u);
         } else refb = CBCG_EDIT_REFB(ed);
         state = ST_SNPCHAR;
-        SYMBOL(K_DENSE, C.M->chars[refb], 5u, 8u, CBCG_EDIT_TARGET(ed), CBCG_SYM_KEY(CBCG_S_CHARS, refb));
-        goto CODE;
+        x = CBCG_EDIT_TARGET(ed);
+        DENSE_DIRECT(C.M->chars[refb], 5u, 8u, CBCG_S_CHARS, refb, x, P_SNPCHAR);
     }
 P_SNPCHAR:
     if (MODE == MODE_DEC && lane == 0) P.edits[e_cursor + ne] = CBCG_EDIT(edp, y, refb);
@@ -1268,6 +1278,7 @@ M_DONE:
 #undef SYMBOL
 #undef VAR_SYMBOL
 #undef CODE_DIRECT
+#undef DENSE_DIRECT
 
     if (MODE == MODE_ENC && !C.err) { if (P.short_flush && !legacy) C.ac_flush_short(); else C.ac_flush(); }
     if (C.err) dev_set_error(P.err, C.err, ((uint64_t)b << 20) | (n_done & 0xfffffu));
