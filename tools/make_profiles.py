@@ -41,7 +41,7 @@ json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 out += ["The launch list is of the whole bench command: the device-resident steps (5 coder launches per direction: generations 0-4) and the",
         "pipelined host-buffer steps (cbcg_encode / cbcg_decode: one K1 launch per chunk, one coder and one K3 launch per group).", "",
         "Reading: K2 (`k2_coder_kernel<mode, legacy>`) is serial integer work per block: 20 warps per SM (96 registers, no spills), 56 % of issue",
-        "slots, 18 % + 10 % of stall samples waiting for instruction fetch (66 KB of SASS against a 32 KB L1.5 instruction cache); DRAM < 2 % of peak.",
+        "slots, 20 % + 11 % of stall samples waiting for instruction fetch (95 KB of SASS against a 32 KB L1.5 instruction cache); DRAM < 2 % of peak.",
         "Its DRAM traffic fell from 1.14 GB to 0.49 GB per last-generation launch with deferred var rows (rows touched once are coded from",
         "the snapshot and never copied). K3 runs at 30 % of the measured HBM peak and is bound by instruction issue (60 % of slots, 58 warp",
         "instructions per read); K1 at 19 %, with a fifth of its stall samples at the barrier behind the look-back over tile edit counts",
