@@ -733,6 +733,10 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
         double sum = 0; for (double x : t) sum += x;
         double init = 0; for (uint32_t k = f0; k < f0 + cnt; k++) init += (double)ctx->hblocks[k].pa_touched * 1e-6;
         fprintf(stderr, "[cbcg] mean block set-up (workspace, models from the snapshot, coder init): %.4f ms\n", init / cnt);
+        if (getenv("CBCG_BLOCK_DUMP")) {
+            FILE *f = fopen(getenv("CBCG_BLOCK_DUMP"), "w");
+            if (f) { for (uint32_t k = f0; k < f0 + cnt; k++) fprintf(f, "%u %u %u %llu\n", ctx->hblocks[k].n_reads, ctx->hblocks[k].n_symbols, ctx->hblocks[k].n_edits, (unsigned long long)ctx->hblocks[k].sym_off); fclose(f); }
+        }
         if (!t.empty()) fprintf(stderr, "[cbcg] last generation, %zu full blocks of %u reads: block time mean %.3f ms, median %.3f, p90 %.3f, p99 %.3f, max %.3f ms\n",
                                 t.size(), ctx->hblocks[f0].n_reads, sum / t.size(), t[t.size() / 2], t[t.size() * 9 / 10], t[t.size() * 99 / 100], t.back());
     }

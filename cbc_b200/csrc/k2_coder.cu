@@ -45,6 +45,8 @@
                                   (cold per-warp values live in shared memory, WarpCold); 6 spills and is slower */
 #endif
 #define K2_THREADS  (K2_WARPS * 32u)
+#define LIKELY(c)   __builtin_expect(!!(c), 1)
+#define UNLIKELY(c) __builtin_expect(!!(c), 0)
 #define FLAG_CAP    128u
 #define PA_STRIDE   260u              /* words per 256-symbol model row: 256 counts, n, padding to 16 bytes */
 #define VAR_DIRECT_MIN_EDITS 32768u       /* blocks with more edits index var rows directly by context */
@@ -307,7 +309,7 @@ struct Coder {
         if (k == 0) return;
         acc = (acc << k) | (uint64_t)v;
         nacc += k;
-        if (nacc >= 32u) {
+        if (UNLIKELY(nacc >= 32u)) {
             uint32_t w = (uint32_t)(acc >> (nacc - 32u));
             if (out_pos + 4u <= cold().io_cap) { if (lane == 0) *reinterpret_cast<uint32_t *>(cold().io + out_pos) = __byte_perm(w, 0u, 0x0123); }
             else err = CBCG_ERR_CAPACITY;
@@ -320,7 +322,7 @@ struct Coder {
        low rest_bits of rest. The usual case is one put; long runs go out of line: the hot loop has to fit the
        instruction cache. */
     __device__ __forceinline__ void emit(uint32_t b0, uint32_t run, uint32_t rest, uint32_t rest_bits) {
-        if (run + 1u + rest_bits <= 32u) {
+        if (LIKELY(run + 1u + rest_bits <= 32u)) {
             const uint32_t inv = b0 ? 0u : 0xffffffffu;
             put_bits((b0 << (run + rest_bits)) | ((inv & ((1u << run) - 1u)) << rest_bits) | rest, run + 1u + rest_bits);
         } else {
@@ -349,7 +351,7 @@ struct Coder {
        it is topped up 32 bits at a time, so a symbol costs shifts, not loads. */
     __device__ __forceinline__ uint32_t get_bits(uint32_t k) {               /* k <= 32 */
         if (k == 0) return 0u;
-        if (dcnt < k) {
+        if (UNLIKELY(dcnt < k)) {
             uint32_t w = 0;
             const uint8_t *in = cold().io; const uint32_t in_len = cold().io_cap;
             if (in_pos + 4u <= in_len) {
@@ -371,7 +373,7 @@ struct Coder {
         if (MODE == MODE_DEC) t = get_bits(CBCG_AC_BITS);                    /* :262 */
     }
     __device__ __forceinline__ void ac_encode(uint32_t lo, uint32_t cnt, uint32_t n) {
-        if (cnt == 0u || n == 0u) { err = CBCG_ERR_INPUT; return; }          /* reference: assert :71 / :293 */
+        if (UNLIKELY(cnt == 0u || n == 0u)) { err = CBCG_ERR_INPUT; return; }          /* reference: assert :71 / :293 */
         ac_narrow(a, lo, lo + cnt, n);
         uint32_t k, bits, m; AcInterval nx;
         ac_renorm_shape(a, k, bits, m, nx);
@@ -423,9 +425,10 @@ struct Coder {
     /* ============================================================ dense models (counts[card], n at [card]) */
     /* cnt and n are the symbol's count and the model total the caller just coded with: no reload on the dependent
        chain. A deferred var row (var_ro, see var_row) is not written: the touch is noted in its hash slot instead. */
+    template <bool IS_VAR>
     __device__ __forceinline__ void dense_update(uint32_t *m, uint32_t card, uint32_t step, uint32_t x, uint32_t cnt, uint32_t n) {
         n += step;
-        if (var_ro) {
+        if (IS_VAR && UNLIKELY(var_ro)) {
             var_ro = false;
             if (n < CBCG_RESCALE) {
                 if (lane == 0) var_hash[defer_idx] = ((uint64_t)defer_key << 32) | VAR_DEFERRED | x;
@@ -448,7 +451,7 @@ struct Coder {
         SYNCW();
         if (lane == 0) { m[x] = cnt + step; m[card] = n; }
         SYNCW();
-        if (n >= CBCG_RESCALE) {                                             /* update_model :38-49 */
+        if (UNLIKELY(n >= CBCG_RESCALE)) {                                   /* update_model :38-49 */
             const uint32_t s = rescale_counts(m, card, lane);
             SYNCW();
             if (lane == 0) m[card] = s;
@@ -467,18 +470,25 @@ struct Coder {
         }
         return v;
     }
-    /* pre: the caller already knows the symbol and its cumulative count (pre_lo); no scan. */
+    /* pre: the caller already knows the symbol and its cumulative count (pre_lo); no scan.
+       SMALL (call sites whose alphabet is a constant 2 or 5: match bit, bases): the first four counts always resolve
+       the symbol (card 5: or it is symbol 4), so the scan code is not instantiated there. IS_VAR: the model may be a
+       deferred var row. Both only prune code: every instantiation computes the same thing. */
+    template <int SMALL, bool IS_VAR>
     __device__ __forceinline__ uint32_t sym_dense(uint32_t *m, uint32_t card, uint32_t step, uint32_t x, bool pre, uint32_t pre_lo) {
         if (err) return 0u;
         const uint32_t n = m[card];
         uint32_t lo = 0, cnt = 0;
         if (pre) { lo = pre_lo; cnt = m[x]; }
         else if (MODE == MODE_ENC) {
-            if (x >= card) { err = CBCG_ERR_INPUT; return 0u; }              /* reference: assert :62 */
-            if (x < 4u) {                                                    /* most symbols are small: one broadcast load */
+            if (UNLIKELY(x >= card)) { err = CBCG_ERR_INPUT; return 0u; }    /* reference: assert :62 */
+            if (SMALL == 2 || LIKELY(x < 4u)) {                                      /* most symbols are small: one broadcast load */
                 const uint4 v = load4(m, 0u, card);
                 lo = (x > 0u ? v.x : 0u) + (x > 1u ? v.y : 0u) + (x > 2u ? v.z : 0u);
                 cnt = x == 0u ? v.x : (x == 1u ? v.y : (x == 2u ? v.z : v.w));
+            } else if (SMALL == 5) {                                         /* symbol 4 of 5 */
+                const uint4 v = load4(m, 0u, card);
+                lo = v.x + v.y + v.z + v.w; cnt = m[4];
             } else {
                 uint32_t s = 0;
                 for (uint32_t base = 0; base < x; base += 128u) {
@@ -492,11 +502,15 @@ struct Coder {
             const uint64_t A = dec_A(n); const uint32_t range = dec_range();
             const uint4 f = load4(m, 0u, card);
             const uint32_t s1 = f.x, s2 = s1 + f.y, s3 = s2 + f.z, s4 = s3 + f.w;
-            if (!DEC_LE(s4)) {                                               /* resolved by the first four counts: no scan */
+            if (LIKELY(!DEC_LE(s4))) {                                       /* resolved by the first four counts: no scan */
                 const uint32_t q = (uint32_t)DEC_LE(s1) + (uint32_t)DEC_LE(s2) + (uint32_t)DEC_LE(s3);
                 lo = q == 0u ? 0u : (q == 1u ? s1 : (q == 2u ? s2 : s3));
                 cnt = q == 0u ? f.x : (q == 1u ? f.y : (q == 2u ? f.z : f.w));
                 x = q;
+            } else if (SMALL == 2) { err = CBCG_ERR_CORRUPT; return 0u; }   /* target beyond the model total */
+            else if (SMALL == 5) {
+                x = 4u; lo = s4; cnt = m[4];
+                if (DEC_LE(s4 + cnt)) { err = CBCG_ERR_CORRUPT; return 0u; }
             } else {
                 uint32_t carry = 0; bool found = false;
                 x = 0;
@@ -522,12 +536,12 @@ struct Coder {
                 }
                 if (!found) { err = CBCG_ERR_CORRUPT; return 0u; }
             }
-            if (x >= card) { err = CBCG_ERR_CORRUPT; return 0u; }
+            if (UNLIKELY(x >= card)) { err = CBCG_ERR_CORRUPT; return 0u; }
         }
         last_lo = lo; last_n = n;
         code_interval(lo, cnt, n);
-        if (err) return 0u;
-        dense_update(m, card, step, x, cnt, n);
+        if (UNLIKELY(err)) return 0u;
+        dense_update<IS_VAR>(m, card, step, x, cnt, n);
         return x;
     }
 
@@ -609,7 +623,7 @@ struct Coder {
         }
         uint32_t nn = n + 8u;
         SYNCW();
-        if (nn >= CBCG_RESCALE) nn = rescale_counts(M->flag_cnt, nused, lane) + (65536u - nused);
+        if (UNLIKELY(nn >= CBCG_RESCALE)) nn = rescale_counts(M->flag_cnt, nused, lane) + (65536u - nused);
         if (lane == 0) M->flag_n = nn;
         SYNCW();
         return x;
@@ -627,7 +641,7 @@ struct Coder {
         else if (lane == 0) pos_gcnt()[slot] += 10u;
         pos_n += 10u;
         SYNCW();
-        if (pos_n >= CBCG_RESCALE) {
+        if (UNLIKELY(pos_n >= CBCG_RESCALE)) {
             uint32_t s = 0;
             if (lane < pos_card) { pos_rc = (pos_rc >> 1) + 1u; s += pos_rc; }
             { uint32_t *gc = pos_gcnt(); for (uint32_t i = 32u + lane; i < pos_card; i += 32u) { uint32_t c = (gc[i] >> 1) + 1u; gc[i] = c; s += c; } }
@@ -959,20 +973,20 @@ k2_coder_kernel(CoderParams P) {
 #define CODE_DIRECT(CALL, STREAM, CTXV, XV, NEXT) do { \
         y = (XV); slot = 1u; \
         if (MODE == MODE_LIST) C.list_put((STREAM), (CTXV), (XV)); else y = (CALL); \
-        if (C.err) goto M_DONE; \
+        if (UNLIKELY(C.err)) goto M_DONE; \
         goto NEXT; } while (0)
     /* The four dense symbols of nearly every read (match bit, SNP count, SNP position, SNP base) get their own coder
        call too; the rare states share the CODE site below and its dispatch. */
-#define DENSE_DIRECT(M, CARD, STEP, STREAM, CTXV, XV, NEXT) do { \
+#define DENSE_DIRECT(SMALL, IS_VAR, M, CARD, STEP, STREAM, CTXV, XV, NEXT) do { \
         y = (XV); \
-        if (MODE == MODE_LIST) C.list_put((STREAM), (CTXV), (XV)); else y = C.sym_dense((M), (CARD), (STEP), (XV), false, 0u); \
-        if (C.err) goto M_DONE; \
+        if (MODE == MODE_LIST) C.list_put((STREAM), (CTXV), (XV)); else y = C.template sym_dense<SMALL, IS_VAR>((M), (CARD), (STEP), (XV), false, 0u); \
+        if (UNLIKELY(C.err)) goto M_DONE; \
         goto NEXT; } while (0)
 CODE:
     if (is_var && MODE != MODE_LIST) { m = C.var_row(ctx); if (!m) goto M_DONE; }
     y = x;
     if (MODE == MODE_LIST) C.list_put(key >> 24, key & 0xffffffu, x);
-    else y = C.sym_dense(m, card, step, x, pre, pre_lo);
+    else y = C.template sym_dense<0, true>(m, card, step, x, pre, pre_lo);
     if (C.err) goto M_DONE;
     switch (state) {
         case ST_HDR: goto P_HDR;       case ST_SAMEREF: goto P_SAMEREF; case ST_RNAME: goto P_RNAME;   case ST_RLEN0: goto P_RLEN0;
@@ -1150,7 +1164,7 @@ P_FLAG:
     state = ST_MATCH;
     ctx = (samepos << 1) | prev_m;
     x = match;
-    DENSE_DIRECT(C.M->match[ctx], 2u, 1u, CBCG_S_MATCH, ctx, x, P_MATCH);
+    DENSE_DIRECT(2, false, C.M->match[ctx], 2u, 1u, CBCG_S_MATCH, ctx, x, P_MATCH);
 P_MATCH:
     match = y; prev_m = y; ne = 0;
     if (MODE == MODE_DEC) { ns = nd = ni = 0; }
@@ -1159,7 +1173,7 @@ P_MATCH:
     /* ---- counts (:557-565) */
     state = ST_SNPS;
     x = ((nd | ni) == 0u) ? ns : 0u;
-    DENSE_DIRECT(C.M->snps, C.L, 10u, CBCG_S_SNPS, 0u, x, P_SNPS);
+    DENSE_DIRECT(0, false, C.M->snps, C.L, 10u, CBCG_S_SNPS, 0u, x, P_SNPS);
 P_SNPS:
     if (MODE == MODE_DEC) { ns = y; nd = ni = 0; if (y != 0u) goto M_COUNTS_DONE; }
     else if ((nd | ni) == 0u) goto M_COUNTS_DONE;
@@ -1208,7 +1222,7 @@ S_SNPVAR: {
         x = CBCG_EDIT_DELTA(ed);
         m = nullptr;
         if (MODE != MODE_LIST) { m = C.var_row(ctx); if (!m) goto M_DONE; }
-        DENSE_DIRECT(m, C.L, 10u, CBCG_S_VAR, ctx, x, P_SNPVAR);
+        DENSE_DIRECT(0, true, m, C.L, 10u, CBCG_S_VAR, ctx, x, P_SNPVAR);
     }
 P_SNPVAR: {
         edp = y;
@@ -1224,7 +1238,7 @@ P_SNPVAR: {
         } else refb = CBCG_EDIT_REFB(ed);
         state = ST_SNPCHAR;
         x = CBCG_EDIT_TARGET(ed);
-        DENSE_DIRECT(C.M->chars[refb], 5u, 8u, CBCG_S_CHARS, refb, x, P_SNPCHAR);
+        DENSE_DIRECT(5, false, C.M->chars[refb], 5u, 8u, CBCG_S_CHARS, refb, x, P_SNPCHAR);
     }
 P_SNPCHAR:
     if (MODE == MODE_DEC && lane == 0) P.edits[e_cursor + ne] = CBCG_EDIT(edp, y, refb);
