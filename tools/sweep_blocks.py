@@ -13,7 +13,8 @@ from cbc_b200.codec import Codec, pin_batch     # noqa: E402
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 sizes = [int(x) if x != "auto" else 0xffffffff for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [256, 512, 1024, 2048, 4096, 16384, 65536]
 gen_mode = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-cfg = synth.SynthConfig.named("config2", scale=scale)
+cfg = synth.SynthConfig.named(os.environ.get("CBC_CONFIG", "config2"), scale=scale)
+L_HDR = {"config1": 100, "config5": 250}.get(os.environ.get("CBC_CONFIG", "config2"), 150)
 g = synth.make_genome(cfg)
 b = synth.make_reads(cfg, g)
 c = Codec(0)
@@ -23,7 +24,7 @@ ref = b.seq_lines()
 for R in sizes:
     rows = []
     for it in range(4):
-        c.encode_resident(150, R, gen_mode)
+        c.encode_resident(L_HDR, R, gen_mode)
         se = c.stats()
         c.decode_resident()
         sd = c.stats()
