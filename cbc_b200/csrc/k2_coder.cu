@@ -1169,6 +1169,14 @@ P_MATCH:
     match = y; prev_m = y; ne = 0;
     if (MODE == MODE_DEC) { ns = nd = ni = 0; }
     if (match) goto M_READ_END;
+    if (MODE == MODE_DEC) {
+        /* the decoder needs the reference base under every SNP it decodes (the context of the base symbol): a
+           dependent byte load from HBM per SNP unless the read's stretch of the reference is already on its way */
+        const uint8_t *rp = C.cold().ref + (pos - 1u);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + 128));
+        if (len > 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + 256));
+    }
 
     /* ---- counts (:557-565) */
     state = ST_SNPS;
@@ -1231,8 +1239,10 @@ P_SNPVAR: {
         C.ring_set(pos + prev - 2u);                                           /* :589 */
         if (MODE == MODE_DEC) {
             uint32_t skipped = 0;                                              /* deletions at or before idx (:426-437) */
-            for (uint32_t q = lane; q < nd; q += 32u) skipped += (C.M->cumdel[q] <= idx);
-            skipped = warp_sum(skipped);
+            if (nd) {
+                for (uint32_t q = lane; q < nd; q += 32u) skipped += (C.M->cumdel[q] <= idx);
+                skipped = warp_sum(skipped);
+            }
             const uint64_t ri = (uint64_t)pos - 1u + idx + skipped;
             refb = base_code(ri < C.cold().ref_len ? (uint32_t)C.cold().ref[ri] : 0u);
         } else refb = CBCG_EDIT_REFB(ed);
