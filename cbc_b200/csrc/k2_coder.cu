@@ -1612,7 +1612,14 @@ __global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
         const uint32_t *ps = reinterpret_cast<const uint32_t *>(P.prev + l.small);
         uint32_t *ns = reinterpret_cast<uint32_t *>(P.next + l.small);
         const uint32_t *fs = reinterpret_cast<const uint32_t *>(P.fin + (uint64_t)b * fin_stride_dev());
-        for (uint32_t i = WM_W(snps) + lane; i < WM_W(flag_key); i += 32u) { const uint32_t d = fs[i] - ps[i]; if (d) atomicAdd(&ns[i], d); }
+        /* four words per lane in flight: each round trip to L2 serves 128 counts */
+        for (uint32_t i0 = WM_W(snps) + lane; i0 < WM_W(flag_key); i0 += 128u) {
+            uint32_t f[4], q[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; u++) { const uint32_t i = i0 + 32u * u; const bool in = i < WM_W(flag_key); f[u] = in ? fs[i] : 0u; q[u] = in ? ps[i] : 0u; }
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; u++) { const uint32_t d = f[u] - q[u]; if (d) atomicAdd(&ns[i0 + 32u * u], d); }
+        }
         /* FLAG: the block's touched values against the dense scratch */
         const WarpModels *fm = reinterpret_cast<const WarpModels *>(fs);
         const uint32_t *dprev = reinterpret_cast<const uint32_t *>(P.next + l.flag_prev);
@@ -1749,11 +1756,16 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
     uint32_t n, mine = 0;
     {
         uint32_t s = 0;
-        for (uint32_t j = 0; j < 64u; j++) {
-            const uint32_t i = base + 32u * j + lane;
-            int32_t v = (int32_t)dacc[i]; if (v < 1) v = 1;
-            dacc[i] = (uint32_t)v; s += (uint32_t)v;
-            mine += (uint32_t)__popc(__ballot_sync(FULL_MASK, v != 1));
+        for (uint32_t j0 = 0; j0 < 64u; j0 += 8u) {          /* eight loads in flight per lane */
+            int32_t v[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; u++) v[u] = (int32_t)dacc[base + 32u * (j0 + u) + lane];
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; u++) {
+                if (v[u] < 1) { v[u] = 1; dacc[base + 32u * (j0 + u) + lane] = 1u; }
+                s += (uint32_t)v[u];
+                mine += (uint32_t)__popc(__ballot_sync(FULL_MASK, v[u] != 1));
+            }
         }
         s = warp_sum(s); if (lane == 0) red[warp] = s; __syncthreads();
         n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
@@ -1776,12 +1788,17 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
     for (uint32_t k = 0; k < 32u; k++) { const uint32_t c = scan[k]; if (k < warp) at += c; total += c; }
     if (total > FLAG_CAP) { if (tid == 0) dev_set_error(P.err, CBCG_ERR_LIMIT, total); }
     else if (mine) {
-        for (uint32_t j = 0; j < 64u; j++) {
-            const uint32_t i = base + 32u * j + lane;
-            const uint32_t c = dacc[i];
-            const uint32_t bal = __ballot_sync(FULL_MASK, c != 1u);
-            if (c != 1u) { const uint32_t o = at + (uint32_t)__popc(bal & ((1u << lane) - 1u)); nm->flag_key[o] = i; nm->flag_cnt[o] = c; }
-            at += (uint32_t)__popc(bal);
+        for (uint32_t j0 = 0; j0 < 64u; j0 += 8u) {
+            uint32_t c[8];
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; u++) c[u] = dacc[base + 32u * (j0 + u) + lane];
+#pragma unroll
+            for (uint32_t u = 0; u < 8u; u++) {
+                const uint32_t i = base + 32u * (j0 + u) + lane;
+                const uint32_t bal = __ballot_sync(FULL_MASK, c[u] != 1u);
+                if (c[u] != 1u) { const uint32_t o = at + (uint32_t)__popc(bal & ((1u << lane) - 1u)); nm->flag_key[o] = i; nm->flag_cnt[o] = c[u]; }
+                at += (uint32_t)__popc(bal);
+            }
         }
     }
     if (tid == 0) { nm->flag_used = total > FLAG_CAP ? 0u : total; nm->flag_n = n; }
