@@ -1658,10 +1658,16 @@ __global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
                 const bool in_prev = (pbm[ctx >> 5] >> (ctx & 31u)) & 1u;
                 const uint32_t *row = rows + (uint64_t)r * w.Lp, *prow = pvar + (uint64_t)ctx * l.Lp;
                 uint32_t *nrow = var + (uint64_t)ctx * l.Lp;
-                for (uint32_t i = lane; i < P.L; i += 32u) {
-                    const uint32_t d = row[i] - (in_prev ? prow[i] : 1u);
-                    if (d) atomicAdd(&nrow[i], d);
+                /* a row is at most 8 x 32 counts: all of its loads go out before the first is needed */
+                uint32_t rv[8], pv[8];
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; u++) {
+                    const uint32_t i = lane + 32u * u;
+                    rv[u] = i < P.L ? row[i] : 0u;
+                    pv[u] = i < P.L ? (in_prev ? prow[i] : 1u) : 0u;
                 }
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; u++) { const uint32_t d = rv[u] - pv[u]; if (d) atomicAdd(&nrow[lane + 32u * u], d); }
             }
         }
     }
