@@ -1676,10 +1676,23 @@ __global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
 /* clamp to >= floor, total, rescale: one dense model by one warp (counts already summed in place). */
 __device__ __forceinline__ void finish_dense(uint32_t lane, const uint32_t *prev_m, uint32_t *m, uint32_t card, uint32_t implicit_ones) {
     uint32_t s = 0;
-    for (uint32_t i = lane; i < card; i += 32u) {
-        int32_t v = (int32_t)m[i]; const int32_t fl = (prev_m && prev_m[i] == 0u) ? 0 : 1;
-        if (v < fl) v = fl;
-        m[i] = (uint32_t)v; s += (uint32_t)v;
+    for (uint32_t i0 = lane; i0 < card; i0 += 256u) {        /* dense models have at most 256 counts: one batch of loads */
+        int32_t v[8]; uint32_t pz[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; u++) {
+            const uint32_t i = i0 + 32u * u;
+            v[u] = i < card ? (int32_t)m[i] : 0;
+            pz[u] = (i < card && prev_m) ? prev_m[i] : 1u;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; u++) {
+            const uint32_t i = i0 + 32u * u;
+            if (i < card) {
+                const int32_t fl = pz[u] == 0u ? 0 : 1;
+                if (v[u] < fl) v[u] = fl;
+                m[i] = (uint32_t)v[u]; s += (uint32_t)v[u];
+            }
+        }
     }
     uint32_t n = warp_sum(s) + implicit_ones;
     while (n >= CBCG_RESCALE) {
@@ -1820,7 +1833,16 @@ __global__ void __launch_bounds__(256) merge_var_finish_kernel(MergeParams P) {
     if (!((bm[ctx >> 5] >> (ctx & 31u)) & 1u)) return;
     uint32_t *row = reinterpret_cast<uint32_t *>(P.next + l.var) + (uint64_t)ctx * l.Lp;
     uint32_t s = 0;
-    for (uint32_t i = lane; i < P.L; i += 32u) { int32_t v = (int32_t)row[i]; if (v < 1) v = 1; row[i] = (uint32_t)v; s += (uint32_t)v; }
+    {
+        int32_t v[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; u++) { const uint32_t i = lane + 32u * u; v[u] = i < P.L ? (int32_t)row[i] : 1; }
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; u++) {
+            const uint32_t i = lane + 32u * u;
+            if (i < P.L) { if (v[u] < 1) { v[u] = 1; row[i] = 1u; } s += (uint32_t)v[u]; }
+        }
+    }
     uint32_t n = warp_sum(s);
     while (n >= CBCG_RESCALE) {
         s = 0;
