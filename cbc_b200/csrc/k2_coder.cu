@@ -1704,6 +1704,92 @@ __device__ __forceinline__ void finish_dense(uint32_t lane, const uint32_t *prev
     __syncwarp();
 }
 
+/* POS alphabet of the new snapshot, one warp: the slots shared with the old snapshot were summed by merge_add; values
+ * new to the snapshot are appended in block order, then order of appearance, equal values summed. The new entries are
+ * collected in shared memory; a lane reads its own block's descriptor and first new values, so that 32 blocks cost two
+ * round trips to memory instead of two per block. */
+#define MERGE_POS_AHEAD 4u
+__device__ __forceinline__ void merge_pos_put(uint32_t lane, uint32_t *sval, uint32_t *scnt, uint32_t &nn, uint32_t cap_new, uint32_t x, uint32_t c) {
+    int found = -1;
+    for (uint32_t q0 = 0; q0 < nn && found < 0; q0 += 32u) {
+        const uint32_t q = q0 + lane;
+        const uint32_t hit = __ballot_sync(FULL_MASK, q < nn && sval[q] == x);
+        if (hit) found = (int)(q0 + (uint32_t)__ffs(hit) - 1u);
+    }
+    if (found >= 0) { if (lane == 0) scnt[found] += c; }
+    else if (nn < cap_new) { if (lane == 0) { sval[nn] = x; scnt[nn] = c; } nn++; }
+    __syncwarp();
+}
+__device__ __noinline__ void merge_pos(const MergeParams &P, const SnapLayout &l, uint32_t lane) {
+    __shared__ uint32_t sval[CBCG_SNAP_POS_MAX], scnt[CBCG_SNAP_POS_MAX];
+    const uint32_t pc = reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr)[0];
+    uint32_t *nhdr = reinterpret_cast<uint32_t *>(P.next + l.pos_hdr);
+    uint32_t *nval = reinterpret_cast<uint32_t *>(P.next + l.pos_val), *ncnt = reinterpret_cast<uint32_t *>(P.next + l.pos_cnt);
+    const BlockDesc *blocks = P.blocks + P.block_begin;
+    const uint32_t cap_new = pc < CBCG_SNAP_POS_MAX ? CBCG_SNAP_POS_MAX - pc : 0u;
+    uint32_t nn = 0;
+    for (uint32_t b0 = 0; b0 < P.n_blocks; b0 += 32u) {
+        const uint32_t bb = b0 + lane;
+        uint32_t nnew = 0;
+        const uint32_t *bval = nullptr, *bcnt = nullptr;
+        if (bb < P.n_blocks) {
+            const BlockDesc &B = blocks[bb];
+            const uint32_t bc = B.pos_card;
+            if (bc > pc) {
+                const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+                bval = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_val) + pc;
+                bcnt = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_cnt) + pc;
+                nnew = bc - pc;
+            }
+        }
+        uint32_t v[MERGE_POS_AHEAD], c[MERGE_POS_AHEAD];
+#pragma unroll
+        for (uint32_t u = 0; u < MERGE_POS_AHEAD; u++) { v[u] = u < nnew ? bval[u] : 0u; c[u] = u < nnew ? bcnt[u] : 0u; }
+        uint32_t grown = __ballot_sync(FULL_MASK, nnew != 0u);
+        while (grown) {                                      /* blocks in ascending order */
+            const uint32_t src = (uint32_t)__ffs(grown) - 1u; grown &= grown - 1u;
+            const uint32_t cnt = __shfl_sync(FULL_MASK, nnew, src);
+#pragma unroll
+            for (uint32_t u = 0; u < MERGE_POS_AHEAD; u++) {
+                const uint32_t x = __shfl_sync(FULL_MASK, v[u], src), cc = __shfl_sync(FULL_MASK, c[u], src);
+                if (u < cnt) merge_pos_put(lane, sval, scnt, nn, cap_new, x, cc);
+            }
+            if (cnt > MERGE_POS_AHEAD) {                     /* a block with many new values (the first generations) */
+                const uint32_t *pv = reinterpret_cast<const uint32_t *>(__shfl_sync(FULL_MASK, (unsigned long long)bval, src));
+                const uint32_t *pn = reinterpret_cast<const uint32_t *>(__shfl_sync(FULL_MASK, (unsigned long long)bcnt, src));
+                for (uint32_t s0 = MERGE_POS_AHEAD; s0 < cnt; s0 += 32u) {
+                    const uint32_t s = s0 + lane;
+                    const uint32_t xv = s < cnt ? pv[s] : 0u, cv = s < cnt ? pn[s] : 0u;
+                    const uint32_t m = cnt - s0 < 32u ? cnt - s0 : 32u;
+                    for (uint32_t k = 0; k < m; k++)
+                        merge_pos_put(lane, sval, scnt, nn, cap_new, __shfl_sync(FULL_MASK, xv, k), __shfl_sync(FULL_MASK, cv, k));
+                }
+            }
+        }
+    }
+    const uint32_t an = pc + nn;
+    for (uint32_t i = lane; i < nn; i += 32u) nval[pc + i] = sval[i];
+    uint32_t s = 0;
+    for (uint32_t i0 = lane; i0 < an; i0 += 256u) {          /* eight loads in flight per lane */
+        int32_t t[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; u++) { const uint32_t i = i0 + 32u * u; t[u] = i < pc ? (int32_t)ncnt[i] : (i < an ? (int32_t)scnt[i - pc] : 1); }
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; u++) {
+            const uint32_t i = i0 + 32u * u;
+            if (i < an) { if (t[u] < 1) t[u] = 1; ncnt[i] = (uint32_t)t[u]; s += (uint32_t)t[u]; }
+        }
+    }
+    uint32_t n = warp_sum(s);
+    while (n >= CBCG_RESCALE) {
+        __syncwarp();
+        s = 0;
+        for (uint32_t i = lane; i < an; i += 32u) { const uint32_t cc = (ncnt[i] >> 1) + 1u; ncnt[i] = cc; s += cc; }
+        n = warp_sum(s);
+    }
+    if (lane == 0) { nhdr[0] = an; nhdr[1] = n; }
+}
+
 /* merge step 3 (one CTA): small models, pos_alpha, POS (values new to the snapshot are appended in block
  * order, then order of appearance), FLAG back to its sorted sparse form. */
 #define MERGE_FIN_WARPS 32u
@@ -1712,6 +1798,10 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
     __shared__ uint32_t scan[1024];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const SnapLayout l = snap_layout(P.L);
+    if (blockIdx.x == 1u) {                                /* the POS alphabet has a CTA (one warp) of its own, beside FLAG */
+        if (warp == 0u) merge_pos(P, l, lane);
+        return;
+    }
     const uint32_t *ps = reinterpret_cast<const uint32_t *>(P.prev + l.small);
     uint32_t *ns = reinterpret_cast<uint32_t *>(P.next + l.small);
     if (warp == 0)       finish_dense(lane, ps + WM_W(snps), ns + WM_W(snps), P.L, 0u);
@@ -1725,46 +1815,6 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
         const uint32_t k = warp - 17u;
         finish_dense(lane, reinterpret_cast<const uint32_t *>(P.prev + l.pos_alpha) + k * PA_STRIDE,
                      reinterpret_cast<uint32_t *>(P.next + l.pos_alpha) + k * PA_STRIDE, 256u, 0u);
-    } else if (warp == 21) {
-        const uint32_t pc = reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr)[0];
-        uint32_t *nhdr = reinterpret_cast<uint32_t *>(P.next + l.pos_hdr);
-        uint32_t *nval = reinterpret_cast<uint32_t *>(P.next + l.pos_val), *ncnt = reinterpret_cast<uint32_t *>(P.next + l.pos_cnt);
-        const BlockDesc *blocks = P.blocks + P.block_begin;
-        uint32_t an = pc;
-        for (uint32_t b0 = 0; b0 < P.n_blocks; b0 += 32u) {
-            const uint32_t bb = b0 + lane;
-            const uint32_t card = bb < P.n_blocks ? blocks[bb].pos_card : 0u;
-            uint32_t grown = __ballot_sync(FULL_MASK, card > pc);
-            while (grown) {                                  /* blocks in ascending order */
-                const uint32_t src = (uint32_t)__ffs(grown) - 1u; grown &= grown - 1u;
-                const BlockDesc &B = blocks[b0 + src];
-                const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
-                const uint32_t *bval = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_val);
-                const uint32_t *bcnt = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_cnt);
-                const uint32_t bc = B.pos_card;
-                for (uint32_t s = pc; s < bc; s++) {
-                    const uint32_t x = bval[s], c = bcnt[s];
-                    int found = -1;
-                    for (uint32_t q0 = pc; q0 < an && found < 0; q0 += 32u) {
-                        const uint32_t q = q0 + lane;
-                        const uint32_t hit = __ballot_sync(FULL_MASK, q < an && nval[q] == x);
-                        if (hit) found = (int)(q0 + (uint32_t)__ffs(hit) - 1u);
-                    }
-                    if (found >= 0) { if (lane == 0) ncnt[found] += c; }
-                    else if (an < CBCG_SNAP_POS_MAX) { if (lane == 0) { nval[an] = x; ncnt[an] = c; } an++; }
-                    __syncwarp();
-                }
-            }
-        }
-        uint32_t s = 0;
-        for (uint32_t i = lane; i < an; i += 32u) { int32_t v = (int32_t)ncnt[i]; if (v < 1) v = 1; ncnt[i] = (uint32_t)v; s += (uint32_t)v; }
-        uint32_t n = warp_sum(s);
-        while (n >= CBCG_RESCALE) {
-            s = 0;
-            for (uint32_t i = lane; i < an; i += 32u) { const uint32_t c = (ncnt[i] >> 1) + 1u; ncnt[i] = c; s += c; }
-            n = warp_sum(s);
-        }
-        if (lane == 0) { nhdr[0] = an; nhdr[1] = n; }
     }
     __syncthreads();
     /* FLAG: clamp, total, rescale over the dense scratch, then ordered compaction of the counts != 1. Warp w owns
@@ -1873,7 +1923,7 @@ int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_block
     MergeParams P = { blocks, block_begin, n_blocks, L, prev, next, fin, ws, err };
     merge_prep_kernel<<<148, 128, 0, st>>>(P);
     merge_add_kernel<<<dim3((n_blocks + 3u) / 4u, MERGE_PARTS), 128, 0, st>>>(P);
-    merge_finish_kernel<<<1, MERGE_FIN_WARPS * 32u, 0, st>>>(P);
+    merge_finish_kernel<<<2, MERGE_FIN_WARPS * 32u, 0, st>>>(P);
     merge_var_finish_kernel<<<(CBCG_VAR_CONTEXTS + 7u) / 8u, 256, 0, st>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
