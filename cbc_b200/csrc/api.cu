@@ -51,6 +51,7 @@ struct cbcg_ctx {
     /* pipelined host-buffer calls (cbcg_encode / cbcg_decode on large batches): a copy stream, side streams for the
        groups of last-generation blocks, and the events that order them */
     cudaStream_t cs = nullptr, ps[PIPE_MAX] = {};
+    cudaStream_t hp = nullptr;                /* high priority: the early generations of a resident encode, beside K1 on a side stream */
     cudaEvent_t cev[PIPE_MAX + 2] = {}, kev2[PIPE_MAX + 2] = {}, dev2[PIPE_MAX + 2] = {}, tev[2 * PIPE_MAX + 4] = {};
     bool pipe_ready = false;
     char errtext[512] = {0};
@@ -198,6 +199,7 @@ extern "C" void cbcg_destroy(cbcg_ctx *ctx) {
     for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     if (ctx->cs) cudaStreamDestroy(ctx->cs);
+    if (ctx->hp) cudaStreamDestroy(ctx->hp);
     for (auto &s : ctx->ps) if (s) cudaStreamDestroy(s);
     for (auto &e : ctx->cev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->kev2) if (e) cudaEventDestroy(e);
@@ -501,21 +503,22 @@ static uint32_t auto_block_reads(cbcg_ctx *ctx, uint64_t n, uint32_t gen_mode, u
 
 /* Generations 0 .. last-1 of ctx->gens with the merges that build the snapshots; *snap_out = the snapshot the last
  * generation starts from. */
-static int run_early_generations(cbcg_ctx *ctx, CoderParams p, uint8_t **snap_out) {
+static int run_early_generations(cbcg_ctx *ctx, CoderParams p, uint8_t **snap_out, cudaStream_t st = nullptr) {
+    if (!st) st = ctx->st;
     const uint64_t sb = snapshot_bytes(p.L);
     uint32_t max_merged = 1;
     for (size_t g = 0; g + 1 < ctx->gens.size(); g++) max_merged = std::max(max_merged, ctx->gens[g].second);
     TRY(ensure(ctx, ctx->snap_a, sb)); TRY(ensure(ctx, ctx->snap_b, sb));
     TRY(ensure(ctx, ctx->fin, (uint64_t)max_merged * fin_stride_bytes()));
     uint8_t *cur = ctx->snap_a.as<uint8_t>(), *other = ctx->snap_b.as<uint8_t>();
-    if (launch_snapshot_init(cur, p.L, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "snapshot init launch failed");
+    if (launch_snapshot_init(cur, p.L, st)) return fail(ctx, CBCG_ERR_CUDA, "snapshot init launch failed");
     ctx->stats.kernel_launches++;
     for (size_t g = 0; g + 1 < ctx->gens.size(); g++) {
         p.block_begin = ctx->gens[g].first; p.n_blocks = ctx->gens[g].second;
         p.snap = cur; p.fin = ctx->fin.as<uint8_t>();
-        if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (launch_coder(p, st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->stats.kernel_launches++;
-        if (launch_merge(p.blocks, p.block_begin, p.n_blocks, p.L, cur, other, ctx->fin.as<uint8_t>(), p.ws, p.err, ctx->st))
+        if (launch_merge(p.blocks, p.block_begin, p.n_blocks, p.L, cur, other, ctx->fin.as<uint8_t>(), p.ws, p.err, st))
             return fail(ctx, CBCG_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->stats.kernel_launches += 4;
         std::swap(cur, other);
@@ -653,6 +656,116 @@ static void finish_encode(cbcg_ctx *ctx, const cbcg_encode_opts *opts, int legac
 }
 
 /* ------------------------------------------------------------------------------------------------ encode */
+/* Resident encode with the head of K1 split off (gen_mode 1, large batches): the early generations only need the
+ * records of their own reads, so K1 runs on those first, and the rest of the batch is extracted on a side stream while
+ * generations 0..3 (a few hundred CTAs at most) and their merges run on the main stream. Same cut, same container as the
+ * one-stream order. The model workspace is sized from the head's edit density (one host round trip, as in the
+ * pipelined host-buffer call); a batch whose tail is much dirtier than its head reports CBCG_ERR_CAPACITY / INTERNAL on
+ * the device and the caller falls back to the one-stream order. CBCG_NO_OVERLAP=1 keeps the one-stream order. */
+#define PIPE_FALLBACK 1            /* not an error: the caller takes the one-stream path */
+static int pipe_init(cbcg_ctx *ctx);
+static int encode_resident_overlapped(cbcg_ctx *ctx, const cbcg_encode_opts *opts) {
+    static const uint32_t sc[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sr[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
+    const uint64_t n = ctx->db.n_reads;
+    const uint32_t L = opts->read_len_header;
+    const uint64_t tile = 128;                              /* K1 tile */
+    uint64_t early = 0;
+    for (uint32_t g = 0; g < CBCG_GEN_LEVELS; g++) early += (uint64_t)sc[g] * sr[g];
+    const uint64_t head_end = ((early + tile - 1) / tile + 1) * tile;   /* + one tile: the record after the last early block exists */
+    if (n < 4 * head_end) return PIPE_FALLBACK;
+    TRY(pipe_init(ctx));
+    cbcg_stats &S = ctx->stats;
+    uint64_t nb = 0;
+    TRY(cut_blocks(ctx, opts->block_reads, 1, &nb));
+    if (ctx->gens.size() != CBCG_GEN_LEVELS + 1) return PIPE_FALLBACK;   /* chromosome runs too short for the schedule */
+    const uint32_t last_first = ctx->gens.back().first, last_n = ctx->gens.back().second;
+    if ((uint64_t)ctx->hblocks[last_first].first_read + tile > head_end) return PIPE_FALLBACK;
+    const bool fixed = ctx->batch_min_len == L && ctx->db.max_len == L;
+
+    const uint64_t edits_cap_guess = ctx->total_bases / 16 + 4096;
+    TRY(ensure(ctx, ctx->recs, (n + 1) * sizeof(cbcg_read_rec)));
+    TRY(ensure(ctx, ctx->tile_desc, ((n + tile - 1) / tile + 2) * 8));
+    if (ctx->edits.cap / 2 < edits_cap_guess) TRY(ensure(ctx, ctx->edits, edits_cap_guess * 2));
+    const uint64_t edits_cap = ctx->edits.cap / 2;
+    TRY(ensure(ctx, ctx->out_off, (nb + 1) * 8));
+    TRY(reset_words(ctx));
+    uint64_t *chain = wptr<uint64_t>(ctx, W_OFF(chain));
+    uint64_t *totals = wptr<uint64_t>(ctx, W_OFF(totals));
+    uint32_t *ticket = wptr<uint32_t>(ctx, W_OFF(ticket));
+    unsigned long long *err = wptr<unsigned long long>(ctx, W_OFF(err));
+    cudaStream_t side = ctx->ps[1];
+
+    /* K1 on the head; its edit total (chain[1]) gives the density the workspace is sized from */
+    if (launch_extract(ctx->db, ctx->dg, ctx->recs.as<cbcg_read_rec>(), ctx->edits.as<uint16_t>(), edits_cap, ctx->tile_desc.as<uint64_t>(),
+                       ticket, &chain[1], err, ctx->st, ctx->tev[0], ctx->tev[1], 0, head_end, nullptr))
+        return fail(ctx, CBCG_ERR_CUDA, "K1 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CU(cudaMemcpyAsync(&ctx->hw->total_edits, &chain[1], 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    const uint64_t proj = std::min<uint64_t>(edits_cap, (uint64_t)((double)ctx->hw->total_edits * ((double)n / (double)head_end) * 1.5) + 65536u);
+    const uint64_t ws_cap = coder_ws_bytes_bound(L, n, proj, nb, 0, 1);
+    const uint64_t pay_cap = coder_payload_bound(n, proj, nb, 0);
+    TRY(ensure(ctx, ctx->ws, ws_cap)); TRY(ensure(ctx, ctx->scratch, pay_cap)); TRY(ensure(ctx, ctx->payload, pay_cap));
+    CU(cudaEventRecord(ctx->ev[1], ctx->st));
+
+    CoderParams p = coder_params(ctx, (uint32_t)nb, L, 0, 0);
+    p.chr = const_cast<uint32_t *>(ctx->db.chr);
+    p.payload = ctx->scratch.as<uint8_t>();
+    p.lean = 1u; p.short_flush = 1u; p.primed = 1u; p.fixed_len = fixed ? 1u : 0u;
+    /* high-priority stream: plan of the early blocks, generations 0..3. K1's grid fills every SM; without the priority
+       the first generation's four CTAs queue behind all of it (measured: the overlap gained nothing). */
+    cudaStream_t hp = ctx->hp;
+    CU(cudaStreamWaitEvent(hp, ctx->ev[1], 0));
+    CoderParams q = p;
+    q.block_begin = 0; q.n_blocks = last_first;
+    if (launch_plan(q, (uint32_t)head_end, 0, ws_cap, pay_cap, totals, hp, nullptr, &chain[1])) return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
+    CU(cudaEventRecord(ctx->kev2[2], hp));
+    CU(cudaEventRecord(ctx->ev[2], hp));
+    /* side stream: K1 on the tail (everything before it on the main stream has completed: the synchronize above) */
+    if (launch_extract(ctx->db, ctx->dg, ctx->recs.as<cbcg_read_rec>(), ctx->edits.as<uint16_t>(), edits_cap,
+                       ctx->tile_desc.as<uint64_t>() + head_end / tile, ticket, &chain[0], err, side, ctx->kev[0], ctx->kev[1],
+                       head_end, n, &chain[1]))
+        return fail(ctx, CBCG_ERR_CUDA, "K1 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    uint8_t *snap = nullptr;
+    TRY(run_early_generations(ctx, p, &snap, hp));
+    CU(cudaEventRecord(ctx->dev2[2], hp));
+    /* side stream: plan of the last generation, behind the tail's K1 and the early blocks' plan (its offsets carry on) */
+    CU(cudaStreamWaitEvent(side, ctx->kev2[2], 0));
+    q.block_begin = last_first; q.n_blocks = last_n;
+    if (launch_plan(q, (uint32_t)n, 0, ws_cap, pay_cap, totals, side, totals, &chain[0])) return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
+    CU(cudaEventRecord(ctx->dev2[1], side));
+    CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[1], 0));
+    CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[2], 0));
+    q.snap = snap; q.fin = nullptr;
+    if (launch_coder(q, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CU(cudaEventRecord(ctx->ev[3], ctx->st));
+    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->st))
+        return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
+    S.kernel_launches += 7;                                 /* K1 x 2, plan x 2, last generation, gather x 2 */
+    CU(cudaEventRecord(ctx->ev[4], ctx->st));
+    CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&ctx->hw->total_bytes, ctx->out_off.as<uint64_t>() + nb, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&ctx->hw->total_edits, &chain[0], 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&ctx->hw->err, err, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (ctx->hw->err) {
+        const int code = -(int)(ctx->hw->err >> 40);
+        if (code == CBCG_ERR_CAPACITY || code == CBCG_ERR_INTERNAL) return PIPE_FALLBACK;   /* projection too small */
+        return device_error(ctx, "block coder");
+    }
+    float head_ms = 0, tail_ms = 0;
+    cudaEventElapsedTime(&head_ms, ctx->tev[0], ctx->tev[1]);
+    cudaEventElapsedTime(&tail_ms, ctx->kev[0], ctx->kev[1]);
+    S.ms_k1 = head_ms + tail_ms;
+    cudaEventElapsedTime(&S.ms_extract, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&S.ms_plan, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&S.ms_code, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&S.ms_gather, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&S.ms_total, ctx->ev[0], ctx->ev[4]);
+    S.d2h_bytes += nb * sizeof(BlockDesc) + 24;
+    finish_encode(ctx, opts, 0, fixed, n, ctx->hw->total_edits, nb, ctx->hw->total_bytes);
+    return CBCG_OK;
+}
+
 extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts) {
     if (!ctx) return CBCG_ERR_ARG;
     TRY(validate_opts(ctx, opts));
@@ -674,6 +787,13 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
 
     CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    if (n && !legacy && opts->gen_mode == 1 && !getenv("CBCG_NO_OVERLAP")) {
+        const int rc = encode_resident_overlapped(ctx, opts);
+        if (rc != PIPE_FALLBACK) return rc;
+        S.kernel_launches = 0; S.d2h_bytes = 0;
+        if (ctx->pipe_ready) { CU(cudaStreamSynchronize(ctx->ps[1])); CU(cudaStreamSynchronize(ctx->hp)); }   /* nothing of the attempt is left in flight */
+        CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    }
     uint64_t n_edits = 0, nb = 0;
     if (n) { TRY(run_extract(ctx)); n_edits = ctx->hw->total_edits; }
     CU(cudaEventRecord(ctx->ev[1], ctx->st));
@@ -792,7 +912,6 @@ extern "C" uint64_t cbcg_encode_bound(const cbcg_batch *b, const cbcg_encode_opt
  * the ones that take least time: all groups end together shortly after the last byte has landed. The same layout lets
  * cbcg_decode start returning text while the large blocks are still being decoded. The cut is recorded in the
  * container's index like any other; the coded bits of a block depend only on its reads and its generation. */
-#define PIPE_FALLBACK 1            /* not an error: the caller takes the one-stream path */
 #define PIPE_CHUNKS 5u             /* tail chunks (after the head that feeds the early generations); <= PIPE_MAX - 1 */
 /* shares of the tail per chunk. Shrinking shares (0.30 .. 0.10) with a steeper ramp were measured and did not pay: a
  * group ends with its slowest block, and small blocks spread more (15.2 + 16.1 ms against 15.6 + 15.7 ms for equal shares). */
@@ -810,6 +929,7 @@ static int pipe_init(cbcg_ctx *ctx) {
     if (ctx->pipe_ready) return 0;
     CU(cudaStreamCreateWithFlags(&ctx->cs, cudaStreamNonBlocking));
     for (auto &s : ctx->ps) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    { int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CU(cudaStreamCreateWithPriority(&ctx->hp, cudaStreamNonBlocking, hi)); }
     for (auto &e : ctx->cev) CU(cudaEventCreate(&e));
     for (auto &e : ctx->kev2) CU(cudaEventCreate(&e));
     for (auto &e : ctx->dev2) CU(cudaEventCreate(&e));

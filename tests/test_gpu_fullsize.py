@@ -71,6 +71,30 @@ def test_config4_shape_many_chromosomes(codec):
     assert struct.unpack_from("<I", cont, 28)[0] == 24
 
 
+def test_resident_encode_orders_agree(codec, monkeypatch):
+    """Large gen_mode-1 batches extract the tail of the batch on a side stream while the early generations are coded
+    (api.cu, encode_resident_overlapped); CBCG_NO_OVERLAP=1 keeps everything on one stream. Same cut, same bytes;
+    an indel-heavy variable-length batch exercises the workspace projection from the head's edit density."""
+    for name, scale, L in (("config1", 1.0, 100), ("config5", 0.35, 250)):
+        cfg = synth.SynthConfig.named(name, scale=scale)
+        g = synth.make_genome(cfg)
+        b = synth.make_reads(cfg, g)
+        codec.set_reference(g)
+        codec.upload(b)
+        monkeypatch.delenv("CBCG_NO_OVERLAP", raising=False)
+        codec.encode_resident(L, AUTO, 1)
+        a = codec.fetch_container().tobytes()
+        sa = codec.stats()
+        monkeypatch.setenv("CBCG_NO_OVERLAP", "1")
+        codec.encode_resident(L, AUTO, 1)
+        assert codec.fetch_container().tobytes() == a
+        sb = codec.stats()
+        assert sa["n_edits"] == sb["n_edits"] and sa["n_symbols"] == sb["n_symbols"] and sa["n_blocks"] == sb["n_blocks"]
+        monkeypatch.delenv("CBCG_NO_OVERLAP")
+        codec.decode_resident()
+        assert codec.fetch_decoded().tobytes() == b.seq_lines()
+
+
 def test_pipelined_host_buffer_encode_and_decode(codec, monkeypatch):
     """cbcg_encode / cbcg_decode on a large batch overlap the PCIe copies with the kernels and size last-generation
     blocks by their place in the batch. Whatever cut the encoder chose, the CPU restatement given the same cut writes
