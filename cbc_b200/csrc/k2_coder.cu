@@ -1565,9 +1565,10 @@ __global__ void __launch_bounds__(128) merge_prep_kernel(MergeParams P) {
     const WarpModels *pm = reinterpret_cast<const WarpModels *>(P.prev + l.small);
     uint32_t *dprev = reinterpret_cast<uint32_t *>(P.next + l.flag_prev), *dacc = reinterpret_cast<uint32_t *>(P.next + l.flag_acc);
     const uint32_t used = pm->flag_used;
+    const uint32_t flag_max = reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr)[2];   /* largest FLAG value any block has touched so far */
     for (uint32_t i = gtid; i < 65536u; i += gsz) {
         uint32_t c = 1u;
-        for (uint32_t j = 0; j < used; j++) if (pm->flag_key[j] == i) c = pm->flag_cnt[j];
+        if (i <= flag_max) for (uint32_t j = 0; j < used; j++) if (pm->flag_key[j] == i) c = pm->flag_cnt[j];
         dprev[i] = c; dacc[i] = c;
     }
     /* var rows */
@@ -1625,7 +1626,10 @@ __global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
         const uint32_t *dprev = reinterpret_cast<const uint32_t *>(P.next + l.flag_prev);
         uint32_t *dacc = reinterpret_cast<uint32_t *>(P.next + l.flag_acc);
         const uint32_t used = fm->flag_used;
-        for (uint32_t j = lane; j < used; j += 32u) { const uint32_t k = fm->flag_key[j] & 0xffffu; const uint32_t d = fm->flag_cnt[j] - dprev[k]; if (d) atomicAdd(&dacc[k], d); }
+        uint32_t kmax = 0;
+        for (uint32_t j = lane; j < used; j += 32u) { const uint32_t k = fm->flag_key[j] & 0xffffu; const uint32_t d = fm->flag_cnt[j] - dprev[k]; if (d) atomicAdd(&dacc[k], d); kmax = max(kmax, k); }
+        kmax = __reduce_max_sync(FULL_MASK, kmax);          /* pos_hdr[2]: bounds the part of the dense scratch that can differ from 1 */
+        if (lane == 0 && kmax > reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr)[2]) atomicMax(reinterpret_cast<uint32_t *>(P.next + l.pos_hdr) + 2, kmax);
     }
     /* POS slots the block shares with the snapshot */
     if (part == 1u % MERGE_PARTS) {
@@ -1704,11 +1708,12 @@ __device__ __forceinline__ void finish_dense(uint32_t lane, const uint32_t *prev
     __syncwarp();
 }
 
-/* POS alphabet of the new snapshot, one warp: the slots shared with the old snapshot were summed by merge_add; values
- * new to the snapshot are appended in block order, then order of appearance, equal values summed. The new entries are
- * collected in shared memory; a lane reads its own block's descriptor and first new values, so that 32 blocks cost two
- * round trips to memory instead of two per block. */
+/* POS alphabet of the new snapshot: the slots shared with the old snapshot were summed by merge_add; values new to the
+ * snapshot are appended in block order, then order of appearance, equal values summed. That order is serial, so one warp
+ * does the appending, into shared memory; what it would wait for is staged by the CTA's other threads, a thread per block
+ * (descriptor, then the block's first new values), so that MERGE_POS_CHUNK blocks cost two round trips to memory. */
 #define MERGE_POS_AHEAD 4u
+#define MERGE_POS_CHUNK 256u
 __device__ __forceinline__ void merge_pos_put(uint32_t lane, uint32_t *sval, uint32_t *scnt, uint32_t &nn, uint32_t cap_new, uint32_t x, uint32_t c) {
     int found = -1;
     for (uint32_t q0 = 0; q0 < nn && found < 0; q0 += 32u) {
@@ -1720,53 +1725,66 @@ __device__ __forceinline__ void merge_pos_put(uint32_t lane, uint32_t *sval, uin
     else if (nn < cap_new) { if (lane == 0) { sval[nn] = x; scnt[nn] = c; } nn++; }
     __syncwarp();
 }
-__device__ __noinline__ void merge_pos(const MergeParams &P, const SnapLayout &l, uint32_t lane) {
+__device__ __noinline__ void merge_pos(const MergeParams &P, const SnapLayout &l, uint32_t tid) {
     __shared__ uint32_t sval[CBCG_SNAP_POS_MAX], scnt[CBCG_SNAP_POS_MAX];
+    __shared__ uint32_t s_new[MERGE_POS_CHUNK], s_v[MERGE_POS_CHUNK][MERGE_POS_AHEAD], s_c[MERGE_POS_CHUNK][MERGE_POS_AHEAD];
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
     const uint32_t pc = reinterpret_cast<const uint32_t *>(P.prev + l.pos_hdr)[0];
     uint32_t *nhdr = reinterpret_cast<uint32_t *>(P.next + l.pos_hdr);
     uint32_t *nval = reinterpret_cast<uint32_t *>(P.next + l.pos_val), *ncnt = reinterpret_cast<uint32_t *>(P.next + l.pos_cnt);
     const BlockDesc *blocks = P.blocks + P.block_begin;
     const uint32_t cap_new = pc < CBCG_SNAP_POS_MAX ? CBCG_SNAP_POS_MAX - pc : 0u;
-    uint32_t nn = 0;
-    for (uint32_t b0 = 0; b0 < P.n_blocks; b0 += 32u) {
-        const uint32_t bb = b0 + lane;
-        uint32_t nnew = 0;
-        const uint32_t *bval = nullptr, *bcnt = nullptr;
-        if (bb < P.n_blocks) {
-            const BlockDesc &B = blocks[bb];
-            const uint32_t bc = B.pos_card;
-            if (bc > pc) {
-                const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
-                bval = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_val) + pc;
-                bcnt = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_cnt) + pc;
-                nnew = bc - pc;
+    uint32_t nn = 0;                                         /* warp 0's */
+    for (uint32_t b0 = 0; b0 < P.n_blocks; b0 += MERGE_POS_CHUNK) {
+        if (tid < MERGE_POS_CHUNK) {
+            const uint32_t bb = b0 + tid;
+            uint32_t nnew = 0;
+            const uint32_t *bval = nullptr, *bcnt = nullptr;
+            if (bb < P.n_blocks) {
+                const BlockDesc &B = blocks[bb];
+                const uint32_t bc = B.pos_card;
+                if (bc > pc) {
+                    const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+                    bval = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_val) + pc;
+                    bcnt = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_cnt) + pc;
+                    nnew = bc - pc;
+                }
             }
+            uint32_t v[MERGE_POS_AHEAD], c[MERGE_POS_AHEAD];
+#pragma unroll
+            for (uint32_t u = 0; u < MERGE_POS_AHEAD; u++) { v[u] = u < nnew ? bval[u] : 0u; c[u] = u < nnew ? bcnt[u] : 0u; }
+            s_new[tid] = nnew;
+#pragma unroll
+            for (uint32_t u = 0; u < MERGE_POS_AHEAD; u++) { s_v[tid][u] = v[u]; s_c[tid][u] = c[u]; }
         }
-        uint32_t v[MERGE_POS_AHEAD], c[MERGE_POS_AHEAD];
-#pragma unroll
-        for (uint32_t u = 0; u < MERGE_POS_AHEAD; u++) { v[u] = u < nnew ? bval[u] : 0u; c[u] = u < nnew ? bcnt[u] : 0u; }
-        uint32_t grown = __ballot_sync(FULL_MASK, nnew != 0u);
-        while (grown) {                                      /* blocks in ascending order */
-            const uint32_t src = (uint32_t)__ffs(grown) - 1u; grown &= grown - 1u;
-            const uint32_t cnt = __shfl_sync(FULL_MASK, nnew, src);
-#pragma unroll
-            for (uint32_t u = 0; u < MERGE_POS_AHEAD; u++) {
-                const uint32_t x = __shfl_sync(FULL_MASK, v[u], src), cc = __shfl_sync(FULL_MASK, c[u], src);
-                if (u < cnt) merge_pos_put(lane, sval, scnt, nn, cap_new, x, cc);
-            }
-            if (cnt > MERGE_POS_AHEAD) {                     /* a block with many new values (the first generations) */
-                const uint32_t *pv = reinterpret_cast<const uint32_t *>(__shfl_sync(FULL_MASK, (unsigned long long)bval, src));
-                const uint32_t *pn = reinterpret_cast<const uint32_t *>(__shfl_sync(FULL_MASK, (unsigned long long)bcnt, src));
-                for (uint32_t s0 = MERGE_POS_AHEAD; s0 < cnt; s0 += 32u) {
-                    const uint32_t s = s0 + lane;
-                    const uint32_t xv = s < cnt ? pv[s] : 0u, cv = s < cnt ? pn[s] : 0u;
-                    const uint32_t m = cnt - s0 < 32u ? cnt - s0 : 32u;
-                    for (uint32_t k = 0; k < m; k++)
-                        merge_pos_put(lane, sval, scnt, nn, cap_new, __shfl_sync(FULL_MASK, xv, k), __shfl_sync(FULL_MASK, cv, k));
+        __syncthreads();
+        if (warp == 0u) {
+            const uint32_t m_blocks = min(MERGE_POS_CHUNK, P.n_blocks - b0);
+            for (uint32_t j0 = 0; j0 < m_blocks; j0 += 32u) {
+                uint32_t grown = __ballot_sync(FULL_MASK, s_new[j0 + lane] != 0u);
+                while (grown) {                              /* blocks in ascending order */
+                    const uint32_t j = j0 + (uint32_t)__ffs(grown) - 1u; grown &= grown - 1u;
+                    const uint32_t cnt = s_new[j];
+                    for (uint32_t u = 0; u < MERGE_POS_AHEAD && u < cnt; u++) merge_pos_put(lane, sval, scnt, nn, cap_new, s_v[j][u], s_c[j][u]);
+                    if (cnt > MERGE_POS_AHEAD) {             /* a block with many new values (the first generations) */
+                        const BlockDesc &B = blocks[b0 + j];
+                        const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+                        const uint32_t *pv = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_val) + pc;
+                        const uint32_t *pn = reinterpret_cast<const uint32_t *>(P.ws + B.ws_off + w.pos_cnt) + pc;
+                        for (uint32_t s0 = MERGE_POS_AHEAD; s0 < cnt; s0 += 32u) {
+                            const uint32_t s = s0 + lane;
+                            const uint32_t xv = s < cnt ? pv[s] : 0u, cv = s < cnt ? pn[s] : 0u;
+                            const uint32_t m = cnt - s0 < 32u ? cnt - s0 : 32u;
+                            for (uint32_t k = 0; k < m; k++)
+                                merge_pos_put(lane, sval, scnt, nn, cap_new, __shfl_sync(FULL_MASK, xv, k), __shfl_sync(FULL_MASK, cv, k));
+                        }
+                    }
                 }
             }
         }
+        __syncthreads();
     }
+    if (warp != 0u) return;
     const uint32_t an = pc + nn;
     for (uint32_t i = lane; i < nn; i += 32u) nval[pc + i] = sval[i];
     uint32_t s = 0;
@@ -1799,7 +1817,7 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const SnapLayout l = snap_layout(P.L);
     if (blockIdx.x == 1u) {                                /* the POS alphabet has a CTA (one warp) of its own, beside FLAG */
-        if (warp == 0u) merge_pos(P, l, lane);
+        merge_pos(P, l, tid);
         return;
     }
     const uint32_t *ps = reinterpret_cast<const uint32_t *>(P.prev + l.small);
@@ -1822,10 +1840,11 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
     WarpModels *nm = reinterpret_cast<WarpModels *>(P.next + l.small);
     uint32_t *dacc = reinterpret_cast<uint32_t *>(P.next + l.flag_acc);
     const uint32_t base = warp * 2048u;
+    const bool live = base <= reinterpret_cast<const uint32_t *>(P.next + l.pos_hdr)[2];   /* beyond the largest touched value every count is 1 */
     uint32_t n, mine = 0;
     {
-        uint32_t s = 0;
-        for (uint32_t j0 = 0; j0 < 64u; j0 += 8u) {          /* eight loads in flight per lane */
+        uint32_t s = live ? 0u : 64u;
+        for (uint32_t j0 = 0; live && j0 < 64u; j0 += 8u) {  /* eight loads in flight per lane */
             int32_t v[8];
 #pragma unroll
             for (uint32_t u = 0; u < 8u; u++) v[u] = (int32_t)dacc[base + 32u * (j0 + u) + lane];
@@ -1842,14 +1861,14 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
     }
     if (n >= CBCG_RESCALE) {                               /* rare: halve-and-increment until the total fits */
         while (n >= CBCG_RESCALE) {
-            uint32_t s = 0;
-            for (uint32_t j = 0; j < 64u; j++) { const uint32_t i = base + 32u * j + lane; const uint32_t c = (dacc[i] >> 1) + 1u; dacc[i] = c; s += c; }
+            uint32_t s = live ? 0u : 64u;                    /* (1 >> 1) + 1 == 1 */
+            for (uint32_t j = 0; live && j < 64u; j++) { const uint32_t i = base + 32u * j + lane; const uint32_t c = (dacc[i] >> 1) + 1u; dacc[i] = c; s += c; }
             s = warp_sum(s); if (lane == 0) red[warp] = s; __syncthreads();
             n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
             __syncthreads();
         }
         mine = 0;
-        for (uint32_t j = 0; j < 64u; j++) mine += (uint32_t)__popc(__ballot_sync(FULL_MASK, dacc[base + 32u * j + lane] != 1u));
+        for (uint32_t j = 0; live && j < 64u; j++) mine += (uint32_t)__popc(__ballot_sync(FULL_MASK, dacc[base + 32u * j + lane] != 1u));
     }
     if (lane == 0) scan[warp] = mine;
     __syncthreads();
