@@ -180,7 +180,7 @@ def run_reference_arm(args):
                          "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------- B200 arm
@@ -431,14 +431,34 @@ def run_b200_arm(args):
         "index_bytes_per_gpu": index_bytes,
     }
     if rank == 0:
-        print(json.dumps(line))
+        emit(json.dumps(line))
     codec.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly one JSON line. Libraries write there behind Python's back (NCCL's version banner did, under
+    torchrun, NCCL_DEBUG_FILE notwithstanding): file descriptor 1 is pointed at stderr for the rest of the process and
+    the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: str):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
