@@ -38,8 +38,10 @@ for f, names in (("r01c_k1k3", {"k1_extract": "k1_extract_kernel", "k3_reconstru
 traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, config 2; the K2 entries are the "
                     "last-generation launch (2959 of 5007 blocks, 92 % of the reads)")
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
-out += ["The launch list is of the whole bench command: the device-resident steps (5 coder launches per direction: generations 0-4) and the",
-        "pipelined host-buffer steps (cbcg_encode / cbcg_decode: one K1 launch per chunk, one coder and one K3 launch per group).", "",
+out += ["The launch list is of the whole bench command: the device-resident steps (5 coder launches per direction: generations 0-4; K1 in two",
+        "launches, the reads of the early generations first, the rest of the batch on a side stream beside them), three one-stream encodes that",
+        "time K1 alone for its roofline entry, and the pipelined host-buffer steps (cbcg_encode / cbcg_decode: one K1 launch per chunk, one coder",
+        "and one K3 launch per group).", "",
         "Reading: K2 (`k2_coder_kernel<mode, legacy>`) is serial integer work per block: 20 warps per SM (96 registers, no spills), 56 % of issue",
         "slots, 20 % + 11 % of stall samples waiting for instruction fetch (95 KB of SASS against a 32 KB L1.5 instruction cache); DRAM < 2 % of peak.",
         "Its DRAM traffic fell from 1.14 GB to 0.49 GB per last-generation launch with deferred var rows (rows touched once are coded from",
