@@ -41,10 +41,10 @@ class Stats(C.Structure):
                 ("n_reads", C.c_uint64), ("n_blocks", C.c_uint64), ("n_symbols", C.c_uint64), ("n_edits", C.c_uint64),
                 ("payload_bytes", C.c_uint64), ("container_bytes", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("retried", C.c_uint32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class CbcgError(RuntimeError):

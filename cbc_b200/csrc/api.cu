@@ -749,7 +749,7 @@ static int encode_resident_overlapped(cbcg_ctx *ctx, const cbcg_encode_opts *opt
     CU(cudaStreamSynchronize(ctx->st));
     if (ctx->hw->err) {
         const int code = -(int)(ctx->hw->err >> 40);
-        if (code == CBCG_ERR_CAPACITY || code == CBCG_ERR_INTERNAL) return PIPE_FALLBACK;   /* projection too small */
+        if (code == CBCG_ERR_CAPACITY || code == CBCG_ERR_INTERNAL) { S.retried = 1u; return PIPE_FALLBACK; }   /* projection too small */
         return device_error(ctx, "block coder");
     }
     float head_ms = 0, tail_ms = 0;
@@ -783,7 +783,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     ctx->have_encoded = false;
     cbcg_stats &S = ctx->stats;
     S.ms_extract = S.ms_plan = S.ms_code = S.ms_gather = S.ms_reconstruct = S.ms_d2h = S.ms_total = S.ms_k1 = S.ms_k3 = 0;
-    S.kernel_launches = 0; S.d2h_bytes = 0;
+    S.kernel_launches = 0; S.d2h_bytes = 0; S.retried = 0;
     if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
 
     CU(cudaEventRecord(ctx->ev[0], ctx->st));

@@ -1554,12 +1554,23 @@ struct MergeParams {
     unsigned long long *err;
 };
 
+/* An earlier stage has failed (the error word is set): blocks of this generation may have returned before touching
+ * their workspace, so their hash tables and final states are not to be read. CTA-uniform. The resident encode runs K1
+ * on the tail of the batch beside the early generations (api.cu), so the word can be set while they are in flight. */
+__device__ __forceinline__ bool merge_aborted(const MergeParams &P) {
+    __shared__ unsigned long long seen;
+    if (threadIdx.x == 0) seen = *reinterpret_cast<volatile unsigned long long *>(P.err);
+    __syncthreads();
+    return seen != 0ull;
+}
+
 /* Offsets (in words) of the count arrays of WarpModels that the merge handles as dense models. */
 #define WM_W(field) ((uint32_t)(offsetof(WarpModels, field) / 4u))
 
 /* merge step 1: dense FLAG scratch = the snapshot's counts (1 where untouched); rows new to the snapshot are
  * created (all ones) by whichever block flips their bit. */
 __global__ void __launch_bounds__(128) merge_prep_kernel(MergeParams P) {
+    if (merge_aborted(P)) return;
     const SnapLayout l = snap_layout(P.L);
     const uint32_t gtid = blockIdx.x * 128u + threadIdx.x, gsz = gridDim.x * 128u;
     const WarpModels *pm = reinterpret_cast<const WarpModels *>(P.prev + l.small);
@@ -1600,6 +1611,7 @@ __global__ void __launch_bounds__(128) merge_prep_kernel(MergeParams P) {
  * (which starts as a copy of the snapshot). Wrapping 32-bit sums; step 3 reads them back as signed. */
 #define MERGE_PARTS 8u
 __global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
+    if (merge_aborted(P)) return;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t b = blockIdx.x * 4u + warp;
     if (b >= P.n_blocks) return;
@@ -1814,6 +1826,7 @@ __device__ __noinline__ void merge_pos(const MergeParams &P, const SnapLayout &l
 __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(MergeParams P) {
     __shared__ uint32_t red[32];
     __shared__ uint32_t scan[1024];
+    if (merge_aborted(P)) return;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const SnapLayout l = snap_layout(P.L);
     if (blockIdx.x == 1u) {                                /* the POS alphabet has a CTA (one warp) of its own, beside FLAG */
@@ -1894,6 +1907,7 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
 
 /* phase 3: clamp, total, rescale every row of the new snapshot (idempotent on rows no block touched). */
 __global__ void __launch_bounds__(256) merge_var_finish_kernel(MergeParams P) {
+    if (merge_aborted(P)) return;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t ctx = blockIdx.x * 8u + warp;
     if (ctx >= CBCG_VAR_CONTEXTS) return;

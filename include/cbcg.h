@@ -80,7 +80,8 @@ typedef struct cbcg_stats {
     uint64_t n_reads, n_blocks, n_symbols, n_edits, payload_bytes, container_bytes;
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t kernel_launches;
-    uint32_t reserved;
+    uint32_t retried;           /* 1: the call started in an overlapped order, found on the device that the sizes projected
+                                   from the head of the batch were too small, and ran again in the one-stream order */
 } cbcg_stats;
 
 /* ---- lifetime */

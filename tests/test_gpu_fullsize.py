@@ -85,6 +85,7 @@ def test_resident_encode_orders_agree(codec, monkeypatch):
         codec.encode_resident(L, AUTO, 1)
         a = codec.fetch_container().tobytes()
         sa = codec.stats()
+        assert sa["retried"] == 0                                         # the projection from the head held
         monkeypatch.setenv("CBCG_NO_OVERLAP", "1")
         codec.encode_resident(L, AUTO, 1)
         assert codec.fetch_container().tobytes() == a
@@ -93,6 +94,68 @@ def test_resident_encode_orders_agree(codec, monkeypatch):
         monkeypatch.delenv("CBCG_NO_OVERLAP")
         codec.decode_resident()
         assert codec.fetch_decoded().tobytes() == b.seq_lines()
+
+
+def _concat(a, b):
+    """Reads of a followed by reads of b (both on the same genome, a's positions below b's)."""
+    from cbc_b200.batch import Batch
+
+    def pool(oa, da, ob, db):
+        return np.concatenate([oa, ob[1:] + oa[-1]]).astype(np.uint64), np.concatenate([da[:int(oa[-1])], db[:int(ob[-1])]])
+    so, s = pool(a.seq_off, a.seq, b.seq_off, b.seq)
+    co, c = pool(a.cigar_off, a.cigar, b.cigar_off, b.cigar)
+    mo, m = pool(a.md_off, a.md, b.md_off, b.md)
+    return Batch(np.concatenate([a.pos, b.pos]), np.concatenate([a.flag, b.flag]), np.concatenate([a.seq_len, b.seq_len]),
+                 np.concatenate([a.chr, b.chr]), so, s, co, c, mo, m)
+
+
+def test_resident_encode_falls_back_when_the_head_misjudges_the_tail(codec, monkeypatch):
+    """The overlapped resident encode sizes the coder's workspace from the edit density of the batch's head. A batch whose
+    first 300 k reads are perfect matches and whose other 900 k are indel-heavy makes that projection far too small: the
+    plan kernel reports it, the coder and merge kernels stand down, and the call takes the one-stream order (exact sizes).
+    The container must be the one-stream order's, and decode to the input."""
+    import dataclasses
+    clean = synth.SynthConfig(seed=91, genome_len=6_000_000, n_reads=1_200_000, len_min=150, len_max=150, p_sub=0.0)
+    dirty = dataclasses.replace(clean, p_sub=0.02, p_indel=0.02)
+    g = synth.make_genome(clean)
+    a, d = synth.make_reads(clean, g), synth.make_reads(dirty, g)
+    mid = 1_500_000
+    ia, id_ = int(np.searchsorted(a.pos, mid)), int(np.searchsorted(d.pos, mid))
+    b = _concat(a.slice(0, ia), d.slice(id_, d.n_reads))
+    assert ia > 280_000 and b.n_reads > 1_100_000 and np.all(np.diff(b.pos.astype(np.int64)) >= 0)
+    codec.set_reference(g)
+    codec.upload(b)
+    monkeypatch.delenv("CBCG_NO_OVERLAP", raising=False)
+    codec.encode_resident(150, AUTO, 1)
+    assert codec.stats()["retried"] == 1
+    got = codec.fetch_container().tobytes()
+    monkeypatch.setenv("CBCG_NO_OVERLAP", "1")
+    codec.encode_resident(150, AUTO, 1)
+    assert codec.stats()["retried"] == 0
+    assert codec.fetch_container().tobytes() == got
+    monkeypatch.delenv("CBCG_NO_OVERLAP")
+    codec.decode_resident()
+    assert codec.fetch_decoded().tobytes() == b.seq_lines()
+    # a fresh context (its edit array starts at the default guess of one entry per 16 bases) and 8 % edited bases: K1 on
+    # the tail runs out of edit entries WHILE the early generations and their merges are in flight on the other stream
+    from cbc_b200.codec import Codec
+    worse = dataclasses.replace(clean, n_reads=1_000_000, p_sub=0.06, p_indel=0.02)
+    w = synth.make_reads(worse, g)
+    c2 = Codec(0)
+    try:
+        c2.set_reference(g)
+        c2.upload(w)
+        c2.encode_resident(150, AUTO, 1)
+        assert c2.stats()["retried"] == 1
+        got = c2.fetch_container().tobytes()
+        c2.decode_resident()
+        assert c2.fetch_decoded().tobytes() == w.seq_lines()
+        monkeypatch.setenv("CBCG_NO_OVERLAP", "1")
+        c2.encode_resident(150, AUTO, 1)
+        assert c2.fetch_container().tobytes() == got
+    finally:
+        monkeypatch.delenv("CBCG_NO_OVERLAP", raising=False)
+        c2.close()
 
 
 def test_pipelined_host_buffer_encode_and_decode(codec, monkeypatch):
