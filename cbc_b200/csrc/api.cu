@@ -920,10 +920,18 @@ static uint64_t pipe_min_reads() {
     const char *e = getenv("CBCG_PIPE_MIN_READS");
     return e ? strtoull(e, nullptr, 10) : (1ull << 20);
 }
-static void pipe_ramp(double *hi, double *lo) {
-    *hi = 1.3; *lo = 0.7;                                   /* measured on config 2: encode 15.6 ms + decode 15.8 ms against 19.2 + 17.6 on one stream */
-    const char *e = getenv("CBCG_PIPE_RAMP");               /* "hi,lo" multipliers of the mean block size (tuning) */
-    if (e) { double a = 0, b = 0; if (sscanf(e, "%lf,%lf", &a, &b) == 2 && a >= b && b > 0.05 && a < 8.0) { *hi = a; *lo = b; } }
+/* Last-generation block size per tail chunk, as multiples of the mean (normalised below so that all blocks stay
+ * co-resident). Convex: the last two chunks' blocks are much the shortest, so that the encoder is done soon after the
+ * last byte has landed and the decoder has its first text early enough to keep the link busy to the end. Measured on
+ * config 2 (encode + decode, ms): linear 1.3 .. 0.7: 14.09 + 14.53; this: 13.97 + 13.68; {1.3,1.2,1.0,0.7,0.45}: 14.24 + 13.51;
+ * {1.4,1.25,1.0,0.7,0.45}: 14.18 + 13.53; {1.35,1.25,1.0,0.65,0.4}: 14.22 + 13.72; {1.3,1.25,1.1,0.7,0.4}: 14.42 + 14.75. */
+static const double PIPE_MULT[PIPE_CHUNKS] = { 1.3, 1.2, 1.0, 0.6, 0.45 };
+static bool pipe_ramp(double *hi, double *lo) {             /* CBCG_PIPE_RAMP="hi,lo": a linear ramp instead (tuning) */
+    const char *e = getenv("CBCG_PIPE_RAMP");
+    if (!e) return false;
+    double a = 0, b = 0;
+    if (sscanf(e, "%lf,%lf", &a, &b) == 2 && a >= b && b > 0.05 && a < 8.0) { *hi = a; *lo = b; return true; }
+    return false;
 }
 static int pipe_init(cbcg_ctx *ctx) {
     if (ctx->pipe_ready) return 0;
@@ -978,10 +986,17 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     uint64_t slots = 0;
     cbcg_encode_opts used = *opts;
     used.block_reads = auto_block_reads(ctx, n, 1, &slots);
-    double hi, lo; pipe_ramp(&hi, &lo);
+    double hi = 0, lo = 0;
     std::vector<SizeStep> ramp;
     double mult[PIPE_CHUNKS], inv = 0;
-    for (uint32_t c = 0; c < PIPE_CHUNKS; c++) { mult[c] = hi - (hi - lo) * (double)c / (double)(PIPE_CHUNKS - 1); inv += PIPE_SHARE[c] / mult[c]; }
+    const bool linear = pipe_ramp(&hi, &lo);
+    for (uint32_t c = 0; c < PIPE_CHUNKS; c++) mult[c] = linear ? hi - (hi - lo) * (double)c / (double)(PIPE_CHUNKS - 1) : PIPE_MULT[c];
+    if (const char *e = getenv("CBCG_PIPE_MULTS")) {        /* tuning: one multiplier per chunk instead of the linear ramp */
+        double m[PIPE_CHUNKS]; int k = 0; const char *q = e;
+        while (k < (int)PIPE_CHUNKS) { char *end; m[k] = strtod(q, &end); if (end == q || m[k] < 0.05 || m[k] > 8.0) break; k++; if (*end != ',') break; q = end + 1; }
+        if (k == (int)PIPE_CHUNKS) for (uint32_t c = 0; c < PIPE_CHUNKS; c++) mult[c] = m[c];
+    }
+    for (uint32_t c = 0; c < PIPE_CHUNKS; c++) inv += PIPE_SHARE[c] / mult[c];
     /* inv > 1: more blocks than resident slots, the last ones would queue */
     for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) {
         const double m = mult[c - 1] * (inv > 1.0 ? inv : 1.0);
@@ -1392,7 +1407,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
         uint32_t marks[PIPE_CHUNKS + 1], nm = 0, ref_size = hb[last_first].n_reads;
         for (uint32_t k = last_first + 1; k + 1 < last_first + last_n && nm <= PIPE_CHUNKS; k++) {
             const uint32_t sz = hb[k].n_reads;
-            if (hb[k].chr == hb[k - 1].chr && (sz * 8u > ref_size * 9u || sz * 9u < ref_size * 8u) && sz == hb[k + 1].n_reads) {
+            if (hb[k].chr == hb[k - 1].chr && (sz * 20u > ref_size * 21u || sz * 21u < ref_size * 20u) && sz == hb[k + 1].n_reads) {
                 if (nm < PIPE_CHUNKS + 1) marks[nm] = k;
                 nm++; ref_size = sz;
             }
@@ -1463,10 +1478,30 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
                 CU(cudaEventRecord(ctx->kev2[0], ctx->st));
                 sd = ctx->ps[0];
                 CU(cudaStreamWaitEvent(sd, ctx->kev2[0], 0));
+                CU(cudaMemcpyAsync(seq_out + r0 * line, ctx->seq_out.as<uint8_t>() + r0 * line, (r1 - r0) * line, cudaMemcpyDeviceToHost, sd));
             }
-            CU(cudaMemcpyAsync(seq_out + r0 * line, ctx->seq_out.as<uint8_t>() + r0 * line, (r1 - r0) * line, cudaMemcpyDeviceToHost, sd));
         } else if (!g) CU(cudaEventRecord(ctx->kev2[0], ctx->st));
-        CU(cudaEventRecord(ctx->dev2[g], sd));
+        if (!g) CU(cudaEventRecord(ctx->dev2[0], sd));
+    }
+    /* The groups' texts go out on ONE stream, in the order the groups are expected to finish (smallest blocks first).
+       Issued per group stream, the copy engine served them in an order of its own: the group that was ready first
+       (6.3 ms) was copied fourth (trace, config 2), and the engine idled until the second group was ready. */
+    {
+        uint32_t order[PIPE_CHUNKS]; uint32_t no = 0;
+        for (uint32_t g = 1; g <= PIPE_CHUNKS; g++) if (gr[g] > gr[g - 1]) order[no++] = g;
+        std::stable_sort(order, order + no, [&](uint32_t a, uint32_t b) {
+            const uint32_t sa = gb[a] > gb[a - 1] ? hb[gb[a - 1]].n_reads : 0u, sb2 = gb[b] > gb[b - 1] ? hb[gb[b - 1]].n_reads : 0u;
+            return sa < sb2;
+        });
+        CU(cudaStreamWaitEvent(ctx->cs, ctx->dev2[0], 0));   /* behind the early generations' text */
+        for (uint32_t k = 0; k < no; k++) {
+            const uint32_t g = order[k];
+            const uint64_t r0 = gr[g - 1], r1 = gr[g];
+            CU(cudaStreamWaitEvent(ctx->cs, ctx->tev[2 * g + 1], 0));
+            CU(cudaMemcpyAsync(seq_out + r0 * line, ctx->seq_out.as<uint8_t>() + r0 * line, (r1 - r0) * line, cudaMemcpyDeviceToHost, ctx->cs));
+            CU(cudaEventRecord(ctx->dev2[g], ctx->cs));
+        }
+        for (uint32_t g = 1; g <= PIPE_CHUNKS; g++) if (gr[g] <= gr[g - 1]) CU(cudaEventRecord(ctx->dev2[g], ctx->ps[g % PIPE_MAX]));
     }
     for (uint32_t g = 0; g <= PIPE_CHUNKS; g++) CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[g], 0));
     CU(cudaEventRecord(ctx->ev[1], ctx->st));

@@ -1,5 +1,6 @@
 """Wall-clock of the host-buffer calls (cbcg_encode / cbcg_decode, pinned buffers) with the pipelined path on and off,
-and for a few ramps (run under gpurun). usage: e2e_probe.py [scale] [ramp ...]   ramp = hi,lo | off"""
+and for a few ramps (run under gpurun). usage: e2e_probe.py [scale] [ramp ...]   ramp = hi,lo (linear) | default | off
+(CBCG_PIPE_MULTS=m1,..,m5 in the environment overrides the multipliers of "default"; tools/probe_mults.sh)"""
 import json
 import os
 import sys
@@ -13,7 +14,7 @@ from cbc_b200 import synth                      # noqa: E402
 from cbc_b200.codec import Codec, pin_batch, pinned_empty     # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-ramps = sys.argv[2:] or ["off", "1.85,0.45"]
+ramps = sys.argv[2:] or ["off", "default"]
 cfg = synth.SynthConfig.named("config2", scale=scale)
 g = synth.make_genome(cfg)
 b = synth.make_reads(cfg, g)
@@ -29,7 +30,10 @@ for ramp in ramps:
         os.environ["CBCG_PIPE_MIN_READS"] = "1000000000000"
     else:
         os.environ["CBCG_PIPE_MIN_READS"] = "100000"
-        os.environ["CBCG_PIPE_RAMP"] = ramp
+        if ramp == "default":
+            os.environ.pop("CBCG_PIPE_RAMP", None)
+        else:
+            os.environ["CBCG_PIPE_RAMP"] = ramp
     te, td = [], []
     for it in range(5):
         t0 = time.perf_counter()
