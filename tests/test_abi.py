@@ -47,3 +47,39 @@ def test_product_code_never_touches_the_oracle():
                 if re.search(r"oracle_lib|cbc_oracle|cbco_|oracle/", t):
                     bad.append(os.path.join(d, fn))
     assert not bad, bad
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The ctypes structures of cbc_b200/codec.py and batch.py against include/cbcg.h as gcc lays it out: sizes and the
+    offset of every field (a header edit that the binding does not follow shows up here, not as a garbled stat)."""
+    import subprocess
+    import numpy as np
+    from cbc_b200 import codec
+    from cbc_b200.batch import CBatch
+    mirrors = {"cbcg_stats": codec.Stats, "cbcg_encode_opts": codec.EncodeOpts, "cbcg_batch": CBatch}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cbcg.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'    printf("{cname} size %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'    printf("{cname} {f} %zu\\n", offsetof({cname}, {f}));')
+    lines.append('    printf("cbcg_read_rec size %zu\\n", sizeof(cbcg_read_rec));')
+    for f in codec.REC_DTYPE.names:
+        lines.append(f'    printf("cbcg_read_rec {f} %zu\\n", offsetof(cbcg_read_rec, {f}));')
+    lines += ['    return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = {}
+    for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n"):
+        if ln:
+            s, f, v = ln.split()
+            got[(s, f)] = int(v)
+    for cname, cls in mirrors.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert got[(cname, f)] == getattr(cls, f).offset, (cname, f)
+    assert got[("cbcg_read_rec", "size")] == codec.REC_DTYPE.itemsize == 16
+    for f in codec.REC_DTYPE.names:
+        assert got[("cbcg_read_rec", f)] == codec.REC_DTYPE.fields[f][1], f
+    assert np.dtype(codec.SYM_DTYPE).itemsize == 8
