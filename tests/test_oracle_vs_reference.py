@@ -119,6 +119,34 @@ def test_live_reference(kw, L):
     assert decoded == ref_decoded == b.seq_lines()
 
 
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kw,L", [
+    (dict(seed=104, genome_len=1_500_000, n_reads=300_000, len_min=150, len_max=150, p_sub=0.005), 150),
+    (dict(seed=105, genome_len=4_500_000, n_reads=300_000, len_min=100, len_max=100, p_sub=0.005, p_indel=0.001), 100),
+])
+def test_live_reference_past_the_rescale_thresholds(kw, L):
+    """300 k reads: the FLAG model (step 8 from n = 65 536), the POS model and the SNP-count model (step 10) all pass
+    rescale = 2^20 (src/stream_model.c:38-49, src/sam_models.c:564) more than once; the small live cases never reach it.
+    Stream bytes against the reference encoder, decoded text against the reference decoder (no symbol trace: the
+    tracer's pointer search takes a minute at this size)."""
+    cfg = synth.SynthConfig(**kw)
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g)
+        synth.write_sam(sam, b, g)
+        ref_stream, _, _ = O.run_reference(sam, fa, d, trace=False)
+        stream, _ = O.encode_legacy(b, g, L)
+        assert stream == ref_stream
+        sp = os.path.join(d, "s.cbc")
+        with open(sp, "wb") as f:
+            f.write(stream)
+        ref_decoded, _ = O.run_reference_decode(sp, fa, d)
+    decoded, _ = O.decode_legacy(stream, g)
+    assert decoded == ref_decoded == b.seq_lines()
+
+
 def _one_read_batch(pos, flag, seq, cigar, md):
     def pool(items):
         off = np.zeros(len(items) + 1, np.uint64)
