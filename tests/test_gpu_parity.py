@@ -110,6 +110,22 @@ def test_single_block_stream_is_byte_identical_to_reference(codec, meta_path):
     assert stream == ref_stream
 
 
+def test_single_block_stream_past_the_rescale_thresholds(codec):
+    """300 k reads in the one warp of the single-block mode: FLAG, POS and SNP-count models pass rescale = 2^20 several
+    times. The CPU restatement writes the reference encoder's bytes for this very input
+    (tests/test_oracle_vs_reference.py::test_live_reference_past_the_rescale_thresholds); the GPU must write them too,
+    and read them back."""
+    cfg = synth.SynthConfig(seed=104, genome_len=1_500_000, n_reads=300_000, len_min=150, len_max=150, p_sub=0.005)
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    codec.set_reference(g)
+    stream = codec.compress(b, 150, block_reads=0)
+    want, _ = O.encode_legacy(b, g, 150)
+    assert stream == want
+    text, n = codec.decompress(stream, legacy=True)
+    assert n == b.n_reads and text == b.seq_lines()
+
+
 # ------------------------------------------------------------------ parity 3: decoded reads
 
 @pytest.mark.parametrize("meta_path", GOLDEN, ids=IDS)
