@@ -66,12 +66,15 @@ class Batch:
 
     def seq_lines(self) -> bytes:
         """SEQ column, one read per line: what the decoder must reproduce."""
-        out = bytearray()
-        seq = self.seq.tobytes()
-        for r in range(self.n_reads):
-            out += seq[int(self.seq_off[r]):int(self.seq_off[r + 1])]
-            out += b"\n"
-        return bytes(out)
+        n = self.n_reads
+        if n == 0:
+            return b""
+        lo, hi = int(self.seq_off[0]), int(self.seq_off[n])
+        out = np.full(hi - lo + n, 10, dtype=np.uint8)            # '\n' everywhere, then the bases around them
+        keep = np.ones(hi - lo + n, dtype=bool)
+        keep[(self.seq_off[1:] - np.uint64(lo)).astype(np.int64) + np.arange(n, dtype=np.int64)] = False
+        out[keep] = self.seq[lo:hi]
+        return out.tobytes()
 
     def total_bases(self) -> int:
         return int(self.seq_len.astype(np.uint64).sum())

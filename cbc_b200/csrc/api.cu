@@ -294,6 +294,9 @@ static int check_batch(cbcg_ctx *ctx, const cbcg_batch *b) {
     if (!b->pos || !b->flag || !b->seq_len || !b->chr || !b->seq_off || !b->seq || !b->cigar_off || !b->cigar || !b->md_off || !b->md)
         return fail(ctx, CBCG_ERR_ARG, "batch has NULL arrays");
     if (b->n_reads >= 0xfffffff0ull) return fail(ctx, CBCG_ERR_ARG, "more than 2^32 reads in one shard");
+    const uint64_t n = b->n_reads;                          /* the copies are sized from the pool offsets' end points */
+    if (b->seq_off[n] < b->seq_off[0] || b->cigar_off[n] < b->cigar_off[0] || b->md_off[n] < b->md_off[0])
+        return fail(ctx, CBCG_ERR_INPUT, "batch pool offsets decrease");
     return 0;
 }
 
@@ -334,13 +337,20 @@ static int batch_copy_range(cbcg_ctx *ctx, const cbcg_batch *b, uint64_t r0, uin
     return 0;
 }
 /* Host scan of the batch: chromosome runs (blocks never span chromosomes), longest and shortest read. */
-static void batch_scan(cbcg_ctx *ctx, const cbcg_batch *b) {
+static int batch_scan(cbcg_ctx *ctx, const cbcg_batch *b) {
     const uint64_t n = b->n_reads;
     uint32_t max_len = 0, min_len = 0xffffffffu;
     ctx->runs.clear();
+    uint64_t bad = 0;
     if (n) {
         const uint16_t *sl = b->seq_len;
-        for (uint64_t r = 0; r < n; r++) { const uint32_t l = sl[r]; max_len = l > max_len ? l : max_len; min_len = l < min_len ? l : min_len; }
+        const uint64_t *so = b->seq_off, *co = b->cigar_off, *mo = b->md_off;
+        for (uint64_t r = 0; r < n; r++) {
+            const uint32_t l = sl[r]; max_len = l > max_len ? l : max_len; min_len = l < min_len ? l : min_len;
+            /* SEQ pool entries are exactly the reads; CIGAR / MD offsets never decrease (kernels size their loops from them) */
+            bad |= (so[r + 1] - so[r]) ^ (uint64_t)l;
+            bad |= (uint64_t)(co[r + 1] < co[r]) | (uint64_t)(mo[r + 1] < mo[r]);
+        }
         ChrRun run = { 0, 0, b->chr[0] };
         const uint32_t *ch = b->chr;
         for (uint64_t r = 0; r < n; r++) {
@@ -352,6 +362,10 @@ static void batch_scan(cbcg_ctx *ctx, const cbcg_batch *b) {
     ctx->db.max_len = max_len;
     ctx->batch_min_len = n ? min_len : 0;
     ctx->total_bases = n ? b->seq_off[n] - b->seq_off[0] : 0;
+    if (n && (min_len == 0 || max_len > CBCG_MAX_READ_LEN))
+        return fail(ctx, CBCG_ERR_INPUT, "read length outside 1..%u (shortest %u, longest %u)", CBCG_MAX_READ_LEN, min_len, max_len);
+    if (bad) return fail(ctx, CBCG_ERR_INPUT, "batch offsets inconsistent: seq_off must advance by seq_len, cigar_off / md_off must not decrease");
+    return 0;
 }
 
 extern "C" int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *b) {
@@ -363,9 +377,10 @@ extern "C" int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *b) {
     CU(cudaEventRecord(ctx->ev[0], ctx->st));
     uint64_t h2d = 0;
     TRY(batch_copy_range(ctx, b, 0, n, ctx->st, &h2d));
-    batch_scan(ctx, b);                                   /* while the copies fly */
+    const int scan_rc = batch_scan(ctx, b);               /* while the copies fly */
     CU(cudaEventRecord(ctx->ev[1], ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
+    if (scan_rc) return scan_rc;                          /* nothing is left in flight that reads the caller's buffers */
     ctx->have_batch = true;
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
     ctx->stats.ms_h2d = ms; ctx->stats.h2d_bytes = h2d; ctx->stats.n_reads = n;
@@ -945,6 +960,15 @@ static int pipe_init(cbcg_ctx *ctx) {
     ctx->pipe_ready = true;
     return 0;
 }
+/* Error exit of a pipelined call: nothing that touches the caller's buffers (or races the next call) stays in flight. */
+static void pipe_drain(cbcg_ctx *ctx) {
+    if (ctx->pipe_ready) {
+        cudaStreamSynchronize(ctx->cs); cudaStreamSynchronize(ctx->hp);
+        for (auto &s : ctx->ps) cudaStreamSynchronize(s);
+    }
+    cudaStreamSynchronize(ctx->st);
+    (void)cudaGetLastError();
+}
 static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encode_opts *opts) {
     static const uint32_t sc[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sr[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
     const uint64_t n = b->n_reads;
@@ -953,6 +977,7 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     uint64_t early = 0;
     for (uint32_t g = 0; g < CBCG_GEN_LEVELS; g++) early += (uint64_t)sc[g] * sr[g];
     if (n < early + tile * (PIPE_CHUNKS + 1)) return PIPE_FALLBACK;
+    if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");   /* before any copy is queued */
     TRY(pipe_init(ctx));
     TRY(batch_prepare(ctx, b));
     set_carveout_all(100);
@@ -978,9 +1003,8 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
         TRY(batch_copy_range(ctx, b, cut[c], cut[c + 1], ctx->cs, &h2d));
         CU(cudaEventRecord(ctx->cev[c], ctx->cs));
     }
-    batch_scan(ctx, b);                                     /* while the copies fly */
+    TRY(batch_scan(ctx, b));                                /* while the copies fly */
     const bool fixed = ctx->batch_min_len == L && ctx->db.max_len == L;
-    if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");
 
     /* the cut: early generations on their schedule, then the ramp */
     uint64_t slots = 0;
@@ -1130,7 +1154,7 @@ extern "C" int cbcg_encode(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_en
         TRY(check_batch(ctx, batch));
         CU(cudaSetDevice(ctx->device));
         const int rc = encode_pipelined(ctx, batch, opts);
-        if (rc < 0) return rc;
+        if (rc < 0) { pipe_drain(ctx); return rc; }          /* copies from the caller's batch may still be queued */
         if (rc == CBCG_OK) return cbcg_fetch_container(ctx, out, out_cap, out_len);
         if (ctx->have_batch) {                              /* fallback with the batch already resident */
             TRY(cbcg_encode_resident(ctx, opts));
@@ -1245,6 +1269,19 @@ extern "C" int cbcg_decoded_size(const uint8_t *in, uint64_t in_len, uint64_t *n
     return CBCG_OK;
 }
 
+/* CBCG_POISON_DECODE=1 (tests, bench.py's correctness step): the decoder's output buffers are the encoder's work
+ * buffers (K1 left this very batch's records and edits in them), so a decoder that wrote nothing would still hand K3
+ * the right answer. Filled with 0xff first, only what the decoder really wrote can come out right. */
+static int poison_decode_outputs(cbcg_ctx *ctx, uint64_t reads_cap, uint64_t edits_cap) {
+    const char *e = getenv("CBCG_POISON_DECODE");
+    if (!e || !*e || *e == '0') return 0;
+    CU(cudaMemsetAsync(ctx->recs.p, 0xff, (reads_cap + 1) * sizeof(cbcg_read_rec), ctx->st));
+    CU(cudaMemsetAsync(ctx->chr_out.p, 0xff, (reads_cap + 1) * 4, ctx->st));
+    CU(cudaMemsetAsync(ctx->edits.p, 0xff, (edits_cap + 64) * 2, ctx->st));
+    if (ctx->seq_out.p) CU(cudaMemsetAsync(ctx->seq_out.p, 0xff, ctx->seq_out.cap, ctx->st));
+    return 0;
+}
+
 /* K2 decode of ctx->hblocks[0..nb) (n_reads, chr, base_pos, n_edits, payload_bytes filled in) whose payload
  * bytes lie back to back in ctx->payload. Leaves recs / edits / chr_out on the device. */
 static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy, bool primed, bool fixed, uint64_t reads_cap, uint64_t edits_cap,
@@ -1258,6 +1295,7 @@ static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy,
                                    : coder_ws_bytes_bound(L, reads_cap, edits_cap, nb, 0, primed);
     TRY(ensure(ctx, ctx->ws, ws_cap));
     TRY(reset_words(ctx));
+    TRY(poison_decode_outputs(ctx, reads_cap, edits_cap));
     CoderParams p = coder_params(ctx, (uint32_t)nb, L, legacy, 1);
     p.chr = ctx->chr_out.as<uint32_t>();
     p.payload = ctx->payload.as<uint8_t>();
@@ -1325,6 +1363,7 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
     CU(cudaSetDevice(ctx->device));
     set_carveout_all(-1);
     ctx->have_decoded = false;
+    ctx->have_encoded = false;                              /* ctx->payload and ctx->hblocks are about to hold another container */
     cbcg_stats &S = ctx->stats;
     S = cbcg_stats();
     CU(cudaEventRecord(ctx->ev[0], ctx->st));
@@ -1388,6 +1427,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
     TRY(pipe_init(ctx));
     set_carveout_all(100);
     ctx->have_decoded = false;
+    ctx->have_encoded = false;                              /* ctx->payload and ctx->hblocks are about to hold another container */
     cbcg_stats &S = ctx->stats;
     S = cbcg_stats();
     uint64_t nr = 0, ne = 0, pb = 0;
@@ -1444,6 +1484,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
     if (pb) CU(cudaMemcpyAsync(ctx->payload.p, in + c.payload_off, pb, cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->blocks.p, hb, (uint64_t)nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
     TRY(reset_words(ctx));
+    TRY(poison_decode_outputs(ctx, nr, ne));
     CoderParams p = coder_params(ctx, nb, c.L, 0, 1);
     p.chr = ctx->chr_out.as<uint32_t>();
     p.payload = ctx->payload.as<uint8_t>();
@@ -1538,6 +1579,7 @@ extern "C" int cbcg_decode(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, in
     if (!legacy) {
         CU(cudaSetDevice(ctx->device));
         const int rc = decode_pipelined(ctx, in, in_len, seq_out, seq_cap, seq_len, n_reads);
+        if (rc < 0) pipe_drain(ctx);                         /* copies into seq_out may still be queued */
         if (rc != PIPE_FALLBACK) return rc;
     }
     TRY(decode_to_records(ctx, in, in_len, legacy, &nr, &ne, &max_len, &fixed_len));

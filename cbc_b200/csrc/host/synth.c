@@ -61,9 +61,10 @@ static uint32_t put_num(uint8_t *dst, uint32_t v) {
     return (uint32_t)n;
 }
 
-/* Generates reads [0, n_reads) of one chromosome. Returns 0 or <0 (capacity). */
+/* Generates reads [lo, hi) of the n reads of one chromosome (all n positions are drawn and sorted, so a sub-range
+ * is the same reads the whole range would hold there). Returns 0 or <0 (capacity). */
 static int gen_chr(const cbcs_params *p, uint32_t chr, const uint8_t *ref, uint64_t ref_len,
-                   uint64_t first_ordinal, uint64_t n, cbcs_out *o) {
+                   uint64_t first_ordinal, uint64_t n, uint64_t lo, uint64_t hi, cbcs_out *o) {
     uint32_t lmax = p->len_max;
     if (ref_len < 4ull * lmax + 16) return -1;
     uint64_t span = ref_len - 2ull * lmax - 8;
@@ -74,7 +75,8 @@ static int gen_chr(const cbcs_params *p, uint32_t chr, const uint8_t *ref, uint6
     qsort(posv, n, sizeof(uint32_t), cmp_u32);
 
     uint8_t cig[2048], md[2048];
-    for (uint64_t i = 0; i < n; i++) {
+    if (hi > n) hi = n;
+    for (uint64_t i = lo; i < hi; i++) {
         uint64_t ord = first_ordinal + i, r_idx = o->n_reads;
         rng r; rng_seed(&r, p->seed, ord);
         uint32_t len = p->len_min + (p->len_max > p->len_min ? rng_below(&r, p->len_max - p->len_min + 1) : 0);
@@ -149,7 +151,10 @@ static int gen_chr(const cbcs_params *p, uint32_t chr, const uint8_t *ref, uint6
     return 0;
 }
 
-int cbcs_reads(const cbcs_params *p, const uint8_t *const *chr_bases, const uint64_t *chr_len, cbcs_out *o) {
+/* Reads [r0, r1) of the whole position-sorted input (ordinals over all chromosomes): what one region shard holds.
+ * chr_bases[c] may be NULL for chromosomes the range does not touch. */
+int cbcs_reads_range(const cbcs_params *p, const uint8_t *const *chr_bases, const uint64_t *chr_len, uint64_t r0, uint64_t r1,
+                     cbcs_out *o) {
     if (!p || !o || p->n_chr == 0 || p->len_min == 0 || p->len_max < p->len_min || p->len_max > 252) return -1;
     o->n_reads = 0; o->seq_size = o->cigar_size = o->md_size = 0;
     if (o->reads_cap) { o->seq_off[0] = o->cigar_off[0] = o->md_off[0] = 0; }
@@ -159,11 +164,30 @@ int cbcs_reads(const cbcs_params *p, const uint8_t *const *chr_bases, const uint
     for (uint32_t c = 0; c < p->n_chr; c++) {
         uint64_t n = (c + 1 == p->n_chr) ? p->n_reads - done
                                          : (uint64_t)((double)p->n_reads * (double)chr_len[c] / (double)total);
-        int rc = gen_chr(p, c, chr_bases[c], chr_len[c], done, n, o);
-        if (rc) return rc;
+        if (done < r1 && done + n > r0) {
+            if (!chr_bases[c]) return -5;
+            const uint64_t lo = r0 > done ? r0 - done : 0, hi = r1 - done < n ? r1 - done : n;
+            int rc = gen_chr(p, c, chr_bases[c], chr_len[c], done, n, lo, hi, o);
+            if (rc) return rc;
+        }
         done += n;
     }
     return 0;
+}
+
+/* Read counts per chromosome, as cbcs_reads / cbcs_reads_range deal them out (out[n_chr]). */
+void cbcs_chr_counts(const cbcs_params *p, const uint64_t *chr_len, uint64_t *out) {
+    uint64_t total = 0, done = 0;
+    for (uint32_t c = 0; c < p->n_chr; c++) total += chr_len[c];
+    for (uint32_t c = 0; c < p->n_chr; c++) {
+        out[c] = (c + 1 == p->n_chr) ? p->n_reads - done : (uint64_t)((double)p->n_reads * (double)chr_len[c] / (double)total);
+        done += out[c];
+    }
+}
+
+int cbcs_reads(const cbcs_params *p, const uint8_t *const *chr_bases, const uint64_t *chr_len, cbcs_out *o) {
+    if (!p) return -1;
+    return cbcs_reads_range(p, chr_bases, chr_len, 0, p->n_reads, o);
 }
 
 int cbcs_write_fasta(const char *path, uint32_t n_chr, const char *const *names,

@@ -32,6 +32,10 @@ typedef struct cbcs_out {
 
 void cbcs_genome(uint64_t seed, uint32_t chr, uint8_t *bases, uint64_t len);
 int cbcs_reads(const cbcs_params *p, const uint8_t *const *chr_bases, const uint64_t *chr_len, cbcs_out *o);
+/* reads [r0, r1) of the whole position-sorted input: one region shard (chr_bases[c] may be NULL where untouched) */
+int cbcs_reads_range(const cbcs_params *p, const uint8_t *const *chr_bases, const uint64_t *chr_len, uint64_t r0, uint64_t r1,
+                     cbcs_out *o);
+void cbcs_chr_counts(const cbcs_params *p, const uint64_t *chr_len, uint64_t *out);
 int cbcs_write_fasta(const char *path, uint32_t n_chr, const char *const *names,
                      const uint8_t *const *chr_bases, const uint64_t *chr_len);
 int cbcs_write_sam(const char *path, const cbcs_out *o, uint32_t n_chr, const char *const *names,

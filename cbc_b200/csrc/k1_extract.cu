@@ -368,11 +368,11 @@ int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, u
     const uint64_t tiles = extract_num_tiles(r_end - r_begin);
     const uint32_t seq_cap = (K1_TILE * b.max_len + 48u) & ~15u;
     const size_t smem = sizeof(K1Smem) + seq_cap + 16;
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(k1_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
-    }
+    /* per device, so no process-wide cache: a context on another GPU of the same process needs it too. The limit is the
+       worst case (CBCG_MAX_READ_LEN); occupancy follows the size actually launched with. */
+    const size_t smem_max = sizeof(K1Smem) + ((K1_TILE * CBCG_MAX_READ_LEN + 48u) & ~15u) + 16;
+    if (smem > smem_max) return -1;
+    if (cudaFuncSetAttribute(k1_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) return -1;
     if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;
     if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;
     if (ev_start) cudaEventRecord(ev_start, st);

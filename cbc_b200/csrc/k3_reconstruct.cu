@@ -375,11 +375,10 @@ int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32
     if (n_reads == 0) return 0;
     const uint64_t tiles = reconstruct_num_tiles(n_reads);
     const size_t smem = sizeof(K3Smem) + (size_t)K3_TILE * (max_len + 1u) + 80;
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(k3_reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
-    }
+    /* per device, so no process-wide cache (see launch_extract) */
+    const size_t smem_max = sizeof(K3Smem) + (size_t)K3_TILE * (CBCG_MAX_READ_LEN + 1u) + 80;
+    if (smem > smem_max) return -1;
+    if (cudaFuncSetAttribute(k3_reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) return -1;
     if (!fixed_len) {                                       /* closed-form offsets use neither the ticket nor the descriptors */
         if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;
         if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;

@@ -20,6 +20,18 @@ CBCS_MAGIC = 0x53434243   # "CBCS"
 CBCS_VERSION = 1
 
 
+def container_head_len(container: bytes) -> int:
+    """Bytes of a "CBCB" container before its payload: the 40-byte header, the chromosome names, the u32 index length and
+    the varint block index itself (what cbcg_fetch_index returns)."""
+    n_chr, = struct.unpack_from("<I", container, 28)
+    o = 40
+    for _ in range(n_chr):
+        nl, = struct.unpack_from("<I", container, o)
+        o += 4 + nl + ((4 - (nl & 3)) & 3)
+    index_bytes, = struct.unpack_from("<I", container, o)
+    return o + 4 + index_bytes
+
+
 def shard_ranges(n_reads: int, world: int) -> List[Tuple[int, int]]:
     """Equal contiguous ordinal ranges [r0, r1) per rank (reads are position-sorted, so these are
     genomic regions). Blocks are cut inside each shard, so shard cuts are block boundaries by construction."""

@@ -39,6 +39,7 @@ def _lib():
         _LIB.cbcs_genome.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64]
         _LIB.cbcs_genome.restype = None
         _LIB.cbcs_reads.argtypes = [C.POINTER(_Params), C.c_void_p, C.c_void_p, C.POINTER(_Out)]
+        _LIB.cbcs_reads_range.argtypes = [C.POINTER(_Params), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(_Out)]
         _LIB.cbcs_write_fasta.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.cbcs_write_sam.argtypes = [C.c_char_p, C.POINTER(_Out), C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
     return _LIB
@@ -114,15 +115,18 @@ def _out_struct(n, seq_cap, cig_cap, md_cap):
     return o, arrs
 
 
-def make_reads(cfg: SynthConfig, genome: Genome) -> Batch:
+def make_reads(cfg: SynthConfig, genome: Genome, r0: int = 0, r1: int | None = None) -> Batch:
+    """Reads [r0, r1) of the position-sorted input `cfg` describes (default: all of it). A sub-range holds exactly the
+    reads the whole input holds there: every read has its own RNG stream keyed by (seed, ordinal)."""
     lib = _lib()
-    n = cfg.n_reads
+    r1 = cfg.n_reads if r1 is None else min(r1, cfg.n_reads)
+    n = max(r1 - r0, 0)
     per_read = 16 + int(cfg.len_max * (4 * cfg.p_indel + 3 * (cfg.p_sub + cfg.p_n)) * 4) + (8 if cfg.p_clip else 0)
     o, arrs = _out_struct(n, n * cfg.len_max + 64, n * per_read + 4096, n * per_read + 4096)
-    p = _Params(cfg.seed, n, cfg.n_chr, cfg.len_min, cfg.len_max, cfg.p_sub, cfg.p_indel, cfg.p_clip,
+    p = _Params(cfg.seed, cfg.n_reads, cfg.n_chr, cfg.len_min, cfg.len_max, cfg.p_sub, cfg.p_indel, cfg.p_clip,
                 cfg.p_rev, cfg.p_n, cfg.flag_mode, cfg.avoid_b3)
     ptrs, lens, _ = genome.c_arrays()
-    rc = lib.cbcs_reads(C.byref(p), ptrs, lens, C.byref(o))
+    rc = lib.cbcs_reads_range(C.byref(p), ptrs, lens, r0, r1, C.byref(o))
     if rc:
         raise RuntimeError(f"cbcs_reads failed: {rc}")
     assert o.n_reads == n

@@ -1,0 +1,101 @@
+"""Region shards on the GPU: two contexts on device 0 stand for two ranks. Each codes its contiguous range of ONE
+position-sorted input with the CUDA coder, the shard containers go into one "CBCS" file at the scanned offsets
+(cbc_b200.shard), and each context decodes the OTHER context's shard from that file: the concatenation
+of the decoded shards is the input. Also: the state of "the last encode" does not survive a decode of another
+container (encode_resident -> decode(other) -> fetch_container must not glue two containers)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from cbc_b200 import shard, synth
+from cbc_b200.codec import CbcgError, Codec
+
+pytestmark = pytest.mark.gpu
+
+AUTO = 0xffffffff
+
+
+@pytest.mark.parametrize("name,scale,world", [("config3", 0.02, 2), ("config4", 0.0005, 3), ("config5", 0.02, 2)])
+def test_cbcs_round_trip_with_the_gpu_coder(name, scale, world):
+    cfg = synth.SynthConfig.named(name, scale=scale)
+    g = synth.make_genome(cfg)
+    whole = synth.make_reads(cfg, g)
+    L = cfg.len_max
+    ranges = shard.shard_ranges(cfg.n_reads, world)
+    codecs = [Codec(0) for _ in range(world)]
+    conts, heads, payloads, parts = [], [], [], []
+    for r, (r0, r1) in enumerate(ranges):
+        mine = synth.make_reads(cfg, g, r0, r1)              # each "rank" generates only its region
+        parts.append(mine)
+        codecs[r].set_reference(g)
+        codecs[r].upload(mine)
+        codecs[r].encode_resident(L, AUTO, 1)
+        head, pb = codecs[r].fetch_index()
+        cont = codecs[r].fetch_container().tobytes()
+        assert cont[:len(head)] == head and len(cont) == len(head) + pb
+        assert shard.container_head_len(cont) == len(head)
+        conts.append(cont); heads.append(head); payloads.append(pb)
+    assert b"".join(p.seq_lines() for p in parts) == whole.seq_lines()
+    layout = shard.layout_from_sizes([len(h) for h in heads], payloads, heads)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "out.cbcs")
+        for r in reversed(range(world)):                     # any write order gives the same file
+            shard.write_shard(path, r, layout, conts[r])
+        with open(path, "rb") as f:
+            data = f.read()
+    assert len(data) == layout.total
+    shards = shard.read_shards(data)
+    text = b""
+    for r in range(world):
+        t, n = codecs[(r + 1) % world].decompress(shards[r])  # decoded by another context: shards are self-contained
+        assert n == parts[r].n_reads
+        text += t
+    assert text == whole.seq_lines()
+    for c in codecs:
+        c.close()
+
+
+def test_last_encode_state_does_not_survive_a_foreign_decode():
+    cfg = synth.SynthConfig(seed=9, genome_len=150_000, n_reads=9_000, len_min=100, len_max=100, p_sub=0.01)
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    a, other = b.slice(0, 5000), b.slice(5000, 9000)
+    c = Codec(0)
+    c.set_reference(g)
+    foreign = c.compress(other, 100, 256, 1)
+    c.upload(a)
+    c.encode_resident(100, 256, 1)
+    mine = c.fetch_container().tobytes()
+    text, n = c.decompress(foreign)                          # overwrites the payload and descriptors of "the last encode"
+    assert n == 4000 and text == other.seq_lines()
+    with pytest.raises(CbcgError):
+        c.fetch_container()
+    with pytest.raises(CbcgError):
+        c.decode_resident()
+    c.encode_resident(100, 256, 1)                           # the batch is still resident
+    assert c.fetch_container().tobytes() == mine
+    c.close()
+
+
+def test_batch_validation_reports_input_errors():
+    cfg = synth.SynthConfig(seed=3, genome_len=50_000, n_reads=500, len_min=100, len_max=100)
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    c = Codec(0)
+    c.set_reference(g)
+    bad = b.slice(0, 500)
+    bad.seq_len[7] = 0
+    with pytest.raises(CbcgError) as e:
+        c.upload(bad)
+    assert e.value.status == -6
+    bad = b.slice(0, 500)
+    bad.md_off[100] = bad.md_off[99] - np.uint64(1) if bad.md_off[99] else np.uint64(5)
+    bad.md_off[99] = bad.md_off[100] + np.uint64(3)
+    with pytest.raises(CbcgError) as e:
+        c.upload(bad)
+    assert e.value.status == -6
+    c.upload(b)                                              # the context is still usable
+    c.encode_resident(100, 128, 0)
+    c.close()

@@ -25,13 +25,7 @@ def _worker(rank, world, port, path, q):
     r0, r1 = shard.shard_ranges(b.n_reads, world)[rank]
     mine = b.slice(r0, r1)
     cont = O.encode_blocked(mine, g, 100, 256)
-    # header + index length: 40 + names + 32 per block
-    import struct
-    n_blocks, n_chr = struct.unpack_from("<II", cont, 24)
-    o = 40
-    for _ in range(n_chr):
-        nl, = struct.unpack_from("<I", cont, o); o += 4 + nl + ((4 - (nl & 3)) & 3)
-    head_len = o + 32 * n_blocks
+    head_len = shard.container_head_len(cont)               # header + names + varint block index: what cbcg_fetch_index returns
     layout = shard.gather_index(cont[:head_len], len(cont) - head_len, dist, torch.device("cpu"))
     assert layout.heads[rank] == cont[:head_len]
     shard.write_shard(path, rank, layout, cont)
