@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "internal.h"
+#include "container.h"
 
 #define ABI_VERSION 1
 
@@ -575,61 +576,6 @@ static CoderParams coder_params(cbcg_ctx *ctx, uint32_t n_blocks, uint32_t L, in
     return p;
 }
 
-static void put32(std::vector<uint8_t> &v, uint32_t x) { for (int i = 0; i < 4; i++) v.push_back((uint8_t)(x >> (8 * i))); }
-static void put64(std::vector<uint8_t> &v, uint64_t x) { for (int i = 0; i < 8; i++) v.push_back((uint8_t)(x >> (8 * i))); }
-
-/* Block index of the container: per block a few delta-coded LEB128 varints ("Container"):
- *   v0 = zigzag(n_reads - previous n_reads) << 2 | chromosome changed << 1 | generation changed
- *   [chromosome ordinal]  [generation increment - 1]
- *   zigzag(second difference of base_pos)  zigzag(difference of n_edits)  zigzag(difference of payload_bytes) */
-struct IndexState { int64_t n_reads, chr, gen, base, d1, edits, payload; };
-static void put_varint(std::vector<uint8_t> &v, uint64_t x) {
-    do { uint8_t c = (uint8_t)(x & 0x7f); x >>= 7; if (x) c |= 0x80; v.push_back(c); } while (x);
-}
-static uint64_t zz(int64_t v) { return ((uint64_t)v << 1) ^ (uint64_t)(v >> 63); }
-static int64_t unzz(uint64_t v) { return (int64_t)(v >> 1) ^ -(int64_t)(v & 1); }
-static void index_put(std::vector<uint8_t> &out, IndexState &st, const BlockDesc &b) {
-    const bool chr_ch = (int64_t)b.chr != st.chr, gen_ch = (int64_t)b.gen != st.gen;
-    put_varint(out, (zz((int64_t)b.n_reads - st.n_reads) << 2) | (chr_ch ? 2u : 0u) | (gen_ch ? 1u : 0u));
-    if (chr_ch) { put_varint(out, b.chr); st.base = 0; st.d1 = 0; }
-    if (gen_ch) put_varint(out, (uint64_t)((int64_t)b.gen - st.gen - 1));
-    const int64_t d1 = (int64_t)b.base_pos - st.base;
-    put_varint(out, zz(d1 - st.d1));
-    put_varint(out, zz((int64_t)b.n_edits - st.edits));
-    put_varint(out, zz((int64_t)b.payload_bytes - st.payload));
-    st.n_reads = b.n_reads; st.chr = b.chr; st.gen = b.gen; st.base = b.base_pos; st.d1 = d1; st.edits = b.n_edits; st.payload = b.payload_bytes;
-}
-static bool get_varint(const uint8_t *p, uint64_t end, uint64_t &o, uint64_t &v) {
-    uint64_t r = 0; int sh = 0;
-    for (;;) {
-        if (o >= end || sh > 63) return false;
-        const uint8_t c = p[o++];
-        r |= (uint64_t)(c & 0x7f) << sh; sh += 7;
-        if (!(c & 0x80)) break;
-    }
-    v = r; return true;
-}
-static bool index_get(const uint8_t *p, uint64_t end, uint64_t &o, IndexState &st, BlockDesc &b) {
-    uint64_t v;
-    if (!get_varint(p, end, o, v)) return false;
-    st.n_reads += unzz(v >> 2);
-    if (v & 2) { uint64_t c; if (!get_varint(p, end, o, c)) return false; st.chr = (int64_t)c; st.base = 0; st.d1 = 0; }
-    if (v & 1) { uint64_t gi; if (!get_varint(p, end, o, gi) || gi > 255) return false; st.gen += (int64_t)gi + 1; }
-    if (!get_varint(p, end, o, v)) return false;
-    st.d1 += unzz(v); st.base += st.d1;
-    if (!get_varint(p, end, o, v)) return false;
-    st.edits += unzz(v);
-    if (!get_varint(p, end, o, v)) return false;
-    st.payload += unzz(v);
-    const int64_t lim = 0xffffffffll;
-    if (st.n_reads < 0 || st.n_reads > lim || st.chr < 0 || st.chr > lim || st.gen < 0 || st.gen > 255 || st.base < 0 || st.base > lim ||
-        st.edits < 0 || st.edits > lim || st.payload < 0 || st.payload > lim) return false;
-    memset(&b, 0, sizeof b);
-    b.n_reads = (uint32_t)st.n_reads; b.chr = (uint32_t)st.chr; b.gen = (uint32_t)st.gen; b.base_pos = (uint32_t)st.base;
-    b.n_edits = (uint32_t)st.edits; b.payload_bytes = (uint32_t)st.payload;
-    return true;
-}
-
 static int validate_opts(cbcg_ctx *ctx, const cbcg_encode_opts *o) {
     if (!o) return fail(ctx, CBCG_ERR_ARG, "NULL options");
     if (o->read_len_header == 0 || o->read_len_header > CBCG_MAX_READ_LEN) return fail(ctx, CBCG_ERR_ARG, "read_len_header must be in 1..%u", CBCG_MAX_READ_LEN);
@@ -647,21 +593,7 @@ static void finish_encode(cbcg_ctx *ctx, const cbcg_encode_opts *opts, int legac
     h.clear();
     uint64_t n_syms = 0;
     for (uint64_t k = 0; k < nb; k++) n_syms += ctx->hblocks[k].n_symbols;
-    if (!legacy) {
-        put32(h, CBCG_MAGIC); put32(h, CBCG_VERSION); put32(h, ctx->db.max_len); put32(h, L);
-        put64(h, n); put32(h, (uint32_t)nb); put32(h, ctx->dg.n_chr); put32(h, opts->block_reads); put32(h, opts->gen_mode | (fixed ? CBCG_MODE_FIXED_LEN : 0u));
-        for (uint32_t c = 0; c < ctx->dg.n_chr; c++) {
-            const std::string &s = ctx->names[c];
-            put32(h, (uint32_t)s.size());
-            h.insert(h.end(), s.begin(), s.end());
-            for (size_t q = s.size(); q & 3; q++) h.push_back(0);
-        }
-        std::vector<uint8_t> ix;
-        IndexState st = { (int64_t)opts->block_reads, 0, 0, 0, 0, 0, 0 };
-        for (uint64_t k = 0; k < nb; k++) index_put(ix, st, ctx->hblocks[k]);
-        put32(h, (uint32_t)ix.size());
-        h.insert(h.end(), ix.begin(), ix.end());
-    }
+    if (!legacy) container_head(h, ctx->db.max_len, L, n, nb, ctx->names, opts->block_reads, opts->gen_mode | (fixed ? CBCG_MODE_FIXED_LEN : 0u), ctx->hblocks);
     ctx->enc_L = L; ctx->enc_block_reads = opts->block_reads; ctx->enc_gen_mode = opts->gen_mode; ctx->enc_legacy = legacy;
     ctx->enc_max_len = ctx->db.max_len; ctx->enc_fixed = fixed ? 1u : 0u;
     ctx->enc_n_reads = n; ctx->enc_n_edits = n_edits; ctx->enc_n_blocks = nb; ctx->enc_payload_bytes = payload_total;
@@ -1225,8 +1157,6 @@ struct Container {
     uint64_t index_off, index_bytes, payload_off;
     std::vector<uint32_t> chr_map;             /* container ordinal -> genome ordinal */
 };
-static uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
-static uint64_t rd64(const uint8_t *p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
 
 /* names == NULL: structure only */
 static int parse_container(const uint8_t *in, uint64_t len, const std::vector<std::string> *names, Container &c) {
@@ -1334,7 +1264,7 @@ static int blocks_from_index(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
                              uint64_t *reads_total, uint64_t *edits_total, uint64_t *payload_total) {
     TRY(ensure_hblocks(ctx, (size_t)c.n_blocks + 1));
     uint64_t nr = 0, ne = 0, pb = 0;
-    IndexState st = { (int64_t)c.block_reads, 0, 0, 0, 0, 0, 0 };
+    IndexState st = index_state(c.block_reads);
     uint64_t o = c.index_off;
     uint32_t prev_gen = 0;
     for (uint32_t k = 0; k < c.n_blocks; k++) {

@@ -50,6 +50,7 @@ struct BlockDesc {
     uint32_t n_rows;                       /*   var rows created */
     uint32_t pa_touched;                   /*   pos_alpha models instantiated */
     uint32_t pad;
+    uint32_t sub_bytes[CBCG_N_SUB];        /* blocked containers (v4): coded size of each substream, A | B | C | D back to back */
 };
 
 /* Coder launch parameters. */
@@ -74,8 +75,8 @@ struct CoderParams {
     uint32_t primed;                       /* gen_mode 1: models start from `snap` instead of the initial state */
     uint32_t fixed_len;                    /* CBCG_MODE_FIXED_LEN: every read is L bases, the length symbol is not coded */
     uint32_t pad;
-    const uint8_t *snap;                   /* snapshot S_{g-1} (snapshot_bytes(L) bytes) */
-    uint8_t *fin;                          /* per block of this launch: final small-model image (NULL: not merged) */
+    const uint8_t *snap;                   /* snapshot S_{g-1} (snapshot_bytes(L) bytes); blocked containers always start from one */
+    uint8_t *fin;                          /* per block (absolute index): its image of the small models (WarpModels), read by the merges */
 };
 #define MAX_NAME 256u
 
@@ -103,7 +104,8 @@ uint64_t snapshot_bytes(uint32_t L);
 uint64_t fin_stride_bytes(void);
 int launch_snapshot_init(uint8_t *snap, uint32_t L, cudaStream_t st);
 int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_blocks, uint32_t L, const uint8_t *prev,
-                 uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, cudaStream_t st);
+                 uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, uint32_t flag_target, cudaStream_t st);
+int launch_roles(const CoderParams &p, cudaStream_t st);      /* k2_blocks.cu: blocked containers, encode / decode */
 void set_carveout_all(int pct);                 /* -1: driver default per kernel; 0..100: one split for every kernel */
 int launch_copy16(void *dst, const void *src, uint64_t bytes, cudaStream_t st);
 uint64_t coder_payload_bound(uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy);

@@ -85,18 +85,130 @@ typedef struct cbcg_read_rec {
 /* ---- blocked container ("CBCB"), new design: the reference stream has no framing
  * (src/compression.c:128-155). Little endian. */
 #define CBCG_MAGIC          0x42434243u   /* "CBCB" */
-#define CBCG_VERSION        3u
+#define CBCG_VERSION        4u
+
+/* Substreams of a block (container v4). The reference interleaves every symbol of a read in ONE arithmetic-coded
+ * stream (src/read_compression.c:15-44), which makes a block one serial chain through every model. A block here holds
+ * four independent arithmetic-coded substreams, one per group of models, each closed by the short flush and stored
+ * back to back (A | B | C | D); the models, their contexts and the order of symbols WITHIN a substream are the
+ * reference's. The encoder codes the four side by side (all symbols are known); the decoder runs three phases,
+ * {A, B} -> C -> D, because match needs samePos (POS), the edits need the counts, and the base context needs the
+ * reference base under the decoded position. A substream in which no symbol was coded is zero bytes long. */
+#define CBCG_N_SUB          4u
+enum cbcg_substream {
+    CBCG_SUB_POS    = 0,   /* pos, pos_alpha                (compress_pos, compress_pos_alpha) */
+    CBCG_SUB_FLAG   = 1,   /* rlength byte 0, flag          (compress_read :29-33, compress_flag) */
+    CBCG_SUB_COUNTS = 2,   /* match, snps, indels           (compress_match, compress_snps, compress_indels) */
+    CBCG_SUB_EDITS  = 3    /* var, chars                    (compress_var, compress_chars) */
+};
+static inline uint32_t cbcg_substream_of(uint32_t stream) {
+    switch (stream) {
+        case 4: case 5:   return CBCG_SUB_POS;      /* CBCG_S_POS, CBCG_S_POS_ALPHA */
+        case 3: case 6:   return CBCG_SUB_FLAG;     /* CBCG_S_RLENGTH, CBCG_S_FLAG */
+        case 7: case 8: case 9: return CBCG_SUB_COUNTS;   /* CBCG_S_MATCH, CBCG_S_SNPS, CBCG_S_INDELS */
+        case 10: case 11: return CBCG_SUB_EDITS;    /* CBCG_S_VAR, CBCG_S_CHARS */
+        default:          return CBCG_SUB_POS;      /* same_ref / rname / codebook are not coded in blocked containers */
+    }
+}
 /* header word 9: low byte = gen_mode; bit 8 = every read is read_len_header bases long, so the length symbol
  * (src/read_compression.c:29-33, one zero-information coder step per read) is not coded either */
 #define CBCG_MODE_GEN_MASK  0xffu
 #define CBCG_MODE_FIXED_LEN 0x100u
 
-/* Generation-primed blocks (gen_mode 1): generation i has CBCG_GEN_COUNTS[i] blocks of
- * CBCG_GEN_READS[i] reads, each starting from the merged final states of the generation before; the
- * last generation takes all remaining reads in blocks of block_reads. */
-#define CBCG_GEN_LEVELS     4
-#define CBCG_GEN_COUNTS     { 16u, 112u, 384u, 1536u }
-#define CBCG_GEN_READS      { 16u, 32u, 64u, 128u }
+/* The FLAG model spends 65 536 / n of its probability on values never seen (src/sam_models.c:96-130: all-ones initial
+ * state), so what a FLAG symbol costs depends on where the model total n stands below the rescale threshold 2^20
+ * (0.09 bits per read at 2^20, 0.19 at 2^19). A merged snapshot therefore is not halved like update_model halves
+ * (which leaves n anywhere in [2^19, 2^20)): its FLAG counts are scaled to the largest total that lets a block of
+ * max_block_reads reads (the longest block of the container) code all its FLAG symbols without reaching the
+ * threshold: c' = max(1, c * (T - 65536) / n), T = cbcg_flag_target(max_block_reads). */
+static inline uint32_t cbcg_flag_target(uint32_t max_block_reads) {
+    const uint64_t head = 8ull * max_block_reads + 64u;
+    return head + (1u << 18) < CBCG_RESCALE ? (uint32_t)(CBCG_RESCALE - head) : (1u << 18);
+}
+
+/* Generation-primed blocks (gen_mode 1): the blocks of generation g start from the merged final states
+ * of generations < g; the last generation takes the remaining reads in blocks of block_reads. The cut is the
+ * encoder's choice and is written to the index (per-block read count and generation): a decoder never calls this.
+ *
+ * cbcg_gen_schedule: the default cut for a shard of n reads (constants measured with the CPU restatement on the named
+ * shapes, profiles/r02_notes.md). What blocking costs against the reference's single stream:
+ *   - 10.6 bytes per block (7.9 of index, 2.7 of closing bits for its four substreams);
+ *   - the `var` model (65 535 sparse contexts) keeps learning for millions of reads: a generation that codes the reads
+ *     (C, rC] from a snapshot frozen at C reads loses about kappa ((r - 1) - ln r) bytes against a model that keeps
+ *     adapting, kappa ~ 2 200 .. 3 400 (every other model is trained after a few thousand reads).
+ * Early generations quadruple the cumulative read count from 4 blocks of 64 reads up to 262 144 (cheap: their blocks are
+ * short); from there k late generations of equal ratio reach n, k chosen for the least serial depth (sum over the
+ * generations of their block size) within the <= 1 % budget; block sizes follow the square root of the generation's
+ * size (least depth for a given block count). Returns the number of early generations (<= CBCG_GEN_MAX) and the last
+ * generation's block size in *last_reads. */
+#define CBCG_GEN_MAX        16
+static inline uint32_t cbcg_isqrt(uint64_t x) {
+    uint64_t r = 0, bit = 1ull << 31;
+    for (; bit; bit >>= 1) { const uint64_t t = r | bit; if (t * t <= x) r = t; }
+    return (uint32_t)r;
+}
+static inline double cbcg_ln(double r) {                                    /* r >= 1; no libm: host, device and oracle agree */
+    double acc = 0.0;
+    while (r > 2.0) { r *= 0.5; acc += 0.6931471805599453; }
+    const double y = (r - 1.0) / (r + 1.0);
+    double t = y, s = 0.0;
+    for (int i = 1; i < 40; i += 2) { s += t / (double)i; t *= y * y; }
+    return acc + 2.0 * s;
+}
+static inline double cbcg_root(double x, uint32_t k) {                      /* x^(1/k), x >= 1, by bisection */
+    double lo = 1.0, hi = x;
+    for (int it = 0; it < 80; it++) {
+        const double mid = 0.5 * (lo + hi);
+        double p = 1.0;
+        for (uint32_t j = 0; j < k; j++) p *= mid;
+        if (p < x) lo = mid; else hi = mid;
+    }
+    return 0.5 * (lo + hi);
+}
+static inline uint32_t cbcg_gen_schedule(uint64_t n, uint32_t *count, uint32_t *reads, uint32_t *last_reads) {
+    uint64_t cum[CBCG_GEN_MAX + 1];
+    uint32_t ne = 0;
+    for (uint64_t c = 256; ne < 6 && c * 2 <= n; c *= 4) cum[ne++] = c;      /* 256 .. 262 144 */
+    if (!ne) { *last_reads = n > 64 ? (uint32_t)(n > 8192 ? 8192 : n) : 64u; return 0; }
+    const double S = 1.66 * (double)n, room = 0.0093 * S, per_block = 10.6, kappa = 3400.0, early_loss = 5000.0;
+    const double c0 = (double)cum[ne - 1];
+    uint32_t best_k = 1; double best_depth = 0.0, best_blocks = 16.0;
+    for (uint32_t k = 1; k <= 6 && ne + k - 1 <= CBCG_GEN_MAX; k++) {
+        const double r = cbcg_root((double)n / c0, k);
+        const double loss = early_loss + kappa * (double)k * ((r - 1.0) - cbcg_ln(r));
+        double blocks = (room - loss) / per_block;
+        if (blocks < 16.0) blocks = 16.0;
+        double sum_sqrt = 0.0, c = 0.0;
+        for (uint32_t g = 0; g < ne; g++) { sum_sqrt += (double)cbcg_isqrt(cum[g] - (uint64_t)c); c = (double)cum[g]; }
+        for (uint32_t j = 1; j <= k; j++) { const double nx = j == k ? (double)n : c * r; sum_sqrt += (double)cbcg_isqrt((uint64_t)(nx - c)); c = nx; }
+        const double depth = sum_sqrt * sum_sqrt / blocks;
+        if (k == 1 || depth < best_depth) { best_depth = depth; best_k = k; best_blocks = blocks; }
+        if (r < 2.0) break;
+    }
+    {                                                                            /* the late generations but the last */
+        const double r = cbcg_root((double)n / c0, best_k);
+        double c = c0;
+        for (uint32_t j = 1; j < best_k; j++) { c *= r; cum[ne++] = (uint64_t)c; }
+    }
+    uint64_t sum_sqrt = 0, prev = 0;
+    for (uint32_t g = 0; g < ne; g++) { sum_sqrt += cbcg_isqrt(cum[g] - prev); prev = cum[g]; }
+    sum_sqrt += cbcg_isqrt(n - prev);
+    const double cc = (double)sum_sqrt / best_blocks;                           /* block size = cc x sqrt(generation size) */
+    prev = 0;
+    for (uint32_t g = 0; g < ne; g++) {
+        const uint64_t size = cum[g] - prev; prev = cum[g];
+        uint64_t b = (uint64_t)(cc * (double)cbcg_isqrt(size));
+        if (g == 0) b = 64;
+        if (b < 32) b = 32;
+        if (b > 16384) b = 16384;
+        reads[g] = (uint32_t)b; count[g] = (uint32_t)((size + b - 1) / b);
+    }
+    uint64_t lb = (uint64_t)(cc * (double)cbcg_isqrt(n - prev));
+    if (lb < 64) lb = 64;
+    if (lb > 16384) lb = 16384;
+    *last_reads = (uint32_t)lb;
+    return ne;
+}
 #define CBCG_SNAP_POS_MAX   4096u         /* a snapshot keeps at most this many POS alphabet entries */
 
 #endif /* CBCG_FORMAT_H */

@@ -121,10 +121,14 @@ static void ac_flush(acoder *a) {
 /* Blocked containers (our format): the shortest tail that still decodes. After renormalisation
  * l < 2^25 <= u, so the value 2^25 ("1", the pending E3 bits as "0", then zeros) lies in [l, u]; the
  * decoder reads zeros past the end of a block, so only 1 + scale3 bits go out, padded to a byte. */
+uint64_t cbco_debug_flush_bits = 0;        /* experiments: bits the short tails added beyond the coded bits */
 static void ac_flush_short(acoder *a) {
+    const uint64_t before = a->w.out->size * 8u + a->w.nbits;
+    cbco_debug_flush_bits -= before;
     bw_bit(&a->w, 1);
     while (a->scale3 > 0) { bw_bit(&a->w, 0); a->scale3--; }
     if (a->w.nbits) bw_finish(&a->w);
+    cbco_debug_flush_bits += a->w.out->size * 8u;
 }
 /* arithmetic_get_symbol_range :373-381 */
 static uint32_t ac_target(const acoder *a, uint32_t n) {
@@ -354,12 +358,24 @@ static void finish_model(model *m, const model *prev, uint32_t prev_card) {
         for (uint32_t i = 0; i < m->card; i++) { m->c[i] = (m->c[i] >> 1) + 1; m->n += m->c[i]; }
     }
 }
-static void merge_finish(models *acc, const models *prev) {
+/* FLAG: clamp, then scale to the target total instead of halving (cbcg_flag_target, cbcg_format.h). */
+static void finish_flag(model *m, uint32_t target) {
+    uint64_t n = 0;
+    for (uint32_t i = 0; i < m->card; i++) { int32_t v = (int32_t)m->c[i]; if (v < 1) v = 1; m->c[i] = (uint32_t)v; n += (uint32_t)v; }
+    if (n > target) {
+        const uint64_t a = target - 65536u;
+        uint64_t s = 0;
+        for (uint32_t i = 0; i < m->card; i++) { uint64_t c = (uint64_t)m->c[i] * a / n; if (c < 1) c = 1; m->c[i] = (uint32_t)c; s += c; }
+        n = s;
+    }
+    m->n = (uint32_t)n;
+}
+static void merge_finish(models *acc, const models *prev, uint32_t flag_target) {
     for (int i = 0; i < 4; i++) { finish_model(&acc->rlength[i], &prev->rlength[i], 255); finish_model(&acc->pos_alpha[i], &prev->pos_alpha[i], 256);
                                   finish_model(&acc->match[i], &prev->match[i], 2); }
     for (int i = 0; i < 6; i++) finish_model(&acc->chars[i], &prev->chars[i], 5);
     finish_model(&acc->same_ref, &prev->same_ref, 2);
-    finish_model(&acc->flag, &prev->flag, 1u << 16);
+    finish_flag(&acc->flag, flag_target);
     finish_model(&acc->snps, &prev->snps, acc->L); finish_model(&acc->indels, &prev->indels, acc->L);
     for (uint32_t ctx = 0; ctx < CBCG_VAR_CONTEXTS; ctx++) if (acc->var[ctx].c) finish_model(&acc->var[ctx], NULL, 0);
     finish_model(&acc->pos.m, NULL, 0);
@@ -401,7 +417,9 @@ static model *model_of(models *M, uint32_t stream, uint32_t ctx) {
  * One object for the three uses of the read-level logic: trace only, encode, decode. */
 typedef struct {
     models M;
-    acoder ac;
+    acoder ac[CBCG_N_SUB];  /* legacy stream: ac[0] codes everything; blocked containers: one coder per substream */
+    int split;              /* 1: blocked container v4, symbols go to the substream of their model (cbcg_substream_of) */
+    uint32_t sub_syms[CBCG_N_SUB];
     int mode;               /* 0 trace only, 1 encode, 2 decode */
     cbco_buf *trace;        /* optional (key, symbol) log, tracer format */
     int err;
@@ -418,7 +436,9 @@ static void put_sym(coder *c, uint32_t stream, uint32_t ctx, uint32_t x) {
     if (c->mode == 1) {
         uint32_t lo = 0;
         for (uint32_t i = 0; i < x; i++) lo += m->c[i];
-        if (ac_encode(&c->ac, lo, lo + m->c[x], m->n)) { c->err = -3; return; }   /* assert :71 */
+        const uint32_t sub = c->split ? cbcg_substream_of(stream) : 0u;
+        c->sub_syms[sub]++;
+        if (ac_encode(&c->ac[sub], lo, lo + m->c[x], m->n)) { c->err = -3; return; }   /* assert :71 */
     }
     model_update(m, x);
 }
@@ -427,7 +447,8 @@ static uint32_t get_sym(coder *c, uint32_t stream, uint32_t ctx) {
     if (c->err) return 0;
     model *m = model_of(&c->M, stream, ctx);
     if (!m) { c->err = -2; return 0; }
-    uint32_t target = ac_target(&c->ac, m->n);
+    acoder *ac = &c->ac[c->split ? cbcg_substream_of(stream) : 0u];
+    uint32_t target = ac_target(ac, m->n);
     uint32_t x = 0, cum = 0;
     while (cum <= target) {
         if (x >= m->card) { c->err = -4; return 0; }           /* corrupt stream */
@@ -435,7 +456,7 @@ static uint32_t get_sym(coder *c, uint32_t stream, uint32_t ctx) {
     }
     x--;
     uint32_t lo = cum - m->c[x];
-    ac_decode(&c->ac, lo, cum, m->n);
+    ac_decode(ac, lo, cum, m->n);
     if (c->trace) { uint32_t rec[2] = { CBCG_SYM_KEY(stream, ctx), x }; buf_put(c->trace, rec, 8); }
     c->n_symbols++;
     model_update(m, x);
@@ -878,12 +899,12 @@ int cbco_encode_legacy(const cbco_batch *b, const cbco_genome *g, uint32_t L, cb
     if (!rc) {
         rstate s; rstate_init(&s, L, 1);
         s.c.trace = trace;
-        ac_init_enc(&s.c.ac, out);
+        ac_init_enc(&s.c.ac[0], out);
         put_header(&s, L);
         rc = code_range(&s, b, g, recs, edits, 0, b->n_reads, 1);
         if (!rc) {
             put_rname(&s, "\n");                                /* src/compression.c:152 */
-            ac_flush(&s.c.ac);
+            ac_flush(&s.c.ac[0]);
             rc = s.c.err;
         }
         rstate_free(&s);
@@ -898,7 +919,7 @@ int cbco_encode_legacy(const cbco_batch *b, const cbco_genome *g, uint32_t L, cb
 int cbco_decode_legacy(const uint8_t *stream, uint64_t stream_len, const cbco_genome *g,
                        cbco_buf *seq_out, uint64_t *n_reads_out) {
     rstate s; rstate_init(&s, 1, 2);
-    ac_init_dec(&s.c.ac, stream, stream_len);
+    ac_init_dec(&s.c.ac[0], stream, stream_len);
     uint32_t L = get_int(&s.c);
     for (int i = 0; i < 32; i++) (void)get_int(&s.c);
     uint32_t lossiness = get_int(&s.c);
@@ -967,7 +988,7 @@ int cbco_symbols(const cbco_batch *b, const cbco_genome *g, const cbcg_read_rec 
  * Each block: models at the reference's initial state (gen 0), fresh coder, prevPos = base_pos
  * (= POS of its first read), prevM = 0, empty SNP-site memory; per read the reference's symbol
  * order with same_ref = 0; closed by the reference's final flush. */
-typedef struct { uint32_t n_reads, chr, base_pos, n_symbols, n_edits, payload_bytes, gen, rsv; } blk_index;
+typedef struct { uint32_t n_reads, chr, base_pos, n_symbols, n_edits, payload_bytes, gen, rsv; uint32_t sub_bytes[CBCG_N_SUB]; } blk_index;
 
 /* Index entries are delta-coded LEB128 varints ("Container"). */
 static void put_varint(cbco_buf *b, uint64_t v) {
@@ -985,7 +1006,7 @@ static int get_varint(const uint8_t *p, uint64_t len, uint64_t *o, uint64_t *v) 
     }
     *v = r; return 0;
 }
-typedef struct { int64_t n_reads, chr, gen, base, d1, edits, payload; } idx_state;
+typedef struct { int64_t n_reads, chr, gen, base, d1, edits, sub[CBCG_N_SUB]; } idx_state;
 static void index_put(cbco_buf *b, idx_state *st, const blk_index *e) {
     int chr_ch = (int64_t)e->chr != st->chr, gen_ch = (int64_t)e->gen != st->gen;
     put_varint(b, (zigzag((int64_t)e->n_reads - st->n_reads) << 2) | (chr_ch ? 2u : 0u) | (gen_ch ? 1u : 0u));
@@ -994,9 +1015,9 @@ static void index_put(cbco_buf *b, idx_state *st, const blk_index *e) {
     int64_t d1 = (int64_t)e->base_pos - st->base;
     put_varint(b, zigzag(d1 - st->d1));
     put_varint(b, zigzag((int64_t)e->n_edits - st->edits));
-    put_varint(b, zigzag((int64_t)e->payload_bytes - st->payload));
+    for (uint32_t k = 0; k < CBCG_N_SUB; k++) { put_varint(b, zigzag((int64_t)e->sub_bytes[k] - st->sub[k])); st->sub[k] = e->sub_bytes[k]; }
     st->n_reads = e->n_reads; st->chr = e->chr; st->gen = e->gen; st->base = e->base_pos; st->d1 = d1;
-    st->edits = e->n_edits; st->payload = e->payload_bytes;
+    st->edits = e->n_edits;
 }
 static int index_get(const uint8_t *p, uint64_t len, uint64_t *o, idx_state *st, blk_index *e) {
     uint64_t v;
@@ -1008,13 +1029,19 @@ static int index_get(const uint8_t *p, uint64_t len, uint64_t *o, idx_state *st,
     st->d1 += unzigzag(v); st->base += st->d1;
     if (get_varint(p, len, o, &v)) return -1;
     st->edits += unzigzag(v);
-    if (get_varint(p, len, o, &v)) return -1;
-    st->payload += unzigzag(v);
+    int64_t total = 0;
+    for (uint32_t k = 0; k < CBCG_N_SUB; k++) {
+        if (get_varint(p, len, o, &v)) return -1;
+        st->sub[k] += unzigzag(v);
+        if (st->sub[k] < 0 || st->sub[k] > 0x3fffffffll) return -1;
+        total += st->sub[k];
+    }
     if (st->n_reads < 0 || st->n_reads > 0xffffffffll || st->chr < 0 || st->gen < 0 || st->gen > 255 || st->base < 0 || st->base > 0xffffffffll ||
-        st->edits < 0 || st->edits > 0xffffffffll || st->payload < 0 || st->payload > 0xffffffffll) return -1;
+        st->edits < 0 || st->edits > 0xffffffffll || total > 0xffffffffll) return -1;
     memset(e, 0, sizeof *e);
     e->n_reads = (uint32_t)st->n_reads; e->chr = (uint32_t)st->chr; e->gen = (uint32_t)st->gen; e->base_pos = (uint32_t)st->base;
-    e->n_edits = (uint32_t)st->edits; e->payload_bytes = (uint32_t)st->payload;
+    e->n_edits = (uint32_t)st->edits; e->payload_bytes = (uint32_t)total;
+    for (uint32_t k = 0; k < CBCG_N_SUB; k++) e->sub_bytes[k] = (uint32_t)st->sub[k];
     return 0;
 }
 
@@ -1053,7 +1080,7 @@ int cbco_encode_like(const uint8_t *p, uint64_t len, const cbco_batch *b, const 
     uint32_t ix_bytes; memcpy(&ix_bytes, p + o, 4); o += 4;
     if (o + ix_bytes > len) return -43;
     blk_index *idx = (blk_index *)calloc((size_t)nb + 1, sizeof(blk_index));
-    idx_state st = { h[8], 0, 0, 0, 0, 0, 0 };
+    idx_state st = { h[8], 0, 0, 0, 0, 0, { 0, 0, 0, 0 } };
     uint64_t io = o;
     for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k])) { free(idx); return -43; }
     int rc = encode_cut(b, g, h[3], h[8], (h[9] & CBCG_MODE_GEN_MASK) ? 1u : 0u, NULL, NULL, idx, nb, out);
@@ -1097,6 +1124,9 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
     }
     first[nb] = b->n_reads;
     const uint32_t last_gen = nb ? idx[nb - 1].gen : 0;
+    uint32_t max_block = 0;
+    for (uint64_t k = 0; k < nb; k++) if (idx[k].n_reads > max_block) max_block = idx[k].n_reads;
+    const uint32_t flag_target = cbcg_flag_target(max_block);
     uint32_t fixed_len = b->n_reads ? L : 0;                   /* every read exactly L bases: CBCG_MODE_FIXED_LEN */
     for (uint64_t r = 0; r < b->n_reads; r++) if (b->seq_len[r] != L) { fixed_len = 0; break; }
     cbco_buf payload = {0};
@@ -1106,18 +1136,26 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
     uint32_t cur_gen = 0;
     for (uint64_t k = 0; k < nb && !rc; k++) {
         if (idx[k].gen != cur_gen) {                           /* generation boundary: the merged state becomes the snapshot */
-            if (acc) { merge_finish(acc, prev); models_free(prev); free(prev); prev = acc; acc = NULL; }
+            if (acc) { merge_finish(acc, prev, flag_target); models_free(prev); free(prev); prev = acc; acc = NULL; }
             cur_gen = idx[k].gen;
         }
         if (!acc && idx[k].gen != last_gen) { acc = (models *)malloc(sizeof(models)); models_clone(acc, prev); }
         rstate s; rstate_init_from(&s, prev, 1);
         s.lean = 1; s.fixed_len = fixed_len;
         uint64_t start = payload.size;
-        ac_init_enc(&s.c.ac, &payload);
+        cbco_buf sub[CBCG_N_SUB]; memset(sub, 0, sizeof sub);
+        s.c.split = 1;
+        for (uint32_t q = 0; q < CBCG_N_SUB; q++) ac_init_enc(&s.c.ac[q], &sub[q]);
         s.prev_pos = idx[k].base_pos; s.have_name = 1; s.cur_chr = idx[k].chr;
         snp_reset(&s.snp, g->len[idx[k].chr] + 2048);
         rc = code_range(&s, b, g, recs, edits, first[k], first[k + 1], 0);
-        if (!rc) { ac_flush_short(&s.c.ac); rc = s.c.err; }
+        for (uint32_t q = 0; q < CBCG_N_SUB; q++) {             /* A | B | C | D, each with its own short tail; nothing coded: nothing stored */
+            if (!rc && s.c.sub_syms[q]) ac_flush_short(&s.c.ac[q]);
+            idx[k].sub_bytes[q] = (!rc && s.c.sub_syms[q]) ? (uint32_t)sub[q].size : 0u;
+            if (idx[k].sub_bytes[q]) buf_put(&payload, sub[q].data, sub[q].size);
+            cbco_buf_free(&sub[q]);
+        }
+        if (!rc) rc = s.c.err;
         idx[k].n_symbols = (uint32_t)s.c.n_symbols;
         uint64_t e_lo = recs[first[k]].edit_off;
         uint64_t e_hi = (first[k + 1] < b->n_reads) ? recs[first[k + 1]].edit_off : (uint64_t)ne;
@@ -1139,7 +1177,7 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
             buf_put_u32(out, nl); buf_put(out, g->name[c], nl); buf_put(out, &z, pad);
         }
         cbco_buf ix = {0};
-        idx_state st = { block_reads, 0, 0, 0, 0, 0, 0 };
+        idx_state st = { block_reads, 0, 0, 0, 0, 0, { 0, 0, 0, 0 } };
         for (uint64_t k = 0; k < nb; k++) index_put(&ix, &st, &idx[k]);
         buf_put_u32(out, (uint32_t)ix.size);
         buf_put(out, ix.data, ix.size);
@@ -1153,9 +1191,11 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
 
 int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads,
                         uint32_t gen_mode, cbco_buf *out) {
-    static const uint32_t count[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, reads[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
+    uint32_t count[CBCG_GEN_MAX], reads[CBCG_GEN_MAX], last = 0, levels = 0;
     if (gen_mode > 1) return -30;
-    return cbco_encode_scheduled(b, g, L, block_reads, gen_mode ? CBCG_GEN_LEVELS : 0u, count, reads, out);
+    if (gen_mode) levels = cbcg_gen_schedule(b->n_reads, count, reads, &last);
+    if (block_reads == 0xffffffffu) block_reads = gen_mode ? last : 1024u;      /* CBCG_BLOCK_AUTO */
+    return cbco_encode_scheduled(b, g, L, block_reads, levels, count, reads, out);
 }
 
 int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cbco_buf *seq_out, uint64_t *n_reads_out) {
@@ -1185,15 +1225,16 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
     if (o + ix_bytes > len || nb > ix_bytes) { free(chr_map); return -43; }
     blk_index *idx = (blk_index *)calloc((size_t)nb + 1, sizeof(blk_index));
     {
-        idx_state st = { h[8], 0, 0, 0, 0, 0, 0 };
+        idx_state st = { h[8], 0, 0, 0, 0, 0, { 0, 0, 0, 0 } };
         uint64_t io = o;
         for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k])) { free(chr_map); free(idx); return -43; }
     }
     o += ix_bytes;
     int rc = 0; uint64_t n = 0;
     uint16_t e[3 * 256 + 8]; uint8_t line[1025];
-    uint32_t last_gen = 0;
-    for (uint32_t k = 0; k < nb; k++) last_gen = idx[k].gen;                  /* the index codes generations in ascending order */
+    uint32_t last_gen = 0, max_block = 0;
+    for (uint32_t k = 0; k < nb; k++) { last_gen = idx[k].gen; if (idx[k].n_reads > max_block) max_block = idx[k].n_reads; }   /* the index codes generations in ascending order */
+    const uint32_t flag_target = cbcg_flag_target(max_block);
     models *prev = (models *)malloc(sizeof(models)), *acc = NULL;
     models_init(prev, L);
     uint32_t cur_gen = 0;
@@ -1201,14 +1242,15 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
         blk_index bi; memcpy(&bi, &idx[k], sizeof bi);
         if (bi.chr >= n_chr || o + bi.payload_bytes > len) { rc = -45; break; }
         if (bi.gen != cur_gen) {
-            if (acc) { merge_finish(acc, prev); models_free(prev); free(prev); prev = acc; acc = NULL; }
+            if (acc) { merge_finish(acc, prev, flag_target); models_free(prev); free(prev); prev = acc; acc = NULL; }
             cur_gen = bi.gen;
         }
         if (!acc && bi.gen != last_gen) { acc = (models *)malloc(sizeof(models)); models_clone(acc, prev); }
         uint32_t chr = chr_map[bi.chr];
         rstate s; rstate_init_from(&s, prev, 2);
         s.lean = 1; s.fixed_len = fixed_len;
-        ac_init_dec(&s.c.ac, p + o, bi.payload_bytes);
+        s.c.split = 1;
+        { uint64_t so = o; for (uint32_t q = 0; q < CBCG_N_SUB; q++) { ac_init_dec(&s.c.ac[q], p + so, bi.sub_bytes[q]); so += bi.sub_bytes[q]; } }
         s.prev_pos = bi.base_pos;
         snp_reset(&s.snp, g->len[chr] + 2048);
         for (uint32_t r = 0; r < bi.n_reads && !rc; r++) {
