@@ -75,6 +75,7 @@ struct cbcg_ctx {
     DevBuf recs, edits, chr_out, tile_desc, words, blocks, ws, scratch, payload, out_off, symbols, seq_out;
     DevBuf snap_a, snap_b, fin;                /* generation snapshots and per-block final states (gen_mode 1) */
     std::vector<std::pair<uint32_t, uint32_t>> gens;   /* (first block, block count) per generation of the last cut */
+    uint32_t max_block_reads = 0;              /* longest block of the last cut / index: sets the merged snapshots' FLAG total (cbcg_flag_target) */
     Words *hw = nullptr;                       /* pinned */
     BlockDesc *hblocks = nullptr; size_t hblocks_cap = 0;   /* pinned */
 
@@ -448,7 +449,9 @@ extern "C" int cbcg_extract(cbcg_ctx *ctx, const cbcg_batch *batch, cbcg_read_re
 /* ------------------------------------------------------------------------------------------------ blocks */
 static void gens_from_blocks(cbcg_ctx *ctx, uint64_t nb) {
     ctx->gens.clear();
+    ctx->max_block_reads = 0;
     for (uint64_t k = 0; k < nb; k++) {
+        ctx->max_block_reads = std::max(ctx->max_block_reads, ctx->hblocks[k].n_reads);
         if (ctx->gens.empty() || ctx->hblocks[k].gen != ctx->hblocks[ctx->gens.back().first].gen) ctx->gens.push_back({ (uint32_t)k, 0u });
         ctx->gens.back().second++;
     }
@@ -459,9 +462,9 @@ static void gens_from_blocks(cbcg_ctx *ctx, uint64_t nb) {
 struct SizeStep { uint64_t r_limit; uint32_t block_reads; };    /* last-generation blocks that start below r_limit get this size */
 static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, uint64_t *n_blocks_out,
                       const std::vector<SizeStep> *ramp = nullptr, bool upload = true) {
-    static const uint32_t sched_count[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sched_reads[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
-    const uint32_t n_sched = gen_mode ? CBCG_GEN_LEVELS : 0u;
     const uint64_t n = ctx->db.n_reads;
+    uint32_t sched_count[CBCG_GEN_MAX], sched_reads[CBCG_GEN_MAX], sched_last = 0;
+    const uint32_t n_sched = gen_mode ? cbcg_gen_schedule(n, sched_count, sched_reads, &sched_last) : 0u;
     uint64_t bound = 1;
     uint32_t min_reads = block_reads;
     if (ramp) for (const SizeStep &st : *ramp) min_reads = std::min(min_reads, std::max(st.block_reads, 1u));
@@ -506,35 +509,40 @@ static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, ui
 /* CBCG_BLOCK_AUTO: reads per last-generation block such that the generation fills the GPU's resident block slots a
  * whole number of times. */
 static uint32_t auto_block_reads(cbcg_ctx *ctx, uint64_t n, uint32_t gen_mode, uint64_t *slots_out = nullptr) {
-    static const uint32_t sc[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sr[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
-    uint64_t early = 0;
-    if (gen_mode) for (uint32_t g = 0; g < CBCG_GEN_LEVELS; g++) early += (uint64_t)sc[g] * sr[g];
-    const uint64_t main_reads = n > early ? n - early : n;
-    const uint64_t slots = coder_resident_blocks(ctx->device);
-    const uint64_t waves = std::max<uint64_t>(1, (main_reads + slots * CBCG_BLOCK_AUTO_MAX - 1) / (slots * CBCG_BLOCK_AUTO_MAX));
-    uint64_t r = (main_reads + waves * slots - 1) / (waves * slots);
-    if (slots_out) *slots_out = slots;
-    return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(r, 64), CBCG_BLOCK_AUTO_MAX);
+    (void)ctx;
+    if (slots_out) *slots_out = 0;
+    if (!gen_mode) return 1024u;
+    uint32_t c[CBCG_GEN_MAX], r[CBCG_GEN_MAX], last = 0;
+    cbcg_gen_schedule(n, c, r, &last);                      /* what the <= 1 % budget leaves for the last generation */
+    return last;
 }
+/* reads the early generations of the default cut hold (everything but the last generation) */
+static uint64_t sched_early_reads(uint64_t n, uint32_t *levels_out = nullptr) {
+    uint32_t c[CBCG_GEN_MAX], r[CBCG_GEN_MAX], last = 0;
+    const uint32_t k = cbcg_gen_schedule(n, c, r, &last);
+    uint64_t early = 0;
+    for (uint32_t g = 0; g < k; g++) early += (uint64_t)c[g] * r[g];
+    if (levels_out) *levels_out = k;
+    return early;
+}
+static int ensure_fin(cbcg_ctx *ctx, uint64_t nb) { return ensure(ctx, ctx->fin, (nb + 1) * fin_stride_bytes()); }
 
 /* Generations 0 .. last-1 of ctx->gens with the merges that build the snapshots; *snap_out = the snapshot the last
  * generation starts from. */
 static int run_early_generations(cbcg_ctx *ctx, CoderParams p, uint8_t **snap_out, cudaStream_t st = nullptr) {
     if (!st) st = ctx->st;
     const uint64_t sb = snapshot_bytes(p.L);
-    uint32_t max_merged = 1;
-    for (size_t g = 0; g + 1 < ctx->gens.size(); g++) max_merged = std::max(max_merged, ctx->gens[g].second);
     TRY(ensure(ctx, ctx->snap_a, sb)); TRY(ensure(ctx, ctx->snap_b, sb));
-    TRY(ensure(ctx, ctx->fin, (uint64_t)max_merged * fin_stride_bytes()));
     uint8_t *cur = ctx->snap_a.as<uint8_t>(), *other = ctx->snap_b.as<uint8_t>();
+    const uint32_t flag_target = cbcg_flag_target(ctx->max_block_reads);
     if (launch_snapshot_init(cur, p.L, st)) return fail(ctx, CBCG_ERR_CUDA, "snapshot init launch failed");
     ctx->stats.kernel_launches++;
     for (size_t g = 0; g + 1 < ctx->gens.size(); g++) {
         p.block_begin = ctx->gens[g].first; p.n_blocks = ctx->gens[g].second;
-        p.snap = cur; p.fin = ctx->fin.as<uint8_t>();
+        p.snap = cur;
         if (launch_coder(p, st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        ctx->stats.kernel_launches++;
-        if (launch_merge(p.blocks, p.block_begin, p.n_blocks, p.L, cur, other, ctx->fin.as<uint8_t>(), p.ws, p.err, st))
+        ctx->stats.kernel_launches += roles_launches(p.mode);
+        if (launch_merge(p.blocks, p.block_begin, p.n_blocks, p.L, cur, other, p.fin + (uint64_t)p.block_begin * fin_stride_bytes(), p.ws, p.err, flag_target, st))
             return fail(ctx, CBCG_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->stats.kernel_launches += 4;
         std::swap(cur, other);
@@ -546,19 +554,22 @@ static int run_early_generations(cbcg_ctx *ctx, CoderParams p, uint8_t **snap_ou
 /* Runs the block coder (encode or decode) over all blocks of ctx->hblocks, generation by generation when primed:
  * blocks of generation g start from snapshot S_{g-1}; after each generation but the last the merge kernels build S_g. */
 static int run_coder_generations(cbcg_ctx *ctx, CoderParams p, uint64_t nb, bool primed) {
-    if (!primed) {
+    if (p.legacy || p.mode == 2u) {                          /* single-block stream / symbol lists: the warp kernel, no snapshot */
         p.block_begin = 0; p.n_blocks = (uint32_t)nb;
         if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->stats.kernel_launches++;
         return 0;
     }
+    /* blocked containers: every block starts from a snapshot. gen_mode 0: all of them from S_{-1}, the reference's initial
+       state (one generation, run_early_generations only writes that snapshot). */
+    (void)primed;
     if (ctx->gens.empty()) return 0;
     uint8_t *cur = nullptr;
     TRY(run_early_generations(ctx, p, &cur));
     p.block_begin = ctx->gens.back().first; p.n_blocks = ctx->gens.back().second;
-    p.snap = cur; p.fin = nullptr;
+    p.snap = cur;
     if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    ctx->stats.kernel_launches++;
+    ctx->stats.kernel_launches += roles_launches(p.mode);
     return 0;
 }
 
@@ -573,6 +584,7 @@ static CoderParams coder_params(cbcg_ctx *ctx, uint32_t n_blocks, uint32_t L, in
     p.ws = ctx->ws.as<uint8_t>();
     p.chr_names = ctx->g_names.as<uint8_t>();
     p.err = wptr<unsigned long long>(ctx, W_OFF(err));
+    p.fin = ctx->fin.as<uint8_t>();                         /* callers ensure_fin(nb) before a blocked launch */
     return p;
 }
 
@@ -612,22 +624,22 @@ static void finish_encode(cbcg_ctx *ctx, const cbcg_encode_opts *opts, int legac
 #define PIPE_FALLBACK 1            /* not an error: the caller takes the one-stream path */
 static int pipe_init(cbcg_ctx *ctx);
 static int encode_resident_overlapped(cbcg_ctx *ctx, const cbcg_encode_opts *opts) {
-    static const uint32_t sc[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sr[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
     const uint64_t n = ctx->db.n_reads;
     const uint32_t L = opts->read_len_header;
     const uint64_t tile = 128;                              /* K1 tile */
-    uint64_t early = 0;
-    for (uint32_t g = 0; g < CBCG_GEN_LEVELS; g++) early += (uint64_t)sc[g] * sr[g];
+    uint32_t levels = 0;
+    const uint64_t early = sched_early_reads(n, &levels);
     const uint64_t head_end = ((early + tile - 1) / tile + 1) * tile;   /* + one tile: the record after the last early block exists */
     if (n < 4 * head_end) return PIPE_FALLBACK;
     TRY(pipe_init(ctx));
     cbcg_stats &S = ctx->stats;
     uint64_t nb = 0;
     TRY(cut_blocks(ctx, opts->block_reads, 1, &nb));
-    if (ctx->gens.size() != CBCG_GEN_LEVELS + 1) return PIPE_FALLBACK;   /* chromosome runs too short for the schedule */
+    if (!levels || ctx->gens.size() != levels + 1u) return PIPE_FALLBACK;   /* chromosome runs too short for the schedule */
     const uint32_t last_first = ctx->gens.back().first, last_n = ctx->gens.back().second;
     if ((uint64_t)ctx->hblocks[last_first].first_read + tile > head_end) return PIPE_FALLBACK;
     const bool fixed = ctx->batch_min_len == L && ctx->db.max_len == L;
+    TRY(ensure_fin(ctx, nb));
 
     const uint64_t edits_cap_guess = ctx->total_bases / 16 + 4096;
     TRY(ensure(ctx, ctx->recs, (n + 1) * sizeof(cbcg_read_rec)));
@@ -682,10 +694,10 @@ static int encode_resident_overlapped(cbcg_ctx *ctx, const cbcg_encode_opts *opt
     CU(cudaEventRecord(ctx->dev2[1], side));
     CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[1], 0));
     CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[2], 0));
-    q.snap = snap; q.fin = nullptr;
+    q.snap = snap;
     if (launch_coder(q, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaEventRecord(ctx->ev[3], ctx->st));
-    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->st))
+    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), 1, ctx->st))
         return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
     S.kernel_launches += 7;                                 /* K1 x 2, plan x 2, last generation, gather x 2 */
     CU(cudaEventRecord(ctx->ev[4], ctx->st));
@@ -752,9 +764,10 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
             CU(cudaMemsetAsync(ctx->recs.p, 0, sizeof(cbcg_read_rec), ctx->st));
             TRY(reset_words(ctx));
         }
-        const bool primed = !legacy && opts->gen_mode == 1;
+        const bool primed = !legacy;                        /* blocked containers: every block starts from a snapshot (gen_mode 0: the initial one) */
         fixed = !legacy && ctx->batch_min_len == L && ctx->db.max_len == L;   /* CBCG_MODE_FIXED_LEN */
         TRY(cut_blocks(ctx, opts->block_reads, opts->gen_mode, &nb));
+        if (!legacy) TRY(ensure_fin(ctx, nb));
         const uint64_t ws_cap = coder_ws_bytes_bound(L, n, n_edits, nb, legacy, primed);
         const uint64_t pay_cap = coder_payload_bound(n, n_edits, nb, legacy);
         TRY(ensure(ctx, ctx->ws, ws_cap));
@@ -771,7 +784,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
         CU(cudaEventRecord(ctx->ev[3], ctx->st));
         /* compact payload: bounded by the scratch size */
         TRY(ensure(ctx, ctx->payload, pay_cap));
-        if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->st))
+        if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), legacy ? 0 : 1, ctx->st))
             return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
         S.kernel_launches += 3;
         CU(cudaEventRecord(ctx->ev[4], ctx->st));
@@ -902,12 +915,11 @@ static void pipe_drain(cbcg_ctx *ctx) {
     (void)cudaGetLastError();
 }
 static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encode_opts *opts) {
-    static const uint32_t sc[CBCG_GEN_LEVELS] = CBCG_GEN_COUNTS, sr[CBCG_GEN_LEVELS] = CBCG_GEN_READS;
     const uint64_t n = b->n_reads;
     const uint32_t L = opts->read_len_header;
     const uint64_t tile = 128;                              /* K1 tile: chunk boundaries are whole tiles */
-    uint64_t early = 0;
-    for (uint32_t g = 0; g < CBCG_GEN_LEVELS; g++) early += (uint64_t)sc[g] * sr[g];
+    uint32_t levels = 0;
+    const uint64_t early = sched_early_reads(n, &levels);
     if (n < early + tile * (PIPE_CHUNKS + 1)) return PIPE_FALLBACK;
     if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");   /* before any copy is queued */
     TRY(pipe_init(ctx));
@@ -956,11 +968,12 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     /* inv > 1: more blocks than resident slots, the last ones would queue */
     for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) {
         const double m = mult[c - 1] * (inv > 1.0 ? inv : 1.0);
-        ramp.push_back({ cut[c + 1], (uint32_t)std::max(64.0, std::min(2.0 * CBCG_BLOCK_AUTO_MAX, m * used.block_reads)) });
+        ramp.push_back({ cut[c + 1], (uint32_t)std::max(64.0, std::min(16384.0, m * used.block_reads)) });
     }
     uint64_t nb = 0;
     TRY(cut_blocks(ctx, used.block_reads, 1, &nb, &ramp, false));
-    if (ctx->gens.size() != CBCG_GEN_LEVELS + 1) return PIPE_FALLBACK;   /* chromosome runs too short for the schedule */
+    if (!levels || ctx->gens.size() != levels + 1u) return PIPE_FALLBACK;   /* chromosome runs too short for the schedule */
+    TRY(ensure_fin(ctx, nb));
     const BlockDesc *hb = ctx->hblocks;
     const uint32_t last_first = ctx->gens.back().first, last_n = ctx->gens.back().second;
     if ((uint64_t)hb[last_first].first_read + tile > head_end) return PIPE_FALLBACK;
@@ -1038,14 +1051,14 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
             CU(cudaEventRecord(ctx->kev2[c], ctx->st));
             cudaStream_t sd = ctx->ps[c % PIPE_MAX];
             CU(cudaStreamWaitEvent(sd, ctx->kev2[c], 0));
-            q.snap = snap; q.fin = nullptr;
+            q.snap = snap;
             if (launch_coder(q, sd)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            S.kernel_launches++;
+            S.kernel_launches += roles_launches(q.mode);
             CU(cudaEventRecord(ctx->dev2[c], sd));
         }
     }
     for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) if (gb[c] > gb[c - 1]) CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[c], 0));
-    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->st))
+    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), 1, ctx->st))
         return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
     S.kernel_launches += 2;
     CU(cudaEventRecord(ctx->ev[4], ctx->st));
@@ -1221,9 +1234,11 @@ static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy,
     TRY(ensure(ctx, ctx->recs, (reads_cap + 1) * sizeof(cbcg_read_rec)));
     TRY(ensure(ctx, ctx->chr_out, (reads_cap + 1) * 4));
     TRY(ensure(ctx, ctx->edits, (edits_cap + 64) * 2));
+    if (!legacy) primed = true;                             /* blocked containers: every block starts from a snapshot */
     const uint64_t ws_cap = legacy ? coder_ws_bytes_bound(L ? L : CBCG_MAX_READ_LEN, reads_cap, 0xffffffffull, 1, 1, 0)
-                                   : coder_ws_bytes_bound(L, reads_cap, edits_cap, nb, 0, primed);
+                                   : coder_ws_bytes_bound(L, reads_cap, edits_cap, nb, 0, 1);
     TRY(ensure(ctx, ctx->ws, ws_cap));
+    if (!legacy) TRY(ensure_fin(ctx, nb));
     TRY(reset_words(ctx));
     TRY(poison_decode_outputs(ctx, reads_cap, edits_cap));
     CoderParams p = coder_params(ctx, (uint32_t)nb, L, legacy, 1);
@@ -1407,6 +1422,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
     TRY(ensure(ctx, ctx->edits, (ne + 64) * 2));
     const uint64_t ws_cap = coder_ws_bytes_bound(c.L, nr, ne, nb, 0, 1);
     TRY(ensure(ctx, ctx->ws, ws_cap));
+    TRY(ensure_fin(ctx, nb));
     TRY(ensure(ctx, ctx->seq_out, bytes + 64));
     TRY(ensure(ctx, ctx->tile_desc, (reconstruct_num_tiles(nr) + 1) * 8));
 
@@ -1432,9 +1448,9 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
         if (g) CU(cudaStreamWaitEvent(sd, ctx->kev2[0], 0));
         if (g && gb[g] > gb[g - 1]) {
             CoderParams q = p;
-            q.block_begin = gb[g - 1]; q.n_blocks = gb[g] - gb[g - 1]; q.snap = snap; q.fin = nullptr;
+            q.block_begin = gb[g - 1]; q.n_blocks = gb[g] - gb[g - 1]; q.snap = snap;
             if (launch_coder(q, sd)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            S.kernel_launches++;
+            S.kernel_launches += roles_launches(q.mode);
         }
         CU(cudaEventRecord(ctx->tev[2 * g], sd));
         if (r1 > r0) {

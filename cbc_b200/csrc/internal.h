@@ -96,8 +96,9 @@ int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_t
                 const uint64_t *carry_in = nullptr, const uint64_t *n_edits_dev = nullptr);
 int launch_coder(const CoderParams &p, cudaStream_t st);
 uint32_t coder_resident_blocks(int device);     /* blocks (warps) of the encode kernel the whole GPU holds at once */
-int launch_gather(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
-                  uint64_t *out_off, cudaStream_t st);
+int launch_gather(BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
+                  uint64_t *out_off, int subs, cudaStream_t st);   /* subs: blocked container, four substreams per block */
+uint32_t roles_launches(uint32_t mode);         /* kernel launches one launch_coder call makes for a blocked container */
 uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy, int primed);
 /* generation snapshots (gen_mode 1) */
 uint64_t snapshot_bytes(uint32_t L);

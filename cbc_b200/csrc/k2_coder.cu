@@ -50,7 +50,7 @@ uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, ui
     return 2u * b + 4096u;                                   /* direct blocks use <= 2 x their hashed size */
 }
 uint64_t coder_payload_bound(uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy) {
-    return payload_cap_bytes(n_reads, n_edits, legacy) + n_blocks * 96u;
+    return payload_cap_bytes(n_reads, n_edits, legacy) + n_blocks * 512u;   /* per block: four substream regions, each with its own slack and alignment */
 }
 uint64_t snapshot_bytes(uint32_t L) { return snap_layout(L).total; }
 uint64_t fin_stride_bytes(void) { return (sizeof(WarpModels) + 15u) & ~15ull; }
@@ -159,7 +159,8 @@ struct Coder {
     /* var */
     uint64_t *var_hash; uint32_t hash_mask; uint32_t n_rows; bool var_direct;
     /* the rest of the block's workspace, addressed from var_hash (ws_layout: pos_cnt | pos_val | pos_alpha | var_hash | var_rows) */
-    __device__ __forceinline__ WarpCold &cold() const { return reinterpret_cast<WarpShared *>(M)->c; }
+    WarpCold *coldp;
+    __device__ __forceinline__ WarpCold &cold() const { return *coldp; }
     __device__ __forceinline__ uint32_t pos_stride() const { return (uint32_t)((((uint64_t)cold().pos_cap * 4u + 15u) & ~15ull) >> 2); }
     __device__ __forceinline__ uint32_t *pos_alpha() const { return reinterpret_cast<uint32_t *>(var_hash) - (4u * PA_STRIDE + 4u); }
     __device__ __forceinline__ uint32_t *pos_gval() const { return pos_alpha() - pos_stride(); }
@@ -771,7 +772,7 @@ k2_coder_kernel(CoderParams P) {
     unsigned long long k2_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k2_t0));
 #endif
     Coder<MODE> C;
-    C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &sshared[warp].m;
+    C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &sshared[warp].m; C.coldp = &sshared[warp].c;
     C.primed = primed; C.lean = lean;
     C.var_defer = primed && P.fin == nullptr; C.var_ro = false; C.defer_idx = 0; C.defer_key = 0;
     if (primed) C.snap = SnapView(P.snap, P.L);
@@ -1195,18 +1196,357 @@ M_DONE:
 }
 
 
+/* ================================================================================================
+ * Blocked containers (format v4): ONE CTA PER BLOCK, ONE WARP PER SUBSTREAM.
+ *
+ * The four substreams of a block (cbcg_format.h: POS | length + FLAG | match + counts | var + bases) are independent
+ * arithmetic-coded streams over disjoint groups of models, so the block is four short chains instead of one long
+ * one, and each warp runs a small loop over ONE kind of symbol -- no state machine, no dispatch, an instruction
+ * footprint of a few hundred instructions per role (round 1's single chain through every model was 5 900
+ * instructions walked by 20 warps per SM, a third of its stall samples waiting for instruction fetch).
+ * Encode: the four warps never talk. Decode: the match context needs samePos, the edit loops need the counts and the
+ * strand, so the roles run as a software pipeline through a ring in shared memory: POS and FLAG run ahead, the counts
+ * follow one read behind them, the edits one read behind the counts; a block takes the time of its longest substream
+ * instead of their sum. Lanes cooperate inside a symbol exactly as in round 1 (Coder<>: strided cumulative counts,
+ * 32-wide hash probe, POS slots in registers). The block's small models live once in shared memory, each field
+ * owned by one role. The scalar twin of these loops (k2_roles.cuh) is what the CPU harness checks against the oracle
+ * and what CBCG_SCALAR_ROLES=1 runs on the GPU as a cross-check. */
+#define K2B_WARPS 4u
+#ifndef K2B_MIN_CTAS
+#define K2B_MIN_CTAS 5
+#endif
+#define K2B_RING 256u
+struct K2BEntry { uint32_t pos, flaglen, counts; };
+struct K2BShared {
+    WarpModels m;
+    WarpCold c[K2B_WARPS];
+    K2BEntry ring[K2B_RING];                   /* decode: what the roles hand each other, by read ordinal mod K2B_RING */
+    volatile uint32_t progress[K2B_WARPS];      /* decode: reads finished by each role */
+    volatile int failed;
+    unsigned long long err_seen;
+};
+/* wait until role `r` has finished read i (returns false when the block has failed) */
+__device__ __forceinline__ bool k2b_wait(K2BShared &S, uint32_t r, uint32_t i, uint32_t &seen) {
+    if (i < seen) return true;
+    for (;;) {
+        const uint32_t v = S.progress[r];
+        if (v > i) { seen = v; return true; }
+        if (S.failed) return false;
+        __nanosleep(40);
+    }
+}
+/* a producer may run at most K2B_RING reads ahead of the edits role (the last consumer) */
+__device__ __forceinline__ bool k2b_room(K2BShared &S, uint32_t i, uint32_t &seen_d) {
+    if (i < seen_d + K2B_RING) return true;
+    for (;;) {
+        const uint32_t v = S.progress[CBCG_SUB_EDITS];
+        if (i < v + K2B_RING) { seen_d = v; return true; }
+        if (S.failed) return false;
+        __nanosleep(100);
+    }
+}
+__device__ __forceinline__ void k2b_publish(K2BShared &S, uint32_t r, uint32_t done, uint32_t lane) {
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); S.progress[r] = done; }
+}
+__device__ __forceinline__ void k2b_copy(uint32_t *dst, const uint32_t *src, uint32_t n, uint32_t lane) { for (uint32_t i = lane; i < n; i += 32u) dst[i] = src[i]; }
+
+template <int MODE>
+__global__ void __launch_bounds__(K2B_WARPS * 32u, K2B_MIN_CTAS)
+k2_block_kernel(CoderParams P) {
+    __shared__ __align__(16) K2BShared S;
+    const uint32_t role = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (threadIdx.x == 0) { S.err_seen = *reinterpret_cast<volatile unsigned long long *>(P.err); S.failed = 0; }
+    if (threadIdx.x < K2B_WARPS) S.progress[threadIdx.x] = 0u;
+    __syncthreads();
+    if (S.err_seen) return;                              /* an earlier stage failed: offsets may be out of range */
+    const uint32_t b = P.block_begin + blockIdx.x;
+    BlockDesc &B = P.blocks[b];
+    const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+    uint8_t *wsb = P.ws + B.ws_off;
+    const uint32_t L = P.L, n_reads = B.n_reads;
+    const bool fixed = P.fixed_len != 0;
+    const uint64_t r0 = B.first_read;
+
+    Coder<MODE> C;
+    C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &S.m; C.coldp = &S.c[role];
+    C.primed = true; C.lean = true; C.var_defer = true; C.var_ro = false; C.defer_idx = 0; C.defer_key = 0;
+    C.snap = SnapView(P.snap, L);
+    C.L = L; C.Lp = w.Lp;
+    C.var_hash = reinterpret_cast<uint64_t *>(wsb + w.var_hash); C.hash_mask = w.hash_cap - 1u; C.var_direct = false;
+    C.codebook = nullptr; C.rname = nullptr; C.list = nullptr; C.list_n = 0; C.list_cap = 0;
+    C.n_rows = 0; C.pa_init = false; C.pos_card = 1u; C.pos_n = 1u; C.pos_rv = 0u; C.pos_rc = 0u;
+    C.last_lo = 0; C.last_n = 0;
+    if (lane == 0) {
+        WarpCold &W = S.c[role];
+        W.pos_cap = w.pos_cap; W.rows_cap = w.rows_cap; W.pad = 0;
+        if (MODE == MODE_ENC) {
+            uint64_t o = B.payload_off;
+            for (uint32_t q = 0; q < role; q++) o += k2_sub_cap(q, n_reads, B.n_edits);
+            W.io = P.payload + o; W.io_cap = (uint32_t)k2_sub_cap(role, n_reads, B.n_edits);
+        } else {
+            uint64_t o = B.payload_off;
+            for (uint32_t q = 0; q < role; q++) o += B.sub_bytes[q];
+            W.io = P.payload + o; W.io_cap = B.sub_bytes[role];
+        }
+        W.ref = nullptr; W.ref_len = 0;
+        if (B.chr < P.genome.n_chr) { W.ref = P.genome.bases + P.genome.chr_off[B.chr]; W.ref_len = P.genome.chr_len[B.chr]; }
+        W.edits_cap_abs = B.edit_base + B.n_edits;
+    }
+    __syncwarp();
+    const WarpModels *SM = reinterpret_cast<const WarpModels *>(C.snap.small());
+    WarpModels *FM = reinterpret_cast<WarpModels *>(P.fin + (uint64_t)b * fin_stride_dev());
+    C.ring_reset();
+    uint32_t i = 0, seen_a = 0, seen_b = 0, seen_c = 0, seen_d = 0;
+    bool bailed = false;                                 /* another role failed: leave without an error of our own */
+#define K2B_FAIL(code) do { C.err = (code); goto role_done; } while (0)
+
+    if (role == CBCG_SUB_POS) {
+        /* ---- A: POS through the growing alphabet (compress_pos :113-159, compress_pos_alpha :75-108) */
+        C.pos_card = C.snap.pos_hdr()[0]; C.pos_n = C.snap.pos_hdr()[1];
+        if (C.pos_card > w.pos_cap) K2B_FAIL(CBCG_ERR_INTERNAL);
+        C.pos_rv = (lane < C.pos_card) ? C.snap.pos_val()[lane] : 0u;
+        C.pos_rc = (lane < C.pos_card) ? C.snap.pos_cnt()[lane] : 0u;
+        for (uint32_t q = 32u + lane; q < C.pos_card; q += 32u) { C.pos_gval()[q] = C.snap.pos_val()[q]; C.pos_gcnt()[q] = C.snap.pos_cnt()[q]; }
+        __syncwarp();
+        C.ac_init();
+        uint32_t prev_pos = B.base_pos;
+        for (; i < n_reads; i++) {
+            uint32_t x = 0, pos = 0, slot = 1u;
+            if (MODE == MODE_ENC) {
+                pos = P.recs[r0 + i].pos;
+                if (pos == 0u || pos < prev_pos || pos - prev_pos + 1u > CBCG_MAX_POS_X) K2B_FAIL(CBCG_ERR_INPUT);
+                x = pos - prev_pos + 1u;
+            } else if (!k2b_room(S, i, seen_d)) { bailed = true; break; }
+            const uint32_t y = C.sym_pos_main(x, slot);
+            if (C.err) break;
+            if (MODE == MODE_DEC) x = y;
+            if (slot == 0u) {                                /* escape: the value itself, 4 bytes MSB first, then a new slot */
+                C.pa_ensure();
+                uint32_t acc = 0;
+                for (uint32_t k = 0; k < 4u; k++) {
+                    const uint32_t yk = C.template sym_dense<0, false>(C.pos_alpha() + k * PA_STRIDE, 256u, 10u, (x >> (24u - 8u * k)) & 0xffu, false, 0u);
+                    acc |= yk << (24u - 8u * k);
+                }
+                if (C.err) break;
+                if (MODE == MODE_DEC) x = acc;
+                C.pos_append(x);
+                if (C.err) break;
+            }
+            if (MODE == MODE_DEC) {
+                if (x == 0u) K2B_FAIL(CBCG_ERR_CORRUPT);
+                pos = prev_pos + x - 1u;
+                if (pos == 0u) K2B_FAIL(CBCG_ERR_CORRUPT);
+                if (lane == 0) { P.recs[r0 + i].pos = pos; P.chr[r0 + i] = B.chr; S.ring[i & (K2B_RING - 1u)].pos = pos; }
+                k2b_publish(S, role, i + 1u, lane);
+            }
+            prev_pos = pos;
+        }
+    } else if (role == CBCG_SUB_FLAG) {
+        /* ---- B: length byte 0 (variable-length containers) and FLAG (compress_read :29-33, compress_flag :50-70) */
+        k2b_copy(S.m.rlen0, SM->rlen0, 256u, lane);
+        k2b_copy(S.m.same_ref, SM->same_ref, 4u + 6u, lane);             /* same_ref, rlenk: never coded here, the merge reads the image */
+        { const uint32_t used = SM->flag_used; k2b_copy(S.m.flag_key, SM->flag_key, used, lane); k2b_copy(S.m.flag_cnt, SM->flag_cnt, used, lane);
+          if (lane == 0) { S.m.flag_used = used; S.m.flag_n = SM->flag_n; } }
+        __syncwarp();
+        C.ac_init();
+        for (; i < n_reads; i++) {
+            uint32_t len = L, flag = 0;
+            if (MODE == MODE_ENC) {
+                const uint32_t v = reinterpret_cast<const uint32_t *>(P.recs + r0 + i)[1];
+                flag = v & 0xffffu; len = v >> 16;
+                if (len == 0u || len > CBCG_MAX_READ_LEN || (fixed && len != L)) K2B_FAIL(CBCG_ERR_INPUT);
+            } else if (!k2b_room(S, i, seen_d)) { bailed = true; break; }
+            if (!fixed) len = C.template sym_dense<0, false>(S.m.rlen0, 255u, 10u, len & 0xffu, false, 0u);
+            flag = C.sym_flag(flag);
+            if (C.err) break;
+            if (MODE == MODE_DEC) {
+                if (len == 0u || len > CBCG_MAX_READ_LEN) K2B_FAIL(CBCG_ERR_CORRUPT);
+                const uint32_t v = flag | (len << 16);
+                if (lane == 0) { reinterpret_cast<uint32_t *>(P.recs + r0 + i)[1] = v; S.ring[i & (K2B_RING - 1u)].flaglen = v; }
+                k2b_publish(S, role, i + 1u, lane);
+            }
+        }
+    } else if (role == CBCG_SUB_COUNTS) {
+        /* ---- C: match bit, SNP count, indel counts (compress_match :164-188, compress_snps / compress_indels :193-228) */
+        k2b_copy(S.m.snps, SM->snps, 512u, lane);                        /* snps, indels */
+        k2b_copy(&S.m.match[0][0], &SM->match[0][0], 16u, lane);
+        __syncwarp();
+        C.ac_init();
+        uint32_t prev_pos = B.base_pos, prev_m = 0u;
+        uint64_t edits_left = B.n_edits;
+        for (; i < n_reads; i++) {
+            uint32_t pos, len = L, match = 0, ns = 0, nd = 0, ni = 0;
+            if (MODE == MODE_ENC) {
+                const uint4 v = reinterpret_cast<const uint4 *>(P.recs)[r0 + i];
+                pos = v.x; len = v.y >> 16; match = v.w & 0xffu; ns = (v.w >> 8) & 0xffu; nd = (v.w >> 16) & 0xffu; ni = v.w >> 24;
+            } else {
+                if (!k2b_wait(S, CBCG_SUB_POS, i, seen_a) || !k2b_wait(S, CBCG_SUB_FLAG, i, seen_b) || !k2b_room(S, i, seen_d)) { bailed = true; break; }
+                const volatile K2BEntry &e = S.ring[i & (K2B_RING - 1u)];
+                pos = e.pos; len = e.flaglen >> 16;
+            }
+            const uint32_t samepos = pos == prev_pos ? 1u : 0u;          /* deltaP == 1 (:170) */
+            prev_pos = pos;
+            match = C.template sym_dense<2, false>(S.m.match[(samepos << 1) | prev_m], 2u, 1u, match, false, 0u);
+            if (C.err) break;
+            prev_m = match;
+            if (!match) {
+                uint32_t x = ((nd | ni) == 0u) ? ns : 0u;
+                x = C.template sym_dense<0, false>(S.m.snps, L, 10u, x, false, 0u);
+                if (MODE == MODE_DEC) { ns = x; nd = ni = 0; }
+                if (!C.err && (MODE == MODE_DEC ? x == 0u : (nd | ni) != 0u)) {          /* :560-565 */
+                    ns = C.template sym_dense<0, false>(S.m.indels, L, 16u, ns, false, 0u);
+                    nd = C.template sym_dense<0, false>(S.m.indels, L, 16u, nd, false, 0u);
+                    ni = C.template sym_dense<0, false>(S.m.indels, L, 16u, ni, false, 0u);
+                }
+                if (C.err) break;
+                if (MODE == MODE_DEC) {
+                    if (ni > len || ns > 255u || nd > 255u || ni > 255u) K2B_FAIL(CBCG_ERR_CORRUPT);
+                    if ((uint64_t)(ns + nd + ni) > edits_left) K2B_FAIL(CBCG_ERR_CAPACITY);
+                    edits_left -= ns + nd + ni;
+                }
+            } else if (MODE == MODE_DEC) { ns = nd = ni = 0; }
+            if (MODE == MODE_DEC) {
+                const uint32_t v = match | (ns << 8) | (nd << 16) | (ni << 24);
+                if (lane == 0) { reinterpret_cast<uint32_t *>(P.recs + r0 + i)[3] = v; S.ring[i & (K2B_RING - 1u)].counts = v; }
+                k2b_publish(S, role, i + 1u, lane);
+            }
+        }
+    } else {
+        /* ---- D: edit positions through the var rows, bases through chars (:568-600; compute_delta_to_first_snp :703-718) */
+        k2b_copy(&S.m.chars[0][0], &SM->chars[0][0], 48u, lane);
+        for (uint32_t q = lane; q <= C.hash_mask; q += 32u) C.var_hash[q] = 0ull;
+        __syncwarp();
+        C.ac_init();
+        if (MODE == MODE_DEC && B.chr >= P.genome.n_chr) K2B_FAIL(CBCG_ERR_NO_REFERENCE);
+        uint64_t e_cursor = B.edit_base;
+        for (; i < n_reads; i++) {
+            uint32_t pos, len, flag, match, ns, nd, ni;
+            const uint16_t *e_in = P.edits;
+            if (MODE == MODE_ENC) {
+                const uint4 v = reinterpret_cast<const uint4 *>(P.recs)[r0 + i];
+                pos = v.x; flag = v.y & 0xffffu; len = v.y >> 16; match = v.w & 0xffu; ns = (v.w >> 8) & 0xffu; nd = (v.w >> 16) & 0xffu; ni = v.w >> 24;
+                e_in = P.edits + v.z;
+                if (!match) asm volatile("prefetch.global.L1 [%0];" ::"l"(e_in));
+            } else {
+                if (!k2b_wait(S, CBCG_SUB_COUNTS, i, seen_c)) { bailed = true; break; }
+                const volatile K2BEntry &e = S.ring[i & (K2B_RING - 1u)];
+                pos = e.pos; flag = e.flaglen & 0xffffu; len = e.flaglen >> 16;
+                const uint32_t cw = e.counts;
+                match = cw & 0xffu; ns = (cw >> 8) & 0xffu; nd = (cw >> 16) & 0xffu; ni = cw >> 24;
+                if (lane == 0) reinterpret_cast<uint32_t *>(P.recs + r0 + i)[2] = (uint32_t)e_cursor;
+            }
+            const uint32_t strand = (flag >> 4) & 1u;                    /* :57-60 */
+            C.ring_advance(pos);
+            if (!match) {
+                if (MODE == MODE_DEC) {                                  /* the reference bases under this read: the context of every decoded base */
+                    const uint8_t *rp = C.cold().ref + (pos - 1u);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + 128));
+                }
+                uint32_t prev = 0, ne = 0;
+                for (uint32_t k = 0; k < nd; k++) {                       /* deletions (:568-572) */
+                    uint32_t *m = C.var_row((prev << 1) | strand);
+                    if (!m) break;
+                    const uint32_t d = C.template sym_dense<0, true>(m, L, 10u, MODE == MODE_ENC ? CBCG_EDIT_DELTA(e_in[k]) : 0u, false, 0u);
+                    if (C.err) break;
+                    prev += d;
+                    if (MODE == MODE_DEC && lane == 0) { P.edits[e_cursor + ne] = CBCG_EDIT(d, 0, 0); S.m.cumdel[k] = (uint16_t)min(prev, 0xffffu); }
+                    ne++;
+                }
+                if (MODE == MODE_DEC) __syncwarp();
+                prev = 0;
+                for (uint32_t k = 0; k < ns && !C.err; k++) {             /* SNPs (:573-593) */
+                    const uint32_t ed = MODE == MODE_ENC ? e_in[nd + k] : 0u;
+                    const uint32_t delta = C.ring_first(pos - 1u + prev, (prev < len) ? pos - 1u + len : pos - 1u + prev, len + 2u);
+                    uint32_t *m = C.var_row((((delta << CBCG_BITS_DELTA) + prev) << 1) | strand);
+                    if (!m) break;
+                    const uint32_t p = C.template sym_dense<0, true>(m, L, 10u, CBCG_EDIT_DELTA(ed), false, 0u);
+                    if (C.err) break;
+                    const uint32_t idx = prev + p;                        /* index in the insertion-free read */
+                    prev += p + 1u;
+                    C.ring_set(pos + prev - 2u);                          /* :589 */
+                    uint32_t refb;
+                    if (MODE == MODE_DEC) {
+                        uint32_t skipped = 0;                             /* deletions at or before idx (:426-437) */
+                        if (nd) { for (uint32_t q = lane; q < nd; q += 32u) skipped += (S.m.cumdel[q] <= idx); skipped = warp_sum(skipped); }
+                        const uint64_t ri = (uint64_t)pos - 1u + idx + skipped;
+                        refb = base_code(ri < C.cold().ref_len ? (uint32_t)C.cold().ref[ri] : 0u);
+                    } else refb = CBCG_EDIT_REFB(ed);
+                    if (refb > 5u) K2B_FAIL(CBCG_ERR_INPUT);
+                    const uint32_t tgt = C.template sym_dense<5, false>(S.m.chars[refb], 5u, 8u, CBCG_EDIT_TARGET(ed), false, 0u);
+                    if (MODE == MODE_DEC && lane == 0) P.edits[e_cursor + ne] = CBCG_EDIT(p, tgt, refb);
+                    ne++;
+                }
+                prev = 0;
+                for (uint32_t k = 0; k < ni && !C.err; k++) {             /* insertions (:594-600) */
+                    const uint32_t ed = MODE == MODE_ENC ? e_in[nd + ns + k] : 0u;
+                    uint32_t *m = C.var_row((prev << 1) | strand);
+                    if (!m) break;
+                    const uint32_t p = C.template sym_dense<0, true>(m, L, 10u, CBCG_EDIT_DELTA(ed), false, 0u);
+                    prev += p;
+                    const uint32_t tgt = C.template sym_dense<5, false>(S.m.chars[CBCG_BP_O], 5u, 8u, CBCG_EDIT_TARGET(ed), false, 0u);
+                    if (MODE == MODE_DEC && lane == 0) P.edits[e_cursor + ne] = CBCG_EDIT(p, tgt, CBCG_BP_O);
+                    ne++;
+                }
+                if (C.err) break;
+                e_cursor += ne;
+            }
+            if (MODE == MODE_DEC) k2b_publish(S, role, i + 1u, lane);
+        }
+        if (MODE == MODE_DEC && !C.err && !bailed && e_cursor - B.edit_base != B.n_edits) C.err = CBCG_ERR_CORRUPT;   /* the index said otherwise */
+    }
+role_done:
+#undef K2B_FAIL
+    if (C.err) {
+        dev_set_error(P.err, C.err, ((uint64_t)b << 20) | (i & 0xfffffu));
+        S.failed = 1;                                        /* releases the roles that wait for this one */
+        return;
+    }
+    if (bailed) return;
+    /* ---- close the substream, leave the final model state where the merge kernels read it */
+    if (MODE == MODE_ENC) {
+        uint32_t bytes = 0;
+        if (C.n_symbols) { C.ac_flush_short(); bytes = C.out_pos; }       /* nothing coded: nothing stored */
+        if (C.err) { dev_set_error(P.err, C.err, (uint64_t)b << 20); return; }
+        if (lane == 0) B.sub_bytes[role] = bytes;
+    }
+    __syncwarp();
+    if (role == CBCG_SUB_POS) {
+        if (lane < C.pos_card) { C.pos_gval()[lane] = C.pos_rv; C.pos_gcnt()[lane] = C.pos_rc; }
+        if (lane == 0) { B.pos_card = C.pos_card; B.pa_touched = C.pa_init ? 1u : 0u; }
+    } else if (role == CBCG_SUB_FLAG) {
+        k2b_copy(FM->rlen0, S.m.rlen0, 256u, lane); k2b_copy(FM->same_ref, S.m.same_ref, 10u, lane);
+        const uint32_t used = S.m.flag_used;
+        k2b_copy(FM->flag_key, S.m.flag_key, used, lane); k2b_copy(FM->flag_cnt, S.m.flag_cnt, used, lane);
+        if (lane == 0) { FM->flag_used = used; FM->flag_n = S.m.flag_n; }
+    } else if (role == CBCG_SUB_COUNTS) {
+        k2b_copy(FM->snps, S.m.snps, 512u, lane); k2b_copy(&FM->match[0][0], &S.m.match[0][0], 16u, lane);
+    } else {
+        k2b_copy(&FM->chars[0][0], &S.m.chars[0][0], 48u, lane);
+        if (lane == 0) B.n_rows = C.n_rows;
+    }
+    if (lane == 0) atomicAdd(&B.n_symbols, C.n_symbols);
+}
+
+int launch_block_kernel(const CoderParams &p, cudaStream_t st) {
+    if (p.n_blocks == 0) return 0;
+    if (p.mode == MODE_ENC) k2_block_kernel<MODE_ENC><<<p.n_blocks, K2B_WARPS * 32u, 0, st>>>(p);
+    else k2_block_kernel<MODE_DEC><<<p.n_blocks, K2B_WARPS * 32u, 0, st>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 uint32_t coder_resident_blocks(int device) {
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) return 148u * 16u;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_coder_kernel<MODE_ENC, false>, (int)K2_THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = K2_MIN_CTAS;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_coder_kernel<MODE_ENC, true>, (int)K2_THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = K2_MIN_CTAS;
     return (uint32_t)sms * (uint32_t)per_sm * K2_WARPS;
 }
 
 __global__ void k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap, uint64_t payload_cap,
                                uint64_t *totals, const uint64_t *carry_in, const uint64_t *n_edits_dev);
-__global__ void k2_payload_scan_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off);
-__global__ void k2_gather_kernel(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out, const uint64_t *out_off);
-__global__ void snapshot_init_kernel(uint8_t *snap, uint32_t L);
+__global__ void k2_payload_scan_kernel(BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off, int subs);
+__global__ void k2_gather_kernel(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out, const uint64_t *out_off, int subs);
 __global__ void snapshot_copy_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint64_t n16);
 struct MergeParams;
 __global__ void merge_prep_kernel(MergeParams P);
@@ -1220,6 +1560,7 @@ __global__ void merge_var_finish_kernel(MergeParams P);
  * kernel on the same split; one-stream calls keep the driver's choices, which are 0.3 ms better for the block coder. */
 void extract_set_carveout(int pct);        /* k1_extract.cu */
 void reconstruct_set_carveout(int pct);    /* k3_reconstruct.cu */
+void roles_set_carveout(int pct);          /* k2_blocks.cu */
 template <class K> static void set_carveout(K kernel, int pct) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }
 /* pct = -1: every kernel gets the split the driver prefers for it (best for each kernel on its own: the one-stream
  * calls); 0..100: that share of shared memory for all of them (the pipelined calls). */
@@ -1229,25 +1570,28 @@ void set_carveout_all(int pct) {
     if (e) pct = atoi(e);
     if (pct == current) return;
     current = pct;
-    set_carveout(k2_coder_kernel<MODE_ENC, false>, pct); set_carveout(k2_coder_kernel<MODE_DEC, false>, pct); set_carveout(k2_coder_kernel<MODE_LIST, false>, pct);
+    set_carveout(k2_coder_kernel<MODE_LIST, false>, pct); set_carveout(k2_block_kernel<MODE_ENC>, pct); set_carveout(k2_block_kernel<MODE_DEC>, pct);
     set_carveout(k2_coder_kernel<MODE_ENC, true>, pct); set_carveout(k2_coder_kernel<MODE_DEC, true>, pct); set_carveout(k2_coder_kernel<MODE_LIST, true>, pct);
     set_carveout(k2_plan_kernel, pct); set_carveout(k2_payload_scan_kernel, pct); set_carveout(k2_gather_kernel, pct);
-    set_carveout(snapshot_init_kernel, pct); set_carveout(snapshot_copy_kernel, pct);
+    set_carveout(snapshot_copy_kernel, pct);
     set_carveout(merge_prep_kernel, pct); set_carveout(merge_add_kernel, pct); set_carveout(merge_finish_kernel, pct); set_carveout(merge_var_finish_kernel, pct);
-    extract_set_carveout(pct); reconstruct_set_carveout(pct);
+    extract_set_carveout(pct); reconstruct_set_carveout(pct); roles_set_carveout(pct);
 }
 
+int launch_block_kernel(const CoderParams &p, cudaStream_t st);
 int launch_coder(const CoderParams &p, cudaStream_t st) {
     if (p.n_blocks == 0) return 0;
+    if (!p.legacy && p.mode != MODE_LIST) {                 /* blocked containers: a CTA per block, a warp per substream */
+        static const bool scalar = getenv("CBCG_SCALAR_ROLES") != nullptr;   /* cross-check: the scalar twin (k2_blocks.cu) */
+        return scalar ? launch_roles(p, st) : launch_block_kernel(p, st);
+    }
     const unsigned grid = (p.n_blocks + K2_WARPS - 1) / K2_WARPS;
     if (p.legacy) {
         if (p.mode == MODE_ENC) k2_coder_kernel<MODE_ENC, true><<<grid, K2_THREADS, 0, st>>>(p);
         else if (p.mode == MODE_DEC) k2_coder_kernel<MODE_DEC, true><<<grid, K2_THREADS, 0, st>>>(p);
         else k2_coder_kernel<MODE_LIST, true><<<grid, K2_THREADS, 0, st>>>(p);
     } else {
-        if (p.mode == MODE_ENC) k2_coder_kernel<MODE_ENC, false><<<grid, K2_THREADS, 0, st>>>(p);
-        else if (p.mode == MODE_DEC) k2_coder_kernel<MODE_DEC, false><<<grid, K2_THREADS, 0, st>>>(p);
-        else k2_coder_kernel<MODE_LIST, false><<<grid, K2_THREADS, 0, st>>>(p);
+        k2_coder_kernel<MODE_LIST, false><<<grid, K2_THREADS, 0, st>>>(p);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1311,6 +1655,10 @@ k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, ui
             if (!dec) d.payload_off = off[1];
             else { d.payload_off = off[1]; d.first_read = (uint32_t)off[3]; d.edit_base = off[4]; }
             d.sym_off = off[2];
+            if (!P.legacy && P.mode != MODE_LIST) {              /* the substream roles add their symbol counts */
+                d.n_symbols = 0; d.pos_card = 0; d.n_rows = 0; d.pa_touched = 0;
+                if (!dec) { d.payload_bytes = 0; for (uint32_t q = 0; q < CBCG_N_SUB; q++) d.sub_bytes[q] = 0; }
+            }
             P.blocks[b] = d;
         }
         __syncthreads();
@@ -1335,7 +1683,7 @@ int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_t
 /* ------------------------------------------------------------------------------------------------
  * gather: block payloads (scratch regions) -> one contiguous payload; out_off[b] = its offset. */
 __global__ void __launch_bounds__(PLAN_THREADS)
-k2_payload_scan_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off) {
+k2_payload_scan_kernel(BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off, int subs) {
     __shared__ uint64_t wsum[32];
     __shared__ uint64_t carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1343,7 +1691,11 @@ k2_payload_scan_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint64_t *out
     __syncthreads();
     for (uint32_t base = 0; base < n_blocks; base += PLAN_THREADS) {
         const uint32_t b = base + tid;
-        const uint64_t v = (b < n_blocks) ? blocks[b].payload_bytes : 0;
+        uint64_t v = 0;
+        if (b < n_blocks) {
+            if (subs) { uint32_t t = 0; for (uint32_t q = 0; q < CBCG_N_SUB; q++) t += blocks[b].sub_bytes[q]; blocks[b].payload_bytes = t; }
+            v = blocks[b].payload_bytes;
+        }
         uint64_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= (uint32_t)o) x += y; }
@@ -1361,21 +1713,29 @@ k2_payload_scan_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint64_t *out
 }
 
 __global__ void k2_gather_kernel(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
-                                 const uint64_t *out_off) {
+                                 const uint64_t *out_off, int subs) {
     for (uint32_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
         const uint8_t *src = scratch + blocks[b].payload_off;
         uint8_t *dst = out + out_off[b];
-        const uint32_t n = blocks[b].payload_bytes;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        if (!subs) {
+            const uint32_t n = blocks[b].payload_bytes;
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+            continue;
+        }
+        for (uint32_t q = 0; q < CBCG_N_SUB; q++) {          /* substreams A | B | C | D from their scratch regions */
+            const uint32_t n = blocks[b].sub_bytes[q];
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+            dst += n; src += k2_sub_cap(q, blocks[b].n_reads, blocks[b].n_edits);
+        }
     }
 }
 
-int launch_gather(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
-                  uint64_t *out_off, cudaStream_t st) {
+int launch_gather(BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
+                  uint64_t *out_off, int subs, cudaStream_t st) {
     if (n_blocks == 0) return 0;
-    k2_payload_scan_kernel<<<1, PLAN_THREADS, 0, st>>>(blocks, n_blocks, out_off);
+    k2_payload_scan_kernel<<<1, PLAN_THREADS, 0, st>>>(blocks, n_blocks, out_off, subs);
     unsigned grid = n_blocks < 148u * 8u ? n_blocks : 148u * 8u;
-    k2_gather_kernel<<<grid, 128, 0, st>>>(blocks, n_blocks, scratch, out, out_off);
+    k2_gather_kernel<<<grid, 128, 0, st>>>(blocks, n_blocks, scratch, out, out_off, subs);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1385,43 +1745,11 @@ int launch_gather(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scr
  * >= 1 (>= 0 where the snapshot held 0) and rescaled like update_model (src/stream_model.c:38-49).
  * The decoder runs the same kernels on the blocks it has decoded. `next` arrives as a byte copy of `prev`. */
 
-__global__ void __launch_bounds__(32) snapshot_init_kernel(uint8_t *snap, uint32_t L) {
-    __shared__ WarpShared WS;
-    WarpModels &M = WS.m;
-    const SnapLayout l = snap_layout(L);
-    const uint32_t lane = threadIdx.x;
-    Coder<MODE_ENC> C;                                     /* borrow the initial-state code of the block coder */
-    C.lane = lane; C.M = &M; C.L = L; C.var_direct = false; C.hash_mask = 0; C.err = 0; C.primed = false; C.var_defer = false; C.var_ro = false;
-    __shared__ uint64_t dummy_hash[32];                     /* init_models clears the block's hash table */
-    C.var_hash = dummy_hash; C.hash_mask = 31u;
-    C.init_models(false);
-    C.init_L_models();
-    for (uint32_t i = lane; i < 256u; i += 32u) M.cumdel[i] = 0;
-    SYNCW();
-    uint32_t *small = reinterpret_cast<uint32_t *>(snap + l.small);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(&M);
-    for (uint32_t i = lane; i < (uint32_t)(sizeof(WarpModels) / 4u); i += 32u) small[i] = src[i];
-    uint32_t *hdr = reinterpret_cast<uint32_t *>(snap + l.pos_hdr);
-    uint32_t *pv = reinterpret_cast<uint32_t *>(snap + l.pos_val), *pc = reinterpret_cast<uint32_t *>(snap + l.pos_cnt);
-    if (lane == 0) { hdr[0] = 1u; hdr[1] = 1u; hdr[2] = 0u; hdr[3] = 0u; pv[0] = 0u; pc[0] = 1u; }   /* escape only (sam_models.c:132-162) */
-    uint32_t *pa = reinterpret_cast<uint32_t *>(snap + l.pos_alpha);
-    for (uint32_t k = 0; k < 4u; k++) { for (uint32_t i = lane; i < 256u; i += 32u) pa[k * PA_STRIDE + i] = 1u; if (lane == 0) pa[k * PA_STRIDE + 256u] = 256u; }
-    uint32_t *bm = reinterpret_cast<uint32_t *>(snap + l.bitmap);
-    for (uint32_t i = lane; i < 2048u; i += 32u) bm[i] = 0u;
-    uint32_t *ones = reinterpret_cast<uint32_t *>(snap + l.ones);
-    for (uint32_t i = lane; i < L; i += 32u) ones[i] = 1u;
-    if (lane == 0) ones[L] = L;
-}
-
-int launch_snapshot_init(uint8_t *snap, uint32_t L, cudaStream_t st) {
-    snapshot_init_kernel<<<1, 32, 0, st>>>(snap, L);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
-
 struct MergeParams {
     const BlockDesc *blocks; uint32_t block_begin, n_blocks, L;
     const uint8_t *prev; uint8_t *next; const uint8_t *fin; const uint8_t *ws;
     unsigned long long *err;
+    uint32_t flag_target;                  /* cbcg_flag_target(longest block of the container) */
 };
 
 /* An earlier stage has failed (the error word is set): blocks of this generation may have returned before touching
@@ -1542,8 +1870,12 @@ __global__ void __launch_bounds__(128) merge_add_kernel(MergeParams P) {
                 const uint64_t e = __shfl_sync(FULL_MASK, sl, src);
                 const uint32_t ctx = (uint32_t)(e >> 32) - 1u, r = (uint32_t)e;
                 const bool in_prev = (pbm[ctx >> 5] >> (ctx & 31u)) & 1u;
-                const uint32_t *row = rows + (uint64_t)r * w.Lp, *prow = pvar + (uint64_t)ctx * l.Lp;
                 uint32_t *nrow = var + (uint64_t)ctx * l.Lp;
+                if (r & VAR_DEFERRED) {                      /* touched once: the row was never built, its one update is the difference */
+                    if (lane == 0) atomicAdd(&nrow[r & 0xffffu], 10u);
+                    continue;
+                }
+                const uint32_t *row = rows + (uint64_t)r * w.Lp, *prow = pvar + (uint64_t)ctx * l.Lp;
                 /* a row is at most 8 x 32 counts: all of its loads go out before the first is needed */
                 uint32_t rv[8], pv[8];
 #pragma unroll
@@ -1742,14 +2074,17 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
         n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
         __syncthreads();
     }
-    if (n >= CBCG_RESCALE) {                               /* rare: halve-and-increment until the total fits */
-        while (n >= CBCG_RESCALE) {
-            uint32_t s = live ? 0u : 64u;                    /* (1 >> 1) + 1 == 1 */
-            for (uint32_t j = 0; live && j < 64u; j++) { const uint32_t i = base + 32u * j + lane; const uint32_t c = (dacc[i] >> 1) + 1u; dacc[i] = c; s += c; }
-            s = warp_sum(s); if (lane == 0) red[warp] = s; __syncthreads();
-            n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
-            __syncthreads();
+    if (n > P.flag_target) {                               /* scale to the target total instead of halving (cbcg_flag_target, cbcg_format.h) */
+        const uint64_t a = (uint64_t)P.flag_target - 65536u, nn = n;
+        uint32_t s = live ? 0u : 64u;                        /* untouched values stay 1 */
+        for (uint32_t j = 0; live && j < 64u; j++) {
+            const uint32_t i = base + 32u * j + lane;
+            uint64_t c = (uint64_t)dacc[i] * a / nn; if (c < 1u) c = 1u;
+            dacc[i] = (uint32_t)c; s += (uint32_t)c;
         }
+        s = warp_sum(s); if (lane == 0) red[warp] = s; __syncthreads();
+        n = 0; for (uint32_t k = 0; k < 32u; k++) n += red[k];
+        __syncthreads();
         mine = 0;
         for (uint32_t j = 0; live && j < 64u; j++) mine += (uint32_t)__popc(__ballot_sync(FULL_MASK, dacc[base + 32u * j + lane] != 1u));
     }
@@ -1819,11 +2154,11 @@ int launch_copy16(void *dst, const void *src, uint64_t bytes, cudaStream_t st) {
 }
 
 int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_blocks, uint32_t L, const uint8_t *prev,
-                 uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, cudaStream_t st) {
+                 uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, uint32_t flag_target, cudaStream_t st) {
     /* next = prev, by a kernel: a cudaMemcpyAsync would queue on a copy engine behind the host <-> device traffic of a
        pipelined call (api.cu) and stall the generations for milliseconds */
     snapshot_copy_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<uint4 *>(next), reinterpret_cast<const uint4 *>(prev), snapshot_bytes(L) / 16u);
-    MergeParams P = { blocks, block_begin, n_blocks, L, prev, next, fin, ws, err };
+    MergeParams P = { blocks, block_begin, n_blocks, L, prev, next, fin, ws, err, flag_target };
     merge_prep_kernel<<<148, 128, 0, st>>>(P);
     merge_add_kernel<<<dim3((n_blocks + 3u) / 4u, MERGE_PARTS), 128, 0, st>>>(P);
     merge_finish_kernel<<<2, MERGE_FIN_WARPS * 32u, 0, st>>>(P);

@@ -1056,11 +1056,11 @@ static void rstate_init_from(rstate *s, const models *snap, int mode) {
  * every block starts from the reference's initial state (gen_mode 0). */
 static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads, uint32_t n_sched,
                       const uint32_t *sched_count, const uint32_t *sched_reads, const blk_index *given, uint64_t n_given,
-                      cbco_buf *out);
+                      uint32_t gen_mode, cbco_buf *out);
 
 int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads,
                           uint32_t n_sched, const uint32_t *sched_count, const uint32_t *sched_reads, cbco_buf *out) {
-    return encode_cut(b, g, L, block_reads, n_sched, sched_count, sched_reads, NULL, 0, out);
+    return encode_cut(b, g, L, block_reads, n_sched, sched_count, sched_reads, NULL, 0, n_sched ? 1u : 0u, out);
 }
 
 /* The batch coded with the block cut of an existing container (per-block read counts and generations taken from its
@@ -1083,14 +1083,14 @@ int cbco_encode_like(const uint8_t *p, uint64_t len, const cbco_batch *b, const 
     idx_state st = { h[8], 0, 0, 0, 0, 0, { 0, 0, 0, 0 } };
     uint64_t io = o;
     for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k])) { free(idx); return -43; }
-    int rc = encode_cut(b, g, h[3], h[8], (h[9] & CBCG_MODE_GEN_MASK) ? 1u : 0u, NULL, NULL, idx, nb, out);
+    int rc = encode_cut(b, g, h[3], h[8], (h[9] & CBCG_MODE_GEN_MASK) ? 1u : 0u, NULL, NULL, idx, nb, h[9] & CBCG_MODE_GEN_MASK, out);
     free(idx);
     return rc;
 }
 
 static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads, uint32_t n_sched,
                       const uint32_t *sched_count, const uint32_t *sched_reads, const blk_index *given, uint64_t n_given,
-                      cbco_buf *out) {
+                      uint32_t gen_mode, cbco_buf *out) {
     if (block_reads == 0) return -30;
     uint64_t cap = 16;
     for (uint64_t r = 0; r < b->n_reads; r++) cap += 3ull * b->seq_len[r] + 8;
@@ -1171,7 +1171,7 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
         for (uint64_t r = 0; r < b->n_reads; r++) if (b->seq_len[r] > max_len) max_len = b->seq_len[r];
         buf_put_u32(out, CBCG_MAGIC); buf_put_u32(out, CBCG_VERSION); buf_put_u32(out, max_len); buf_put_u32(out, L);
         buf_put_u64(out, b->n_reads); buf_put_u32(out, (uint32_t)nb); buf_put_u32(out, g->n_chr);
-        buf_put_u32(out, block_reads); buf_put_u32(out, (n_sched ? 1u : 0u) | (fixed_len ? CBCG_MODE_FIXED_LEN : 0u));
+        buf_put_u32(out, block_reads); buf_put_u32(out, gen_mode | (fixed_len ? CBCG_MODE_FIXED_LEN : 0u));
         for (uint32_t c = 0; c < g->n_chr; c++) {
             uint32_t nl = (uint32_t)strlen(g->name[c]), pad = (4 - (nl & 3)) & 3; uint32_t z = 0;
             buf_put_u32(out, nl); buf_put(out, g->name[c], nl); buf_put(out, &z, pad);
@@ -1195,7 +1195,7 @@ int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, u
     if (gen_mode > 1) return -30;
     if (gen_mode) levels = cbcg_gen_schedule(b->n_reads, count, reads, &last);
     if (block_reads == 0xffffffffu) block_reads = gen_mode ? last : 1024u;      /* CBCG_BLOCK_AUTO */
-    return cbco_encode_scheduled(b, g, L, block_reads, levels, count, reads, out);
+    return encode_cut(b, g, L, block_reads, levels, count, reads, NULL, 0, gen_mode, out);
 }
 
 int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cbco_buf *seq_out, uint64_t *n_reads_out) {

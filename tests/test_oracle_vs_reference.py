@@ -77,7 +77,7 @@ def test_blocked_container_roundtrip(block_reads):
     assert n == b.n_reads and decoded == b.seq_lines()
 
 
-def test_container_v3_fixed_length_flag_and_recoding_with_a_given_cut():
+def test_container_v4_fixed_length_flag_and_recoding_with_a_given_cut():
     """Equal-length input sets CBCG_MODE_FIXED_LEN (no length symbol), variable-length input does not; the restatement
     re-encodes a batch with the cut of an existing container (what the GPU's self-chosen cuts are checked with)."""
     import struct
@@ -87,7 +87,7 @@ def test_container_v3_fixed_length_flag_and_recoding_with_a_given_cut():
         for gen_mode in (0, 1):
             c = O.encode_blocked(b, g, L, 384, gen_mode)
             version, mode = struct.unpack_from("<I", c, 4)[0], struct.unpack_from("<I", c, 36)[0]
-            assert version == 3 and (mode & 0xff) == gen_mode and bool(mode & 0x100) == fixed
+            assert version == 4 and (mode & 0xff) == gen_mode and bool(mode & 0x100) == fixed
             text, n = O.decode_blocked(c, g)
             assert n == b.n_reads and text == b.seq_lines()
             assert O.encode_like(c, b, g) == c
