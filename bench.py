@@ -388,7 +388,7 @@ def run_b200_arm(args):
 
     def resident_step(record: bool):
         nonlocal launches, index_bytes, block_reads_used, layout
-        codec.encode_resident(L, R, G)
+        codec.encode_resident(L, R, G, args.substreams)
         se = codec.stats()
         head, payload = codec.fetch_index()
         if dist is not None:                                  # container index: all-gather of per-shard block tables
@@ -466,7 +466,7 @@ def run_b200_arm(args):
         if rank == 0:
             os.unlink(path)
         codec.upload(pb)                                      # the decode above replaced the resident state
-        codec.encode_resident(L, R, G)
+        codec.encode_resident(L, R, G, args.substreams)
 
     # K1 alone, for its roofline entry: in the timed steps above the tail of K1 runs on a side stream beside the early
     # generations of the block coder (api.cu, encode_resident_overlapped), which stretches its own launch time;
@@ -474,7 +474,7 @@ def run_b200_arm(args):
     os.environ["CBCG_NO_OVERLAP"] = "1"
     k1_alone = []
     for _ in range(3):
-        codec.encode_resident(L, R, G)
+        codec.encode_resident(L, R, G, args.substreams)
         k1_alone.append(codec.stats()["ms_k1"])
     del os.environ["CBCG_NO_OVERLAP"]
     if codec.stats()["container_bytes"] != container_bytes:
@@ -496,7 +496,7 @@ def run_b200_arm(args):
 
     def e2e_one(k):
         c2 = codecs[k]
-        nc = c2.compress_into(subs[k], L, R, outs_c[k], G)
+        nc = c2.compress_into(subs[k], L, R, outs_c[k], G, args.substreams)
         s1 = c2.stats()
         head, payload = c2.fetch_index()
         nt, nr = c2.decompress_into(outs_c[k][:nc], outs_t[k])
@@ -638,7 +638,7 @@ def run_b200_arm(args):
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": wl_text, "named_config": cnum, "n_reads_per_gpu": n, "n_reads_total": int(total_reads), "read_len": L,
-                   "block_reads": block_reads_used, "block_reads_auto": R == 0xffffffff, "gen_mode": G, "blocks_per_gpu": int(se["n_blocks"]),
+                   "block_reads": block_reads_used, "block_reads_auto": R == 0xffffffff, "gen_mode": G, "substreams_per_block": args.substreams, "blocks_per_gpu": int(se["n_blocks"]),
                    "l2": "inputs larger than L2 (batch %.0f MB, decoded text %.0f MB per GPU)" % (s1["h2d_bytes"] / 1e6, (bases + n) / 1e6),
                    "parallelism": (f"{world} region shard(s) of one position-sorted input" if not args.replicas else f"{world} replicas") + ", no collective on the coding path",
                    "batches_in_flight": 1},
@@ -695,6 +695,7 @@ def main():
     ap.add_argument("--block-reads", type=int, default=0xffffffff, help="reads per block; default: CBCG_BLOCK_AUTO")
     ap.add_argument("--inflight", type=int, default=1, help="contexts (host threads / streams) the e2e leg keeps in flight")
     ap.add_argument("--gen-mode", type=int, default=1, help="1: generation-primed blocks (default), 0: cold blocks")
+    ap.add_argument("--substreams", type=int, default=1, choices=[1, 4], help="arithmetic-coded streams per block: 1 (default) or 4 (CBCG_MODE_SPLIT4)")
     ap.add_argument("--scale", type=float, default=0.0, help="shrink the workload; default 1.0 (config 4: 0.1, stated in config.workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / blocking-overhead / CLI legs")
     ap.add_argument("--no-cli", action="store_true", help="skip the file-to-file CLI leg")

@@ -31,7 +31,7 @@ EXPORTS = ["cbcg_create", "cbcg_destroy", "cbcg_strerror", "cbcg_last_error", "c
 
 class EncodeOpts(C.Structure):
     _fields_ = [("read_len_header", C.c_uint32), ("block_reads", C.c_uint32), ("gen_mode", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("substreams", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -196,11 +196,11 @@ class Codec:
 
     # ---- compress() / decompress() (src/compression.c:112-216) over host buffers
     def compress(self, batch: Batch, read_len_header: int, block_reads: int = 0, gen_mode: int = 0,
-                 out: Optional[np.ndarray] = None) -> bytes:
+                 out: Optional[np.ndarray] = None, substreams: int = 1) -> bytes:
         """block_reads == 0: the reference's own single stream (byte-identical to `program -c 1`, -DDEBUG).
-        gen_mode 1: generation-primed blocks."""
+        gen_mode 1: generation-primed blocks. substreams 4: four arithmetic-coded substreams per block."""
         cb = batch.c_struct()
-        opts = EncodeOpts(read_len_header, block_reads, gen_mode, 0)
+        opts = EncodeOpts(read_len_header, block_reads, gen_mode, substreams)
         cap = int(self.lib.cbcg_encode_bound(C.byref(cb), C.byref(opts)))
         buf = out if out is not None and out.nbytes >= cap else np.empty(cap, np.uint8)
         n = C.c_uint64(0)
@@ -233,10 +233,11 @@ class Codec:
             self._check(rc)
             return out[:n.value].tobytes(), nr.value
 
-    def compress_into(self, batch: Batch, read_len_header: int, block_reads: int, out: np.ndarray, gen_mode: int = 0) -> int:
+    def compress_into(self, batch: Batch, read_len_header: int, block_reads: int, out: np.ndarray, gen_mode: int = 0,
+                      substreams: int = 1) -> int:
         """cbcg_encode into a caller-owned (ideally pinned) buffer; returns the container size."""
         cb = batch.c_struct()
-        opts = EncodeOpts(read_len_header, block_reads, gen_mode, 0)
+        opts = EncodeOpts(read_len_header, block_reads, gen_mode, substreams)
         n = C.c_uint64(0)
         self._check(self.lib.cbcg_encode(self.h, C.byref(cb), C.byref(opts), out.ctypes.data, out.nbytes, C.byref(n)))
         return n.value
@@ -279,8 +280,8 @@ class Codec:
         cb = batch.c_struct()
         self._check(self.lib.cbcg_batch_upload(self.h, C.byref(cb)))
 
-    def encode_resident(self, read_len_header: int, block_reads: int, gen_mode: int = 0):
-        opts = EncodeOpts(read_len_header, block_reads, gen_mode, 0)
+    def encode_resident(self, read_len_header: int, block_reads: int, gen_mode: int = 0, substreams: int = 1):
+        opts = EncodeOpts(read_len_header, block_reads, gen_mode, substreams)
         self._check(self.lib.cbcg_encode_resident(self.h, C.byref(opts)))
 
     def decode_resident(self):

@@ -75,13 +75,14 @@ struct cbcg_ctx {
     DevBuf recs, edits, chr_out, tile_desc, words, blocks, ws, scratch, payload, out_off, symbols, seq_out;
     DevBuf snap_a, snap_b, fin;                /* generation snapshots and per-block final states (gen_mode 1) */
     std::vector<std::pair<uint32_t, uint32_t>> gens;   /* (first block, block count) per generation of the last cut */
+    uint32_t n_sub = 1;                        /* substreams per block of the call in progress (opts->substreams / the container's mode word) */
     uint32_t max_block_reads = 0;              /* longest block of the last cut / index: sets the merged snapshots' FLAG total (cbcg_flag_target) */
     Words *hw = nullptr;                       /* pinned */
     BlockDesc *hblocks = nullptr; size_t hblocks_cap = 0;   /* pinned */
 
     /* result of the last encode */
     bool have_encoded = false;
-    uint32_t enc_L = 0, enc_block_reads = 0, enc_gen_mode = 0, enc_legacy = 0, enc_max_len = 0, enc_fixed = 0;
+    uint32_t enc_L = 0, enc_block_reads = 0, enc_gen_mode = 0, enc_legacy = 0, enc_max_len = 0, enc_fixed = 0, enc_n_sub = 1;
     uint32_t batch_min_len = 0;               /* shortest read of the resident batch (host scan at upload) */
     uint64_t enc_n_reads = 0, enc_n_edits = 0, enc_n_blocks = 0, enc_payload_bytes = 0;
     std::vector<uint8_t> enc_head;             /* container header + index */
@@ -464,7 +465,7 @@ static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, ui
                       const std::vector<SizeStep> *ramp = nullptr, bool upload = true) {
     const uint64_t n = ctx->db.n_reads;
     uint32_t sched_count[CBCG_GEN_MAX], sched_reads[CBCG_GEN_MAX], sched_last = 0;
-    const uint32_t n_sched = gen_mode ? cbcg_gen_schedule(n, sched_count, sched_reads, &sched_last) : 0u;
+    const uint32_t n_sched = gen_mode ? cbcg_gen_schedule(n, ctx->n_sub, sched_count, sched_reads, &sched_last) : 0u;
     uint64_t bound = 1;
     uint32_t min_reads = block_reads;
     if (ramp) for (const SizeStep &st : *ramp) min_reads = std::min(min_reads, std::max(st.block_reads, 1u));
@@ -509,17 +510,28 @@ static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, ui
 /* CBCG_BLOCK_AUTO: reads per last-generation block such that the generation fills the GPU's resident block slots a
  * whole number of times. */
 static uint32_t auto_block_reads(cbcg_ctx *ctx, uint64_t n, uint32_t gen_mode, uint64_t *slots_out = nullptr) {
-    (void)ctx;
     if (slots_out) *slots_out = 0;
     if (!gen_mode) return 1024u;
     uint32_t c[CBCG_GEN_MAX], r[CBCG_GEN_MAX], last = 0;
-    cbcg_gen_schedule(n, c, r, &last);                      /* what the <= 1 % budget leaves for the last generation */
-    return last;
+    const uint32_t k = cbcg_gen_schedule(n, ctx->n_sub, c, r, &last);   /* what the <= 1 % budget leaves for the last generation */
+    if (ctx->n_sub > 1u) return last;
+    /* one warp per block: the last generation runs in whole waves of the GPU's resident warps (a few blocks beyond a wave
+       cost a whole block time); rounded to fewer, larger blocks, never more */
+    uint64_t early = 0;
+    for (uint32_t g = 0; g < k; g++) early += (uint64_t)c[g] * r[g];
+    const uint64_t rest = n > early ? n - early : 0;
+    const uint64_t slots = coder_resident_blocks(ctx->device);
+    if (slots_out) *slots_out = slots;
+    if (!rest || !slots) return last;
+    const uint64_t blocks = (rest + last - 1) / last;
+    const uint64_t waves = std::max<uint64_t>(1, blocks / slots);
+    if (blocks <= slots * waves) return last;
+    return (uint32_t)std::min<uint64_t>((rest + waves * slots - 1) / (waves * slots), 16384u);
 }
 /* reads the early generations of the default cut hold (everything but the last generation) */
-static uint64_t sched_early_reads(uint64_t n, uint32_t *levels_out = nullptr) {
+static uint64_t sched_early_reads(cbcg_ctx *ctx, uint64_t n, uint32_t *levels_out = nullptr) {
     uint32_t c[CBCG_GEN_MAX], r[CBCG_GEN_MAX], last = 0;
-    const uint32_t k = cbcg_gen_schedule(n, c, r, &last);
+    const uint32_t k = cbcg_gen_schedule(n, ctx->n_sub, c, r, &last);
     uint64_t early = 0;
     for (uint32_t g = 0; g < k; g++) early += (uint64_t)c[g] * r[g];
     if (levels_out) *levels_out = k;
@@ -585,6 +597,7 @@ static CoderParams coder_params(cbcg_ctx *ctx, uint32_t n_blocks, uint32_t L, in
     p.chr_names = ctx->g_names.as<uint8_t>();
     p.err = wptr<unsigned long long>(ctx, W_OFF(err));
     p.fin = ctx->fin.as<uint8_t>();                         /* callers ensure_fin(nb) before a blocked launch */
+    p.n_sub = legacy ? 1u : ctx->n_sub;
     return p;
 }
 
@@ -592,6 +605,7 @@ static int validate_opts(cbcg_ctx *ctx, const cbcg_encode_opts *o) {
     if (!o) return fail(ctx, CBCG_ERR_ARG, "NULL options");
     if (o->read_len_header == 0 || o->read_len_header > CBCG_MAX_READ_LEN) return fail(ctx, CBCG_ERR_ARG, "read_len_header must be in 1..%u", CBCG_MAX_READ_LEN);
     if (o->gen_mode > 1) return fail(ctx, CBCG_ERR_ARG, "gen_mode %u is not supported by this build", o->gen_mode);
+    if (o->substreams != 0 && o->substreams != 1 && o->substreams != CBCG_N_SUB) return fail(ctx, CBCG_ERR_ARG, "substreams must be 0, 1 or %u", CBCG_N_SUB);
     return 0;
 }
 
@@ -605,9 +619,10 @@ static void finish_encode(cbcg_ctx *ctx, const cbcg_encode_opts *opts, int legac
     h.clear();
     uint64_t n_syms = 0;
     for (uint64_t k = 0; k < nb; k++) n_syms += ctx->hblocks[k].n_symbols;
-    if (!legacy) container_head(h, ctx->db.max_len, L, n, nb, ctx->names, opts->block_reads, opts->gen_mode | (fixed ? CBCG_MODE_FIXED_LEN : 0u), ctx->hblocks);
+    const uint32_t n_sub = opts->substreams == CBCG_N_SUB ? CBCG_N_SUB : 1u;
+    if (!legacy) container_head(h, ctx->db.max_len, L, n, nb, ctx->names, opts->block_reads, opts->gen_mode | (fixed ? CBCG_MODE_FIXED_LEN : 0u) | (n_sub > 1u ? CBCG_MODE_SPLIT4 : 0u), ctx->hblocks);
     ctx->enc_L = L; ctx->enc_block_reads = opts->block_reads; ctx->enc_gen_mode = opts->gen_mode; ctx->enc_legacy = legacy;
-    ctx->enc_max_len = ctx->db.max_len; ctx->enc_fixed = fixed ? 1u : 0u;
+    ctx->enc_max_len = ctx->db.max_len; ctx->enc_fixed = fixed ? 1u : 0u; ctx->enc_n_sub = legacy ? 1u : n_sub;
     ctx->enc_n_reads = n; ctx->enc_n_edits = n_edits; ctx->enc_n_blocks = nb; ctx->enc_payload_bytes = payload_total;
     ctx->have_encoded = true;
     S.n_reads = n; S.n_blocks = nb; S.n_edits = n_edits; S.n_symbols = n_syms;
@@ -628,7 +643,7 @@ static int encode_resident_overlapped(cbcg_ctx *ctx, const cbcg_encode_opts *opt
     const uint32_t L = opts->read_len_header;
     const uint64_t tile = 128;                              /* K1 tile */
     uint32_t levels = 0;
-    const uint64_t early = sched_early_reads(n, &levels);
+    const uint64_t early = sched_early_reads(ctx, n, &levels);
     const uint64_t head_end = ((early + tile - 1) / tile + 1) * tile;   /* + one tile: the record after the last early block exists */
     if (n < 4 * head_end) return PIPE_FALLBACK;
     TRY(pipe_init(ctx));
@@ -697,7 +712,7 @@ static int encode_resident_overlapped(cbcg_ctx *ctx, const cbcg_encode_opts *opt
     q.snap = snap;
     if (launch_coder(q, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaEventRecord(ctx->ev[3], ctx->st));
-    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), 1, ctx->st))
+    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->n_sub > 1u ? 1 : 0, ctx->st))
         return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
     S.kernel_launches += 7;                                 /* K1 x 2, plan x 2, last generation, gather x 2 */
     CU(cudaEventRecord(ctx->ev[4], ctx->st));
@@ -734,6 +749,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     const uint64_t n = ctx->db.n_reads;
     const int legacy = opts->block_reads == 0;
     const uint32_t L = opts->read_len_header;
+    ctx->n_sub = (!legacy && opts->substreams == CBCG_N_SUB) ? CBCG_N_SUB : 1u;
     cbcg_encode_opts auto_opts = *opts;
     if (opts->block_reads == CBCG_BLOCK_AUTO) {             /* last generation = a whole number of full waves */
         auto_opts.block_reads = auto_block_reads(ctx, n, opts->gen_mode);
@@ -784,7 +800,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
         CU(cudaEventRecord(ctx->ev[3], ctx->st));
         /* compact payload: bounded by the scratch size */
         TRY(ensure(ctx, ctx->payload, pay_cap));
-        if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), legacy ? 0 : 1, ctx->st))
+        if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), (!legacy && ctx->n_sub > 1u) ? 1 : 0, ctx->st))
             return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
         S.kernel_launches += 3;
         CU(cudaEventRecord(ctx->ev[4], ctx->st));
@@ -916,10 +932,11 @@ static void pipe_drain(cbcg_ctx *ctx) {
 }
 static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encode_opts *opts) {
     const uint64_t n = b->n_reads;
+    ctx->n_sub = opts->substreams == CBCG_N_SUB ? CBCG_N_SUB : 1u;
     const uint32_t L = opts->read_len_header;
     const uint64_t tile = 128;                              /* K1 tile: chunk boundaries are whole tiles */
     uint32_t levels = 0;
-    const uint64_t early = sched_early_reads(n, &levels);
+    const uint64_t early = sched_early_reads(ctx, n, &levels);
     if (n < early + tile * (PIPE_CHUNKS + 1)) return PIPE_FALLBACK;
     if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");   /* before any copy is queued */
     TRY(pipe_init(ctx));
@@ -1058,7 +1075,7 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
         }
     }
     for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) if (gb[c] > gb[c - 1]) CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[c], 0));
-    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), 1, ctx->st))
+    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->n_sub > 1u ? 1 : 0, ctx->st))
         return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
     S.kernel_launches += 2;
     CU(cudaEventRecord(ctx->ev[4], ctx->st));
@@ -1122,6 +1139,7 @@ extern "C" int cbcg_extract_symbols(cbcg_ctx *ctx, const cbcg_batch *batch, cons
     TRY(cbcg_batch_upload(ctx, batch));
     const uint64_t n = ctx->db.n_reads;
     const int legacy = opts->block_reads == 0;
+    ctx->n_sub = (!legacy && opts->substreams == CBCG_N_SUB) ? CBCG_N_SUB : 1u;
     *n_symbols = 0; if (n_blocks) *n_blocks = 0;
     uint64_t n_edits = 0, nb = 0;
     if (n) { TRY(run_extract(ctx)); n_edits = ctx->hw->total_edits; }
@@ -1165,7 +1183,7 @@ extern "C" int cbcg_extract_symbols(cbcg_ctx *ctx, const cbcg_batch *batch, cons
 
 /* ------------------------------------------------------------------------------------------------ decode */
 struct Container {
-    uint32_t max_len, L, n_blocks, n_chr, block_reads, gen_mode, fixed_len;
+    uint32_t max_len, L, n_blocks, n_chr, block_reads, gen_mode, fixed_len, n_sub;
     uint64_t n_reads;
     uint64_t index_off, index_bytes, payload_off;
     std::vector<uint32_t> chr_map;             /* container ordinal -> genome ordinal */
@@ -1179,7 +1197,8 @@ static int parse_container(const uint8_t *in, uint64_t len, const std::vector<st
     c.n_blocks = rd32(in + 24); c.n_chr = rd32(in + 28); c.block_reads = rd32(in + 32);
     const uint32_t mode = rd32(in + 36);
     c.gen_mode = mode & CBCG_MODE_GEN_MASK; c.fixed_len = (mode & CBCG_MODE_FIXED_LEN) ? 1u : 0u;
-    if ((mode & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_FIXED_LEN)) || (c.fixed_len && c.max_len != c.L)) return CBCG_ERR_FORMAT;
+    c.n_sub = (mode & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u;
+    if ((mode & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_FIXED_LEN | CBCG_MODE_SPLIT4)) || (c.fixed_len && c.max_len != c.L)) return CBCG_ERR_FORMAT;
     if (c.L == 0 || c.L > CBCG_MAX_READ_LEN || c.max_len > CBCG_MAX_READ_LEN || c.n_chr > MAX_CHR || c.gen_mode > 1) return CBCG_ERR_FORMAT;
     if (c.n_reads >= 0xfffffff0ull) return CBCG_ERR_FORMAT;
     uint64_t o = 40;
@@ -1284,7 +1303,7 @@ static int blocks_from_index(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
     uint32_t prev_gen = 0;
     for (uint32_t k = 0; k < c.n_blocks; k++) {
         BlockDesc &b = ctx->hblocks[k];
-        if (!index_get(in, c.index_off + c.index_bytes, o, st, b)) return fail(ctx, CBCG_ERR_FORMAT, "block index entry %u malformed", k);
+        if (!index_get(in, c.index_off + c.index_bytes, o, st, b, c.n_sub)) return fail(ctx, CBCG_ERR_FORMAT, "block index entry %u malformed", k);
         const uint32_t chr = b.chr;
         if (chr >= c.n_chr) return fail(ctx, CBCG_ERR_FORMAT, "block %u names chromosome %u of %u", k, chr, c.n_chr);
         if (c.chr_map[chr] == 0xffffffffu) return fail(ctx, CBCG_ERR_NO_REFERENCE, "block %u: chromosome not in the loaded reference", k);
@@ -1317,6 +1336,7 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
         int rc = parse_container(in, in_len, &ctx->names, c);
         if (rc) return fail(ctx, rc, "malformed container header");
         uint64_t nr = 0, ne = 0, pb = 0;
+        ctx->n_sub = c.n_sub;
         TRY(blocks_from_index(ctx, in, in_len, c, &nr, &ne, &pb));
         *max_len = c.max_len ? c.max_len : 1;
         *fixed_len = c.fixed_len ? c.L : 0u;
@@ -1376,6 +1396,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
     cbcg_stats &S = ctx->stats;
     S = cbcg_stats();
     uint64_t nr = 0, ne = 0, pb = 0;
+    ctx->n_sub = c.n_sub;
     TRY(blocks_from_index(ctx, in, in_len, c, &nr, &ne, &pb));
     if (ctx->gens.size() < 2) return PIPE_FALLBACK;
     const uint32_t nb = c.n_blocks;
@@ -1586,6 +1607,7 @@ extern "C" int cbcg_decode_resident(cbcg_ctx *ctx) {
     const uint64_t nb = ctx->enc_n_blocks;
     if (!nb) { ctx->dec_bytes = 0; ctx->dec_n_reads = 0; ctx->have_decoded = true; return CBCG_OK; }
     const int legacy = (int)ctx->enc_legacy;
+    ctx->n_sub = ctx->enc_n_sub;
     /* hblocks still hold the encoder's descriptors (n_reads, chr, base_pos, n_edits, payload_bytes); the compact
        payload is in ctx->payload in block order. */
     uint64_t nr = 0, ne = 0;

@@ -9,8 +9,9 @@
  *       zigzag(n_reads - previous n_reads) << 2 | chromosome changed << 1 | generation changed
  *       [chromosome ordinal]  [generation increment - 1]
  *       zigzag(second difference of base_pos)  zigzag(difference of n_edits)
- *       four times zigzag(difference of the substream's byte count against the previous block's same substream)
- *   payload: per block its substreams A | B | C | D back to back
+ *       per substream (four with CBCG_MODE_SPLIT4 in `mode`, else one) zigzag(difference of its byte count against the
+ *       previous block's same substream)
+ *   payload: per block its substreams (A | B | C | D, or the one stream) back to back
  */
 #pragma once
 #include <stdint.h>
@@ -31,7 +32,7 @@ static inline void put_varint(std::vector<uint8_t> &v, uint64_t x) {
 }
 static inline uint64_t zz(int64_t v) { return ((uint64_t)v << 1) ^ (uint64_t)(v >> 63); }
 static inline int64_t unzz(uint64_t v) { return (int64_t)(v >> 1) ^ -(int64_t)(v & 1); }
-static inline void index_put(std::vector<uint8_t> &out, IndexState &st, const BlockDesc &b) {
+static inline void index_put(std::vector<uint8_t> &out, IndexState &st, const BlockDesc &b, uint32_t n_sub) {
     const bool chr_ch = (int64_t)b.chr != st.chr, gen_ch = (int64_t)b.gen != st.gen;
     put_varint(out, (zz((int64_t)b.n_reads - st.n_reads) << 2) | (chr_ch ? 2u : 0u) | (gen_ch ? 1u : 0u));
     if (chr_ch) { put_varint(out, b.chr); st.base = 0; st.d1 = 0; }
@@ -39,7 +40,7 @@ static inline void index_put(std::vector<uint8_t> &out, IndexState &st, const Bl
     const int64_t d1 = (int64_t)b.base_pos - st.base;
     put_varint(out, zz(d1 - st.d1));
     put_varint(out, zz((int64_t)b.n_edits - st.edits));
-    for (uint32_t k = 0; k < CBCG_N_SUB; k++) { put_varint(out, zz((int64_t)b.sub_bytes[k] - st.sub[k])); st.sub[k] = b.sub_bytes[k]; }
+    for (uint32_t k = 0; k < n_sub; k++) { put_varint(out, zz((int64_t)b.sub_bytes[k] - st.sub[k])); st.sub[k] = b.sub_bytes[k]; }
     st.n_reads = b.n_reads; st.chr = b.chr; st.gen = b.gen; st.base = b.base_pos; st.d1 = d1; st.edits = b.n_edits;
 }
 static inline bool get_varint(const uint8_t *p, uint64_t end, uint64_t &o, uint64_t &v) {
@@ -52,7 +53,7 @@ static inline bool get_varint(const uint8_t *p, uint64_t end, uint64_t &o, uint6
     }
     v = r; return true;
 }
-static inline bool index_get(const uint8_t *p, uint64_t end, uint64_t &o, IndexState &st, BlockDesc &b) {
+static inline bool index_get(const uint8_t *p, uint64_t end, uint64_t &o, IndexState &st, BlockDesc &b, uint32_t n_sub) {
     uint64_t v;
     if (!get_varint(p, end, o, v)) return false;
     st.n_reads += unzz(v >> 2);
@@ -63,7 +64,7 @@ static inline bool index_get(const uint8_t *p, uint64_t end, uint64_t &o, IndexS
     if (!get_varint(p, end, o, v)) return false;
     st.edits += unzz(v);
     int64_t total = 0;
-    for (uint32_t k = 0; k < CBCG_N_SUB; k++) {
+    for (uint32_t k = 0; k < n_sub; k++) {
         if (!get_varint(p, end, o, v)) return false;
         st.sub[k] += unzz(v);
         if (st.sub[k] < 0 || st.sub[k] > 0x3fffffffll) return false;
@@ -75,7 +76,7 @@ static inline bool index_get(const uint8_t *p, uint64_t end, uint64_t &o, IndexS
     memset(&b, 0, sizeof b);
     b.n_reads = (uint32_t)st.n_reads; b.chr = (uint32_t)st.chr; b.gen = (uint32_t)st.gen; b.base_pos = (uint32_t)st.base;
     b.n_edits = (uint32_t)st.edits; b.payload_bytes = (uint32_t)total;
-    for (uint32_t k = 0; k < CBCG_N_SUB; k++) b.sub_bytes[k] = (uint32_t)st.sub[k];
+    for (uint32_t k = 0; k < n_sub; k++) b.sub_bytes[k] = (uint32_t)st.sub[k];
     return true;
 }
 
@@ -92,7 +93,8 @@ static inline void container_head(std::vector<uint8_t> &h, uint32_t max_len, uin
     }
     std::vector<uint8_t> ix;
     IndexState st = index_state(block_reads);
-    for (uint64_t k = 0; k < nb; k++) index_put(ix, st, hb[k]);
+    const uint32_t n_sub = (mode & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u;
+    for (uint64_t k = 0; k < nb; k++) index_put(ix, st, hb[k], n_sub);
     put32(h, (uint32_t)ix.size());
     h.insert(h.end(), ix.begin(), ix.end());
 }

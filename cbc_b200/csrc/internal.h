@@ -74,7 +74,7 @@ struct CoderParams {
     uint32_t short_flush;                  /* blocked containers: 1 + scale3 closing bits instead of the reference's 26+ */
     uint32_t primed;                       /* gen_mode 1: models start from `snap` instead of the initial state */
     uint32_t fixed_len;                    /* CBCG_MODE_FIXED_LEN: every read is L bases, the length symbol is not coded */
-    uint32_t pad;
+    uint32_t n_sub;                        /* blocked containers: 1 (one stream per block) or CBCG_N_SUB (CBCG_MODE_SPLIT4) */
     const uint8_t *snap;                   /* snapshot S_{g-1} (snapshot_bytes(L) bytes); blocked containers always start from one */
     uint8_t *fin;                          /* per block (absolute index): its image of the small models (WarpModels), read by the merges */
 };

@@ -50,7 +50,7 @@ uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, ui
     return 2u * b + 4096u;                                   /* direct blocks use <= 2 x their hashed size */
 }
 uint64_t coder_payload_bound(uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy) {
-    return payload_cap_bytes(n_reads, n_edits, legacy) + n_blocks * 512u;   /* per block: four substream regions, each with its own slack and alignment */
+    return payload_cap_bytes(n_reads, n_edits, legacy ? 2 : 0) + n_blocks * 512u;   /* per block: four substream regions, each with its own slack and alignment */
 }
 uint64_t snapshot_bytes(uint32_t L) { return snap_layout(L).total; }
 uint64_t fin_stride_bytes(void) { return (sizeof(WarpModels) + 15u) & ~15ull; }
@@ -774,7 +774,7 @@ k2_coder_kernel(CoderParams P) {
     Coder<MODE> C;
     C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &sshared[warp].m; C.coldp = &sshared[warp].c;
     C.primed = primed; C.lean = lean;
-    C.var_defer = primed && P.fin == nullptr; C.var_ro = false; C.defer_idx = 0; C.defer_key = 0;
+    C.var_defer = primed; C.var_ro = false; C.defer_idx = 0; C.defer_key = 0;   /* merge_add adds a deferred slot's one update */
     if (primed) C.snap = SnapView(P.snap, P.L);
     C.L = P.L; C.Lp = (P.L + 1u + 31u) & ~31u;
     /* workspace */
@@ -792,7 +792,7 @@ k2_coder_kernel(CoderParams P) {
             WarpCold &W = C.cold();
             W.pos_cap = w.pos_cap; W.rows_cap = w.rows_cap;
             W.io = P.payload + B.payload_off;
-            W.io_cap = (MODE == MODE_DEC) ? B.payload_bytes : (uint32_t)payload_cap_bytes(B.n_reads, B.n_edits, legacy);
+            W.io_cap = (MODE == MODE_DEC) ? B.payload_bytes : (uint32_t)payload_cap_bytes(B.n_reads, B.n_edits, legacy ? 2 : 1);
             W.ref = nullptr; W.ref_len = 0;
             if (!legacy && B.chr < P.genome.n_chr) { W.ref = P.genome.bases + P.genome.chr_off[B.chr]; W.ref_len = P.genome.chr_len[B.chr]; }
             W.edits_cap_abs = B.edit_base + B.n_edits;
@@ -1179,7 +1179,7 @@ M_DONE:
     if (C.err) dev_set_error(P.err, C.err, ((uint64_t)b << 20) | (n_done & 0xfffffu));
     if (primed && P.fin && !C.err) {                     /* final state for the generation merge */
         SYNCW();
-        uint32_t *dst = reinterpret_cast<uint32_t *>(P.fin + (uint64_t)bl * fin_stride_dev());
+        uint32_t *dst = reinterpret_cast<uint32_t *>(P.fin + (uint64_t)b * fin_stride_dev());
         const uint32_t *src = reinterpret_cast<const uint32_t *>(C.M);
         for (uint32_t q = lane; q < (uint32_t)(sizeof(WarpModels) / 4u); q += 32u) dst[q] = src[q];
         if (lane < C.pos_card) { C.pos_gval()[lane] = C.pos_rv; C.pos_gcnt()[lane] = C.pos_rc; }
@@ -1190,7 +1190,7 @@ M_DONE:
 #endif
     if (lane == 0) {
         B.n_symbols = (MODE == MODE_LIST) ? C.list_n : C.n_symbols;
-        if (MODE == MODE_ENC) B.payload_bytes = C.out_pos;
+        if (MODE == MODE_ENC) { B.payload_bytes = C.out_pos; B.sub_bytes[0] = C.out_pos; }
         if (MODE == MODE_DEC) { B.n_reads = n_done; B.n_edits = (uint32_t)(e_cursor - B.edit_base); B.pad = decode_L; }
     }
 }
@@ -1539,7 +1539,7 @@ int launch_block_kernel(const CoderParams &p, cudaStream_t st) {
 uint32_t coder_resident_blocks(int device) {
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) return 148u * 16u;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_coder_kernel<MODE_ENC, true>, (int)K2_THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = K2_MIN_CTAS;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_coder_kernel<MODE_ENC, false>, (int)K2_THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = K2_MIN_CTAS;
     return (uint32_t)sms * (uint32_t)per_sm * K2_WARPS;
 }
 
@@ -1570,7 +1570,8 @@ void set_carveout_all(int pct) {
     if (e) pct = atoi(e);
     if (pct == current) return;
     current = pct;
-    set_carveout(k2_coder_kernel<MODE_LIST, false>, pct); set_carveout(k2_block_kernel<MODE_ENC>, pct); set_carveout(k2_block_kernel<MODE_DEC>, pct);
+    set_carveout(k2_coder_kernel<MODE_ENC, false>, pct); set_carveout(k2_coder_kernel<MODE_DEC, false>, pct); set_carveout(k2_coder_kernel<MODE_LIST, false>, pct);
+    set_carveout(k2_block_kernel<MODE_ENC>, pct); set_carveout(k2_block_kernel<MODE_DEC>, pct);
     set_carveout(k2_coder_kernel<MODE_ENC, true>, pct); set_carveout(k2_coder_kernel<MODE_DEC, true>, pct); set_carveout(k2_coder_kernel<MODE_LIST, true>, pct);
     set_carveout(k2_plan_kernel, pct); set_carveout(k2_payload_scan_kernel, pct); set_carveout(k2_gather_kernel, pct);
     set_carveout(snapshot_copy_kernel, pct);
@@ -1581,7 +1582,7 @@ void set_carveout_all(int pct) {
 int launch_block_kernel(const CoderParams &p, cudaStream_t st);
 int launch_coder(const CoderParams &p, cudaStream_t st) {
     if (p.n_blocks == 0) return 0;
-    if (!p.legacy && p.mode != MODE_LIST) {                 /* blocked containers: a CTA per block, a warp per substream */
+    if (!p.legacy && p.mode != MODE_LIST && p.n_sub > 1u) { /* four-substream containers: a CTA per block, a warp per substream */
         static const bool scalar = getenv("CBCG_SCALAR_ROLES") != nullptr;   /* cross-check: the scalar twin (k2_blocks.cu) */
         return scalar ? launch_roles(p, st) : launch_block_kernel(p, st);
     }
@@ -1591,7 +1592,9 @@ int launch_coder(const CoderParams &p, cudaStream_t st) {
         else if (p.mode == MODE_DEC) k2_coder_kernel<MODE_DEC, true><<<grid, K2_THREADS, 0, st>>>(p);
         else k2_coder_kernel<MODE_LIST, true><<<grid, K2_THREADS, 0, st>>>(p);
     } else {
-        k2_coder_kernel<MODE_LIST, false><<<grid, K2_THREADS, 0, st>>>(p);
+        if (p.mode == MODE_ENC) k2_coder_kernel<MODE_ENC, false><<<grid, K2_THREADS, 0, st>>>(p);
+        else if (p.mode == MODE_DEC) k2_coder_kernel<MODE_DEC, false><<<grid, K2_THREADS, 0, st>>>(p);
+        else k2_coder_kernel<MODE_LIST, false><<<grid, K2_THREADS, 0, st>>>(p);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1629,7 +1632,7 @@ k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, ui
             }
             const uint64_t ws_edits = (dec && P.legacy) ? 0xffffffffull : d.n_edits;
             v[0] = ws_layout(P.L ? P.L : 252u, d.n_reads, ws_edits, P.legacy, P.primed && P.mode != MODE_LIST).total;
-            v[1] = dec ? d.payload_bytes : payload_cap_bytes(d.n_reads, d.n_edits, P.legacy);
+            v[1] = dec ? d.payload_bytes : payload_cap_bytes(d.n_reads, d.n_edits, P.legacy ? 2 : (P.n_sub <= 1u ? 1 : 0));
             v[2] = (P.mode == MODE_LIST) ? symlist_cap(d.n_reads, d.n_edits, P.legacy) : 0;
             v[3] = d.n_reads; v[4] = d.n_edits;
         }
@@ -1655,7 +1658,7 @@ k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, ui
             if (!dec) d.payload_off = off[1];
             else { d.payload_off = off[1]; d.first_read = (uint32_t)off[3]; d.edit_base = off[4]; }
             d.sym_off = off[2];
-            if (!P.legacy && P.mode != MODE_LIST) {              /* the substream roles add their symbol counts */
+            if (!P.legacy && P.mode != MODE_LIST && P.n_sub > 1u) {   /* the substream roles add their symbol counts */
                 d.n_symbols = 0; d.pos_card = 0; d.n_rows = 0; d.pa_touched = 0;
                 if (!dec) { d.payload_bytes = 0; for (uint32_t q = 0; q < CBCG_N_SUB; q++) d.sub_bytes[q] = 0; }
             }

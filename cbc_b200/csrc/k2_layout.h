@@ -78,10 +78,11 @@ K2_HD uint64_t k2_sub_cap(uint32_t q, uint64_t n_reads, uint64_t n_edits) {
     const uint64_t syms = q == CBCG_SUB_POS ? 5u * n_reads : q == CBCG_SUB_FLAG ? 2u * n_reads : q == CBCG_SUB_COUNTS ? 5u * n_reads : 2u * n_edits;
     return ((syms * 20u) / 8u + 64u + 15u) & ~15ull;
 }
-K2_HD uint64_t payload_cap_bytes(uint64_t n_reads, uint64_t n_edits, int legacy) {
-    if (!legacy) return k2_sub_cap(0, n_reads, n_edits) + k2_sub_cap(1, n_reads, n_edits) + k2_sub_cap(2, n_reads, n_edits) + k2_sub_cap(3, n_reads, n_edits);
-    /* <= 16 symbols per read + 2 per edit + header / names, <= 20 bits each */
-    uint64_t syms = 16u * n_reads + 2u * n_edits + 136u + 4096u + 8u;
+/* Room for a block's coded bytes (encoder). layout 0: four substream regions; 1: one stream per block (<= 12 symbols
+ * per read + 2 per edit, <= 20 bits each); 2: the reference's own stream (+ header ints and names). */
+K2_HD uint64_t payload_cap_bytes(uint64_t n_reads, uint64_t n_edits, int layout) {
+    if (layout == 0) return k2_sub_cap(0, n_reads, n_edits) + k2_sub_cap(1, n_reads, n_edits) + k2_sub_cap(2, n_reads, n_edits) + k2_sub_cap(3, n_reads, n_edits);
+    const uint64_t syms = (layout == 2 ? 16u : 12u) * n_reads + 2u * n_edits + (layout == 2 ? 136u + 4096u : 0u) + 8u;
     return ((syms * 20u) / 8u + 64u + 15u) & ~15ull;
 }
 K2_HD uint64_t symlist_cap(uint64_t n_reads, uint64_t n_edits, int legacy) {

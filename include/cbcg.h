@@ -69,7 +69,8 @@ typedef struct cbcg_encode_opts {
                                    `program -c 1` built with -DDEBUG): the verification mode */
     uint32_t gen_mode;          /* 0: every block starts from the reference's initial model state;
                                    1: generation-primed blocks */
-    uint32_t reserved;
+    uint32_t substreams;        /* blocked containers: 0 / 1: one arithmetic-coded stream per block (every symbol of a read in
+                                   the reference's order); 4: four substreams per block (CBCG_MODE_SPLIT4, cbcg_format.h) */
 } cbcg_encode_opts;
 
 /* Per-call device timings (CUDA events on the library's stream), for bench.py / profiling. */

@@ -114,6 +114,10 @@ static inline uint32_t cbcg_substream_of(uint32_t stream) {
  * (src/read_compression.c:29-33, one zero-information coder step per read) is not coded either */
 #define CBCG_MODE_GEN_MASK  0xffu
 #define CBCG_MODE_FIXED_LEN 0x100u
+/* bit 9: every block holds the four substreams above, and its index entry four byte counts; clear: ONE arithmetic-coded
+ * stream per block with every symbol of a read in the reference's own order (src/read_compression.c:15-44), one byte
+ * count. Same models, same symbols either way. */
+#define CBCG_MODE_SPLIT4    0x200u
 
 /* The FLAG model spends 65 536 / n of its probability on values never seen (src/sam_models.c:96-130: all-ones initial
  * state), so what a FLAG symbol costs depends on where the model total n stands below the rescale threshold 2^20
@@ -132,7 +136,7 @@ static inline uint32_t cbcg_flag_target(uint32_t max_block_reads) {
  *
  * cbcg_gen_schedule: the default cut for a shard of n reads (constants measured with the CPU restatement on the named
  * shapes, profiles/r02_notes.md). What blocking costs against the reference's single stream:
- *   - 10.6 bytes per block (7.9 of index, 2.7 of closing bits for its four substreams);
+ *   - 10.6 bytes per block with four substreams (7.9 of index, 2.7 of closing bits), 5.4 with one (4.7 + 0.7);
  *   - the `var` model (65 535 sparse contexts) keeps learning for millions of reads: a generation that codes the reads
  *     (C, rC] from a snapshot frozen at C reads loses about kappa ((r - 1) - ln r) bytes against a model that keeps
  *     adapting, kappa ~ 2 200 .. 3 400 (every other model is trained after a few thousand reads).
@@ -165,16 +169,20 @@ static inline double cbcg_root(double x, uint32_t k) {                      /* x
     }
     return 0.5 * (lo + hi);
 }
-static inline uint32_t cbcg_gen_schedule(uint64_t n, uint32_t *count, uint32_t *reads, uint32_t *last_reads) {
+static inline uint32_t cbcg_gen_schedule(uint64_t n, uint32_t n_sub, uint32_t *count, uint32_t *reads, uint32_t *last_reads) {
     uint64_t cum[CBCG_GEN_MAX + 1];
     uint32_t ne = 0;
     for (uint64_t c = 256; ne < 6 && c * 2 <= n; c *= 4) cum[ne++] = c;      /* 256 .. 262 144 */
     if (!ne) { *last_reads = n > 64 ? (uint32_t)(n > 8192 ? 8192 : n) : 64u; return 0; }
-    const double S = 1.66 * (double)n, room = 0.0093 * S, per_block = 10.6, kappa = 3400.0, early_loss = 5000.0;
+    /* kappa grows with the input (the var model keeps discovering contexts): 2 200 measured at 3 M reads, 3 400 at 6 M */
+    double kappa = 2800.0;                                                       /* ... and no smaller below 3 M */
+    { double x = (double)n / 3.0e6, f = 1.0; while (x >= 2.0) { x *= 0.5; f *= 1.516; } if (x > 1.0) f *= 1.0 + 0.516 * (x - 1.0); kappa *= f; }
+    const double S = 1.66 * (double)n, room = 0.0092 * S, per_block = n_sub > 1u ? 10.6 : 5.4, early_loss = n < 2000000u ? 6000.0 : 3000.0;
     const double c0 = (double)cum[ne - 1];
     uint32_t best_k = 1; double best_depth = 0.0, best_blocks = 16.0;
     for (uint32_t k = 1; k <= 6 && ne + k - 1 <= CBCG_GEN_MAX; k++) {
         const double r = cbcg_root((double)n / c0, k);
+        if (r > 4.0 && k < 6) continue;                                          /* a frozen snapshot coding more than 4x its training costs more than the model says */
         const double loss = early_loss + kappa * (double)k * ((r - 1.0) - cbcg_ln(r));
         double blocks = (room - loss) / per_block;
         if (blocks < 16.0) blocks = 16.0;
@@ -182,7 +190,7 @@ static inline uint32_t cbcg_gen_schedule(uint64_t n, uint32_t *count, uint32_t *
         for (uint32_t g = 0; g < ne; g++) { sum_sqrt += (double)cbcg_isqrt(cum[g] - (uint64_t)c); c = (double)cum[g]; }
         for (uint32_t j = 1; j <= k; j++) { const double nx = j == k ? (double)n : c * r; sum_sqrt += (double)cbcg_isqrt((uint64_t)(nx - c)); c = nx; }
         const double depth = sum_sqrt * sum_sqrt / blocks;
-        if (k == 1 || depth < best_depth) { best_depth = depth; best_k = k; best_blocks = blocks; }
+        if (best_depth == 0.0 || depth < best_depth) { best_depth = depth; best_k = k; best_blocks = blocks; }
         if (r < 2.0) break;
     }
     {                                                                            /* the late generations but the last */

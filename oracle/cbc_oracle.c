@@ -1007,7 +1007,7 @@ static int get_varint(const uint8_t *p, uint64_t len, uint64_t *o, uint64_t *v) 
     *v = r; return 0;
 }
 typedef struct { int64_t n_reads, chr, gen, base, d1, edits, sub[CBCG_N_SUB]; } idx_state;
-static void index_put(cbco_buf *b, idx_state *st, const blk_index *e) {
+static void index_put(cbco_buf *b, idx_state *st, const blk_index *e, uint32_t n_sub) {
     int chr_ch = (int64_t)e->chr != st->chr, gen_ch = (int64_t)e->gen != st->gen;
     put_varint(b, (zigzag((int64_t)e->n_reads - st->n_reads) << 2) | (chr_ch ? 2u : 0u) | (gen_ch ? 1u : 0u));
     if (chr_ch) { put_varint(b, e->chr); st->base = 0; st->d1 = 0; }
@@ -1015,11 +1015,11 @@ static void index_put(cbco_buf *b, idx_state *st, const blk_index *e) {
     int64_t d1 = (int64_t)e->base_pos - st->base;
     put_varint(b, zigzag(d1 - st->d1));
     put_varint(b, zigzag((int64_t)e->n_edits - st->edits));
-    for (uint32_t k = 0; k < CBCG_N_SUB; k++) { put_varint(b, zigzag((int64_t)e->sub_bytes[k] - st->sub[k])); st->sub[k] = e->sub_bytes[k]; }
+    for (uint32_t k = 0; k < n_sub; k++) { put_varint(b, zigzag((int64_t)e->sub_bytes[k] - st->sub[k])); st->sub[k] = e->sub_bytes[k]; }
     st->n_reads = e->n_reads; st->chr = e->chr; st->gen = e->gen; st->base = e->base_pos; st->d1 = d1;
     st->edits = e->n_edits;
 }
-static int index_get(const uint8_t *p, uint64_t len, uint64_t *o, idx_state *st, blk_index *e) {
+static int index_get(const uint8_t *p, uint64_t len, uint64_t *o, idx_state *st, blk_index *e, uint32_t n_sub) {
     uint64_t v;
     if (get_varint(p, len, o, &v)) return -1;
     st->n_reads += unzigzag(v >> 2);
@@ -1030,7 +1030,7 @@ static int index_get(const uint8_t *p, uint64_t len, uint64_t *o, idx_state *st,
     if (get_varint(p, len, o, &v)) return -1;
     st->edits += unzigzag(v);
     int64_t total = 0;
-    for (uint32_t k = 0; k < CBCG_N_SUB; k++) {
+    for (uint32_t k = 0; k < n_sub; k++) {
         if (get_varint(p, len, o, &v)) return -1;
         st->sub[k] += unzigzag(v);
         if (st->sub[k] < 0 || st->sub[k] > 0x3fffffffll) return -1;
@@ -1041,7 +1041,7 @@ static int index_get(const uint8_t *p, uint64_t len, uint64_t *o, idx_state *st,
     memset(e, 0, sizeof *e);
     e->n_reads = (uint32_t)st->n_reads; e->chr = (uint32_t)st->chr; e->gen = (uint32_t)st->gen; e->base_pos = (uint32_t)st->base;
     e->n_edits = (uint32_t)st->edits; e->payload_bytes = (uint32_t)total;
-    for (uint32_t k = 0; k < CBCG_N_SUB; k++) e->sub_bytes[k] = (uint32_t)st->sub[k];
+    for (uint32_t k = 0; k < n_sub; k++) e->sub_bytes[k] = (uint32_t)st->sub[k];
     return 0;
 }
 
@@ -1060,7 +1060,7 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
 
 int cbco_encode_scheduled(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads,
                           uint32_t n_sched, const uint32_t *sched_count, const uint32_t *sched_reads, cbco_buf *out) {
-    return encode_cut(b, g, L, block_reads, n_sched, sched_count, sched_reads, NULL, 0, n_sched ? 1u : 0u, out);
+    return encode_cut(b, g, L, block_reads & 0x7fffffffu, n_sched, sched_count, sched_reads, NULL, 0, (n_sched ? 1u : 0u) | ((block_reads & 0x80000000u) ? CBCG_MODE_SPLIT4 : 0u), out);   /* experiments: bit 31 of block_reads asks for four substreams */
 }
 
 /* The batch coded with the block cut of an existing container (per-block read counts and generations taken from its
@@ -1082,8 +1082,8 @@ int cbco_encode_like(const uint8_t *p, uint64_t len, const cbco_batch *b, const 
     blk_index *idx = (blk_index *)calloc((size_t)nb + 1, sizeof(blk_index));
     idx_state st = { h[8], 0, 0, 0, 0, 0, { 0, 0, 0, 0 } };
     uint64_t io = o;
-    for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k])) { free(idx); return -43; }
-    int rc = encode_cut(b, g, h[3], h[8], (h[9] & CBCG_MODE_GEN_MASK) ? 1u : 0u, NULL, NULL, idx, nb, h[9] & CBCG_MODE_GEN_MASK, out);
+    for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k], (h[9] & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u)) { free(idx); return -43; }
+    int rc = encode_cut(b, g, h[3], h[8], (h[9] & CBCG_MODE_GEN_MASK) ? 1u : 0u, NULL, NULL, idx, nb, h[9] & (CBCG_MODE_GEN_MASK | CBCG_MODE_SPLIT4), out);
     free(idx);
     return rc;
 }
@@ -1124,6 +1124,7 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
     }
     first[nb] = b->n_reads;
     const uint32_t last_gen = nb ? idx[nb - 1].gen : 0;
+    const uint32_t n_sub = (gen_mode & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u;
     uint32_t max_block = 0;
     for (uint64_t k = 0; k < nb; k++) if (idx[k].n_reads > max_block) max_block = idx[k].n_reads;
     const uint32_t flag_target = cbcg_flag_target(max_block);
@@ -1144,14 +1145,15 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
         s.lean = 1; s.fixed_len = fixed_len;
         uint64_t start = payload.size;
         cbco_buf sub[CBCG_N_SUB]; memset(sub, 0, sizeof sub);
-        s.c.split = 1;
-        for (uint32_t q = 0; q < CBCG_N_SUB; q++) ac_init_enc(&s.c.ac[q], &sub[q]);
+        s.c.split = n_sub > 1u;
+        for (uint32_t q = 0; q < n_sub; q++) ac_init_enc(&s.c.ac[q], &sub[q]);
         s.prev_pos = idx[k].base_pos; s.have_name = 1; s.cur_chr = idx[k].chr;
         snp_reset(&s.snp, g->len[idx[k].chr] + 2048);
         rc = code_range(&s, b, g, recs, edits, first[k], first[k + 1], 0);
-        for (uint32_t q = 0; q < CBCG_N_SUB; q++) {             /* A | B | C | D, each with its own short tail; nothing coded: nothing stored */
-            if (!rc && s.c.sub_syms[q]) ac_flush_short(&s.c.ac[q]);
-            idx[k].sub_bytes[q] = (!rc && s.c.sub_syms[q]) ? (uint32_t)sub[q].size : 0u;
+        for (uint32_t q = 0; q < n_sub; q++) {                   /* A | B | C | D, each with its own short tail; nothing coded: nothing stored */
+            const int any = n_sub == 1u || s.c.sub_syms[q];         /* a single-stream block always closes its stream */
+            if (!rc && any) ac_flush_short(&s.c.ac[q]);
+            idx[k].sub_bytes[q] = (!rc && any) ? (uint32_t)sub[q].size : 0u;
             if (idx[k].sub_bytes[q]) buf_put(&payload, sub[q].data, sub[q].size);
             cbco_buf_free(&sub[q]);
         }
@@ -1171,14 +1173,14 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
         for (uint64_t r = 0; r < b->n_reads; r++) if (b->seq_len[r] > max_len) max_len = b->seq_len[r];
         buf_put_u32(out, CBCG_MAGIC); buf_put_u32(out, CBCG_VERSION); buf_put_u32(out, max_len); buf_put_u32(out, L);
         buf_put_u64(out, b->n_reads); buf_put_u32(out, (uint32_t)nb); buf_put_u32(out, g->n_chr);
-        buf_put_u32(out, block_reads); buf_put_u32(out, gen_mode | (fixed_len ? CBCG_MODE_FIXED_LEN : 0u));
+        buf_put_u32(out, block_reads); buf_put_u32(out, gen_mode | (fixed_len ? CBCG_MODE_FIXED_LEN : 0u));   /* gen_mode: generations | CBCG_MODE_SPLIT4 */
         for (uint32_t c = 0; c < g->n_chr; c++) {
             uint32_t nl = (uint32_t)strlen(g->name[c]), pad = (4 - (nl & 3)) & 3; uint32_t z = 0;
             buf_put_u32(out, nl); buf_put(out, g->name[c], nl); buf_put(out, &z, pad);
         }
         cbco_buf ix = {0};
         idx_state st = { block_reads, 0, 0, 0, 0, 0, { 0, 0, 0, 0 } };
-        for (uint64_t k = 0; k < nb; k++) index_put(&ix, &st, &idx[k]);
+        for (uint64_t k = 0; k < nb; k++) index_put(&ix, &st, &idx[k], n_sub);
         buf_put_u32(out, (uint32_t)ix.size);
         buf_put(out, ix.data, ix.size);
         cbco_buf_free(&ix);
@@ -1192,9 +1194,9 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
 int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads,
                         uint32_t gen_mode, cbco_buf *out) {
     uint32_t count[CBCG_GEN_MAX], reads[CBCG_GEN_MAX], last = 0, levels = 0;
-    if (gen_mode > 1) return -30;
-    if (gen_mode) levels = cbcg_gen_schedule(b->n_reads, count, reads, &last);
-    if (block_reads == 0xffffffffu) block_reads = gen_mode ? last : 1024u;      /* CBCG_BLOCK_AUTO */
+    if ((gen_mode & CBCG_MODE_GEN_MASK) > 1 || (gen_mode & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_SPLIT4))) return -30;   /* low byte: generations; bit 9: four substreams */
+    if (gen_mode & CBCG_MODE_GEN_MASK) levels = cbcg_gen_schedule(b->n_reads, (gen_mode & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u, count, reads, &last);
+    if (block_reads == 0xffffffffu) block_reads = (gen_mode & CBCG_MODE_GEN_MASK) ? last : 1024u;      /* CBCG_BLOCK_AUTO */
     return encode_cut(b, g, L, block_reads, levels, count, reads, NULL, 0, gen_mode, out);
 }
 
@@ -1205,7 +1207,8 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
     uint32_t L = h[3]; uint64_t n_reads; memcpy(&n_reads, p + 16, 8);
     uint32_t nb = h[6], n_chr = h[7], gen_mode = h[9] & CBCG_MODE_GEN_MASK;
     const uint32_t fixed_len = (h[9] & CBCG_MODE_FIXED_LEN) ? L : 0;
-    if (gen_mode > 1 || (h[9] & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_FIXED_LEN)) || n_chr > g->n_chr) return -42;
+    if (gen_mode > 1 || (h[9] & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_FIXED_LEN | CBCG_MODE_SPLIT4)) || n_chr > g->n_chr) return -42;
+    const uint32_t n_sub = (h[9] & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u;
     if (fixed_len && h[2] != L) return -42;
     uint64_t o = 40;
     /* container chromosome ordinal -> genome ordinal, by name */
@@ -1227,7 +1230,7 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
     {
         idx_state st = { h[8], 0, 0, 0, 0, 0, { 0, 0, 0, 0 } };
         uint64_t io = o;
-        for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k])) { free(chr_map); free(idx); return -43; }
+        for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k], n_sub)) { free(chr_map); free(idx); return -43; }
     }
     o += ix_bytes;
     int rc = 0; uint64_t n = 0;
@@ -1249,8 +1252,8 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
         uint32_t chr = chr_map[bi.chr];
         rstate s; rstate_init_from(&s, prev, 2);
         s.lean = 1; s.fixed_len = fixed_len;
-        s.c.split = 1;
-        { uint64_t so = o; for (uint32_t q = 0; q < CBCG_N_SUB; q++) { ac_init_dec(&s.c.ac[q], p + so, bi.sub_bytes[q]); so += bi.sub_bytes[q]; } }
+        s.c.split = n_sub > 1u;
+        { uint64_t so = o; for (uint32_t q = 0; q < n_sub; q++) { ac_init_dec(&s.c.ac[q], p + so, bi.sub_bytes[q]); so += bi.sub_bytes[q]; } }
         s.prev_pos = bi.base_pos;
         snp_reset(&s.snp, g->len[chr] + 2048);
         for (uint32_t r = 0; r < bi.n_reads && !rc; r++) {

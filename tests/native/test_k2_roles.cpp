@@ -151,7 +151,7 @@ int main(int argc, char **argv) {
 
     /* ---- the cut (api.cu cut_blocks): generations on the schedule, never across a chromosome change */
     uint32_t sc[CBCG_GEN_MAX], sr[CBCG_GEN_MAX], last = 0, levels = 0;
-    if (gen_mode) levels = cbcg_gen_schedule(n, sc, sr, &last);
+    if (gen_mode) levels = cbcg_gen_schedule(n, CBCG_N_SUB, sc, sr, &last);
     if (block_reads == 0xffffffffu) block_reads = gen_mode ? last : 1024u;
     std::vector<BlockDesc> hb;
     {
@@ -213,7 +213,7 @@ int main(int argc, char **argv) {
     /* ---- 1. encode, frame, compare with the oracle's container */
     if (run_generations(MODE_ENC)) return 1;
     std::vector<uint8_t> head, cont;
-    container_head(head, max_len, L, n, nb, names, block_reads, gen_mode | (fixed ? CBCG_MODE_FIXED_LEN : 0u), hb.data());
+    container_head(head, max_len, L, n, nb, names, block_reads, gen_mode | CBCG_MODE_SPLIT4 | (fixed ? CBCG_MODE_FIXED_LEN : 0u), hb.data());
     cont = head;
     for (auto &d : hb) {
         uint64_t off = d.payload_off;
@@ -221,8 +221,8 @@ int main(int argc, char **argv) {
         for (uint32_t q = 0; q < CBCG_N_SUB; q++) { cont.insert(cont.end(), scratch.begin() + off, scratch.begin() + off + d.sub_bytes[q]); off += k2_sub_cap(q, d.n_reads, d.n_edits); d.payload_bytes += d.sub_bytes[q]; }
     }
     cbco_buf ref = { 0, 0, 0 };
-    const int orc = gen_mode ? cbco_encode_blocked(&ob, &og, L, argc > 10 ? block_reads : 0xffffffffu, gen_mode, &ref)
-                             : cbco_encode_blocked(&ob, &og, L, block_reads, 0, &ref);
+    const int orc = gen_mode ? cbco_encode_blocked(&ob, &og, L, argc > 10 ? block_reads : 0xffffffffu, gen_mode | CBCG_MODE_SPLIT4, &ref)
+                             : cbco_encode_blocked(&ob, &og, L, block_reads, CBCG_MODE_SPLIT4, &ref);
     if (orc) { fprintf(stderr, "oracle encode failed: %d\n", orc); return 1; }
     if (ref.size != cont.size() || memcmp(ref.data, cont.data(), cont.size())) {
         size_t d = 0; while (d < cont.size() && d < ref.size && cont[d] == ref.data[d]) d++;
