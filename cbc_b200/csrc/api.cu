@@ -465,7 +465,7 @@ static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, ui
                       const std::vector<SizeStep> *ramp = nullptr, bool upload = true) {
     const uint64_t n = ctx->db.n_reads;
     uint32_t sched_count[CBCG_GEN_MAX], sched_reads[CBCG_GEN_MAX], sched_last = 0;
-    const uint32_t n_sched = gen_mode ? cbcg_gen_schedule(n, ctx->n_sub, sched_count, sched_reads, &sched_last) : 0u;
+    const uint32_t n_sched = gen_mode ? cbcg_gen_schedule(n, ctx->n_sub, sched_count, sched_reads, &sched_last, nullptr) : 0u;
     uint64_t bound = 1;
     uint32_t min_reads = block_reads;
     if (ramp) for (const SizeStep &st : *ramp) min_reads = std::min(min_reads, std::max(st.block_reads, 1u));
@@ -513,7 +513,7 @@ static uint32_t auto_block_reads(cbcg_ctx *ctx, uint64_t n, uint32_t gen_mode, u
     if (slots_out) *slots_out = 0;
     if (!gen_mode) return 1024u;
     uint32_t c[CBCG_GEN_MAX], r[CBCG_GEN_MAX], last = 0;
-    const uint32_t k = cbcg_gen_schedule(n, ctx->n_sub, c, r, &last);   /* what the <= 1 % budget leaves for the last generation */
+    const uint32_t k = cbcg_gen_schedule(n, ctx->n_sub, c, r, &last, nullptr);   /* what the <= 1 % budget leaves for the last generation */
     if (ctx->n_sub > 1u) return last;
     /* one warp per block: the last generation runs in whole waves of the GPU's resident warps (a few blocks beyond a wave
        cost a whole block time); rounded to fewer, larger blocks, never more */
@@ -531,7 +531,7 @@ static uint32_t auto_block_reads(cbcg_ctx *ctx, uint64_t n, uint32_t gen_mode, u
 /* reads the early generations of the default cut hold (everything but the last generation) */
 static uint64_t sched_early_reads(cbcg_ctx *ctx, uint64_t n, uint32_t *levels_out = nullptr) {
     uint32_t c[CBCG_GEN_MAX], r[CBCG_GEN_MAX], last = 0;
-    const uint32_t k = cbcg_gen_schedule(n, ctx->n_sub, c, r, &last);
+    const uint32_t k = cbcg_gen_schedule(n, ctx->n_sub, c, r, &last, nullptr);
     uint64_t early = 0;
     for (uint32_t g = 0; g < k; g++) early += (uint64_t)c[g] * r[g];
     if (levels_out) *levels_out = k;

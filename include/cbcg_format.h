@@ -118,6 +118,13 @@ static inline uint32_t cbcg_substream_of(uint32_t stream) {
  * stream per block with every symbol of a read in the reference's own order (src/read_compression.c:15-44), one byte
  * count. Same models, same symbols either way. */
 #define CBCG_MODE_SPLIT4    0x200u
+/* bits 16..23: the blocks of the first that many generations hold four substreams, the later ones a single stream (the
+ * default cut: the narrow early generations are latency-bound and run three times faster as four short chains, the
+ * wide last generation is bound by instruction issue and by its bytes per block, where one stream is cheaper). */
+#define CBCG_MODE_SPLIT_GENS(mode)        (((mode) >> 16) & 0xffu)
+#define CBCG_MODE_WITH_SPLIT_GENS(k)      (((uint32_t)(k) & 0xffu) << 16)
+#define CBCG_BLOCK_NSUB(mode, gen)        ((((mode) & CBCG_MODE_SPLIT4) || (uint32_t)(gen) < CBCG_MODE_SPLIT_GENS(mode)) ? CBCG_N_SUB : 1u)
+#define CBCG_MODE_LAYOUT_MASK             (CBCG_MODE_SPLIT4 | 0xff0000u)
 
 /* The FLAG model spends 65 536 / n of its probability on values never seen (src/sam_models.c:96-130: all-ones initial
  * state), so what a FLAG symbol costs depends on where the model total n stands below the rescale threshold 2^20
@@ -169,28 +176,46 @@ static inline double cbcg_root(double x, uint32_t k) {                      /* x
     }
     return 0.5 * (lo + hi);
 }
-static inline uint32_t cbcg_gen_schedule(uint64_t n, uint32_t n_sub, uint32_t *count, uint32_t *reads, uint32_t *last_reads) {
+/* layout: 1 = one stream per block, 4 = four substreams per block, 0 = four in the narrow early generations (cumulative
+ * reads <= 262 144) and one from there on (the default; *split_gens receives the number of four-substream generations).
+ * Bytes per block c and time per read of serial depth tau differ by layout (measured on B200: tau = 4.5 us for the single
+ * chain, 1.5 us for four short ones; c = 5.4 / 10.6 bytes): the least sum of tau_k b_k within the byte budget has
+ * b_k ~ sqrt(c_k n_k / tau_k). A generation of single-stream blocks gains nothing from more blocks than one wave of
+ * the GPU's resident warps (it is bound by instruction issue from there on), a four-substream generation is held to
+ * one wave of resident CTAs. */
+#define CBCG_SCHED_WAVE_BLOCKS 720u      /* resident CTAs of the four-substream kernel (148 SMs x 5, less a margin) */
+#define CBCG_SCHED_WAVE_WARPS  2960u     /* resident warps of the single-chain kernel (148 SMs x 20) */
+static inline uint32_t cbcg_gen_schedule(uint64_t n, uint32_t layout, uint32_t *count, uint32_t *reads, uint32_t *last_reads, uint32_t *split_gens) {
     uint64_t cum[CBCG_GEN_MAX + 1];
     uint32_t ne = 0;
-    for (uint64_t c = 256; ne < 6 && c * 2 <= n; c *= 4) cum[ne++] = c;      /* 256 .. 262 144 */
+    /* Around 3 M reads a coarser ladder (ratios 15, 7.4, 8, then the rest) measured inside the budget with a quarter less
+       depth than the fourfold ladder (config 2: +0.90 % at depth 1 158 against +0.81 % at 1 533); below that size its
+       loss is too large a share of the stream (config 1: +1.5 %), above it the last generation's is (6 M reads: +1.1 %). */
+    const int coarse = n >= 2000000u && n < 4500000u;
+    if (coarse) { cum[0] = 256; cum[1] = 3840; cum[2] = 28416; cum[3] = 225024; ne = 4; }
+    else for (uint64_t c = 256; ne < 6 && c * 2 <= n; c *= 4) cum[ne++] = c;      /* 256 .. 262 144 */
+    if (split_gens) *split_gens = layout == 4u ? 255u : 0u;
     if (!ne) { *last_reads = n > 64 ? (uint32_t)(n > 8192 ? 8192 : n) : 64u; return 0; }
+    const uint32_t n_early = ne;
     /* kappa grows with the input (the var model keeps discovering contexts): 2 200 measured at 3 M reads, 3 400 at 6 M */
     double kappa = 2800.0;                                                       /* ... and no smaller below 3 M */
     { double x = (double)n / 3.0e6, f = 1.0; while (x >= 2.0) { x *= 0.5; f *= 1.516; } if (x > 1.0) f *= 1.0 + 0.516 * (x - 1.0); kappa *= f; }
-    const double S = 1.66 * (double)n, room = 0.0092 * S, per_block = n_sub > 1u ? 10.6 : 5.4, early_loss = n < 2000000u ? 6000.0 : 3000.0;
+    const double S = 1.66 * (double)n, room = 0.0092 * S, early_loss = n < 2000000u ? 6000.0 : 3000.0;
+    const double c_early = layout == 1u ? 5.4 : 10.6, c_late = layout == 4u ? 10.6 : 5.4;
+    const double t_early = layout == 1u ? 4.5 : 1.5, t_late = layout == 4u ? 1.5 : 4.5;
     const double c0 = (double)cum[ne - 1];
-    uint32_t best_k = 1; double best_depth = 0.0, best_blocks = 16.0;
+    uint32_t best_k = 1; double best_time = 0.0, best_bytes = 200.0;
     for (uint32_t k = 1; k <= 6 && ne + k - 1 <= CBCG_GEN_MAX; k++) {
         const double r = cbcg_root((double)n / c0, k);
-        if (r > 4.0 && k < 6) continue;                                          /* a frozen snapshot coding more than 4x its training costs more than the model says */
-        const double loss = early_loss + kappa * (double)k * ((r - 1.0) - cbcg_ln(r));
-        double blocks = (room - loss) / per_block;
-        if (blocks < 16.0) blocks = 16.0;
-        double sum_sqrt = 0.0, c = 0.0;
-        for (uint32_t g = 0; g < ne; g++) { sum_sqrt += (double)cbcg_isqrt(cum[g] - (uint64_t)c); c = (double)cum[g]; }
-        for (uint32_t j = 1; j <= k; j++) { const double nx = j == k ? (double)n : c * r; sum_sqrt += (double)cbcg_isqrt((uint64_t)(nx - c)); c = nx; }
-        const double depth = sum_sqrt * sum_sqrt / blocks;
-        if (best_depth == 0.0 || depth < best_depth) { best_depth = depth; best_k = k; best_blocks = blocks; }
+        if (r > 4.0 && k < 6 && !coarse) continue;                               /* a frozen snapshot coding more than 4x its training costs more than the model says */
+        const double loss = coarse ? (k == 1 ? 19000.0 * (double)n / 3.0e6 : 1.0e12) : early_loss + kappa * (double)k * ((r - 1.0) - cbcg_ln(r));
+        double bytes = room - loss;
+        if (bytes < 200.0) bytes = 200.0;
+        double sum = 0.0, c = 0.0;                                               /* time = (sum sqrt(c n tau))^2 / bytes */
+        for (uint32_t g = 0; g < ne; g++) { sum += (double)cbcg_isqrt((uint64_t)((double)(cum[g] - (uint64_t)c) * c_early * t_early)); c = (double)cum[g]; }
+        for (uint32_t j = 1; j <= k; j++) { const double nx = j == k ? (double)n : c * r; sum += (double)cbcg_isqrt((uint64_t)((nx - c) * c_late * t_late)); c = nx; }
+        const double time = sum * sum / bytes;
+        if (best_time == 0.0 || time < best_time) { best_time = time; best_k = k; best_bytes = bytes; }
         if (r < 2.0) break;
     }
     {                                                                            /* the late generations but the last */
@@ -198,20 +223,43 @@ static inline uint32_t cbcg_gen_schedule(uint64_t n, uint32_t n_sub, uint32_t *c
         double c = c0;
         for (uint32_t j = 1; j < best_k; j++) { c *= r; cum[ne++] = (uint64_t)c; }
     }
-    uint64_t sum_sqrt = 0, prev = 0;
-    for (uint32_t g = 0; g < ne; g++) { sum_sqrt += cbcg_isqrt(cum[g] - prev); prev = cum[g]; }
-    sum_sqrt += cbcg_isqrt(n - prev);
-    const double cc = (double)sum_sqrt / best_blocks;                           /* block size = cc x sqrt(generation size) */
-    prev = 0;
+    cum[ne] = n;                                                                 /* stage ne = the last generation */
+    if (split_gens && layout == 0u) *split_gens = n_early;
+    uint64_t bsz[CBCG_GEN_MAX + 1];
+    int fixed[CBCG_GEN_MAX + 1];
+    for (uint32_t g = 0; g <= ne; g++) fixed[g] = 0;
+    double bytes = best_bytes;
+    for (int pass = 0; pass < 3; pass++) {                                       /* clamped generations hand their bytes to the others */
+        double sum = 0.0; uint64_t prev = 0;
+        for (uint32_t g = 0; g <= ne; g++) {
+            const uint64_t size = cum[g] - prev; prev = cum[g];
+            const int early = g < n_early;
+            if (!fixed[g]) sum += (double)cbcg_isqrt((uint64_t)((double)size * (early ? c_early * t_early : c_late * t_late)));
+        }
+        const double lambda = bytes > 1.0 ? sum / bytes : sum;
+        int changed = 0; prev = 0;
+        for (uint32_t g = 0; g <= ne; g++) {
+            const uint64_t size = cum[g] - prev; prev = cum[g];
+            if (fixed[g]) continue;
+            const int early = g < n_early;
+            const int four = early ? layout != 1u : layout == 4u;
+            uint64_t b = (uint64_t)(lambda * (double)cbcg_isqrt((uint64_t)((double)size * (early ? c_early / t_early : c_late / t_late) * 1.0e4)) / 100.0);
+            if (b < 32) b = 32;
+            const uint64_t wave = four ? CBCG_SCHED_WAVE_BLOCKS : CBCG_SCHED_WAVE_WARPS;
+            const uint64_t floor_b = (size + wave - 1) / wave;                    /* more blocks than one wave buy no time */
+            if (b < floor_b) { b = floor_b; fixed[g] = 1; changed = 1; bytes -= (early ? c_early : c_late) * (double)((size + b - 1) / b); }
+            bsz[g] = b;
+        }
+        if (!changed) break;
+        if (bytes < 200.0) bytes = 200.0;
+    }
     for (uint32_t g = 0; g < ne; g++) {
-        const uint64_t size = cum[g] - prev; prev = cum[g];
-        uint64_t b = (uint64_t)(cc * (double)cbcg_isqrt(size));
-        if (g == 0) b = 64;
-        if (b < 32) b = 32;
+        uint64_t b = g == 0 ? 64 : bsz[g];
         if (b > 16384) b = 16384;
+        const uint64_t size = cum[g] - (g ? cum[g - 1] : 0);
         reads[g] = (uint32_t)b; count[g] = (uint32_t)((size + b - 1) / b);
     }
-    uint64_t lb = (uint64_t)(cc * (double)cbcg_isqrt(n - prev));
+    uint64_t lb = bsz[ne];
     if (lb < 64) lb = 64;
     if (lb > 16384) lb = 16384;
     *last_reads = (uint32_t)lb;

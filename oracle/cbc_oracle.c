@@ -1195,7 +1195,7 @@ int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, u
                         uint32_t gen_mode, cbco_buf *out) {
     uint32_t count[CBCG_GEN_MAX], reads[CBCG_GEN_MAX], last = 0, levels = 0;
     if ((gen_mode & CBCG_MODE_GEN_MASK) > 1 || (gen_mode & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_SPLIT4))) return -30;   /* low byte: generations; bit 9: four substreams */
-    if (gen_mode & CBCG_MODE_GEN_MASK) levels = cbcg_gen_schedule(b->n_reads, (gen_mode & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u, count, reads, &last);
+    if (gen_mode & CBCG_MODE_GEN_MASK) levels = cbcg_gen_schedule(b->n_reads, (gen_mode & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u, count, reads, &last, NULL);
     if (block_reads == 0xffffffffu) block_reads = (gen_mode & CBCG_MODE_GEN_MASK) ? last : 1024u;      /* CBCG_BLOCK_AUTO */
     return encode_cut(b, g, L, block_reads, levels, count, reads, NULL, 0, gen_mode, out);
 }

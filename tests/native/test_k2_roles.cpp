@@ -151,7 +151,7 @@ int main(int argc, char **argv) {
 
     /* ---- the cut (api.cu cut_blocks): generations on the schedule, never across a chromosome change */
     uint32_t sc[CBCG_GEN_MAX], sr[CBCG_GEN_MAX], last = 0, levels = 0;
-    if (gen_mode) levels = cbcg_gen_schedule(n, CBCG_N_SUB, sc, sr, &last);
+    if (gen_mode) levels = cbcg_gen_schedule(n, CBCG_N_SUB, sc, sr, &last, nullptr);
     if (block_reads == 0xffffffffu) block_reads = gen_mode ? last : 1024u;
     std::vector<BlockDesc> hb;
     {
