@@ -331,7 +331,7 @@ def k2_issue_profile():
 
 def run_b200_arm(args):
     import torch
-    from cbc_b200.codec import Codec, pin_batch, pinned_empty
+    from cbc_b200.codec import Codec, CompactBatch, pin_batch, pinned_empty
     from cbc_b200 import shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -491,16 +491,25 @@ def run_b200_arm(args):
     for c2 in codecs[1:]:
         c2.set_reference(g)
     subs = [pin_batch(b.slice(a_, b_)) if K > 1 else pb for a_, b_ in cuts]
+    # what crosses the link: the compact form of the batch (2 bits per base, text lengths, chromosome runs: cbcg_batch_compact),
+    # packed by the host C code (cbch_pack_batch, what the SAM ingest hands over) into pinned memory before the timed region
+    compacts = [CompactBatch(sb_) for sb_ in subs] if args.e2e_input == "compact" else None
     outs_c = [pinned_empty(int(container_bytes * 1.5 / K) + 65536, np.uint8) for _ in range(K)]
     outs_t = [pinned_empty(sb_.total_bases() + sb_.n_reads + 64, np.uint8) for sb_ in subs]
 
     def e2e_one(k):
         c2 = codecs[k]
-        nc = c2.compress_into(subs[k], L, R, outs_c[k], G, args.substreams)
+        t_a = time.perf_counter()
+        nc = (c2.compress_compact_into(compacts[k], L, R, outs_c[k], G, args.substreams) if compacts
+              else c2.compress_into(subs[k], L, R, outs_c[k], G, args.substreams))
+        t_b = time.perf_counter()
         s1 = c2.stats()
         head, payload = c2.fetch_index()
+        t_c = time.perf_counter()
         nt, nr = c2.decompress_into(outs_c[k][:nc], outs_t[k])
+        t_d = time.perf_counter()
         s2 = c2.stats()
+        s1["wall_ms"] = (t_b - t_a) * 1e3; s2["wall_ms"] = (t_d - t_c) * 1e3
         return nc, nt, s1, s2, head, payload
 
     pool = ThreadPoolExecutor(K)
@@ -527,9 +536,10 @@ def run_b200_arm(args):
     e2e = {"value": total_reads / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(sum(r_[2]["h2d_bytes"] + r_[3]["h2d_bytes"] for r_ in res)),
            "d2h_bytes_per_step": int(sum(r_[2]["d2h_bytes"] + r_[3]["d2h_bytes"] for r_ in res)),
-           "contexts_in_flight": K, "container_bytes": int(e2e_container),
+           "contexts_in_flight": K, "container_bytes": int(e2e_container), "input_form": args.e2e_input,
            "bits_per_base": 8.0 * e2e_container / bases,
-           "compress_ms": float(np.mean([r_[2]["ms_total"] for r_ in res])), "decompress_ms": float(np.mean([r_[3]["ms_total"] for r_ in res]))}
+           "compress_ms": float(np.mean([r_[2]["ms_total"] for r_ in res])), "decompress_ms": float(np.mean([r_[3]["ms_total"] for r_ in res])),
+           "compress_call_wall_ms": float(np.mean([r_[2]["wall_ms"] for r_ in res])), "decompress_call_wall_ms": float(np.mean([r_[3]["wall_ms"] for r_ in res]))}
     s1 = {"h2d_bytes": sum(r_[2]["h2d_bytes"] for r_ in res)}
     pool.shutdown()
     for c2 in codecs[1:]:
@@ -696,6 +706,8 @@ def main():
     ap.add_argument("--inflight", type=int, default=1, help="contexts (host threads / streams) the e2e leg keeps in flight")
     ap.add_argument("--gen-mode", type=int, default=1, help="1: generation-primed blocks (default), 0: cold blocks")
     ap.add_argument("--substreams", type=int, default=1, choices=[1, 4], help="arithmetic-coded streams per block: 1 (default) or 4 (CBCG_MODE_SPLIT4)")
+    ap.add_argument("--e2e-input", default="compact", choices=["compact", "soa"],
+                    help="host buffers of the e2e leg: cbcg_batch_compact (2 bits per base; default) or the plain SoA cbcg_batch")
     ap.add_argument("--scale", type=float, default=0.0, help="shrink the workload; default 1.0 (config 4: 0.1, stated in config.workload)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / blocking-overhead / CLI legs")
     ap.add_argument("--no-cli", action="store_true", help="skip the file-to-file CLI leg")

@@ -22,11 +22,26 @@ REC_DTYPE = np.dtype([("pos", "<u4"), ("flag", "<u2"), ("len", "<u2"), ("edit_of
                       ("match", "u1"), ("n_snps", "u1"), ("n_dels", "u1"), ("n_ins", "u1")])
 SYM_DTYPE = np.dtype([("key", "<u4"), ("value", "<u4")])
 
+class CBatchCompact(C.Structure):
+    """Mirror of ``cbcg_batch_compact`` (include/cbcg.h): the form of a batch that crosses the host-device link."""
+    _fields_ = [("n_reads", C.c_uint64), ("pos", C.c_void_p), ("flag", C.c_void_p), ("seq_len", C.c_void_p),
+                ("cigar_len", C.c_void_p), ("md_len", C.c_void_p), ("n_runs", C.c_uint32), ("pad", C.c_uint32),
+                ("run_first", C.c_void_p), ("run_chr", C.c_void_p), ("seq2", C.c_void_p), ("n_exc", C.c_uint64),
+                ("exc_read", C.c_void_p), ("exc_base", C.c_void_p), ("exc_char", C.c_void_p), ("cigar", C.c_void_p),
+                ("md", C.c_void_p), ("tile_base", C.c_void_p), ("max_len", C.c_uint32), ("min_len", C.c_uint32)]
+
+
+class _CbchCompact(C.Structure):
+    """Mirror of ``cbch_compact`` (csrc/host/sam_ingest.h)."""
+    _fields_ = [("v", CBatchCompact), ("alloc", C.c_void_p), ("release", C.c_void_p), ("bytes", C.c_uint64)]
+
+
 EXPORTS = ["cbcg_create", "cbcg_destroy", "cbcg_strerror", "cbcg_last_error", "cbcg_abi_version", "cbcg_get_stats",
            "cbcg_host_alloc", "cbcg_host_free", "cbcg_set_reference", "cbcg_extract", "cbcg_extract_symbols",
            "cbcg_encode", "cbcg_encode_bound", "cbcg_decode", "cbcg_decoded_size", "cbcg_decode_edits",
            "cbcg_reconstruct", "cbcg_batch_upload", "cbcg_encode_resident", "cbcg_decode_resident",
-           "cbcg_fetch_container", "cbcg_fetch_decoded", "cbcg_fetch_index", "cbcg_mark", "cbcg_elapsed_ms"]
+           "cbcg_fetch_container", "cbcg_fetch_decoded", "cbcg_fetch_index", "cbcg_mark", "cbcg_elapsed_ms",
+           "cbcg_encode_compact", "cbcg_batch_upload_compact"]
 
 
 class EncodeOpts(C.Structure):
@@ -83,6 +98,8 @@ def load_library():
         lib.cbcg_decode_edits.argtypes = [vp, vp, u64, C.c_int, vp, u64, vp, vp, u64, P(u64), P(u64)]
         lib.cbcg_reconstruct.argtypes = [vp, u64, vp, vp, vp, u64, vp, u64, P(u64)]
         lib.cbcg_batch_upload.argtypes = [vp, P(CBatch)]
+        lib.cbcg_batch_upload_compact.argtypes = [vp, P(CBatchCompact)]
+        lib.cbcg_encode_compact.argtypes = [vp, P(CBatchCompact), P(EncodeOpts), vp, u64, P(u64)]
         lib.cbcg_encode_resident.argtypes = [vp, P(EncodeOpts)]
         lib.cbcg_decode_resident.argtypes = [vp]
         lib.cbcg_fetch_container.argtypes = [vp, vp, u64, P(u64)]
@@ -121,6 +138,55 @@ def pin_batch(b: Batch) -> Batch:
         return out
     return Batch(pin(b.pos), pin(b.flag), pin(b.seq_len), pin(b.chr), pin(b.seq_off), pin(b.seq),
                  pin(b.cigar_off), pin(b.cigar), pin(b.md_off), pin(b.md))
+
+
+_HOSTLIB = None
+
+
+def _hostlib():
+    global _HOSTLIB
+    if _HOSTLIB is None:
+        path = os.path.join(_HERE, "_build", "libcbchost.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `make host`")
+        _HOSTLIB = C.CDLL(path)
+        _HOSTLIB.cbch_pack_batch.argtypes = [C.POINTER(CBatch), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(_CbchCompact)]
+        _HOSTLIB.cbch_free_compact.argtypes = [C.POINTER(_CbchCompact)]
+        _HOSTLIB.cbch_free_compact.restype = None
+    return _HOSTLIB
+
+
+class CompactBatch:
+    """A batch packed for the link by the host C code (cbch_pack_batch): 2 bits per base, text lengths, chromosome runs.
+    pinned: its arrays live in page-locked memory from cbcg_host_alloc."""
+
+    def __init__(self, batch: Batch, pinned: bool = True, threads: int = 0):
+        self.c = _CbchCompact()
+        self.n_reads = batch.n_reads
+        cb = batch.c_struct()
+        alloc = release = None
+        if pinned:
+            lib = load_library()
+            alloc = C.cast(lib.cbcg_host_alloc, C.c_void_p)
+            release = C.cast(lib.cbcg_host_free, C.c_void_p)
+        rc = _hostlib().cbch_pack_batch(C.byref(cb), threads, alloc, release, C.byref(self.c))
+        if rc:
+            raise MemoryError(f"cbch_pack_batch: {rc}")
+
+    @property
+    def link_bytes(self) -> int:
+        return int(self.c.bytes)
+
+    def close(self):
+        if self.c is not None:
+            _hostlib().cbch_free_compact(C.byref(self.c))
+            self.c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Codec:
@@ -241,6 +307,17 @@ class Codec:
         n = C.c_uint64(0)
         self._check(self.lib.cbcg_encode(self.h, C.byref(cb), C.byref(opts), out.ctypes.data, out.nbytes, C.byref(n)))
         return n.value
+
+    def compress_compact_into(self, compact: "CompactBatch", read_len_header: int, block_reads: int, out: np.ndarray,
+                              gen_mode: int = 0, substreams: int = 1) -> int:
+        """cbcg_encode_compact: the same container from a third of the bytes on the link."""
+        opts = EncodeOpts(read_len_header, block_reads, gen_mode, substreams)
+        n = C.c_uint64(0)
+        self._check(self.lib.cbcg_encode_compact(self.h, C.byref(compact.c.v), C.byref(opts), out.ctypes.data, out.nbytes, C.byref(n)))
+        return n.value
+
+    def upload_compact(self, compact: "CompactBatch"):
+        self._check(self.lib.cbcg_batch_upload_compact(self.h, C.byref(compact.c.v)))
 
     def decompress_into(self, data: np.ndarray, out: np.ndarray, legacy: bool = False) -> Tuple[int, int]:
         """cbcg_decode from / into caller-owned buffers; returns (text bytes, reads)."""

@@ -71,6 +71,10 @@ struct cbcg_ctx {
     uint64_t total_bases = 0;
     bool have_batch = false;
 
+    /* compact batches (cbcg_batch_compact): staging for what is unpacked on the device */
+    DevBuf c_seq2, c_cl, c_ml, c_tile, c_rfirst, c_rchr, c_er, c_eb, c_ec;
+    uint64_t *h_tile = nullptr; size_t h_tile_cap = 0;   /* pinned: one (seq, seq2, cigar, md) byte offset per tile of 128 reads */
+
     /* work buffers */
     DevBuf recs, edits, chr_out, tile_desc, words, blocks, ws, scratch, payload, out_off, symbols, seq_out;
     DevBuf snap_a, snap_b, fin;                /* generation snapshots and per-block final states (gen_mode 1) */
@@ -197,6 +201,8 @@ extern "C" void cbcg_destroy(cbcg_ctx *ctx) {
     for (DevBuf *b : all) free_buf(*b);
     if (ctx->hw) cudaFreeHost(ctx->hw);
     if (ctx->hblocks) cudaFreeHost(ctx->hblocks);
+    if (ctx->h_tile) cudaFreeHost(ctx->h_tile);
+    for (DevBuf *d : { &ctx->c_seq2, &ctx->c_cl, &ctx->c_ml, &ctx->c_tile, &ctx->c_rfirst, &ctx->c_rchr, &ctx->c_er, &ctx->c_eb, &ctx->c_ec }) free_buf(*d);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->mark) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
@@ -369,6 +375,137 @@ static int batch_scan(cbcg_ctx *ctx, const cbcg_batch *b) {
         return fail(ctx, CBCG_ERR_INPUT, "read length outside 1..%u (shortest %u, longest %u)", CBCG_MAX_READ_LEN, min_len, max_len);
     if (bad) return fail(ctx, CBCG_ERR_INPUT, "batch offsets inconsistent: seq_off must advance by seq_len, cigar_off / md_off must not decrease");
     return 0;
+}
+
+static int reset_words(cbcg_ctx *ctx);
+static int fetch_words(cbcg_ctx *ctx);
+/* ---- compact batches: what crosses the link packed, rebuilt into the layout above on the device (k0_unpack.cu) */
+struct BatchSrc { const cbcg_batch *full; const cbcg_batch_compact *compact; uint64_t n; };
+static int check_compact(cbcg_ctx *ctx, const cbcg_batch_compact *b) {
+    if (!b) return fail(ctx, CBCG_ERR_ARG, "NULL batch");
+    if (b->n_reads == 0) return 0;
+    if (!b->pos || !b->flag || !b->seq_len || !b->cigar_len || !b->md_len || !b->n_runs || !b->run_first || !b->run_chr || !b->seq2 || !b->cigar || !b->md ||
+        !b->tile_base || (b->n_exc && (!b->exc_read || !b->exc_base || !b->exc_char)))
+        return fail(ctx, CBCG_ERR_ARG, "compact batch has NULL arrays");
+    if (b->n_reads >= 0xfffffff0ull) return fail(ctx, CBCG_ERR_ARG, "more than 2^32 reads in one shard");
+    if (b->run_first[0] != 0) return fail(ctx, CBCG_ERR_INPUT, "the first chromosome run must start at read 0");
+    if (b->min_len == 0 || b->max_len > CBCG_MAX_READ_LEN || b->min_len > b->max_len)
+        return fail(ctx, CBCG_ERR_INPUT, "read length outside 1..%u (shortest %u, longest %u)", CBCG_MAX_READ_LEN, b->min_len, b->max_len);
+    const uint64_t tiles = (b->n_reads + 127u) / 128u;
+    for (int q = 0; q < 4; q++) if (b->tile_base[q] != 0) return fail(ctx, CBCG_ERR_INPUT, "compact batch: tile offsets must start at 0");
+    if (b->tile_base[tiles * 4] > b->n_reads * (uint64_t)b->max_len || b->tile_base[tiles * 4 + 1] > b->tile_base[tiles * 4])
+        return fail(ctx, CBCG_ERR_INPUT, "compact batch: totals inconsistent");
+    return 0;
+}
+/* Device buffers of a compact batch and ctx->db; chromosome runs and the exception list are checked here (both short),
+ * the per-read lengths are checked against the tile offsets by the unpack kernel. No pass over the reads on the host. */
+static int compact_buffers(cbcg_ctx *ctx, const cbcg_batch_compact *b) {
+    const uint64_t n = b->n_reads, tiles = (n + 127u) / 128u;
+    ctx->have_batch = false; ctx->have_encoded = false;
+    ctx->runs.clear();
+    ctx->stats = cbcg_stats();
+    uint64_t seq_b = 0;
+    if (n) {
+        for (uint64_t t = 0; t < tiles; t++)
+            for (int q = 0; q < 4; q++) if (b->tile_base[(t + 1) * 4 + q] < b->tile_base[t * 4 + q]) return fail(ctx, CBCG_ERR_INPUT, "compact batch: tile offsets decrease");
+        for (uint32_t k = 0; k < b->n_runs; k++) {
+            const uint64_t first = b->run_first[k], end = k + 1 < b->n_runs ? b->run_first[k + 1] : n;
+            if (end <= first || end > n) return fail(ctx, CBCG_ERR_INPUT, "compact batch: chromosome runs out of order");
+            ctx->runs.push_back({ first, end - first, b->run_chr[k] });
+        }
+        for (uint64_t e = 1; e < b->n_exc; e++) if (b->exc_read[e] < b->exc_read[e - 1]) return fail(ctx, CBCG_ERR_INPUT, "compact batch: exception list not sorted by read");
+        if (b->n_exc && b->exc_read[b->n_exc - 1] >= n) return fail(ctx, CBCG_ERR_INPUT, "compact batch: exception outside the batch");
+        for (uint64_t e = 0; e < b->n_exc; e++) if (b->exc_base[e] >= b->max_len) return fail(ctx, CBCG_ERR_INPUT, "compact batch: exception beyond the longest read");
+        const uint64_t *tot = b->tile_base + tiles * 4;
+        seq_b = tot[0];
+        const uint64_t s2_b = tot[1], cig_b = tot[2], md_b = tot[3];
+        TRY(ensure(ctx, ctx->b_pos, n * 4));  TRY(ensure(ctx, ctx->b_flag, n * 2)); TRY(ensure(ctx, ctx->b_len, n * 2));
+        TRY(ensure(ctx, ctx->b_chr, n * 4));
+        TRY(ensure(ctx, ctx->b_soff, (n + 1) * 8)); TRY(ensure(ctx, ctx->b_coff, (n + 1) * 8)); TRY(ensure(ctx, ctx->b_moff, (n + 1) * 8));
+        TRY(ensure(ctx, ctx->b_seq, seq_b + 4 * 0u + POOL_PAD)); TRY(ensure(ctx, ctx->b_cigar, cig_b + POOL_PAD)); TRY(ensure(ctx, ctx->b_md, md_b + POOL_PAD));
+        TRY(ensure(ctx, ctx->c_seq2, s2_b + POOL_PAD)); TRY(ensure(ctx, ctx->c_cl, n * 2)); TRY(ensure(ctx, ctx->c_ml, n * 2));
+        TRY(ensure(ctx, ctx->c_tile, (tiles + 1) * 32)); TRY(ensure(ctx, ctx->c_rfirst, (uint64_t)b->n_runs * 8)); TRY(ensure(ctx, ctx->c_rchr, (uint64_t)b->n_runs * 4));
+        TRY(ensure(ctx, ctx->c_er, b->n_exc * 4 + 16)); TRY(ensure(ctx, ctx->c_eb, b->n_exc * 2 + 16)); TRY(ensure(ctx, ctx->c_ec, b->n_exc + 16));
+    }
+    ctx->db.n_reads = n;
+    ctx->db.pos = ctx->b_pos.as<uint32_t>(); ctx->db.flag = ctx->b_flag.as<uint16_t>(); ctx->db.seq_len = ctx->b_len.as<uint16_t>();
+    ctx->db.chr = ctx->b_chr.as<uint32_t>();
+    ctx->db.seq_off = ctx->b_soff.as<uint64_t>(); ctx->db.seq = ctx->b_seq.as<uint8_t>();
+    ctx->db.cigar_off = ctx->b_coff.as<uint64_t>(); ctx->db.cigar = ctx->b_cigar.as<uint8_t>();
+    ctx->db.md_off = ctx->b_moff.as<uint64_t>(); ctx->db.md = ctx->b_md.as<uint8_t>();
+    ctx->db.max_len = n ? b->max_len : 0; ctx->batch_min_len = n ? b->min_len : 0; ctx->total_bases = seq_b;
+    return 0;
+}
+/* the small pieces every chunk needs: tile offsets, chromosome runs, the exception list (first on the link) */
+static int compact_copy_head(cbcg_ctx *ctx, const cbcg_batch_compact *b, cudaStream_t st, uint64_t *bytes) {
+    const uint64_t tiles = (b->n_reads + 127u) / 128u;
+    struct { void *d; const void *h; uint64_t bytes; } cp[] = {
+        { ctx->c_tile.p, b->tile_base, (tiles + 1) * 32 }, { ctx->c_rfirst.p, b->run_first, (uint64_t)b->n_runs * 8 }, { ctx->c_rchr.p, b->run_chr, (uint64_t)b->n_runs * 4 },
+        { ctx->c_er.p, b->exc_read, b->n_exc * 4 }, { ctx->c_eb.p, b->exc_base, b->n_exc * 2 }, { ctx->c_ec.p, b->exc_char, b->n_exc } };
+    for (auto &c : cp) { if (c.bytes) CU(cudaMemcpyAsync(c.d, c.h, c.bytes, cudaMemcpyHostToDevice, st)); *bytes += c.bytes; }
+    return 0;
+}
+/* reads [r0, r1), both multiples of 128 (or the end of the batch) */
+static int compact_copy_range(cbcg_ctx *ctx, const cbcg_batch_compact *b, uint64_t r0, uint64_t r1, cudaStream_t st, uint64_t *bytes) {
+    if (r1 <= r0) return 0;
+    const uint64_t m = r1 - r0;
+    const uint64_t *t0 = b->tile_base + (r0 >> 7) * 4, *t1 = b->tile_base + ((r1 + 127u) >> 7) * 4;
+    const uint64_t s0 = t0[1], s1 = t1[1], c0 = t0[2], c1 = t1[2], m0 = t0[3], m1 = t1[3];
+    struct { void *d; const void *h; uint64_t bytes; } cp[] = {
+        { ctx->b_pos.as<uint32_t>() + r0, b->pos + r0, m * 4 }, { ctx->b_flag.as<uint16_t>() + r0, b->flag + r0, m * 2 },
+        { ctx->b_len.as<uint16_t>() + r0, b->seq_len + r0, m * 2 }, { ctx->c_cl.as<uint16_t>() + r0, b->cigar_len + r0, m * 2 },
+        { ctx->c_ml.as<uint16_t>() + r0, b->md_len + r0, m * 2 }, { ctx->c_seq2.as<uint8_t>() + s0, b->seq2 + s0, s1 - s0 },
+        { ctx->b_cigar.as<uint8_t>() + c0, b->cigar + c0, c1 - c0 }, { ctx->b_md.as<uint8_t>() + m0, b->md + m0, m1 - m0 } };
+    for (auto &c : cp) { if (c.bytes) CU(cudaMemcpyAsync(c.d, c.h, c.bytes, cudaMemcpyHostToDevice, st)); *bytes += c.bytes; }
+    return 0;
+}
+/* reads [r0, r1) (r0 a multiple of 128) from the staging buffers into the SoA batch */
+static int compact_unpack_range(cbcg_ctx *ctx, const cbcg_batch_compact *b, uint64_t r0, uint64_t r1, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    if (launch_unpack(r0, r1, b->n_reads, ctx->b_len.as<uint16_t>(), ctx->c_cl.as<uint16_t>(), ctx->c_ml.as<uint16_t>(), ctx->c_seq2.as<uint8_t>(),
+                      ctx->c_tile.as<uint64_t>(), ctx->c_rfirst.as<uint64_t>(), ctx->c_rchr.as<uint32_t>(), b->n_runs,
+                      ctx->b_soff.as<uint64_t>(), ctx->b_coff.as<uint64_t>(), ctx->b_moff.as<uint64_t>(), ctx->b_seq.as<uint8_t>(), ctx->b_chr.as<uint32_t>(),
+                      wptr<unsigned long long>(ctx, W_OFF(err)), st))
+        return fail(ctx, CBCG_ERR_CUDA, "unpack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->stats.kernel_launches++;
+    if (b->n_exc) {
+        const uint32_t *lo = std::lower_bound(b->exc_read, b->exc_read + b->n_exc, (uint32_t)r0);
+        const uint32_t *hi = std::lower_bound(b->exc_read, b->exc_read + b->n_exc, (uint32_t)std::min<uint64_t>(r1, 0xffffffffull));
+        const uint64_t e0 = (uint64_t)(lo - b->exc_read), e1 = (uint64_t)(hi - b->exc_read);
+        if (e1 > e0) {
+            if (launch_patch(ctx->c_er.as<uint32_t>() + e0, ctx->c_eb.as<uint16_t>() + e0, ctx->c_ec.as<uint8_t>() + e0, e1 - e0, ctx->b_soff.as<uint64_t>(), ctx->b_seq.as<uint8_t>(), st))
+                return fail(ctx, CBCG_ERR_CUDA, "patch launch failed");
+            ctx->stats.kernel_launches++;
+        }
+    }
+    return 0;
+}
+static int src_prepare(cbcg_ctx *ctx, const BatchSrc &s) { return s.compact ? compact_buffers(ctx, s.compact) : batch_prepare(ctx, s.full); }
+static int src_copy_range(cbcg_ctx *ctx, const BatchSrc &s, uint64_t r0, uint64_t r1, cudaStream_t st, uint64_t *bytes) {
+    return s.compact ? compact_copy_range(ctx, s.compact, r0, r1, st, bytes) : batch_copy_range(ctx, s.full, r0, r1, st, bytes);
+}
+
+extern "C" int cbcg_batch_upload_compact(cbcg_ctx *ctx, const cbcg_batch_compact *b) {
+    if (!ctx) return CBCG_ERR_ARG;
+    TRY(check_compact(ctx, b));
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = b->n_reads;
+    TRY(compact_buffers(ctx, b));
+    CU(cudaEventRecord(ctx->ev[0], ctx->st));
+    uint64_t h2d = 0;
+    if (n) {
+        TRY(reset_words(ctx));
+        TRY(compact_copy_head(ctx, b, ctx->st, &h2d));
+        TRY(compact_copy_range(ctx, b, 0, n, ctx->st, &h2d));
+        TRY(compact_unpack_range(ctx, b, 0, n, ctx->st));
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->st));
+    if (n) { TRY(fetch_words(ctx)); TRY(device_error(ctx, "compact batch")); }
+    else CU(cudaStreamSynchronize(ctx->st));
+    ctx->have_batch = true;
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_h2d = ms; ctx->stats.h2d_bytes = h2d; ctx->stats.n_reads = n;
+    return CBCG_OK;
 }
 
 extern "C" int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *b) {
@@ -902,6 +1039,9 @@ static uint64_t pipe_min_reads() {
  * config 2 (encode + decode, ms): linear 1.3 .. 0.7: 14.09 + 14.53; this: 13.97 + 13.68; {1.3,1.2,1.0,0.7,0.45}: 14.24 + 13.51;
  * {1.4,1.25,1.0,0.7,0.45}: 14.18 + 13.53; {1.35,1.25,1.0,0.65,0.4}: 14.22 + 13.72; {1.3,1.25,1.1,0.7,0.4}: 14.42 + 14.75. */
 static const double PIPE_MULT[PIPE_CHUNKS] = { 1.3, 1.2, 1.0, 0.6, 0.45 };
+/* a compact batch is on the device after a third of the time: the encoder no longer waits for the link, a flatter ramp
+   (which the decoder still wants: small blocks decode first and their text goes out while the large ones run) */
+static const double PIPE_MULT_COMPACT[PIPE_CHUNKS] = { 1.15, 1.1, 1.0, 0.8, 0.6 };
 static bool pipe_ramp(double *hi, double *lo) {             /* CBCG_PIPE_RAMP="hi,lo": a linear ramp instead (tuning) */
     const char *e = getenv("CBCG_PIPE_RAMP");
     if (!e) return false;
@@ -930,8 +1070,8 @@ static void pipe_drain(cbcg_ctx *ctx) {
     cudaStreamSynchronize(ctx->st);
     (void)cudaGetLastError();
 }
-static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encode_opts *opts) {
-    const uint64_t n = b->n_reads;
+static int encode_pipelined(cbcg_ctx *ctx, const BatchSrc &src, const cbcg_encode_opts *opts) {
+    const uint64_t n = src.n;
     ctx->n_sub = opts->substreams == CBCG_N_SUB ? CBCG_N_SUB : 1u;
     const uint32_t L = opts->read_len_header;
     const uint64_t tile = 128;                              /* K1 tile: chunk boundaries are whole tiles */
@@ -940,7 +1080,7 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     if (n < early + tile * (PIPE_CHUNKS + 1)) return PIPE_FALLBACK;
     if (!ctx->dg.n_chr) return fail(ctx, CBCG_ERR_NO_REFERENCE, "cbcg_set_reference has not been called");   /* before any copy is queued */
     TRY(pipe_init(ctx));
-    TRY(batch_prepare(ctx, b));
+    TRY(src_prepare(ctx, src));
     set_carveout_all(100);
     cbcg_stats &S = ctx->stats;
 
@@ -960,11 +1100,12 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     CU(cudaEventRecord(ctx->ev[0], ctx->st));
     CU(cudaStreamWaitEvent(ctx->cs, ctx->ev[0], 0));        /* copies start after whatever the caller left on the main stream */
     uint64_t h2d = 0;
+    if (src.compact) TRY(compact_copy_head(ctx, src.compact, ctx->cs, &h2d));
     for (uint32_t c = 0; c <= PIPE_CHUNKS; c++) {
-        TRY(batch_copy_range(ctx, b, cut[c], cut[c + 1], ctx->cs, &h2d));
+        TRY(src_copy_range(ctx, src, cut[c], cut[c + 1], ctx->cs, &h2d));
         CU(cudaEventRecord(ctx->cev[c], ctx->cs));
     }
-    TRY(batch_scan(ctx, b));                                /* while the copies fly */
+    if (src.full) TRY(batch_scan(ctx, src.full));           /* while the copies fly (a compact batch brings its figures with it) */
     const bool fixed = ctx->batch_min_len == L && ctx->db.max_len == L;
 
     /* the cut: early generations on their schedule, then the ramp */
@@ -975,7 +1116,7 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     std::vector<SizeStep> ramp;
     double mult[PIPE_CHUNKS], inv = 0;
     const bool linear = pipe_ramp(&hi, &lo);
-    for (uint32_t c = 0; c < PIPE_CHUNKS; c++) mult[c] = linear ? hi - (hi - lo) * (double)c / (double)(PIPE_CHUNKS - 1) : PIPE_MULT[c];
+    for (uint32_t c = 0; c < PIPE_CHUNKS; c++) mult[c] = linear ? hi - (hi - lo) * (double)c / (double)(PIPE_CHUNKS - 1) : (src.compact ? PIPE_MULT_COMPACT[c] : PIPE_MULT[c]);
     if (const char *e = getenv("CBCG_PIPE_MULTS")) {        /* tuning: one multiplier per chunk instead of the linear ramp */
         double m[PIPE_CHUNKS]; int k = 0; const char *q = e;
         while (k < (int)PIPE_CHUNKS) { char *end; m[k] = strtod(q, &end); if (end == q || m[k] < 0.05 || m[k] > 8.0) break; k++; if (*end != ',') break; q = end + 1; }
@@ -1034,6 +1175,7 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     uint64_t tile_off = 0;
     for (uint32_t c = 0; c <= PIPE_CHUNKS; c++) {
         CU(cudaStreamWaitEvent(ctx->st, ctx->cev[c], 0));
+        if (src.compact) TRY(compact_unpack_range(ctx, src.compact, cut[c], cut[c + 1], ctx->st));   /* 2-bit SEQ, lengths, runs -> the SoA batch */
         /* K1 on the chunk; its edit entries continue the previous chunk's */
         if (launch_extract(ctx->db, ctx->dg, ctx->recs.as<cbcg_read_rec>(), ctx->edits.as<uint16_t>(), edits_cap,
                            ctx->tile_desc.as<uint64_t>() + tile_off, wptr<uint32_t>(ctx, W_OFF(ticket)), &chain[(c + 1u) & 1u],
@@ -1108,14 +1250,13 @@ static int encode_pipelined(cbcg_ctx *ctx, const cbcg_batch *b, const cbcg_encod
     return CBCG_OK;
 }
 
-extern "C" int cbcg_encode(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_encode_opts *opts,
-                           uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+static int encode_from(cbcg_ctx *ctx, const BatchSrc &src, const cbcg_encode_opts *opts, uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
     if (!ctx || !out_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_encode: bad argument");
     TRY(validate_opts(ctx, opts));
-    if (opts->block_reads == CBCG_BLOCK_AUTO && opts->gen_mode == 1 && batch && batch->n_reads >= pipe_min_reads()) {
-        TRY(check_batch(ctx, batch));
+    if (src.compact) TRY(check_compact(ctx, src.compact)); else TRY(check_batch(ctx, src.full));
+    if (opts->block_reads == CBCG_BLOCK_AUTO && opts->gen_mode == 1 && src.n >= pipe_min_reads()) {
         CU(cudaSetDevice(ctx->device));
-        const int rc = encode_pipelined(ctx, batch, opts);
+        const int rc = encode_pipelined(ctx, src, opts);
         if (rc < 0) { pipe_drain(ctx); return rc; }          /* copies from the caller's batch may still be queued */
         if (rc == CBCG_OK) return cbcg_fetch_container(ctx, out, out_cap, out_len);
         if (ctx->have_batch) {                              /* fallback with the batch already resident */
@@ -1123,11 +1264,23 @@ extern "C" int cbcg_encode(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_en
             return cbcg_fetch_container(ctx, out, out_cap, out_len);
         }
     }
-    TRY(cbcg_batch_upload(ctx, batch));
+    if (src.compact) TRY(cbcg_batch_upload_compact(ctx, src.compact)); else TRY(cbcg_batch_upload(ctx, src.full));
     const float ms_h2d = ctx->stats.ms_h2d; const uint64_t h2d = ctx->stats.h2d_bytes;
     TRY(cbcg_encode_resident(ctx, opts));
     ctx->stats.ms_h2d = ms_h2d; ctx->stats.h2d_bytes = h2d;
     return cbcg_fetch_container(ctx, out, out_cap, out_len);
+}
+extern "C" int cbcg_encode(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_encode_opts *opts,
+                           uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+    if (!batch) return fail(ctx, CBCG_ERR_ARG, "NULL batch");
+    const BatchSrc src = { batch, nullptr, batch->n_reads };
+    return encode_from(ctx, src, opts, out, out_cap, out_len);
+}
+extern "C" int cbcg_encode_compact(cbcg_ctx *ctx, const cbcg_batch_compact *batch, const cbcg_encode_opts *opts,
+                                   uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+    if (!batch) return fail(ctx, CBCG_ERR_ARG, "NULL batch");
+    const BatchSrc src = { nullptr, batch, batch->n_reads };
+    return encode_from(ctx, src, opts, out, out_cap, out_len);
 }
 
 /* ------------------------------------------------------------------------------------------------ symbol lists */

@@ -330,3 +330,119 @@ void cbch_batch_view(const cbch_batch *b, cbcg_batch *v) {
     v->n_reads = b->n_reads; v->pos = b->pos; v->flag = b->flag; v->seq_len = b->seq_len; v->chr = b->chr;
     v->seq_off = b->seq_off; v->seq = b->seq; v->cigar_off = b->cigar_off; v->cigar = b->cigar; v->md_off = b->md_off; v->md = b->md;
 }
+
+
+/* ------------------------------------------------------------------------------------------------ compact batches */
+typedef struct {
+    const cbcg_batch *b; cbch_compact *c; uint64_t r0, r1;
+    uint8_t *seq2; uint16_t *cl, *ml; uint64_t *so, *co, *mo;
+    uint64_t n_exc; uint32_t *er; uint16_t *eb; uint8_t *ec; uint64_t exc_cap; int oom;
+} pack_job;
+static inline unsigned base2(uint8_t ch) { return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u; }
+static void pack_part(pack_job *j) {
+    const cbcg_batch *b = j->b;
+    for (uint64_t r = j->r0; r < j->r1; r++) {
+        const uint8_t *s = b->seq + b->seq_off[r];
+        const uint32_t len = b->seq_len[r];
+        uint8_t *d = j->seq2 + j->so[r];
+        for (uint32_t i = 0; i < len; i += 4) {
+            unsigned byte = 0;
+            for (uint32_t k = 0; k < 4 && i + k < len; k++) {
+                unsigned c2 = base2(s[i + k]);
+                if (c2 > 3u) {
+                    if (j->n_exc == j->exc_cap) {
+                        uint64_t nc = j->exc_cap ? j->exc_cap * 2 : 1024;
+                        uint32_t *er = realloc(j->er, nc * 4); uint16_t *eb = realloc(j->eb, nc * 2); uint8_t *ec = realloc(j->ec, nc);
+                        if (!er || !eb || !ec) { j->oom = 1; free(er ? er : j->er); free(eb ? eb : j->eb); free(ec ? ec : j->ec); j->er = NULL; j->eb = NULL; j->ec = NULL; return; }
+                        j->er = er; j->eb = eb; j->ec = ec; j->exc_cap = nc;
+                    }
+                    j->er[j->n_exc] = (uint32_t)r; j->eb[j->n_exc] = (uint16_t)(i + k); j->ec[j->n_exc] = s[i + k]; j->n_exc++;
+                    c2 = 0;
+                }
+                byte |= c2 << (2 * k);
+            }
+            d[i >> 2] = (uint8_t)byte;
+        }
+        j->cl[r] = (uint16_t)(b->cigar_off[r + 1] - b->cigar_off[r]);
+        j->ml[r] = (uint16_t)(b->md_off[r + 1] - b->md_off[r]);
+    }
+}
+static void *pack_thread(void *arg) { pack_part((pack_job *)arg); return NULL; }
+
+void cbch_free_compact(cbch_compact *c) {
+    if (!c) return;
+    void (*rel)(void *) = c->release ? c->release : free;
+    cbcg_batch_compact *v = &c->v;
+    rel((void *)v->pos); rel((void *)v->flag); rel((void *)v->seq_len); rel((void *)v->cigar_len); rel((void *)v->md_len);
+    rel((void *)v->run_first); rel((void *)v->run_chr); rel((void *)v->seq2); rel((void *)v->exc_read); rel((void *)v->exc_base); rel((void *)v->exc_char);
+    rel((void *)v->cigar); rel((void *)v->md);
+    rel((void *)v->tile_base);
+    memset(c, 0, sizeof *c);
+}
+
+int cbch_pack_batch(const cbcg_batch *b, int n_threads, void *(*alloc)(size_t), void (*release)(void *), cbch_compact *out) {
+    memset(out, 0, sizeof *out);
+    if (!alloc) { alloc = malloc; release = free; }
+    out->alloc = alloc; out->release = release;
+    const uint64_t n = b->n_reads;
+    cbcg_batch_compact *v = &out->v;
+    v->n_reads = n;
+    if (!n) return CBCH_OK;
+    if (n_threads <= 0) n_threads = cbch_default_threads();
+    if ((uint64_t)n_threads > n) n_threads = (int)n;
+    uint64_t *so = malloc((n + 1) * 8), *co = malloc((n + 1) * 8), *mo = malloc((n + 1) * 8);
+    if (!so || !co || !mo) { free(so); free(co); free(mo); return CBCH_ERR_NOMEM; }
+    uint64_t o = 0, n_runs = 0;
+    for (uint64_t r = 0; r < n; r++) {
+        so[r] = o; o += ((uint64_t)b->seq_len[r] + 3u) >> 2;
+        co[r] = b->cigar_off[r] - b->cigar_off[0]; mo[r] = b->md_off[r] - b->md_off[0];
+        if (r == 0 || b->chr[r] != b->chr[r - 1]) n_runs++;
+    }
+    so[n] = o; co[n] = b->cigar_off[n] - b->cigar_off[0]; mo[n] = b->md_off[n] - b->md_off[0];
+    {   /* one entry per tile of 128 reads, and the totals */
+        const uint64_t tiles = (n + 127u) / 128u;
+        uint64_t *tb = alloc((tiles + 1) * 32);
+        v->tile_base = tb;
+        if (!tb) { free(so); free(co); free(mo); return CBCH_ERR_NOMEM; }
+        uint32_t mx = 0, mn = 0xffffffffu;
+        const uint64_t s0 = b->seq_off[0];
+        for (uint64_t r = 0; r < n; r++) { const uint32_t l = b->seq_len[r]; if (l > mx) mx = l; if (l < mn) mn = l; }
+        for (uint64_t t = 0; t <= tiles; t++) { const uint64_t r = t * 128u < n ? t * 128u : n; tb[4 * t] = b->seq_off[r] - s0; tb[4 * t + 1] = so[r]; tb[4 * t + 2] = co[r]; tb[4 * t + 3] = mo[r]; }
+        v->max_len = mx; v->min_len = mn;
+    }
+    uint32_t *pos = alloc(n * 4); uint16_t *flag = alloc(n * 2), *sl = alloc(n * 2), *cl = alloc(n * 2), *ml = alloc(n * 2);
+    uint64_t *rf = alloc(n_runs * 8); uint32_t *rc = alloc(n_runs * 4);
+    uint8_t *seq2 = alloc(o + 64), *cig = alloc(co[n] + 64), *md = alloc(mo[n] + 64);
+    v->pos = pos; v->flag = flag; v->seq_len = sl; v->cigar_len = cl; v->md_len = ml; v->run_first = rf; v->run_chr = rc; v->seq2 = seq2; v->cigar = cig; v->md = md;
+    if (!pos || !flag || !sl || !cl || !ml || !rf || !rc || !seq2 || !cig || !md) { free(so); free(co); free(mo); cbch_free_compact(out); return CBCH_ERR_NOMEM; }
+    memcpy(pos, b->pos, n * 4); memcpy(flag, b->flag, n * 2); memcpy(sl, b->seq_len, n * 2);
+    memcpy(cig, b->cigar + b->cigar_off[0], co[n]); memcpy(md, b->md + b->md_off[0], mo[n]);
+    { uint64_t k = 0; for (uint64_t r = 0; r < n; r++) if (r == 0 || b->chr[r] != b->chr[r - 1]) { rf[k] = r; rc[k] = b->chr[r]; k++; } v->n_runs = (uint32_t)n_runs; }
+    pack_job *jobs = calloc((size_t)n_threads, sizeof *jobs);
+    pthread_t *th = calloc((size_t)n_threads, sizeof *th);
+    if (!jobs || !th) { free(jobs); free(th); free(so); free(co); free(mo); cbch_free_compact(out); return CBCH_ERR_NOMEM; }
+    for (int t = 0; t < n_threads; t++) {
+        jobs[t].b = b; jobs[t].c = out; jobs[t].r0 = n * (uint64_t)t / (uint64_t)n_threads; jobs[t].r1 = n * (uint64_t)(t + 1) / (uint64_t)n_threads;
+        jobs[t].seq2 = seq2; jobs[t].cl = cl; jobs[t].ml = ml; jobs[t].so = so; jobs[t].co = co; jobs[t].mo = mo;
+    }
+    int started = 0;
+    for (int t = 1; t < n_threads; t++) { if (pthread_create(&th[t], NULL, pack_thread, &jobs[t])) break; started = t; }
+    for (int t = started + 1; t < n_threads; t++) pack_part(&jobs[t]);
+    pack_part(&jobs[0]);
+    for (int t = 1; t <= started; t++) pthread_join(th[t], NULL);
+    uint64_t n_exc = 0; int oom = 0;
+    for (int t = 0; t < n_threads; t++) { n_exc += jobs[t].n_exc; oom |= jobs[t].oom; }
+    if (!oom && n_exc) {
+        uint32_t *er = alloc(n_exc * 4); uint16_t *eb = alloc(n_exc * 2); uint8_t *ec = alloc(n_exc);
+        v->exc_read = er; v->exc_base = eb; v->exc_char = ec;
+        if (!er || !eb || !ec) oom = 1;
+        else { uint64_t k = 0; for (int t = 0; t < n_threads; t++) { memcpy(er + k, jobs[t].er, jobs[t].n_exc * 4); memcpy(eb + k, jobs[t].eb, jobs[t].n_exc * 2); memcpy(ec + k, jobs[t].ec, jobs[t].n_exc); k += jobs[t].n_exc; } }
+    }
+    v->n_exc = oom ? 0 : n_exc;
+    for (int t = 0; t < n_threads; t++) { free(jobs[t].er); free(jobs[t].eb); free(jobs[t].ec); }
+    free(jobs); free(th);
+    out->bytes = n * (4 + 2 + 2 + 2 + 2) + o + co[n] + mo[n] + n_runs * 12 + n_exc * 7 + ((n + 127u) / 128u + 1) * 32;
+    free(so); free(co); free(mo);
+    if (oom) { cbch_free_compact(out); return CBCH_ERR_NOMEM; }
+    return CBCH_OK;
+}

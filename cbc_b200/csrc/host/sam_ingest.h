@@ -46,6 +46,17 @@ int  cbch_default_threads(void);
 void cbch_free_batch(cbch_batch *b);
 void cbch_batch_view(const cbch_batch *b, cbcg_batch *view);
 
+/* The compact form of a batch (cbcg_batch_compact, include/cbcg.h): what crosses the host-device link. All arrays are
+ * allocated with `alloc` (NULL: malloc; pass cbcg_host_alloc for page-locked memory) and released with cbch_free_compact
+ * through `release`. n_threads <= 0: the default worker count. */
+typedef struct cbch_compact {
+    cbcg_batch_compact v;                 /* the view handed to cbcg_encode_compact */
+    void *(*alloc)(size_t); void (*release)(void *);
+    uint64_t bytes;                       /* what will cross the link */
+} cbch_compact;
+int  cbch_pack_batch(const cbcg_batch *b, int n_threads, void *(*alloc)(size_t), void (*release)(void *), cbch_compact *out);
+void cbch_free_compact(cbch_compact *c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,11 @@ int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32
                        const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len, uint32_t fixed_len,
                        uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
                        unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop);
+/* k0_unpack.cu: reads [r_begin, r_end) of a compact batch (r_begin a multiple of 128) -> the SoA batch */
+int launch_unpack(uint64_t r_begin, uint64_t r_end, uint64_t n_reads, const uint16_t *seq_len, const uint16_t *cigar_len, const uint16_t *md_len,
+                  const uint8_t *seq2, const uint64_t *tile_base, const uint64_t *run_first, const uint32_t *run_chr, uint32_t n_runs,
+                  uint64_t *seq_off, uint64_t *cigar_off, uint64_t *md_off, uint8_t *seq, uint32_t *chr, unsigned long long *err, cudaStream_t st);
+int launch_patch(const uint32_t *exc_read, const uint16_t *exc_base, const uint8_t *exc_char, uint64_t n_exc, const uint64_t *seq_off, uint8_t *seq, cudaStream_t st);
 uint64_t extract_num_tiles(uint64_t n_reads);
 uint64_t reconstruct_num_tiles(uint64_t n_reads);
 int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap,

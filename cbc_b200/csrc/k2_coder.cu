@@ -1561,6 +1561,7 @@ __global__ void merge_var_finish_kernel(MergeParams P);
 void extract_set_carveout(int pct);        /* k1_extract.cu */
 void reconstruct_set_carveout(int pct);    /* k3_reconstruct.cu */
 void roles_set_carveout(int pct);          /* k2_blocks.cu */
+void unpack_set_carveout(int pct);         /* k0_unpack.cu */
 template <class K> static void set_carveout(K kernel, int pct) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }
 /* pct = -1: every kernel gets the split the driver prefers for it (best for each kernel on its own: the one-stream
  * calls); 0..100: that share of shared memory for all of them (the pipelined calls). */
@@ -1576,7 +1577,7 @@ void set_carveout_all(int pct) {
     set_carveout(k2_plan_kernel, pct); set_carveout(k2_payload_scan_kernel, pct); set_carveout(k2_gather_kernel, pct);
     set_carveout(snapshot_copy_kernel, pct);
     set_carveout(merge_prep_kernel, pct); set_carveout(merge_add_kernel, pct); set_carveout(merge_finish_kernel, pct); set_carveout(merge_var_finish_kernel, pct);
-    extract_set_carveout(pct); reconstruct_set_carveout(pct); roles_set_carveout(pct);
+    extract_set_carveout(pct); reconstruct_set_carveout(pct); roles_set_carveout(pct); unpack_set_carveout(pct);
 }
 
 int launch_block_kernel(const CoderParams &p, cudaStream_t st);

@@ -55,6 +55,35 @@ typedef struct cbcg_batch {
     const uint64_t *md_off;     const uint8_t *md;      /* MD:Z payload (read_line_t.edits) */
 } cbcg_batch;
 
+/* The same batch in the form that crosses the host-device link (about 60 bytes per 150-base read instead of 196): SEQ at
+ * 2 bits per base, every read starting on a byte (ceil(len / 4) bytes; base i in bits 2 (i & 3) of byte i >> 2;
+ * A C G T = 0 1 2 3), whatever is not A, C, G or T listed apart (packed as 0); CIGAR and MD text as lengths, not offsets;
+ * chromosomes as runs (reads are sorted). tile_base holds, for every tile of 128 reads and once more for the end of the
+ * batch, the bytes of SEQ, seq2, CIGAR and MD text that precede it (4 x u64 per entry): the library cuts the batch
+ * into pipeline chunks at tile boundaries with it, the per-read offsets are rebuilt on the device (which also checks
+ * the lengths against it), where the batch is unpacked into the cbcg_batch layout before K1 reads it.
+ * cbch_pack_batch (csrc/host/sam_ingest.h) makes one from a cbcg_batch; the SAM ingest can fill one directly. */
+typedef struct cbcg_batch_compact {
+    uint64_t n_reads;
+    const uint32_t *pos;
+    const uint16_t *flag;
+    const uint16_t *seq_len;
+    const uint16_t *cigar_len;
+    const uint16_t *md_len;
+    uint32_t n_runs; uint32_t pad;
+    const uint64_t *run_first;  /* first read ordinal of each chromosome run, ascending; run_first[0] == 0 */
+    const uint32_t *run_chr;    /* its chromosome ordinal */
+    const uint8_t *seq2;
+    uint64_t n_exc;             /* bases that are not A / C / G / T */
+    const uint32_t *exc_read;   /* read ordinal, ascending */
+    const uint16_t *exc_base;   /* index of the base in the read */
+    const uint8_t *exc_char;    /* the character */
+    const uint8_t *cigar;
+    const uint8_t *md;
+    const uint64_t *tile_base;  /* ((n_reads + 127) / 128 + 1) x { SEQ bytes, seq2 bytes, CIGAR bytes, MD bytes } before the tile */
+    uint32_t max_len, min_len;  /* longest / shortest SEQ */
+} cbcg_batch_compact;
+
 /* block_reads value that lets the library size blocks so that the last generation fills the GPU's resident
  * block slots a whole number of times (reads per block <= CBCG_BLOCK_AUTO_MAX). The choice is written to the
  * container header like any other block size. */
@@ -126,6 +155,10 @@ int cbcg_extract_symbols(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_enco
 int cbcg_encode(cbcg_ctx *ctx, const cbcg_batch *batch, const cbcg_encode_opts *opts,
                 uint8_t *out, uint64_t out_cap, uint64_t *out_len);
 uint64_t cbcg_encode_bound(const cbcg_batch *batch, const cbcg_encode_opts *opts);
+/* The same from a compact batch: a third of the bytes on the link, the same container byte for byte. */
+int cbcg_encode_compact(cbcg_ctx *ctx, const cbcg_batch_compact *batch, const cbcg_encode_opts *opts,
+                        uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+int cbcg_batch_upload_compact(cbcg_ctx *ctx, const cbcg_batch_compact *batch);   /* becomes the resident batch */
 
 /* ---- K2 + K3: decode. Replaces decompress() + print_line (src/compression.c:173-216, 16-40):
  * seq_out receives SEQ + '\n' per read. legacy != 0: `in` is a bare reference stream. */

@@ -325,3 +325,30 @@ def test_config2_slice_roundtrip_and_resident_path(codec):
         codec.encode_resident(150, 1024, gen_mode)
         assert codec.fetch_container().tobytes() == cont
     assert sizes[1] < 0.8 * sizes[0]              # primed blocks recover most of the cold-start loss
+
+
+def test_cigar_operations_beyond_midS_on_the_gpu(codec):
+    """K1 reads a CIGAR as written -- H and P skipped, = and X counted as M -- like the restatement (which is pinned to the
+    reference where the reference's own parser survives them: tests/test_oracle_vs_reference.py); a skipped region (N)
+    is an input error."""
+    from test_oracle_vs_reference import _rewrite_cigars, _eqx_from_md
+    from cbc_b200.codec import CbcgError
+    g, plain = _synth(seed=131, genome_len=200_000, n_reads=6_000, len_min=100, len_max=100, p_sub=0.01, p_indel=0.004)
+
+    def respell(r, cigar, md):
+        if b"I" in cigar or b"D" in cigar:
+            return b"4H" + cigar + b"6H"
+        return cigar + b"7H" if r % 3 == 0 else _eqx_from_md(100, md) if r % 3 == 1 else b"3H" + cigar + b"2P"
+    b = _rewrite_cigars(plain, respell)
+    codec.set_reference(g)
+    recs, edits = codec.extract(b)
+    orecs, oedits = O.extract(plain, g)
+    assert np.array_equal(recs, orecs) and np.array_equal(edits, oedits)
+    stream = codec.compress(b, 100, block_reads=0)
+    assert stream == O.encode_legacy(plain, g, 100)[0]
+    text, n = codec.decompress(stream, legacy=True)
+    assert n == b.n_reads and text == b.seq_lines()
+    bad = _rewrite_cigars(plain, lambda r, cigar, md: b"50M100N50M" if r == 17 else cigar)
+    with pytest.raises(CbcgError) as e:
+        codec.extract(bad)
+    assert e.value.status == -6

@@ -99,3 +99,67 @@ def test_batch_validation_reports_input_errors():
     c.upload(b)                                              # the context is still usable
     c.encode_resident(100, 128, 0)
     c.close()
+
+
+@pytest.mark.parametrize("name,scale,L", [("config2", 0.01, 150), ("config5", 0.01, 250), ("config4", 0.0005, 150)])
+def test_compact_batch_gives_the_same_container(name, scale, L):
+    """cbcg_encode_compact: the batch crosses the link at 2 bits per base and is unpacked on the device (k0_unpack.cu); the
+    container is the cbcg_encode one byte for byte -- small batches (one-stream path), bases that are not A/C/G/T, several
+    chromosomes, variable length."""
+    from cbc_b200.codec import CompactBatch
+    cfg = synth.SynthConfig.named(name, scale=scale)
+    cfg.p_n = 0.003
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    c = Codec(0)
+    c.set_reference(g)
+    cb = CompactBatch(b)
+    assert cb.link_bytes < 0.45 * (b.seq.nbytes + b.cigar.nbytes + b.md.nbytes + b.n_reads * 36)
+    for R, gm in ((AUTO, 1), (300, 0), (0, 0)):
+        want = c.compress(b, L, R, gm)
+        out = np.empty(len(want) + 4096, np.uint8)
+        n = c.compress_compact_into(cb, L, R, out, gm)
+        assert out[:n].tobytes() == want
+    c.upload_compact(cb)
+    recs, edits = c.extract(b)                                # K1 over a normally uploaded batch ...
+    c.upload_compact(cb)
+    c.encode_resident(L, 256, 1)
+    text, nr = c.decompress(c.fetch_container().tobytes())
+    assert nr == b.n_reads and text == b.seq_lines()
+    cb.close(); c.close()
+
+
+def test_compact_batch_through_the_pipelined_encode(monkeypatch):
+    from cbc_b200.codec import CompactBatch
+    monkeypatch.setenv("CBCG_PIPE_MIN_READS", "200000")
+    cfg = synth.SynthConfig.named("config2", scale=0.2)       # ~600 k reads: the chunked, overlapped path
+    cfg.p_n = 0.001
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    c = Codec(0)
+    c.set_reference(g)
+    want = c.compress(b, 150, AUTO, 1)
+    cb = CompactBatch(b)
+    out = np.empty(len(want) + 65536, np.uint8)
+    n = c.compress_compact_into(cb, 150, AUTO, out, 1)
+    got = out[:n].tobytes()
+    # the encoder sizes last-generation blocks by how fast the batch arrives (a flatter ramp for the compact form): another
+    # cut than the plain batch's, and the CPU restatement given that cut writes the same bytes
+    import oracle_lib as O
+    assert got == O.encode_like(got, b, g)
+    assert abs(len(got) - len(want)) < 0.002 * len(want)
+    st = c.stats()
+    assert st["h2d_bytes"] < 0.45 * (b.seq.nbytes + b.cigar.nbytes + b.md.nbytes + b.n_reads * 36)
+    text, nr = c.decompress(got)
+    assert nr == b.n_reads and text == b.seq_lines()
+    # lengths that disagree with the tile offsets are caught on the device
+    import ctypes as C
+    sl = np.ctypeslib.as_array(C.cast(cb.c.v.seq_len, C.POINTER(C.c_uint16)), (b.n_reads,))
+    sl[1000] += 1
+    with pytest.raises(CbcgError) as e:
+        c.compress_compact_into(cb, 150, AUTO, out, 1)
+    assert e.value.status == -6
+    sl[1000] -= 1
+    n2 = c.compress_compact_into(cb, 150, AUTO, out, 1)     # and the context is still usable
+    assert out[:n2].tobytes() == got
+    cb.close(); c.close()

@@ -159,3 +159,48 @@ def test_threaded_ingest_does_not_depend_on_the_worker_count(lib):
             hb = HBatch()
             assert lib.cbch_read_sam_mt(sam.encode(), C.byref(f_), 0, T, C.byref(hb), err, 256) == -5
             assert err.value.decode().startswith(f"line {bad_at + 1}:"), (T, err.value)
+
+
+def test_compact_batch_packer_round_trips():
+    """cbch_pack_batch (2 bits per base, text lengths, chromosome runs, a list for whatever is not A/C/G/T): unpacked on
+    the host it is the batch again, whatever the worker count."""
+    import ctypes as C
+    from cbc_b200 import synth
+    from cbc_b200.codec import CompactBatch
+    cfg = synth.SynthConfig(seed=3, genome_len=200_000, n_chr=3, n_reads=5000, len_min=50, len_max=250, p_sub=0.01, p_indel=0.01,
+                            p_clip=0.2, p_n=0.01)
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    images = []
+    for threads in (1, 3, 8):
+        c = CompactBatch(b, pinned=False, threads=threads)
+        v = c.c.v
+        n = v.n_reads
+        assert n == b.n_reads and v.n_runs == 3
+
+        def arr(ptr, ct, m):
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), (m,)).copy() if m else np.zeros(0, np.uint64)
+        so = np.concatenate([[0], np.cumsum((b.seq_len.astype(np.uint64) + 3) // 4)]).astype(np.uint64)
+        tb = arr(v.tile_base, C.c_uint64, 4 * ((n + 127) // 128 + 1)).reshape(-1, 4)
+        cut = np.minimum(np.arange(tb.shape[0]) * 128, n)
+        assert np.array_equal(tb[:, 0], b.seq_off[cut]) and np.array_equal(tb[:, 1], so[cut])
+        assert np.array_equal(tb[:, 2], b.cigar_off[cut]) and np.array_equal(tb[:, 3], b.md_off[cut])
+        assert v.max_len == int(b.seq_len.max()) and v.min_len == int(b.seq_len.min())
+        seq2 = arr(v.seq2, C.c_uint8, int(so[n]))
+        lut = np.frombuffer(b"ACGT", np.uint8)
+        out = []
+        for r in range(n):
+            by = seq2[int(so[r]):int(so[r + 1])]
+            out.append(lut[np.stack([(by >> (2 * k)) & 3 for k in range(4)], axis=1).reshape(-1)[:int(b.seq_len[r])]])
+        seq = np.concatenate(out)
+        er, eb, ec = arr(v.exc_read, C.c_uint32, v.n_exc), arr(v.exc_base, C.c_uint16, v.n_exc), arr(v.exc_char, C.c_uint8, v.n_exc)
+        assert v.n_exc > 0 and np.all(np.diff(er.astype(np.int64)) >= 0)
+        seq[b.seq_off[er].astype(np.int64) + eb] = ec
+        assert np.array_equal(seq, b.seq[:len(seq)])
+        assert np.array_equal(arr(v.cigar_len, C.c_uint16, n), np.diff(b.cigar_off).astype(np.uint16))
+        assert np.array_equal(arr(v.md_len, C.c_uint16, n), np.diff(b.md_off).astype(np.uint16))
+        assert np.array_equal(arr(v.run_chr, C.c_uint32, 3), np.array([0, 1, 2], np.uint32))
+        assert c.link_bytes < 0.45 * (b.seq.nbytes + b.cigar.nbytes + b.md.nbytes + n * 36)
+        images.append((seq2.tobytes(), er.tobytes(), eb.tobytes(), ec.tobytes()))
+        c.close()
+    assert images[0] == images[1] == images[2]

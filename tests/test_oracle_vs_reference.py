@@ -190,3 +190,137 @@ def test_known_answer_survey_appendix_a():
               (S["var"], 1, 17), (S["var"], 35, 0), (S["var"], 35, 74), (S["var"], 183, 0), (S["var"], 183, 0),
               (S["var"], 1, 49), (S["chars"], 5, 0), (S["var"], 99, 41), (S["chars"], 5, 1)]
     assert body[:len(expect)] == expect
+
+
+def _rewrite_cigars(b: Batch, fn) -> Batch:
+    """The batch with every read's CIGAR text replaced by fn(read ordinal, cigar bytes, md bytes)."""
+    cig = [fn(r, b.cigar[int(b.cigar_off[r]):int(b.cigar_off[r + 1])].tobytes(), b.md[int(b.md_off[r]):int(b.md_off[r + 1])].tobytes())
+           for r in range(b.n_reads)]
+    off = np.zeros(b.n_reads + 1, np.uint64)
+    off[1:] = np.cumsum([len(x) for x in cig])
+    return Batch(b.pos, b.flag, b.seq_len, b.chr, b.seq_off, b.seq, off, np.frombuffer(b"".join(cig), np.uint8).copy(), b.md_off, b.md)
+
+
+def _eqx_from_md(length: int, md: bytes) -> bytes:
+    """'100M' with MD '60A39' -> '60=1X39=' (substitution-only reads)."""
+    import re
+    out, run = [], 0
+    for tok in re.findall(rb"\d+|[A-Z]", md):
+        if tok.isdigit():
+            if int(tok):
+                out.append(b"%d=" % int(tok))
+        else:
+            out.append(b"1X")
+    return b"".join(out) or b"%d=" % length
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built")
+def test_live_reference_leading_hard_clips():
+    """CIGAR operations the reference does not know (src/read_compression.c:543-547: `default: break`, which leaves the
+    operation's count in front of the next one and never advances past it). A LEADING hard clip on a read without
+    insertions, deletions or soft clips is harmless there (nobody uses the M count), and common in real files: the
+    restatement, which skips H / P, writes the reference's stream byte for byte and both decoders return the reads."""
+    cfg = synth.SynthConfig(seed=131, genome_len=200_000, n_reads=6_000, len_min=100, len_max=100, p_sub=0.01)
+    g = synth.make_genome(cfg)
+    plain = synth.make_reads(cfg, g)
+    b = _rewrite_cigars(plain, lambda r, cigar, md: (b"5H" + cigar) if r % 2 == 0 else cigar)
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g)
+        synth.write_sam(sam, b, g)
+        ref_stream, ref_trace, _ = O.run_reference(sam, fa, d, trace=True)
+        stream, trace = O.encode_legacy(b, g, 100, want_trace=True)
+        assert stream == ref_stream and np.array_equal(trace, ref_trace)
+        ref_decoded, _ = O.run_reference_decode(os.path.join(d, "ref.cbc"), fa, d)
+    assert O.encode_legacy(plain, g, 100)[0] == stream            # the clips change nothing in the stream
+    decoded, _ = O.decode_legacy(stream, g)
+    assert decoded == ref_decoded == b.seq_lines()
+
+
+def test_trailing_hard_clips_and_eq_x_cigars_are_read_as_written():
+    """A CIGAR that ENDS in an operation the reference does not know ("100M7H", "60=1X39=") sends its parser past the end
+    of the string (`while (*cigar != 0)` with a pointer that no longer advances: src/read_compression.c:308, :543):
+    undefined behaviour, typically the `pos == chrPos` assertion of :41. Here they are read as written -- H and P
+    skipped, = and X counted as M -- and give the stream of the plain spelling."""
+    cfg = synth.SynthConfig(seed=131, genome_len=200_000, n_reads=3_000, len_min=100, len_max=100, p_sub=0.01)
+    g = synth.make_genome(cfg)
+    plain = synth.make_reads(cfg, g)
+
+    def respell(r, cigar, md):
+        return cigar + b"7H" if r % 3 == 0 else _eqx_from_md(100, md) if r % 3 == 1 else b"3H" + cigar + b"2P"
+    b = _rewrite_cigars(plain, respell)
+    stream, _ = O.encode_legacy(b, g, 100)
+    assert stream == O.encode_legacy(plain, g, 100)[0]
+    decoded, _ = O.decode_legacy(stream, g)
+    assert decoded == b.seq_lines()
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built")
+def test_unknown_cigar_operation_before_an_indel_is_where_the_reference_breaks():
+    """"5H40M1I59M": the reference adds 5 (the hard clip's count, still in front of the M) instead of 40 to its match
+    counter, so the insertion is recorded at the wrong place and its own decoder does not return the read
+    (degraded contracts). The restatement -- and K1, which is held to it -- parse the CIGAR as
+    written and round-trip; the streams differ by design."""
+    cfg = synth.SynthConfig(seed=132, genome_len=100_000, n_reads=2_000, len_min=100, len_max=100, p_sub=0.005, p_indel=0.01)
+    g = synth.make_genome(cfg)
+    plain = synth.make_reads(cfg, g)
+    n_indel = sum(1 for r in range(plain.n_reads) if b"I" in plain.cigar[int(plain.cigar_off[r]):int(plain.cigar_off[r + 1])].tobytes())
+    assert n_indel > 100
+    b = _rewrite_cigars(plain, lambda r, cigar, md: b"5H" + cigar)
+    stream, _ = O.encode_legacy(b, g, 100)
+    assert stream == O.encode_legacy(plain, g, 100)[0]            # H skipped: the stream of the unclipped reads
+    decoded, _ = O.decode_legacy(stream, g)
+    assert decoded == b.seq_lines()
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g)
+        synth.write_sam(sam, b, g)
+        try:
+            ref_stream, _, _ = O.run_reference(sam, fa, d)
+        except RuntimeError:
+            return                                                # the reference encoder died on it: nothing to compare
+        assert ref_stream != stream
+        try:
+            ref_decoded, _ = O.run_reference_decode(os.path.join(d, "ref.cbc"), fa, d)
+        except RuntimeError:
+            return                                                # ... or its decoder did
+        assert ref_decoded != b.seq_lines()                       # it decodes to something else than the input
+
+
+def test_spliced_alignment_is_refused():
+    """'N' (a skipped region): the reference ignores it and reconstructs the rest of the read against the wrong reference
+    bases; here it is an input error (CBCG_ERR_INPUT on the GPU, < 0 from the restatement)."""
+    cfg = synth.SynthConfig(seed=133, genome_len=50_000, n_reads=200, len_min=100, len_max=100, p_sub=0.01)
+    g = synth.make_genome(cfg)
+    plain = synth.make_reads(cfg, g)
+    b = _rewrite_cigars(plain, lambda r, cigar, md: b"50M100N50M" if r == 17 else cigar)
+    with pytest.raises(RuntimeError):
+        O.encode_legacy(b, g, 100)
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kw", [
+    dict(seed=141, genome_len=400_000, n_reads=8_000, len_min=50, len_max=250, p_sub=0.005, p_indel=0.02, p_clip=0.3),
+    dict(seed=142, genome_len=300_000, n_reads=10_000, len_min=80, len_max=120, p_sub=0.01, p_indel=0.002),
+])
+def test_live_reference_variable_length_encoder_trace(kw):
+    """Config-5 shape through `program -c 1 -l` (src/main.c:159: the header read length is the longest SEQ): the reference
+    DEcoder cannot decode variable-length reads, but its ENcoder runs, so the restatement's stream and
+    symbol trace are pinned to it; the decode half of the contract is the restatement's own (== input SEQ)."""
+    cfg = synth.SynthConfig(**kw)
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    L = int(b.seq_len.max())
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g)
+        synth.write_sam(sam, b, g)
+        try:
+            ref_stream, ref_trace, _ = O.run_reference(sam, fa, d, trace=True, var_length=True)
+        except RuntimeError as e:
+            pytest.skip(f"the reference encoder does not survive this shape: {e}")
+    stream, trace = O.encode_legacy(b, g, L, want_trace=True)
+    assert stream == ref_stream
+    assert np.array_equal(trace, ref_trace)
+    decoded, n = O.decode_legacy(stream, g)
+    assert n == b.n_reads and decoded == b.seq_lines()
