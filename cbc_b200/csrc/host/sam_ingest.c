@@ -246,17 +246,49 @@ int cbch_read_sam(const char *path, const cbch_fasta *fa, int var_length, cbch_b
 /* The file is cut at line starts into n_threads ranges of about equal bytes; every worker parses its range into its own
  * batch, then copies it to its place in the merged one (two rounds of threads, no locks). The result does not depend
  * on n_threads. */
+int cbch_map(const char *path, int populate, cbch_mapped *out) {
+    out->p = NULL; out->n = 0;
+    out->fd = open(path, O_RDONLY);
+    if (out->fd < 0) return CBCH_ERR_IO;
+    struct stat st;
+    if (fstat(out->fd, &st)) { close(out->fd); out->fd = -1; return CBCH_ERR_IO; }
+    out->n = (uint64_t)st.st_size;
+    if (out->n == 0) return CBCH_OK;
+    void *p = mmap(NULL, (size_t)out->n, PROT_READ, MAP_PRIVATE | (populate ? MAP_POPULATE : 0), out->fd, 0);
+    if (p == MAP_FAILED) { close(out->fd); out->fd = -1; return CBCH_ERR_IO; }
+    madvise(p, (size_t)out->n, MADV_SEQUENTIAL);
+    out->p = (const uint8_t *)p;
+    return CBCH_OK;
+}
+void cbch_unmap(cbch_mapped *m) { if (m->p) munmap((void *)m->p, (size_t)m->n); if (m->fd >= 0) close(m->fd); m->p = NULL; m->fd = -1; }
+const uint8_t *cbch_next_line(const uint8_t *p, const uint8_t *end) {
+    const uint8_t *nl = p < end ? memchr(p, '\n', (size_t)(end - p)) : NULL;
+    return nl ? nl + 1 : end;
+}
+
 int cbch_read_sam_mt(const char *path, const cbch_fasta *fa, int var_length, int n_threads, cbch_batch *b, char *err, size_t errlen) {
     memset(b, 0, sizeof *b);
     mapped m;
     if (map_file(path, &m)) return fail(err, errlen, CBCH_ERR_IO, "cannot open %s", path);
+    const int rc = cbch_ingest_range(m.p, m.p + m.n, fa, var_length, n_threads, 0, b, err, errlen);
+    unmap_file(&m);
+    return rc;
+}
+
+/* The lines of [begin, end) (begin at a line start). header_len != 0: the read length of the stream header is given
+ * (a later batch of a file takes the first batch's: get_read_length looks at the file's second record). */
+int cbch_ingest_range(const uint8_t *begin, const uint8_t *range_end, const cbch_fasta *fa, int var_length, int n_threads, uint32_t header_len,
+                      cbch_batch *b, char *err, size_t errlen) {
+    memset(b, 0, sizeof *b);
+    const char *path = "the SAM input";
+    struct { const uint8_t *p; size_t n; } m = { begin, (size_t)(range_end - begin) };
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 64) n_threads = 64;
     if (m.n < (size_t)n_threads * 4096u) n_threads = (int)(m.n / 4096u) + 1;       /* small files: fewer workers */
     ingest_part *w = calloc((size_t)n_threads, sizeof *w);
     merge_job *jobs = calloc((size_t)n_threads, sizeof *jobs);
     pthread_t *th = calloc((size_t)n_threads, sizeof *th);
-    if (!w || !jobs || !th) { free(w); free(jobs); free(th); unmap_file(&m); return fail(err, errlen, CBCH_ERR_NOMEM, "out of memory"); }
+    if (!w || !jobs || !th) { free(w); free(jobs); free(th); return fail(err, errlen, CBCH_ERR_NOMEM, "out of memory"); }
     const uint8_t *end = m.p + m.n, *cur = m.p;
     for (int t = 0; t < n_threads; t++) {
         const uint8_t *stop = end;
@@ -277,7 +309,6 @@ int cbch_read_sam_mt(const char *path, const cbch_fasta *fa, int var_length, int
     parse_range(&w[0]);
     for (int t = 1; t <= started; t++) pthread_join(th[t], NULL);
     const double t_parsed = now_s();
-    unmap_file(&m);
 
     /* whole-file facts, and the first error in file order */
     int rc = CBCH_OK;
@@ -309,7 +340,7 @@ int cbch_read_sam_mt(const char *path, const cbch_fasta *fa, int var_length, int
         for (int t = 1; t <= started; t++) pthread_join(th[t], NULL);
         b->seq_off[n] = so; b->cigar_off[n] = co; b->md_off[n] = mo;
         /* get_read_length (:47-53): fixed-length mode takes the SECOND record's SEQ length; -l takes the maximum */
-        b->read_len_header = var_length ? b->max_len : (records >= 2 ? lens[1] : lens[0]);
+        b->read_len_header = var_length ? b->max_len : header_len ? header_len : (records >= 2 ? lens[1] : lens[0]);
     }
     const double t_merged = now_s();
     for (int t = 0; t < n_threads; t++) cbch_free_batch(&w[t].part);

@@ -43,6 +43,15 @@ int  cbch_read_sam(const char *path, const cbch_fasta *fa, int var_length, cbch_
  * cut at line starts, the ranges are parsed in parallel and merged; the result does not depend on the count. */
 int  cbch_read_sam_mt(const char *path, const cbch_fasta *fa, int var_length, int n_threads, cbch_batch *out, char *err, size_t errlen);
 int  cbch_default_threads(void);
+/* Streaming: the file mapped once (populate: fault it all in now, for files that fit in memory), cut at line starts with
+ * cbch_next_line, ingested range by range. header_len != 0 overrides the fixed-length header value (later batches of a
+ * file take the first batch's). */
+typedef struct cbch_mapped { const uint8_t *p; uint64_t n; int fd; } cbch_mapped;
+int  cbch_map(const char *path, int populate, cbch_mapped *out);
+void cbch_unmap(cbch_mapped *m);
+const uint8_t *cbch_next_line(const uint8_t *p, const uint8_t *end);
+int  cbch_ingest_range(const uint8_t *begin, const uint8_t *end, const cbch_fasta *fa, int var_length, int n_threads, uint32_t header_len,
+                       cbch_batch *out, char *err, size_t errlen);
 void cbch_free_batch(cbch_batch *b);
 void cbch_batch_view(const cbch_batch *b, cbcg_batch *view);
 

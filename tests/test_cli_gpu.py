@@ -54,3 +54,33 @@ def test_cli_roundtrip_and_reference_compatibility(kw, L):
 def test_cli_errors():
     p = subprocess.run([CLI, "-c", "only_one_file"], capture_output=True, text=True)
     assert p.returncode != 0 and "Missing required filenames" in p.stderr
+
+
+def test_cli_streams_batches_to_several_contexts():
+    """`-B 1 -g 0,0`: the SAM text is cut into 1 MB batches at line starts, parsed and packed on an ingest thread while two
+    device threads (here two contexts on GPU 0: the multi-GPU path) code them, and written in order as one "CBCS" file
+    of self-contained containers; `cbc -d -g 0,0` reads it back, and so does the Python side (cbc_b200.shard)."""
+    from cbc_b200 import shard
+    from cbc_b200.codec import Codec
+    cfg = synth.SynthConfig(seed=43, genome_len=900_000, n_chr=3, n_reads=40_000, len_min=100, len_max=100, p_sub=0.005, p_indel=0.002)
+    g = synth.make_genome(cfg); b = synth.make_reads(cfg, g)
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g); synth.write_sam(sam, b, g)
+        assert os.path.getsize(sam) > 8 << 20
+        out = _run("-c", "-B", "1", "-g", "0,0", sam, os.path.join(d, "a.cbcs"), fa)
+        assert "on 2 device(s)" in out
+        with open(os.path.join(d, "a.cbcs"), "rb") as f:
+            data = f.read()
+        shards = shard.read_shards(data)
+        assert len(shards) >= 8
+        c = Codec(0); c.set_reference(g)
+        text = b"".join(c.decompress(s)[0] for s in shards)
+        c.close()
+        assert text == b.seq_lines()
+        _run("-d", "-g", "0,0", os.path.join(d, "a.cbcs"), os.path.join(d, "a.txt"), fa)
+        with open(os.path.join(d, "a.txt"), "rb") as f:
+            assert f.read() == b.seq_lines()
+        one = _run("-c", sam, os.path.join(d, "one.cbc"), fa)                     # one batch: a plain CBCB container
+        assert "batches 1 " in one
+        assert len(data) < 1.05 * os.path.getsize(os.path.join(d, "one.cbc"))
