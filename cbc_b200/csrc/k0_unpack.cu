@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(K0_TILE) k0_unpack_kernel(UnpackParams P) {
     }
     if (live) {
         P.seq_off[r] = off[0]; P.cigar_off[r] = off[2]; P.md_off[r] = off[3];
-        if (r + 1 == P.n_reads) { P.seq_off[r + 1] = off[0] + v[0]; P.cigar_off[r + 1] = off[2] + v[2]; P.md_off[r + 1] = off[3] + v[3]; }
+        /* the end offset of the range's last read: K1 runs on this range before the next one is unpacked */
+        if (r + 1 == P.r_end) { P.seq_off[r + 1] = off[0] + v[0]; P.cigar_off[r + 1] = off[2] + v[2]; P.md_off[r + 1] = off[3] + v[3]; }
         uint32_t lo = 0, hi = P.n_runs;                       /* the chromosome run this read lies in */
         while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (P.run_first[mid] <= r) lo = mid; else hi = mid; }
         P.chr[r] = P.run_chr[lo];

@@ -141,8 +141,13 @@ def test_compact_batch_through_the_pipelined_encode(monkeypatch):
     want = c.compress(b, 150, AUTO, 1)
     cb = CompactBatch(b)
     out = np.empty(len(want) + 65536, np.uint8)
-    n = c.compress_compact_into(cb, 150, AUTO, out, 1)
+    fresh = Codec(0)                                          # a context whose buffers have never held this batch in any form
+    fresh.set_reference(g)
+    n = fresh.compress_compact_into(cb, 150, AUTO, out, 1)
     got = out[:n].tobytes()
+    fresh.close()
+    n = c.compress_compact_into(cb, 150, AUTO, out, 1)
+    assert out[:n].tobytes() == got
     # the encoder sizes last-generation blocks by how fast the batch arrives (a flatter ramp for the compact form): another
     # cut than the plain batch's, and the CPU restatement given that cut writes the same bytes
     import oracle_lib as O
