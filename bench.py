@@ -705,7 +705,8 @@ def main():
     ap.add_argument("--block-reads", type=int, default=0xffffffff, help="reads per block; default: CBCG_BLOCK_AUTO")
     ap.add_argument("--inflight", type=int, default=1, help="contexts (host threads / streams) the e2e leg keeps in flight")
     ap.add_argument("--gen-mode", type=int, default=1, help="1: generation-primed blocks (default), 0: cold blocks")
-    ap.add_argument("--substreams", type=int, default=1, choices=[1, 4], help="arithmetic-coded streams per block: 1 (default) or 4 (CBCG_MODE_SPLIT4)")
+    ap.add_argument("--substreams", type=int, default=0, choices=[0, 1, 4],
+                    help="arithmetic-coded streams per block: 0 = the library's default (four in the narrow early generations, one in the wide ones), 1, or 4 everywhere")
     ap.add_argument("--e2e-input", default="compact", choices=["compact", "soa"],
                     help="host buffers of the e2e leg: cbcg_batch_compact (2 bits per base; default) or the plain SoA cbcg_batch")
     ap.add_argument("--scale", type=float, default=0.0, help="shrink the workload; default 1.0 (config 4: 0.1, stated in config.workload)")

@@ -79,14 +79,15 @@ struct cbcg_ctx {
     DevBuf recs, edits, chr_out, tile_desc, words, blocks, ws, scratch, payload, out_off, symbols, seq_out;
     DevBuf snap_a, snap_b, fin;                /* generation snapshots and per-block final states (gen_mode 1) */
     std::vector<std::pair<uint32_t, uint32_t>> gens;   /* (first block, block count) per generation of the last cut */
-    uint32_t n_sub = 1;                        /* substreams per block of the call in progress (opts->substreams / the container's mode word) */
+    uint32_t layout = 1;                       /* the call in progress: 1 = one stream per block, 4 = four substreams, 0 = four in the narrow early generations */
+    uint32_t layout_mode = 0;                  /* the same as container mode bits (CBCG_MODE_SPLIT4 / split generations), set by the cut or read from the header */
     uint32_t max_block_reads = 0;              /* longest block of the last cut / index: sets the merged snapshots' FLAG total (cbcg_flag_target) */
     Words *hw = nullptr;                       /* pinned */
     BlockDesc *hblocks = nullptr; size_t hblocks_cap = 0;   /* pinned */
 
     /* result of the last encode */
     bool have_encoded = false;
-    uint32_t enc_L = 0, enc_block_reads = 0, enc_gen_mode = 0, enc_legacy = 0, enc_max_len = 0, enc_fixed = 0, enc_n_sub = 1;
+    uint32_t enc_L = 0, enc_block_reads = 0, enc_gen_mode = 0, enc_legacy = 0, enc_max_len = 0, enc_fixed = 0, enc_layout_mode = 0;
     uint32_t batch_min_len = 0;               /* shortest read of the resident batch (host scan at upload) */
     uint64_t enc_n_reads = 0, enc_n_edits = 0, enc_n_blocks = 0, enc_payload_bytes = 0;
     std::vector<uint8_t> enc_head;             /* container header + index */
@@ -602,7 +603,9 @@ static int cut_blocks(cbcg_ctx *ctx, uint32_t block_reads, uint32_t gen_mode, ui
                       const std::vector<SizeStep> *ramp = nullptr, bool upload = true) {
     const uint64_t n = ctx->db.n_reads;
     uint32_t sched_count[CBCG_GEN_MAX], sched_reads[CBCG_GEN_MAX], sched_last = 0;
-    const uint32_t n_sched = gen_mode ? cbcg_gen_schedule(n, ctx->n_sub, sched_count, sched_reads, &sched_last, nullptr) : 0u;
+    uint32_t split_gens = 0;
+    const uint32_t n_sched = gen_mode ? cbcg_gen_schedule(n, ctx->layout, sched_count, sched_reads, &sched_last, &split_gens) : 0u;
+    ctx->layout_mode = ctx->layout == 4u ? CBCG_MODE_SPLIT4 : (ctx->layout == 0u && gen_mode) ? CBCG_MODE_WITH_SPLIT_GENS(split_gens) : 0u;
     uint64_t bound = 1;
     uint32_t min_reads = block_reads;
     if (ramp) for (const SizeStep &st : *ramp) min_reads = std::min(min_reads, std::max(st.block_reads, 1u));
@@ -650,8 +653,8 @@ static uint32_t auto_block_reads(cbcg_ctx *ctx, uint64_t n, uint32_t gen_mode, u
     if (slots_out) *slots_out = 0;
     if (!gen_mode) return 1024u;
     uint32_t c[CBCG_GEN_MAX], r[CBCG_GEN_MAX], last = 0;
-    const uint32_t k = cbcg_gen_schedule(n, ctx->n_sub, c, r, &last, nullptr);   /* what the <= 1 % budget leaves for the last generation */
-    if (ctx->n_sub > 1u) return last;
+    const uint32_t k = cbcg_gen_schedule(n, ctx->layout, c, r, &last, nullptr);   /* what the <= 1 % budget leaves for the last generation */
+    if (ctx->layout == 4u) return last;
     /* one warp per block: the last generation runs in whole waves of the GPU's resident warps (a few blocks beyond a wave
        cost a whole block time); rounded to fewer, larger blocks, never more */
     uint64_t early = 0;
@@ -668,7 +671,7 @@ static uint32_t auto_block_reads(cbcg_ctx *ctx, uint64_t n, uint32_t gen_mode, u
 /* reads the early generations of the default cut hold (everything but the last generation) */
 static uint64_t sched_early_reads(cbcg_ctx *ctx, uint64_t n, uint32_t *levels_out = nullptr) {
     uint32_t c[CBCG_GEN_MAX], r[CBCG_GEN_MAX], last = 0;
-    const uint32_t k = cbcg_gen_schedule(n, ctx->n_sub, c, r, &last, nullptr);
+    const uint32_t k = cbcg_gen_schedule(n, ctx->layout, c, r, &last, nullptr);
     uint64_t early = 0;
     for (uint32_t g = 0; g < k; g++) early += (uint64_t)c[g] * r[g];
     if (levels_out) *levels_out = k;
@@ -678,6 +681,9 @@ static int ensure_fin(cbcg_ctx *ctx, uint64_t nb) { return ensure(ctx, ctx->fin,
 
 /* Generations 0 .. last-1 of ctx->gens with the merges that build the snapshots; *snap_out = the snapshot the last
  * generation starts from. */
+/* substreams of the blocks of the generation that block k belongs to */
+static uint32_t gen_n_sub(const cbcg_ctx *ctx, uint32_t k) { return CBCG_BLOCK_NSUB(ctx->layout_mode, ctx->hblocks[k].gen); }
+
 static int run_early_generations(cbcg_ctx *ctx, CoderParams p, uint8_t **snap_out, cudaStream_t st = nullptr) {
     if (!st) st = ctx->st;
     const uint64_t sb = snapshot_bytes(p.L);
@@ -688,6 +694,7 @@ static int run_early_generations(cbcg_ctx *ctx, CoderParams p, uint8_t **snap_ou
     ctx->stats.kernel_launches++;
     for (size_t g = 0; g + 1 < ctx->gens.size(); g++) {
         p.block_begin = ctx->gens[g].first; p.n_blocks = ctx->gens[g].second;
+        p.n_sub = gen_n_sub(ctx, p.block_begin);
         p.snap = cur;
         if (launch_coder(p, st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->stats.kernel_launches += roles_launches(p.mode);
@@ -716,6 +723,7 @@ static int run_coder_generations(cbcg_ctx *ctx, CoderParams p, uint64_t nb, bool
     uint8_t *cur = nullptr;
     TRY(run_early_generations(ctx, p, &cur));
     p.block_begin = ctx->gens.back().first; p.n_blocks = ctx->gens.back().second;
+    p.n_sub = gen_n_sub(ctx, p.block_begin);
     p.snap = cur;
     if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     ctx->stats.kernel_launches += roles_launches(p.mode);
@@ -734,10 +742,14 @@ static CoderParams coder_params(cbcg_ctx *ctx, uint32_t n_blocks, uint32_t L, in
     p.chr_names = ctx->g_names.as<uint8_t>();
     p.err = wptr<unsigned long long>(ctx, W_OFF(err));
     p.fin = ctx->fin.as<uint8_t>();                         /* callers ensure_fin(nb) before a blocked launch */
-    p.n_sub = legacy ? 1u : ctx->n_sub;
+    p.layout_mode = legacy ? 0u : ctx->layout_mode;
+    p.n_sub = 1u;                                           /* per launch: gen_n_sub() */
     return p;
 }
 
+/* opts->substreams: 1 = one stream per block, 4 = four substreams, 0 = the default: four in the narrow early generations of
+ * a generation-primed container (they are latency-bound: three times faster as four short chains), one elsewhere */
+static uint32_t opts_layout(const cbcg_encode_opts *o) { return o->substreams == CBCG_N_SUB ? 4u : (o->substreams == 0u && o->gen_mode == 1u) ? 0u : 1u; }
 static int validate_opts(cbcg_ctx *ctx, const cbcg_encode_opts *o) {
     if (!o) return fail(ctx, CBCG_ERR_ARG, "NULL options");
     if (o->read_len_header == 0 || o->read_len_header > CBCG_MAX_READ_LEN) return fail(ctx, CBCG_ERR_ARG, "read_len_header must be in 1..%u", CBCG_MAX_READ_LEN);
@@ -756,10 +768,9 @@ static void finish_encode(cbcg_ctx *ctx, const cbcg_encode_opts *opts, int legac
     h.clear();
     uint64_t n_syms = 0;
     for (uint64_t k = 0; k < nb; k++) n_syms += ctx->hblocks[k].n_symbols;
-    const uint32_t n_sub = opts->substreams == CBCG_N_SUB ? CBCG_N_SUB : 1u;
-    if (!legacy) container_head(h, ctx->db.max_len, L, n, nb, ctx->names, opts->block_reads, opts->gen_mode | (fixed ? CBCG_MODE_FIXED_LEN : 0u) | (n_sub > 1u ? CBCG_MODE_SPLIT4 : 0u), ctx->hblocks);
+    if (!legacy) container_head(h, ctx->db.max_len, L, n, nb, ctx->names, opts->block_reads, opts->gen_mode | (fixed ? CBCG_MODE_FIXED_LEN : 0u) | ctx->layout_mode, ctx->hblocks);
     ctx->enc_L = L; ctx->enc_block_reads = opts->block_reads; ctx->enc_gen_mode = opts->gen_mode; ctx->enc_legacy = legacy;
-    ctx->enc_max_len = ctx->db.max_len; ctx->enc_fixed = fixed ? 1u : 0u; ctx->enc_n_sub = legacy ? 1u : n_sub;
+    ctx->enc_max_len = ctx->db.max_len; ctx->enc_fixed = fixed ? 1u : 0u; ctx->enc_layout_mode = legacy ? 0u : ctx->layout_mode;
     ctx->enc_n_reads = n; ctx->enc_n_edits = n_edits; ctx->enc_n_blocks = nb; ctx->enc_payload_bytes = payload_total;
     ctx->have_encoded = true;
     S.n_reads = n; S.n_blocks = nb; S.n_edits = n_edits; S.n_symbols = n_syms;
@@ -846,10 +857,10 @@ static int encode_resident_overlapped(cbcg_ctx *ctx, const cbcg_encode_opts *opt
     CU(cudaEventRecord(ctx->dev2[1], side));
     CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[1], 0));
     CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[2], 0));
-    q.snap = snap;
+    q.snap = snap; q.n_sub = gen_n_sub(ctx, q.block_begin);
     if (launch_coder(q, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaEventRecord(ctx->ev[3], ctx->st));
-    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->n_sub > 1u ? 1 : 0, ctx->st))
+    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), 1, ctx->layout_mode, ctx->st))
         return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
     S.kernel_launches += 7;                                 /* K1 x 2, plan x 2, last generation, gather x 2 */
     CU(cudaEventRecord(ctx->ev[4], ctx->st));
@@ -886,7 +897,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
     const uint64_t n = ctx->db.n_reads;
     const int legacy = opts->block_reads == 0;
     const uint32_t L = opts->read_len_header;
-    ctx->n_sub = (!legacy && opts->substreams == CBCG_N_SUB) ? CBCG_N_SUB : 1u;
+    ctx->layout = legacy ? 1u : opts_layout(opts);
     cbcg_encode_opts auto_opts = *opts;
     if (opts->block_reads == CBCG_BLOCK_AUTO) {             /* last generation = a whole number of full waves */
         auto_opts.block_reads = auto_block_reads(ctx, n, opts->gen_mode);
@@ -937,7 +948,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
         CU(cudaEventRecord(ctx->ev[3], ctx->st));
         /* compact payload: bounded by the scratch size */
         TRY(ensure(ctx, ctx->payload, pay_cap));
-        if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), (!legacy && ctx->n_sub > 1u) ? 1 : 0, ctx->st))
+        if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), legacy ? 0 : 1, ctx->layout_mode, ctx->st))
             return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
         S.kernel_launches += 3;
         CU(cudaEventRecord(ctx->ev[4], ctx->st));
@@ -1072,7 +1083,7 @@ static void pipe_drain(cbcg_ctx *ctx) {
 }
 static int encode_pipelined(cbcg_ctx *ctx, const BatchSrc &src, const cbcg_encode_opts *opts) {
     const uint64_t n = src.n;
-    ctx->n_sub = opts->substreams == CBCG_N_SUB ? CBCG_N_SUB : 1u;
+    ctx->layout = opts_layout(opts);
     const uint32_t L = opts->read_len_header;
     const uint64_t tile = 128;                              /* K1 tile: chunk boundaries are whole tiles */
     uint32_t levels = 0;
@@ -1210,14 +1221,14 @@ static int encode_pipelined(cbcg_ctx *ctx, const BatchSrc &src, const cbcg_encod
             CU(cudaEventRecord(ctx->kev2[c], ctx->st));
             cudaStream_t sd = ctx->ps[c % PIPE_MAX];
             CU(cudaStreamWaitEvent(sd, ctx->kev2[c], 0));
-            q.snap = snap;
+            q.snap = snap; q.n_sub = gen_n_sub(ctx, q.block_begin);
             if (launch_coder(q, sd)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             S.kernel_launches += roles_launches(q.mode);
             CU(cudaEventRecord(ctx->dev2[c], sd));
         }
     }
     for (uint32_t c = 1; c <= PIPE_CHUNKS; c++) if (gb[c] > gb[c - 1]) CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[c], 0));
-    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), ctx->n_sub > 1u ? 1 : 0, ctx->st))
+    if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), 1, ctx->layout_mode, ctx->st))
         return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
     S.kernel_launches += 2;
     CU(cudaEventRecord(ctx->ev[4], ctx->st));
@@ -1292,7 +1303,7 @@ extern "C" int cbcg_extract_symbols(cbcg_ctx *ctx, const cbcg_batch *batch, cons
     TRY(cbcg_batch_upload(ctx, batch));
     const uint64_t n = ctx->db.n_reads;
     const int legacy = opts->block_reads == 0;
-    ctx->n_sub = (!legacy && opts->substreams == CBCG_N_SUB) ? CBCG_N_SUB : 1u;
+    ctx->layout = legacy ? 1u : opts_layout(opts);
     *n_symbols = 0; if (n_blocks) *n_blocks = 0;
     uint64_t n_edits = 0, nb = 0;
     if (n) { TRY(run_extract(ctx)); n_edits = ctx->hw->total_edits; }
@@ -1336,7 +1347,7 @@ extern "C" int cbcg_extract_symbols(cbcg_ctx *ctx, const cbcg_batch *batch, cons
 
 /* ------------------------------------------------------------------------------------------------ decode */
 struct Container {
-    uint32_t max_len, L, n_blocks, n_chr, block_reads, gen_mode, fixed_len, n_sub;
+    uint32_t max_len, L, n_blocks, n_chr, block_reads, gen_mode, fixed_len, layout_mode;
     uint64_t n_reads;
     uint64_t index_off, index_bytes, payload_off;
     std::vector<uint32_t> chr_map;             /* container ordinal -> genome ordinal */
@@ -1350,8 +1361,8 @@ static int parse_container(const uint8_t *in, uint64_t len, const std::vector<st
     c.n_blocks = rd32(in + 24); c.n_chr = rd32(in + 28); c.block_reads = rd32(in + 32);
     const uint32_t mode = rd32(in + 36);
     c.gen_mode = mode & CBCG_MODE_GEN_MASK; c.fixed_len = (mode & CBCG_MODE_FIXED_LEN) ? 1u : 0u;
-    c.n_sub = (mode & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u;
-    if ((mode & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_FIXED_LEN | CBCG_MODE_SPLIT4)) || (c.fixed_len && c.max_len != c.L)) return CBCG_ERR_FORMAT;
+    c.layout_mode = mode & CBCG_MODE_LAYOUT_MASK;
+    if ((mode & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_FIXED_LEN | CBCG_MODE_LAYOUT_MASK)) || (c.fixed_len && c.max_len != c.L)) return CBCG_ERR_FORMAT;
     if (c.L == 0 || c.L > CBCG_MAX_READ_LEN || c.max_len > CBCG_MAX_READ_LEN || c.n_chr > MAX_CHR || c.gen_mode > 1) return CBCG_ERR_FORMAT;
     if (c.n_reads >= 0xfffffff0ull) return CBCG_ERR_FORMAT;
     uint64_t o = 40;
@@ -1456,7 +1467,7 @@ static int blocks_from_index(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
     uint32_t prev_gen = 0;
     for (uint32_t k = 0; k < c.n_blocks; k++) {
         BlockDesc &b = ctx->hblocks[k];
-        if (!index_get(in, c.index_off + c.index_bytes, o, st, b, c.n_sub)) return fail(ctx, CBCG_ERR_FORMAT, "block index entry %u malformed", k);
+        if (!index_get(in, c.index_off + c.index_bytes, o, st, b, c.layout_mode)) return fail(ctx, CBCG_ERR_FORMAT, "block index entry %u malformed", k);
         const uint32_t chr = b.chr;
         if (chr >= c.n_chr) return fail(ctx, CBCG_ERR_FORMAT, "block %u names chromosome %u of %u", k, chr, c.n_chr);
         if (c.chr_map[chr] == 0xffffffffu) return fail(ctx, CBCG_ERR_NO_REFERENCE, "block %u: chromosome not in the loaded reference", k);
@@ -1489,7 +1500,7 @@ static int decode_to_records(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, 
         int rc = parse_container(in, in_len, &ctx->names, c);
         if (rc) return fail(ctx, rc, "malformed container header");
         uint64_t nr = 0, ne = 0, pb = 0;
-        ctx->n_sub = c.n_sub;
+        ctx->layout_mode = c.layout_mode;
         TRY(blocks_from_index(ctx, in, in_len, c, &nr, &ne, &pb));
         *max_len = c.max_len ? c.max_len : 1;
         *fixed_len = c.fixed_len ? c.L : 0u;
@@ -1549,7 +1560,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
     cbcg_stats &S = ctx->stats;
     S = cbcg_stats();
     uint64_t nr = 0, ne = 0, pb = 0;
-    ctx->n_sub = c.n_sub;
+    ctx->layout_mode = c.layout_mode;
     TRY(blocks_from_index(ctx, in, in_len, c, &nr, &ne, &pb));
     if (ctx->gens.size() < 2) return PIPE_FALLBACK;
     const uint32_t nb = c.n_blocks;
@@ -1622,7 +1633,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
         if (g) CU(cudaStreamWaitEvent(sd, ctx->kev2[0], 0));
         if (g && gb[g] > gb[g - 1]) {
             CoderParams q = p;
-            q.block_begin = gb[g - 1]; q.n_blocks = gb[g] - gb[g - 1]; q.snap = snap;
+            q.block_begin = gb[g - 1]; q.n_blocks = gb[g] - gb[g - 1]; q.snap = snap; q.n_sub = gen_n_sub(ctx, q.block_begin);
             if (launch_coder(q, sd)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             S.kernel_launches += roles_launches(q.mode);
         }
@@ -1760,7 +1771,7 @@ extern "C" int cbcg_decode_resident(cbcg_ctx *ctx) {
     const uint64_t nb = ctx->enc_n_blocks;
     if (!nb) { ctx->dec_bytes = 0; ctx->dec_n_reads = 0; ctx->have_decoded = true; return CBCG_OK; }
     const int legacy = (int)ctx->enc_legacy;
-    ctx->n_sub = ctx->enc_n_sub;
+    ctx->layout_mode = ctx->enc_layout_mode;
     /* hblocks still hold the encoder's descriptors (n_reads, chr, base_pos, n_edits, payload_bytes); the compact
        payload is in ctx->payload in block order. */
     uint64_t nr = 0, ne = 0;

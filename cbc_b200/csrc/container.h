@@ -9,7 +9,7 @@
  *       zigzag(n_reads - previous n_reads) << 2 | chromosome changed << 1 | generation changed
  *       [chromosome ordinal]  [generation increment - 1]
  *       zigzag(second difference of base_pos)  zigzag(difference of n_edits)
- *       per substream (four with CBCG_MODE_SPLIT4 in `mode`, else one) zigzag(difference of its byte count against the
+ *       per substream (four or one: CBCG_BLOCK_NSUB(mode, generation)) zigzag(difference of its byte count against the
  *       previous block's same substream)
  *   payload: per block its substreams (A | B | C | D, or the one stream) back to back
  */
@@ -32,7 +32,8 @@ static inline void put_varint(std::vector<uint8_t> &v, uint64_t x) {
 }
 static inline uint64_t zz(int64_t v) { return ((uint64_t)v << 1) ^ (uint64_t)(v >> 63); }
 static inline int64_t unzz(uint64_t v) { return (int64_t)(v >> 1) ^ -(int64_t)(v & 1); }
-static inline void index_put(std::vector<uint8_t> &out, IndexState &st, const BlockDesc &b, uint32_t n_sub) {
+static inline void index_put(std::vector<uint8_t> &out, IndexState &st, const BlockDesc &b, uint32_t mode) {
+    const uint32_t n_sub = CBCG_BLOCK_NSUB(mode, b.gen);
     const bool chr_ch = (int64_t)b.chr != st.chr, gen_ch = (int64_t)b.gen != st.gen;
     put_varint(out, (zz((int64_t)b.n_reads - st.n_reads) << 2) | (chr_ch ? 2u : 0u) | (gen_ch ? 1u : 0u));
     if (chr_ch) { put_varint(out, b.chr); st.base = 0; st.d1 = 0; }
@@ -53,7 +54,7 @@ static inline bool get_varint(const uint8_t *p, uint64_t end, uint64_t &o, uint6
     }
     v = r; return true;
 }
-static inline bool index_get(const uint8_t *p, uint64_t end, uint64_t &o, IndexState &st, BlockDesc &b, uint32_t n_sub) {
+static inline bool index_get(const uint8_t *p, uint64_t end, uint64_t &o, IndexState &st, BlockDesc &b, uint32_t mode) {
     uint64_t v;
     if (!get_varint(p, end, o, v)) return false;
     st.n_reads += unzz(v >> 2);
@@ -64,6 +65,7 @@ static inline bool index_get(const uint8_t *p, uint64_t end, uint64_t &o, IndexS
     if (!get_varint(p, end, o, v)) return false;
     st.edits += unzz(v);
     int64_t total = 0;
+    const uint32_t n_sub = CBCG_BLOCK_NSUB(mode, st.gen);
     for (uint32_t k = 0; k < n_sub; k++) {
         if (!get_varint(p, end, o, v)) return false;
         st.sub[k] += unzz(v);
@@ -93,8 +95,7 @@ static inline void container_head(std::vector<uint8_t> &h, uint32_t max_len, uin
     }
     std::vector<uint8_t> ix;
     IndexState st = index_state(block_reads);
-    const uint32_t n_sub = (mode & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u;
-    for (uint64_t k = 0; k < nb; k++) index_put(ix, st, hb[k], n_sub);
+    for (uint64_t k = 0; k < nb; k++) index_put(ix, st, hb[k], mode);
     put32(h, (uint32_t)ix.size());
     h.insert(h.end(), ix.begin(), ix.end());
 }

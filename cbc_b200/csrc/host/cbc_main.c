@@ -64,21 +64,25 @@ typedef struct shared {
     double t_gpu_ready;
 } shared;
 
-typedef struct devthread { shared *S; int device; pthread_t th; int rc; char err[256]; } devthread;
+typedef struct devthread { shared *S; int device; pthread_t th; int rc; char err[256]; double create_s, setref_s, call_s, alloc_s; } devthread;
 
 static void *device_main(void *arg) {
     devthread *D = (devthread *)arg;
     shared *S = D->S;
     cbcg_ctx *ctx = NULL;
+    double tq = now();
     int rc = cbcg_create(D->device, &ctx);                       /* context creation runs beside the FASTA / SAM ingest */
+    D->create_s = now() - tq;
     if (rc) { snprintf(D->err, sizeof D->err, "device %d: %s", D->device, cbcg_strerror(rc)); D->rc = rc; }
     pthread_mutex_lock(&S->mu);
     while (!S->fa_ready) pthread_cond_wait(&S->cv, &S->mu);
     pthread_mutex_unlock(&S->mu);
+    tq = now();
     if (!rc) {
         rc = cbcg_set_reference(ctx, S->fa->n, (const char *const *)S->fa->names, (const uint8_t *const *)S->fa->bases, S->fa->len);
         if (rc) { snprintf(D->err, sizeof D->err, "device %d: %s", D->device, cbcg_last_error(ctx)); D->rc = rc; }
     }
+    D->setref_s = now() - tq;
     pthread_mutex_lock(&S->mu);
     if (S->t_gpu_ready == 0) S->t_gpu_ready = now();
     pthread_mutex_unlock(&S->mu);
@@ -93,6 +97,7 @@ static void *device_main(void *arg) {
             cbcg_encode_opts o = { J->header_len ? J->header_len : 1u, S->single ? 0u : S->block_reads, S->single ? 0u : 1u, 0u };
             cbcg_batch v; cbch_batch_view(&J->hb, &v);
             uint64_t cap = J->bound, n = 0;
+            tq = now();
             J->out = (uint8_t *)malloc(cap ? cap : 1);
             if (!J->out) { J->rc = CBCG_ERR_NOMEM; snprintf(J->err, sizeof J->err, "out of memory"); }
             else {
@@ -100,6 +105,7 @@ static void *device_main(void *arg) {
                 if (rc == CBCG_ERR_CAPACITY && n > cap) { free(J->out); J->out = (uint8_t *)malloc(n); rc = J->out ? cbcg_fetch_container(ctx, J->out, n, &n) : CBCG_ERR_NOMEM; }
                 if (rc) { J->rc = rc; snprintf(J->err, sizeof J->err, "%s", cbcg_last_error(ctx)); }
                 J->out_len = n;
+                D->call_s += now() - tq;
                 cbcg_stats st; cbcg_get_stats(ctx, &st); J->device_ms = st.ms_total; J->n_blocks = st.n_blocks;
             }
             if (J->have_compact) cbch_free_compact(&J->cb);
@@ -108,11 +114,13 @@ static void *device_main(void *arg) {
             if (!J->legacy && cbcg_decoded_size(J->in, J->in_len, &n_reads, &cap) != CBCG_OK) { J->rc = CBCG_ERR_FORMAT; snprintf(J->err, sizeof J->err, "malformed container"); }
             else {
                 if (J->legacy) cap = 1u << 20;
+                tq = now();
                 J->out = (uint8_t *)malloc(cap ? cap : 1);
                 rc = J->out ? cbcg_decode(ctx, J->in, J->in_len, J->legacy, J->out, cap, &n, &n_reads) : CBCG_ERR_NOMEM;
                 if (rc == CBCG_ERR_CAPACITY && n > cap) { free(J->out); J->out = (uint8_t *)malloc(n); rc = J->out ? cbcg_fetch_decoded(ctx, J->out, n, &n) : CBCG_ERR_NOMEM; }
                 if (rc) { J->rc = rc; snprintf(J->err, sizeof J->err, "%s", ctx ? cbcg_last_error(ctx) : "no context"); }
                 J->out_len = n; J->n_reads = n_reads;
+                D->call_s += now() - tq;
                 cbcg_stats st; cbcg_get_stats(ctx, &st); J->device_ms = st.ms_total;
             }
         }
@@ -328,6 +336,8 @@ int main(int argc, char **argv) {
             printf("reads %llu, shards %llu on %d device(s), gpu ready %.3f s, device %.3f ms\n", (unsigned long long)total_reads, (unsigned long long)S.n_jobs, n_dev, S.t_gpu_ready - t0, device_ms);
         }
     }
+    if (getenv("CBC_TRACE")) for (int d = 0; d < n_dev; d++)
+        fprintf(stderr, "[cbc] device %d: context %.3f s, reference upload %.3f s, coding calls %.3f s; writer done at %.3f s\n", dev[d], D[d].create_s, D[d].setref_s, D[d].call_s, t2 - t0);
     for (uint64_t k = 0; k < S.n_jobs; k++) { free(S.jobs[k]->out); free(S.jobs[k]); }
     free(S.jobs); free(cut); free(in); free(shard_off); free(shard_len);
     if (mode == 'c') cbch_unmap(&map);

@@ -74,7 +74,8 @@ struct CoderParams {
     uint32_t short_flush;                  /* blocked containers: 1 + scale3 closing bits instead of the reference's 26+ */
     uint32_t primed;                       /* gen_mode 1: models start from `snap` instead of the initial state */
     uint32_t fixed_len;                    /* CBCG_MODE_FIXED_LEN: every read is L bases, the length symbol is not coded */
-    uint32_t n_sub;                        /* blocked containers: 1 (one stream per block) or CBCG_N_SUB (CBCG_MODE_SPLIT4) */
+    uint32_t n_sub;                        /* blocked containers: substreams of the blocks of THIS launch (one generation): 1 or CBCG_N_SUB */
+    uint32_t layout_mode;                  /* the container's layout bits (CBCG_MODE_SPLIT4, split generations): CBCG_BLOCK_NSUB(layout_mode, gen) per block */
     const uint8_t *snap;                   /* snapshot S_{g-1} (snapshot_bytes(L) bytes); blocked containers always start from one */
     uint8_t *fin;                          /* per block (absolute index): its image of the small models (WarpModels), read by the merges */
 };
@@ -102,7 +103,7 @@ int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_t
 int launch_coder(const CoderParams &p, cudaStream_t st);
 uint32_t coder_resident_blocks(int device);     /* blocks (warps) of the encode kernel the whole GPU holds at once */
 int launch_gather(BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
-                  uint64_t *out_off, int subs, cudaStream_t st);   /* subs: blocked container, four substreams per block */
+                  uint64_t *out_off, int blocked, uint32_t layout_mode, cudaStream_t st);   /* blocked: CBCG_BLOCK_NSUB(layout_mode, gen) pieces per block */
 uint32_t roles_launches(uint32_t mode);         /* kernel launches one launch_coder call makes for a blocked container */
 uint64_t coder_ws_bytes_bound(uint32_t L, uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy, int primed);
 /* generation snapshots (gen_mode 1) */

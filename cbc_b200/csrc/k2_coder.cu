@@ -1545,8 +1545,8 @@ uint32_t coder_resident_blocks(int device) {
 
 __global__ void k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap, uint64_t payload_cap,
                                uint64_t *totals, const uint64_t *carry_in, const uint64_t *n_edits_dev);
-__global__ void k2_payload_scan_kernel(BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off, int subs);
-__global__ void k2_gather_kernel(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out, const uint64_t *out_off, int subs);
+__global__ void k2_payload_scan_kernel(BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off, int blocked, uint32_t layout_mode);
+__global__ void k2_gather_kernel(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out, const uint64_t *out_off, int blocked, uint32_t layout_mode);
 __global__ void snapshot_copy_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint64_t n16);
 struct MergeParams;
 __global__ void merge_prep_kernel(MergeParams P);
@@ -1633,7 +1633,7 @@ k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, ui
             }
             const uint64_t ws_edits = (dec && P.legacy) ? 0xffffffffull : d.n_edits;
             v[0] = ws_layout(P.L ? P.L : 252u, d.n_reads, ws_edits, P.legacy, P.primed && P.mode != MODE_LIST).total;
-            v[1] = dec ? d.payload_bytes : payload_cap_bytes(d.n_reads, d.n_edits, P.legacy ? 2 : (P.n_sub <= 1u ? 1 : 0));
+            v[1] = dec ? d.payload_bytes : payload_cap_bytes(d.n_reads, d.n_edits, P.legacy ? 2 : (CBCG_BLOCK_NSUB(P.layout_mode, d.gen) <= 1u ? 1 : 0));
             v[2] = (P.mode == MODE_LIST) ? symlist_cap(d.n_reads, d.n_edits, P.legacy) : 0;
             v[3] = d.n_reads; v[4] = d.n_edits;
         }
@@ -1659,7 +1659,7 @@ k2_plan_kernel(CoderParams P, uint32_t n_reads_total, uint64_t n_edits_total, ui
             if (!dec) d.payload_off = off[1];
             else { d.payload_off = off[1]; d.first_read = (uint32_t)off[3]; d.edit_base = off[4]; }
             d.sym_off = off[2];
-            if (!P.legacy && P.mode != MODE_LIST && P.n_sub > 1u) {   /* the substream roles add their symbol counts */
+            if (!P.legacy && P.mode != MODE_LIST && CBCG_BLOCK_NSUB(P.layout_mode, d.gen) > 1u) {   /* the substream roles add their symbol counts */
                 d.n_symbols = 0; d.pos_card = 0; d.n_rows = 0; d.pa_touched = 0;
                 if (!dec) { d.payload_bytes = 0; for (uint32_t q = 0; q < CBCG_N_SUB; q++) d.sub_bytes[q] = 0; }
             }
@@ -1687,7 +1687,7 @@ int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_t
 /* ------------------------------------------------------------------------------------------------
  * gather: block payloads (scratch regions) -> one contiguous payload; out_off[b] = its offset. */
 __global__ void __launch_bounds__(PLAN_THREADS)
-k2_payload_scan_kernel(BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off, int subs) {
+k2_payload_scan_kernel(BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off, int blocked, uint32_t layout_mode) {
     __shared__ uint64_t wsum[32];
     __shared__ uint64_t carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -1697,7 +1697,7 @@ k2_payload_scan_kernel(BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off, 
         const uint32_t b = base + tid;
         uint64_t v = 0;
         if (b < n_blocks) {
-            if (subs) { uint32_t t = 0; for (uint32_t q = 0; q < CBCG_N_SUB; q++) t += blocks[b].sub_bytes[q]; blocks[b].payload_bytes = t; }
+            if (blocked && CBCG_BLOCK_NSUB(layout_mode, blocks[b].gen) > 1u) { uint32_t t = 0; for (uint32_t q = 0; q < CBCG_N_SUB; q++) t += blocks[b].sub_bytes[q]; blocks[b].payload_bytes = t; }
             v = blocks[b].payload_bytes;
         }
         uint64_t x = v;
@@ -1717,11 +1717,11 @@ k2_payload_scan_kernel(BlockDesc *blocks, uint32_t n_blocks, uint64_t *out_off, 
 }
 
 __global__ void k2_gather_kernel(const BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
-                                 const uint64_t *out_off, int subs) {
+                                 const uint64_t *out_off, int blocked, uint32_t layout_mode) {
     for (uint32_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
         const uint8_t *src = scratch + blocks[b].payload_off;
         uint8_t *dst = out + out_off[b];
-        if (!subs) {
+        if (!blocked || CBCG_BLOCK_NSUB(layout_mode, blocks[b].gen) <= 1u) {
             const uint32_t n = blocks[b].payload_bytes;
             for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
             continue;
@@ -1735,11 +1735,11 @@ __global__ void k2_gather_kernel(const BlockDesc *blocks, uint32_t n_blocks, con
 }
 
 int launch_gather(BlockDesc *blocks, uint32_t n_blocks, const uint8_t *scratch, uint8_t *out,
-                  uint64_t *out_off, int subs, cudaStream_t st) {
+                  uint64_t *out_off, int blocked, uint32_t layout_mode, cudaStream_t st) {
     if (n_blocks == 0) return 0;
-    k2_payload_scan_kernel<<<1, PLAN_THREADS, 0, st>>>(blocks, n_blocks, out_off, subs);
+    k2_payload_scan_kernel<<<1, PLAN_THREADS, 0, st>>>(blocks, n_blocks, out_off, blocked, layout_mode);
     unsigned grid = n_blocks < 148u * 8u ? n_blocks : 148u * 8u;
-    k2_gather_kernel<<<grid, 128, 0, st>>>(blocks, n_blocks, scratch, out, out_off, subs);
+    k2_gather_kernel<<<grid, 128, 0, st>>>(blocks, n_blocks, scratch, out, out_off, blocked, layout_mode);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -125,6 +125,8 @@ static inline uint32_t cbcg_substream_of(uint32_t stream) {
 #define CBCG_MODE_WITH_SPLIT_GENS(k)      (((uint32_t)(k) & 0xffu) << 16)
 #define CBCG_BLOCK_NSUB(mode, gen)        ((((mode) & CBCG_MODE_SPLIT4) || (uint32_t)(gen) < CBCG_MODE_SPLIT_GENS(mode)) ? CBCG_N_SUB : 1u)
 #define CBCG_MODE_LAYOUT_MASK             (CBCG_MODE_SPLIT4 | 0xff0000u)
+/* API only, never stored: ask the encoder for the default cut's layout (four substreams in its narrow early generations) */
+#define CBCG_MODE_REQ_HYBRID              0x400u
 
 /* The FLAG model spends 65 536 / n of its probability on values never seen (src/sam_models.c:96-130: all-ones initial
  * state), so what a FLAG symbol costs depends on where the model total n stands below the rescale threshold 2^20

@@ -1019,7 +1019,7 @@ static void index_put(cbco_buf *b, idx_state *st, const blk_index *e, uint32_t n
     st->n_reads = e->n_reads; st->chr = e->chr; st->gen = e->gen; st->base = e->base_pos; st->d1 = d1;
     st->edits = e->n_edits;
 }
-static int index_get(const uint8_t *p, uint64_t len, uint64_t *o, idx_state *st, blk_index *e, uint32_t n_sub) {
+static int index_get(const uint8_t *p, uint64_t len, uint64_t *o, idx_state *st, blk_index *e, uint32_t mode) {
     uint64_t v;
     if (get_varint(p, len, o, &v)) return -1;
     st->n_reads += unzigzag(v >> 2);
@@ -1030,6 +1030,7 @@ static int index_get(const uint8_t *p, uint64_t len, uint64_t *o, idx_state *st,
     if (get_varint(p, len, o, &v)) return -1;
     st->edits += unzigzag(v);
     int64_t total = 0;
+    const uint32_t n_sub = CBCG_BLOCK_NSUB(mode, st->gen);
     for (uint32_t k = 0; k < n_sub; k++) {
         if (get_varint(p, len, o, &v)) return -1;
         st->sub[k] += unzigzag(v);
@@ -1082,8 +1083,8 @@ int cbco_encode_like(const uint8_t *p, uint64_t len, const cbco_batch *b, const 
     blk_index *idx = (blk_index *)calloc((size_t)nb + 1, sizeof(blk_index));
     idx_state st = { h[8], 0, 0, 0, 0, 0, { 0, 0, 0, 0 } };
     uint64_t io = o;
-    for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k], (h[9] & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u)) { free(idx); return -43; }
-    int rc = encode_cut(b, g, h[3], h[8], (h[9] & CBCG_MODE_GEN_MASK) ? 1u : 0u, NULL, NULL, idx, nb, h[9] & (CBCG_MODE_GEN_MASK | CBCG_MODE_SPLIT4), out);
+    for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k], h[9])) { free(idx); return -43; }
+    int rc = encode_cut(b, g, h[3], h[8], (h[9] & CBCG_MODE_GEN_MASK) ? 1u : 0u, NULL, NULL, idx, nb, h[9] & (CBCG_MODE_GEN_MASK | CBCG_MODE_LAYOUT_MASK), out);
     free(idx);
     return rc;
 }
@@ -1124,7 +1125,6 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
     }
     first[nb] = b->n_reads;
     const uint32_t last_gen = nb ? idx[nb - 1].gen : 0;
-    const uint32_t n_sub = (gen_mode & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u;
     uint32_t max_block = 0;
     for (uint64_t k = 0; k < nb; k++) if (idx[k].n_reads > max_block) max_block = idx[k].n_reads;
     const uint32_t flag_target = cbcg_flag_target(max_block);
@@ -1145,6 +1145,7 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
         s.lean = 1; s.fixed_len = fixed_len;
         uint64_t start = payload.size;
         cbco_buf sub[CBCG_N_SUB]; memset(sub, 0, sizeof sub);
+        const uint32_t n_sub = CBCG_BLOCK_NSUB(gen_mode, idx[k].gen);
         s.c.split = n_sub > 1u;
         for (uint32_t q = 0; q < n_sub; q++) ac_init_enc(&s.c.ac[q], &sub[q]);
         s.prev_pos = idx[k].base_pos; s.have_name = 1; s.cur_chr = idx[k].chr;
@@ -1180,7 +1181,7 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
         }
         cbco_buf ix = {0};
         idx_state st = { block_reads, 0, 0, 0, 0, 0, { 0, 0, 0, 0 } };
-        for (uint64_t k = 0; k < nb; k++) index_put(&ix, &st, &idx[k], n_sub);
+        for (uint64_t k = 0; k < nb; k++) index_put(&ix, &st, &idx[k], CBCG_BLOCK_NSUB(gen_mode, idx[k].gen));
         buf_put_u32(out, (uint32_t)ix.size);
         buf_put(out, ix.data, ix.size);
         cbco_buf_free(&ix);
@@ -1194,8 +1195,13 @@ static int encode_cut(const cbco_batch *b, const cbco_genome *g, uint32_t L, uin
 int cbco_encode_blocked(const cbco_batch *b, const cbco_genome *g, uint32_t L, uint32_t block_reads,
                         uint32_t gen_mode, cbco_buf *out) {
     uint32_t count[CBCG_GEN_MAX], reads[CBCG_GEN_MAX], last = 0, levels = 0;
-    if ((gen_mode & CBCG_MODE_GEN_MASK) > 1 || (gen_mode & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_SPLIT4))) return -30;   /* low byte: generations; bit 9: four substreams */
-    if (gen_mode & CBCG_MODE_GEN_MASK) levels = cbcg_gen_schedule(b->n_reads, (gen_mode & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u, count, reads, &last, NULL);
+    if ((gen_mode & CBCG_MODE_GEN_MASK) > 1 || (gen_mode & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_LAYOUT_MASK | CBCG_MODE_REQ_HYBRID))) return -30;
+    /* low byte: generations; bit 9: four substreams everywhere; bits 16..23: in that many leading generations; bit 10: the default cut's own choice */
+    const uint32_t layout = (gen_mode & CBCG_MODE_SPLIT4) ? 4u : ((gen_mode & CBCG_MODE_REQ_HYBRID) && (gen_mode & CBCG_MODE_GEN_MASK)) ? 0u : 1u;
+    uint32_t split_gens = 0;
+    if (gen_mode & CBCG_MODE_GEN_MASK) levels = cbcg_gen_schedule(b->n_reads, layout, count, reads, &last, &split_gens);
+    if (layout == 0u) gen_mode = (gen_mode & ~CBCG_MODE_REQ_HYBRID) | CBCG_MODE_WITH_SPLIT_GENS(split_gens);
+    gen_mode &= ~CBCG_MODE_REQ_HYBRID;
     if (block_reads == 0xffffffffu) block_reads = (gen_mode & CBCG_MODE_GEN_MASK) ? last : 1024u;      /* CBCG_BLOCK_AUTO */
     return encode_cut(b, g, L, block_reads, levels, count, reads, NULL, 0, gen_mode, out);
 }
@@ -1207,8 +1213,7 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
     uint32_t L = h[3]; uint64_t n_reads; memcpy(&n_reads, p + 16, 8);
     uint32_t nb = h[6], n_chr = h[7], gen_mode = h[9] & CBCG_MODE_GEN_MASK;
     const uint32_t fixed_len = (h[9] & CBCG_MODE_FIXED_LEN) ? L : 0;
-    if (gen_mode > 1 || (h[9] & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_FIXED_LEN | CBCG_MODE_SPLIT4)) || n_chr > g->n_chr) return -42;
-    const uint32_t n_sub = (h[9] & CBCG_MODE_SPLIT4) ? CBCG_N_SUB : 1u;
+    if (gen_mode > 1 || (h[9] & ~(CBCG_MODE_GEN_MASK | CBCG_MODE_FIXED_LEN | CBCG_MODE_LAYOUT_MASK)) || n_chr > g->n_chr) return -42;
     if (fixed_len && h[2] != L) return -42;
     uint64_t o = 40;
     /* container chromosome ordinal -> genome ordinal, by name */
@@ -1230,7 +1235,7 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
     {
         idx_state st = { h[8], 0, 0, 0, 0, 0, { 0, 0, 0, 0 } };
         uint64_t io = o;
-        for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k], n_sub)) { free(chr_map); free(idx); return -43; }
+        for (uint32_t k = 0; k < nb; k++) if (index_get(p, o + ix_bytes, &io, &st, &idx[k], h[9])) { free(chr_map); free(idx); return -43; }
     }
     o += ix_bytes;
     int rc = 0; uint64_t n = 0;
@@ -1252,6 +1257,7 @@ int cbco_decode_blocked(const uint8_t *p, uint64_t len, const cbco_genome *g, cb
         uint32_t chr = chr_map[bi.chr];
         rstate s; rstate_init_from(&s, prev, 2);
         s.lean = 1; s.fixed_len = fixed_len;
+        const uint32_t n_sub = CBCG_BLOCK_NSUB(h[9], bi.gen);
         s.c.split = n_sub > 1u;
         { uint64_t so = o; for (uint32_t q = 0; q < n_sub; q++) { ac_init_dec(&s.c.ac[q], p + so, bi.sub_bytes[q]); so += bi.sub_bytes[q]; } }
         s.prev_pos = bi.base_pos;

@@ -68,6 +68,28 @@ def test_config3_shape_half_size_budget(codec):
     assert 0.0 < overhead <= 0.01, overhead                               # (round 1: 1.24 % on config 3)
 
 
+@pytest.mark.parametrize("name,L", [("config2", 150), ("config1", 100)])
+def test_default_layout_full_size_budget(codec, name, L):
+    """substreams = 0, what the command line and bench.py use: four substreams in the narrow early generations, one
+    stream in the wide ones. Same bytes as the CPU restatement given the cut, inside the budget, decodes to the input."""
+    cfg = synth.SynthConfig.named(name)
+    g = synth.make_genome(cfg)
+    b = synth.make_reads(cfg, g)
+    codec.set_reference(g)
+    codec.upload(b)
+    codec.encode_resident(L, AUTO, 1, substreams=0)
+    cont = codec.fetch_container().tobytes()
+    codec.decode_resident()
+    assert codec.fetch_decoded().tobytes() == b.seq_lines()
+    mode = struct.unpack_from("<I", cont, 36)[0]
+    assert (mode >> 16) & 0xff >= 4 and not mode & 0x200
+    assert cont == O.encode_like(cont, b, g)
+    single, _ = O.encode_legacy(b, g, L)
+    assert 0.0 < (len(cont) - len(single)) / len(single) <= 0.01
+    text, n = codec.decompress(cont)                                      # host-buffer (pipelined) decode
+    assert n == b.n_reads and text == b.seq_lines()
+
+
 def test_four_substream_container_full_size(codec):
     """CBCG_MODE_SPLIT4 at config-2 size: a CTA per block, a warp per substream, pipelined decode; the CPU restatement
     writes the same bytes for the same cut, and the budget holds."""

@@ -158,7 +158,7 @@ def test_reconstruct_matches_oracle(codec, meta_path):
 
 # ------------------------------------------------------------------ blocked container
 
-@pytest.mark.parametrize("substreams", [1, 4])
+@pytest.mark.parametrize("substreams", [1, 4, 0])
 @pytest.mark.parametrize("gen_mode", [0, 1])
 @pytest.mark.parametrize("name,block_reads", [("subs_150", 256), ("indels_100", 1), ("clips_100", 97),
                                               ("two_chr", 1000), ("indels_250", 64), ("paired_flags_n", 100000),
@@ -169,7 +169,8 @@ def test_blocked_container_equals_oracle_and_roundtrips(codec, name, block_reads
     meta, g, b, _ = _load(GOLDEN[IDS.index(name)])
     codec.set_reference(g)
     c = codec.compress(b, meta["read_len_header"], block_reads=block_reads, gen_mode=gen_mode, substreams=substreams)
-    assert c == O.encode_blocked(b, g, meta["read_len_header"], block_reads, gen_mode | (0x200 if substreams == 4 else 0))
+    flags = gen_mode | (0x200 if substreams == 4 else 0x400 if substreams == 0 else 0)   # 0x400: the default cut's own layout
+    assert c == O.encode_blocked(b, g, meta["read_len_header"], block_reads, flags)
     text, n = codec.decompress(c)
     assert n == b.n_reads and text == b.seq_lines()
     otext, on = O.decode_blocked(c, g)
