@@ -77,6 +77,7 @@ struct cbcg_ctx {
 
     /* work buffers */
     DevBuf recs, edits, chr_out, tile_desc, words, blocks, ws, scratch, payload, out_off, symbols, seq_out;
+    DevBuf tri;                                /* two-kernel encode: the symbols' intervals between the model and the interval kernel */
     DevBuf snap_a, snap_b, fin;                /* generation snapshots and per-block final states (gen_mode 1) */
     std::vector<std::pair<uint32_t, uint32_t>> gens;   /* (first block, block count) per generation of the last cut */
     uint32_t layout = 1;                       /* the call in progress: 1 = one stream per block, 4 = four substreams, 0 = four in the narrow early generations */
@@ -678,6 +679,13 @@ static uint64_t sched_early_reads(cbcg_ctx *ctx, uint64_t n, uint32_t *levels_ou
     return early;
 }
 static int ensure_fin(cbcg_ctx *ctx, uint64_t nb) { return ensure(ctx, ctx->fin, (nb + 1) * fin_stride_bytes()); }
+/* Interval buffer of the two-kernel encode (blocked containers): regions are addressed by absolute read and edit offsets
+ * (k2_tri_off), so it is sized by the batch and the capacity of the edit array. */
+static int ensure_tri(cbcg_ctx *ctx, CoderParams &p, uint64_t n, uint64_t nb) {
+    TRY(ensure(ctx, ctx->tri, k2_tri_slots(n, ctx->edits.cap / 2, nb) * 16));
+    p.tri = ctx->tri.as<K2Tri>();
+    return 0;
+}
 
 /* Generations 0 .. last-1 of ctx->gens with the merges that build the snapshots; *snap_out = the snapshot the last
  * generation starts from. */
@@ -697,7 +705,7 @@ static int run_early_generations(cbcg_ctx *ctx, CoderParams p, uint8_t **snap_ou
         p.n_sub = gen_n_sub(ctx, p.block_begin);
         p.snap = cur;
         if (launch_coder(p, st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        ctx->stats.kernel_launches += roles_launches(p.mode);
+        ctx->stats.kernel_launches += coder_launches(p);
         if (launch_merge(p.blocks, p.block_begin, p.n_blocks, p.L, cur, other, p.fin + (uint64_t)p.block_begin * fin_stride_bytes(), p.ws, p.err, flag_target, st))
             return fail(ctx, CBCG_ERR_CUDA, "merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->stats.kernel_launches += 4;
@@ -726,7 +734,7 @@ static int run_coder_generations(cbcg_ctx *ctx, CoderParams p, uint64_t nb, bool
     p.n_sub = gen_n_sub(ctx, p.block_begin);
     p.snap = cur;
     if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    ctx->stats.kernel_launches += roles_launches(p.mode);
+    ctx->stats.kernel_launches += coder_launches(p);
     return 0;
 }
 
@@ -833,6 +841,7 @@ static int encode_resident_overlapped(cbcg_ctx *ctx, const cbcg_encode_opts *opt
     p.chr = const_cast<uint32_t *>(ctx->db.chr);
     p.payload = ctx->scratch.as<uint8_t>();
     p.lean = 1u; p.short_flush = 1u; p.primed = 1u; p.fixed_len = fixed ? 1u : 0u;
+    TRY(ensure_tri(ctx, p, n, nb));
     /* high-priority stream: plan of the early blocks, generations 0..3. K1's grid fills every SM; without the priority
        the first generation's four CTAs queue behind all of it (measured: the overlap gained nothing). */
     cudaStream_t hp = ctx->hp;
@@ -941,6 +950,7 @@ extern "C" int cbcg_encode_resident(cbcg_ctx *ctx, const cbcg_encode_opts *opts)
         p.chr = const_cast<uint32_t *>(ctx->db.chr);
         p.payload = ctx->scratch.as<uint8_t>();
         p.lean = legacy ? 0u : 1u; p.short_flush = legacy ? 0u : 1u; p.primed = primed ? 1u : 0u; p.fixed_len = fixed ? 1u : 0u;
+        if (!legacy) TRY(ensure_tri(ctx, p, n, nb));
         if (launch_plan(p, (uint32_t)n, n_edits, ws_cap, pay_cap, wptr<uint64_t>(ctx, W_OFF(totals)), ctx->st))
             return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
         CU(cudaEventRecord(ctx->ev[2], ctx->st));
@@ -1206,6 +1216,7 @@ static int encode_pipelined(cbcg_ctx *ctx, const BatchSrc &src, const cbcg_encod
             pay_cap = coder_payload_bound(n, proj, nb, 0);
             TRY(ensure(ctx, ctx->ws, ws_cap)); TRY(ensure(ctx, ctx->scratch, pay_cap)); TRY(ensure(ctx, ctx->payload, pay_cap));
             p.ws = ctx->ws.as<uint8_t>(); p.payload = ctx->scratch.as<uint8_t>();
+            TRY(ensure_tri(ctx, p, n, nb));
         }
         /* plan of the blocks that are now complete */
         CoderParams q = p;
@@ -1223,7 +1234,7 @@ static int encode_pipelined(cbcg_ctx *ctx, const BatchSrc &src, const cbcg_encod
             CU(cudaStreamWaitEvent(sd, ctx->kev2[c], 0));
             q.snap = snap; q.n_sub = gen_n_sub(ctx, q.block_begin);
             if (launch_coder(q, sd)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            S.kernel_launches += roles_launches(q.mode);
+            S.kernel_launches += coder_launches(q);
             CU(cudaEventRecord(ctx->dev2[c], sd));
         }
     }
@@ -1635,7 +1646,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
             CoderParams q = p;
             q.block_begin = gb[g - 1]; q.n_blocks = gb[g] - gb[g - 1]; q.snap = snap; q.n_sub = gen_n_sub(ctx, q.block_begin);
             if (launch_coder(q, sd)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            S.kernel_launches += roles_launches(q.mode);
+            S.kernel_launches += coder_launches(q);
         }
         CU(cudaEventRecord(ctx->tev[2 * g], sd));
         if (r1 > r0) {

@@ -131,8 +131,13 @@ __device__ __noinline__ void emit_long(BitSink *bs, uint32_t b0, uint32_t run, u
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-template <int MODE>
+/* TRI: the encoder's model half on its own (k2_model_kernel): every coder step is replaced by a store of the symbol's
+   interval (cumulative count, count, model total) for the interval kernel (k2_code_kernel) to code. */
+#define TRI_ESC 1u                             /* on a POS interval: the escape's four byte symbols follow (in the block's escape list) */
+template <int MODE, bool TRI = false>
 struct Coder {
+    /* --- TRI: where the next interval goes, and the flag bits that go with it */
+    uint4 *tri_at; uint32_t tri_flag;
     /* --- arithmetic coder state (uniform across the warp) */
     AcInterval a;
     uint32_t t;
@@ -289,7 +294,11 @@ struct Coder {
 
     /* one coder step given the symbol's interval; decode: caller found (lo, cnt) from the target */
     __device__ __forceinline__ void code_interval(uint32_t lo, uint32_t cnt, uint32_t n) {
-        if (MODE == MODE_ENC) ac_encode(lo, cnt, n); else ac_decode_step(lo, cnt, n);
+        if (TRI) {
+            if (UNLIKELY(cnt == 0u || n == 0u)) { err = CBCG_ERR_INPUT; return; }          /* reference: assert :71 / :293 */
+            if (lane == 0) *tri_at = make_uint4(lo, cnt, n, tri_flag);
+            tri_flag = 0u;
+        } else if (MODE == MODE_ENC) ac_encode(lo, cnt, n); else ac_decode_step(lo, cnt, n);
         n_symbols++;
     }
 
@@ -559,7 +568,7 @@ struct Coder {
                 }
                 lo += warp_sum(c);
             }
-            if (!found) { slot = 0; lo = 0; cnt = __shfl_sync(FULL_MASK, pos_rc, 0); }
+            if (!found) { slot = 0; lo = 0; cnt = __shfl_sync(FULL_MASK, pos_rc, 0); if (TRI) tri_flag = TRI_ESC; }
         } else {
             const uint64_t A = dec_A(pos_n); const uint32_t range = dec_range();
             uint32_t carry = 0; bool found = false;
@@ -1536,6 +1545,251 @@ int launch_block_kernel(const CoderParams &p, cudaStream_t st) {
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+/* ================================================================================================
+ * Encode of one-stream blocks in TWO KERNELS: models (here), then intervals (k2_code_kernel, k2_blocks.cu).
+ *
+ * An encoder knows every symbol and every context before it codes anything: the adaptive models (stream_model.c
+ * :31-76) never look at the coder's interval, only the coder (Arithmetic_stream.c:274-345) does. The one-kernel encoder
+ * above runs both behind each other, 175 warp instructions per symbol, all 32 lanes repeating the interval arithmetic,
+ * every block one chain of ~4 700 dependent symbols. Here
+ *   - the model half runs as FOUR INDEPENDENT CHAINS per block (POS | length + FLAG | match + counts | var + bases: the
+ *     model groups of cbcg_format.h), a warp each, lanes cooperating inside a symbol as before; a chain is a short loop
+ *     over one kind of symbol -- no state machine, no interval arithmetic, no bit packer -- and writes each symbol's
+ *     interval (cumulative count, count, total: 20 bits each) to the slot the symbol has in the block's stream order
+ *     (slot = running sum over the reads' symbol counts, which every chain forms for itself from the records);
+ *   - the interval half is one THREAD per block: 32 blocks per warp run the same ~60 instructions per symbol on
+ *     different data (closed-form renormalisation: no data-dependent loop), reading their slots in order.
+ * Same models, same order, same intervals: the container is byte-identical to the one-kernel encoder's (and to the
+ * oracle's). POS escapes are the one symbol whose presence the other chains cannot know: the POS triple carries a flag
+ * and the four byte symbols go to an escape list that the interval kernel splices in. */
+#ifndef K2M_MIN_CTAS
+#define K2M_MIN_CTAS 8
+#endif
+__device__ __forceinline__ uint32_t k2m_slots(uint32_t cw, uint32_t lead) {       /* symbols of one read in stream order */
+    const uint32_t match = cw & 0xffu, ns = (cw >> 8) & 0xffu, nd = (cw >> 16) & 0xffu, ni = cw >> 24;
+    return lead + 3u + (match ? 0u : 1u + ((nd | ni) ? 3u : 0u) + nd + 2u * ns + 2u * ni);
+}
+__global__ void __launch_bounds__(K2_THREADS, K2M_MIN_CTAS)
+k2_model_kernel(CoderParams P, uint32_t role_mask) {
+    __shared__ __align__(16) WarpShared sh[K2_WARPS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t role = (CBCG_N_SUB - 1u) - blockIdx.y;                 /* the longest chain (var + bases) is scheduled first */
+    if (!((role_mask >> role) & 1u)) return;                              /* timing experiments only (CBCG_K2M_ROLES) */
+    const uint32_t bl = blockIdx.x * K2_WARPS + warp;
+    if (bl >= P.n_blocks) return;
+    if (*reinterpret_cast<volatile unsigned long long *>(P.err)) return;   /* an earlier stage failed: offsets may be out of range */
+    const uint32_t b = P.block_begin + bl;
+    BlockDesc &B = P.blocks[b];
+    const WsLayout w = ws_layout(P.L, B.n_reads, B.n_edits, 0, 1);
+    uint8_t *wsb = P.ws + B.ws_off;
+    const uint32_t L = P.L, n_reads = B.n_reads;
+    const bool fixed = P.fixed_len != 0;
+    const uint32_t lead = fixed ? 0u : 1u;                                 /* the length symbol of variable-length containers */
+    const uint64_t r0 = B.first_read;
+    WarpModels &S = sh[warp].m;
+
+    Coder<MODE_ENC, true> C;
+    C.lane = lane; C.err = 0; C.n_symbols = 0; C.M = &S; C.coldp = &sh[warp].c;
+    C.primed = true; C.lean = true; C.var_defer = true; C.var_ro = false; C.defer_idx = 0; C.defer_key = 0;
+    C.snap = SnapView(P.snap, L);
+    C.L = L; C.Lp = w.Lp;
+    C.var_hash = reinterpret_cast<uint64_t *>(wsb + w.var_hash); C.hash_mask = w.hash_cap - 1u; C.var_direct = false;
+    C.codebook = nullptr; C.rname = nullptr; C.list = nullptr; C.list_n = 0; C.list_cap = 0;
+    C.n_rows = 0; C.pa_init = false; C.pos_card = 1u; C.pos_n = 1u; C.pos_rv = 0u; C.pos_rc = 0u;
+    C.last_lo = 0; C.last_n = 0; C.tri_flag = 0u;
+    if (lane == 0) {
+        WarpCold &W = sh[warp].c;
+        W.pos_cap = w.pos_cap; W.rows_cap = w.rows_cap; W.pad = 0; W.io = nullptr; W.io_cap = 0; W.ref = nullptr; W.ref_len = 0;
+        W.edits_cap_abs = B.edit_base + B.n_edits;
+    }
+    __syncwarp();
+    uint4 *T = reinterpret_cast<uint4 *>(P.tri) + k2_tri_off(B, b);
+    uint4 *slots = T + 1;
+    const WarpModels *SM = reinterpret_cast<const WarpModels *>(C.snap.small());
+    WarpModels *FM = reinterpret_cast<WarpModels *>(P.fin + (uint64_t)b * fin_stride_dev());
+    const uint4 *recs = reinterpret_cast<const uint4 *>(P.recs) + r0;
+    uint32_t i = 0, slot = 0;
+#define K2M_FAIL(code) do { C.err = (code); goto chain_done; } while (0)
+
+    if (B.chr >= P.genome.n_chr) K2M_FAIL(CBCG_ERR_NO_REFERENCE);         /* blocks never span chromosomes: the host cut them */
+    if (role == CBCG_SUB_POS) {
+        /* ---- POS through the growing alphabet (compress_pos :113-159, compress_pos_alpha :75-108) */
+        C.pos_card = C.snap.pos_hdr()[0]; C.pos_n = C.snap.pos_hdr()[1];
+        if (C.pos_card > w.pos_cap) K2M_FAIL(CBCG_ERR_INTERNAL);
+        C.pos_rv = (lane < C.pos_card) ? C.snap.pos_val()[lane] : 0u;
+        C.pos_rc = (lane < C.pos_card) ? C.snap.pos_cnt()[lane] : 0u;
+        for (uint32_t q = 32u + lane; q < C.pos_card; q += 32u) { C.pos_gval()[q] = C.snap.pos_val()[q]; C.pos_gcnt()[q] = C.snap.pos_cnt()[q]; }
+        __syncwarp();
+        uint4 *esc = T + k2_tri_esc(B);
+        uint32_t prev_pos = B.base_pos;
+        uint4 v = n_reads ? recs[0] : make_uint4(0u, 0u, 0u, 0u);
+        for (; i < n_reads; i++) {
+            const uint4 nx = (i + 1u < n_reads) ? recs[i + 1u] : v;        /* next read's record: off the chain */
+            const uint32_t pos = v.x;
+            if (pos == 0u || pos < prev_pos || pos - prev_pos + 1u > CBCG_MAX_POS_X) K2M_FAIL(CBCG_ERR_INPUT);
+            const uint32_t x = pos - prev_pos + 1u;
+            uint32_t s = 1u;
+            C.tri_at = slots + slot + lead;
+            C.sym_pos_main(x, s);
+            if (C.err) break;
+            if (s == 0u) {                                   /* escape: the value itself, 4 bytes MSB first, then a new slot */
+                C.pa_ensure();
+                for (uint32_t k = 0; k < 4u; k++) {
+                    C.tri_at = esc++;
+                    C.template sym_dense<0, false>(C.pos_alpha() + k * PA_STRIDE, 256u, 10u, (x >> (24u - 8u * k)) & 0xffu, false, 0u);
+                }
+                if (C.err) break;
+                C.pos_append(x);
+                if (C.err) break;
+            }
+            prev_pos = pos;
+            slot += k2m_slots(v.w, lead);
+            v = nx;
+        }
+    } else if (role == CBCG_SUB_FLAG) {
+        /* ---- length byte 0 (variable-length containers) and FLAG (compress_read :29-33, compress_flag :50-70) */
+        k2b_copy(S.rlen0, SM->rlen0, 256u, lane);
+        k2b_copy(S.same_ref, SM->same_ref, 4u + 6u, lane);                 /* same_ref, rlenk: never coded here, the merge reads the image */
+        { const uint32_t used = SM->flag_used; k2b_copy(S.flag_key, SM->flag_key, used, lane); k2b_copy(S.flag_cnt, SM->flag_cnt, used, lane);
+          if (lane == 0) { S.flag_used = used; S.flag_n = SM->flag_n; } }
+        __syncwarp();
+        uint4 v = n_reads ? recs[0] : make_uint4(0u, 0u, 0u, 0u);
+        for (; i < n_reads; i++) {
+            const uint4 nx = (i + 1u < n_reads) ? recs[i + 1u] : v;
+            const uint32_t flag = v.y & 0xffffu, len = v.y >> 16;
+            if (len == 0u || len > CBCG_MAX_READ_LEN || (fixed && len != L)) K2M_FAIL(CBCG_ERR_INPUT);
+            if (!fixed) { C.tri_at = slots + slot; C.template sym_dense<0, false>(S.rlen0, 255u, 10u, len & 0xffu, false, 0u); }
+            C.tri_at = slots + slot + lead + 1u;
+            C.sym_flag(flag);
+            if (C.err) break;
+            slot += k2m_slots(v.w, lead);
+            v = nx;
+        }
+        if (!C.err && lane == 0) T[0] = make_uint4(slot, 0u, 0u, 0u);                 /* the block's main slots: what the interval kernel walks */
+    } else if (role == CBCG_SUB_COUNTS) {
+        /* ---- match bit, SNP count, indel counts (compress_match :164-188, compress_snps / compress_indels :193-228) */
+        k2b_copy(S.snps, SM->snps, 512u, lane);                            /* snps, indels */
+        k2b_copy(&S.match[0][0], &SM->match[0][0], 16u, lane);
+        __syncwarp();
+        uint32_t prev_pos = B.base_pos, prev_m = 0u;
+        uint4 v = n_reads ? recs[0] : make_uint4(0u, 0u, 0u, 0u);
+        for (; i < n_reads; i++) {
+            const uint4 nx = (i + 1u < n_reads) ? recs[i + 1u] : v;
+            const uint32_t pos = v.x, match = v.w & 0xffu, ns = (v.w >> 8) & 0xffu, nd = (v.w >> 16) & 0xffu, ni = v.w >> 24;
+            const uint32_t samepos = pos == prev_pos ? 1u : 0u;            /* deltaP == 1 (:170) */
+            prev_pos = pos;
+            uint4 *at = slots + slot + lead + 2u;
+            C.tri_at = at;
+            C.template sym_dense<2, false>(S.match[(samepos << 1) | prev_m], 2u, 1u, match, false, 0u);
+            if (C.err) break;
+            prev_m = match;
+            if (!match) {
+                C.tri_at = at + 1;
+                C.template sym_dense<0, false>(S.snps, L, 10u, ((nd | ni) == 0u) ? ns : 0u, false, 0u);
+                if (!C.err && (nd | ni) != 0u) {                           /* :560-565 */
+                    C.tri_at = at + 2; C.template sym_dense<0, false>(S.indels, L, 16u, ns, false, 0u);
+                    C.tri_at = at + 3; C.template sym_dense<0, false>(S.indels, L, 16u, nd, false, 0u);
+                    C.tri_at = at + 4; C.template sym_dense<0, false>(S.indels, L, 16u, ni, false, 0u);
+                }
+                if (C.err) break;
+            }
+            slot += k2m_slots(v.w, lead);
+            v = nx;
+        }
+    } else {
+        /* ---- edit positions through the var rows, bases through chars (:568-600; compute_delta_to_first_snp :703-718) */
+        k2b_copy(&S.chars[0][0], &SM->chars[0][0], 48u, lane);
+        for (uint32_t q = lane; q <= C.hash_mask; q += 32u) C.var_hash[q] = 0ull;
+        __syncwarp();
+        C.ring_reset();
+        uint4 v = n_reads ? recs[0] : make_uint4(0u, 0u, 0u, 0u);
+        for (; i < n_reads; i++) {
+            const uint4 nx = (i + 1u < n_reads) ? recs[i + 1u] : v;
+            const uint32_t pos = v.x, flag = v.y & 0xffffu, len = v.y >> 16, match = v.w & 0xffu;
+            const uint32_t ns = (v.w >> 8) & 0xffu, nd = (v.w >> 16) & 0xffu, ni = v.w >> 24;
+            if (pos == 0u) K2M_FAIL(CBCG_ERR_INPUT);
+            if (!(nx.w & 0xffu)) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.edits + nx.z));
+            const uint32_t strand = (flag >> 4) & 1u;                      /* :57-60 */
+            C.ring_advance(pos);
+            if (!match) {
+                const uint16_t *e_in = P.edits + v.z;
+                uint4 *at = slots + slot + lead + 4u + ((nd | ni) ? 3u : 0u);
+                uint32_t prev = 0;
+                for (uint32_t k = 0; k < nd; k++) {                         /* deletions (:568-572) */
+                    uint32_t *m = C.var_row((prev << 1) | strand);
+                    if (!m) break;
+                    const uint32_t d = CBCG_EDIT_DELTA((uint32_t)e_in[k]);
+                    C.tri_at = at++;
+                    C.template sym_dense<0, true>(m, L, 10u, d, false, 0u);
+                    if (C.err) break;
+                    prev += d;
+                }
+                prev = 0;
+                for (uint32_t k = 0; k < ns && !C.err; k++) {               /* SNPs (:573-593) */
+                    const uint32_t ed = e_in[nd + k];
+                    const uint32_t delta = C.ring_first(pos - 1u + prev, (prev < len) ? pos - 1u + len : pos - 1u + prev, len + 2u);
+                    uint32_t *m = C.var_row((((delta << CBCG_BITS_DELTA) + prev) << 1) | strand);
+                    if (!m) break;
+                    const uint32_t p = CBCG_EDIT_DELTA(ed);
+                    C.tri_at = at++;
+                    C.template sym_dense<0, true>(m, L, 10u, p, false, 0u);
+                    if (C.err) break;
+                    prev += p + 1u;
+                    C.ring_set(pos + prev - 2u);                            /* :589 */
+                    const uint32_t refb = CBCG_EDIT_REFB(ed);
+                    if (refb > 5u) K2M_FAIL(CBCG_ERR_INPUT);
+                    C.tri_at = at++;
+                    C.template sym_dense<5, false>(S.chars[refb], 5u, 8u, CBCG_EDIT_TARGET(ed), false, 0u);
+                }
+                prev = 0;
+                for (uint32_t k = 0; k < ni && !C.err; k++) {               /* insertions (:594-600) */
+                    const uint32_t ed = e_in[nd + ns + k];
+                    uint32_t *m = C.var_row((prev << 1) | strand);
+                    if (!m) break;
+                    const uint32_t p = CBCG_EDIT_DELTA(ed);
+                    C.tri_at = at++;
+                    C.template sym_dense<0, true>(m, L, 10u, p, false, 0u);
+                    prev += p;
+                    C.tri_at = at++;
+                    C.template sym_dense<5, false>(S.chars[CBCG_BP_O], 5u, 8u, CBCG_EDIT_TARGET(ed), false, 0u);
+                }
+                if (C.err) break;
+            }
+            slot += k2m_slots(v.w, lead);
+            v = nx;
+        }
+    }
+chain_done:
+#undef K2M_FAIL
+    if (C.err) { dev_set_error(P.err, C.err, ((uint64_t)b << 20) | (i & 0xfffffu)); return; }
+    /* ---- leave the final model state where the merge kernels read it */
+    __syncwarp();
+    if (role == CBCG_SUB_POS) {
+        if (lane < C.pos_card) { C.pos_gval()[lane] = C.pos_rv; C.pos_gcnt()[lane] = C.pos_rc; }
+        if (lane == 0) { B.pos_card = C.pos_card; B.pa_touched = C.pa_init ? 1u : 0u; }
+    } else if (role == CBCG_SUB_FLAG) {
+        k2b_copy(FM->rlen0, S.rlen0, 256u, lane); k2b_copy(FM->same_ref, S.same_ref, 10u, lane);
+        const uint32_t used = S.flag_used;
+        k2b_copy(FM->flag_key, S.flag_key, used, lane); k2b_copy(FM->flag_cnt, S.flag_cnt, used, lane);
+        if (lane == 0) { FM->flag_used = used; FM->flag_n = S.flag_n; }
+    } else if (role == CBCG_SUB_COUNTS) {
+        k2b_copy(FM->snps, S.snps, 512u, lane); k2b_copy(&FM->match[0][0], &S.match[0][0], 16u, lane);
+    } else {
+        k2b_copy(&FM->chars[0][0], &S.chars[0][0], 48u, lane);
+        if (lane == 0) B.n_rows = C.n_rows;
+    }
+}
+
+/* one-stream blocks, encode: the model kernel, then the interval kernel (k2_blocks.cu) */
+static int launch_split_encode(const CoderParams &p, cudaStream_t st) {
+    const dim3 grid((p.n_blocks + K2_WARPS - 1u) / K2_WARPS, CBCG_N_SUB);
+    const char *rm = getenv("CBCG_K2M_ROLES");                          /* timing experiments: chains to run (tools/role_times.py) */
+    const uint32_t role_mask = rm ? (uint32_t)atoi(rm) : 0xfu;
+    k2_model_kernel<<<grid, K2_THREADS, 0, st>>>(p, role_mask);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return launch_code_kernel(p, st);
+}
+
 uint32_t coder_resident_blocks(int device) {
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) return 148u * 16u;
@@ -1572,7 +1826,7 @@ void set_carveout_all(int pct) {
     if (pct == current) return;
     current = pct;
     set_carveout(k2_coder_kernel<MODE_ENC, false>, pct); set_carveout(k2_coder_kernel<MODE_DEC, false>, pct); set_carveout(k2_coder_kernel<MODE_LIST, false>, pct);
-    set_carveout(k2_block_kernel<MODE_ENC>, pct); set_carveout(k2_block_kernel<MODE_DEC>, pct);
+    set_carveout(k2_block_kernel<MODE_ENC>, pct); set_carveout(k2_block_kernel<MODE_DEC>, pct); set_carveout(k2_model_kernel, pct);
     set_carveout(k2_coder_kernel<MODE_ENC, true>, pct); set_carveout(k2_coder_kernel<MODE_DEC, true>, pct); set_carveout(k2_coder_kernel<MODE_LIST, true>, pct);
     set_carveout(k2_plan_kernel, pct); set_carveout(k2_payload_scan_kernel, pct); set_carveout(k2_gather_kernel, pct);
     set_carveout(snapshot_copy_kernel, pct);
@@ -1580,6 +1834,15 @@ void set_carveout_all(int pct) {
     extract_set_carveout(pct); reconstruct_set_carveout(pct); roles_set_carveout(pct); unpack_set_carveout(pct);
 }
 
+static bool split_encode(const CoderParams &p) {
+    static const bool one_kernel = getenv("CBCG_ONE_KERNEL_ENCODE") != nullptr;   /* cross-check: the one-kernel encoder */
+    return !one_kernel && !p.legacy && p.mode == MODE_ENC && p.tri && p.primed && p.n_sub <= 1u;
+}
+uint32_t coder_launches(const CoderParams &p) {
+    if (p.n_blocks == 0) return 0u;
+    if (!p.legacy && p.mode != MODE_LIST && p.n_sub > 1u) return roles_launches(p.mode);
+    return split_encode(p) ? 2u : 1u;
+}
 int launch_block_kernel(const CoderParams &p, cudaStream_t st);
 int launch_coder(const CoderParams &p, cudaStream_t st) {
     if (p.n_blocks == 0) return 0;
@@ -1587,6 +1850,7 @@ int launch_coder(const CoderParams &p, cudaStream_t st) {
         static const bool scalar = getenv("CBCG_SCALAR_ROLES") != nullptr;   /* cross-check: the scalar twin (k2_blocks.cu) */
         return scalar ? launch_roles(p, st) : launch_block_kernel(p, st);
     }
+    if (split_encode(p)) return launch_split_encode(p, st);
     const unsigned grid = (p.n_blocks + K2_WARPS - 1) / K2_WARPS;
     if (p.legacy) {
         if (p.mode == MODE_ENC) k2_coder_kernel<MODE_ENC, true><<<grid, K2_THREADS, 0, st>>>(p);
