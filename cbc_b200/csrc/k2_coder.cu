@@ -1565,6 +1565,9 @@ int launch_block_kernel(const CoderParams &p, cudaStream_t st) {
 #ifndef K2M_MIN_CTAS
 #define K2M_MIN_CTAS 8
 #endif
+/* chains of a block: POS | length + FLAG | match + counts | edit positions + bases (CBCG_SUB_*; the grid runs them from
+   the last to the first: the longest chain is scheduled first) */
+#define K2M_ROLES      CBCG_N_SUB
 __device__ __forceinline__ uint32_t k2m_slots(uint32_t cw, uint32_t lead) {       /* symbols of one read in stream order */
     const uint32_t match = cw & 0xffu, ns = (cw >> 8) & 0xffu, nd = (cw >> 16) & 0xffu, ni = cw >> 24;
     return lead + 3u + (match ? 0u : 1u + ((nd | ni) ? 3u : 0u) + nd + 2u * ns + 2u * ni);
@@ -1573,7 +1576,7 @@ __global__ void __launch_bounds__(K2_THREADS, K2M_MIN_CTAS)
 k2_model_kernel(CoderParams P, uint32_t role_mask) {
     __shared__ __align__(16) WarpShared sh[K2_WARPS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t role = (CBCG_N_SUB - 1u) - blockIdx.y;                 /* the longest chain (var + bases) is scheduled first */
+    const uint32_t role = (K2M_ROLES - 1u) - blockIdx.y;                  /* the longest chain (edit positions) is scheduled first */
     if (!((role_mask >> role) & 1u)) return;                              /* timing experiments only (CBCG_K2M_ROLES) */
     const uint32_t bl = blockIdx.x * K2_WARPS + warp;
     if (bl >= P.n_blocks) return;
@@ -1647,25 +1650,73 @@ k2_model_kernel(CoderParams P, uint32_t role_mask) {
             v = nx;
         }
     } else if (role == CBCG_SUB_FLAG) {
-        /* ---- length byte 0 (variable-length containers) and FLAG (compress_read :29-33, compress_flag :50-70) */
+        /* ---- length byte 0 (variable-length containers) and FLAG (compress_read :29-33, compress_flag :50-70).
+           While the sparse FLAG table has <= 32 touched values it lives one entry per lane, ascending like the table in
+           shared memory: key, count, and the extras (count - 1) of all entries below, kept up to date by a predicated add
+           per update -- so a symbol's cumulative count x + extras(below x) is two ballots and two shuffles, no scan. An
+           insertion into a full warp or a rescale writes the entries to shared memory and carries on there (sym_flag). */
         k2b_copy(S.rlen0, SM->rlen0, 256u, lane);
         k2b_copy(S.same_ref, SM->same_ref, 4u + 6u, lane);                 /* same_ref, rlenk: never coded here, the merge reads the image */
-        { const uint32_t used = SM->flag_used; k2b_copy(S.flag_key, SM->flag_key, used, lane); k2b_copy(S.flag_cnt, SM->flag_cnt, used, lane);
-          if (lane == 0) { S.flag_used = used; S.flag_n = SM->flag_n; } }
+        uint32_t used = SM->flag_used, fn = SM->flag_n;
+        k2b_copy(S.flag_key, SM->flag_key, used, lane); k2b_copy(S.flag_cnt, SM->flag_cnt, used, lane);
+        if (lane == 0) { S.flag_used = used; S.flag_n = fn; }
         __syncwarp();
+        bool in_regs = used <= 32u;
+        uint32_t fk = 0xffffffffu, fc = 1u, fE = 0u, etot = 0u;
+#define K2M_FLAG_LOAD() do { \
+            fk = (lane < used) ? S.flag_key[lane] : 0xffffffffu; fc = (lane < used) ? S.flag_cnt[lane] : 1u; \
+            const uint32_t e1_ = fc - 1u, in_ = warp_incl_scan(e1_); fE = in_ - e1_; etot = __shfl_sync(FULL_MASK, in_, 31); } while (0)
+#define K2M_FLAG_STORE() do { \
+            if (lane < used) { S.flag_key[lane] = fk; S.flag_cnt[lane] = fc; } \
+            if (lane == 0) { S.flag_used = used; S.flag_n = fn; } \
+            __syncwarp(); } while (0)
+        if (in_regs) K2M_FLAG_LOAD();
         uint4 v = n_reads ? recs[0] : make_uint4(0u, 0u, 0u, 0u);
         for (; i < n_reads; i++) {
             const uint4 nx = (i + 1u < n_reads) ? recs[i + 1u] : v;
             const uint32_t flag = v.y & 0xffffu, len = v.y >> 16;
             if (len == 0u || len > CBCG_MAX_READ_LEN || (fixed && len != L)) K2M_FAIL(CBCG_ERR_INPUT);
             if (!fixed) { C.tri_at = slots + slot; C.template sym_dense<0, false>(S.rlen0, 255u, 10u, len & 0xffu, false, 0u); }
-            C.tri_at = slots + slot + lead + 1u;
-            C.sym_flag(flag);
-            if (C.err) break;
+            uint4 *at = slots + slot + lead + 1u;
+            bool coded = false;
+            if (LIKELY(in_regs)) {
+                const uint32_t p = (uint32_t)__popc(__ballot_sync(FULL_MASK, fk < flag));       /* entries below: lanes 0 .. p-1 */
+                const bool found = __ballot_sync(FULL_MASK, fk == flag) != 0u;
+                const uint32_t Ep = __shfl_sync(FULL_MASK, fE, p & 31u), cp = __shfl_sync(FULL_MASK, fc, p & 31u);
+                const uint32_t below = p < used ? Ep : etot;
+                if (found || used < 32u) {
+                    if (lane == 0) *at = make_uint4(flag + below, found ? cp : 1u, fn, 0u);
+                    C.n_symbols++;
+                    if (found) { if (lane == p) fc += 8u; }                  /* update_model, step 8 */
+                    else {                                                   /* first touch: (flag, 1 + 8) enters at p */
+                        const uint32_t ku = __shfl_up_sync(FULL_MASK, fk, 1), cu = __shfl_up_sync(FULL_MASK, fc, 1), eu = __shfl_up_sync(FULL_MASK, fE, 1);
+                        if (lane > p) { fk = ku; fc = cu; fE = eu; }
+                        if (lane == p) { fk = flag; fc = 9u; fE = below; }
+                        used++;
+                    }
+                    if (lane > p) fE += 8u;
+                    etot += 8u; fn += 8u;
+                    if (UNLIKELY(fn >= CBCG_RESCALE)) {                      /* update_model :38-49, on the table in shared memory */
+                        K2M_FLAG_STORE();
+                        fn = rescale_counts(S.flag_cnt, used, lane) + (65536u - used);
+                        __syncwarp();
+                        K2M_FLAG_LOAD();
+                    }
+                    coded = true;
+                } else { K2M_FLAG_STORE(); in_regs = false; }                /* a 33rd value: the table moves to shared memory */
+            }
+            if (!coded) {
+                C.tri_at = at;
+                C.sym_flag(flag);
+                if (C.err) break;
+            }
             slot += k2m_slots(v.w, lead);
             v = nx;
         }
-        if (!C.err && lane == 0) T[0] = make_uint4(slot, 0u, 0u, 0u);                 /* the block's main slots: what the interval kernel walks */
+        if (!C.err && in_regs) K2M_FLAG_STORE();
+#undef K2M_FLAG_LOAD
+#undef K2M_FLAG_STORE
+        if (!C.err && lane == 0) T[0] = make_uint4(slot, 0u, 0u, 0u);   /* the block's main slots: what the interval kernel walks */
     } else if (role == CBCG_SUB_COUNTS) {
         /* ---- match bit, SNP count, indel counts (compress_match :164-188, compress_snps / compress_indels :193-228) */
         k2b_copy(S.snps, SM->snps, 512u, lane);                            /* snps, indels */
@@ -1697,7 +1748,11 @@ k2_model_kernel(CoderParams P, uint32_t role_mask) {
             v = nx;
         }
     } else {
-        /* ---- edit positions through the var rows, bases through chars (:568-600; compute_delta_to_first_snp :703-718) */
+        /* ---- edit positions through the var rows, bases through chars (:568-600; compute_delta_to_first_snp :703-718).
+           Measured and dropped: the bases as a fifth chain of their own (220 M more warp instructions for the second walk
+           over the records, 0.24 ms slower: the kernel as a whole is bound by instruction issue, not by its longest chain);
+           asking for the next context's hash line and snapshot row one symbol ahead (the contexts depend on the input
+           alone): this chain alone 1.65 -> 1.79 ms. */
         k2b_copy(&S.chars[0][0], &SM->chars[0][0], 48u, lane);
         for (uint32_t q = lane; q <= C.hash_mask; q += 32u) C.var_hash[q] = 0ull;
         __syncwarp();
@@ -1782,7 +1837,7 @@ chain_done:
 
 /* one-stream blocks, encode: the model kernel, then the interval kernel (k2_blocks.cu) */
 static int launch_split_encode(const CoderParams &p, cudaStream_t st) {
-    const dim3 grid((p.n_blocks + K2_WARPS - 1u) / K2_WARPS, CBCG_N_SUB);
+    const dim3 grid((p.n_blocks + K2_WARPS - 1u) / K2_WARPS, K2M_ROLES);
     const char *rm = getenv("CBCG_K2M_ROLES");                          /* timing experiments: chains to run (tools/role_times.py) */
     const uint32_t role_mask = rm ? (uint32_t)atoi(rm) : 0xfu;
     k2_model_kernel<<<grid, K2_THREADS, 0, st>>>(p, role_mask);
