@@ -347,6 +347,16 @@ static int batch_copy_range(cbcg_ctx *ctx, const cbcg_batch *b, uint64_t r0, uin
     for (auto &c : cp) { if (c.bytes) CU(cudaMemcpyAsync(c.d, c.h, c.bytes, cudaMemcpyHostToDevice, st)); *bytes += c.bytes; }
     return 0;
 }
+/* K1's reference window (DevBatch.ref_cap): bytes of reference that 128 position-adjacent reads span at this batch's
+ * coverage, twice over, plus a read. From the first and last POS of every chromosome run. */
+static uint32_t ref_window_estimate(const cbcg_ctx *ctx, const uint32_t *pos, uint64_t n, uint32_t max_len) {
+    if (!n || !pos) return 0u;
+    uint64_t span = 0;
+    for (const ChrRun &r : ctx->runs) if (r.n) { const uint32_t a = pos[r.first], z = pos[r.first + r.n - 1]; if (z > a) span += z - a; }
+    const double per_read = (double)span / (double)n;
+    const double want = per_read * 128.0 * 2.0 + max_len + 64.0;
+    return want > 1e9 ? 0u : (uint32_t)want;
+}
 /* Host scan of the batch: chromosome runs (blocks never span chromosomes), longest and shortest read. */
 static int batch_scan(cbcg_ctx *ctx, const cbcg_batch *b) {
     const uint64_t n = b->n_reads;
@@ -371,6 +381,7 @@ static int batch_scan(cbcg_ctx *ctx, const cbcg_batch *b) {
         ctx->runs.push_back(run);
     }
     ctx->db.max_len = max_len;
+    ctx->db.ref_cap = ref_window_estimate(ctx, b->pos, n, max_len);
     ctx->batch_min_len = n ? min_len : 0;
     ctx->total_bases = n ? b->seq_off[n] - b->seq_off[0] : 0;
     if (n && (min_len == 0 || max_len > CBCG_MAX_READ_LEN))
@@ -436,6 +447,7 @@ static int compact_buffers(cbcg_ctx *ctx, const cbcg_batch_compact *b) {
     ctx->db.cigar_off = ctx->b_coff.as<uint64_t>(); ctx->db.cigar = ctx->b_cigar.as<uint8_t>();
     ctx->db.md_off = ctx->b_moff.as<uint64_t>(); ctx->db.md = ctx->b_md.as<uint8_t>();
     ctx->db.max_len = n ? b->max_len : 0; ctx->batch_min_len = n ? b->min_len : 0; ctx->total_bases = seq_b;
+    ctx->db.ref_cap = ref_window_estimate(ctx, b->pos, n, ctx->db.max_len);
     return 0;
 }
 /* the small pieces every chunk needs: tile offsets, chromosome runs, the exception list (first on the link) */
@@ -871,7 +883,7 @@ static int encode_resident_overlapped(cbcg_ctx *ctx, const cbcg_encode_opts *opt
     CU(cudaEventRecord(ctx->ev[3], ctx->st));
     if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), 1, ctx->layout_mode, ctx->st))
         return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
-    S.kernel_launches += 7;                                 /* K1 x 2, plan x 2, last generation, gather x 2 */
+    S.kernel_launches += 6 + coder_launches(q);             /* K1 x 2, plan x 2, gather x 2, the last generation */
     CU(cudaEventRecord(ctx->ev[4], ctx->st));
     CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaMemcpyAsync(&ctx->hw->total_bytes, ctx->out_off.as<uint64_t>() + nb, 8, cudaMemcpyDeviceToHost, ctx->st));
@@ -1453,8 +1465,22 @@ static int run_decode_blocks(cbcg_ctx *ctx, uint64_t nb, uint32_t L, int legacy,
     return 0;
 }
 
+/* K3's reference window from the block index (ctx->hblocks, nb > 1 blocks of a blocked container): the distance between
+ * the first reads of consecutive blocks of a chromosome, per read, for a tile of 128 reads, twice over, plus a read. */
+static uint32_t ref_window_from_blocks(const cbcg_ctx *ctx, uint32_t max_len) {
+    const uint64_t nb = ctx->gens.empty() ? 0 : (uint64_t)ctx->gens.back().first + ctx->gens.back().second;   /* blocks of the last cut / index */
+    if (nb < 2 || !ctx->hblocks) return 0u;
+    uint64_t span = 0, reads = 0;
+    for (uint64_t k = 0; k + 1 < nb; k++) {
+        const BlockDesc &a = ctx->hblocks[k], &z = ctx->hblocks[k + 1];
+        if (a.chr == z.chr && z.base_pos >= a.base_pos && z.first_read > a.first_read) { span += z.base_pos - a.base_pos; reads += z.first_read - a.first_read; }
+    }
+    if (!reads) return 0u;
+    const double want = (double)span / (double)reads * 128.0 * 2.0 + max_len + 64.0;
+    return want > 1e9 ? 0u : (uint32_t)want;
+}
 /* fixed_len != 0: every record is that long (CBCG_MODE_FIXED_LEN container, or checked by the caller). */
-static int run_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, uint32_t max_len, uint32_t fixed_len, const uint32_t *chr_dev) {
+static int run_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, uint32_t max_len, uint32_t fixed_len, const uint32_t *chr_dev, uint32_t ref_cap_hint = 0) {
     const uint64_t out_cap = n_reads * ((uint64_t)max_len + 1u);
     TRY(ensure(ctx, ctx->seq_out, out_cap + 64));
     TRY(ensure(ctx, ctx->tile_desc, (reconstruct_num_tiles(n_reads) + 1) * 8));
@@ -1462,7 +1488,7 @@ static int run_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, uint32_t max_len, ui
     if (launch_reconstruct(n_reads, ctx->recs.as<cbcg_read_rec>(), chr_dev, ctx->edits.as<uint16_t>(), ctx->dg,
                            ctx->seq_out.as<uint8_t>(), out_cap, max_len, fixed_len, ctx->tile_desc.as<uint64_t>(),
                            wptr<uint32_t>(ctx, W_OFF(ticket)), wptr<uint64_t>(ctx, W_OFF(total_bytes)),
-                           wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st, ctx->kev[2], ctx->kev[3]))
+                           wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st, ctx->kev[2], ctx->kev[3], ref_cap_hint))
         return fail(ctx, CBCG_ERR_CUDA, "K3 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     ctx->stats.kernel_launches++;
     return 0;
@@ -1576,6 +1602,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
     if (ctx->gens.size() < 2) return PIPE_FALLBACK;
     const uint32_t nb = c.n_blocks;
     BlockDesc *hb = ctx->hblocks;
+    const uint32_t k3_ref_cap = ref_window_from_blocks(ctx, c.L);
     const uint32_t last_first = ctx->gens.back().first, last_n = ctx->gens.back().second;
     uint64_t early_reads = 0;
     for (uint32_t k = 0; k < last_first; k++) early_reads += hb[k].n_reads;
@@ -1653,7 +1680,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
             if (launch_reconstruct(r1 - r0, ctx->recs.as<cbcg_read_rec>() + r0, ctx->chr_out.as<uint32_t>() + r0, ctx->edits.as<uint16_t>(),
                                    ctx->dg, ctx->seq_out.as<uint8_t>() + r0 * line, (r1 - r0) * line, c.L, c.L, ctx->tile_desc.as<uint64_t>(),
                                    wptr<uint32_t>(ctx, W_OFF(ticket)), wptr<uint64_t>(ctx, W_OFF(total_bytes)),
-                                   wptr<unsigned long long>(ctx, W_OFF(err)), sd, nullptr, nullptr))
+                                   wptr<unsigned long long>(ctx, W_OFF(err)), sd, nullptr, nullptr, k3_ref_cap))
                 return fail(ctx, CBCG_ERR_CUDA, "K3 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             S.kernel_launches++;
             CU(cudaEventRecord(ctx->tev[2 * g + 1], sd));
@@ -1728,7 +1755,7 @@ extern "C" int cbcg_decode(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, in
     if (n_reads) *n_reads = nr;
     if (!nr) return CBCG_OK;
     if (legacy) max_len = CBCG_MAX_READ_LEN;                /* per-read lengths are coded mod 256 (src/read_compression.c:29-33) */
-    TRY(run_reconstruct(ctx, nr, max_len, fixed_len, ctx->chr_out.as<uint32_t>()));
+    TRY(run_reconstruct(ctx, nr, max_len, fixed_len, ctx->chr_out.as<uint32_t>(), legacy ? 0u : ref_window_from_blocks(ctx, max_len)));
     CU(cudaEventRecord(ctx->ev[3], ctx->st));
     TRY(fetch_words(ctx));
     TRY(device_error(ctx, "read reconstruction"));
@@ -1795,7 +1822,8 @@ extern "C" int cbcg_decode_resident(cbcg_ctx *ctx) {
     CU(cudaEventRecord(ctx->ev[1], ctx->st));
     if (nr) {
         TRY(run_reconstruct(ctx, nr, legacy ? CBCG_MAX_READ_LEN : std::max(ctx->enc_max_len, 1u),
-                            (!legacy && ctx->enc_fixed) ? ctx->enc_L : 0u, ctx->chr_out.as<uint32_t>()));
+                            (!legacy && ctx->enc_fixed) ? ctx->enc_L : 0u, ctx->chr_out.as<uint32_t>(),
+                            legacy ? 0u : ref_window_from_blocks(ctx, std::max(ctx->enc_max_len, 1u))));
         CU(cudaEventRecord(ctx->ev[2], ctx->st));
         TRY(fetch_words(ctx));
         TRY(device_error(ctx, "read reconstruction"));

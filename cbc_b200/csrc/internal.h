@@ -17,6 +17,7 @@ struct DevBatch {
     const uint64_t *cigar_off; const uint8_t *cigar;
     const uint64_t *md_off;    const uint8_t *md;
     uint32_t max_len;                      /* max(seq_len) */
+    uint32_t ref_cap;                      /* K1: bytes of reference a tile of 128 reads is expected to span, with margin (0: no estimate) */
 };
 
 /* Reference genome resident in HBM: one byte per base, upper-cased, records concatenated with
@@ -104,7 +105,7 @@ int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, u
 int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr, const uint16_t *edits,
                        const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len, uint32_t fixed_len,
                        uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
-                       unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop);
+                       unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop, uint32_t ref_cap_hint = 0);
 /* k0_unpack.cu: reads [r_begin, r_end) of a compact batch (r_begin a multiple of 128) -> the SoA batch */
 int launch_unpack(uint64_t r_begin, uint64_t r_end, uint64_t n_reads, const uint16_t *seq_len, const uint16_t *cigar_len, const uint16_t *md_len,
                   const uint8_t *seq2, const uint64_t *tile_base, const uint64_t *run_first, const uint32_t *run_chr, uint32_t n_runs,

@@ -16,12 +16,13 @@
  *   - phase 3, lane per read: the same walk again, now writing u16 edit entries and the 16-byte record.
  * Algorithmic HBM bytes per read: L + CIGAR + MD + 24 (fixed fields) + L/coverage (window) + 16 + 2*edits.
  */
+#include <algorithm>
 #include "common.cuh"
 #include "internal.h"
 
 #define K1_TILE     128u          /* reads per tile == threads per CTA */
 #define K1_WARPS    (K1_TILE / 32u)
-#define K1_REF_CAP  8192u         /* bytes of reference window staged per tile */
+#define K1_REF_CAP  8192u         /* most bytes of reference window staged per tile (DevBatch.ref_cap picks less for dense batches) */
 
 uint64_t extract_num_tiles(uint64_t n_reads) { return (n_reads + K1_TILE - 1) / K1_TILE; }
 
@@ -196,16 +197,16 @@ struct K1Smem {
     uint16_t len[K1_TILE];
     uint16_t chr_ok[K1_TILE];        /* bit 0: read may use the staged window, bit 1: read passes the input checks */
     uint16_t ecache[K1_TILE][K1_ECACHE];
-    __align__(16) uint8_t ref[K1_REF_CAP + 64];
-    __align__(16) uint8_t seq[16];   /* really K1_TILE * max_len + 48 (dynamic) */
+    __align__(16) uint8_t dyn[16];   /* ref_cap + 64 bytes of reference window, then K1_TILE * max_len + 48 bytes of SEQ (dynamic) */
 };
 
 __global__ void __launch_bounds__(K1_TILE)
 k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uint16_t *__restrict__ edits,
                   uint64_t edits_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_edits,
-                  unsigned long long *err, uint32_t seq_cap, uint64_t r_begin, uint64_t r_end, const uint64_t *edit_base) {
+                  unsigned long long *err, uint32_t seq_cap, uint32_t ref_cap, uint64_t r_begin, uint64_t r_end, const uint64_t *edit_base) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     K1Smem &S = *reinterpret_cast<K1Smem *>(smem_raw);
+    uint8_t *const s_ref = S.dyn, *const s_seq = S.dyn + ref_cap + 64u;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if (tid == 0) {
@@ -233,7 +234,7 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
         ref0 = g.bases + g.chr_off[chr0];
         w0 = pos0 ? ((uint64_t)(pos0 - 1u) & ~15ull) : 0ull;
         uint64_t avail = (clen0 + REF_PAD > w0) ? ((clen0 + REF_PAD - w0) & ~15ull) : 0ull;
-        ref_bytes = (uint32_t)min((uint64_t)K1_REF_CAP, avail);
+        ref_bytes = (uint32_t)min((uint64_t)ref_cap, avail);
         /* position-sorted input: the tile's last read bounds the window (a read beyond it takes the HBM path) */
         if (chr_l == chr0 && pos_l >= pos0 && pos0) {
             const uint64_t need = ((uint64_t)(pos_l - 1u) - w0 + b.max_len + 8u + 15u) & ~15ull;
@@ -243,8 +244,8 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
     if (tid == 0) {
         uint32_t tx = (seq_ok ? (uint32_t)seq_bytes : 0u) + ref_bytes;
         mbar_expect_tx(&S.bar, tx);
-        if (seq_ok && seq_bytes) tma_load_1d(S.seq, b.seq + a0, (uint32_t)seq_bytes, &S.bar);
-        if (ref_bytes) tma_load_1d(S.ref, ref0 + w0, ref_bytes, &S.bar);
+        if (seq_ok && seq_bytes) tma_load_1d(s_seq, b.seq + a0, (uint32_t)seq_bytes, &S.bar);
+        if (ref_bytes) tma_load_1d(s_ref, ref0 + w0, ref_bytes, &S.bar);
     }
 
     /* per-read fixed fields while the copies fly */
@@ -282,12 +283,12 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
                        lies inside the read, so nothing has to be masked; both sides are fetched at their own alignment */
                     const uint32_t o = min(sub * 16u, len - 16u);
                     if (sub * 16u < len) {
-                        const uint4 sv = k1_lds16(S.seq, soff + o), rv = k1_lds16(S.ref, S.roff[i] + o);
+                        const uint4 sv = k1_lds16(s_seq, soff + o), rv = k1_lds16(s_ref, S.roff[i] + o);
                         diff = (sv.x ^ rv.x) | (sv.y ^ rv.y) | (sv.z ^ rv.z) | (sv.w ^ rv.w);
                     }
                 } else if (ok) {                          /* window miss: straight from HBM */
                     const uint8_t *rp = g.bases + g.chr_off[b.chr[r0 + i]] + (S.pos[i] - 1u);
-                    for (uint32_t j = sub; j < len; j += 16u) diff |= (uint32_t)(S.seq[soff + j] ^ rp[j]);
+                    for (uint32_t j = sub; j < len; j += 16u) diff |= (uint32_t)(s_seq[soff + j] ^ rp[j]);
                 }
             }
             const uint32_t bal = __ballot_sync(FULL_MASK, diff != 0u);
@@ -306,7 +307,7 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
         bool bad = !seq_ok || my_pos == 0u || my_len == 0u || my_len > CBCG_MAX_READ_LEN || my_chr >= g.n_chr;
         if (!bad && !(my_cnt >> 24)) {
             EditSink sink = { nullptr, 0u, 0u, 0u, 0u, 0u, 0, S.ecache[tid] };
-            walk_read(S.seq + S.soff[tid], my_len, my_cig, my_clen, my_md, my_mlen, sink);
+            walk_read(s_seq + S.soff[tid], my_len, my_cig, my_clen, my_md, my_mlen, sink);
             if (sink.err) bad = true;
             else { my_cnt = sink.n_snps | (sink.n_dels << 8) | (sink.n_ins << 16); my_total = sink.n_snps + sink.n_dels + sink.n_ins; }
         }
@@ -351,7 +352,7 @@ k1_extract_kernel(DevBatch b, DevGenome g, cbcg_read_rec *__restrict__ recs, uin
                 }
             } else {
                 EditSink sink = { edits + off, rec.n_dels, rec.n_snps, 0u, 0u, 0u, 0, nullptr };
-                walk_read(S.seq + S.soff[tid], my_len, my_cig, my_clen, my_md, my_mlen, sink);
+                walk_read(s_seq + S.soff[tid], my_len, my_cig, my_clen, my_md, my_mlen, sink);
             }
         }
     }
@@ -367,17 +368,20 @@ int launch_extract(const DevBatch &b, const DevGenome &g, cbcg_read_rec *recs, u
     if (r_begin >= r_end) return 0;
     const uint64_t tiles = extract_num_tiles(r_end - r_begin);
     const uint32_t seq_cap = (K1_TILE * b.max_len + 48u) & ~15u;
-    const size_t smem = sizeof(K1Smem) + seq_cap + 16;
+    /* reference window: what a tile of position-adjacent reads spans at the batch's coverage, twice over (a read beyond
+       the window takes the HBM path); the smaller the window, the more tiles an SM holds */
+    const uint32_t ref_cap = b.ref_cap ? std::min<uint32_t>(std::max<uint32_t>((b.ref_cap + 511u) & ~511u, 1024u), K1_REF_CAP) : K1_REF_CAP;
+    const size_t smem = sizeof(K1Smem) + ref_cap + 64 + seq_cap + 16;
     /* per device, so no process-wide cache: a context on another GPU of the same process needs it too. The limit is the
        worst case (CBCG_MAX_READ_LEN); occupancy follows the size actually launched with. */
-    const size_t smem_max = sizeof(K1Smem) + ((K1_TILE * CBCG_MAX_READ_LEN + 48u) & ~15u) + 16;
+    const size_t smem_max = sizeof(K1Smem) + K1_REF_CAP + 64 + ((K1_TILE * CBCG_MAX_READ_LEN + 48u) & ~15u) + 16;
     if (smem > smem_max) return -1;
     if (cudaFuncSetAttribute(k1_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) return -1;
     if (cudaMemsetAsync(tile_desc, 0, tiles * sizeof(uint64_t), st) != cudaSuccess) return -1;
     if (cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st) != cudaSuccess) return -1;
     if (ev_start) cudaEventRecord(ev_start, st);
     k1_extract_kernel<<<(unsigned)tiles, K1_TILE, smem, st>>>(b, g, recs, edits, edits_cap, tile_desc, ticket,
-                                                             total_edits, err, seq_cap, r_begin, r_end, edit_base);
+                                                             total_edits, err, seq_cap, ref_cap, r_begin, r_end, edit_base);
     if (ev_stop) cudaEventRecord(ev_stop, st);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

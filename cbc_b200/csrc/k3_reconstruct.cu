@@ -14,24 +14,32 @@
  * reads need no separate scan pass.
  * Algorithmic HBM bytes per read: 16 (record) + 2*edits + 4 (chr) + L/coverage (window) + L + 1 (output).
  */
+#include <algorithm>
 #include "common.cuh"
 #include "internal.h"
 
 #define K3_TILE     128u
 #define K3_WARPS    8u
 #define K3_THREADS  (K3_WARPS * 32u)
-#define K3_REF_CAP  8192u
+#define K3_REF_CAP  8192u         /* most bytes of reference window staged per tile */
 #define K3_CHUNKS   ((K3_TILE * (CBCG_MAX_READ_LEN + 1u) + 48u) / 16u)   /* 16-byte pieces of the largest tile image */
 
 uint64_t reconstruct_num_tiles(uint64_t n_reads) { return (n_reads + K3_TILE - 1) / K3_TILE; }
 
-struct K3Warp {                       /* per-warp scratch: edit positions of the read being built */
-    uint16_t cumdel[256];             /* cumulative deletion offsets */
-    uint16_t snp_at[256];             /* aligned index of each SNP */
-    uint16_t ins_at[256];             /* output index of each inserted base */
-    uint8_t  snp_ch[256];
-    uint8_t  ins_ch[256];
+/* Scratch of a read that is built base by base: edit positions. Every warp has room for K3_EDITS_SMALL edits of a kind
+ * (nearly every read); a read with more of one kind waits for the CTA's one full-size scratch (255 of a kind, the
+ * format's limit), which warp 0 works through after the others are done: per-warp full-size scratch was 16 KB of a
+ * 49 KB CTA and cost two resident CTAs per SM. */
+#define K3_EDITS_SMALL 64u
+template <uint32_t CAP> struct K3Scratch {
+    uint16_t cumdel[CAP];             /* cumulative deletion offsets */
+    uint16_t snp_at[CAP];             /* aligned index of each SNP */
+    uint16_t ins_at[CAP];             /* output index of each inserted base */
+    uint8_t  snp_ch[CAP];
+    uint8_t  ins_ch[CAP];
 };
+typedef K3Scratch<K3_EDITS_SMALL> K3Warp;
+typedef K3Scratch<256u> K3Big;
 
 struct K3Smem {
     uint64_t bar;
@@ -45,11 +53,13 @@ struct K3Smem {
     uint32_t so[K3_TILE + 1];         /* offset of the read's first base in ref[] (reads on the copy path), else 0 */
     uint8_t  slow[K3_TILE];           /* reads built base by base (indels, reads outside the window) */
     uint8_t  is_slow[K3_TILE];
-    uint8_t  rd_of[K3_CHUNKS + 2];    /* read that owns the first byte of each 16-byte piece of the image */
+    uint8_t  big[K3_TILE];            /* reads with more than K3_EDITS_SMALL edits of a kind */
+    uint32_t n_big;
     K3Warp w[K3_WARPS];
-    __align__(16) uint8_t ref_front[32];   /* pieces at a tile's edge read up to 16 bytes before a read's first base */
-    __align__(16) uint8_t ref[K3_REF_CAP + 64];
-    __align__(16) uint8_t out[16];    /* really K3_TILE * (max_len + 1) + 48 (dynamic) */
+    K3Big wbig;
+    __align__(16) uint8_t dyn[16];    /* 32 bytes of front pad (pieces at a tile's edge read up to 16 bytes before a read's first base),
+                                         ref_cap + 64 bytes of reference window, K3_TILE * (max_len + 1) + 48 bytes of tile image,
+                                         one owner byte per 16-byte piece of the image (dynamic) */
 };
 
 /* 16 bytes of the staged window from byte offset `off` (any alignment, >= -32): two aligned 16-byte loads, the
@@ -80,13 +90,15 @@ __device__ __forceinline__ uint4 k3_merge(const uint4 a, const uint4 b, uint32_t
     return v;
 }
 
-__global__ void __launch_bounds__(K3_THREADS)
+__global__ void __launch_bounds__(K3_THREADS, 6)
 k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, const uint32_t *__restrict__ chr_of,
                       const uint16_t *__restrict__ edits, DevGenome g, uint8_t *__restrict__ out, uint64_t out_cap,
                       uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes, unsigned long long *err,
-                      uint32_t max_len, uint32_t fixed_len) {
+                      uint32_t max_len, uint32_t fixed_len, uint32_t ref_cap) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     K3Smem &S = *reinterpret_cast<K3Smem *>(smem_raw);
+    uint8_t *const s_ref = S.dyn + 32u, *const s_out = s_ref + ref_cap + 64u;
+    uint8_t *const s_own = s_out + ((K3_TILE * (max_len + 1u) + 48u + 15u) & ~15u);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     /* Tiles take their index from a ticket so that the look-back below cannot deadlock; with closed-form offsets
@@ -98,7 +110,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
         tile = S.tile;
     }
     if (tid == 0) {
-        S.n_slow = 0;
+        S.n_slow = 0; S.n_big = 0;
         mbar_init(&S.bar, 1);
         mbar_fence_init();
     }
@@ -128,7 +140,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
         const uint64_t clen0 = g.chr_len[chr0];
         w0 = pos0 ? ((uint64_t)(pos0 - 1u) & ~15ull) : 0ull;
         uint64_t avail = (clen0 + REF_PAD > w0) ? ((clen0 + REF_PAD - w0) & ~15ull) : 0ull;
-        ref_bytes = (uint32_t)min((uint64_t)K3_REF_CAP, avail);
+        ref_bytes = (uint32_t)min((uint64_t)ref_cap, avail);
         /* position-sorted input: the tile's last read bounds the window (a read beyond it misses the window and is
            built from HBM) */
         const uint32_t pos_l = S.rec[nr - 1u].pos;
@@ -139,7 +151,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
     }
     if (tid == 0) {
         mbar_expect_tx(&S.bar, ref_bytes);
-        if (ref_bytes) tma_load_1d(S.ref, g.bases + g.chr_off[chr0] + w0, ref_bytes, &S.bar);
+        if (ref_bytes) tma_load_1d(s_ref, g.bases + g.chr_off[chr0] + w0, ref_bytes, &S.bar);
     }
 
     /* Which reads are plain copies of the window, possibly with a few substituted bases? (perfect matches :383-384
@@ -193,13 +205,13 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
     const uint64_t tile_base = fixed_len ? r0 * (uint64_t)(fixed_len + 1u) : S.tile_base;
     /* smem image is shifted so that smem offset == global offset (mod 16): the middle can leave by TMA */
     const uint32_t shift = (uint32_t)((uint64_t)(out + tile_base) & 15ull);
-    uint8_t *img = S.out + shift;
+    uint8_t *img = s_out + shift;
     const uint32_t n_chunks = (shift + tile_total + 15u) >> 4;
     /* owner of the first byte of every 16-byte piece: read i owns the pieces that start inside its line */
     if (tid < nr) {
         const uint32_t c_lo = (tid == 0u) ? 0u : ((shift + my_off + 15u) >> 4);
         const uint32_t c_hi = (shift + my_off + my_bytes + 15u) >> 4;       /* first piece of the next read */
-        for (uint32_t c = c_lo; c < c_hi && c < n_chunks; c++) S.rd_of[c] = (uint8_t)tid;
+        for (uint32_t c = c_lo; c < c_hi && c < n_chunks; c++) s_own[c] = (uint8_t)tid;
     }
     __syncthreads();
     mbar_wait(&S.bar, 0);
@@ -209,12 +221,12 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
        bytes that their own builder overwrites below. */
     if (!tile_short && ref_bytes) {
         for (uint32_t c = tid; c < n_chunks; c += K3_THREADS) {
-            const uint32_t i = S.rd_of[c];
+            const uint32_t i = s_own[c];
             const int32_t j0 = (int32_t)(16u * c) - (int32_t)(shift + S.out_off[i]);   /* read-relative index of the piece's first byte */
             const int32_t rem = (int32_t)S.rec[i].len - j0;                             /* bases of read i from there on */
-            uint4 v = lds_16_unaligned(S.ref, (int32_t)S.so[i] + j0);
-            if (rem < 16) v = k3_merge(v, lds_16_unaligned(S.ref, (int32_t)S.so[i + 1u] - rem - 1), (uint32_t)rem);   /* rem >= 0: the piece starts inside line i */
-            *reinterpret_cast<uint4 *>(S.out + 16u * c) = v;
+            uint4 v = lds_16_unaligned(s_ref, (int32_t)S.so[i] + j0);
+            if (rem < 16) v = k3_merge(v, lds_16_unaligned(s_ref, (int32_t)S.so[i + 1u] - rem - 1), (uint32_t)rem);   /* rem >= 0: the piece starts inside line i */
+            *reinterpret_cast<uint4 *>(s_out + 16u * c) = v;
         }
     }
     __syncthreads();
@@ -238,10 +250,16 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
         if (bad) { dev_set_error(err, CBCG_ERR_CORRUPT, r0 + tid); for (uint32_t j = 0; j < len; j++) dst[j] = 'N'; }
     }
 
-    K3Warp &W = S.w[warp];
-    const uint32_t n_slow = S.n_slow;
-    for (uint32_t sidx = warp; sidx < n_slow; sidx += K3_WARPS) {
-        const uint32_t i = S.slow[sidx];
+    /* reads built base by base, a warp each: first pass with the warps' own scratch, second pass (warp 0) for the reads
+       that need the full-size one. One copy of the builder: the scratch is reached through pointers. */
+    struct { uint16_t *cumdel, *snp_at, *ins_at; uint8_t *snp_ch, *ins_ch; } W;
+    for (uint32_t pass = 0; pass < 2u; pass++) {
+    if (pass) { if (!__syncthreads_or(S.n_big != 0u)) break; }               /* CTA-uniform: n_big is final after the barrier */
+    const uint32_t n_list = pass ? S.n_big : S.n_slow, cap = pass ? 256u : K3_EDITS_SMALL;
+    if (pass) { W.cumdel = S.wbig.cumdel; W.snp_at = S.wbig.snp_at; W.ins_at = S.wbig.ins_at; W.snp_ch = S.wbig.snp_ch; W.ins_ch = S.wbig.ins_ch; }
+    else { K3Warp &w = S.w[warp]; W.cumdel = w.cumdel; W.snp_at = w.snp_at; W.ins_at = w.ins_at; W.snp_ch = w.snp_ch; W.ins_ch = w.ins_ch; }
+    for (uint32_t sidx = pass ? (warp ? n_list : 0u) : warp; sidx < n_list; sidx += pass ? 1u : K3_WARPS) {
+        const uint32_t i = pass ? S.big[sidx] : S.slow[sidx];
         const cbcg_read_rec &rec = S.rec[i];
         const uint32_t len = rec.len, pos = rec.pos, chr = S.chr[i];
         uint8_t *dst = img + S.out_off[i];
@@ -263,7 +281,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
         }
         const bool in_win = (chr == chr0) && ref_bytes && (uint64_t)(pos - 1u) >= w0 &&
                             ((uint64_t)(pos - 1u) - w0 + aligned + nd <= ref_bytes);
-        const uint8_t *src = in_win ? (S.ref + (uint32_t)((uint64_t)(pos - 1u) - w0)) : (gref + (pos - 1u));
+        const uint8_t *src = in_win ? (s_ref + (uint32_t)((uint64_t)(pos - 1u) - w0)) : (gref + (pos - 1u));
 
         if ((nd | ns | ni) == 0u) {                         /* perfect match or no edits: straight copy */
             for (uint32_t j = lane; j < len; j += 32u) dst[j] = src[j];
@@ -289,6 +307,10 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
                 for (uint32_t j = lane; j < len; j += 32u) dst[j] = 'N';
             }
             __syncwarp();
+            continue;
+        }
+        if (max(nd, max(ns, ni)) > cap) {                   /* waits for the CTA's full-size scratch */
+            if (lane == 0) S.big[atomicAdd(&S.n_big, 1u)] = (uint8_t)i;
             continue;
         }
         /* edit positions: prefix sums of the deltas (lists are short; 32 entries per step) */
@@ -349,6 +371,7 @@ k3_reconstruct_kernel(uint64_t n_reads, const cbcg_read_rec *__restrict__ recs, 
         if (lane == 0) dst[len] = '\n';
         __syncwarp();
     }
+    }
     fence_proxy_async_smem();          /* generic-proxy smem writes -> visible to the bulk store */
     __syncthreads();
 
@@ -371,12 +394,15 @@ void reconstruct_set_carveout(int pct) { cudaFuncSetAttribute(k3_reconstruct_ker
 int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32_t *chr, const uint16_t *edits,
                        const DevGenome &g, uint8_t *out, uint64_t out_cap, uint32_t max_len, uint32_t fixed_len,
                        uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
-                       unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop) {
+                       unsigned long long *err, cudaStream_t st, cudaEvent_t ev_start, cudaEvent_t ev_stop, uint32_t ref_cap_hint) {
     if (n_reads == 0) return 0;
     const uint64_t tiles = reconstruct_num_tiles(n_reads);
-    const size_t smem = sizeof(K3Smem) + (size_t)K3_TILE * (max_len + 1u) + 80;
+    /* reference window: what a tile spans at the input's coverage (the caller's estimate), twice over; 0: the largest */
+    const uint32_t ref_cap = ref_cap_hint ? std::min<uint32_t>(std::max<uint32_t>((ref_cap_hint + 511u) & ~511u, 1024u), K3_REF_CAP) : K3_REF_CAP;
+    const auto smem_for = [](uint32_t rc, uint32_t ml) { const size_t img = ((size_t)K3_TILE * (ml + 1u) + 48u + 15u) & ~(size_t)15u; return sizeof(K3Smem) + 32 + rc + 64 + img + (img >> 4) + 32; };
+    const size_t smem = smem_for(ref_cap, max_len);
     /* per device, so no process-wide cache (see launch_extract) */
-    const size_t smem_max = sizeof(K3Smem) + (size_t)K3_TILE * (CBCG_MAX_READ_LEN + 1u) + 80;
+    const size_t smem_max = smem_for(K3_REF_CAP, CBCG_MAX_READ_LEN);
     if (smem > smem_max) return -1;
     if (cudaFuncSetAttribute(k3_reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess) return -1;
     if (!fixed_len) {                                       /* closed-form offsets use neither the ticket nor the descriptors */
@@ -385,7 +411,7 @@ int launch_reconstruct(uint64_t n_reads, const cbcg_read_rec *recs, const uint32
     }
     if (ev_start) cudaEventRecord(ev_start, st);
     k3_reconstruct_kernel<<<(unsigned)tiles, K3_THREADS, smem, st>>>(n_reads, recs, chr, edits, g, out, out_cap,
-                                                                    tile_desc, ticket, total_bytes, err, max_len, fixed_len);
+                                                                    tile_desc, ticket, total_bytes, err, max_len, fixed_len, ref_cap);
     if (ev_stop) cudaEventRecord(ev_stop, st);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
