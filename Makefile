@@ -6,7 +6,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -O3 -std=c++17 -lineinfo --extended-lambda $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall -Iinclude -Icbc_b200/csrc
 BUILD     := cbc_b200/_build
 CU_SRC    := $(wildcard cbc_b200/csrc/*.cu)
-CU_HDR    := $(wildcard cbc_b200/csrc/*.cuh) $(wildcard include/*.h)
+CU_HDR    := $(wildcard cbc_b200/csrc/*.cuh) $(wildcard cbc_b200/csrc/*.h) $(wildcard include/*.h)
 HOST_SRC  := cbc_b200/csrc/host/sam_ingest.c
 HOST_HDR  := $(wildcard cbc_b200/csrc/host/*.h) $(wildcard include/*.h)
 

@@ -24,7 +24,9 @@
 #define K2_THREADS  (K2_WARPS * 32u)
 #define LIKELY(c)   __builtin_expect(!!(c), 1)
 #define UNLIKELY(c) __builtin_expect(!!(c), 0)
-#define FLAG_CAP    128u
+#ifndef FLAG_CAP
+#define FLAG_CAP    256u              /* distinct FLAG values a block / a snapshot may hold (the sparse table's size; 128 -> 256 measured time-neutral) */
+#endif
 #define PA_STRIDE   260u              /* words per 256-symbol model row: 256 counts, n, padding to 16 bytes */
 #define VAR_DIRECT_MIN_EDITS 32768u       /* blocks with more edits index var rows directly by context */
 #define VAR_DEFERRED 0x80000000u           /* hash value: row not built yet, low 16 bits = the one symbol coded in it */

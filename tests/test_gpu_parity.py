@@ -354,3 +354,42 @@ def test_cigar_operations_beyond_midS_on_the_gpu(codec):
     with pytest.raises(CbcgError) as e:
         codec.extract(bad)
     assert e.value.status == -6
+
+
+def _with_flags(b, n_distinct, seed):
+    """The batch with its FLAG column replaced by n_distinct values (strand bit included), position order untouched."""
+    rng = np.random.default_rng(seed)
+    values = rng.choice(4096, size=n_distinct, replace=False).astype(np.uint16)
+    flag = values[rng.integers(0, n_distinct, size=b.n_reads)]
+    flag[:n_distinct] = values                                   # every value occurs
+    return Batch(b.pos, np.ascontiguousarray(flag), b.seq_len, b.chr, b.seq_off, b.seq, b.cigar_off, b.cigar, b.md_off, b.md)
+
+
+@pytest.mark.gpu
+def test_two_hundred_distinct_flags(codec):
+    """The sparse FLAG table holds 256 touched values per block and per snapshot (the reference's model has all 65 536:
+    src/sam_models.c:96-130). 200 distinct values in one block and in the merged snapshots: single-block stream, cold and
+    generation-primed containers equal the restatement's, and decode back; the warp-per-chain encoder's table leaves its
+    registers for shared memory at the 33rd value."""
+    g, b0 = _synth(seed=31, genome_len=200_000, n_reads=30_000, len_min=100, len_max=100, p_sub=0.01, p_indel=0.0)
+    b = _with_flags(b0, 200, 7)
+    codec.set_reference(g)
+    stream = codec.compress(b, 100, block_reads=0)
+    ostream, _ = O.encode_legacy(b, g, 100)
+    assert stream == ostream
+    for gen_mode, block_reads in ((0, 30_000), (1, 4_000), (1, 512)):
+        c = codec.compress(b, 100, block_reads=block_reads, gen_mode=gen_mode, substreams=1)
+        assert c == O.encode_blocked(b, g, 100, block_reads, gen_mode)
+        text, n = codec.decompress(c)
+        assert n == b.n_reads and text == b.seq_lines()
+
+
+@pytest.mark.gpu
+def test_more_distinct_flags_than_the_table_holds_is_an_error(codec):
+    """Beyond 256 distinct FLAG values in a block the encoder reports CBCG_ERR_LIMIT (-12) instead of coding wrongly."""
+    from cbc_b200.codec import CbcgError
+    g, b0 = _synth(seed=32, genome_len=100_000, n_reads=8_000, len_min=100, len_max=100, p_sub=0.01, p_indel=0.0)
+    b = _with_flags(b0, 300, 8)
+    codec.set_reference(g)
+    with pytest.raises(CbcgError):
+        codec.compress(b, 100, block_reads=8_000, gen_mode=0, substreams=1)
