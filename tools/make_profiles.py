@@ -1,14 +1,37 @@
-"""Turn the ncu outputs in gpurun_out/ into the committed summaries under profiles/ (round tag r01)."""
+"""Turn the outputs of tools/profile_round.sh (gpurun_out/<tag>_*) into the committed summaries under profiles/:
+bench lines per named config, the reference arm's line, the ncu launch list with per-kernel shares, ncu --set full
+summaries of the hot kernels, DRAM traffic per launch (traffic.json, read by bench.py) and the block coder's
+instructions per symbol (k2_issue.json, read by bench.py).   usage: make_profiles.py [tag=r02f] [round=r02]"""
 import csv, io, json, os, shutil, subprocess, sys
 from collections import defaultdict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
-shutil.copy(os.path.join(G, "r01_launches_final.csv"), os.path.join(P, "r01_launches.csv"))
-bench = json.load(open(os.path.join(P, "r01_bench_n1.json")))
-out = ["# Round 1: ncu summaries of the final build (B200, config 2: 3 014 484 reads x 150 bp, automatic block size, primed blocks)", "",
-       "Command profiled: `python bench.py --steps 1 --warmup 1 --no-cpu`, each ncu pass run only after the same command had exited 0 without ncu.", "",
-       "## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, profiles/r01_launches.csv; cold-cache, serialised)", ""]
-rows = [r for r in csv.reader(open(os.path.join(G, "r01_launches_final.csv"))) if len(r) > 10 and r[0].isdigit()]
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02f"
+rnd = sys.argv[2] if len(sys.argv) > 2 else "r02"
+
+def first_json(path):
+    for line in open(path):
+        if line.startswith("{"):
+            return json.loads(line)
+
+for c in (1, 2, 3, 5):
+    src = os.path.join(G, f"{tag}_bench_config{c}.json")
+    if os.path.exists(src):
+        shutil.copy(src, os.path.join(P, f"{rnd}_bench_config{c}.json"))
+shutil.copy(os.path.join(G, f"{tag}_bench_reference.json"), os.path.join(P, f"{rnd}_bench_reference_arm.json"))
+shutil.copy(os.path.join(G, f"{tag}_launches.csv"), os.path.join(P, f"{rnd}_launches.csv"))
+shutil.copy(os.path.join(G, f"{tag}_k2_launches.csv"), os.path.join(P, f"{rnd}_k2_launches.csv"))
+bench = first_json(os.path.join(P, f"{rnd}_bench_config2.json"))
+n_sym = bench["symbols_per_s_encode"] * bench["stage_ms"]["k2e"] * 1e-3
+subprocess.run([sys.executable, os.path.join(ROOT, "tools", "k2_issue.py"), os.path.join("profiles", f"{rnd}_k2_launches.csv"), str(round(n_sym)),
+                os.path.join("profiles", "k2_issue.json")], cwd=ROOT, check=True, stdout=subprocess.DEVNULL)
+
+out = [f"# Round 2: ncu summaries of the final build (B200, config 2: 3 014 484 reads x 150 bp, automatic block size, default layout)", "",
+       "Commands profiled: `python bench.py --config 2 --steps 1 --warmup 1 --no-cpu` (launch list) and `python tools/sweep_blocks.py 1 auto 1`",
+       "(one resident encode + decode per pass, one stream per block in every generation; per-kernel figures and the full captures); every",
+       "ncu pass ran only after the same command had exited 0 without ncu (tools/profile_round.sh).", "",
+       f"## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, profiles/{rnd}_launches.csv; cold-cache, serialised)", ""]
+rows = [r for r in csv.reader(open(os.path.join(P, f"{rnd}_launches.csv"))) if len(r) > 10 and r[0].isdigit()]
 agg = defaultdict(lambda: [0, 0.0])
 for r in rows:
     k = r[4].split("(")[0].replace("void ", ""); agg[k][0] += 1; agg[k][1] += float(r[-1])
@@ -16,17 +39,25 @@ tot = sum(v[1] for v in agg.values())
 out += ["| kernel | launches | total ms | share |", "|---|---|---|---|"]
 out += [f"| {k} | {v[0]} | {v[1] / 1e6:.3f} | {100 * v[1] / tot:.1f}% |" for k, v in sorted(agg.items(), key=lambda x: -x[1][1])]
 sm = bench["stage_ms"]
-k2 = sm["k2e"] + sm["k2d"]
-out += ["", f"bench.py's CUDA-event stage times for the same build (profiles/r01_bench_n1.json): K2 encode {sm['k2e']:.2f} ms, K2 decode {sm['k2d']:.2f} ms, "
+coder = sum(v[1] for k, v in agg.items() if "k2_" in k or "merge" in k or "snapshot" in k)
+out += ["", f"bench.py's CUDA-event stage times for the same build (profiles/{rnd}_bench_config2.json): K2 encode {sm['k2e']:.2f} ms, K2 decode {sm['k2d']:.2f} ms, "
         f"K1 {sm['k1']:.2f} ms, K3 {sm['k3']:.2f} ms of a {bench['ms_per_step']:.1f} ms step: the block coder (with its generation merges) is "
-        f"{100 * k2 / bench['ms_per_step']:.0f} % of the step there and {100 * sum(v[1] for k, v in agg.items() if 'k2_' in k or 'merge' in k or 'snapshot' in k) / tot:.0f} % of the ncu launch list.", ""]
+        f"{100 * (sm['k2e'] + sm['k2d']) / bench['ms_per_step']:.0f} % of the step there and {100 * coder / tot:.0f} % of the ncu launch list "
+        "(which also holds the K1-alone encodes and the pipelined host-buffer steps of the bench command).", ""]
+ki = json.load(open(os.path.join(P, "k2_issue.json")))
+out += [f"## Block coder per pass (profiles/{rnd}_k2_launches.csv -> profiles/k2_issue.json)", "",
+        "| direction | warp instructions per symbol | issue-slot utilisation (time-weighted) | launches | ncu ms |", "|---|---|---|---|---|"]
+out += [f"| {d} | {ki[d]['warp_inst_per_symbol']} | {ki[d]['issue_active_pct']} % | {ki[d]['launches_per_pass']:.0f} | {ki[d]['ncu_ms_per_pass']} |" for d in ("encode", "decode")]
+out += ["", "| kernel (per pass) | ms | M warp instructions |", "|---|---|---|"]
+out += [f"| {k} | {v['ms']} | {v['warp_inst_M']} |" for k, v in ki["kernels"].items()]
+out += [""]
 traffic = {}
 def val(r, idx, units, m):
     return float(r[idx[m]]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[idx[m]]]
-for f, names in (("r01c_k1k3", {"k1_extract": "k1_extract_kernel", "k3_reconstruct": "k3_reconstruct_kernel"}),
-                 ("r01c_k2e", {"k2_coder": "k2_coder_kernel<encode>"}), ("r01c_k2d", {"k2_coder": "k2_coder_kernel<decode>"})):
+for f, names in ((f"{tag}_k1k3", {"k1_extract": "k1_extract_kernel", "k3_reconstruct": "k3_reconstruct_kernel"}),
+                 (f"{tag}_k2enc", {"k2_model": "k2_model_kernel", "k2_code": "k2_code_kernel"}), (f"{tag}_k2dec", {"k2_coder": "k2_coder_kernel<decode>"})):
     rep = os.path.join(G, f + ".ncu-rep")
-    out += [f"## `ncu --set full --clock-control none`: gpurun_out/{f}.ncu-rep", "```"]
+    out += [f"## `ncu --set full --clock-control none --import-source on`: gpurun_out/{f}.ncu-rep", "```"]
     out += subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout.rstrip().split("\n")
     out += ["```", ""]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -35,18 +66,12 @@ for f, names in (("r01c_k1k3", {"k1_extract": "k1_extract_kernel", "k3_reconstru
         for pat, key in names.items():
             if pat in r[idx["Kernel Name"]] and key not in traffic:
                 traffic[key] = int(val(r, idx, units, "dram__bytes_read.sum") + val(r, idx, units, "dram__bytes_write.sum"))
-traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, config 2; the K2 entries are the "
-                    "last-generation launch (2959 of 5007 blocks, 92 % of the reads)")
+traffic["k2 block coder (encode)"] = traffic.get("k2_model_kernel", 0) + traffic.get("k2_code_kernel", 0)
+traffic["k2 block coder (decode)"] = traffic.get("k2_coder_kernel<decode>", 0)
+traffic["_reads_per_launch"] = 3014484
+traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, config 2; K1: the launch over the tail of the batch "
+                    "(2 789 k of the 3 014 k reads); the block coder entries are the last generation's launches (2 958 blocks, 92 % of the reads): "
+                    "model kernel + interval kernel for encode")
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
-out += ["The launch list is of the whole bench command: the device-resident steps (5 coder launches per direction: generations 0-4; K1 in two",
-        "launches, the reads of the early generations first, the rest of the batch on a side stream beside them), three one-stream encodes that",
-        "time K1 alone for its roofline entry, and the pipelined host-buffer steps (cbcg_encode / cbcg_decode: one K1 launch per chunk, one coder",
-        "and one K3 launch per group).", "",
-        "Reading: K2 (`k2_coder_kernel<mode, legacy>`) is serial integer work per block: 20 warps per SM (96 registers, no spills), 56 % of issue",
-        "slots, 20 % + 11 % of stall samples waiting for instruction fetch (95 KB of SASS against a 32 KB L1.5 instruction cache); DRAM < 2 % of peak.",
-        "Its DRAM traffic fell from 1.14 GB to 0.49 GB per last-generation launch with deferred var rows (rows touched once are coded from",
-        "the snapshot and never copied). K3 runs at 30 % of the measured HBM peak and is bound by instruction issue (60 % of slots, 58 warp",
-        "instructions per read); K1 at 19 %, with a fifth of its stall samples at the barrier behind the look-back over tile edit counts",
-        "(the wait for every earlier in-flight tile to have counted its edits) and 97 warp instructions per read."]
-open(os.path.join(P, "r01_ncu_summary.md"), "w").write("\n".join(out) + "\n")
-print(traffic)
+open(os.path.join(P, f"{rnd}_ncu_summary.md"), "w").write("\n".join(out) + "\n")
+print(json.dumps(traffic, indent=1))

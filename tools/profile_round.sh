@@ -18,9 +18,9 @@ ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.
     --clock-control none -k regex:"k2_model|k2_code|k2_coder|k2_block" -c 48 --csv --log-file gpurun_out/${tag}_k2_launches.csv \
     python tools/sweep_blocks.py 1 auto 1 > gpurun_out/${tag}_ncu_k2l.log 2>&1; echo "k2 list rc=$?"
 # full captures (one launch each, the last generation's): model kernel, interval kernel, decoder, K1 (tail launch), K3
-ncu --set full --import-source on --clock-control none -k regex:"k2_model|k2_code" -s 2 -c 2 -o gpurun_out/${tag}_k2enc -f \
+ncu --set full --import-source on --clock-control none -k regex:"k2_model|k2_code" -s 8 -c 2 -o gpurun_out/${tag}_k2enc -f \
     python tools/sweep_blocks.py 1 auto 1 > gpurun_out/${tag}_ncu_k2enc.log 2>&1; echo "k2enc rc=$?"
-ncu --set full --import-source on --clock-control none -k regex:"k2_coder" -s 1 -c 1 -o gpurun_out/${tag}_k2dec -f \
+ncu --set full --import-source on --clock-control none -k regex:"k2_coder" -s 4 -c 1 -o gpurun_out/${tag}_k2dec -f \
     python tools/sweep_blocks.py 1 auto 1 > gpurun_out/${tag}_ncu_k2dec.log 2>&1; echo "k2dec rc=$?"
 ncu --set full --import-source on --clock-control none -k regex:"k1_extract|k3_reconstruct" -s 1 -c 2 -o gpurun_out/${tag}_k1k3 -f \
     python tools/sweep_blocks.py 1 auto 1 > gpurun_out/${tag}_ncu_k1k3.log 2>&1; echo "k1k3 rc=$?"
