@@ -90,6 +90,7 @@ struct cbcg_ctx {
     bool have_encoded = false;
     uint32_t enc_L = 0, enc_block_reads = 0, enc_gen_mode = 0, enc_legacy = 0, enc_max_len = 0, enc_fixed = 0, enc_layout_mode = 0;
     uint32_t batch_min_len = 0;               /* shortest read of the resident batch (host scan at upload) */
+    bool batch_indel_heavy = false;           /* CIGAR text per read well beyond "<len>M": most reads carry indels / clips (picks the model kernel's edit walk) */
     uint64_t enc_n_reads = 0, enc_n_edits = 0, enc_n_blocks = 0, enc_payload_bytes = 0;
     std::vector<uint8_t> enc_head;             /* container header + index */
 
@@ -382,6 +383,7 @@ static int batch_scan(cbcg_ctx *ctx, const cbcg_batch *b) {
     }
     ctx->db.max_len = max_len;
     ctx->db.ref_cap = ref_window_estimate(ctx, b->pos, n, max_len);
+    ctx->batch_indel_heavy = n && (b->cigar_off[n] - b->cigar_off[0]) > n * 6ull;      /* "150M" is 4 bytes, "60M1I39M" 8 */
     ctx->batch_min_len = n ? min_len : 0;
     ctx->total_bases = n ? b->seq_off[n] - b->seq_off[0] : 0;
     if (n && (min_len == 0 || max_len > CBCG_MAX_READ_LEN))
@@ -448,6 +450,7 @@ static int compact_buffers(cbcg_ctx *ctx, const cbcg_batch_compact *b) {
     ctx->db.md_off = ctx->b_moff.as<uint64_t>(); ctx->db.md = ctx->b_md.as<uint8_t>();
     ctx->db.max_len = n ? b->max_len : 0; ctx->batch_min_len = n ? b->min_len : 0; ctx->total_bases = seq_b;
     ctx->db.ref_cap = ref_window_estimate(ctx, b->pos, n, ctx->db.max_len);
+    ctx->batch_indel_heavy = n && b->tile_base[((n + 127) / 128) * 4 + 2] > n * 6ull;     /* CIGAR bytes of the whole batch */
     return 0;
 }
 /* the small pieces every chunk needs: tile offsets, chromosome runs, the exception list (first on the link) */
@@ -744,7 +747,7 @@ static int run_coder_generations(cbcg_ctx *ctx, CoderParams p, uint64_t nb, bool
     TRY(run_early_generations(ctx, p, &cur));
     p.block_begin = ctx->gens.back().first; p.n_blocks = ctx->gens.back().second;
     p.n_sub = gen_n_sub(ctx, p.block_begin);
-    p.snap = cur;
+    p.snap = cur; p.no_merge = 1u;                          /* the last generation: nobody merges its blocks */
     if (launch_coder(p, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     ctx->stats.kernel_launches += coder_launches(p);
     return 0;
@@ -764,6 +767,7 @@ static CoderParams coder_params(cbcg_ctx *ctx, uint32_t n_blocks, uint32_t L, in
     p.fin = ctx->fin.as<uint8_t>();                         /* callers ensure_fin(nb) before a blocked launch */
     p.layout_mode = legacy ? 0u : ctx->layout_mode;
     p.n_sub = 1u;                                           /* per launch: gen_n_sub() */
+    p.indel_heavy = ctx->batch_indel_heavy ? 1u : 0u;
     return p;
 }
 
@@ -878,7 +882,7 @@ static int encode_resident_overlapped(cbcg_ctx *ctx, const cbcg_encode_opts *opt
     CU(cudaEventRecord(ctx->dev2[1], side));
     CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[1], 0));
     CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[2], 0));
-    q.snap = snap; q.n_sub = gen_n_sub(ctx, q.block_begin);
+    q.snap = snap; q.n_sub = gen_n_sub(ctx, q.block_begin); q.no_merge = 1u;
     if (launch_coder(q, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaEventRecord(ctx->ev[3], ctx->st));
     if (launch_gather(p.blocks, (uint32_t)nb, ctx->scratch.as<uint8_t>(), ctx->payload.as<uint8_t>(), ctx->out_off.as<uint64_t>(), 1, ctx->layout_mode, ctx->st))
@@ -1244,7 +1248,7 @@ static int encode_pipelined(cbcg_ctx *ctx, const BatchSrc &src, const cbcg_encod
             CU(cudaEventRecord(ctx->kev2[c], ctx->st));
             cudaStream_t sd = ctx->ps[c % PIPE_MAX];
             CU(cudaStreamWaitEvent(sd, ctx->kev2[c], 0));
-            q.snap = snap; q.n_sub = gen_n_sub(ctx, q.block_begin);
+            q.snap = snap; q.n_sub = gen_n_sub(ctx, q.block_begin); q.no_merge = 1u;
             if (launch_coder(q, sd)) return fail(ctx, CBCG_ERR_CUDA, "K2 launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             S.kernel_launches += coder_launches(q);
             CU(cudaEventRecord(ctx->dev2[c], sd));

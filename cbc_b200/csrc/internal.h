@@ -75,6 +75,9 @@ struct CoderParams {
     uint32_t short_flush;                  /* blocked containers: 1 + scale3 closing bits instead of the reference's 26+ */
     uint32_t primed;                       /* gen_mode 1: models start from `snap` instead of the initial state */
     uint32_t fixed_len;                    /* CBCG_MODE_FIXED_LEN: every read is L bases, the length symbol is not coded */
+    uint32_t no_merge;                     /* the blocks of this launch are not merged into a snapshot afterwards (the last generation): their final
+                                              model states are not needed */
+    uint32_t indel_heavy;                  /* host estimate: the batch's CIGAR text per read says most reads carry indels / clips */
     uint32_t n_sub;                        /* blocked containers: substreams of the blocks of THIS launch (one generation): 1 or CBCG_N_SUB */
     uint32_t layout_mode;                  /* the container's layout bits (CBCG_MODE_SPLIT4, split generations): CBCG_BLOCK_NSUB(layout_mode, gen) per block */
     const uint8_t *snap;                   /* snapshot S_{g-1} (snapshot_bytes(L) bytes); blocked containers always start from one */

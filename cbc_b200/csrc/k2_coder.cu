@@ -1572,6 +1572,9 @@ __device__ __forceinline__ uint32_t k2m_slots(uint32_t cw, uint32_t lead) {     
     const uint32_t match = cw & 0xffu, ns = (cw >> 8) & 0xffu, nd = (cw >> 16) & 0xffu, ni = cw >> 24;
     return lead + 3u + (match ? 0u : 1u + ((nd | ni) ? 3u : 0u) + nd + 2u * ns + 2u * ni);
 }
+/* GROUPED: the edit positions of an unmerged generation by context (below); its own instantiation, so that the serial walk
+   of the other keeps its registers (the two together spill into the serial loop: config 5 +5 %). */
+template <bool GROUPED>
 __global__ void __launch_bounds__(K2_THREADS, K2M_MIN_CTAS)
 k2_model_kernel(CoderParams P, uint32_t role_mask) {
     __shared__ __align__(16) WarpShared sh[K2_WARPS];
@@ -1747,12 +1750,158 @@ k2_model_kernel(CoderParams P, uint32_t role_mask) {
             slot += k2m_slots(v.w, lead);
             v = nx;
         }
+    } else if (GROUPED && 8ull * n_reads + 2ull * B.n_edits + 8ull < (1ull << 24)) {     /* slot indices are packed in 24 bits below */
+        /* ---- edit positions and bases of a generation that nobody merges (the last one: 92 % of the reads), WITHOUT the
+           serial walk through the var rows. A var context's model is touched by a handful of symbols per block and is
+           independent of every other context's; what orders the symbols is only the SNP-site ring (input alone) and the
+           earlier symbols of the SAME context. So:
+             A. one sequential pass over the reads forms every position symbol's context (ring_first / ring_set as in
+                compute_delta_to_first_snp :703-718), lists (context, symbol, slot) and codes the bases through chars
+                (shared memory, cheap) on the way;
+             B. the list is linked by context, 32 symbols a step: each symbol learns the previous symbol of its context
+                (warp match for the ones in the same step, a hash of last occurrences for the earlier ones);
+             C. a LANE per symbol: cumulative count and count from the snapshot's row (read only; all-ones for a context
+                the snapshot lacks), plus 10 for every earlier symbol of the context below / at the symbol (update_model's
+                step) -- no row is copied, no row is written, no symbol waits for another context's.
+           A context whose total would reach the rescale threshold inside the block sends the block through the serial
+           walk below instead (never seen on the named shapes: totals start far from 2^20). */
+        /* Step C walks back over the earlier symbols of a symbol's context: fine for the handful a context sees in a
+           block, quadratic for a context that thousands of symbols share -- the first deletion / insertion of a read has
+           context (0, strand) whatever the read. Indel-heavy blocks take the serial walk (config 5: measured twice as slow
+           here), and so does any block in which a context turns out to be shared by more than K2M_CTX_MAX symbols. */
+#define K2M_INDEL_MAX 1024u
+#define K2M_CTX_MAX   1023u
+        {
+            uint32_t indels = 0;
+            for (uint32_t q = lane; q < n_reads; q += 32u) { const uint32_t cw = recs[q].w; if (!(cw & 0xffu)) indels += ((cw >> 16) & 0xffu) + (cw >> 24); }
+            if (warp_sum(indels) > K2M_INDEL_MAX) goto edits_serial;
+        }
+        k2b_copy(&S.chars[0][0], &SM->chars[0][0], 48u, lane);
+        for (uint32_t q = lane; q <= C.hash_mask; q += 32u) C.var_hash[q] = 0ull;
+        __syncwarp();
+        C.ring_reset();
+        uint32_t *it_ctx = C.var_rows();                                    /* the rows' room in the workspace: 4 words per symbol of <= n_edits */
+        uint32_t *it_xs = it_ctx + B.n_edits, *it_prev = it_xs + B.n_edits, *it_ord = it_prev + B.n_edits;
+        uint32_t K = 0, max_ord = 0;
+        uint4 v = n_reads ? recs[0] : make_uint4(0u, 0u, 0u, 0u);
+        for (; i < n_reads; i++) {                                          /* ---- A */
+            const uint4 nx = (i + 1u < n_reads) ? recs[i + 1u] : v;
+            const uint32_t pos = v.x, flag = v.y & 0xffffu, len = v.y >> 16, match = v.w & 0xffu;
+            const uint32_t ns = (v.w >> 8) & 0xffu, nd = (v.w >> 16) & 0xffu, ni = v.w >> 24;
+            if (pos == 0u) K2M_FAIL(CBCG_ERR_INPUT);
+            if (!(nx.w & 0xffu)) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.edits + nx.z));
+            const uint32_t strand = (flag >> 4) & 1u;                      /* :57-60 */
+            C.ring_advance(pos);
+            if (!match) {
+                const uint16_t *e_in = P.edits + v.z;
+                uint32_t at = slot + lead + 4u + ((nd | ni) ? 3u : 0u);     /* slot index of the read's first edit symbol */
+                if (K + nd + ns + ni > B.n_edits) K2M_FAIL(CBCG_ERR_INTERNAL);
+#define K2M_ITEM(CTX, X) do { const uint32_t c_ = (CTX), x_ = (X); \
+                    if (c_ >= CBCG_VAR_CONTEXTS || x_ >= L) K2M_FAIL(CBCG_ERR_INPUT); \
+                    if (lane == 0) { it_ctx[K] = c_; it_xs[K] = (at << 8) | x_; } K++; at++; } while (0)
+                uint32_t prev = 0;
+                for (uint32_t k = 0; k < nd; k++) {                         /* deletions (:568-572) */
+                    const uint32_t d = CBCG_EDIT_DELTA((uint32_t)e_in[k]);
+                    K2M_ITEM((prev << 1) | strand, d);
+                    prev += d;
+                }
+                prev = 0;
+                for (uint32_t k = 0; k < ns; k++) {                         /* SNPs (:573-593) */
+                    const uint32_t ed = e_in[nd + k];
+                    const uint32_t delta = C.ring_first(pos - 1u + prev, (prev < len) ? pos - 1u + len : pos - 1u + prev, len + 2u);
+                    const uint32_t p = CBCG_EDIT_DELTA(ed);
+                    K2M_ITEM((((delta << CBCG_BITS_DELTA) + prev) << 1) | strand, p);
+                    prev += p + 1u;
+                    C.ring_set(pos + prev - 2u);                            /* :589 */
+                    const uint32_t refb = CBCG_EDIT_REFB(ed);
+                    if (refb > 5u) K2M_FAIL(CBCG_ERR_INPUT);
+                    C.tri_at = slots + at; at++;
+                    C.template sym_dense<5, false>(S.chars[refb], 5u, 8u, CBCG_EDIT_TARGET(ed), false, 0u);
+                    if (C.err) break;
+                }
+                prev = 0;
+                for (uint32_t k = 0; k < ni && !C.err; k++) {               /* insertions (:594-600) */
+                    const uint32_t ed = e_in[nd + ns + k];
+                    const uint32_t p = CBCG_EDIT_DELTA(ed);
+                    K2M_ITEM((prev << 1) | strand, p);
+                    prev += p;
+                    C.tri_at = slots + at; at++;
+                    C.template sym_dense<5, false>(S.chars[CBCG_BP_O], 5u, 8u, CBCG_EDIT_TARGET(ed), false, 0u);
+                }
+#undef K2M_ITEM
+                if (C.err) break;
+            }
+            slot += k2m_slots(v.w, lead);
+            v = nx;
+        }
+        if (C.err) goto chain_done;
+        __syncwarp();
+        for (uint32_t base = 0; base < K; base += 32u) {                    /* ---- B */
+            const uint32_t kk = base + lane;
+            const bool valid = kk < K;
+            const uint32_t c = valid ? it_ctx[kk] : 0xffffff00u + lane;    /* lanes past the list: a group of their own */
+            const uint32_t peers = __match_any_sync(FULL_MASK, c);
+            const uint32_t below = peers & ((1u << lane) - 1u);
+            const bool top = (peers >> lane) == 1u;                         /* the group's last symbol of this step: it updates the hash */
+            uint32_t prev = 0xffffffffu;
+            if (valid) {
+                const uint64_t key = (uint64_t)(c + 1u) << 32;
+                uint32_t h = (c * 0x9E3779B1u) >> 7;
+                for (;;) {
+                    const uint32_t idx = h & C.hash_mask;
+                    const uint64_t e = C.var_hash[idx];
+                    if ((e >> 32) == (uint64_t)(c + 1u)) { prev = (uint32_t)e; if (top) C.var_hash[idx] = key | kk; break; }
+                    if (e == 0ull) {
+                        if (!top) break;                                    /* nothing earlier; the top lane makes the entry */
+                        if (atomicCAS(reinterpret_cast<unsigned long long *>(&C.var_hash[idx]), 0ull, key | kk) == 0ull) break;
+                        continue;                                           /* another context took the slot in this step: look again */
+                    }
+                    h++;
+                }
+                /* ordinal of the symbol within its context: the ones of this step, and those before the step's first */
+                const uint32_t ord = (uint32_t)__popc(below) + (prev != 0xffffffffu ? it_ord[prev] + 1u : 0u);
+                if (below) prev = base + 31u - (uint32_t)__clz(below);      /* the nearest earlier symbol of the context is in this step */
+                it_prev[kk] = prev; it_ord[kk] = ord;
+                max_ord = max(max_ord, ord);
+            }
+            __syncwarp();
+        }
+        if (warp_sum(max_ord > K2M_CTX_MAX ? 1u : 0u)) { i = 0; slot = 0; goto edits_serial; }
+        __threadfence_block();
+        __syncwarp();
+        bool redo = false;
+        for (uint32_t base = 0; base < K; base += 32u) {                    /* ---- C */
+            const uint32_t kk = base + lane;
+            if (kk < K) {
+                const uint32_t c = it_ctx[kk], xs = it_xs[kk], x = xs & 0xffu;
+                const uint32_t *row = ((C.snap.bitmap()[c >> 5] >> (c & 31u)) & 1u) ? C.snap.var_row(c) : C.snap.ones();
+                uint32_t n = row[L], cnt = row[x], lo = 0;
+                uint32_t j = 0;
+                for (; j + 4u <= x; j += 4u) { const uint4 q = *reinterpret_cast<const uint4 *>(row + j); lo += q.x + q.y + q.z + q.w; }
+                if (j < x) { const uint4 q = *reinterpret_cast<const uint4 *>(row + j); lo += q.x + (j + 1u < x ? q.y : 0u) + (j + 2u < x ? q.z : 0u); }
+                for (uint32_t e = it_prev[kk]; e != 0xffffffffu; e = it_prev[e]) {   /* earlier symbols of the context: update_model, step 10 */
+                    const uint32_t xe = it_xs[e] & 0xffu;
+                    n += 10u; lo += xe < x ? 10u : 0u; cnt += xe == x ? 10u : 0u;
+                }
+                if (n + 10u >= CBCG_RESCALE) redo = true;
+                else if (cnt == 0u || n == 0u) C.err = CBCG_ERR_INPUT;       /* reference: assert :71 / :293 */
+                else slots[xs >> 8] = make_uint4(lo, cnt, n, 0u);
+            }
+        }
+        if (__any_sync(FULL_MASK, C.err != 0)) { if (!C.err) C.err = CBCG_ERR_INPUT; goto chain_done; }
+        if (__any_sync(FULL_MASK, redo)) {                                  /* a total reaches the threshold: the serial walk, from the top */
+            i = 0; slot = 0;
+            goto edits_serial;
+        }
+        if (lane == 0) B.n_rows = 0u;
+        goto chain_done;
     } else {
         /* ---- edit positions through the var rows, bases through chars (:568-600; compute_delta_to_first_snp :703-718).
            Measured and dropped: the bases as a fifth chain of their own (220 M more warp instructions for the second walk
            over the records, 0.24 ms slower: the kernel as a whole is bound by instruction issue, not by its longest chain);
            asking for the next context's hash line and snapshot row one symbol ahead (the contexts depend on the input
            alone): this chain alone 1.65 -> 1.79 ms. */
+edits_serial:
         k2b_copy(&S.chars[0][0], &SM->chars[0][0], 48u, lane);
         for (uint32_t q = lane; q <= C.hash_mask; q += 32u) C.var_hash[q] = 0ull;
         __syncwarp();
@@ -1840,7 +1989,9 @@ static int launch_split_encode(const CoderParams &p, cudaStream_t st) {
     const dim3 grid((p.n_blocks + K2_WARPS - 1u) / K2_WARPS, K2M_ROLES);
     const char *rm = getenv("CBCG_K2M_ROLES");                          /* timing experiments: chains to run (tools/role_times.py) */
     const uint32_t role_mask = rm ? (uint32_t)atoi(rm) : 0xfu;
-    k2_model_kernel<<<grid, K2_THREADS, 0, st>>>(p, role_mask);
+    /* indel-heavy input (the host's estimate from the CIGAR text per read): every block would fall back to the serial walk */
+    if (p.no_merge && !p.indel_heavy) k2_model_kernel<true><<<grid, K2_THREADS, 0, st>>>(p, role_mask);
+    else k2_model_kernel<false><<<grid, K2_THREADS, 0, st>>>(p, role_mask);
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launch_code_kernel(p, st);
 }
@@ -1881,7 +2032,7 @@ void set_carveout_all(int pct) {
     if (pct == current) return;
     current = pct;
     set_carveout(k2_coder_kernel<MODE_ENC, false>, pct); set_carveout(k2_coder_kernel<MODE_DEC, false>, pct); set_carveout(k2_coder_kernel<MODE_LIST, false>, pct);
-    set_carveout(k2_block_kernel<MODE_ENC>, pct); set_carveout(k2_block_kernel<MODE_DEC>, pct); set_carveout(k2_model_kernel, pct);
+    set_carveout(k2_block_kernel<MODE_ENC>, pct); set_carveout(k2_block_kernel<MODE_DEC>, pct); set_carveout(k2_model_kernel<true>, pct); set_carveout(k2_model_kernel<false>, pct);
     set_carveout(k2_coder_kernel<MODE_ENC, true>, pct); set_carveout(k2_coder_kernel<MODE_DEC, true>, pct); set_carveout(k2_coder_kernel<MODE_LIST, true>, pct);
     set_carveout(k2_plan_kernel, pct); set_carveout(k2_payload_scan_kernel, pct); set_carveout(k2_gather_kernel, pct);
     set_carveout(snapshot_copy_kernel, pct);

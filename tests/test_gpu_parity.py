@@ -393,3 +393,19 @@ def test_more_distinct_flags_than_the_table_holds_is_an_error(codec):
     codec.set_reference(g)
     with pytest.raises(CbcgError):
         codec.compress(b, 100, block_reads=8_000, gen_mode=0, substreams=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("block_reads", [1500, 6000])
+def test_var_contexts_shared_by_many_symbols_of_a_block(codec, block_reads):
+    """Sparse coverage: no earlier SNP site lies under any read, so the first SNP of every read has the same var context
+    (sentinel delta, strand). The model kernel's context-grouped walk over the edit positions (last generation) meets
+    contexts with hundreds of symbols per block (block_reads 1500: inside its limit) and with thousands (6000: the block
+    falls back to the serial walk after the grouping pass); both must write the restatement's container."""
+    g, b = _synth(seed=41, genome_len=2_000_000, n_reads=6_000, len_min=100, len_max=100, p_sub=0.02, p_indel=0.0)
+    codec.set_reference(g)
+    for gen_mode in (0, 1):
+        c = codec.compress(b, 100, block_reads=block_reads, gen_mode=gen_mode, substreams=1)
+        assert c == O.encode_blocked(b, g, 100, block_reads, gen_mode)
+        text, n = codec.decompress(c)
+        assert n == b.n_reads and text == b.seq_lines()
