@@ -55,32 +55,61 @@ uint32_t roles_launches(uint32_t mode) { static const bool scalar = getenv("CBCG
  * cover -- a POS escape (its four byte symbols come from the escape list), an E3 run that does not fit one 32-bit put,
  * a full payload region -- raises a flag; the group of four is then redone from the saved state by the general coder. */
 struct K2CState { uint32_t l, u, scale3, nacc, out_pos; uint64_t acc; };
-__device__ __forceinline__ uint32_t k2c_fast(K2CState &s, const uint4 t, uint8_t *out, uint32_t out_cap) {
-    const uint32_t lo = t.x, cnt = t.y, n = t.z;
-    AcInterval a = { s.l, s.u };
-    ac_narrow(a, lo, lo + cnt, n);
-    uint32_t k, bits, m; AcInterval nx;
-    ac_renorm_shape(a, k, bits, m, nx);
-    /* the k shared bits: the first, then the pending E3 bits inverted (:318-322), then the other k - 1 */
-    const uint32_t run = k ? s.scale3 : 0u;
-    const uint32_t nb = k ? k + run : 0u;
-    const uint32_t rest_bits = k ? k - 1u : 0u;
-    const uint32_t b0 = (bits >> rest_bits) & 1u;
-    const uint32_t inv = b0 ? 0u : 0xffffffffu;
-    const uint32_t runc = run & 31u, sh = (runc + rest_bits) & 31u;          /* in range whenever nb <= 32 */
-    const uint32_t v = (b0 << sh) | ((inv & ((1u << runc) - 1u)) << rest_bits) | (bits & ((1u << rest_bits) - 1u));
-    uint32_t slow = (nb > 32u) | (t.w != 0u) | (cnt == 0u) | (n == 0u);
-    const uint64_t acc = (s.acc << (nb & 63u)) | (uint64_t)v;
-    const uint32_t nacc = s.nacc + nb;
-    const bool full = nacc >= 32u;
-    const bool room = s.out_pos + 4u <= out_cap;
-    slow |= (uint32_t)(full && !room);
-    if (full && room) *reinterpret_cast<uint32_t *>(out + s.out_pos) = __byte_perm((uint32_t)(acc >> ((nacc - 32u) & 63u)), 0u, 0x0123);
-    s.out_pos += full ? 4u : 0u;
-    s.nacc = full ? nacc - 32u : nacc;
-    s.acc = acc & ((1ull << s.nacc) - 1ull);
-    s.scale3 = (k ? 0u : s.scale3) + m;
-    s.l = nx.l; s.u = nx.u;
+/* Four symbols in three passes, so that the order of the instructions is the order of their dependences (one warp per SM
+ * issues in order: whatever stands between two links of the chain through the interval delays it):
+ *   1. what depends on the slots alone: the reciprocal of the total, the bounds as doubles;
+ *   2. the chain: range -> two quotients (ac_muldiv's estimate and remainder fix) -> shared-prefix shift -> E3 shift;
+ *   3. the bits: packing and the predicated store, a short chain of its own through the accumulator. */
+__device__ __forceinline__ uint32_t k2c_fast4(K2CState &s, const uint4 (&t)[4], uint8_t *out, uint32_t out_cap) {
+    /* pass 1 turns each bound into a 32-bit fraction of the total, F = trunc(bound * 2^32 / n) (within one of the floor:
+       the reciprocal is good to 2^-44; a bound equal to the total saturates to 2^32 - 1), so that the chain's quotient
+       floor(range * bound / n) is ONE integer multiply-high, off by at most one like ac_muldiv's estimate and put right by
+       the same remainder test -- the FP64 conversions and multiplies (the longest latencies of the step) leave the chain. */
+    uint32_t fh[4], fl[4], hi[4], slow = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        hi[q] = t[q].x + t[q].y;
+        const double r32 = __dmul_rn(ac_rcp(t[q].z), 4294967296.0);
+        fh[q] = __double2uint_rz(__dmul_rn(__uint2double_rn(hi[q]), r32));
+        fl[q] = __double2uint_rz(__dmul_rn(__uint2double_rn(t[q].x), r32));
+        slow |= (t[q].w != 0u) | (t[q].y == 0u) | (t[q].z == 0u);
+    }
+    uint32_t k[4], bits[4], m[4];
+    uint32_t l = s.l, u = s.u;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t range = u - l + 1u, n = t[q].z;
+        uint32_t qh = __umulhi(range, fh[q]), ql = __umulhi(range, fl[q]);
+        const int32_t rh = (int32_t)(range * hi[q] - qh * n), rl = (int32_t)(range * t[q].x - ql * n);   /* estimates are off by at most one */
+        qh += rh < 0 ? 0xffffffffu : (rh >= (int32_t)n ? 1u : 0u);
+        ql += rl < 0 ? 0xffffffffu : (rl >= (int32_t)n ? 1u : 0u);
+        AcInterval a = { l + ql, l + qh - 1u }, nx;
+        ac_renorm_shape(a, k[q], bits[q], m[q], nx);
+        l = nx.l; u = nx.u;
+    }
+    s.l = l; s.u = u;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        /* the k shared bits: the first, then the pending E3 bits inverted (:318-322), then the other k - 1 */
+        const uint32_t run = k[q] ? s.scale3 : 0u;
+        const uint32_t nb = k[q] ? k[q] + run : 0u;
+        const uint32_t rest_bits = k[q] ? k[q] - 1u : 0u;
+        const uint32_t b0 = (bits[q] >> rest_bits) & 1u;
+        const uint32_t inv = b0 ? 0u : 0xffffffffu;
+        const uint32_t runc = run & 31u, sh = (runc + rest_bits) & 31u;      /* in range whenever nb <= 32 */
+        const uint32_t v = (b0 << sh) | ((inv & ((1u << runc) - 1u)) << rest_bits) | (bits[q] & ((1u << rest_bits) - 1u));
+        slow |= (nb > 32u);
+        const uint64_t acc = (s.acc << (nb & 63u)) | (uint64_t)v;           /* bits above nacc are never read: no masking */
+        const uint32_t nacc = s.nacc + nb;
+        const bool full = nacc >= 32u;
+        const bool room = s.out_pos + 4u <= out_cap;
+        slow |= (uint32_t)(full && !room);
+        if (full && room) *reinterpret_cast<uint32_t *>(out + s.out_pos) = __byte_perm((uint32_t)(acc >> ((nacc - 32u) & 63u)), 0u, 0x0123);
+        s.out_pos += full ? 4u : 0u;
+        s.nacc = full ? nacc - 32u : nacc;
+        s.acc = acc;
+        s.scale3 = (k[q] ? 0u : s.scale3) + m[q];
+    }
     return slow;
 }
 /* the general coder over `count` main slots from T (and the escapes they flag) */
@@ -130,10 +159,12 @@ k2_code_kernel(CoderParams P) {
 #pragma unroll
             for (uint32_t q = 0; q < K2C_GROUP; q++) nxt[q] = src[(g + 1u) * K2C_GROUP + q];
         }
+        /* the loads above are a group ahead of their use, which does not cover a miss to HBM (13 % of the stall samples
+           waited for them): ask for the line four groups ahead */
+        if (g + 4u < groups) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (g + 4u) * K2C_GROUP));
         const K2CState saved = st;
         uint32_t slow = 0;
-#pragma unroll
-        for (uint32_t q = 0; q < K2C_GROUP; q++) slow |= k2c_fast(st, cur[q], out, out_cap);
+        slow = k2c_fast4(st, cur, out, out_cap);
         if (K2R_UNLIKELY(slow)) {                            /* through copies: the state itself stays in registers */
             K2CState tmp = saved; const uint4 *e2 = esc; uint32_t ns2 = 0;
             err = k2c_general(&tmp, src + g * K2C_GROUP, K2C_GROUP, &e2, out, out_cap, &ns2);
