@@ -168,3 +168,50 @@ def test_compact_batch_through_the_pipelined_encode(monkeypatch):
     n2 = c.compress_compact_into(cb, 150, AUTO, out, 1)     # and the context is still usable
     assert out[:n2].tobytes() == got
     cb.close(); c.close()
+
+
+def test_contexts_in_flight_from_their_own_host_threads():
+    """cbcg.h: one host thread per context, no globals. Three contexts on device 0, each driven by its own thread, code
+    DIFFERENT batches at the same time (resident round trips and host-buffer calls interleaved): every container equals
+    the one the same batch gives on a quiet device, every decode returns its own input. This is how bench.py keeps
+    several batches in flight per GPU."""
+    import threading
+    cfgs = [synth.SynthConfig.named("config2", scale=0.05), synth.SynthConfig.named("config5", scale=0.03),
+            synth.SynthConfig.named("config1", scale=0.2)]
+    jobs = []
+    for cfg in cfgs:
+        g = synth.make_genome(cfg)
+        b = synth.make_reads(cfg, g)
+        c = Codec(0)
+        c.set_reference(g)
+        jobs.append((cfg, g, b, c))
+    quiet = []
+    for cfg, g, b, c in jobs:                                 # one at a time first
+        c.upload(b)
+        c.encode_resident(cfg.len_max, AUTO, 1, 0)
+        quiet.append(c.fetch_container().tobytes())
+    quiet_host = [c.compress(b, cfg.len_max, AUTO, 1, None, 0) for cfg, g, b, c in jobs]
+    errors = []
+
+    def work(k):
+        cfg, g, b, c = jobs[k]
+        try:
+            for it in range(4):
+                c.upload(b)
+                c.encode_resident(cfg.len_max, AUTO, 1, 0)
+                assert c.fetch_container().tobytes() == quiet[k], f"context {k}: container differs under concurrency"
+                c.decode_resident()
+                assert c.fetch_decoded().tobytes() == b.seq_lines(), f"context {k}: resident decode differs"
+                cont = c.compress(b, cfg.len_max, AUTO, 1, None, 0)
+                assert cont == quiet_host[k], f"context {k}: host-buffer container differs"
+                text, n = c.decompress(cont)
+                assert n == b.n_reads and text == b.seq_lines(), f"context {k}: host-buffer decode differs"
+        except Exception as e:                               # noqa: BLE001 -- reported by the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    for _, _, _, c in jobs:
+        c.close()
+    assert not errors, errors
