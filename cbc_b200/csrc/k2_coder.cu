@@ -496,7 +496,10 @@ struct Coder {
         uint32_t nused = used;
         if (found_idx >= 0) { if (lane == 0) M->flag_cnt[found_idx] += 8u; }
         else {
-            if (used >= FLAG_CAP) { err = CBCG_ERR_LIMIT; return 0u; }
+            if (UNLIKELY(used >= FLAG_CAP)) {
+                if (!lean && MODE != MODE_LIST) { err = CBCG_ERR_LIMIT; return 0u; }     /* the reference's own stream adapts all 65 536 values */
+                return x;                                                             /* rule F1 (cbcg_format.h): coded at count 1, model unchanged */
+            }
             flag_insert(M->flag_key, M->flag_cnt, used, x, lane);
             if (lane == 0) M->flag_used = used + 1u;
             nused = used + 1u;
@@ -2566,8 +2569,38 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
     __syncthreads();
     uint32_t at = 0, total = 0;
     for (uint32_t k = 0; k < 32u; k++) { const uint32_t c = scan[k]; if (k < warp) at += c; total += c; }
-    if (total > FLAG_CAP) { if (tid == 0) dev_set_error(P.err, CBCG_ERR_LIMIT, total); }
-    else if (mine) {
+    if (total > FLAG_CAP) {
+        /* rule F2 (cbcg_format.h): more adapted values than a snapshot holds. The counts <= T go back to 1, T the smallest
+           threshold that leaves at most FLAG_CAP of them: bisection over T, every step one pass over the dense scratch
+           (uniform control flow: every thread holds the same bounds). Rare: inputs with hundreds of distinct FLAG values. */
+        uint32_t t_lo = 1u, t_hi = 0x7fffffffu;
+        while (t_lo < t_hi) {
+            const uint32_t mid = t_lo + (t_hi - t_lo) / 2u;
+            uint32_t above = 0;
+            for (uint32_t j = 0; live && j < 64u; j++) above += (uint32_t)__popc(__ballot_sync(FULL_MASK, dacc[base + 32u * j + lane] > mid));
+            __syncthreads();
+            if (lane == 0) red[warp] = above;
+            __syncthreads();
+            uint32_t all = 0; for (uint32_t k = 0; k < 32u; k++) all += red[k];
+            if (all <= FLAG_CAP) t_hi = mid; else t_lo = mid + 1u;
+        }
+        uint32_t s = live ? 0u : 64u;
+        mine = 0;
+        for (uint32_t j = 0; live && j < 64u; j++) {
+            const uint32_t i = base + 32u * j + lane;
+            uint32_t c = dacc[i];
+            if (c <= t_lo) { c = 1u; dacc[i] = 1u; }
+            s += c;
+            mine += (uint32_t)__popc(__ballot_sync(FULL_MASK, c != 1u));
+        }
+        s = warp_sum(s);
+        __syncthreads();
+        if (lane == 0) { red[warp] = s; scan[warp] = mine; }
+        __syncthreads();
+        n = 0; at = 0; total = 0;
+        for (uint32_t k = 0; k < 32u; k++) { n += red[k]; const uint32_t c = scan[k]; if (k < warp) at += c; total += c; }
+    }
+    if (mine) {
         for (uint32_t j0 = 0; j0 < 64u; j0 += 8u) {
             uint32_t c[8];
 #pragma unroll
@@ -2581,7 +2614,7 @@ __global__ void __launch_bounds__(MERGE_FIN_WARPS * 32u) merge_finish_kernel(Mer
             }
         }
     }
-    if (tid == 0) { nm->flag_used = total > FLAG_CAP ? 0u : total; nm->flag_n = n; }
+    if (tid == 0) { nm->flag_used = total; nm->flag_n = n; }
 }
 
 /* phase 3: clamp, total, rescale every row of the new snapshot (idempotent on rows no block touched). */

@@ -25,7 +25,7 @@
 #define LIKELY(c)   __builtin_expect(!!(c), 1)
 #define UNLIKELY(c) __builtin_expect(!!(c), 0)
 #ifndef FLAG_CAP
-#define FLAG_CAP    256u              /* distinct FLAG values a block / a snapshot may hold (the sparse table's size; 128 -> 256 measured time-neutral) */
+#define FLAG_CAP    CBCG_FLAG_ADAPT_MAX   /* distinct FLAG values a block / a snapshot adapts (the sparse table's size, a format constant: rules F1 / F2 in cbcg_format.h; 128 -> 256 measured time-neutral) */
 #endif
 #define PA_STRIDE   260u              /* words per 256-symbol model row: 256 counts, n, padding to 16 bytes */
 #define VAR_DIRECT_MIN_EDITS 32768u       /* blocks with more edits index var rows directly by context */

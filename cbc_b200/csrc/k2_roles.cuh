@@ -254,7 +254,7 @@ K2_HD uint32_t k2_sym_flag(K2Ac &ac, WarpModels *M, uint32_t x) {
     uint32_t nused = used;
     if (found) M->flag_cnt[idx] = cnt + 8u;
     else {
-        if (used >= FLAG_CAP) { ac.err = CBCG_ERR_LIMIT; return 0u; }
+        if (K2R_UNLIKELY(used >= FLAG_CAP)) return x;                     /* rule F1 (cbcg_format.h): coded at count 1, model unchanged */
         for (uint32_t j = used; j > idx; j--) { M->flag_key[j] = M->flag_key[j - 1u]; M->flag_cnt[j] = M->flag_cnt[j - 1u]; }
         M->flag_key[idx] = x; M->flag_cnt[idx] = 1u + 8u;
         nused = used + 1u; M->flag_used = nused;

@@ -268,5 +268,16 @@ static inline uint32_t cbcg_gen_schedule(uint64_t n, uint32_t layout, uint32_t *
     return ne;
 }
 #define CBCG_SNAP_POS_MAX   4096u         /* a snapshot keeps at most this many POS alphabet entries */
+/* FLAG in blocked containers is bounded by design (the reference's dense model takes all 65 536 values at
+ * 65 536 scan steps per symbol, src/sam_models.c:96-130, src/stream_model.c:64-67). A block, and a snapshot, ADAPT at most
+ * CBCG_FLAG_ADAPT_MAX distinct values (values whose count is not the initial 1):
+ *   F1 (block): a value that is not yet adapted arrives while CBCG_FLAG_ADAPT_MAX are -- it is coded with its count of 1 and
+ *       the model is left as it was (no increment of the count or of the total), by encoder and decoder alike;
+ *   F2 (snapshot merge): if more than CBCG_FLAG_ADAPT_MAX merged counts differ from 1, the counts <= T go back to 1, T the
+ *       smallest threshold that leaves at most CBCG_FLAG_ADAPT_MAX of them (after the clamp and the scaling to the target
+ *       total); the total is the sum of what is left.
+ * The single-block mode is the reference's own stream and adapts every value; there the table's size is an error
+ * (CBCG_ERR_LIMIT). */
+#define CBCG_FLAG_ADAPT_MAX 256u
 
 #endif /* CBCG_FORMAT_H */

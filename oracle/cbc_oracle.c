@@ -239,6 +239,8 @@ typedef struct models_s {
     model *var;                 /* CBCG_VAR_CONTEXTS lazily initialised rows (c == NULL: untouched) */
     posmodel pos;
     const struct models_s *base; /* primed blocks: untouched var rows are read from this snapshot (copy on first touch) */
+    uint32_t flag_adapted;      /* FLAG values whose count is not the initial 1 (blocked containers adapt at most
+                                   CBCG_FLAG_ADAPT_MAX of them: rules F1 / F2, cbcg_format.h) */
 } models;
 
 static void chars_init(model *m, int row) {
@@ -310,6 +312,7 @@ static void models_clone(models *M, const models *S) {
     M->var = (model *)calloc(CBCG_VAR_CONTEXTS, sizeof(model));
     pos_clone(&M->pos, &S->pos);
     M->base = S;
+    M->flag_adapted = S->flag_adapted;
 }
 /* acc += (fin - prev), wrapping 32-bit (exact as long as the true sum stays inside int32). */
 static void merge_model(model *acc, const model *fin, const model *prev) {
@@ -359,7 +362,7 @@ static void finish_model(model *m, const model *prev, uint32_t prev_card) {
     }
 }
 /* FLAG: clamp, then scale to the target total instead of halving (cbcg_flag_target, cbcg_format.h). */
-static void finish_flag(model *m, uint32_t target) {
+static uint32_t finish_flag(model *m, uint32_t target) {
     uint64_t n = 0;
     for (uint32_t i = 0; i < m->card; i++) { int32_t v = (int32_t)m->c[i]; if (v < 1) v = 1; m->c[i] = (uint32_t)v; n += (uint32_t)v; }
     if (n > target) {
@@ -368,14 +371,29 @@ static void finish_flag(model *m, uint32_t target) {
         for (uint32_t i = 0; i < m->card; i++) { uint64_t c = (uint64_t)m->c[i] * a / n; if (c < 1) c = 1; m->c[i] = (uint32_t)c; s += c; }
         n = s;
     }
+    /* rule F2 (cbcg_format.h): at most CBCG_FLAG_ADAPT_MAX counts differ from 1 in a snapshot */
+    uint32_t adapted = 0;
+    for (uint32_t i = 0; i < m->card; i++) adapted += m->c[i] != 1u;
+    if (adapted > CBCG_FLAG_ADAPT_MAX) {
+        uint32_t lo = 1u, hi = 0x7fffffffu;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2u;
+            uint32_t above = 0;
+            for (uint32_t i = 0; i < m->card; i++) above += m->c[i] > mid;
+            if (above <= CBCG_FLAG_ADAPT_MAX) hi = mid; else lo = mid + 1u;
+        }
+        n = 0; adapted = 0;
+        for (uint32_t i = 0; i < m->card; i++) { if (m->c[i] <= lo) m->c[i] = 1u; n += m->c[i]; adapted += m->c[i] != 1u; }
+    }
     m->n = (uint32_t)n;
+    return adapted;
 }
 static void merge_finish(models *acc, const models *prev, uint32_t flag_target) {
     for (int i = 0; i < 4; i++) { finish_model(&acc->rlength[i], &prev->rlength[i], 255); finish_model(&acc->pos_alpha[i], &prev->pos_alpha[i], 256);
                                   finish_model(&acc->match[i], &prev->match[i], 2); }
     for (int i = 0; i < 6; i++) finish_model(&acc->chars[i], &prev->chars[i], 5);
     finish_model(&acc->same_ref, &prev->same_ref, 2);
-    finish_flag(&acc->flag, flag_target);
+    acc->flag_adapted = finish_flag(&acc->flag, flag_target);
     finish_model(&acc->snps, &prev->snps, acc->L); finish_model(&acc->indels, &prev->indels, acc->L);
     for (uint32_t ctx = 0; ctx < CBCG_VAR_CONTEXTS; ctx++) if (acc->var[ctx].c) finish_model(&acc->var[ctx], NULL, 0);
     finish_model(&acc->pos.m, NULL, 0);
@@ -421,11 +439,20 @@ typedef struct {
     int split;              /* 1: blocked container v4, symbols go to the substream of their model (cbcg_substream_of) */
     uint32_t sub_syms[CBCG_N_SUB];
     int mode;               /* 0 trace only, 1 encode, 2 decode */
+    int flag_bound;         /* blocked containers: rule F1 (cbcg_format.h) */
     cbco_buf *trace;        /* optional (key, symbol) log, tracer format */
     int err;
     uint64_t n_symbols;
 } coder;
 
+/* Rule F1 (cbcg_format.h): a block adapts at most CBCG_FLAG_ADAPT_MAX distinct FLAG values; a further new value has
+ * just been coded with its count of 1 and leaves the model as it was. Returns 1 when the update is to be skipped. */
+static int flag_saturated(coder *c, const model *m, uint32_t x) {
+    if (m->c[x] != 1u) return 0;                              /* already adapted */
+    if (c->flag_bound && c->M.flag_adapted >= CBCG_FLAG_ADAPT_MAX) return 1;
+    c->M.flag_adapted++;
+    return 0;
+}
 /* send_value_to_as + update_model (src/stream_model.c:53-76,31-51) */
 static void put_sym(coder *c, uint32_t stream, uint32_t ctx, uint32_t x) {
     if (c->err) return;
@@ -440,6 +467,7 @@ static void put_sym(coder *c, uint32_t stream, uint32_t ctx, uint32_t x) {
         c->sub_syms[sub]++;
         if (ac_encode(&c->ac[sub], lo, lo + m->c[x], m->n)) { c->err = -3; return; }   /* assert :71 */
     }
+    if (stream == CBCG_S_FLAG && flag_saturated(c, m, x)) return;
     model_update(m, x);
 }
 /* read_value_from_as + update_model (src/stream_model.c:78-117) */
@@ -459,6 +487,7 @@ static uint32_t get_sym(coder *c, uint32_t stream, uint32_t ctx) {
     ac_decode(ac, lo, cum, m->n);
     if (c->trace) { uint32_t rec[2] = { CBCG_SYM_KEY(stream, ctx), x }; buf_put(c->trace, rec, 8); }
     c->n_symbols++;
+    if (stream == CBCG_S_FLAG && flag_saturated(c, m, x)) return x;
     model_update(m, x);
     return x;
 }
@@ -1050,6 +1079,7 @@ static void rstate_init_from(rstate *s, const models *snap, int mode) {
     memset(s, 0, sizeof *s);
     models_clone(&s->c.M, snap);
     s->c.mode = mode;
+    s->c.flag_bound = 1;                                       /* every block of a blocked container */
 }
 
 /* Blocks: generation i < n_sched has sched_count[i] blocks of sched_reads[i] reads, the last generation

@@ -111,6 +111,18 @@ static int host_merge(const BlockDesc *blocks, uint32_t b0, uint32_t nb, uint32_
             n = s;
         }
         uint32_t used = 0;
+        for (uint32_t i = 0; i < 65536; i++) used += facc[i] != 1u;
+        if (used > FLAG_CAP) {                                 /* rule F2 (cbcg_format.h): the counts <= T go back to 1 */
+            uint32_t lo = 1u, hi = 0x7fffffffu;
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo) / 2u; uint32_t above = 0;
+                for (uint32_t i = 0; i < 65536; i++) above += facc[i] > mid;
+                if (above <= FLAG_CAP) hi = mid; else lo = mid + 1u;
+            }
+            n = 0;
+            for (uint32_t i = 0; i < 65536; i++) { if (facc[i] <= lo) facc[i] = 1u; n += facc[i]; }
+        }
+        used = 0;
         for (uint32_t i = 0; i < 65536; i++) if (facc[i] != 1u) { if (used >= FLAG_CAP) return CBCG_ERR_LIMIT; nm->flag_key[used] = i; nm->flag_cnt[used] = facc[i]; used++; }
         nm->flag_used = used; nm->flag_n = (uint32_t)n;
     }
@@ -143,6 +155,17 @@ int main(int argc, char **argv) {
     o.seq_off = so.data(); o.seq = seq.data(); o.seq_cap = seq.size(); o.cigar_off = co.data(); o.cigar = cig.data(); o.cigar_cap = cig.size();
     o.md_off = mo.data(); o.md = md.data(); o.md_cap = md.size();
     if (cbcs_reads(&sp, cptr.data(), clen.data(), &o)) { fprintf(stderr, "generator failed\n"); return 1; }
+    if (argc > 12) {                                           /* n_flags distinct FLAG values (strand bit included); argv[13] = 1: drawn at random from the first read on
+                                                                  (otherwise the first n_flags reads carry one each, which fills the first snapshot at once) */
+        const int random_head = argc > 13 && atoi(argv[13]);
+        const uint32_t nf = (uint32_t)atoi(argv[12]);
+        uint64_t x = sp.seed * 0x9e3779b97f4a7c15ull + 1u;
+        for (uint64_t r = 0; r < n; r++) {
+            x = x * 6364136223846793005ull + 1442695040888963407ull;
+            const uint32_t k = (r < nf && !random_head) ? (uint32_t)r : (uint32_t)((x >> 33) % nf);
+            flag[r] = (uint16_t)((k * 13u + 5u) % 4096u);        /* 13 is odd: distinct k < 4096 give distinct values */
+        }
+    }
     cbco_batch ob = { n, pos.data(), flag.data(), slen.data(), chr.data(), so.data(), seq.data(), co.data(), cig.data(), mo.data(), md.data() };
     cbco_genome og = { sp.n_chr, cptr.data(), clen.data(), nptr.data() };
     std::vector<cbcg_read_rec> recs(n + 1); std::vector<uint16_t> edits(3 * seq.size() + 64);

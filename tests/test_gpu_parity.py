@@ -356,12 +356,14 @@ def test_cigar_operations_beyond_midS_on_the_gpu(codec):
     assert e.value.status == -6
 
 
-def _with_flags(b, n_distinct, seed):
-    """The batch with its FLAG column replaced by n_distinct values (strand bit included), position order untouched."""
+def _with_flags(b, n_distinct, seed, random_head=False):
+    """The batch with its FLAG column replaced by n_distinct values (strand bit included), position order untouched.
+    random_head: values drawn at random from the first read on; otherwise the first n_distinct reads carry one each."""
     rng = np.random.default_rng(seed)
     values = rng.choice(4096, size=n_distinct, replace=False).astype(np.uint16)
     flag = values[rng.integers(0, n_distinct, size=b.n_reads)]
-    flag[:n_distinct] = values                                   # every value occurs
+    if not random_head:
+        flag[:n_distinct] = values                               # every value occurs
     return Batch(b.pos, np.ascontiguousarray(flag), b.seq_len, b.chr, b.seq_off, b.seq, b.cigar_off, b.cigar, b.md_off, b.md)
 
 
@@ -385,14 +387,31 @@ def test_two_hundred_distinct_flags(codec):
 
 
 @pytest.mark.gpu
-def test_more_distinct_flags_than_the_table_holds_is_an_error(codec):
-    """Beyond 256 distinct FLAG values in a block the encoder reports CBCG_ERR_LIMIT (-12) instead of coding wrongly."""
+@pytest.mark.parametrize("n_distinct,random_head", [(300, False), (1500, True), (400, True)])
+def test_more_distinct_flags_than_a_block_adapts(codec, n_distinct, random_head):
+    """Blocked containers bound the FLAG model by design (cbcg_format.h, rules F1 / F2): a block adapts 256 distinct values
+    and codes further new ones at their initial count of 1, a merged snapshot keeps the 256 largest counts. 300 ... 1 500
+    distinct values -- more than a block and more than any snapshot holds; with random_head the blocks of one generation
+    adapt different values, so that their merge has to drop some (F2) -- in cold, generation-primed, one-stream,
+    four-substream and default-layout containers: the restatement's bytes, and the input back. The single-block mode is
+    the reference's own stream, whose model adapts every value: there the table's size stays an error."""
     from cbc_b200.codec import CbcgError
-    g, b0 = _synth(seed=32, genome_len=100_000, n_reads=8_000, len_min=100, len_max=100, p_sub=0.01, p_indel=0.0)
-    b = _with_flags(b0, 300, 8)
+    g, b0 = _synth(seed=32, genome_len=150_000, n_reads=24_000, len_min=100, len_max=100, p_sub=0.01, p_indel=0.0)
+    b = _with_flags(b0, n_distinct, 8, random_head)
     codec.set_reference(g)
-    with pytest.raises(CbcgError):
-        codec.compress(b, 100, block_reads=8_000, gen_mode=0, substreams=1)
+    for gen_mode, block_reads, sub in ((0, 24_000, 1), (0, 3_000, 1), (1, 2_000, 1), (1, 512, 1), (1, 2_000, 4), (1, 0xffffffff, 0)):
+        c = codec.compress(b, 100, block_reads=block_reads, gen_mode=gen_mode, substreams=sub)
+        if sub == 1:
+            assert c == O.encode_blocked(b, g, 100, block_reads, gen_mode), (gen_mode, block_reads)
+        else:
+            assert c == O.encode_like(c, b, g), (gen_mode, block_reads, sub)
+        text, n = codec.decompress(c)
+        assert n == b.n_reads and text == b.seq_lines(), (gen_mode, block_reads, sub)
+        otext, on = O.decode_blocked(c, g)
+        assert on == b.n_reads and otext == b.seq_lines()
+    with pytest.raises(CbcgError) as e:
+        codec.compress(b, 100, block_reads=0)
+    assert e.value.status == -10
 
 
 @pytest.mark.gpu

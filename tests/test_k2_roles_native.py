@@ -22,7 +22,7 @@ def harness():
 
 
 CASES = [
-    # seed n_reads genome len_min len_max p_sub p_indel p_clip gen_mode [block_reads [n_chr]]
+    # seed n_reads genome len_min len_max p_sub p_indel p_clip gen_mode [block_reads [n_chr [n_flags [random_head]]]]
     "5 20000 300000 150 150 0.005 0 0 0 512",
     "6 20000 300000 150 150 0.005 0 0 1",
     "7 30000 400000 100 100 0.01 0.002 0.05 0 777",
@@ -36,6 +36,13 @@ CASES = [
     "15 400000 2000000 100 100 0.02 0 0 0 100000",
     "16 1 100000 100 100 0.01 0 0 1",
     "17 3 100000 100 100 0.01 0 0 0 2",
+    # more distinct FLAG values than a block adapts / a snapshot keeps (rules F1 / F2, cbcg_format.h)
+    "18 30000 300000 100 100 0.01 0 0 0 4000 1 300",
+    "19 30000 300000 100 100 0.01 0 0 1 4294967295 1 300",
+    "20 60000 400000 100 100 0.01 0.001 0 1 4294967295 1 1500",
+    "21 20000 300000 100 100 0.01 0 0 0 20000 1 3000",
+    "22 60000 400000 100 100 0.01 0 0 1 4294967295 1 1500 1",   # the blocks of a generation adapt different values: the merge keeps 256 (F2)
+    "23 200000 1000000 100 100 0.01 0 0 1 4294967295 1 400 1",
 ]
 
 
