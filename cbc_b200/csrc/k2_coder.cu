@@ -175,6 +175,7 @@ struct Coder {
     bool var_defer, var_ro; uint32_t defer_idx, defer_key;   /* deferred rows of the last generation (var_row) */
     /* legacy-only */
     uint32_t *codebook, *rname;
+    __device__ __forceinline__ uint32_t *flag_spill() const { return rname + 256u * PA_STRIDE + 4u; }   /* ws_layout: 2 x 65 536 words behind rname */
     /* primed blocks */
     bool primed, lean; SnapView snap;
     /* SNP-site ring: word (p >> 5) & 31 lives in lane; covers [ring_base, ring_base + 1024) */
@@ -447,13 +448,19 @@ struct Coder {
         if (err) return 0u;
         const uint32_t used = M->flag_used, n = M->flag_n;
         uint32_t lo, cnt; int found_idx = -1;
+        /* The table lives in shared memory while it has fewer than FLAG_CAP entries. Blocked containers never grow it
+           further (rule F1); the single-block mode is the reference's own stream, whose model adapts all 65 536 values
+           (src/sam_models.c:96-130): there the table moves to the workspace when it reaches FLAG_CAP entries. */
+        const bool unbounded = !lean && MODE != MODE_LIST;
+        uint32_t *fkey = M->flag_key, *fcnt = M->flag_cnt;
+        if (unbounded && UNLIKELY(used >= FLAG_CAP)) { fkey = flag_spill(); fcnt = fkey + 65536u; }
         if (MODE == MODE_ENC) {
             if (x > 0xffffu) { err = CBCG_ERR_INPUT; return 0u; }
             uint32_t extra = 0; cnt = 1u;
             for (uint32_t base = 0; base < used; base += 32u) {
                 const uint32_t i = base + lane;
-                const uint32_t k = (i < used) ? M->flag_key[i] : 0xffffffffu;
-                const uint32_t c = (i < used) ? M->flag_cnt[i] : 1u;
+                const uint32_t k = (i < used) ? fkey[i] : 0xffffffffu;
+                const uint32_t c = (i < used) ? fcnt[i] : 1u;
                 if (k < x) extra += c - 1u;
                 const uint32_t hit = __ballot_sync(FULL_MASK, k == x);
                 if (hit) { const uint32_t h = (uint32_t)__ffs(hit) - 1u; cnt = __shfl_sync(FULL_MASK, c, h); found_idx = (int)(base + h); }
@@ -468,8 +475,8 @@ struct Coder {
             for (uint32_t base = 0; base < used && !done; base += 32u) {
                 const uint32_t i = base + lane;
                 const bool valid = i < used;
-                const uint32_t k = valid ? M->flag_key[i] : 0xffffffffu;
-                const uint32_t c = valid ? M->flag_cnt[i] : 1u;
+                const uint32_t k = valid ? fkey[i] : 0xffffffffu;
+                const uint32_t c = valid ? fcnt[i] : 1u;
                 const uint32_t e = c - 1u;
                 const uint32_t incl = warp_incl_scan(e) + carry;
                 const uint32_t E = incl - e;                       /* extras of all touched values below this one */
@@ -494,19 +501,22 @@ struct Coder {
         /* update_model with step 8 */
         SYNCW();
         uint32_t nused = used;
-        if (found_idx >= 0) { if (lane == 0) M->flag_cnt[found_idx] += 8u; }
+        if (found_idx >= 0) { if (lane == 0) fcnt[found_idx] += 8u; }
         else {
-            if (UNLIKELY(used >= FLAG_CAP)) {
-                if (!lean && MODE != MODE_LIST) { err = CBCG_ERR_LIMIT; return 0u; }     /* the reference's own stream adapts all 65 536 values */
-                return x;                                                             /* rule F1 (cbcg_format.h): coded at count 1, model unchanged */
-            }
-            flag_insert(M->flag_key, M->flag_cnt, used, x, lane);
+            if (UNLIKELY(used >= FLAG_CAP) && !unbounded) return x;                  /* rule F1 (cbcg_format.h): coded at count 1, model unchanged */
+            flag_insert(fkey, fcnt, used, x, lane);
             if (lane == 0) M->flag_used = used + 1u;
             nused = used + 1u;
+            if (unbounded && UNLIKELY(nused == FLAG_CAP)) {                         /* the table outgrows shared memory: on to the workspace */
+                SYNCW();
+                uint32_t *sk = flag_spill();
+                for (uint32_t i = lane; i < FLAG_CAP; i += 32u) { sk[i] = M->flag_key[i]; sk[65536u + i] = M->flag_cnt[i]; }
+                fcnt = sk + 65536u;
+            }
         }
         uint32_t nn = n + 8u;
         SYNCW();
-        if (UNLIKELY(nn >= CBCG_RESCALE)) nn = rescale_counts(M->flag_cnt, nused, lane) + (65536u - nused);
+        if (UNLIKELY(nn >= CBCG_RESCALE)) nn = rescale_counts(fcnt, nused, lane) + (65536u - nused);
         if (lane == 0) M->flag_n = nn;
         SYNCW();
         return x;

@@ -69,6 +69,7 @@ K2_HD WsLayout ws_layout(uint32_t L, uint64_t n_reads, uint64_t n_edits, int leg
     w.var_rows = o;  o += (uint64_t)w.rows_cap * w.Lp * 4u;
     w.codebook = o;  if (legacy) o += 4u * PA_STRIDE * 4u + 16u;
     w.rname = o;     if (legacy) o += 256u * PA_STRIDE * 4u + 16u;
+    if (legacy) o += 2u * 65536u * 4u;                                         /* FLAG table beyond FLAG_CAP entries: keys, then counts, right behind rname (Coder::flag_spill) */
     w.total = (o + 255u) & ~255ull;
     return w;
 }

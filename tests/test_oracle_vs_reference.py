@@ -120,6 +120,35 @@ def test_live_reference(kw, L):
 
 
 @pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built")
+def test_live_reference_hundreds_of_distinct_flag_values():
+    """The reference's FLAG model has all 65 536 symbols (src/sam_models.c:96-130): 700 distinct values in one stream, more
+    than the GPU coder's shared-memory table holds (its single-block mode continues in the workspace: tests/test_gpu_parity.py
+    compares it with this restatement). Stream bytes and symbol trace against the reference encoder, text against its decoder."""
+    cfg = synth.SynthConfig(seed=106, genome_len=200_000, n_reads=20_000, len_min=100, len_max=100, p_sub=0.005)
+    g = synth.make_genome(cfg)
+    b0 = synth.make_reads(cfg, g)
+    rng = np.random.default_rng(5)
+    mapped = np.array([v for v in range(4096) if not v & 4], dtype=np.uint16)       # 0x4 = unmapped: not on this path
+    values = rng.choice(mapped, size=700, replace=False)
+    flag = np.ascontiguousarray(values[rng.integers(0, 700, size=b0.n_reads)])
+    b = Batch(b0.pos, flag, b0.seq_len, b0.chr, b0.seq_off, b0.seq, b0.cigar_off, b0.cigar, b0.md_off, b0.md)
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g)
+        synth.write_sam(sam, b, g)
+        ref_stream, ref_trace, _ = O.run_reference(sam, fa, d, trace=True)
+        stream, trace = O.encode_legacy(b, g, 100, want_trace=True)
+        assert stream == ref_stream
+        assert np.array_equal(trace, ref_trace)
+        sp = os.path.join(d, "s.cbc")
+        with open(sp, "wb") as f:
+            f.write(stream)
+        ref_decoded, _ = O.run_reference_decode(sp, fa, d)
+    decoded, _ = O.decode_legacy(stream, g)
+    assert decoded == ref_decoded == b.seq_lines()
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("kw,L", [
     (dict(seed=104, genome_len=1_500_000, n_reads=300_000, len_min=150, len_max=150, p_sub=0.005), 150),
     (dict(seed=105, genome_len=4_500_000, n_reads=300_000, len_min=100, len_max=100, p_sub=0.005, p_indel=0.001), 100),
