@@ -41,7 +41,7 @@ EXPORTS = ["cbcg_create", "cbcg_destroy", "cbcg_strerror", "cbcg_last_error", "c
            "cbcg_encode", "cbcg_encode_bound", "cbcg_decode", "cbcg_decoded_size", "cbcg_decode_edits",
            "cbcg_reconstruct", "cbcg_batch_upload", "cbcg_encode_resident", "cbcg_decode_resident",
            "cbcg_fetch_container", "cbcg_fetch_decoded", "cbcg_fetch_index", "cbcg_mark", "cbcg_elapsed_ms",
-           "cbcg_encode_compact", "cbcg_batch_upload_compact"]
+           "cbcg_encode_compact", "cbcg_batch_upload_compact", "cbcg_cigar_bound", "cbcg_cigar_pack", "cbcg_cigar_unpack"]
 
 
 class EncodeOpts(C.Structure):
@@ -105,6 +105,9 @@ def load_library():
         lib.cbcg_fetch_container.argtypes = [vp, vp, u64, P(u64)]
         lib.cbcg_fetch_decoded.argtypes = [vp, vp, u64, P(u64)]
         lib.cbcg_fetch_index.argtypes = [vp, vp, u64, P(u64), P(u64)]
+        lib.cbcg_cigar_bound.argtypes = [P(CBatch)]; lib.cbcg_cigar_bound.restype = u64
+        lib.cbcg_cigar_pack.argtypes = [vp, P(CBatch), vp, u64, P(u64)]
+        lib.cbcg_cigar_unpack.argtypes = [vp, vp, u64, C.c_int, vp, u64, vp, u64, P(u64), P(u64)]
         lib.cbcg_mark.argtypes = [vp, C.c_int]
         lib.cbcg_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, P(C.c_float)]
         _LIB = lib
@@ -296,6 +299,33 @@ class Codec:
             if rc == -5 and n.value > out.nbytes:
                 out = np.empty(n.value, np.uint8)
                 rc = self.lib.cbcg_fetch_decoded(self.h, out.ctypes.data, out.nbytes, C.byref(n))
+            self._check(rc)
+            return out[:n.value].tobytes(), nr.value
+
+    def cigar_pack(self, batch: Batch) -> bytes:
+        """The CIGAR side section of a batch (cbcg.h): reads whose CIGAR is not the one their indels
+        imply, as a class (end operations are soft clips) or verbatim."""
+        cb = batch.c_struct()
+        cap = int(self.lib.cbcg_cigar_bound(C.byref(cb)))
+        out = np.empty(max(cap, 24), np.uint8)
+        n = C.c_uint64(0)
+        self._check(self.lib.cbcg_cigar_pack(self.h, C.byref(cb), out.ctypes.data, out.nbytes, C.byref(n)))
+        return out[:n.value].tobytes()
+
+    def cigar_unpack(self, data: bytes, section: Optional[bytes], legacy: bool = False) -> Tuple[bytes, int]:
+        """(CIGAR + '\\n' per read in read order, read count) of a container and its side section (None: the implied CIGARs)."""
+        src = np.frombuffer(data, np.uint8)
+        sec = np.frombuffer(section, np.uint8) if section is not None else None
+        size = max(len(data) * 4, 1 << 16)
+        while True:
+            out = np.empty(size, np.uint8)
+            n, nr = C.c_uint64(0), C.c_uint64(0)
+            rc = self.lib.cbcg_cigar_unpack(self.h, src.ctypes.data, src.nbytes, int(legacy),
+                                            sec.ctypes.data if sec is not None else None, sec.nbytes if sec is not None else 0,
+                                            out.ctypes.data, out.nbytes, C.byref(n), C.byref(nr))
+            if rc == -5 and n.value > out.nbytes:
+                size = int(n.value)
+                continue
             self._check(rc)
             return out[:n.value].tobytes(), nr.value
 

@@ -77,6 +77,7 @@ struct cbcg_ctx {
 
     /* work buffers */
     DevBuf recs, edits, chr_out, tile_desc, words, blocks, ws, scratch, payload, out_off, symbols, seq_out;
+    DevBuf cig_cls, cig_exc, cig_out;          /* CIGAR recovery (k4_cigar.cu): classes, verbatim texts, emitted text */
     DevBuf tri;                                /* two-kernel encode: the symbols' intervals between the model and the interval kernel */
     DevBuf snap_a, snap_b, fin;                /* generation snapshots and per-block final states (gen_mode 1) */
     std::vector<std::pair<uint32_t, uint32_t>> gens;   /* (first block, block count) per generation of the last cut */
@@ -200,7 +201,7 @@ extern "C" void cbcg_destroy(cbcg_ctx *ctx) {
     DevBuf *all[] = { &ctx->g_bases, &ctx->g_off, &ctx->g_len, &ctx->g_names, &ctx->b_pos, &ctx->b_flag, &ctx->b_len, &ctx->b_chr,
                       &ctx->b_soff, &ctx->b_seq, &ctx->b_coff, &ctx->b_cigar, &ctx->b_moff, &ctx->b_md, &ctx->recs, &ctx->edits,
                       &ctx->chr_out, &ctx->tile_desc, &ctx->words, &ctx->blocks, &ctx->ws, &ctx->scratch, &ctx->payload,
-                      &ctx->out_off, &ctx->symbols, &ctx->seq_out, &ctx->snap_a, &ctx->snap_b, &ctx->fin };
+                      &ctx->out_off, &ctx->symbols, &ctx->seq_out, &ctx->snap_a, &ctx->snap_b, &ctx->fin, &ctx->cig_cls, &ctx->cig_exc, &ctx->cig_out };
     for (DevBuf *b : all) free_buf(*b);
     if (ctx->hw) cudaFreeHost(ctx->hw);
     if (ctx->hblocks) cudaFreeHost(ctx->hblocks);
@@ -1797,6 +1798,119 @@ extern "C" int cbcg_decode_edits(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_l
     if (nr && recs) CU(cudaMemcpyAsync(recs, ctx->recs.p, nr * sizeof(cbcg_read_rec), cudaMemcpyDeviceToHost, ctx->st));
     if (nr && chr) CU(cudaMemcpyAsync(chr, ctx->chr_out.p, nr * 4, cudaMemcpyDeviceToHost, ctx->st));
     if (ne && edits) CU(cudaMemcpyAsync(edits, ctx->edits.p, ne * 2, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CBCG_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ CIGAR recovery
+ * (kernels and the meaning of the classes: k4_cigar.cu.) The side section of a batch, "CBCC":
+ *   u32 magic, u32 version (1), u64 n_reads, u64 n_entries, then per read whose class is not 0, in read order:
+ *   varint(read - previous listed read), u8 class, and for class 4 varint(length) + the CIGAR text.
+ * A batch whose CIGARs are all what their indels imply (configs 1-4) costs the 24 header bytes. */
+#define CBCC_MAGIC 0x43434243u
+extern "C" uint64_t cbcg_cigar_bound(const cbcg_batch *b) {
+    if (!b) return 0;
+    return 24u + b->n_reads * 16u + (b->cigar_off && b->n_reads ? b->cigar_off[b->n_reads] : 0u);
+}
+extern "C" int cbcg_cigar_pack(cbcg_ctx *ctx, const cbcg_batch *batch, uint8_t *out, uint64_t out_cap, uint64_t *out_len) {
+    if (!ctx || !batch || !out_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_cigar_pack: bad argument");
+    *out_len = 0;
+    TRY(cbcg_batch_upload(ctx, batch));
+    const uint64_t n = ctx->db.n_reads;
+    std::vector<uint8_t> cls(n);
+    if (n) {
+        TRY(run_extract(ctx));
+        TRY(ensure(ctx, ctx->cig_cls, n + 64));
+        if (launch_cigar_class(n, ctx->recs.as<cbcg_read_rec>(), ctx->edits.as<uint16_t>(), ctx->db.cigar_off, ctx->db.cigar,
+                               ctx->cig_cls.as<uint8_t>(), ctx->st))
+            return fail(ctx, CBCG_ERR_CUDA, "CIGAR class launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        CU(cudaMemcpyAsync(cls.data(), ctx->cig_cls.p, n, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+    }
+    std::vector<uint8_t> sec(24);
+    uint64_t entries = 0, prev = 0;
+    for (uint64_t r = 0; r < n; r++) {
+        if (!cls[r]) continue;
+        put_varint(sec, r - prev); prev = r;
+        sec.push_back(cls[r]);
+        if (cls[r] >= 4u) {
+            const uint64_t a = batch->cigar_off[r], l = batch->cigar_off[r + 1] - a;
+            put_varint(sec, l);
+            sec.insert(sec.end(), batch->cigar + a, batch->cigar + a + l);
+        }
+        entries++;
+    }
+    const uint32_t magic = CBCC_MAGIC, version = 1u;
+    memcpy(&sec[0], &magic, 4); memcpy(&sec[4], &version, 4); memcpy(&sec[8], &n, 8); memcpy(&sec[16], &entries, 8);
+    *out_len = sec.size();
+    if (!out || sec.size() > out_cap) return fail(ctx, CBCG_ERR_CAPACITY, "CIGAR section is %llu bytes, room for %llu", (unsigned long long)sec.size(), (unsigned long long)out_cap);
+    memcpy(out, sec.data(), sec.size());
+    return CBCG_OK;
+}
+/* container (or legacy stream) + its section -> the CIGAR of every read, '\n'-terminated, in read order. section == NULL:
+ * every read gets the CIGAR its indels imply (soft clips read as insertions). */
+extern "C" int cbcg_cigar_unpack(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy, const uint8_t *section, uint64_t section_len,
+                                 uint8_t *cigar_out, uint64_t cigar_cap, uint64_t *cigar_len, uint64_t *n_reads) {
+    if (!ctx || !cigar_len) return fail(ctx, CBCG_ERR_ARG, "cbcg_cigar_unpack: bad argument");
+    *cigar_len = 0; if (n_reads) *n_reads = 0;
+    uint64_t nr = 0, ne = 0; uint32_t max_len = 1, fixed_len = 0;
+    TRY(decode_to_records(ctx, in, in_len, legacy, &nr, &ne, &max_len, &fixed_len));
+    if (n_reads) *n_reads = nr;
+    if (!nr) return CBCG_OK;
+    std::vector<uint8_t> cls(nr, 0);
+    std::vector<uint64_t> exc_read, exc_off(1, 0);
+    std::vector<uint8_t> exc_text;
+    uint64_t text_bound = 0;
+    if (section) {
+        uint32_t magic = 0, version = 0; uint64_t sn = 0, entries = 0;
+        if (section_len < 24) return fail(ctx, CBCG_ERR_FORMAT, "CIGAR section too short");
+        memcpy(&magic, section, 4); memcpy(&version, section + 4, 4); memcpy(&sn, section + 8, 8); memcpy(&entries, section + 16, 8);
+        if (magic != CBCC_MAGIC || version != 1u) return fail(ctx, CBCG_ERR_FORMAT, "not a CIGAR section");
+        if (sn != nr) return fail(ctx, CBCG_ERR_FORMAT, "CIGAR section of %llu reads beside a container of %llu", (unsigned long long)sn, (unsigned long long)nr);
+        uint64_t o = 24, prev = 0;
+        for (uint64_t k = 0; k < entries; k++) {
+            uint64_t d = 0, l = 0;
+            if (!get_varint(section, section_len, o, d) || o >= section_len) return fail(ctx, CBCG_ERR_FORMAT, "CIGAR section truncated");
+            const uint64_t r = prev + d;
+            if (r >= nr || (k && d == 0)) return fail(ctx, CBCG_ERR_FORMAT, "CIGAR section lists read %llu", (unsigned long long)r);
+            prev = r;
+            const uint8_t c = section[o++];
+            if (c == 0 || c > 4) return fail(ctx, CBCG_ERR_FORMAT, "CIGAR section: class %u", (unsigned)c);
+            cls[r] = c;
+            if (c == 4) {
+                if (!get_varint(section, section_len, o, l) || l > section_len - o) return fail(ctx, CBCG_ERR_FORMAT, "CIGAR section truncated");
+                exc_read.push_back(r);
+                exc_text.insert(exc_text.end(), section + o, section + o + l);
+                exc_off.push_back(exc_text.size());
+                o += l;
+            }
+        }
+    }
+    text_bound = exc_text.size() + nr * 4ull + ne * 12ull + nr * 8ull + 64;   /* per read: '\n' + <= 2 operations per indel event + 2 M runs, <= 6 bytes each */
+    const uint64_t n_exc = exc_read.size();
+    const uint64_t exc_bytes = (n_exc + 1) * 16 + exc_text.size() + 64;
+    TRY(ensure(ctx, ctx->cig_cls, nr + 64));
+    TRY(ensure(ctx, ctx->cig_exc, exc_bytes));
+    TRY(ensure(ctx, ctx->cig_out, text_bound));
+    TRY(ensure(ctx, ctx->tile_desc, (cigar_num_tiles(nr) + 1) * 8));
+    uint64_t *d_read = ctx->cig_exc.as<uint64_t>(), *d_off = d_read + n_exc;
+    uint8_t *d_text = reinterpret_cast<uint8_t *>(d_off + n_exc + 1);
+    CU(cudaMemcpyAsync(ctx->cig_cls.p, cls.data(), nr, cudaMemcpyHostToDevice, ctx->st));
+    if (n_exc) CU(cudaMemcpyAsync(d_read, exc_read.data(), n_exc * 8, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(d_off, exc_off.data(), (n_exc + 1) * 8, cudaMemcpyHostToDevice, ctx->st));
+    if (!exc_text.empty()) CU(cudaMemcpyAsync(d_text, exc_text.data(), exc_text.size(), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemsetAsync(wptr<unsigned long long>(ctx, W_OFF(err)), 0, 8, ctx->st));
+    if (launch_cigar_emit(nr, ctx->recs.as<cbcg_read_rec>(), ctx->edits.as<uint16_t>(), ctx->cig_cls.as<uint8_t>(), d_read, d_off, d_text, n_exc,
+                          ctx->cig_out.as<uint8_t>(), text_bound, ctx->tile_desc.as<uint64_t>(), wptr<uint32_t>(ctx, W_OFF(ticket)),
+                          wptr<uint64_t>(ctx, W_OFF(total_bytes)), wptr<unsigned long long>(ctx, W_OFF(err)), ctx->st))
+        return fail(ctx, CBCG_ERR_CUDA, "CIGAR emit launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->stats.kernel_launches++;
+    TRY(fetch_words(ctx));                                   /* synchronises: the host vectors above may go */
+    TRY(device_error(ctx, "CIGAR recovery"));
+    const uint64_t bytes = ctx->hw->total_bytes;
+    *cigar_len = bytes;
+    if (bytes > cigar_cap || !cigar_out) return fail(ctx, CBCG_ERR_CAPACITY, "CIGAR text is %llu bytes, room for %llu", (unsigned long long)bytes, (unsigned long long)cigar_cap);
+    CU(cudaMemcpyAsync(cigar_out, ctx->cig_out.p, bytes, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     return CBCG_OK;
 }

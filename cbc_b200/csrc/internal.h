@@ -114,6 +114,14 @@ int launch_unpack(uint64_t r_begin, uint64_t r_end, uint64_t n_reads, const uint
                   const uint8_t *seq2, const uint64_t *tile_base, const uint64_t *run_first, const uint32_t *run_chr, uint32_t n_runs,
                   uint64_t *seq_off, uint64_t *cigar_off, uint64_t *md_off, uint8_t *seq, uint32_t *chr, unsigned long long *err, cudaStream_t st);
 int launch_patch(const uint32_t *exc_read, const uint16_t *exc_base, const uint8_t *exc_char, uint64_t n_exc, const uint64_t *seq_off, uint8_t *seq, cudaStream_t st);
+/* k4_cigar.cu: CIGAR recovery. cls: per read, 0 implied / 1, 2, 3 end operations are soft clips / 4 verbatim */
+int launch_cigar_class(uint64_t n_reads, const cbcg_read_rec *recs, const uint16_t *edits, const uint64_t *cigar_off,
+                       const uint8_t *cigar, uint8_t *cls, cudaStream_t st);
+uint64_t cigar_num_tiles(uint64_t n_reads);
+int launch_cigar_emit(uint64_t n_reads, const cbcg_read_rec *recs, const uint16_t *edits, const uint8_t *cls,
+                      const uint64_t *exc_read, const uint64_t *exc_off, const uint8_t *exc_text, uint64_t n_exc,
+                      uint8_t *out, uint64_t out_cap, uint64_t *tile_desc, uint32_t *ticket, uint64_t *total_bytes,
+                      unsigned long long *err, cudaStream_t st);
 uint64_t extract_num_tiles(uint64_t n_reads);
 uint64_t reconstruct_num_tiles(uint64_t n_reads);
 int launch_plan(const CoderParams &p, uint32_t n_reads_total, uint64_t n_edits_total, uint64_t ws_cap,

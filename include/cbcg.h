@@ -179,6 +179,20 @@ int cbcg_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, const cbcg_read_rec *recs,
                      const uint16_t *edits, uint64_t n_edits, uint8_t *seq_out, uint64_t seq_cap,
                      uint64_t *seq_len);
 
+/* ---- CIGAR recovery. Upstream declares reconstructCigar / cigarFlags (include/sam_block.h:179,443)
+ * and sketches decompress_cigar (src/read_decompression.c:91-113: a per-read flag "the CIGAR is the one the indels
+ * imply", the text itself otherwise) without implementing either; the coded stream therefore returns SEQ only. These two
+ * calls add the rest as a side section that travels beside the container (the CLI appends it with -C): reads whose
+ * CIGAR is what their deletions and insertions imply -- every read of configs 1-4 -- cost nothing, reads whose end
+ * operations are soft clips (coded as insertions by the reference, src/read_compression.c:358-479) cost two bytes, any
+ * other CIGAR (=, X, H, P, ...) is kept verbatim. cbcg_cigar_pack runs K1 on the batch and classifies every read on the
+ * device; cbcg_cigar_unpack decodes the container to edit records and writes every read's CIGAR + '\n' in read order
+ * (section == NULL: the implied CIGARs alone). */
+uint64_t cbcg_cigar_bound(const cbcg_batch *batch);
+int cbcg_cigar_pack(cbcg_ctx *ctx, const cbcg_batch *batch, uint8_t *out, uint64_t out_cap, uint64_t *out_len);
+int cbcg_cigar_unpack(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy, const uint8_t *section, uint64_t section_len,
+                      uint8_t *cigar_out, uint64_t cigar_cap, uint64_t *cigar_len, uint64_t *n_reads);
+
 /* ---- device-resident variants (inputs already in HBM when the timed region starts): upload once,
  * run many times. Results stay on the device until fetched. Used by bench.py for `value`. */
 int cbcg_batch_upload(cbcg_ctx *ctx, const cbcg_batch *batch);                 /* replaces the resident batch */
