@@ -8,6 +8,8 @@
  *          -l       variable-length reads: header read length = longest SEQ (src/main.c -l)
  *          -g LIST  CUDA devices, e.g. `-g 0,1,2,3`: batches (region shards of the sorted input) are dealt out to them
  *          -B MB    SAM text per batch (default 2048): memory is bounded by three batches whatever the file size
+ *          -C       CIGAR recovery (cbcg_cigar_pack / cbcg_cigar_unpack): -c also writes <out>.cig, the side
+ *                   sections of the batches (u64 length + section each); -d reads <in>.cig and writes "CIGAR<TAB>SEQ" lines
  *
  * Host C only: SAM/FASTA ingest (sam_ingest.c) and file I/O; the coding runs on the GPU through include/cbcg.h.
  * Where the reference's compress() (src/compression.c:112-170) reads a line, codes it and moves on, this driver
@@ -33,8 +35,8 @@
 static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
 
 static int usage(void) {
-    fprintf(stderr, "usage: cbc -c [-1] [-l] [-b reads_per_block] [-g devices] [-B batch_MB] <sam> <out> <ref.fa>\n"
-                    "       cbc -d [-g devices] <in> <out> <ref.fa>\n");
+    fprintf(stderr, "usage: cbc -c [-1] [-l] [-C] [-b reads_per_block] [-g devices] [-B batch_MB] <sam> <out> <ref.fa>\n"
+                    "       cbc -d [-C] [-g devices] <in> <out> <ref.fa>\n");
     return 2;
 }
 
@@ -45,6 +47,9 @@ typedef struct job {
     cbch_batch hb; cbch_compact cb; int have_compact;
     /* decompress */
     const uint8_t *in; uint64_t in_len; int legacy;
+    /* CIGAR recovery (-C): compress: the batch's side section; decompress: in = its section, out = the CIGAR lines */
+    const uint8_t *cig_in; uint64_t cig_in_len;
+    uint8_t *cig; uint64_t cig_len;
     /* result */
     uint8_t *out; uint64_t out_len; uint64_t n_reads; float device_ms; uint64_t n_blocks;
     int rc; char err[256];
@@ -59,7 +64,7 @@ typedef struct shared {
     uint64_t next_take;                         /* next job a device thread takes */
     int producer_failed;
     /* run parameters */
-    int mode, single, var_length; uint32_t block_reads;
+    int mode, single, var_length, with_cigar; uint32_t block_reads;
     const cbch_fasta *fa; int fa_ready;
     double t_gpu_ready;
 } shared;
@@ -107,6 +112,13 @@ static void *device_main(void *arg) {
                 J->out_len = n;
                 D->call_s += now() - tq;
                 cbcg_stats st; cbcg_get_stats(ctx, &st); J->device_ms = st.ms_total; J->n_blocks = st.n_blocks;
+                if (!rc && S->with_cigar) {                       /* the batch is still whole (ingest kept it) */
+                    uint64_t ccap = cbcg_cigar_bound(&v), cn = 0;
+                    J->cig = (uint8_t *)malloc(ccap ? ccap : 1);
+                    rc = J->cig ? cbcg_cigar_pack(ctx, &v, J->cig, ccap, &cn) : CBCG_ERR_NOMEM;
+                    if (rc) { J->rc = rc; snprintf(J->err, sizeof J->err, "%s", cbcg_last_error(ctx)); }
+                    J->cig_len = cn;
+                }
             }
             if (J->have_compact) cbch_free_compact(&J->cb);
         } else {
@@ -122,6 +134,17 @@ static void *device_main(void *arg) {
                 J->out_len = n; J->n_reads = n_reads;
                 D->call_s += now() - tq;
                 cbcg_stats st; cbcg_get_stats(ctx, &st); J->device_ms = st.ms_total;
+                if (!rc && S->with_cigar) {
+                    uint64_t ccap = J->in_len * 4 + (1u << 16), cn = 0, nr2 = 0;
+                    J->cig = (uint8_t *)malloc(ccap);
+                    rc = J->cig ? cbcg_cigar_unpack(ctx, J->in, J->in_len, J->legacy, J->cig_in, J->cig_in_len, J->cig, ccap, &cn, &nr2) : CBCG_ERR_NOMEM;
+                    if (rc == CBCG_ERR_CAPACITY && cn > ccap) {
+                        free(J->cig); J->cig = (uint8_t *)malloc(cn); ccap = cn;
+                        rc = J->cig ? cbcg_cigar_unpack(ctx, J->in, J->in_len, J->legacy, J->cig_in, J->cig_in_len, J->cig, ccap, &cn, &nr2) : CBCG_ERR_NOMEM;
+                    }
+                    if (rc) { J->rc = rc; snprintf(J->err, sizeof J->err, "%s", cbcg_last_error(ctx)); }
+                    J->cig_len = cn;
+                }
             }
         }
         pthread_mutex_lock(&S->mu);
@@ -166,7 +189,7 @@ static void *ingest_main(void *arg) {
             cbcg_encode_opts o = { J->hb.read_len_header ? J->hb.read_len_header : 1u, S->single ? 0u : S->block_reads, S->single ? 0u : 1u, 0u };
             J->bound = cbcg_encode_bound(&v, &o);
             J->seq_bases = J->hb.n_reads ? J->hb.seq_off[J->hb.n_reads] : 0; J->header_len = J->hb.read_len_header; J->n_reads = J->hb.n_reads;
-            if (!S->single && J->hb.n_reads && cbch_pack_batch(&v, 0, NULL, NULL, &J->cb) == CBCH_OK) {   /* 2 bits per base on the link */
+            if (!S->single && !S->with_cigar && J->hb.n_reads && cbch_pack_batch(&v, 0, NULL, NULL, &J->cb) == CBCH_OK) {   /* 2 bits per base on the link */
                 J->have_compact = 1;
                 const uint64_t unm = J->hb.n_unmapped;
                 cbch_free_batch(&J->hb);                          /* the packed form is all the device thread needs */
@@ -195,7 +218,7 @@ static int parse_devices(const char *s, int *dev) {
 }
 
 int main(int argc, char **argv) {
-    int mode = 0, single = 0, var_length = 0, n_dev = 1, dev[MAX_DEV] = { 0 };
+    int mode = 0, single = 0, var_length = 0, with_cigar = 0, n_dev = 1, dev[MAX_DEV] = { 0 };
     uint32_t block_reads = CBCG_BLOCK_AUTO;
     uint64_t batch_mb = 2048;
     const char *files[4]; int nfiles = 0;
@@ -205,6 +228,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(a, "-d") || !strcmp(a, "-x")) mode = 'd';
         else if (!strcmp(a, "-1")) single = 1;
         else if (!strcmp(a, "-l")) var_length = 1;
+        else if (!strcmp(a, "-C")) with_cigar = 1;
         else if (!strcmp(a, "-b") && i + 1 < argc) block_reads = (uint32_t)strtoul(argv[++i], NULL, 10);
         else if (!strcmp(a, "-B") && i + 1 < argc) batch_mb = strtoull(argv[++i], NULL, 10);
         else if (!strcmp(a, "-g") && i + 1 < argc) { n_dev = parse_devices(argv[++i], dev); if (n_dev < 1) return usage(); }
@@ -225,13 +249,13 @@ int main(int argc, char **argv) {
     const double t0 = now();
     shared S; memset(&S, 0, sizeof S);
     pthread_mutex_init(&S.mu, NULL); pthread_cond_init(&S.cv, NULL);
-    S.mode = mode; S.single = single; S.var_length = var_length; S.block_reads = block_reads;
+    S.mode = mode; S.single = single; S.var_length = var_length; S.block_reads = block_reads; S.with_cigar = with_cigar;
     devthread D[MAX_DEV]; memset(D, 0, sizeof D);
 
     /* ---- the input, cut into jobs (before the device threads start: they index S.jobs) */
     cbch_mapped map; memset(&map, 0, sizeof map); map.fd = -1;
     const uint8_t **cut = NULL;
-    uint8_t *in = NULL; uint64_t in_len = 0;
+    uint8_t *in = NULL, *cig_file = NULL; uint64_t in_len = 0;
     if (mode == 'c') {
         printf("Compressing...\n");
         const uint64_t batch_bytes = batch_mb << 20;
@@ -267,6 +291,23 @@ int main(int argc, char **argv) {
             if (off > in_len || len > in_len - off) { fprintf(stderr, "cbc: truncated CBCS file\n"); return 1; }
             S.jobs[k]->in = in + off; S.jobs[k]->in_len = len;
         }
+        if (with_cigar) {                                      /* <in>.cig: u64 length + section per batch, in batch order */
+            char path[4096]; snprintf(path, sizeof path, "%s.cig", files[0]);
+            FILE *fc = fopen(path, "rb");
+            if (!fc) { fprintf(stderr, "cbc: cannot open %s\n", path); return 1; }
+            fseek(fc, 0, SEEK_END); long csz = ftell(fc); fseek(fc, 0, SEEK_SET);
+            cig_file = (uint8_t *)malloc(csz > 0 ? (size_t)csz : 1);
+            if (!cig_file || fread(cig_file, 1, (size_t)csz, fc) != (size_t)csz) { fprintf(stderr, "cbc: cannot read %s\n", path); return 1; }
+            fclose(fc);
+            uint64_t o = 0;
+            for (uint64_t k = 0; k < S.n_jobs; k++) {
+                uint64_t l = 0;
+                if (o + 8 > (uint64_t)csz) { fprintf(stderr, "cbc: %s holds fewer sections than the input has batches\n", path); return 1; }
+                memcpy(&l, cig_file + o, 8); o += 8;
+                if (l > (uint64_t)csz - o) { fprintf(stderr, "cbc: truncated %s\n", path); return 1; }
+                S.jobs[k]->cig_in = cig_file + o; S.jobs[k]->cig_in_len = l; o += l;
+            }
+        }
         S.produced = S.n_jobs;
     }
     if ((uint64_t)n_dev > S.n_jobs) n_dev = (int)S.n_jobs;
@@ -284,6 +325,12 @@ int main(int argc, char **argv) {
     uint64_t total_reads = 0, total_out = 0, total_blocks = 0; double device_ms = 0;
     FILE *fo = fopen(files[1], "wb");
     if (!fo) { fprintf(stderr, "cbc: cannot write %s\n", files[1]); status = 1; }
+    FILE *fcig = NULL; uint64_t cig_bytes = 0;
+    if (with_cigar && mode == 'c' && !status) {
+        char path[4096]; snprintf(path, sizeof path, "%s.cig", files[1]);
+        fcig = fopen(path, "wb");
+        if (!fcig) { fprintf(stderr, "cbc: cannot write %s\n", path); status = 1; }
+    }
     ingest_arg IA; memset(&IA, 0, sizeof IA);
     pthread_t ith; int have_ith = 0;
     const double t1 = now();
@@ -303,12 +350,26 @@ int main(int argc, char **argv) {
         job *J = wait_done(&S, k);
         if (!J) { fprintf(stderr, "cbc: %s\n", IA.err[0] ? IA.err : "ingest failed"); status = 1; break; }
         if (J->rc) { fprintf(stderr, "cbc: %s\n", J->err); status = 1; break; }
-        if (J->out_len && fwrite(J->out, 1, J->out_len, fo) != J->out_len) { fprintf(stderr, "cbc: cannot write %s\n", files[1]); status = 1; break; }
+        if (with_cigar && mode == 'd') {                         /* "CIGAR<TAB>SEQ" per read: the two texts hold one line per read each */
+            const uint8_t *c = J->cig, *ce = J->cig + J->cig_len, *q = J->out, *qe = J->out + J->out_len;
+            while (c < ce && q < qe) {
+                const uint8_t *cn = (const uint8_t *)memchr(c, '\n', (size_t)(ce - c)), *qn = (const uint8_t *)memchr(q, '\n', (size_t)(qe - q));
+                if (!cn || !qn) break;
+                if (fwrite(c, 1, (size_t)(cn - c), fo) != (size_t)(cn - c) || fputc('\t', fo) == EOF || fwrite(q, 1, (size_t)(qn - q + 1), fo) != (size_t)(qn - q + 1)) { status = 1; break; }
+                c = cn + 1; q = qn + 1;
+            }
+            if (!status && (c != ce || q != qe)) { fprintf(stderr, "cbc: CIGAR and SEQ line counts differ\n"); status = 1; }
+            if (status) break;
+        } else if (J->out_len && fwrite(J->out, 1, J->out_len, fo) != J->out_len) { fprintf(stderr, "cbc: cannot write %s\n", files[1]); status = 1; break; }
+        if (fcig) {
+            if (fwrite(&J->cig_len, 1, 8, fcig) != 8 || (J->cig_len && fwrite(J->cig, 1, J->cig_len, fcig) != J->cig_len)) { fprintf(stderr, "cbc: cannot write the CIGAR sections\n"); status = 1; break; }
+            cig_bytes += 8 + J->cig_len;
+        }
         if (sharded) { shard_off[k] = filepos; shard_len[k] = J->out_len; filepos += J->out_len; }
         total_reads += J->n_reads; total_out += J->out_len; total_blocks += J->n_blocks; device_ms += J->device_ms;
         if (mode == 'c') { seq_bases += J->seq_bases; cbch_free_batch(&J->hb); }
         pthread_mutex_lock(&S.mu);
-        free(J->out); J->out = NULL; J->written = 1;              /* frees a slot of the ingest window */
+        free(J->out); J->out = NULL; free(J->cig); J->cig = NULL; J->written = 1;     /* frees a slot of the ingest window */
         pthread_cond_broadcast(&S.cv);
         pthread_mutex_unlock(&S.mu);
     }
@@ -320,12 +381,14 @@ int main(int argc, char **argv) {
         total_out += 16 + 16 * S.n_jobs;
     }
     if (fo && fclose(fo)) status = 1;
+    if (fcig && fclose(fcig)) status = 1;
     const double t2 = now();
     if (have_ith) pthread_join(ith, NULL);
     for (int d = 0; d < n_dev; d++) pthread_join(D[d].th, NULL);
     if (!status) {
         if (mode == 'c') {
             printf("Final Size: %llu\n", (unsigned long long)total_out);
+            if (with_cigar) printf("CIGAR sections: %llu bytes\n", (unsigned long long)cig_bytes);
             printf("Compression took %f\n", t2 - t1);
             printf("reads %llu (unmapped skipped %llu), blocks %llu, batches %llu on %d device(s), %.4f bits/base, fasta %.3f s, ingest %.3f s (%.2f GB/s), gpu ready %.3f s, device %.3f ms\n",
                    (unsigned long long)total_reads, (unsigned long long)IA.n_unmapped, (unsigned long long)total_blocks, (unsigned long long)S.n_jobs, n_dev,
@@ -338,8 +401,8 @@ int main(int argc, char **argv) {
     }
     if (getenv("CBC_TRACE")) for (int d = 0; d < n_dev; d++)
         fprintf(stderr, "[cbc] device %d: context %.3f s, reference upload %.3f s, coding calls %.3f s; writer done at %.3f s\n", dev[d], D[d].create_s, D[d].setref_s, D[d].call_s, t2 - t0);
-    for (uint64_t k = 0; k < S.n_jobs; k++) { free(S.jobs[k]->out); free(S.jobs[k]); }
-    free(S.jobs); free(cut); free(in); free(shard_off); free(shard_len);
+    for (uint64_t k = 0; k < S.n_jobs; k++) { free(S.jobs[k]->out); free(S.jobs[k]->cig); free(S.jobs[k]); }
+    free(S.jobs); free(cut); free(in); free(cig_file); free(shard_off); free(shard_len);
     if (mode == 'c') cbch_unmap(&map);
     cbch_free_fasta(&fa);
     printf("Total time elapsed: %f seconds.\n", now() - t0);

@@ -84,3 +84,24 @@ def test_cli_streams_batches_to_several_contexts():
         one = _run("-c", sam, os.path.join(d, "one.cbc"), fa)                     # one batch: a plain CBCB container
         assert "batches 1 " in one
         assert os.path.getsize(os.path.join(d, "one.cbc")) < len(data)           # a few thousand reads per shard: every shard pays its own start-up
+
+
+def test_cli_cigar_recovery():
+    """`-C`: `cbc -c -C` writes the CIGAR side sections to <out>.cig, `cbc -d -C` returns
+    "CIGAR<TAB>SEQ" per read -- the input's CIGAR text byte for byte (variable-length reads with indels and soft clips,
+    several batches on two contexts)."""
+    cfg = synth.SynthConfig(seed=44, genome_len=500_000, n_reads=30_000, len_min=50, len_max=250, p_sub=0.005, p_indel=0.02, p_clip=0.3)
+    g = synth.make_genome(cfg); b = synth.make_reads(cfg, g)
+    cig = [b.cigar[int(b.cigar_off[r]):int(b.cigar_off[r + 1])].tobytes() for r in range(b.n_reads)]
+    seqs = b.seq_lines().split(b"\n")[:-1]
+    want = b"".join(c + b"\t" + s + b"\n" for c, s in zip(cig, seqs))
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        synth.write_fasta(fa, g); synth.write_sam(sam, b, g)
+        for extra in ((), ("-B", "1", "-g", "0,0")):
+            out = _run("-c", "-l", "-C", *extra, sam, os.path.join(d, "a.cbc"), fa)
+            assert "CIGAR sections:" in out
+            assert os.path.getsize(os.path.join(d, "a.cbc.cig")) < sum(len(c) for c in cig) // 3
+            _run("-d", "-C", *extra[2:], os.path.join(d, "a.cbc"), os.path.join(d, "a.txt"), fa)
+            with open(os.path.join(d, "a.txt"), "rb") as f:
+                assert f.read() == want
