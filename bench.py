@@ -764,7 +764,7 @@ def main():
     ap.add_argument("--block-reads", type=int, default=0xffffffff, help="reads per block; default: CBCG_BLOCK_AUTO")
     ap.add_argument("--batches-in-flight", type=int, default=2,
                     help="resident leg: batches coded at once per GPU, a context and a host thread each (value = their joint throughput)")
-    ap.add_argument("--inflight", type=int, default=1, help="contexts (host threads / streams) the e2e leg keeps in flight")
+    ap.add_argument("--inflight", type=int, default=2, help="e2e leg: batches in flight per GPU through the host-buffer calls, a context and a host thread each")
     ap.add_argument("--gen-mode", type=int, default=1, help="1: generation-primed blocks (default), 0: cold blocks")
     ap.add_argument("--substreams", type=int, default=0, choices=[0, 1, 4],
                     help="arithmetic-coded streams per block: 0 = the library's default (four in the narrow early generations, one in the wide ones), 1, or 4 everywhere")
