@@ -319,6 +319,13 @@ def cli_leg(sample, genome, L, var_length, workdir):
 
 # ---------------------------------------------------------------------------------------------- B200 arm
 
+def auto_in_flight(n_reads: int) -> int:
+    """Batches kept in flight per GPU when the command line does not say: two, and more for batches that fill only part
+    of the device (config 1's 1 M reads occupy a third of the resident warp slots: 19.9 / 13.0 / 8.5 ms per batch at
+    1 / 2 / 4 in flight, tools/inflight_probe.py; config 2: 12.1 / 11.0 / 10.5)."""
+    return 2 if n_reads >= 2_000_000 else 3 if n_reads >= 1_200_000 else 4
+
+
 def k2_issue_profile():
     """Per-launch figures of the block coder from the committed ncu capture (profiles/k2_issue.json, written by
     tools/ncu_summary.py from the `--set full` report of this command)."""
@@ -426,7 +433,7 @@ def run_b200_arm(args):
     # of one batch (4 ... 700 of 2 960 resident warps) run in the slots the other batch's work leaves free. A step is one
     # round trip of EVERY batch in flight; timed with CUDA events recorded on an idle device at both ends.
     import threading
-    KB = max(1, args.batches_in_flight)
+    KB = args.batches_in_flight if args.batches_in_flight > 0 else auto_in_flight(n)
     res_codecs = [codec]
     for _ in range(KB - 1):
         c2 = Codec(local)
@@ -532,7 +539,7 @@ def run_b200_arm(args):
     # set of CUDA streams each (the ABI's threading model): the text of batch k is on the PCIe link while batch k+1 is
     # being decoded, which is how a streaming caller keeps both busy. Every context codes the WHOLE batch from the same
     # pinned input into its own pinned output buffers; a step is one round trip of every batch in flight.
-    K = max(1, args.inflight)
+    K = args.inflight if args.inflight > 0 else auto_in_flight(n)
     codecs = [codec] + [Codec(local) for _ in range(K - 1)]
     for c2 in codecs[1:]:
         c2.set_reference(g)
@@ -762,9 +769,10 @@ def main():
                     help="named shape of BASELINE.json; default: 2 on one GPU, 3 on 2 / 4 GPUs, 4 (scaled) on 8")
     ap.add_argument("--replicas", action="store_true", help="N > 1: one config-2-sized region per rank (round 1's workload) instead of region shards of one input")
     ap.add_argument("--block-reads", type=int, default=0xffffffff, help="reads per block; default: CBCG_BLOCK_AUTO")
-    ap.add_argument("--batches-in-flight", type=int, default=2,
-                    help="resident leg: batches coded at once per GPU, a context and a host thread each (value = their joint throughput)")
-    ap.add_argument("--inflight", type=int, default=2, help="e2e leg: batches in flight per GPU through the host-buffer calls, a context and a host thread each")
+    ap.add_argument("--batches-in-flight", type=int, default=0,
+                    help="resident leg: batches coded at once per GPU, a context and a host thread each (value = their joint throughput); "
+                         "default: 2, more for batches that fill only part of the device (auto_in_flight)")
+    ap.add_argument("--inflight", type=int, default=0, help="e2e leg: batches in flight per GPU through the host-buffer calls, a context and a host thread each (default: as --batches-in-flight)")
     ap.add_argument("--gen-mode", type=int, default=1, help="1: generation-primed blocks (default), 0: cold blocks")
     ap.add_argument("--substreams", type=int, default=0, choices=[0, 1, 4],
                     help="arithmetic-coded streams per block: 0 = the library's default (four in the narrow early generations, one in the wide ones), 1, or 4 everywhere")

@@ -13,7 +13,12 @@ d = defaultdict(dict)
 for r in csv.reader(open(path)):
     if len(r) > 10 and r[0].isdigit():
         i = int(r[0]); d[i]["k"] = r[4]; d[i]["grid"] = int(r[8].strip("()").split(",")[0]); d[i][r[-3]] = float(r[-1].replace(",", ""))
-is_dec = lambda k: "<(int)1" in k or "<1" in k
+def is_dec(k):
+    """k2_coder_kernel<MODE, LEGACY> and k2_block_kernel<MODE>: MODE 1 is the decoder. The model and the interval kernel are
+    the two halves of the encoder whatever their template arguments say (k2_model_kernel<BY_CONTEXT>)."""
+    if "k2_model_kernel" in k or "k2_code_kernel" in k:
+        return False
+    return "<(int)1" in k or "<1" in k
 big = max(v["grid"] for v in d.values() if is_dec(v["k"]))
 ends = [i for i in sorted(d) if is_dec(d[i]["k"]) and d[i]["grid"] == big]      # a pass ends with the decoder's last generation
 iters = float(len(ends))

@@ -41,8 +41,8 @@ out += [f"| {k} | {v[0]} | {v[1] / 1e6:.3f} | {100 * v[1] / tot:.1f}% |" for k, 
 sm = bench["stage_ms"]
 coder = sum(v[1] for k, v in agg.items() if "k2_" in k or "merge" in k or "snapshot" in k)
 out += ["", f"bench.py's CUDA-event stage times for the same build (profiles/{rnd}_bench_config2.json): K2 encode {sm['k2e']:.2f} ms, K2 decode {sm['k2d']:.2f} ms, "
-        f"K1 {sm['k1']:.2f} ms, K3 {sm['k3']:.2f} ms of a {bench['ms_per_step']:.1f} ms step: the block coder (with its generation merges) is "
-        f"{100 * (sm['k2e'] + sm['k2d']) / bench['ms_per_step']:.0f} % of the step there and {100 * coder / tot:.0f} % of the ncu launch list "
+        f"K1 {sm['k1']:.2f} ms, K3 {sm['k3']:.2f} ms of a {bench.get('single_batch', bench)['ms_per_step']:.1f} ms round trip of one batch with the device to itself: the block coder (with its generation merges) is "
+        f"{100 * (sm['k2e'] + sm['k2d']) / bench.get('single_batch', bench)['ms_per_step']:.0f} % of the step there and {100 * coder / tot:.0f} % of the ncu launch list "
         "(which also holds the K1-alone encodes and the pipelined host-buffer steps of the bench command).", ""]
 ki = json.load(open(os.path.join(P, "k2_issue.json")))
 out += [f"## Block coder per pass (profiles/{rnd}_k2_launches.csv -> profiles/k2_issue.json)", "",
