@@ -2013,6 +2013,7 @@ uint32_t coder_resident_blocks(int device) {
     int sms = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) return 148u * 16u;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_coder_kernel<MODE_ENC, false>, (int)K2_THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = K2_MIN_CTAS;
+    if (per_sm > 5) per_sm = 5;                              /* the cut (and with it the container) does not follow a build with more resident CTAs */
     return (uint32_t)sms * (uint32_t)per_sm * K2_WARPS;
 }
 
