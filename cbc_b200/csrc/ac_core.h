@@ -64,13 +64,14 @@ struct AcInterval { uint32_t l, u; };
 
 /* Interval update of arithmetic_encoder_step / arithmetic_decoder_step (:295-296, :402-403):
  * u is computed from the old l, both products in 64 bits, truncated to 32. */
-AC_HD void ac_narrow(AcInterval &a, uint32_t lo, uint32_t hi, uint32_t n) {
+/* r = ac_rcp(n): a caller that knows n before it knows the symbol (every decoder step) forms it off the dependent chain */
+AC_HD void ac_narrow_r(AcInterval &a, uint32_t lo, uint32_t hi, uint32_t n, double r) {
     const uint32_t range = a.u - a.l + 1u;                 /* <= 2^26 */
-    const double r = ac_rcp(n);
     const uint32_t nu = a.l + ac_muldiv(range, hi, 0u, n, r) - 1u;
     const uint32_t nl = a.l + ac_muldiv(range, lo, 0u, n, r);
     a.u = nu; a.l = nl;
 }
+AC_HD void ac_narrow(AcInterval &a, uint32_t lo, uint32_t hi, uint32_t n) { ac_narrow_r(a, lo, hi, n, ac_rcp(n)); }
 
 /* Renormalisation shape: k E1/E2 shifts (the top k bits of l are the emitted bits), then m E3 shifts. */
 AC_HD void ac_renorm_shape(const AcInterval &a, uint32_t &k, uint32_t &bits, uint32_t &m, AcInterval &out) {

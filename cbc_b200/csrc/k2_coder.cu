@@ -134,6 +134,63 @@ __device__ __noinline__ void emit_long(BitSink *bs, uint32_t b0, uint32_t run, u
 /* TRI: the encoder's model half on its own (k2_model_kernel): every coder step is replaced by a store of the symbol's
    interval (cumulative count, count, model total) for the interval kernel (k2_code_kernel) to code. */
 #define TRI_ESC 1u                             /* on a POS interval: the escape's four byte symbols follow (in the block's escape list) */
+/* The decoder's coder step as ONE copy of code (K2_SHARED_DEC_STEP): interval update, renormalisation shape, the next
+ * k + m stream bits, the tag -- 40 % of the instructions the decoder executes, which the direct call sites of the state
+ * machine would otherwise each hold inline (six hot sites: a hot loop of 24 KB walked by warps that are rarely at the
+ * same place, 23 % of the decoder's stall samples waiting for instruction fetch). State travels by value in registers
+ * (whole-program compilation: ptxas gives a non-inlined device function its own register convention, no stack). */
+struct AcDecState { uint32_t l, u, t, dcnt, in_pos; uint64_t dbuf; };
+__device__ __noinline__ AcDecState ac_decode_step_shared(AcDecState s, uint32_t lo, uint32_t cnt, uint32_t n, double rn, const WarpCold *cold) {
+    AcInterval a = { s.l, s.u };
+    ac_narrow_r(a, lo, lo + cnt, n, rn);
+    uint32_t k, bits, m; AcInterval nx;
+    ac_renorm_shape(a, k, bits, m, nx);
+    uint32_t left = k + m;                                                /* up to 51 bits; the tag keeps the last 26 */
+    s.l = nx.l; s.u = nx.u;
+    if (left == 0u) return s;
+    if (LIKELY(left < 32u)) {
+        /* nearly every step: fewer than 32 bits, one top-up at most, and 32-bit arithmetic for the tag (bits shifted past
+           bit 31 are past the 26 the tag keeps) */
+        if (UNLIKELY(s.dcnt < left)) {
+            uint32_t w = 0;
+            const uint8_t *in = cold->io; const uint32_t in_len = cold->io_cap;
+            if (s.in_pos + 4u <= in_len) {
+                w = ((uint32_t)in[s.in_pos] << 24) | ((uint32_t)in[s.in_pos + 1u] << 16) | ((uint32_t)in[s.in_pos + 2u] << 8) | (uint32_t)in[s.in_pos + 3u];
+            } else if (s.in_pos < in_len) w = refill_tail(in, s.in_pos, in_len);
+            s.in_pos += 4u;
+            s.dbuf |= (uint64_t)w << (32u - s.dcnt);
+            s.dcnt += 32u;
+        }
+        const uint32_t in32 = (uint32_t)(s.dbuf >> 32) >> (32u - left);
+        s.dbuf <<= left;
+        s.dcnt -= left;
+        uint32_t r = ((s.t << left) | in32) & CBCG_AC_TOP;
+        if (m) r ^= CBCG_AC_MSB;
+        s.t = r;
+        return s;
+    }
+    uint64_t in64 = 0;
+    while (left) {
+        const uint32_t take = left < 32u ? left : 32u;
+        if (UNLIKELY(s.dcnt < take)) {
+            uint32_t w = 0;
+            const uint8_t *in = cold->io; const uint32_t in_len = cold->io_cap;
+            if (s.in_pos + 4u <= in_len) {
+                w = ((uint32_t)in[s.in_pos] << 24) | ((uint32_t)in[s.in_pos + 1u] << 16) | ((uint32_t)in[s.in_pos + 2u] << 8) | (uint32_t)in[s.in_pos + 3u];
+            } else if (s.in_pos < in_len) w = refill_tail(in, s.in_pos, in_len);
+            s.in_pos += 4u;
+            s.dbuf |= (uint64_t)w << (32u - s.dcnt);
+            s.dcnt += 32u;
+        }
+        in64 = (in64 << take) | (uint32_t)(s.dbuf >> (64u - take));
+        s.dbuf <<= take;
+        s.dcnt -= take;
+        left -= take;
+    }
+    s.t = ac_tag_shift(s.t, k, m, (uint32_t)in64);
+    return s;
+}
+
 template <int MODE, bool TRI = false>
 struct Coder {
     /* --- TRI: where the next interval goes, and the flag bits that go with it */
@@ -261,8 +318,13 @@ struct Coder {
         scale3 += (int32_t)m;
         a = nx;
     }
-    __device__ __forceinline__ void ac_decode_step(uint32_t lo, uint32_t cnt, uint32_t n) {
-        ac_narrow(a, lo, lo + cnt, n);
+    __device__ __forceinline__ void ac_decode_step(uint32_t lo, uint32_t cnt, uint32_t n, double rn) {
+#ifdef K2_SHARED_DEC_STEP
+        const AcDecState r = ac_decode_step_shared(AcDecState{ a.l, a.u, t, dcnt, in_pos, dbuf }, lo, cnt, n, rn, coldp);
+        a.l = r.l; a.u = r.u; t = r.t; dcnt = r.dcnt; in_pos = r.in_pos; dbuf = r.dbuf;
+        return;
+#endif
+        ac_narrow_r(a, lo, lo + cnt, n, rn);
         uint32_t k, bits, m; AcInterval nx;
         ac_renorm_shape(a, k, bits, m, nx);
         uint32_t s = k + m;                                                   /* up to 51 bits; the tag keeps the last 26 */
@@ -294,12 +356,15 @@ struct Coder {
 #define DEC_LE(c) ((uint64_t)(c) * range <= A)               /* c <= target */
 
     /* one coder step given the symbol's interval; decode: caller found (lo, cnt) from the target */
-    __device__ __forceinline__ void code_interval(uint32_t lo, uint32_t cnt, uint32_t n) {
+    /* decoder: the reciprocal of the model total, formed before the search so that it is ready when the symbol is */
+    __device__ __forceinline__ double dec_rcp(uint32_t n) const { return MODE == MODE_DEC ? ac_rcp(n) : 0.0; }
+    __device__ __forceinline__ void code_interval(uint32_t lo, uint32_t cnt, uint32_t n) { code_interval(lo, cnt, n, dec_rcp(n)); }
+    __device__ __forceinline__ void code_interval(uint32_t lo, uint32_t cnt, uint32_t n, double rn) {
         if (TRI) {
             if (UNLIKELY(cnt == 0u || n == 0u)) { err = CBCG_ERR_INPUT; return; }          /* reference: assert :71 / :293 */
             if (lane == 0) *tri_at = make_uint4(lo, cnt, n, tri_flag);
             tri_flag = 0u;
-        } else if (MODE == MODE_ENC) ac_encode(lo, cnt, n); else ac_decode_step(lo, cnt, n);
+        } else if (MODE == MODE_ENC) ac_encode(lo, cnt, n); else ac_decode_step(lo, cnt, n, rn);
         n_symbols++;
     }
 
@@ -359,6 +424,7 @@ struct Coder {
     __device__ __forceinline__ uint32_t sym_dense(uint32_t *m, uint32_t card, uint32_t step, uint32_t x, bool pre, uint32_t pre_lo) {
         if (err) return 0u;
         const uint32_t n = m[card];
+        const double rn = dec_rcp(n);
         uint32_t lo = 0, cnt = 0;
         if (pre) { lo = pre_lo; cnt = m[x]; }
         else if (MODE == MODE_ENC) {
@@ -420,7 +486,7 @@ struct Coder {
             if (UNLIKELY(x >= card)) { err = CBCG_ERR_CORRUPT; return 0u; }
         }
         last_lo = lo; last_n = n;
-        code_interval(lo, cnt, n);
+        code_interval(lo, cnt, n, rn);
         if (UNLIKELY(err)) return 0u;
         dense_update<IS_VAR>(m, card, step, x, cnt, n);
         return x;
@@ -447,6 +513,7 @@ struct Coder {
     __device__ __forceinline__ uint32_t sym_flag(uint32_t x) {
         if (err) return 0u;
         const uint32_t used = M->flag_used, n = M->flag_n;
+        const double rn = dec_rcp(n);
         uint32_t lo, cnt; int found_idx = -1;
         /* The table lives in shared memory while it has fewer than FLAG_CAP entries. Blocked containers never grow it
            further (rule F1); the single-block mode is the reference's own stream, whose model adapts all 65 536 values
@@ -496,7 +563,7 @@ struct Coder {
             if (!done) { const uint32_t target = ac_target(a, t, n); x = target - carry; lo = target; cnt = 1u; }   /* every touched value lies below */
             if (x > 0xffffu) { err = CBCG_ERR_CORRUPT; return 0u; }
         }
-        code_interval(lo, cnt, n);
+        code_interval(lo, cnt, n, rn);
         if (err) return 0u;
         /* update_model with step 8 */
         SYNCW();
@@ -565,6 +632,7 @@ struct Coder {
     __device__ __forceinline__ uint32_t sym_pos_main(uint32_t x, uint32_t &slot) {
         slot = 0;
         if (err) return 0u;
+        const double rn = dec_rcp(pos_n);
         uint32_t lo = 0, cnt = 0;
         if (MODE == MODE_ENC) {
             bool found = false;
@@ -600,7 +668,7 @@ struct Coder {
             }
             if (!found) { err = CBCG_ERR_CORRUPT; return 0u; }
         }
-        code_interval(lo, cnt, pos_n);
+        code_interval(lo, cnt, pos_n, rn);
         if (err) return 0u;
         pos_update(slot);
         return x;

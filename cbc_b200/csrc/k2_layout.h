@@ -22,6 +22,9 @@
                                   (cold per-warp values live in shared memory, WarpCold); 6 spills and is slower */
 #endif
 #define K2_THREADS  (K2_WARPS * 32u)
+#ifndef K2_INLINE_DEC_STEP
+#define K2_SHARED_DEC_STEP 1   /* the decoder's coder step as one non-inlined copy (k2_coder.cu, ac_decode_step_shared); -DK2_INLINE_DEC_STEP: inline at every site */
+#endif
 #define LIKELY(c)   __builtin_expect(!!(c), 1)
 #define UNLIKELY(c) __builtin_expect(!!(c), 0)
 #ifndef FLAG_CAP
