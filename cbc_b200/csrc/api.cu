@@ -550,10 +550,19 @@ static int reset_words(cbcg_ctx *ctx) {
     CU(cudaMemsetAsync(ctx->words.p, 0, sizeof(Words), ctx->st));
     return 0;
 }
+/* the device words -> their pinned host mirror, written by a kernel: a cudaMemcpyAsync would queue on the device -> host
+   copy engine behind the decoded text of another batch in flight on this GPU (k2_coder.cu, "Small transfers by the SMs") */
 static int fetch_words(cbcg_ctx *ctx) {
-    CU(cudaMemcpyAsync(ctx->hw, ctx->words.p, sizeof(Words), cudaMemcpyDeviceToHost, ctx->st));
+    static_assert(sizeof(Words) % 8 == 0 && sizeof(Words) / 8 <= 32, "Words travels as <= 32 64-bit words");
+    if (launch_copy_words(ctx->hw, ctx->words.p, (uint32_t)(sizeof(Words) / 8), ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "word copy launch failed");
     CU(cudaStreamSynchronize(ctx->st));
     return 0;
+}
+/* pinned (cudaHostAlloc / cbcg_host_alloc / registered) host memory: the device reads and writes it in place */
+static bool host_mapped(const void *p) {
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost && a.devicePointer == p;
 }
 
 /* Runs K1 on the resident batch; on return ctx->hw->total_edits is valid. */
@@ -1023,8 +1032,11 @@ extern "C" int cbcg_fetch_container(cbcg_ctx *ctx, uint8_t *out, uint64_t out_ca
     if (total > out_cap || (!out && total)) return fail(ctx, CBCG_ERR_CAPACITY, "container is %llu bytes, room for %llu", (unsigned long long)total, (unsigned long long)out_cap);
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventRecord(ctx->ev[5], ctx->st));
-    if (ctx->enc_payload_bytes)
-        CU(cudaMemcpyAsync(out + ctx->enc_head.size(), ctx->payload.p, ctx->enc_payload_bytes, cudaMemcpyDeviceToHost, ctx->st));
+    if (ctx->enc_payload_bytes) {
+        if (host_mapped(out)) {                              /* pinned buffer: written in place by the SMs, no copy-engine queue */
+            if (launch_d2h_bytes(out + ctx->enc_head.size(), ctx->payload.p, ctx->enc_payload_bytes, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "container copy launch failed");
+        } else CU(cudaMemcpyAsync(out + ctx->enc_head.size(), ctx->payload.p, ctx->enc_payload_bytes, cudaMemcpyDeviceToHost, ctx->st));
+    }
     if (!ctx->enc_head.empty()) memcpy(out, ctx->enc_head.data(), ctx->enc_head.size());
     CU(cudaEventRecord(ctx->ev[6], ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
@@ -1260,10 +1272,13 @@ static int encode_pipelined(cbcg_ctx *ctx, const BatchSrc &src, const cbcg_encod
         return fail(ctx, CBCG_ERR_CUDA, "gather launch failed");
     S.kernel_launches += 2;
     CU(cudaEventRecord(ctx->ev[4], ctx->st));
-    CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaMemcpyAsync(&ctx->hw->total_bytes, ctx->out_off.as<uint64_t>() + nb, 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaMemcpyAsync(&ctx->hw->total_edits, &chain[(PIPE_CHUNKS + 1u) & 1u], 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaMemcpyAsync(&ctx->hw->err, wptr<unsigned long long>(ctx, W_OFF(err)), 8, cudaMemcpyDeviceToHost, ctx->st));
+    /* results to the pinned host mirrors by kernels, not by the device -> host copy engine (another batch's text may be
+       queued there: k2_coder.cu, "Small transfers by the SMs") */
+    if (launch_copy16(ctx->hblocks, ctx->blocks.p, nb * sizeof(BlockDesc), ctx->st) ||
+        launch_copy_words(&ctx->hw->total_bytes, ctx->out_off.as<uint64_t>() + nb, 1, ctx->st) ||
+        launch_copy_words(&ctx->hw->total_edits, &chain[(PIPE_CHUNKS + 1u) & 1u], 1, ctx->st) ||
+        launch_copy_words(&ctx->hw->err, wptr<unsigned long long>(ctx, W_OFF(err)), 1, ctx->st))
+        return fail(ctx, CBCG_ERR_CUDA, "result copy launch failed");
     CU(cudaStreamSynchronize(ctx->st));
     ctx->have_batch = true;
     if (getenv("CBCG_PIPE_TRACE")) {                        /* when each chunk landed, was extracted and planned, and was coded */
@@ -1643,7 +1658,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
             gb[g] = k; gr[g] = r;
         }
     }
-    TRY(ensure(ctx, ctx->payload, pb + 64));
+    TRY(ensure(ctx, ctx->payload, pb + 96));
     TRY(ensure(ctx, ctx->blocks, ((uint64_t)nb + 1) * sizeof(BlockDesc)));
     TRY(ensure(ctx, ctx->recs, (nr + 1) * sizeof(cbcg_read_rec)));
     TRY(ensure(ctx, ctx->chr_out, (nr + 1) * 4));
@@ -1655,13 +1670,23 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
     TRY(ensure(ctx, ctx->tile_desc, (reconstruct_num_tiles(nr) + 1) * 8));
 
     CU(cudaEventRecord(ctx->ev[0], ctx->st));
-    if (pb) CU(cudaMemcpyAsync(ctx->payload.p, in + c.payload_off, pb, cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemcpyAsync(ctx->blocks.p, hb, (uint64_t)nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->st));
+    /* the container and the descriptors come in by kernels when the caller's buffer is pinned (read in place over PCIe:
+       the host -> device copy engine may be busy with another batch's input); the payload keeps the misalignment it has in
+       the caller's buffer, the coder reads it byte by byte */
+    uint32_t pay_shift = 0;
+    if (pb && host_mapped(in)) {
+        const uint8_t *src = in + c.payload_off;
+        pay_shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint64_t body = (pb + pay_shift) & ~15ull, tail = pb + pay_shift - body;     /* nothing is read past the caller's last byte */
+        if (launch_copy16(ctx->payload.p, src - pay_shift, body, ctx->st) ||
+            launch_d2h_bytes(ctx->payload.as<uint8_t>() + body, src - pay_shift + body, tail, ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "payload copy launch failed");
+    } else if (pb) CU(cudaMemcpyAsync(ctx->payload.p, in + c.payload_off, pb, cudaMemcpyHostToDevice, ctx->st));
+    if (launch_copy16(ctx->blocks.p, hb, (uint64_t)nb * sizeof(BlockDesc), ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "descriptor copy launch failed");
     TRY(reset_words(ctx));
     TRY(poison_decode_outputs(ctx, nr, ne));
     CoderParams p = coder_params(ctx, nb, c.L, 0, 1);
     p.chr = ctx->chr_out.as<uint32_t>();
-    p.payload = ctx->payload.as<uint8_t>();
+    p.payload = ctx->payload.as<uint8_t>() + pay_shift;
     p.lean = 1u; p.short_flush = 1u; p.primed = 1u; p.fixed_len = 1u;
     if (launch_plan(p, (uint32_t)nr, ne, ws_cap, ~0ull, wptr<uint64_t>(ctx, W_OFF(totals)), ctx->st))
         return fail(ctx, CBCG_ERR_CUDA, "plan launch failed");
@@ -1720,7 +1745,7 @@ static int decode_pipelined(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, u
     }
     for (uint32_t g = 0; g <= PIPE_CHUNKS; g++) CU(cudaStreamWaitEvent(ctx->st, ctx->dev2[g], 0));
     CU(cudaEventRecord(ctx->ev[1], ctx->st));
-    CU(cudaMemcpyAsync(ctx->hblocks, ctx->blocks.p, (uint64_t)nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost, ctx->st));
+    if (launch_copy16(ctx->hblocks, ctx->blocks.p, (uint64_t)nb * sizeof(BlockDesc), ctx->st)) return fail(ctx, CBCG_ERR_CUDA, "descriptor copy launch failed");
     TRY(fetch_words(ctx));
     TRY(device_error(ctx, "pipelined decode"));
     uint64_t got_r = 0, got_e = 0;

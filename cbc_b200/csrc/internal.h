@@ -144,4 +144,6 @@ int launch_roles(const CoderParams &p, cudaStream_t st);      /* k2_blocks.cu: b
 int launch_code_kernel(const CoderParams &p, cudaStream_t st); /* k2_blocks.cu: the interval half of a two-kernel encode */
 void set_carveout_all(int pct);                 /* -1: driver default per kernel; 0..100: one split for every kernel */
 int launch_copy16(void *dst, const void *src, uint64_t bytes, cudaStream_t st);
+int launch_d2h_bytes(void *dst_host, const void *src_dev, uint64_t bytes, cudaStream_t st);   /* dst: mapped pinned host memory, any alignment */
+int launch_copy_words(void *dst, const void *src, uint32_t n_words, cudaStream_t st);          /* <= 32 64-bit words */
 uint64_t coder_payload_bound(uint64_t n_reads, uint64_t n_edits, uint64_t n_blocks, int legacy);

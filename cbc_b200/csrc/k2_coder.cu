@@ -2739,6 +2739,40 @@ int launch_copy16(void *dst, const void *src, uint64_t bytes, cudaStream_t st) {
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+/* Small transfers by the SMs instead of a copy engine: with several batches in flight on one GPU (a context each) the
+ * copy engine of a direction is one queue for all of them, and a 5 MB container or a 380 KB descriptor table waits there
+ * behind another batch's 461 MB of decoded text (measured: 4 ms of a compress call at two batches in flight, 21 ms at
+ * six). Pinned host memory is mapped into the device's address space (UVA), so a kernel reads and writes it directly. */
+__global__ void __launch_bounds__(256) link_d2h_bytes_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint64_t n) {
+    /* dst: mapped host memory at any alignment; 16-byte stores on its aligned grid, the ragged ends byte by byte */
+    const uint64_t m = (uint64_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    uint8_t *base = dst - m;
+    const uint64_t n16 = (m + n + 15u) / 16u, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const int64_t first = (int64_t)(16u * i) - (int64_t)m;             /* src index of this piece's first byte */
+        if (first >= 0 && (uint64_t)first + 16u <= n) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                w[q] = (uint32_t)src[first + 4 * q] | ((uint32_t)src[first + 4 * q + 1] << 8) | ((uint32_t)src[first + 4 * q + 2] << 16) | ((uint32_t)src[first + 4 * q + 3] << 24);
+            *reinterpret_cast<uint4 *>(base + 16u * i) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (int j = 0; j < 16; j++) { const int64_t k = first + j; if (k >= 0 && (uint64_t)k < n) base[16u * i + j] = src[k]; }
+        }
+    }
+}
+int launch_d2h_bytes(void *dst_host, const void *src_dev, uint64_t bytes, cudaStream_t st) {
+    if (!bytes) return 0;
+    const uint64_t n16 = (bytes + 31u) / 16u;
+    link_d2h_bytes_kernel<<<(unsigned)std::min<uint64_t>(148u * 8u, (n16 + 255u) / 256u), 256, 0, st>>>(reinterpret_cast<uint8_t *>(dst_host), reinterpret_cast<const uint8_t *>(src_dev), bytes);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+__global__ void link_words_kernel(uint64_t *dst, const uint64_t *src, uint32_t n) { if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x]; }
+int launch_copy_words(void *dst, const void *src, uint32_t n_words, cudaStream_t st) {     /* <= 32 64-bit words, either side may be mapped host memory */
+    link_words_kernel<<<1, 32, 0, st>>>(reinterpret_cast<uint64_t *>(dst), reinterpret_cast<const uint64_t *>(src), n_words);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 int launch_merge(const BlockDesc *blocks, uint32_t block_begin, uint32_t n_blocks, uint32_t L, const uint8_t *prev,
                  uint8_t *next, const uint8_t *fin, const uint8_t *ws, unsigned long long *err, uint32_t flag_target, cudaStream_t st) {
     /* next = prev, by a kernel: a cudaMemcpyAsync would queue on a copy engine behind the host <-> device traffic of a
