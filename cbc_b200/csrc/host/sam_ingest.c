@@ -366,17 +366,44 @@ void cbch_batch_view(const cbch_batch *b, cbcg_batch *v) {
 /* ------------------------------------------------------------------------------------------------ compact batches */
 typedef struct {
     const cbcg_batch *b; cbch_compact *c; uint64_t r0, r1;
-    uint8_t *seq2; uint16_t *cl, *ml; uint64_t *so, *co, *mo;
+    uint8_t *seq2; uint16_t *cl, *ml; uint64_t *so;
+    uint32_t *pos; uint16_t *flag, *sl; uint8_t *cig, *md;      /* every worker also copies its reads' fixed fields and CIGAR / MD text */
     uint64_t n_exc; uint32_t *er; uint16_t *eb; uint8_t *ec; uint64_t exc_cap; int oom;
 } pack_job;
 static inline unsigned base2(uint8_t ch) { return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u; }
+/* Eight bases at once: the 2-bit code of A / C / G / T is ((c >> 1) ^ (c >> 2)) & 3 (A 0, C 1, G 2, T 3, the order of
+ * base2 and of the device's unpack); the ASCII letter is rebuilt from the code and compared with the input, so anything that
+ * is not one of the four upper-case letters sends the group to the byte-by-byte path (which lists it as an exception).
+ * Bases k = 0 .. 3 of a byte sit at bits 2k, as below. Returns 0 when the group needs the slow path. */
+static inline int pack8(const uint8_t *s, uint8_t *d2) {
+    uint64_t x; memcpy(&x, s, 8);
+#if defined(__BYTE_ORDER__) && __BYTE_ORDER__ != __ORDER_LITTLE_ENDIAN__
+    return 0;
+#endif
+    const uint64_t L = 0x0101010101010101ull;
+    const uint64_t y = ((x >> 1) ^ (x >> 2)) & (3u * L);
+    const uint64_t c0 = y & L, c1 = (y >> 1) & L, both = c0 & c1;
+    const uint64_t e = (0x40u * L) | (both << 4) | (c1 << 2) | ((c1 ^ c0) << 1) | (both ^ L);
+    if (x != e) return 0;
+    const uint32_t lo = (uint32_t)y, hi = (uint32_t)(y >> 32);
+    d2[0] = (uint8_t)(lo | (lo >> 6) | (lo >> 12) | (lo >> 18));
+    d2[1] = (uint8_t)(hi | (hi >> 6) | (hi >> 12) | (hi >> 18));
+    return 1;
+}
 static void pack_part(pack_job *j) {
     const cbcg_batch *b = j->b;
+    if (j->r1 > j->r0) {
+        const uint64_t m = j->r1 - j->r0, c0 = b->cigar_off[0], m0 = b->md_off[0];
+        memcpy(j->pos + j->r0, b->pos + j->r0, m * 4); memcpy(j->flag + j->r0, b->flag + j->r0, m * 2); memcpy(j->sl + j->r0, b->seq_len + j->r0, m * 2);
+        memcpy(j->cig + (b->cigar_off[j->r0] - c0), b->cigar + b->cigar_off[j->r0], b->cigar_off[j->r1] - b->cigar_off[j->r0]);
+        memcpy(j->md + (b->md_off[j->r0] - m0), b->md + b->md_off[j->r0], b->md_off[j->r1] - b->md_off[j->r0]);
+    }
     for (uint64_t r = j->r0; r < j->r1; r++) {
         const uint8_t *s = b->seq + b->seq_off[r];
         const uint32_t len = b->seq_len[r];
         uint8_t *d = j->seq2 + j->so[r];
         for (uint32_t i = 0; i < len; i += 4) {
+            if (i + 8u <= len && !(i & 4u) && pack8(s + i, d + (i >> 2))) { i += 4; continue; }   /* two bytes done: skip the second group too */
             unsigned byte = 0;
             for (uint32_t k = 0; k < 4 && i + k < len; k++) {
                 unsigned c2 = base2(s[i + k]);
@@ -421,46 +448,50 @@ int cbch_pack_batch(const cbcg_batch *b, int n_threads, void *(*alloc)(size_t), 
     if (!n) return CBCH_OK;
     if (n_threads <= 0) n_threads = cbch_default_threads();
     if ((uint64_t)n_threads > n) n_threads = (int)n;
-    uint64_t *so = malloc((n + 1) * 8), *co = malloc((n + 1) * 8), *mo = malloc((n + 1) * 8);
-    if (!so || !co || !mo) { free(so); free(co); free(mo); return CBCH_ERR_NOMEM; }
+    const int trace = getenv("CBCH_TRACE") != NULL;
+    const double t_begin = now_s();
+    uint64_t *so = malloc((n + 1) * 8);
+    if (!so) return CBCH_ERR_NOMEM;
     uint64_t o = 0, n_runs = 0;
+    uint32_t mx = 0, mn = 0xffffffffu;
     for (uint64_t r = 0; r < n; r++) {
-        so[r] = o; o += ((uint64_t)b->seq_len[r] + 3u) >> 2;
-        co[r] = b->cigar_off[r] - b->cigar_off[0]; mo[r] = b->md_off[r] - b->md_off[0];
+        const uint32_t l = b->seq_len[r];
+        so[r] = o; o += ((uint64_t)l + 3u) >> 2;
+        if (l > mx) mx = l;
+        if (l < mn) mn = l;
         if (r == 0 || b->chr[r] != b->chr[r - 1]) n_runs++;
     }
-    so[n] = o; co[n] = b->cigar_off[n] - b->cigar_off[0]; mo[n] = b->md_off[n] - b->md_off[0];
+    so[n] = o;
+    const uint64_t s0 = b->seq_off[0], c0 = b->cigar_off[0], m0 = b->md_off[0], co_n = b->cigar_off[n] - c0, mo_n = b->md_off[n] - m0;
     {   /* one entry per tile of 128 reads, and the totals */
         const uint64_t tiles = (n + 127u) / 128u;
         uint64_t *tb = alloc((tiles + 1) * 32);
         v->tile_base = tb;
-        if (!tb) { free(so); free(co); free(mo); return CBCH_ERR_NOMEM; }
-        uint32_t mx = 0, mn = 0xffffffffu;
-        const uint64_t s0 = b->seq_off[0];
-        for (uint64_t r = 0; r < n; r++) { const uint32_t l = b->seq_len[r]; if (l > mx) mx = l; if (l < mn) mn = l; }
-        for (uint64_t t = 0; t <= tiles; t++) { const uint64_t r = t * 128u < n ? t * 128u : n; tb[4 * t] = b->seq_off[r] - s0; tb[4 * t + 1] = so[r]; tb[4 * t + 2] = co[r]; tb[4 * t + 3] = mo[r]; }
+        if (!tb) { free(so); return CBCH_ERR_NOMEM; }
+        for (uint64_t t = 0; t <= tiles; t++) { const uint64_t r = t * 128u < n ? t * 128u : n; tb[4 * t] = b->seq_off[r] - s0; tb[4 * t + 1] = so[r]; tb[4 * t + 2] = b->cigar_off[r] - c0; tb[4 * t + 3] = b->md_off[r] - m0; }
         v->max_len = mx; v->min_len = mn;
     }
     uint32_t *pos = alloc(n * 4); uint16_t *flag = alloc(n * 2), *sl = alloc(n * 2), *cl = alloc(n * 2), *ml = alloc(n * 2);
     uint64_t *rf = alloc(n_runs * 8); uint32_t *rc = alloc(n_runs * 4);
-    uint8_t *seq2 = alloc(o + 64), *cig = alloc(co[n] + 64), *md = alloc(mo[n] + 64);
+    uint8_t *seq2 = alloc(o + 64), *cig = alloc(co_n + 64), *md = alloc(mo_n + 64);
     v->pos = pos; v->flag = flag; v->seq_len = sl; v->cigar_len = cl; v->md_len = ml; v->run_first = rf; v->run_chr = rc; v->seq2 = seq2; v->cigar = cig; v->md = md;
-    if (!pos || !flag || !sl || !cl || !ml || !rf || !rc || !seq2 || !cig || !md) { free(so); free(co); free(mo); cbch_free_compact(out); return CBCH_ERR_NOMEM; }
-    memcpy(pos, b->pos, n * 4); memcpy(flag, b->flag, n * 2); memcpy(sl, b->seq_len, n * 2);
-    memcpy(cig, b->cigar + b->cigar_off[0], co[n]); memcpy(md, b->md + b->md_off[0], mo[n]);
+    if (!pos || !flag || !sl || !cl || !ml || !rf || !rc || !seq2 || !cig || !md) { free(so); cbch_free_compact(out); return CBCH_ERR_NOMEM; }
     { uint64_t k = 0; for (uint64_t r = 0; r < n; r++) if (r == 0 || b->chr[r] != b->chr[r - 1]) { rf[k] = r; rc[k] = b->chr[r]; k++; } v->n_runs = (uint32_t)n_runs; }
+    const double t_head = now_s();
     pack_job *jobs = calloc((size_t)n_threads, sizeof *jobs);
     pthread_t *th = calloc((size_t)n_threads, sizeof *th);
-    if (!jobs || !th) { free(jobs); free(th); free(so); free(co); free(mo); cbch_free_compact(out); return CBCH_ERR_NOMEM; }
+    if (!jobs || !th) { free(jobs); free(th); free(so); cbch_free_compact(out); return CBCH_ERR_NOMEM; }
     for (int t = 0; t < n_threads; t++) {
         jobs[t].b = b; jobs[t].c = out; jobs[t].r0 = n * (uint64_t)t / (uint64_t)n_threads; jobs[t].r1 = n * (uint64_t)(t + 1) / (uint64_t)n_threads;
-        jobs[t].seq2 = seq2; jobs[t].cl = cl; jobs[t].ml = ml; jobs[t].so = so; jobs[t].co = co; jobs[t].mo = mo;
+        jobs[t].seq2 = seq2; jobs[t].cl = cl; jobs[t].ml = ml; jobs[t].so = so;
+        jobs[t].pos = pos; jobs[t].flag = flag; jobs[t].sl = sl; jobs[t].cig = cig; jobs[t].md = md;
     }
     int started = 0;
     for (int t = 1; t < n_threads; t++) { if (pthread_create(&th[t], NULL, pack_thread, &jobs[t])) break; started = t; }
     for (int t = started + 1; t < n_threads; t++) pack_part(&jobs[t]);
     pack_part(&jobs[0]);
     for (int t = 1; t <= started; t++) pthread_join(th[t], NULL);
+    if (trace) fprintf(stderr, "[cbch pack] %d workers: offsets + copies %.1f ms, bases %.1f ms\n", n_threads, (t_head - t_begin) * 1e3, (now_s() - t_head) * 1e3);
     uint64_t n_exc = 0; int oom = 0;
     for (int t = 0; t < n_threads; t++) { n_exc += jobs[t].n_exc; oom |= jobs[t].oom; }
     if (!oom && n_exc) {
@@ -472,8 +503,8 @@ int cbch_pack_batch(const cbcg_batch *b, int n_threads, void *(*alloc)(size_t), 
     v->n_exc = oom ? 0 : n_exc;
     for (int t = 0; t < n_threads; t++) { free(jobs[t].er); free(jobs[t].eb); free(jobs[t].ec); }
     free(jobs); free(th);
-    out->bytes = n * (4 + 2 + 2 + 2 + 2) + o + co[n] + mo[n] + n_runs * 12 + n_exc * 7 + ((n + 127u) / 128u + 1) * 32;
-    free(so); free(co); free(mo);
+    out->bytes = n * (4 + 2 + 2 + 2 + 2) + o + co_n + mo_n + n_runs * 12 + n_exc * 7 + ((n + 127u) / 128u + 1) * 32;
+    free(so);
     if (oom) { cbch_free_compact(out); return CBCH_ERR_NOMEM; }
     return CBCH_OK;
 }

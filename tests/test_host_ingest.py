@@ -200,6 +200,13 @@ def test_compact_batch_packer_round_trips():
         assert np.array_equal(arr(v.cigar_len, C.c_uint16, n), np.diff(b.cigar_off).astype(np.uint16))
         assert np.array_equal(arr(v.md_len, C.c_uint16, n), np.diff(b.md_off).astype(np.uint16))
         assert np.array_equal(arr(v.run_chr, C.c_uint32, 3), np.array([0, 1, 2], np.uint32))
+        # the fixed fields and the CIGAR / MD text travel as they are (copied by the workers, each its own reads)
+        assert np.array_equal(arr(v.pos, C.c_uint32, n), b.pos) and np.array_equal(arr(v.flag, C.c_uint16, n), b.flag)
+        assert np.array_equal(arr(v.seq_len, C.c_uint16, n), b.seq_len)
+        assert np.array_equal(arr(v.cigar, C.c_uint8, int(b.cigar_off[n])), b.cigar[:int(b.cigar_off[n])])
+        assert np.array_equal(arr(v.md, C.c_uint8, int(b.md_off[n])), b.md[:int(b.md_off[n])])
+        run_first = arr(v.run_first, C.c_uint64, 3)
+        assert run_first[0] == 0 and np.array_equal(b.chr[run_first.astype(np.int64)], np.array([0, 1, 2], np.uint32))
         assert c.link_bytes < 0.45 * (b.seq.nbytes + b.cigar.nbytes + b.md.nbytes + n * 36)
         images.append((seq2.tobytes(), er.tobytes(), eb.tobytes(), ec.tobytes()))
         c.close()
