@@ -187,7 +187,9 @@ int cbcg_reconstruct(cbcg_ctx *ctx, uint64_t n_reads, const cbcg_read_rec *recs,
  * operations are soft clips (coded as insertions by the reference, src/read_compression.c:358-479) cost two bytes, any
  * other CIGAR (=, X, H, P, ...) is kept verbatim. cbcg_cigar_pack runs K1 on the batch and classifies every read on the
  * device; cbcg_cigar_unpack decodes the container to edit records and writes every read's CIGAR + '\n' in read order
- * (section == NULL: the implied CIGARs alone). */
+ * (section == NULL: the implied CIGARs alone). State: cbcg_cigar_pack uploads `batch` (it becomes the resident batch, like
+ * cbcg_batch_upload) and cbcg_cigar_unpack is a decode (it invalidates "the last encode", like cbcg_decode of a foreign
+ * container); neither touches the container's bytes. Section layout ("CBCC" v1): api.cu, above cbcg_cigar_bound. */
 uint64_t cbcg_cigar_bound(const cbcg_batch *batch);
 int cbcg_cigar_pack(cbcg_ctx *ctx, const cbcg_batch *batch, uint8_t *out, uint64_t out_cap, uint64_t *out_len);
 int cbcg_cigar_unpack(cbcg_ctx *ctx, const uint8_t *in, uint64_t in_len, int legacy, const uint8_t *section, uint64_t section_len,
